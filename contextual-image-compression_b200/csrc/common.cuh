@@ -1,0 +1,99 @@
+// Shared helpers for libcic.so (sm_100a).  Host-side error plumbing + device-side math that
+// must round exactly like the reference's op-by-op fp32 graph (no FMA contraction where the
+// reference executes separate TF ops).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/cic.h"
+
+namespace cic {
+
+void set_error(const char* fmt, ...);
+
+#define CIC_CHECK_CUDA(expr)                                                                   \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      cic::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return CIC_ERR_CUDA;                                                                     \
+    }                                                                                          \
+  } while (0)
+
+#define CIC_CHECK_LAUNCH(name)                                                                 \
+  do {                                                                                         \
+    cudaError_t _e = cudaGetLastError();                                                       \
+    if (_e != cudaSuccess) {                                                                   \
+      cic::set_error("launch of %s failed: %s (%s:%d)", name, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return CIC_ERR_CUDA;                                                                     \
+    }                                                                                          \
+  } while (0)
+
+#define CIC_REQUIRE(cond, ...)                                                                 \
+  do {                                                                                         \
+    if (!(cond)) {                                                                             \
+      cic::set_error(__VA_ARGS__);                                                             \
+      return CIC_ERR_INVALID;                                                                  \
+    }                                                                                          \
+  } while (0)
+
+// launch counter: every kernel launch of this library goes through CIC_COUNT_LAUNCH so that
+// bench.py can report `gpu_launches` from the library's own bookkeeping.
+extern thread_local long long g_launch_count;
+#define CIC_COUNT_LAUNCH() (++cic::g_launch_count)
+
+int sm_count();
+
+// TF 'same' padding: out = ceil(in/s); total = max((out-1)*s + k - in, 0); before = total/2.
+inline int same_out(int in, int s) { return (in + s - 1) / s; }
+inline int same_pad_before(int in, int k, int s) {
+  int out = same_out(in, s);
+  int total = (out - 1) * s + k - in;
+  if (total < 0) total = 0;
+  return total / 2;
+}
+
+// ---- device math ---------------------------------------------------------------------------
+__device__ __forceinline__ float act_apply(float v, int act) {
+  switch (act) {
+    case CIC_ACT_RELU: return fmaxf(v, 0.f);
+    case CIC_ACT_LRELU02: return v > 0.f ? v : __fmul_rn(v, 0.2f);
+    case CIC_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
+    case CIC_ACT_TANH: return tanhf(v);
+    default: return v;
+  }
+}
+
+__device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + expf(-v)); }
+
+// t = clip(bpp/5, 0, 1) (GAN_functions.py:631-633); separate roundings like the TF ops.
+__device__ __forceinline__ float rate_t(float bpp) { return fminf(fmaxf(__fdiv_rn(bpp, 5.0f), 0.f), 1.f); }
+__device__ __forceinline__ float rate_thr(float t) { return __fsub_rn(0.9f, __fmul_rn(0.85f, t)); }  // :642-644
+__device__ __forceinline__ float rate_qs(float t) { return __fsub_rn(0.9f, __fmul_rn(0.8f, t)); }    // :647-649
+// dt = sigmoid((mask^0.7 - thr) * 20) (GAN_functions.py:651-657)
+__device__ __forceinline__ float dyn_threshold(float m, float thr) {
+  float es = powf(m, 0.7f);
+  return sigmoidf_(__fmul_rn(__fsub_rn(es, thr), 20.0f));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+}  // namespace cic

@@ -1,0 +1,302 @@
+// Fused PSNR + MSE + SSIM reductions (GAN_functions.py:724-759, test_autoencoder.py:49-66).
+//
+// One pass over the image pair: each CTA owns a 32x32 pixel tile, stages the tile plus a 3-pixel
+// halo of both images in shared memory (the 7x7 uniform window of scikit-image's
+// structural_similarity), accumulates the squared error of its own pixels, runs the separable
+// window sums and reduces the SSIM map of its pixels with warp shuffles; one atomicAdd(double) per
+// CTA and quantity.  Algorithmic traffic: 24 B/pixel for an fp32 RGB pair, 6 B/pixel for uint8.
+//
+// Numerics follow scikit-image op by op: scipy.ndimage.uniform_filter filters axis 0 then axis 1,
+// accumulating in double and storing each pass in the image dtype (float32 for float32 input,
+// float64 for uint8 input); the SSIM expression is evaluated in that dtype with separate roundings
+// (no FMA contraction); the cropped mean and the squared-error mean accumulate in double.  SSIM
+// pixels within 3 px of the border are cropped by scikit-image, so the 'reflect' boundary rule of
+// uniform_filter never reaches a pixel that counts and no padding is needed.
+#include "common.cuh"
+
+namespace cic {
+
+constexpr int TS = 32;        // owned tile edge
+constexpr int HALO = 3;       // (win_size - 1) / 2
+constexpr int TP = TS + 2 * HALO;
+
+// ------------------------------------------------------------------------------------------
+// float32 path: d_a, d_b (B,H,W,C); v = (x + pre_add) * pre_mul
+// acc[b*4 + 1] += sum of SSIM map (all channels), acc[b*4 + 3] += sum of squared error
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+metrics_f32_kernel(const float* __restrict__ A, const float* __restrict__ Bm, double* __restrict__ acc, int H, int W,
+                   int C, float pre_add, float pre_mul, float c1, float c2, float cov_norm) {
+  __shared__ float sa[TP][TP + 1];
+  __shared__ float sb[TP][TP + 1];
+  __shared__ float sv[5][TS][TP + 1];  // vertical-pass results: a, b, aa, bb, ab
+  __shared__ double red[2][8];
+
+  const int tiles_x = (W + TS - 1) / TS;
+  const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+  const int c = blockIdx.y, b = blockIdx.z;
+  const int x0 = tx * TS, y0 = ty * TS;
+  const size_t img_base = (size_t)b * H * W * C;
+
+  // 1. stage tile + halo (zero outside the image; such values only reach cropped SSIM pixels)
+  double sse = 0.0;
+  for (int i = threadIdx.x; i < TP * TP; i += blockDim.x) {
+    const int ly = i / TP, lx = i % TP;
+    const int gy = y0 + ly - HALO, gx = x0 + lx - HALO;
+    float va = 0.f, vb = 0.f;
+    if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+      const size_t idx = img_base + ((size_t)gy * W + gx) * C + c;
+      va = __fmul_rn(__fadd_rn(__ldg(A + idx), pre_add), pre_mul);
+      vb = __fmul_rn(__fadd_rn(__ldg(Bm + idx), pre_add), pre_mul);
+      if (ly >= HALO && ly < HALO + TS && lx >= HALO && lx < HALO + TS) {
+        const float d = __fsub_rn(va, vb);
+        sse += (double)__fmul_rn(d, d);
+      }
+    }
+    sa[ly][lx] = va;
+    sb[ly][lx] = vb;
+  }
+  __syncthreads();
+
+  // 2. vertical pass (axis 0 first, like scipy): owned rows x (owned + halo) columns
+  for (int i = threadIdx.x; i < TS * TP; i += blockDim.x) {
+    const int r = i / TP, lx = i % TP;
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+      const float va = sa[r + k][lx], vb = sb[r + k][lx];
+      s0 += (double)va;
+      s1 += (double)vb;
+      s2 += (double)__fmul_rn(va, va);
+      s3 += (double)__fmul_rn(vb, vb);
+      s4 += (double)__fmul_rn(va, vb);
+    }
+    sv[0][r][lx] = (float)(s0 / 7.0);
+    sv[1][r][lx] = (float)(s1 / 7.0);
+    sv[2][r][lx] = (float)(s2 / 7.0);
+    sv[3][r][lx] = (float)(s3 / 7.0);
+    sv[4][r][lx] = (float)(s4 / 7.0);
+  }
+  __syncthreads();
+
+  // 3. horizontal pass + SSIM expression for owned pixels that survive the 3-px crop
+  double ssum = 0.0;
+  for (int i = threadIdx.x; i < TS * TS; i += blockDim.x) {
+    const int r = i / TS, cx = i % TS;
+    const int gy = y0 + r, gx = x0 + cx;
+    if (gy < HALO || gy >= H - HALO || gx < HALO || gx >= W - HALO) continue;
+    double s[5];
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+      double t = 0;
+#pragma unroll
+      for (int k = 0; k < 7; ++k) t += (double)sv[q][r][cx + k];
+      s[q] = t;
+    }
+    const float ux = (float)(s[0] / 7.0), uy = (float)(s[1] / 7.0);
+    const float uxx = (float)(s[2] / 7.0), uyy = (float)(s[3] / 7.0), uxy = (float)(s[4] / 7.0);
+    const float vx = __fmul_rn(cov_norm, __fsub_rn(uxx, __fmul_rn(ux, ux)));
+    const float vy = __fmul_rn(cov_norm, __fsub_rn(uyy, __fmul_rn(uy, uy)));
+    const float vxy = __fmul_rn(cov_norm, __fsub_rn(uxy, __fmul_rn(ux, uy)));
+    const float a1 = __fadd_rn(__fmul_rn(__fmul_rn(2.0f, ux), uy), c1);
+    const float a2 = __fadd_rn(__fmul_rn(2.0f, vxy), c2);
+    const float b1 = __fadd_rn(__fadd_rn(__fmul_rn(ux, ux), __fmul_rn(uy, uy)), c1);
+    const float b2 = __fadd_rn(__fadd_rn(vx, vy), c2);
+    const float S = __fdiv_rn(__fmul_rn(a1, a2), __fmul_rn(b1, b2));
+    ssum += (double)S;
+  }
+
+  // 4. CTA reduction, one atomic per quantity
+  sse = warp_sum(sse);
+  ssum = warp_sum(ssum);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red[0][warp] = sse; red[1][warp] = ssum; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t0 = 0, t1 = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { t0 += red[0][w]; t1 += red[1][w]; }
+    atomicAdd(acc + (size_t)b * 4 + 3, t0);
+    atomicAdd(acc + (size_t)b * 4 + 1, t1);
+  }
+}
+
+// out[b] = {psnr, ssim, mse, sse}
+__global__ void metrics_finalize_kernel(double* __restrict__ acc, int batch, double n_elems, double n_ssim,
+                                        double data_range) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  double* o = acc + (size_t)b * 4;
+  const double sse = o[3];
+  const double mse = sse / n_elems;
+  o[2] = mse;
+  o[1] = n_ssim > 0 ? o[1] / n_ssim : 0.0;
+  o[0] = 10.0 * log10(data_range * data_range / mse);  // +inf when mse == 0, like scikit-image
+}
+
+// ------------------------------------------------------------------------------------------
+// uint8 BGR path (test_autoencoder.py:49-66).  acc[b*4+0] wrapped-mse sum, +1 ssim sum, +3 sse
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int bgr2gray_u8(int b, int g, int r) {
+  return (b * 3735 + g * 19235 + r * 9798 + 16384) >> 15;  // OpenCV 4.x fixed point, 15-bit coefficients
+}
+
+constexpr int GTSY = 16;  // gray/uint8 kernel: 32 x 16 tile (double-precision window sums need 2x the smem)
+constexpr int GTPY = GTSY + 2 * HALO;
+__global__ void __launch_bounds__(256)
+metrics_gray_u8_kernel(const uint8_t* __restrict__ A, const uint8_t* __restrict__ Bm, double* __restrict__ acc, int H,
+                       int W, double c1, double c2, double cov_norm) {
+  __shared__ float sa[GTPY][TP + 1];  // gray values 0..255 are exact in float
+  __shared__ float sb[GTPY][TP + 1];
+  __shared__ double sv[5][GTSY][TP + 1];
+  __shared__ double red[3][8];
+
+  const int tiles_x = (W + TS - 1) / TS;
+  const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+  const int b = blockIdx.z;
+  const int x0 = tx * TS, y0 = ty * GTSY;
+  const size_t img_base = (size_t)b * H * W * 3;
+
+  unsigned long long sse = 0, wrapped = 0;
+  for (int i = threadIdx.x; i < GTPY * TP; i += blockDim.x) {
+    const int ly = i / TP, lx = i % TP;
+    const int gy = y0 + ly - HALO, gx = x0 + lx - HALO;
+    float va = 0.f, vb = 0.f;
+    if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+      const size_t idx = img_base + ((size_t)gy * W + gx) * 3;
+      const int a0 = A[idx], a1 = A[idx + 1], a2 = A[idx + 2];
+      const int b0 = Bm[idx], b1 = Bm[idx + 1], b2 = Bm[idx + 2];
+      va = (float)bgr2gray_u8(a0, a1, a2);
+      vb = (float)bgr2gray_u8(b0, b1, b2);
+      if (ly >= HALO && ly < HALO + GTSY && lx >= HALO && lx < HALO + TS) {
+        const int d0 = a0 - b0, d1 = a1 - b1, d2 = a2 - b2;
+        sse += (unsigned long long)(d0 * d0 + d1 * d1 + d2 * d2);
+        // numpy uint8 arithmetic: (a-b) wraps mod 256, then the square wraps mod 256
+        const unsigned w0 = (unsigned)(d0 & 255), w1 = (unsigned)(d1 & 255), w2 = (unsigned)(d2 & 255);
+        wrapped += ((w0 * w0) & 255u) + ((w1 * w1) & 255u) + ((w2 * w2) & 255u);
+      }
+    }
+    sa[ly][lx] = va;
+    sb[ly][lx] = vb;
+  }
+  __syncthreads();
+
+  for (int i = threadIdx.x; i < GTSY * TP; i += blockDim.x) {
+    const int r = i / TP, lx = i % TP;
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+      const double va = sa[r + k][lx], vb = sb[r + k][lx];
+      s0 += va; s1 += vb; s2 += va * va; s3 += vb * vb; s4 += va * vb;   // integers: exact
+    }
+    sv[0][r][lx] = s0 / 7.0; sv[1][r][lx] = s1 / 7.0; sv[2][r][lx] = s2 / 7.0;
+    sv[3][r][lx] = s3 / 7.0; sv[4][r][lx] = s4 / 7.0;
+  }
+  __syncthreads();
+
+  double ssum = 0.0;
+  for (int i = threadIdx.x; i < GTSY * TS; i += blockDim.x) {
+    const int r = i / TS, cx = i % TS;
+    const int gy = y0 + r, gx = x0 + cx;
+    if (gy < HALO || gy >= H - HALO || gx < HALO || gx >= W - HALO) continue;
+    double s[5];
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+      double t = 0;
+#pragma unroll
+      for (int k = 0; k < 7; ++k) t += sv[q][r][cx + k];
+      s[q] = t / 7.0;
+    }
+    const double ux = s[0], uy = s[1], uxx = s[2], uyy = s[3], uxy = s[4];
+    const double vx = __dmul_rn(cov_norm, __dsub_rn(uxx, __dmul_rn(ux, ux)));
+    const double vy = __dmul_rn(cov_norm, __dsub_rn(uyy, __dmul_rn(uy, uy)));
+    const double vxy = __dmul_rn(cov_norm, __dsub_rn(uxy, __dmul_rn(ux, uy)));
+    const double a1 = __dadd_rn(__dmul_rn(__dmul_rn(2.0, ux), uy), c1);
+    const double a2 = __dadd_rn(__dmul_rn(2.0, vxy), c2);
+    const double b1 = __dadd_rn(__dadd_rn(__dmul_rn(ux, ux), __dmul_rn(uy, uy)), c1);
+    const double b2 = __dadd_rn(__dadd_rn(vx, vy), c2);
+    ssum += __ddiv_rn(__dmul_rn(a1, a2), __dmul_rn(b1, b2));
+  }
+
+  double d_sse = warp_sum((double)sse), d_wr = warp_sum((double)wrapped);
+  ssum = warp_sum(ssum);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red[0][warp] = d_sse; red[1][warp] = ssum; red[2][warp] = d_wr; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t0 = 0, t1 = 0, t2 = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { t0 += red[0][w]; t1 += red[1][w]; t2 += red[2][w]; }
+    atomicAdd(acc + (size_t)b * 4 + 3, t0);
+    atomicAdd(acc + (size_t)b * 4 + 1, t1);
+    atomicAdd(acc + (size_t)b * 4 + 0, t2);
+  }
+}
+
+// out[b] = {psnr, ssim, true mse, wrapped uint8 "mse"}
+__global__ void metrics_gray_finalize_kernel(double* __restrict__ acc, int batch, double n_elems, double n_ssim) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  double* o = acc + (size_t)b * 4;
+  const double wrapped = o[0], sse = o[3];
+  const double mse = sse / n_elems;
+  o[0] = 10.0 * log10(255.0 * 255.0 / mse);
+  o[1] = n_ssim > 0 ? o[1] / n_ssim : 0.0;
+  o[2] = mse;
+  o[3] = wrapped / n_elems;
+}
+
+}  // namespace cic
+
+using namespace cic;
+
+extern "C" int cic_metrics_psnr_ssim_f32(const float* d_a, const float* d_b, double* d_out, int batch, int h, int w,
+                                         int channels, float pre_add, float pre_mul, float data_range, void* stream) {
+  CIC_REQUIRE(d_a && d_b && d_out, "cic_metrics_psnr_ssim_f32: null pointer");
+  CIC_REQUIRE(batch >= 0 && h >= 7 && w >= 7 && channels >= 1 && channels <= 65535,
+              "cic_metrics_psnr_ssim_f32: needs h,w >= 7 (7x7 SSIM window), got %dx%dx%d", h, w, channels);
+  if (batch == 0) return CIC_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  CIC_CHECK_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * 4 * batch, st));
+  const int tiles = ((w + TS - 1) / TS) * ((h + TS - 1) / TS);
+  // scikit-image: K1 = 0.01, K2 = 0.03, C = (K*R)^2, cov_norm = 49/48; python-float scalars are
+  // combined with float32 arrays in float32
+  const float c1 = (float)((0.01 * (double)data_range) * (0.01 * (double)data_range));
+  const float c2 = (float)((0.03 * (double)data_range) * (0.03 * (double)data_range));
+  const float cov_norm = (float)(49.0 / 48.0);
+  for (int b0 = 0; b0 < batch; b0 += 65535) {
+    int nb = batch - b0 < 65535 ? batch - b0 : 65535;
+    dim3 grid(tiles, channels, nb);
+    metrics_f32_kernel<<<grid, 256, 0, st>>>(d_a + (size_t)b0 * h * w * channels, d_b + (size_t)b0 * h * w * channels,
+                                              d_out + (size_t)b0 * 4, h, w, channels, pre_add, pre_mul, c1, c2, cov_norm);
+    CIC_COUNT_LAUNCH();
+    CIC_CHECK_LAUNCH("metrics_f32_kernel");
+  }
+  metrics_finalize_kernel<<<(batch + 127) / 128, 128, 0, st>>>(d_out, batch, (double)h * w * channels,
+                                                               (double)(h - 6) * (w - 6) * channels, (double)data_range);
+  CIC_COUNT_LAUNCH();
+  CIC_CHECK_LAUNCH("metrics_finalize_kernel");
+  return CIC_OK;
+}
+
+extern "C" int cic_metrics_psnr_ssim_gray_u8(const uint8_t* d_a, const uint8_t* d_b, double* d_out, int batch, int h,
+                                             int w, void* stream) {
+  CIC_REQUIRE(d_a && d_b && d_out, "cic_metrics_psnr_ssim_gray_u8: null pointer");
+  CIC_REQUIRE(batch >= 0 && h >= 7 && w >= 7, "cic_metrics_psnr_ssim_gray_u8: needs h,w >= 7, got %dx%d", h, w);
+  if (batch == 0) return CIC_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  CIC_CHECK_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * 4 * batch, st));
+  const int tiles = ((w + TS - 1) / TS) * ((h + GTSY - 1) / GTSY);
+  const double c1 = (0.01 * 255.0) * (0.01 * 255.0), c2 = (0.03 * 255.0) * (0.03 * 255.0);
+  for (int b0 = 0; b0 < batch; b0 += 65535) {
+    int nb = batch - b0 < 65535 ? batch - b0 : 65535;
+    dim3 grid(tiles, 1, nb);
+    metrics_gray_u8_kernel<<<grid, 256, 0, st>>>(d_a + (size_t)b0 * h * w * 3, d_b + (size_t)b0 * h * w * 3,
+                                                  d_out + (size_t)b0 * 4, h, w, c1, c2, 49.0 / 48.0);
+    CIC_COUNT_LAUNCH();
+    CIC_CHECK_LAUNCH("metrics_gray_u8_kernel");
+  }
+  metrics_gray_finalize_kernel<<<(batch + 127) / 128, 128, 0, st>>>(d_out, batch, (double)h * w * 3,
+                                                                    (double)(h - 6) * (w - 6));
+  CIC_COUNT_LAUNCH();
+  CIC_CHECK_LAUNCH("metrics_gray_finalize_kernel");
+  return CIC_OK;
+}

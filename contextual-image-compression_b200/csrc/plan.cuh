@@ -1,0 +1,77 @@
+// cic_plan: device-resident packed weights + the graph walkers of the reference's models.
+#pragma once
+#include "common.cuh"
+#include "igemm_simt.cuh"
+
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+namespace cic {
+
+struct DevTensor {
+  float* p = nullptr;
+  std::vector<int64_t> shape;
+  size_t numel() const {
+    size_t n = 1;
+    for (auto s : shape) n *= (size_t)s;
+    return n;
+  }
+};
+
+// name -> device tensor; owns the allocations
+class WeightStore {
+ public:
+  ~WeightStore();
+  int upload(const std::string& name, const float* h, const std::vector<int64_t>& shape);
+  const DevTensor* find(const std::string& name) const;
+  float* ptr(const std::string& name) const {
+    const DevTensor* t = find(name);
+    return t ? t->p : nullptr;
+  }
+  size_t bytes() const { return bytes_; }
+
+ private:
+  std::map<std::string, DevTensor> t_;
+  size_t bytes_ = 0;
+};
+
+// bump allocator over the caller's workspace; with base == nullptr it only measures
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0, off = 0, peak = 0;
+  bool overflow = false;
+  void* alloc_bytes(size_t n) {
+    off = (off + 255) & ~(size_t)255;
+    void* r = base ? base + off : nullptr;
+    off += n;
+    if (off > peak) peak = off;
+    if (base && off > cap) overflow = true;
+    return r;
+  }
+  float* f32(size_t n) { return (float*)alloc_bytes(n * sizeof(float)); }
+  size_t mark() const { return off; }
+  void release(size_t m) { off = m; }
+};
+
+struct Ctx {
+  Arena arena;
+  cudaStream_t st = nullptr;
+  bool dry = false;  // measure workspace only, launch nothing
+};
+
+int run_dense(const float* x, const float* kernel, const float* bias, const float* scale, const float* shift, float* y,
+              int batch, int in_dim, int out_dim, int act, float* ws, size_t ws_floats, cudaStream_t st);
+void pack_deconv_phases(const float* k, int cout, int cin, std::vector<float>& out);
+
+}  // namespace cic
+
+struct cic_plan {
+  int kind = 0;
+  cic_plan_opts opts{};
+  cic::WeightStore w;
+  long long last_launches = 0;
+  // CIC_PLAN_ADAPTIVE owns its seven sub-models
+  std::unique_ptr<cic_plan> hq_enc, lq_enc, hq_gen, lq_gen, sal_hq, sal_lq, rd;
+};

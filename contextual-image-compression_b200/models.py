@@ -1,0 +1,391 @@
+"""Keras-like model objects over libcic plans.
+
+The reference's callers use two protocols:
+  * `model.predict(x_or_list, verbose=0)` -> numpy array / list of numpy arrays
+    (`test_autoencoder.py:85`, `GAN_test.py:292,567`);
+  * `model(list, training=False)` -> sequence whose elements support `[0]` and `.numpy()`
+    (`GAN_functions.py:867-871`) - CPU torch tensors satisfy that.
+`forward_device` is the zero-copy entry point (CUDA tensors in, CUDA tensors out) used by the
+benchmark's device-resident leg and by the multi-GPU runner.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib, runtime, weights as W
+from .runtime import ptr, to_device_f32
+
+
+def _make_tensor_array(named: Dict[str, np.ndarray]):
+    keep = []
+    arr = (_lib.cic_tensor * max(len(named), 1))()
+    for i, (name, a) in enumerate(named.items()):
+        a32 = np.ascontiguousarray(a, dtype=np.float32)
+        keep.append(a32)
+        bname = name.encode()
+        keep.append(bname)
+        arr[i].name = bname
+        arr[i].h_data = a32.ctypes.data_as(C.POINTER(C.c_float))
+        arr[i].ndim = a32.ndim
+        for d in range(a32.ndim):
+            arr[i].shape[d] = a32.shape[d]
+    return arr, keep
+
+
+class Plan:
+    """RAII wrapper of a cic_plan*."""
+
+    def __init__(self, kind: int, named_weights: Dict[str, np.ndarray], img_shape=(0, 0, 3), latent_dim=0,
+                 add_attention=False, precision: Optional[str] = None):
+        runtime.require_cuda()
+        opts = _lib.cic_plan_opts()
+        opts.precision = runtime.precision_code(precision)
+        opts.img_h, opts.img_w, opts.img_c = int(img_shape[0]), int(img_shape[1]), int(img_shape[2])
+        opts.latent_dim = int(latent_dim)
+        opts.add_attention = int(bool(add_attention))
+        arr, keep = _make_tensor_array(named_weights)
+        self.handle = _lib.lib.cic_plan_create(kind, arr, len(named_weights), C.byref(opts))
+        del keep
+        if not self.handle:
+            raise _lib.CicError(_lib.ERR_INVALID, _lib.last_error())
+        self.kind = kind
+        self.precision = precision or runtime.get_precision()
+
+    def workspace(self, batch: int, h: int = 0, w: int = 0) -> torch.Tensor:
+        n = _lib.lib.cic_plan_workspace_bytes(self.handle, batch, h, w)
+        return runtime.Workspace.get(int(n))
+
+    def last_launch_count(self) -> int:
+        return int(_lib.lib.cic_plan_last_launch_count(self.handle))
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h:
+            try:
+                _lib.lib.cic_plan_destroy(h)
+            except Exception:
+                pass
+            self.handle = None
+
+
+class Model:
+    """Common predict / __call__ protocol; subclasses implement forward_device."""
+
+    name = "model"
+
+    def __init__(self):
+        self._plan: Optional[Plan] = None
+        self._plan_precision: Optional[str] = None
+        self.weights: Dict[str, np.ndarray] = {}
+
+    # -- weights ------------------------------------------------------------------------------
+    def get_weights_dict(self) -> Dict[str, np.ndarray]:
+        return self.weights
+
+    def set_weights_dict(self, w: Dict[str, np.ndarray]) -> None:
+        self.weights = w
+        self._plan = None
+
+    def count_params(self) -> int:
+        return int(sum(int(np.prod(v.shape)) for v in self._flat_weights().values()))
+
+    def _flat_weights(self) -> Dict[str, np.ndarray]:
+        return self.weights
+
+    # -- plan ---------------------------------------------------------------------------------
+    def _make_plan(self, precision: str) -> Plan:
+        raise NotImplementedError
+
+    def plan(self) -> Plan:
+        prec = runtime.get_precision()
+        if self._plan is None or self._plan_precision != prec:
+            self._plan = self._make_plan(prec)
+            self._plan_precision = prec
+        return self._plan
+
+    # -- protocols ----------------------------------------------------------------------------
+    def forward_device(self, inputs: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+        raise NotImplementedError
+
+    def _run(self, inputs) -> List[torch.Tensor]:
+        xs = [to_device_f32(x) for x in runtime.as_list(inputs)]
+        return self.forward_device(xs)
+
+    def predict(self, x, verbose=0, batch_size=None):
+        outs = self._run(x)
+        host = [o.cpu().numpy() for o in outs]
+        return host if self._multi_output else host[0]
+
+    def __call__(self, inputs, training=False):
+        if training:
+            raise NotImplementedError("training is outside the accelerated inference path (SURVEY.md §2 #19-20)")
+        outs = [o.cpu() for o in self._run(inputs)]
+        return outs if self._multi_output else outs[0]
+
+    _multi_output = False
+
+    def summary(self):
+        print(f"Model: {self.name}  params: {self.count_params():,}")
+        for k, v in self._flat_weights().items():
+            print(f"  {k:40s} {tuple(v.shape)}")
+
+
+# --------------------------------------------------------------------------------------------
+class AutoencoderModel(Model):
+    """`build_autoencoder(input_shape)` (train_autoencoder.py:9-40); shape-generic in H, W (% 4 == 0)."""
+
+    name = "autoencoder"
+
+    def __init__(self, input_shape, seed: int = 0):
+        super().__init__()
+        self.input_shape = tuple(int(v) for v in input_shape)
+        self.weights = W.synthetic_autoencoder(seed=seed, channels=self.input_shape[2], keras_default=True)
+
+    def _make_plan(self, precision):
+        return Plan(_lib.PLAN_AUTOENCODER, self.weights, img_shape=(0, 0, self.input_shape[2]), precision=precision)
+
+    def forward_device(self, inputs, want_u8: bool = False):
+        x = inputs[0]
+        if x.dim() != 4 or x.shape[3] != self.input_shape[2]:
+            raise ValueError(f"expected (B,H,W,{self.input_shape[2]}) input, got {tuple(x.shape)}")
+        b, h, w, c = x.shape
+        if h % 4 or w % 4:
+            raise ValueError(f"autoencoder needs H and W divisible by 4, got {h}x{w}")
+        plan = self.plan()
+        y = torch.empty_like(x)
+        y8 = torch.empty((b, h, w, c), dtype=torch.uint8, device=x.device) if want_u8 else None
+        ws = plan.workspace(b, h, w)
+        _lib.check(_lib.lib.cic_autoencoder_forward(plan.handle, ptr(x), ptr(y), ptr(y8), b, h, w, ptr(ws), ws.numel(),
+                                                    runtime.stream_ptr()))
+        return [y, y8] if want_u8 else [y]
+
+
+class EncoderModel(Model):
+    """`build_encoder(img_shape, latent_dim, name, add_attention)` (GAN_functions.py:280-331)."""
+
+    _multi_output = True
+
+    def __init__(self, img_shape, latent_dim, name="encoder", add_attention=True, seed: int = 0):
+        super().__init__()
+        self.img_shape = tuple(int(v) for v in img_shape)
+        self.latent_dim = int(latent_dim)
+        self.name = name
+        self.add_attention = bool(add_attention)
+        self.weights = W.synthetic_encoder(self.img_shape, self.latent_dim, self.add_attention, seed, keras_default=True)
+
+    def _make_plan(self, precision):
+        return Plan(_lib.PLAN_ENCODER, self.weights, self.img_shape, self.latent_dim, self.add_attention, precision)
+
+    def forward_device(self, inputs):
+        x = inputs[0]
+        h, w, c = self.img_shape
+        if tuple(x.shape[1:]) != (h, w, c):
+            raise ValueError(f"{self.name}: expected (B,{h},{w},{c}), got {tuple(x.shape)}")
+        b = x.shape[0]
+        dev = x.device
+        lat = torch.empty((b, self.latent_dim), dtype=torch.float32, device=dev)
+        x1 = torch.empty((b, h // 2, w // 2, 64), dtype=torch.float32, device=dev)
+        x2 = torch.empty((b, h // 4, w // 4, 128), dtype=torch.float32, device=dev)
+        x3 = torch.empty((b, h // 8, w // 8, 256), dtype=torch.float32, device=dev)
+        plan = self.plan()
+        ws = plan.workspace(b)
+        _lib.check(_lib.lib.cic_encoder_forward(plan.handle, ptr(x), ptr(lat), ptr(x1), ptr(x2), ptr(x3), b, ptr(ws),
+                                                ws.numel(), runtime.stream_ptr()))
+        return [lat, x1, x2, x3]
+
+
+class GeneratorModel(Model):
+    """`build_generator(latent_dim, img_shape, name)` (GAN_functions.py:236-278)."""
+
+    def __init__(self, latent_dim, img_shape, name="generator", seed: int = 0):
+        super().__init__()
+        self.img_shape = tuple(int(v) for v in img_shape)
+        self.latent_dim = int(latent_dim)
+        self.name = name
+        self.weights = W.synthetic_generator(self.latent_dim, self.img_shape, seed, keras_default=True)
+
+    def _make_plan(self, precision):
+        return Plan(_lib.PLAN_GENERATOR, self.weights, self.img_shape, self.latent_dim, False, precision)
+
+    def forward_device(self, inputs):
+        if len(inputs) != 4:
+            raise ValueError(f"{self.name} takes [latent, skip1, skip2, skip3]")
+        lat, s1, s2, s3 = inputs
+        h, w, c = self.img_shape
+        b = lat.shape[0]
+        want = [(b, self.latent_dim), (b, h // 2, w // 2, 64), (b, h // 4, w // 4, 128), (b, h // 8, w // 8, 256)]
+        for t, s in zip(inputs, want):
+            if tuple(t.shape) != s:
+                raise ValueError(f"{self.name}: expected input shapes {want}, got {runtime.shapes_str(inputs)}")
+        out = torch.empty((b, h, w, c), dtype=torch.float32, device=lat.device)
+        plan = self.plan()
+        ws = plan.workspace(b)
+        _lib.check(_lib.lib.cic_generator_forward(plan.handle, ptr(lat), ptr(s1), ptr(s2), ptr(s3), ptr(out), b, ptr(ws),
+                                                  ws.numel(), runtime.stream_ptr()))
+        return [out]
+
+
+class LatentSaliencyModel(Model):
+    """`build_latent_saliency_model(latent_dim, name)` (GAN_functions.py:210-234)."""
+
+    def __init__(self, latent_dim, name="latent_saliency_module", seed: int = 0):
+        super().__init__()
+        self.latent_dim = int(latent_dim)
+        self.name = name
+        self.weights = W.synthetic_latent_saliency(self.latent_dim, seed, keras_default=True)
+
+    def _make_plan(self, precision):
+        return Plan(_lib.PLAN_SALIENCY, self.weights, (0, 0, 3), self.latent_dim, False, precision)
+
+    def forward_device(self, inputs):
+        lat = inputs[0]
+        if lat.dim() != 2 or lat.shape[1] != self.latent_dim:
+            raise ValueError(f"{self.name}: expected (B,{self.latent_dim}), got {tuple(lat.shape)}")
+        b = lat.shape[0]
+        out = torch.empty((b, 1), dtype=torch.float32, device=lat.device)
+        plan = self.plan()
+        ws = plan.workspace(b)
+        _lib.check(_lib.lib.cic_saliency_forward(plan.handle, ptr(lat), ptr(out), b, ptr(ws), ws.numel(), runtime.stream_ptr()))
+        return [out]
+
+
+class RDOptimizerModel(Model):
+    """`build_rate_distortion_optimizer(img_shape, latent_dims, name)` (GAN_functions.py:495-557).
+
+    Inputs `[img, saliency, target_bpp]` like the reference; the image is unused by the graph (:500).
+    """
+
+    def __init__(self, img_shape, latent_dims=None, name="rd_optimizer", seed: int = 0):
+        super().__init__()
+        self.img_shape = tuple(int(v) for v in img_shape)
+        self.latent_dims = latent_dims
+        self.name = name
+        self.weights = W.synthetic_rd_optimizer(seed, keras_default=True)
+
+    def _make_plan(self, precision):
+        return Plan(_lib.PLAN_RD, self.weights, self.img_shape, 0, False, precision)
+
+    def forward_device(self, inputs):
+        if len(inputs) == 3:
+            _, mask, bpp = inputs
+        elif len(inputs) == 2:
+            mask, bpp = inputs
+        else:
+            raise ValueError(f"{self.name} takes [img, saliency, target_bpp]")
+        h, w, _ = self.img_shape
+        b = mask.shape[0]
+        if tuple(mask.shape) != (b, h, w, 1):
+            raise ValueError(f"{self.name}: saliency must be (B,{h},{w},1), got {tuple(mask.shape)}")
+        bpp = bpp.reshape(-1).contiguous()
+        out = torch.empty((b, 3), dtype=torch.float32, device=mask.device)
+        plan = self.plan()
+        ws = plan.workspace(b)
+        _lib.check(_lib.lib.cic_rd_forward(plan.handle, ptr(mask), ptr(bpp), ptr(out), b, ptr(ws), ws.numel(), runtime.stream_ptr()))
+        return [out]
+
+
+class AdaptiveCompressionModel(Model):
+    """The 3-input / 5-output `adaptive_model` of build_adaptive_compression_model (GAN_functions.py:686-698).
+
+    predict([img, mask, bpp]) -> [blended, hq_latent_quantized, lq_latent_quantized, rd_params, dynamic_threshold].
+    Images may be any multiple of the model's tile (256 in the reference); they are coded as independent tiles,
+    and the latent outputs then have one row per tile in (image, tile-row, tile-col) order.
+    """
+
+    name = "adaptive_compression_model"
+    _multi_output = True
+    SUBS = ("hq_encoder", "hq_generator", "lq_encoder", "lq_generator", "latent_saliency_hq", "latent_saliency_lq",
+            "rd_optimizer")
+
+    def __init__(self, img_shape, base_latent_dim, components: Dict[str, Model]):
+        super().__init__()
+        self.img_shape = tuple(int(v) for v in img_shape)
+        self.base_latent_dim = int(base_latent_dim)
+        self.components = components
+        self._seen = None
+
+    def _flat_weights(self):
+        flat = {}
+        for sub in self.SUBS:
+            for k, v in self.components[sub].weights.items():
+                flat[f"{sub}/{k}"] = v
+        return flat
+
+    def set_weights_dict(self, w):
+        """Accepts {sub_model: {name: array}} (weights.synthetic_adaptive) and shares it with the sub-models."""
+        for sub in self.SUBS:
+            self.components[sub].set_weights_dict(w[sub])
+        self._plan = None
+
+    def get_weights_dict(self):
+        return {sub: self.components[sub].weights for sub in self.SUBS}
+
+    def plan(self):
+        # sub-models may have had their weights replaced individually: rebuild when identities change
+        ids = tuple(id(self.components[s].weights) for s in self.SUBS)
+        if self._seen != ids:
+            self._plan = None
+            self._seen = ids
+        return super().plan()
+
+    def _make_plan(self, precision):
+        return Plan(_lib.PLAN_ADAPTIVE, self._flat_weights(), self.img_shape, self.base_latent_dim, False, precision)
+
+    def forward_device(self, inputs, extras: bool = False):
+        if len(inputs) != 3:
+            raise ValueError("adaptive model takes [image, saliency, target_bpp]")
+        img, mask, bpp = inputs
+        T = self.img_shape[0]
+        n, h, w, c = img.shape
+        if c != 3 or h % T or w % T:
+            raise ValueError(f"image must be (B, k*{T}, m*{T}, 3), got {tuple(img.shape)}")
+        if mask.dim() == 3:
+            mask = mask.unsqueeze(-1)
+        if tuple(mask.shape) != (n, h, w, 1):
+            raise ValueError(f"saliency must be ({n},{h},{w},1), got {tuple(mask.shape)}")
+        bpp = bpp.reshape(-1).contiguous()
+        if bpp.numel() != n:
+            raise ValueError(f"target_bpp must have one value per image ({n}), got {bpp.numel()}")
+        nt = n * (h // T) * (w // T)
+        dev = img.device
+        base = self.base_latent_dim
+        f32 = dict(dtype=torch.float32, device=dev)
+        out = {
+            "blended": torch.empty((n, h, w, 3), **f32),
+            "hq_latent_q": torch.empty((nt, 2 * base), **f32),
+            "lq_latent_q": torch.empty((nt, base), **f32),
+            "rd_params": torch.empty((nt, 3), **f32),
+            "dt": torch.empty((n, h, w, 1), **f32),
+            "hq_ratio_sum": torch.empty((n,), dtype=torch.float64, device=dev),
+        }
+        if extras:
+            out.update({
+                "hq_symbols": torch.empty((nt, 2 * base), dtype=torch.int32, device=dev),
+                "lq_symbols": torch.empty((nt, base), dtype=torch.int32, device=dev),
+                "hq_latent": torch.empty((nt, 2 * base), **f32),
+                "lq_latent": torch.empty((nt, base), **f32),
+                "hq_scale": torch.empty((nt,), **f32),
+                "lq_scale": torch.empty((nt,), **f32),
+                "hq_out": torch.empty((n, h, w, 3), **f32),
+                "lq_out": torch.empty((n, h, w, 3), **f32),
+            })
+        io = _lib.cic_adaptive_io()
+        io.d_img, io.d_mask, io.d_bpp = ptr(img), ptr(mask), ptr(bpp)
+        io.d_blended, io.d_hq_latent_q, io.d_lq_latent_q = ptr(out["blended"]), ptr(out["hq_latent_q"]), ptr(out["lq_latent_q"])
+        io.d_rd_params, io.d_dt, io.d_hq_ratio_sum = ptr(out["rd_params"]), ptr(out["dt"]), ptr(out["hq_ratio_sum"])
+        if extras:
+            io.d_hq_symbols, io.d_lq_symbols = ptr(out["hq_symbols"]), ptr(out["lq_symbols"])
+            io.d_hq_latent, io.d_lq_latent = ptr(out["hq_latent"]), ptr(out["lq_latent"])
+            io.d_hq_scale, io.d_lq_scale = ptr(out["hq_scale"]), ptr(out["lq_scale"])
+            io.d_hq_out, io.d_lq_out = ptr(out["hq_out"]), ptr(out["lq_out"])
+        plan = self.plan()
+        ws = plan.workspace(n, h, w)
+        _lib.check(_lib.lib.cic_adaptive_forward(plan.handle, C.byref(io), n, h, w, ptr(ws), ws.numel(), runtime.stream_ptr()))
+        self.last = out
+        if extras:
+            return out
+        return [out["blended"], out["hq_latent_q"], out["lq_latent_q"], out["rd_params"], out["dt"]]

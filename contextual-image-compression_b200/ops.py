@@ -1,0 +1,193 @@
+"""Python faces of the stand-alone libcic operators (device tensors in, device tensors out)."""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib, runtime
+from .runtime import ptr, to_device_f32
+
+_ACT = {None: _lib.ACT_NONE, "linear": _lib.ACT_NONE, "relu": _lib.ACT_RELU, "lrelu": _lib.ACT_LRELU02,
+        "sigmoid": _lib.ACT_SIGMOID, "tanh": _lib.ACT_TANH}
+
+
+def conv2d_same(x, kernel, bias=None, stride=1, activation=None, scale=None, shift=None) -> torch.Tensor:
+    """Keras Conv2D(padding='same'); x (B,H,W,Cin), kernel (kh,kw,Cin,Cout)."""
+    x, kernel = to_device_f32(x), to_device_f32(kernel)
+    b, h, w, cin = x.shape
+    kh, kw, cin2, cout = kernel.shape
+    if cin != cin2:
+        raise ValueError(f"kernel expects {cin2} input channels, input has {cin}")
+    bias = to_device_f32(bias) if bias is not None else None
+    scale = to_device_f32(scale) if scale is not None else None
+    shift = to_device_f32(shift) if shift is not None else None
+    ho, wo = -(-h // stride), -(-w // stride)
+    y = torch.empty((b, ho, wo, cout), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib.cic_conv2d_nhwc_f32(ptr(x), ptr(kernel), ptr(bias), ptr(scale), ptr(shift), ptr(y), b, h, w, cin,
+                                            cout, kh, kw, stride, _ACT[activation], runtime.stream_ptr()))
+    return y
+
+
+def conv2d_transpose_k4s2(x, kernel, bias=None, activation=None, scale=None, shift=None) -> torch.Tensor:
+    """Keras Conv2DTranspose(kernel 4, stride 2, 'same'); kernel (4,4,Cout,Cin)."""
+    x, kernel = to_device_f32(x), to_device_f32(kernel)
+    b, h, w, cin = x.shape
+    if tuple(kernel.shape[:2]) != (4, 4) or kernel.shape[3] != cin:
+        raise ValueError(f"kernel must be (4,4,Cout,{cin}), got {tuple(kernel.shape)}")
+    cout = kernel.shape[2]
+    bias = to_device_f32(bias) if bias is not None else None
+    scale = to_device_f32(scale) if scale is not None else None
+    shift = to_device_f32(shift) if shift is not None else None
+    y = torch.empty((b, 2 * h, 2 * w, cout), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib.cic_conv2d_transpose4x4s2_nhwc_f32(ptr(x), ptr(kernel), ptr(bias), ptr(scale), ptr(shift), ptr(y),
+                                                           b, h, w, cin, cout, _ACT[activation], runtime.stream_ptr()))
+    return y
+
+
+def dense(x, kernel, bias=None, activation=None) -> torch.Tensor:
+    x, kernel = to_device_f32(x), to_device_f32(kernel)
+    b, k = x.shape
+    if kernel.shape[0] != k:
+        raise ValueError(f"kernel expects {kernel.shape[0]} inputs, got {k}")
+    n = kernel.shape[1]
+    bias = to_device_f32(bias) if bias is not None else None
+    y = torch.empty((b, n), dtype=torch.float32, device=x.device)
+    wsb = int(_lib.lib.cic_dense_workspace_bytes(b, k, n))
+    ws = runtime.Workspace.get(wsb) if wsb else None
+    _lib.check(_lib.lib.cic_dense_f32(ptr(x), ptr(kernel), ptr(bias), ptr(y), b, k, n, _ACT[activation], ptr(ws),
+                                      ws.numel() if ws is not None else 0, runtime.stream_ptr()))
+    return y
+
+
+def self_attention(x, wq, bq, wk, bk, wv, bv, gamma: float) -> torch.Tensor:
+    """SelfAttention.call (GAN_functions.py:344-369); x (B,H,W,C); wq/wk (1,1,C,C/8) or (C,C/8); wv (.,C,C)."""
+    x = to_device_f32(x)
+    b, h, w, c = x.shape
+    wq, wk, wv = (to_device_f32(t).reshape(c, -1) for t in (wq, wk, wv))
+    bq, bk, bv = (to_device_f32(t) if t is not None else None for t in (bq, bk, bv))
+    y = torch.empty_like(x)
+    wsb = int(_lib.lib.cic_attention_workspace_bytes(b, h * w, c))
+    ws = runtime.Workspace.get(wsb)
+    _lib.check(_lib.lib.cic_self_attention_f32(ptr(x), ptr(wq), ptr(bq), ptr(wk), ptr(bk), ptr(wv), ptr(bv), float(gamma),
+                                               ptr(y), b, h * w, c, ptr(ws), ws.numel(), runtime.stream_ptr()))
+    return y
+
+
+def quantize_latent(latent, saliency, quant_strength, want=("deq",)):
+    """AdaptiveQuantizationLayer.call (GAN_functions.py:435-446).  Returns a dict with the requested
+    outputs among 'deq', 'symbols', 'pre', 'scale'."""
+    latent = to_device_f32(latent)
+    b, L = latent.shape
+    sal = to_device_f32(saliency).reshape(-1)
+    qs = to_device_f32(quant_strength).reshape(-1)
+    if sal.numel() != b or qs.numel() != b:
+        raise ValueError(f"saliency and quant_strength need one value per row ({b}), got {sal.numel()} and {qs.numel()}")
+    dev = latent.device
+    out = {}
+    if "deq" in want:
+        out["deq"] = torch.empty_like(latent)
+    if "symbols" in want:
+        out["symbols"] = torch.empty((b, L), dtype=torch.int32, device=dev)
+    if "pre" in want:
+        out["pre"] = torch.empty_like(latent)
+    if "scale" in want:
+        out["scale"] = torch.empty((b,), dtype=torch.float32, device=dev)
+    _lib.check(_lib.lib.cic_quantize_latent(ptr(latent), ptr(sal), ptr(qs), ptr(out.get("deq")), ptr(out.get("symbols")),
+                                            ptr(out.get("pre")), ptr(out.get("scale")), b, L, runtime.stream_ptr()))
+    return out
+
+
+def rate_scalars(target_bpp):
+    """t, hq_lq_threshold, quant_strength of GAN_functions.py:631-649."""
+    bpp = to_device_f32(target_bpp).reshape(-1)
+    n = bpp.numel()
+    t, thr, qs = (torch.empty_like(bpp) for _ in range(3))
+    _lib.check(_lib.lib.cic_rate_scalars(ptr(bpp), ptr(t), ptr(thr), ptr(qs), n, runtime.stream_ptr()))
+    return t, thr, qs
+
+
+def roi_mask_blend(hq, lq, mask, target_bpp, want_dt=True, want_sum=True):
+    """dt = sigmoid((mask^0.7 - thr)*20); out = hq*dt + lq*(1-dt) (GAN_functions.py:651-684).
+    hq/lq may be None to get only the bit-allocation map."""
+    mask = to_device_f32(mask)
+    b = mask.shape[0]
+    hw = int(np.prod(mask.shape[1:3]))
+    bpp = to_device_f32(target_bpp).reshape(-1)
+    if bpp.numel() != b:
+        raise ValueError("one target bpp per image")
+    dev = mask.device
+    out = None
+    c = 3
+    if hq is not None:
+        hq, lq = to_device_f32(hq), to_device_f32(lq)
+        if hq.shape != lq.shape or hq.shape[0] != b or int(np.prod(hq.shape[1:3])) != hw:
+            raise ValueError(f"hq {tuple(hq.shape)}, lq {tuple(lq.shape)} and mask {tuple(mask.shape)} do not agree")
+        c = hq.shape[-1]
+        out = torch.empty_like(hq)
+    dt = torch.empty(mask.shape, dtype=torch.float32, device=dev) if want_dt else None
+    s = torch.empty((b,), dtype=torch.float64, device=dev) if want_sum else None
+    _lib.check(_lib.lib.cic_roi_mask_blend(ptr(hq), ptr(lq), ptr(mask), ptr(bpp), ptr(out), ptr(dt), ptr(s), b, hw, c,
+                                           runtime.stream_ptr()))
+    return out, dt, s
+
+
+def hq_ratio_sweep(mask, bpp_levels) -> torch.Tensor:
+    """(B, n_levels) float64 hq_ratio = mean(dt) for every image x target bpp, one pass over the masks."""
+    mask = to_device_f32(mask)
+    b = mask.shape[0]
+    hw = int(np.prod(mask.shape[1:3]))
+    levels = to_device_f32(np.asarray(bpp_levels, dtype=np.float32) if not isinstance(bpp_levels, torch.Tensor) else bpp_levels).reshape(-1)
+    out = torch.empty((b, levels.numel()), dtype=torch.float64, device=mask.device)
+    _lib.check(_lib.lib.cic_hq_ratio_sweep(ptr(mask), ptr(levels), levels.numel(), ptr(out), b, hw, runtime.stream_ptr()))
+    return out
+
+
+def symbol_entropy_bits(symbols: torch.Tensor) -> torch.Tensor:
+    if symbols.dtype != torch.int32 or not symbols.is_cuda:
+        symbols = torch.as_tensor(np.asarray(symbols.cpu() if isinstance(symbols, torch.Tensor) else symbols)).to(torch.int32).to(runtime.require_cuda())
+    symbols = symbols.contiguous()
+    b, L = symbols.shape
+    out = torch.empty((b,), dtype=torch.float64, device=symbols.device)
+    _lib.check(_lib.lib.cic_symbol_entropy_bits(ptr(symbols), ptr(out), b, L, runtime.stream_ptr()))
+    return out
+
+
+def f32_to_u8_trunc(x, mul: float = 255.0) -> torch.Tensor:
+    x = to_device_f32(x)
+    y = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    _lib.check(_lib.lib.cic_f32_to_u8_trunc(ptr(x), ptr(y), x.numel(), float(mul), runtime.stream_ptr()))
+    return y
+
+
+def metrics_f32(a, b, signed_range: bool, data_range: float = 1.0) -> torch.Tensor:
+    """(B,4) float64 [psnr, ssim, mse, sse]; signed_range maps [-1,1] -> [0,1] first (compute_metrics)."""
+    a, b = to_device_f32(a), to_device_f32(b)
+    if a.dim() == 3:
+        a, b = a.unsqueeze(0), b.unsqueeze(0)
+    if a.shape != b.shape:
+        raise ValueError(f"shape mismatch {tuple(a.shape)} vs {tuple(b.shape)}")
+    n, h, w, c = a.shape
+    out = torch.empty((n, 4), dtype=torch.float64, device=a.device)
+    pre_add, pre_mul = (1.0, 0.5) if signed_range else (0.0, 1.0)
+    _lib.check(_lib.lib.cic_metrics_psnr_ssim_f32(ptr(a), ptr(b), ptr(out), n, h, w, c, pre_add, pre_mul, float(data_range),
+                                                  runtime.stream_ptr()))
+    return out
+
+
+def metrics_gray_u8(a, b) -> torch.Tensor:
+    """(B,4) float64 [psnr, ssim(gray), true mse, wrapped uint8 mse] for uint8 BGR images."""
+    dev = runtime.require_cuda()
+    ta = torch.as_tensor(a).to(dev).contiguous()
+    tb = torch.as_tensor(b).to(dev).contiguous()
+    if ta.dtype != torch.uint8 or tb.dtype != torch.uint8:
+        raise ValueError("uint8 images expected")
+    if ta.dim() == 3:
+        ta, tb = ta.unsqueeze(0), tb.unsqueeze(0)
+    n, h, w, c = ta.shape
+    if c != 3 or ta.shape != tb.shape:
+        raise ValueError(f"expected matching (B,H,W,3) images, got {tuple(ta.shape)} and {tuple(tb.shape)}")
+    out = torch.empty((n, 4), dtype=torch.float64, device=dev)
+    _lib.check(_lib.lib.cic_metrics_psnr_ssim_gray_u8(ptr(ta), ptr(tb), ptr(out), n, h, w, runtime.stream_ptr()))
+    return out

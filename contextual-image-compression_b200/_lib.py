@@ -59,6 +59,8 @@ PROTOTYPES = {
     "cic_plan_destroy": (None, [_vp]),
     "cic_plan_workspace_bytes": (_sz, [_vp, _i, _i, _i]),
     "cic_plan_last_launch_count": (_i, [_vp]),
+    "cic_plan_set_profiling": (_i, [_vp, _i]),
+    "cic_plan_get_profile": (_sz, [_vp, C.c_char_p, _sz]),
     "cic_autoencoder_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
     "cic_encoder_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
     "cic_generator_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _sz, _vp]),

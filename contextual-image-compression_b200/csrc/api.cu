@@ -80,7 +80,7 @@ static void fill_conv(IGemmParams& p, const float* x, int batch, int h, int w, i
 extern "C" int cic_conv2d_nhwc_f32(const float* d_x, const float* d_kernel, const float* d_bias, const float* d_scale,
                                    const float* d_shift, float* d_y, int batch, int h, int w, int cin, int cout, int kh,
                                    int kw, int stride, int act, void* stream) {
-  CIC_REQUIRE(d_x && d_kernel && d_y, "cic_conv2d_nhwc_f32: null pointer");
+  CIC_REQUIRE(batch == 0 || (d_x && d_kernel && d_y), "cic_conv2d_nhwc_f32: null pointer");
   CIC_REQUIRE(batch >= 0 && h > 0 && w > 0 && cin > 0 && cout > 0 && kh > 0 && kw > 0 && stride > 0,
               "cic_conv2d_nhwc_f32: bad shape");
   CIC_REQUIRE((d_scale == nullptr) == (d_shift == nullptr), "cic_conv2d_nhwc_f32: scale and shift go together");
@@ -169,9 +169,9 @@ int run_dense(const float* x, const float* kernel, const float* bias, const floa
 
 extern "C" int cic_dense_f32(const float* d_x, const float* d_kernel, const float* d_bias, float* d_y, int batch,
                              int in_dim, int out_dim, int act, void* d_workspace, size_t workspace_bytes, void* stream) {
-  CIC_REQUIRE(d_x && d_kernel && d_y, "cic_dense_f32: null pointer");
   CIC_REQUIRE(batch >= 0 && in_dim > 0 && out_dim > 0, "cic_dense_f32: bad shape");
   if (batch == 0) return CIC_OK;
+  CIC_REQUIRE(d_x && d_kernel && d_y, "cic_dense_f32: null pointer");
   return run_dense(d_x, d_kernel, d_bias, nullptr, nullptr, d_y, batch, in_dim, out_dim, act, (float*)d_workspace,
                    workspace_bytes / sizeof(float), (cudaStream_t)stream);
 }

@@ -67,11 +67,11 @@ roi_blend_c3_kernel(const float* __restrict__ hq, const float* __restrict__ lq, 
   const float thr = rate_thr(rate_t(bpp[img]));
   const size_t pbase = (size_t)img * hw;
   const int nquad = hw >> 2;
-  float local = 0.f;
+  double local = 0.0;
   for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nquad; q += gridDim.x * blockDim.x) {
     const float4 m = __ldg(reinterpret_cast<const float4*>(mask + pbase) + q);
     float d[4] = {dyn_threshold(m.x, thr), dyn_threshold(m.y, thr), dyn_threshold(m.z, thr), dyn_threshold(m.w, thr)};
-    local += (d[0] + d[1]) + (d[2] + d[3]);
+    local += ((double)d[0] + (double)d[1]) + ((double)d[2] + (double)d[3]);
     if (dt_out) reinterpret_cast<float4*>(dt_out + pbase)[q] = make_float4(d[0], d[1], d[2], d[3]);
     if (BLEND) {
       const float4* h4 = reinterpret_cast<const float4*>(hq + pbase * 3) + (size_t)q * 3;
@@ -96,7 +96,7 @@ roi_blend_c3_kernel(const float* __restrict__ hq, const float* __restrict__ lq, 
   }
   if (dt_sum) {
     __shared__ double wsum[8];
-    double s = warp_sum((double)local);
+    double s = warp_sum(local);
     if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = s;
     __syncthreads();
     if (threadIdx.x < 32) {
@@ -148,7 +148,7 @@ hq_ratio_sweep_kernel(const float* __restrict__ mask, const float* __restrict__ 
 #pragma unroll
   for (int l = 0; l < kMaxLevels; ++l) acc[l] = 0.f;
   const size_t pbase = (size_t)img * hw;
-  const int nquad = hw >> 2;
+  const int nquad = (hw & 3) == 0 ? (hw >> 2) : 0;  // 128-bit loads need every image base 16-byte aligned
   for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nquad; q += gridDim.x * blockDim.x) {
     const float4 m = __ldg(reinterpret_cast<const float4*>(mask + pbase) + q);
     const float es[4] = {powf(m.x, 0.7f), powf(m.y, 0.7f), powf(m.z, 0.7f), powf(m.w, 0.7f)};
@@ -161,9 +161,9 @@ hq_ratio_sweep_kernel(const float* __restrict__ mask, const float* __restrict__ 
       }
     }
   }
-  // tail pixels (hw not a multiple of 4)
-  if (blockIdx.x == 0) {
-    for (int p = (nquad << 2) + threadIdx.x; p < hw; p += blockDim.x) {
+  // scalar path when hw is not a multiple of 4
+  {
+    for (int p = (nquad << 2) + blockIdx.x * blockDim.x + threadIdx.x; p < hw; p += gridDim.x * blockDim.x) {
       const float es = powf(mask[pbase + p], 0.7f);
       for (int l = 0; l < n_levels; ++l) acc[l] += sigmoidf_(__fmul_rn(__fsub_rn(es, s_thr[l]), 20.0f));
     }
@@ -255,9 +255,9 @@ using namespace cic;
 extern "C" int cic_quantize_latent(const float* d_latent, const float* d_sal, const float* d_qs, float* d_deq,
                                    int32_t* d_symbols, float* d_pre, float* d_scale, int batch, int latent_dim,
                                    void* stream) {
-  CIC_REQUIRE(d_latent && d_sal && d_qs, "cic_quantize_latent: null input");
   CIC_REQUIRE(batch >= 0 && latent_dim > 0, "cic_quantize_latent: bad shape (%d,%d)", batch, latent_dim);
   if (batch == 0) return CIC_OK;
+  CIC_REQUIRE(d_latent && d_sal && d_qs, "cic_quantize_latent: null input");
   int gx = (latent_dim / 4 + 255) / 256;
   if (gx < 1) gx = 1;
   if (gx > 64) gx = 64;
@@ -270,8 +270,9 @@ extern "C" int cic_quantize_latent(const float* d_latent, const float* d_sal, co
 }
 
 extern "C" int cic_rate_scalars(const float* d_bpp, float* d_t, float* d_thr, float* d_qs, int n, void* stream) {
-  CIC_REQUIRE(d_bpp && n >= 0, "cic_rate_scalars: bad args");
+  CIC_REQUIRE(n >= 0, "cic_rate_scalars: bad args");
   if (n == 0) return CIC_OK;
+  CIC_REQUIRE(d_bpp, "cic_rate_scalars: null input");
   rate_scalars_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_bpp, d_t, d_thr, d_qs, n);
   CIC_COUNT_LAUNCH();
   CIC_CHECK_LAUNCH("rate_scalars_kernel");
@@ -281,10 +282,10 @@ extern "C" int cic_rate_scalars(const float* d_bpp, float* d_t, float* d_thr, fl
 extern "C" int cic_roi_mask_blend(const float* d_hq, const float* d_lq, const float* d_mask, const float* d_bpp,
                                   float* d_out, float* d_dt, double* d_dt_sum, int batch, int hw, int channels,
                                   void* stream) {
-  CIC_REQUIRE(d_mask && d_bpp, "cic_roi_mask_blend: null mask/bpp");
-  CIC_REQUIRE((d_hq == nullptr) == (d_lq == nullptr), "cic_roi_mask_blend: hq and lq must both be given or both NULL");
   CIC_REQUIRE(batch >= 0 && hw > 0 && channels > 0, "cic_roi_mask_blend: bad shape");
   if (batch == 0) return CIC_OK;
+  CIC_REQUIRE(d_mask && d_bpp, "cic_roi_mask_blend: null mask/bpp");
+  CIC_REQUIRE((d_hq == nullptr) == (d_lq == nullptr), "cic_roi_mask_blend: hq and lq must both be given or both NULL");
   cudaStream_t st = (cudaStream_t)stream;
   if (d_dt_sum) CIC_CHECK_CUDA(cudaMemsetAsync(d_dt_sum, 0, sizeof(double) * batch, st));
   const bool blend = d_hq != nullptr && d_out != nullptr;
@@ -309,10 +310,10 @@ extern "C" int cic_roi_mask_blend(const float* d_hq, const float* d_lq, const fl
 
 extern "C" int cic_hq_ratio_sweep(const float* d_mask, const float* d_bpp_levels, int n_levels, double* d_ratio,
                                   int batch, int hw, void* stream) {
-  CIC_REQUIRE(d_mask && d_bpp_levels && d_ratio, "cic_hq_ratio_sweep: null pointer");
   CIC_REQUIRE(n_levels >= 1 && n_levels <= kMaxLevels, "cic_hq_ratio_sweep: n_levels must be in [1,%d]", kMaxLevels);
   CIC_REQUIRE(batch >= 0 && hw > 0, "cic_hq_ratio_sweep: bad shape");
   if (batch == 0) return CIC_OK;
+  CIC_REQUIRE(d_mask && d_bpp_levels && d_ratio, "cic_hq_ratio_sweep: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   CIC_CHECK_CUDA(cudaMemsetAsync(d_ratio, 0, sizeof(double) * batch * n_levels, st));
   int gx = grid_for((size_t)hw / 4 + 1, 256, 4);
@@ -331,8 +332,9 @@ extern "C" int cic_hq_ratio_sweep(const float* d_mask, const float* d_bpp_levels
 
 extern "C" int cic_symbol_entropy_bits(const int32_t* d_symbols, double* d_bits, int batch, int latent_dim,
                                        void* stream) {
-  CIC_REQUIRE(d_symbols && d_bits && batch >= 0 && latent_dim > 0, "cic_symbol_entropy_bits: bad args");
+  CIC_REQUIRE(batch >= 0 && latent_dim > 0, "cic_symbol_entropy_bits: bad shape");
   if (batch == 0) return CIC_OK;
+  CIC_REQUIRE(d_symbols && d_bits, "cic_symbol_entropy_bits: null pointer");
   symbol_entropy_kernel<<<batch, 256, 0, (cudaStream_t)stream>>>(d_symbols, d_bits, latent_dim);
   CIC_COUNT_LAUNCH();
   CIC_CHECK_LAUNCH("symbol_entropy_kernel");
@@ -340,8 +342,8 @@ extern "C" int cic_symbol_entropy_bits(const int32_t* d_symbols, double* d_bits,
 }
 
 extern "C" int cic_f32_to_u8_trunc(const float* d_x, uint8_t* d_y, size_t n, float mul, void* stream) {
-  CIC_REQUIRE(d_x && d_y, "cic_f32_to_u8_trunc: null pointer");
   if (n == 0) return CIC_OK;
+  CIC_REQUIRE(d_x && d_y, "cic_f32_to_u8_trunc: null pointer");
   f32_to_u8_kernel<<<grid_for(n / 4 + 1, 256, 8), 256, 0, (cudaStream_t)stream>>>(d_x, d_y, n, mul);
   CIC_COUNT_LAUNCH();
   CIC_CHECK_LAUNCH("f32_to_u8_kernel");

@@ -250,7 +250,7 @@ using namespace cic;
 
 extern "C" int cic_metrics_psnr_ssim_f32(const float* d_a, const float* d_b, double* d_out, int batch, int h, int w,
                                          int channels, float pre_add, float pre_mul, float data_range, void* stream) {
-  CIC_REQUIRE(d_a && d_b && d_out, "cic_metrics_psnr_ssim_f32: null pointer");
+  CIC_REQUIRE(batch == 0 || (d_a && d_b && d_out), "cic_metrics_psnr_ssim_f32: null pointer");
   CIC_REQUIRE(batch >= 0 && h >= 7 && w >= 7 && channels >= 1 && channels <= 65535,
               "cic_metrics_psnr_ssim_f32: needs h,w >= 7 (7x7 SSIM window), got %dx%dx%d", h, w, channels);
   if (batch == 0) return CIC_OK;
@@ -279,7 +279,7 @@ extern "C" int cic_metrics_psnr_ssim_f32(const float* d_a, const float* d_b, dou
 
 extern "C" int cic_metrics_psnr_ssim_gray_u8(const uint8_t* d_a, const uint8_t* d_b, double* d_out, int batch, int h,
                                              int w, void* stream) {
-  CIC_REQUIRE(d_a && d_b && d_out, "cic_metrics_psnr_ssim_gray_u8: null pointer");
+  CIC_REQUIRE(batch == 0 || (d_a && d_b && d_out), "cic_metrics_psnr_ssim_gray_u8: null pointer");
   CIC_REQUIRE(batch >= 0 && h >= 7 && w >= 7, "cic_metrics_psnr_ssim_gray_u8: needs h,w >= 7, got %dx%d", h, w);
   if (batch == 0) return CIC_OK;
   cudaStream_t st = (cudaStream_t)stream;

@@ -55,10 +55,42 @@ struct Arena {
   void release(size_t m) { off = m; }
 };
 
+// Optional per-layer timing: CUDA events recorded on the launch stream around every layer of a
+// forward call (cic_plan_set_profiling).  bench.py uses it for the live roofline of the conv GEMMs.
+struct Profiler {
+  struct Rec {
+    std::string name;
+    cudaEvent_t e0, e1;
+    double flops, bytes;
+  };
+  bool on = false;
+  std::vector<Rec> recs;
+  std::vector<cudaEvent_t> pool;
+  std::string prefix;
+  ~Profiler();
+  cudaEvent_t get_event();
+  void reset();
+  int begin(const std::string& name, double flops, double bytes, cudaStream_t st);
+  void end(int idx, cudaStream_t st);
+  std::string report();  // synchronises; one "name,ms,flops,bytes" line per layer
+};
+
 struct Ctx {
   Arena arena;
   cudaStream_t st = nullptr;
   bool dry = false;  // measure workspace only, launch nothing
+  Profiler* prof = nullptr;
+};
+
+struct Scope {  // RAII layer bracket
+  Ctx& c;
+  int idx = -1;
+  Scope(Ctx& ctx, const std::string& name, double flops = 0, double bytes = 0) : c(ctx) {
+    if (c.prof && c.prof->on && !c.dry) idx = c.prof->begin(name, flops, bytes, c.st);
+  }
+  ~Scope() {
+    if (idx >= 0) c.prof->end(idx, c.st);
+  }
 };
 
 int run_dense(const float* x, const float* kernel, const float* bias, const float* scale, const float* shift, float* y,
@@ -72,6 +104,7 @@ struct cic_plan {
   cic_plan_opts opts{};
   cic::WeightStore w;
   long long last_launches = 0;
+  cic::Profiler prof;
   // CIC_PLAN_ADAPTIVE owns its seven sub-models
   std::unique_ptr<cic_plan> hq_enc, lq_enc, hq_gen, lq_gen, sal_hq, sal_lq, rd;
 };

@@ -39,6 +39,42 @@ const DevTensor* WeightStore::find(const std::string& name) const {
   return it == t_.end() ? nullptr : &it->second;
 }
 
+Profiler::~Profiler() {
+  for (auto& r : recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  for (auto e : pool) cudaEventDestroy(e);
+}
+cudaEvent_t Profiler::get_event() {
+  if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+void Profiler::reset() {
+  for (auto& r : recs) { pool.push_back(r.e0); pool.push_back(r.e1); }
+  recs.clear();
+}
+int Profiler::begin(const std::string& name, double flops, double bytes, cudaStream_t st) {
+  Rec r{prefix + name, get_event(), get_event(), flops, bytes};
+  cudaEventRecord(r.e0, st);
+  recs.push_back(r);
+  return (int)recs.size() - 1;
+}
+void Profiler::end(int idx, cudaStream_t st) {
+  if (idx >= 0 && idx < (int)recs.size()) cudaEventRecord(recs[idx].e1, st);
+}
+std::string Profiler::report() {
+  std::string out;
+  char line[256];
+  for (auto& r : recs) {
+    float ms = 0.f;
+    cudaEventSynchronize(r.e1);
+    cudaEventElapsedTime(&ms, r.e0, r.e1);
+    snprintf(line, sizeof(line), "%s,%.6f,%.6e,%.6e\n", r.name.c_str(), ms, r.flops, r.bytes);
+    out += line;
+  }
+  return out;
+}
+
 // ---- host-side tensor lookup during plan creation ---------------------------------------------
 struct HostTensors {
   const cic_tensor* t;
@@ -260,9 +296,12 @@ static Srcs two(const float* p0, int C0, int up0, const float* p1, int C1) {
   return r;
 }
 
-static int conv_same(Ctx& c, const Srcs& in, int batch, int H, int W, const float* kernel, int kh, int kw, int stride,
-                     int cout, const float* bias, const float* scale, const float* shift, int act, float* out) {
+static int conv_same(Ctx& c, const char* name, const Srcs& in, int batch, int H, int W, const float* kernel, int kh, int kw,
+                     int stride, int cout, const float* bias, const float* scale, const float* shift, int act, float* out) {
   if (c.dry) return CIC_OK;
+  const int cin_ = in.s[0].C + (in.n > 1 ? in.s[1].C : 0);
+  const double mrows = (double)batch * same_out(H, stride) * same_out(W, stride);
+  Scope sc(c, name, 2.0 * mrows * cout * kh * kw * cin_, 4.0 * ((double)batch * H * W * cin_ + mrows * cout));
   IGemmParams p{};
   p.src[0] = in.s[0];
   p.src[1] = in.s[1];
@@ -279,10 +318,11 @@ static int conv_same(Ctx& c, const Srcs& in, int batch, int H, int W, const floa
   return launch_igemm(p, c.st);
 }
 
-static int deconv_k4s2(Ctx& c, const Srcs& in, int batch, int H, int W, const float* phases, int cout, const float* bias,
-                       const float* scale, const float* shift, int act, float* out) {
+static int deconv_k4s2(Ctx& c, const char* name, const Srcs& in, int batch, int H, int W, const float* phases, int cout,
+                       const float* bias, const float* scale, const float* shift, int act, float* out) {
   if (c.dry) return CIC_OK;
   const int cin = in.s[0].C + (in.n > 1 ? in.s[1].C : 0);
+  Scope sc(c, name, 2.0 * (double)batch * H * W * 4 * 4 * cin * cout, 4.0 * (double)batch * H * W * (cin + 4.0 * cout));
   for (int ph = 0; ph < 4; ++ph) {
     const int py = ph >> 1, px = ph & 1;
     IGemmParams p{};
@@ -304,8 +344,9 @@ static int deconv_k4s2(Ctx& c, const Srcs& in, int batch, int H, int W, const fl
   return CIC_OK;
 }
 
-static int dense(Ctx& c, const float* x, const float* kernel, const float* bias, const float* scale, const float* shift,
-                 float* y, int batch, int in_dim, int out_dim, int act) {
+static int dense(Ctx& c, const char* name, const float* x, const float* kernel, const float* bias, const float* scale,
+                 const float* shift, float* y, int batch, int in_dim, int out_dim, int act) {
+  Scope sc(c, name, 2.0 * batch * (double)in_dim * out_dim, 4.0 * ((double)in_dim * out_dim + (double)batch * (in_dim + out_dim)));
   const size_t wsb = cic_dense_workspace_bytes(batch, in_dim, out_dim);
   const size_t mk = c.arena.mark();
   float* ws = wsb ? (float*)c.arena.alloc_bytes(wsb) : nullptr;
@@ -316,9 +357,10 @@ static int dense(Ctx& c, const float* x, const float* kernel, const float* bias,
 }
 
 // SelfAttention.call: qkv 1x1 conv -> S = q k^T -> softmax rows -> gamma * (P v) + x
-static int attention_f32(Ctx& c, const float* x, const float* wqkv, const float* bqkv, const float* d_gamma, float gamma_host,
+static int attention_f32(Ctx& c, const char* name, const float* x, const float* wqkv, const float* bqkv, const float* d_gamma, float gamma_host,
                          bool gamma_on_device, float* y, int batch, int tokens, int C) {
   const int dq = C / 8, N = 2 * dq + C;
+  Scope sc(c, name, 2.0 * batch * tokens * ((double)C * N + (double)tokens * dq + (double)tokens * C), 8.0 * batch * tokens * C);
   const int chunk_max = 32;  // images per pass: bounds the tokens x tokens score matrix workspace
   const size_t mk = c.arena.mark();
   const int chunk = batch < chunk_max ? batch : chunk_max;
@@ -334,7 +376,7 @@ static int attention_f32(Ctx& c, const float* x, const float* wqkv, const float*
     const int nb = batch - b0 < chunk ? batch - b0 : chunk;
     const float* xb = x + (size_t)b0 * tokens * C;
     // q, k, v projections as one GEMM: (nb*tokens, C) x (C, N)
-    rc = conv_same(c, one(xb, C), nb * tokens, 1, 1, wqkv, 1, 1, 1, N, bqkv, nullptr, nullptr, CIC_ACT_NONE, qkv);
+    rc = conv_same(c, "qkv", one(xb, C), nb * tokens, 1, 1, wqkv, 1, 1, 1, N, bqkv, nullptr, nullptr, CIC_ACT_NONE, qkv);
     if (rc) break;
     // S[b] = q[b] k[b]^T  (no 1/sqrt(d) scaling, GAN_functions.py:358)
     IGemmParams p{};
@@ -380,15 +422,17 @@ int autoencoder_forward_f32(cic_plan* pl, Ctx& c, const float* x, float* y, uint
   int rc;
 #define K(n) w.ptr(n "/kernel"), 3, 3, 1
 #define Bv(n) w.ptr(n "/bias"), nullptr, nullptr
-  if ((rc = conv_same(c, one(x, C), B, H, W, K("conv1"), 32, Bv("conv1"), CIC_ACT_RELU, x1))) return rc;          // :14
-  if ((rc = launch_maxpool2x2(x1, x1p, B, H, W, 32, c.st))) return rc;                                              // :15
-  if ((rc = conv_same(c, one(x1p, 32), B, H / 2, W / 2, K("conv2"), 64, Bv("conv2"), CIC_ACT_RELU, x2))) return rc;  // :17
-  if ((rc = launch_maxpool2x2(x2, enc, B, H / 2, W / 2, 64, c.st))) return rc;                                      // :18
-  if ((rc = conv_same(c, one(enc, 64), B, H / 4, W / 4, K("conv3"), 64, Bv("conv3"), CIC_ACT_RELU, y3))) return rc;  // :21
-  if ((rc = conv_same(c, one(x2, 64), B, H / 2, W / 2, K("conv_x2"), 64, Bv("conv_x2"), CIC_ACT_RELU, x2r))) return rc;  // :25
+  if ((rc = conv_same(c, "conv1", one(x, C), B, H, W, K("conv1"), 32, Bv("conv1"), CIC_ACT_RELU, x1))) return rc;          // :14
+  { Scope sc(c, "pool1", 0, 4.0 * px * 32 * 1.25);
+    if ((rc = launch_maxpool2x2(x1, x1p, B, H, W, 32, c.st))) return rc; }                                              // :15
+  if ((rc = conv_same(c, "conv2", one(x1p, 32), B, H / 2, W / 2, K("conv2"), 64, Bv("conv2"), CIC_ACT_RELU, x2))) return rc;  // :17
+  { Scope sc(c, "pool2", 0, 4.0 * px / 4 * 64 * 1.25);
+    if ((rc = launch_maxpool2x2(x2, enc, B, H / 2, W / 2, 64, c.st))) return rc; }                                      // :18
+  if ((rc = conv_same(c, "conv3", one(enc, 64), B, H / 4, W / 4, K("conv3"), 64, Bv("conv3"), CIC_ACT_RELU, y3))) return rc;  // :21
+  if ((rc = conv_same(c, "conv_x2", one(x2, 64), B, H / 2, W / 2, K("conv_x2"), 64, Bv("conv_x2"), CIC_ACT_RELU, x2r))) return rc;  // :25
   // :22 UpSampling2D + :26 concatenate folded into the gather of conv5 (:28)
-  if ((rc = conv_same(c, two(y3, 64, 1, x2r, 64), B, H / 2, W / 2, K("conv5"), 32, Bv("conv5"), CIC_ACT_RELU, y5))) return rc;
-  if ((rc = conv_same(c, one(x1, 32), B, H, W, K("conv_x1"), 32, Bv("conv_x1"), CIC_ACT_RELU, x1r))) return rc;     // :32
+  if ((rc = conv_same(c, "conv5", two(y3, 64, 1, x2r, 64), B, H / 2, W / 2, K("conv5"), 32, Bv("conv5"), CIC_ACT_RELU, y5))) return rc;
+  if ((rc = conv_same(c, "conv_x1", one(x1, 32), B, H, W, K("conv_x1"), 32, Bv("conv_x1"), CIC_ACT_RELU, x1r))) return rc;     // :32
 #undef K
 #undef Bv
   // :29 UpSampling2D + :33 concatenate + :35 Conv2D(3, sigmoid)
@@ -397,7 +441,9 @@ int autoencoder_forward_f32(cic_plan* pl, Ctx& c, const float* x, float* y, uint
   s.src[1] = ConvSrc{x1r, 32, 32, 0};
   s.nsrc = 2; s.Cin = 64; s.batch = B; s.H = H; s.W = W; s.kh = 3; s.kw = 3; s.pad_t = 1; s.pad_l = 1;
   s.Wmat = w.ptr("conv_out/kernel"); s.bias = w.ptr("conv_out/bias"); s.N = C; s.act = CIC_ACT_SIGMOID; s.out = y;
-  if ((rc = launch_conv_small_n(s, c.st))) return rc;
+  { Scope sc(c, "conv_out", 2.0 * px * 9 * 64 * C, 4.0 * px * (64 + C));
+    if ((rc = launch_conv_small_n(s, c.st))) return rc; }
+  Scope sc(c, "cast_u8", 0, 5.0 * px * C);
   if (y_u8) rc = cic_f32_to_u8_trunc(y, y_u8, px * C, 255.0f, c.st);                                                 // test_autoencoder.py:88
   return rc;
 }
@@ -412,20 +458,20 @@ int encoder_forward_f32(cic_plan* pl, Ctx& c, const float* img, float* latent, f
   float* x3a = pl->opts.add_attention ? c.arena.f32(px / 64 * 256) : x3;
   float* x4 = c.arena.f32(px / 256 * 512);
   int rc;
-  if ((rc = conv_same(c, one(img, C), B, H, W, w.ptr("conv1/kernel"), 4, 4, 2, 64, w.ptr("conv1/bias"), nullptr, nullptr,
+  if ((rc = conv_same(c, "conv1", one(img, C), B, H, W, w.ptr("conv1/kernel"), 4, 4, 2, 64, w.ptr("conv1/bias"), nullptr, nullptr,
                       CIC_ACT_LRELU02, x1))) return rc;                                                              // :300-301
-  if ((rc = conv_same(c, one(x1, 64), B, H / 2, W / 2, w.ptr("conv2/kernel"), 4, 4, 2, 128, w.ptr("conv2/bias"),
+  if ((rc = conv_same(c, "conv2", one(x1, 64), B, H / 2, W / 2, w.ptr("conv2/kernel"), 4, 4, 2, 128, w.ptr("conv2/bias"),
                       w.ptr("bn2/scale"), w.ptr("bn2/shift"), CIC_ACT_LRELU02, x2))) return rc;                      // :304-306
-  if ((rc = conv_same(c, one(x2, 128), B, H / 4, W / 4, w.ptr("conv3/kernel"), 4, 4, 2, 256, w.ptr("conv3/bias"),
+  if ((rc = conv_same(c, "conv3", one(x2, 128), B, H / 4, W / 4, w.ptr("conv3/kernel"), 4, 4, 2, 256, w.ptr("conv3/bias"),
                       w.ptr("bn3/scale"), w.ptr("bn3/shift"), CIC_ACT_LRELU02, x3))) return rc;                      // :309-311
   if (pl->opts.add_attention) {                                                                                      // :315-318
-    if ((rc = attention_f32(c, x3, w.ptr("attn/qkv/kernel"), w.ptr("attn/qkv/bias"), w.ptr("attn/gamma"), 0.f, true, x3a, B,
+    if ((rc = attention_f32(c, "attention", x3, w.ptr("attn/qkv/kernel"), w.ptr("attn/qkv/bias"), w.ptr("attn/gamma"), 0.f, true, x3a, B,
                             (H / 8) * (W / 8), 256))) return rc;
   }
-  if ((rc = conv_same(c, one(x3a, 256), B, H / 8, W / 8, w.ptr("conv4/kernel"), 4, 4, 2, 512, w.ptr("conv4/bias"),
+  if ((rc = conv_same(c, "conv4", one(x3a, 256), B, H / 8, W / 8, w.ptr("conv4/kernel"), 4, 4, 2, 512, w.ptr("conv4/bias"),
                       w.ptr("bn4/scale"), w.ptr("bn4/shift"), CIC_ACT_LRELU02, x4))) return rc;                      // :320-322
   const int feat = (H / 16) * (W / 16) * 512;
-  return dense(c, x4, w.ptr("dense/kernel"), w.ptr("dense/bias"), nullptr, nullptr, latent, B, feat, L, CIC_ACT_NONE);  // :325-326
+  return dense(c, "dense", x4, w.ptr("dense/kernel"), w.ptr("dense/bias"), nullptr, nullptr, latent, B, feat, L, CIC_ACT_NONE);  // :325-326
 }
 
 int generator_forward_f32(cic_plan* pl, Ctx& c, const float* latent, const float* s1, const float* s2, const float* s3,
@@ -441,10 +487,10 @@ int generator_forward_f32(cic_plan* pl, Ctx& c, const float* latent, const float
   float* g4 = c.arena.f32(px * 32);
   int rc;
   // :247-250 Dense -> Reshape(h16,w16,512) NHWC -> BN -> LeakyReLU
-  if ((rc = dense(c, latent, w.ptr("dense/kernel"), w.ptr("dense/bias"), w.ptr("bn0/scale"), w.ptr("bn0/shift"), g0, B, L, feat,
+  if ((rc = dense(c, "dense", latent, w.ptr("dense/kernel"), w.ptr("dense/bias"), w.ptr("bn0/scale"), w.ptr("bn0/shift"), g0, B, L, feat,
                   CIC_ACT_LRELU02))) return rc;
 #define DC(i, srcs, hh, ww, co, dst)                                                                             \
-  if ((rc = deconv_k4s2(c, srcs, B, hh, ww, w.ptr("deconv" #i "/phases"), co, w.ptr("deconv" #i "/bias"),       \
+  if ((rc = deconv_k4s2(c, "deconv" #i, srcs, B, hh, ww, w.ptr("deconv" #i "/phases"), co, w.ptr("deconv" #i "/bias"),       \
                         w.ptr("bn" #i "/scale"), w.ptr("bn" #i "/shift"), CIC_ACT_LRELU02, dst))) return rc
   DC(1, one(g0, 512), h16, w16, 256, g1);                            // :253-255
   DC(2, two(g1, 256, 0, s3, 256), 2 * h16, 2 * w16, 128, g2);        // :256 concat skip3, :258-260
@@ -457,6 +503,7 @@ int generator_forward_f32(cic_plan* pl, Ctx& c, const float* latent, const float
   s.nsrc = 1; s.Cin = 32; s.batch = B; s.H = H; s.W = W; s.kh = 4; s.kw = 4;
   s.pad_t = same_pad_before(H, 4, 1); s.pad_l = same_pad_before(W, 4, 1);
   s.Wmat = w.ptr("conv_out/kernel"); s.bias = w.ptr("conv_out/bias"); s.N = C; s.act = CIC_ACT_TANH; s.out = out;
+  Scope sc(c, "conv_out", 2.0 * px * 16 * 32 * C, 4.0 * px * (32 + C));
   return launch_conv_small_n(s, c.st);
 }
 
@@ -466,9 +513,9 @@ int saliency_forward_f32(cic_plan* pl, Ctx& c, const float* latent, float* score
   float* h1 = c.arena.f32((size_t)B * 512);
   float* h2 = c.arena.f32((size_t)B * 256);
   int rc;
-  if ((rc = dense(c, latent, w.ptr("dense1/kernel"), w.ptr("dense1/bias"), nullptr, nullptr, h1, B, L, 512, CIC_ACT_RELU))) return rc;
-  if ((rc = dense(c, h1, w.ptr("dense2/kernel"), w.ptr("dense2/bias"), nullptr, nullptr, h2, B, 512, 256, CIC_ACT_RELU))) return rc;
-  return dense(c, h2, w.ptr("dense3/kernel"), w.ptr("dense3/bias"), nullptr, nullptr, score, B, 256, 1, CIC_ACT_SIGMOID);
+  if ((rc = dense(c, "dense1", latent, w.ptr("dense1/kernel"), w.ptr("dense1/bias"), nullptr, nullptr, h1, B, L, 512, CIC_ACT_RELU))) return rc;
+  if ((rc = dense(c, "dense2", h1, w.ptr("dense2/kernel"), w.ptr("dense2/bias"), nullptr, nullptr, h2, B, 512, 256, CIC_ACT_RELU))) return rc;
+  return dense(c, "dense3", h2, w.ptr("dense3/kernel"), w.ptr("dense3/bias"), nullptr, nullptr, score, B, 256, 1, CIC_ACT_SIGMOID);
 }
 
 int rd_forward_f32(cic_plan* pl, Ctx& c, const float* mask, const float* bpp, float* rd_params, int B) {
@@ -481,9 +528,9 @@ int rd_forward_f32(cic_plan* pl, Ctx& c, const float* mask, const float* bpp, fl
   float* d1 = c.arena.f32((size_t)B * 128);
   float* base = c.arena.f32((size_t)B * 3);
   int rc;
-  if ((rc = conv_same(c, one(mask, 1), B, H, W, w.ptr("conv1/kernel"), 3, 3, 2, 32, w.ptr("conv1/bias"), nullptr, nullptr,
+  if ((rc = conv_same(c, "conv1", one(mask, 1), B, H, W, w.ptr("conv1/kernel"), 3, 3, 2, 32, w.ptr("conv1/bias"), nullptr, nullptr,
                       CIC_ACT_LRELU02, r1))) return rc;                                                   // :511-512
-  if ((rc = conv_same(c, one(r1, 32), B, h2, w2, w.ptr("conv2/kernel"), 3, 3, 2, 64, w.ptr("conv2/bias"), nullptr, nullptr,
+  if ((rc = conv_same(c, "conv2", one(r1, 32), B, h2, w2, w.ptr("conv2/kernel"), 3, 3, 2, 64, w.ptr("conv2/bias"), nullptr, nullptr,
                       CIC_ACT_LRELU02, r2))) return rc;                                                   // :513-514
   if (!c.dry) {
     if ((rc = launch_global_avg_pool(r2, feat, B, h4 * w4, 64, 65, c.st))) return rc;                     // :515
@@ -491,8 +538,8 @@ int rd_forward_f32(cic_plan* pl, Ctx& c, const float* mask, const float* bpp, fl
     CIC_COUNT_LAUNCH();
     CIC_CHECK_LAUNCH("rd_set_t_kernel");
   }
-  if ((rc = dense(c, feat, w.ptr("dense1/kernel"), w.ptr("dense1/bias"), nullptr, nullptr, d1, B, 65, 128, CIC_ACT_LRELU02))) return rc;  // :521-522
-  if ((rc = dense(c, d1, w.ptr("dense2/kernel"), w.ptr("dense2/bias"), nullptr, nullptr, base, B, 128, 3, CIC_ACT_NONE))) return rc;      // :525
+  if ((rc = dense(c, "dense1", feat, w.ptr("dense1/kernel"), w.ptr("dense1/bias"), nullptr, nullptr, d1, B, 65, 128, CIC_ACT_LRELU02))) return rc;  // :521-522
+  if ((rc = dense(c, "dense2", d1, w.ptr("dense2/kernel"), w.ptr("dense2/bias"), nullptr, nullptr, base, B, 128, 3, CIC_ACT_NONE))) return rc;      // :525
   if (!c.dry) {
     rd_finalize_kernel<<<(B + 127) / 128, 128, 0, c.st>>>(base, bpp, rd_params, B);                        // :529-541
     CIC_COUNT_LAUNCH();
@@ -544,27 +591,34 @@ int adaptive_forward_f32(cic_plan* pl, Ctx& c, const cic_adaptive_io* io, int n_
   float* lx2 = c.arena.f32(tpx / 16 * 128);
   float* lx3 = c.arena.f32(tpx / 64 * 256);
   size_t mk = c.arena.mark();
+  if (c.prof) c.prof->prefix = "hq_enc/";
   if ((rc = encoder_forward_f32(pl->hq_enc.get(), c, img_t, hq_lat, hx1, hx2, hx3, nt))) return rc;
   c.arena.release(mk);
+  if (c.prof) c.prof->prefix = "lq_enc/";
   if ((rc = encoder_forward_f32(pl->lq_enc.get(), c, img_t, lq_lat, lx1, lx2, lx3, nt))) return rc;
   c.arena.release(mk);
   // 3. latent saliency (:619-620)
   float* sal_hq = c.arena.f32(nt);
   float* sal_lq = c.arena.f32(nt);
   mk = c.arena.mark();
+  if (c.prof) c.prof->prefix = "sal_hq/";
   if ((rc = saliency_forward_f32(pl->sal_hq.get(), c, hq_lat, sal_hq, nt))) return rc;
   c.arena.release(mk);
+  if (c.prof) c.prof->prefix = "sal_lq/";
   if ((rc = saliency_forward_f32(pl->sal_lq.get(), c, lq_lat, sal_lq, nt))) return rc;
   c.arena.release(mk);
   // 4. rate-distortion parameters (:624) - an output only; they do not drive the quantiser or blend
   if (io->d_rd_params || c.dry) {
+    if (c.prof) c.prof->prefix = "rd/";
     if ((rc = rd_forward_f32(pl->rd.get(), c, mask_t, bpp_t, io->d_rd_params, nt))) return rc;
     c.arena.release(mk);
   }
   // 5. quantise (:661-666)
   float* hq_q = io->d_hq_latent_q ? io->d_hq_latent_q : c.arena.f32((size_t)nt * 2 * base);
   float* lq_q = io->d_lq_latent_q ? io->d_lq_latent_q : c.arena.f32((size_t)nt * base);
+  if (c.prof) c.prof->prefix = "";
   if (!c.dry) {
+    Scope sc(c, "quantize", 0, 12.0 * nt * 3 * base);
     if ((rc = cic_quantize_latent(hq_lat, sal_hq, qs_t, hq_q, io->d_hq_symbols, nullptr, io->d_hq_scale, nt, 2 * base, c.st))) return rc;
     if ((rc = cic_quantize_latent(lq_lat, sal_lq, qs_t, lq_q, io->d_lq_symbols, nullptr, io->d_lq_scale, nt, base, c.st))) return rc;
   }
@@ -572,8 +626,10 @@ int adaptive_forward_f32(cic_plan* pl, Ctx& c, const cic_adaptive_io* io, int n_
   float* hq_out_t = (!tiled && io->d_hq_out) ? io->d_hq_out : c.arena.f32(tpx * 3);
   float* lq_out_t = (!tiled && io->d_lq_out) ? io->d_lq_out : c.arena.f32(tpx * 3);
   mk = c.arena.mark();
+  if (c.prof) c.prof->prefix = "hq_gen/";
   if ((rc = generator_forward_f32(pl->hq_gen.get(), c, hq_q, hx1, hx2, hx3, hq_out_t, nt))) return rc;
   c.arena.release(mk);
+  if (c.prof) c.prof->prefix = "lq_gen/";
   if ((rc = generator_forward_f32(pl->lq_gen.get(), c, lq_q, lx1, lx2, lx3, lq_out_t, nt))) return rc;
   c.arena.release(mk);
   // 7. dynamic threshold + blend on whole images (:651-657, :682-684)
@@ -589,7 +645,9 @@ int adaptive_forward_f32(cic_plan* pl, Ctx& c, const cic_adaptive_io* io, int n_
     hq_img = hi;
     lq_img = li;
   }
+  if (c.prof) c.prof->prefix = "";
   if (!c.dry) {
+    Scope sc(c, "roi_blend", 0, 44.0 * n_img * img_h * img_w);
     float* blended = io->d_blended;
     if ((rc = cic_roi_mask_blend(blended ? hq_img : nullptr, blended ? lq_img : nullptr, io->d_mask, io->d_bpp, blended,
                                  io->d_dt, io->d_hq_ratio_sum, n_img, img_h * img_w, 3, c.st))) return rc;
@@ -665,6 +723,24 @@ extern "C" void cic_plan_destroy(cic_plan* plan) { delete plan; }
 
 extern "C" int cic_plan_last_launch_count(const cic_plan* plan) { return plan ? (int)plan->last_launches : 0; }
 
+extern "C" int cic_plan_set_profiling(cic_plan* plan, int on) {
+  CIC_REQUIRE(plan, "cic_plan_set_profiling: null plan");
+  plan->prof.on = on != 0;
+  if (!on) plan->prof.reset();
+  return CIC_OK;
+}
+
+extern "C" size_t cic_plan_get_profile(cic_plan* plan, char* buf, size_t cap) {
+  if (!plan) return 0;
+  const std::string rep = plan->prof.report();
+  if (buf && cap > 0) {
+    const size_t n = rep.size() < cap - 1 ? rep.size() : cap - 1;
+    memcpy(buf, rep.data(), n);
+    buf[n] = 0;
+  }
+  return rep.size() + 1;
+}
+
 static int dispatch(cic_plan* pl, Ctx& c, int batch, int h, int w, const void* a0, const void* a1, const void* a2,
                     const void* a3, void* o0, void* o1, void* o2, void* o3, void* o4) {
   const bool tc = pl->opts.precision == CIC_PREC_TC;
@@ -717,6 +793,8 @@ static int run(cic_plan* pl, int batch, int h, int w, void* ws, size_t ws_bytes,
   c.arena.base = (char*)ws;
   c.arena.cap = ws_bytes;
   c.st = (cudaStream_t)stream;
+  c.prof = &pl->prof;
+  if (pl->prof.on) { pl->prof.reset(); pl->prof.prefix = ""; }
   const long long before = g_launch_count;
   int rc = dispatch(pl, c, batch, h, w, a0, a1, a2, a3, o0, o1, o2, o3, nullptr);
   pl->last_launches = g_launch_count - before;
@@ -730,7 +808,7 @@ static int run(cic_plan* pl, int batch, int h, int w, void* ws, size_t ws_bytes,
 extern "C" int cic_autoencoder_forward(cic_plan* plan, const float* d_x, float* d_y, uint8_t* d_y_u8, int batch, int h,
                                        int w, void* d_workspace, size_t workspace_bytes, void* stream) {
   CIC_REQUIRE(plan && plan->kind == CIC_PLAN_AUTOENCODER, "cic_autoencoder_forward: not an autoencoder plan");
-  CIC_REQUIRE(d_x && d_y, "cic_autoencoder_forward: null pointer");
+  CIC_REQUIRE(batch == 0 || (d_x && d_y), "cic_autoencoder_forward: null pointer");
   CIC_REQUIRE(h > 0 && w > 0 && h % 4 == 0 && w % 4 == 0, "cic_autoencoder_forward: H and W must be multiples of 4, got %dx%d", h, w);
   return run(plan, batch, h, w, d_workspace, workspace_bytes, stream, d_x, nullptr, nullptr, nullptr, d_y, d_y_u8, nullptr, nullptr);
 }
@@ -738,7 +816,7 @@ extern "C" int cic_autoencoder_forward(cic_plan* plan, const float* d_x, float* 
 extern "C" int cic_encoder_forward(cic_plan* plan, const float* d_img, float* d_latent, float* d_x1, float* d_x2,
                                    float* d_x3, int batch, void* d_workspace, size_t workspace_bytes, void* stream) {
   CIC_REQUIRE(plan && plan->kind == CIC_PLAN_ENCODER, "cic_encoder_forward: not an encoder plan");
-  CIC_REQUIRE(d_img && d_latent, "cic_encoder_forward: null pointer");
+  CIC_REQUIRE(batch == 0 || (d_img && d_latent), "cic_encoder_forward: null pointer");
   return run(plan, batch, plan->opts.img_h, plan->opts.img_w, d_workspace, workspace_bytes, stream, d_img, nullptr, nullptr,
              nullptr, d_latent, d_x1, d_x2, d_x3);
 }
@@ -747,7 +825,7 @@ extern "C" int cic_generator_forward(cic_plan* plan, const float* d_latent, cons
                                      const float* d_skip3, float* d_out, int batch, void* d_workspace,
                                      size_t workspace_bytes, void* stream) {
   CIC_REQUIRE(plan && plan->kind == CIC_PLAN_GENERATOR, "cic_generator_forward: not a generator plan");
-  CIC_REQUIRE(d_latent && d_skip1 && d_skip2 && d_skip3 && d_out, "cic_generator_forward: null pointer");
+  CIC_REQUIRE(batch == 0 || (d_latent && d_skip1 && d_skip2 && d_skip3 && d_out), "cic_generator_forward: null pointer");
   return run(plan, batch, plan->opts.img_h, plan->opts.img_w, d_workspace, workspace_bytes, stream, d_latent, d_skip1, d_skip2,
              d_skip3, d_out, nullptr, nullptr, nullptr);
 }
@@ -755,7 +833,7 @@ extern "C" int cic_generator_forward(cic_plan* plan, const float* d_latent, cons
 extern "C" int cic_saliency_forward(cic_plan* plan, const float* d_latent, float* d_score, int batch, void* d_workspace,
                                     size_t workspace_bytes, void* stream) {
   CIC_REQUIRE(plan && plan->kind == CIC_PLAN_SALIENCY, "cic_saliency_forward: not a saliency plan");
-  CIC_REQUIRE(d_latent && d_score, "cic_saliency_forward: null pointer");
+  CIC_REQUIRE(batch == 0 || (d_latent && d_score), "cic_saliency_forward: null pointer");
   return run(plan, batch, 0, 0, d_workspace, workspace_bytes, stream, d_latent, nullptr, nullptr, nullptr, d_score, nullptr,
              nullptr, nullptr);
 }
@@ -763,7 +841,7 @@ extern "C" int cic_saliency_forward(cic_plan* plan, const float* d_latent, float
 extern "C" int cic_rd_forward(cic_plan* plan, const float* d_mask, const float* d_bpp, float* d_rd_params, int batch,
                               void* d_workspace, size_t workspace_bytes, void* stream) {
   CIC_REQUIRE(plan && plan->kind == CIC_PLAN_RD, "cic_rd_forward: not an rd plan");
-  CIC_REQUIRE(d_mask && d_bpp && d_rd_params, "cic_rd_forward: null pointer");
+  CIC_REQUIRE(batch == 0 || (d_mask && d_bpp && d_rd_params), "cic_rd_forward: null pointer");
   return run(plan, batch, plan->opts.img_h, plan->opts.img_w, d_workspace, workspace_bytes, stream, d_mask, d_bpp, nullptr,
              nullptr, d_rd_params, nullptr, nullptr, nullptr);
 }
@@ -771,7 +849,7 @@ extern "C" int cic_rd_forward(cic_plan* plan, const float* d_mask, const float* 
 extern "C" int cic_adaptive_forward(cic_plan* plan, const cic_adaptive_io* io, int n_img, int img_h, int img_w,
                                     void* d_workspace, size_t workspace_bytes, void* stream) {
   CIC_REQUIRE(plan && plan->kind == CIC_PLAN_ADAPTIVE, "cic_adaptive_forward: not an adaptive plan");
-  CIC_REQUIRE(io && io->d_img && io->d_mask && io->d_bpp, "cic_adaptive_forward: null input");
+  CIC_REQUIRE(io && (n_img == 0 || (io->d_img && io->d_mask && io->d_bpp)), "cic_adaptive_forward: null input");
   const int T = plan->opts.img_h;
   CIC_REQUIRE(plan->opts.img_h == plan->opts.img_w, "cic_adaptive_forward: square model tiles only");
   CIC_REQUIRE(img_h > 0 && img_w > 0 && img_h % T == 0 && img_w % T == 0,
@@ -813,5 +891,5 @@ extern "C" int cic_self_attention_f32(const float* d_x, const float* d_wq, const
   if (d_bq) CIC_CHECK_CUDA(cudaMemcpyAsync(bqkv, d_bq, dq * sizeof(float), cudaMemcpyDeviceToDevice, st));
   if (d_bk) CIC_CHECK_CUDA(cudaMemcpyAsync(bqkv + dq, d_bk, dq * sizeof(float), cudaMemcpyDeviceToDevice, st));
   if (d_bv) CIC_CHECK_CUDA(cudaMemcpyAsync(bqkv + 2 * dq, d_bv, channels * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  return attention_f32(c, d_x, wqkv, bqkv, nullptr, gamma, false, d_y, batch, tokens, channels);
+  return attention_f32(c, "attention", d_x, wqkv, bqkv, nullptr, gamma, false, d_y, batch, tokens, channels);
 }

@@ -62,6 +62,20 @@ class Plan:
     def last_launch_count(self) -> int:
         return int(_lib.lib.cic_plan_last_launch_count(self.handle))
 
+    def set_profiling(self, on: bool) -> None:
+        _lib.check(_lib.lib.cic_plan_set_profiling(self.handle, int(on)))
+
+    def profile(self):
+        """[(layer, ms, flops, bytes)] of the last forward call (needs set_profiling(True) before it)."""
+        n = int(_lib.lib.cic_plan_get_profile(self.handle, None, 0))
+        buf = C.create_string_buffer(n + 16)
+        _lib.lib.cic_plan_get_profile(self.handle, buf, n + 16)
+        rows = []
+        for line in buf.value.decode().splitlines():
+            name, ms, fl, by = line.rsplit(",", 3)
+            rows.append((name, float(ms), float(fl), float(by)))
+        return rows
+
     def __del__(self):
         h = getattr(self, "handle", None)
         if h:
@@ -115,9 +129,26 @@ class Model:
         xs = [to_device_f32(x) for x in runtime.as_list(inputs)]
         return self.forward_device(xs)
 
-    def predict(self, x, verbose=0, batch_size=None):
+    def predict(self, x, verbose=0, batch_size=None, reuse_output_buffers=False):
+        """Keras-style predict: numpy (or torch, ideally pinned) in, numpy out.
+
+        reuse_output_buffers=True returns views of per-model pinned staging buffers that the next
+        predict() overwrites - the high-throughput mode (async D2H into pinned memory, one sync)."""
         outs = self._run(x)
-        host = [o.cpu().numpy() for o in outs]
+        if not reuse_output_buffers:
+            host = [o.cpu().numpy() for o in outs]
+        else:
+            stage = self.__dict__.setdefault("_stage", {})
+            host_t = []
+            for i, o in enumerate(outs):
+                key = (i, tuple(o.shape), o.dtype)
+                buf = stage.get(key)
+                if buf is None:
+                    buf = stage[key] = torch.empty(o.shape, dtype=o.dtype, pin_memory=True)
+                buf.copy_(o, non_blocking=True)
+                host_t.append(buf)
+            torch.cuda.current_stream().synchronize()
+            host = [b.numpy() for b in host_t]
         return host if self._multi_output else host[0]
 
     def __call__(self, inputs, training=False):
@@ -386,6 +417,7 @@ class AdaptiveCompressionModel(Model):
         ws = plan.workspace(n, h, w)
         _lib.check(_lib.lib.cic_adaptive_forward(plan.handle, C.byref(io), n, h, w, ptr(ws), ws.numel(), runtime.stream_ptr()))
         self.last = out
+        self._last_inputs = [img, mask, bpp]
         if extras:
             return out
         return [out["blended"], out["hq_latent_q"], out["lq_latent_q"], out["rd_params"], out["dt"]]

@@ -95,6 +95,12 @@ size_t cic_plan_workspace_bytes(const cic_plan* plan, int batch, int h, int w);
 /* Number of this library's kernels the last forward call on this plan launched. */
 int cic_plan_last_launch_count(const cic_plan* plan);
 
+/* Per-layer device timing of forward calls on this plan (CUDA events on the launch stream around every
+ * layer).  cic_plan_get_profile synchronises and writes one "name,ms,flops,bytes" line per layer of the
+ * last forward call into buf (NUL-terminated, truncated to cap); returns the size needed. */
+int cic_plan_set_profiling(cic_plan* plan, int on);
+size_t cic_plan_get_profile(cic_plan* plan, char* buf, size_t cap);
+
 /* build_autoencoder(...).predict  (train_autoencoder.py:9-40, test_autoencoder.py:85-88).
  * d_x (B,H,W,3) in [0,1] -> d_y (B,H,W,3) in (0,1); optional d_y_u8 = (y*255).astype(uint8)
  * (truncation, test_autoencoder.py:88). */

@@ -62,6 +62,7 @@ def test_argument_validation_without_gpu(cic):
     lib = cic._lib.lib
     assert lib.cic_quantize_latent(None, None, None, None, None, None, None, 1, 8, None) == cic._lib.ERR_INVALID
     assert "null" in cic._lib.last_error()
+    assert lib.cic_quantize_latent(None, None, None, None, None, None, None, 0, 8, None) == cic._lib.OK   # empty batch
     assert lib.cic_hq_ratio_sweep(1, 1, 99, 1, 1, 16, None) == cic._lib.ERR_INVALID
     assert lib.cic_metrics_psnr_ssim_f32(1, 1, 1, 1, 4, 4, 3, 0.0, 1.0, 1.0, None) == cic._lib.ERR_INVALID
     assert "7x7" in cic._lib.last_error()

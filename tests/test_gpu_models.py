@@ -24,6 +24,8 @@ LATENT_TOL = {"fp32": 2e-4, "tc": 2e-3}
 
 @pytest.fixture(params=PRECISIONS)
 def precision(request, cic):
+    if request.param == "tc" and os.environ.get("CIC_SKIP_TC") == "1":
+        pytest.skip("CIC_SKIP_TC=1")
     old = cic.get_precision()
     cic.set_precision(request.param)
     yield request.param

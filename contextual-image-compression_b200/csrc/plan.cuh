@@ -96,13 +96,56 @@ struct Scope {  // RAII layer bracket
 int run_dense(const float* x, const float* kernel, const float* bias, const float* scale, const float* shift, float* y,
               int batch, int in_dim, int out_dim, int act, float* ws, size_t ws_floats, cudaStream_t st);
 void pack_deconv_phases(const float* k, int cout, int cin, std::vector<float>& out);
+int launch_expand_bpp(const float* bpp, float* bpp_t, float* qs_t, int n_tiles, int tiles_per_img, cudaStream_t st);
 
+// named raw device buffers (packed bf16 weights of the tensor-core path)
+class BufStore {
+ public:
+  ~BufStore() {
+    for (auto& kv : b_) cudaFree(kv.second);
+  }
+  void* alloc(const std::string& name, size_t bytes) {
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+    auto it = b_.find(name);
+    if (it != b_.end()) cudaFree(it->second);
+    b_[name] = p;
+    return p;
+  }
+  void* ptr(const std::string& name) const {
+    auto it = b_.find(name);
+    return it == b_.end() ? nullptr : it->second;
+  }
+
+ private:
+  std::map<std::string, void*> b_;
+};
+
+}  // namespace cic
+
+struct cic_plan;
+namespace cic {
+// walkers: CIC_PREC_FP32 (plans.cu) and CIC_PREC_TC (plans_tc.cu)
+int build_plan_tc(cic_plan* pl, const cic_tensor* tensors, int n, const std::string& prefix);
+int autoencoder_forward_f32(cic_plan* pl, Ctx& c, const float* x, float* y, uint8_t* y_u8, int B, int H, int W);
+int encoder_forward_f32(cic_plan* pl, Ctx& c, const float* img, float* latent, float* x1, float* x2, float* x3, int B);
+int generator_forward_f32(cic_plan* pl, Ctx& c, const float* latent, const float* s1, const float* s2, const float* s3,
+                          float* out, int B);
+int saliency_forward_f32(cic_plan* pl, Ctx& c, const float* latent, float* score, int B);
+int rd_forward_f32(cic_plan* pl, Ctx& c, const float* mask, const float* bpp, float* rd_params, int B);
+int adaptive_forward_f32(cic_plan* pl, Ctx& c, const cic_adaptive_io* io, int n_img, int img_h, int img_w);
+int autoencoder_forward_tc(cic_plan* pl, Ctx& c, const float* x, float* y, uint8_t* y_u8, int B, int H, int W);
+int encoder_forward_tc(cic_plan* pl, Ctx& c, const float* img, float* latent, float* x1, float* x2, float* x3, int B);
+int generator_forward_tc(cic_plan* pl, Ctx& c, const float* latent, const float* s1, const float* s2, const float* s3,
+                         float* out, int B);
+int adaptive_forward_tc(cic_plan* pl, Ctx& c, const cic_adaptive_io* io, int n_img, int img_h, int img_w);
 }  // namespace cic
 
 struct cic_plan {
   int kind = 0;
   cic_plan_opts opts{};
   cic::WeightStore w;
+  cic::BufStore tcw;
   long long last_launches = 0;
   cic::Profiler prof;
   // CIC_PLAN_ADAPTIVE owns its seven sub-models

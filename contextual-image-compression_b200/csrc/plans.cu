@@ -231,7 +231,6 @@ static int build_rd(cic_plan* pl, const HostTensors& hs) {
   return CIC_OK;
 }
 
-int build_plan_tc(cic_plan* pl, const cic_tensor* tensors, int n, const std::string& prefix);  // plans_tc.cu
 
 static int build_any(cic_plan* pl, const cic_tensor* tensors, int n, const std::string& prefix) {
   HostTensors hs{tensors, n, prefix};
@@ -548,11 +547,12 @@ int rd_forward_f32(cic_plan* pl, Ctx& c, const float* mask, const float* bpp, fl
   return CIC_OK;
 }
 
-int adaptive_forward_tc(cic_plan* pl, Ctx& c, const cic_adaptive_io* io, int n_img, int img_h, int img_w);  // plans_tc.cu
-int autoencoder_forward_tc(cic_plan* pl, Ctx& c, const float* x, float* y, uint8_t* y_u8, int B, int H, int W);
-int encoder_forward_tc(cic_plan* pl, Ctx& c, const float* img, float* latent, float* x1, float* x2, float* x3, int B);
-int generator_forward_tc(cic_plan* pl, Ctx& c, const float* latent, const float* s1, const float* s2, const float* s3,
-                         float* out, int B);
+int launch_expand_bpp(const float* bpp, float* bpp_t, float* qs_t, int n_tiles, int tiles_per_img, cudaStream_t st) {
+  expand_bpp_kernel<<<(n_tiles + 127) / 128, 128, 0, st>>>(bpp, bpp_t, qs_t, n_tiles, tiles_per_img);
+  CIC_COUNT_LAUNCH();
+  CIC_CHECK_LAUNCH("expand_bpp_kernel");
+  return CIC_OK;
+}
 
 int adaptive_forward_f32(cic_plan* pl, Ctx& c, const cic_adaptive_io* io, int n_img, int img_h, int img_w) {
   const int T = pl->opts.img_h, base = pl->opts.latent_dim;
@@ -576,11 +576,7 @@ int adaptive_forward_f32(cic_plan* pl, Ctx& c, const cic_adaptive_io* io, int n_
   }
   float* bpp_t = c.arena.f32(nt);
   float* qs_t = c.arena.f32(nt);
-  if (!c.dry) {
-    expand_bpp_kernel<<<(nt + 127) / 128, 128, 0, c.st>>>(io->d_bpp, bpp_t, qs_t, nt, tpi);               // :631-649
-    CIC_COUNT_LAUNCH();
-    CIC_CHECK_LAUNCH("expand_bpp_kernel");
-  }
+  if (!c.dry && (rc = launch_expand_bpp(io->d_bpp, bpp_t, qs_t, nt, tpi, c.st))) return rc;              // :631-649
   // 1-2. encoders (:604-617)
   float* hq_lat = io->d_hq_latent ? io->d_hq_latent : c.arena.f32((size_t)nt * 2 * base);
   float* lq_lat = io->d_lq_latent ? io->d_lq_latent : c.arena.f32((size_t)nt * base);

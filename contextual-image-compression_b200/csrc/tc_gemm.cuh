@@ -1,0 +1,200 @@
+// tcgen05 / TMEM / TMA implicit-GEMM for sm_100a: the CIC_PREC_TC arithmetic of the conv, transposed
+// conv, dense and attention matmuls.
+//
+//   D[128 x BN] (fp32, TMEM) += A[128 x 64] (bf16, smem, K-major, 128B swizzle) * B[BN x 64]^T (same)
+//
+// A is the im2col view of an NHWC bf16 activation tensor: one TMA box {64 channels, TW, TH, TB}
+// per (tap, 64-channel chunk) lands as 128 rows x 128 B, which *is* the canonical K-major SWIZZLE_128B
+// UMMA operand layout, and TMA's out-of-bounds zero fill implements TF 'same' padding.  Stride-2 convs
+// read through a 5-D view (x-parity folded into the channel dim, y-parity as its own dim) so no
+// traversal strides are needed; transposed 4x4/stride-2 convs run as four 2x2 phases selected by
+// blockIdx.z.  B is the layer's weight matrix pre-packed to bf16 [N][K] (K ordered tap-major).
+// In SPLIT mode A and B are (hi, lo) bf16 pairs and each K block issues three MMAs
+// (hi*hi + lo*hi + hi*lo): error-compensated bf16 that reproduces fp32 products to ~2^-17 relative.
+//
+// Warp roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer (one
+// lane), warps 2-5 = epilogue (tcgen05.ld -> bias / folded BN / activation -> global).  A ring of
+// kStages smem slots with full/empty mbarriers decouples TMA from the tensor pipe; tcgen05.commit
+// releases slots and signals the epilogue.
+#pragma once
+#include "common.cuh"
+
+#include <cuda.h>
+
+namespace cic {
+
+enum TcOutMode { TC_OUT_BF16 = 0, TC_OUT_F32 = 1, TC_OUT_PARTIAL = 2, TC_OUT_BF16_T = 3 };
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;
+constexpr int TC_MAX_TAPS = 16;
+
+struct TcTap {  // TMA coordinate deltas of one filter tap
+  int16_t dc;   // added to the channel coordinate (x-parity * ld for the stride-2 view)
+  int16_t dx, dy;
+  int16_t pz;   // y-parity coordinate of the stride-2 view
+};
+
+struct TcParams {
+  // geometry of the M tile: rows = (tb, th, tw)
+  int TW, TH, TB;
+  int tiles_x, tiles_y, tiles_b;
+  int Wo, Ho, batch;      // output positions per batch item and batch size (row validity)
+  int a5d;                // 1: A maps are the 5-D stride-2 view
+  int nsrc;               // channel-concatenated sources
+  int src_blocks[2];      // 64-channel blocks per tap from each source
+  int src_coff[2];        // channel offset inside each source's pixel record
+  int ntaps;
+  TcTap taps[4][TC_MAX_TAPS];  // [phase][tap]
+  int nphases;            // 4 for transposed conv
+  int splits;             // split-K factor (blockIdx.z = phase * splits + split)
+  int kblocks;            // total K blocks = ntaps * (src_blocks[0] + src_blocks[1])
+  int N, N_pad;           // real / padded output channels (B rows per phase = N_pad)
+  int b_batched;          // 1: B has one matrix per batch item (attention); tile never spans items
+  // epilogue
+  const float* bias;
+  const float* scale;
+  const float* shift;
+  float alpha;
+  int act;
+  int out_mode;
+  void* out_hi;           // bf16 (or fp32 for TC_OUT_F32 / TC_OUT_PARTIAL)
+  void* out_lo;           // optional bf16 low part
+  const __nv_bfloat16* res_hi;  // optional residual (same addressing as the bf16 output)
+  const __nv_bfloat16* res_lo;
+  int out_ld, out_coff;
+  int out_H, out_W;
+  int out_ys, out_xs;
+  int8_t out_y0[4], out_x0[4];  // per phase
+  int up2;                // 1: replicate every output pixel 2x2 (nearest up-sampling fused into the store)
+  long long m_total;      // rows of the partial buffer
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3,
+                                            int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::
+          "r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, bf16 x bf16 -> fp32, single CTA
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier when all previously issued MMAs of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory operand descriptor (sm_100 format): rows of 128 B, 8-row groups
+// 1024 B apart (SBO); LBO unused for a single 128 B atom along K.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);  // start address, bits [0,14)
+  d |= (uint64_t)(1024 >> 4) << 32;             // stride byte offset, bits [32,46)
+  d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                       // layout type SWIZZLE_128B
+  return d;
+}
+
+// instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = n
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+template <int BN, bool SPLIT>
+struct TcCfg {
+  static constexpr int kABytes = TC_BM * TC_BK * 2;         // 16 KB
+  static constexpr int kBBytes = BN * TC_BK * 2;
+  static constexpr int kStageBytes = (SPLIT ? 2 : 1) * (kABytes + kBBytes);
+  static constexpr int kBudget = SPLIT ? 196608 : (BN >= 256 ? 196608 : 98304);  // 1 or 2 CTAs per SM
+  static constexpr int kStages = (kBudget / kStageBytes) < 2 ? 2 : ((kBudget / kStageBytes) > 8 ? 8 : (kBudget / kStageBytes));
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kTmemCols = BN < 32 ? 32 : BN;
+};
+
+struct TcMaps {
+  CUtensorMap a[2][2];  // [source][hi, lo]
+  CUtensorMap b[2];     // [hi, lo]
+};
+
+int launch_tc_gemm(const TcMaps& maps, const TcParams& p, int block_n, bool split, cudaStream_t st);
+
+}  // namespace cic

@@ -1,0 +1,74 @@
+// Host-side description of a tcgen05 layer launch (activation views, packed weights, epilogue) and the
+// small conversion kernels around the tensor-core path.
+#pragma once
+#include "tc_gemm.cuh"
+
+namespace cic {
+
+typedef __nv_bfloat16 bf16;
+
+struct TcAct {      // NHWC bf16 activation view: channels [coff, coff + C) of pixel records of `ld` elements
+  const bf16* hi;
+  const bf16* lo;   // nullptr when the tensor has no low part
+  int C, ld, coff;
+};
+
+struct TcMat {      // B operand: [batches][rows][K] bf16, K contiguous
+  const bf16* hi;
+  const bf16* lo;
+  int K;                   // elements per row used by the GEMM
+  int rows;                // rows per batch (phases * N_pad for weights)
+  long long row_stride;    // elements
+  int batches;
+  long long batch_stride;  // elements
+};
+
+struct TcEpilogue {
+  const float* bias = nullptr;
+  const float* scale = nullptr;
+  const float* shift = nullptr;
+  float alpha = 1.f;
+  int act = CIC_ACT_NONE;
+  int out_mode = TC_OUT_BF16;
+  void* out_hi = nullptr;
+  void* out_lo = nullptr;
+  const bf16* res_hi = nullptr;
+  const bf16* res_lo = nullptr;
+  int out_ld = 0, out_coff = 0;
+  int up2 = 0;
+};
+
+enum TcKind { TC_CONV_S1 = 0, TC_CONV_S2 = 1, TC_DECONV_K4S2 = 2 };
+
+struct TcLayer {
+  int kind = TC_CONV_S1;
+  TcAct src[2];
+  int nsrc = 1;
+  int batch = 0, H = 0, W = 0;  // input size per batch item
+  int kh = 1, kw = 1, pad_t = 0, pad_l = 0;
+  TcMat w{};
+  int N = 0;          // output channels (rows of w per phase)
+  bool split = false;  // 3-term split-bf16 (needs src[].lo and w.lo)
+  int splits = 1;      // split-K; > 1 requires epi.out_mode == TC_OUT_PARTIAL
+  bool b_batched = false;
+  TcEpilogue epi;
+};
+
+int tc_encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box);
+int tc_run_layer(const TcLayer& L, cudaStream_t st);
+int tc_pick_block_n(int N, bool split);
+
+// fp32 [K][N] (row-major, Keras kernel / Dense layout) -> bf16 hi/lo [N_pad][K] (K contiguous), zero rows >= N
+int tc_pack_weight(const float* src, int K, int N, int N_pad, bf16* hi, bf16* lo, cudaStream_t st);
+// fp32 -> bf16 hi (+ lo)
+int tc_split_f32(const float* src, bf16* hi, bf16* lo, size_t n, cudaStream_t st);
+// bf16 hi (+ lo) -> fp32, with strided source records (ld, coff) -> dense C
+int tc_join_to_f32(const bf16* hi, const bf16* lo, float* dst, size_t pixels, int C, int ld, int coff, cudaStream_t st);
+// split-K partials [splits][M][N] -> epilogue -> fp32 [M][N] and/or bf16 hi/lo [M][N]
+int tc_splitk_reduce(const float* partial, int splits, long long M, int N, const float* bias, const float* scale,
+                     const float* shift, int act, float* out_f32, bf16* out_hi, bf16* out_lo, cudaStream_t st);
+// row softmax of fp32 logits -> bf16 hi/lo probabilities (tf.nn.softmax(axis=-1), GAN_functions.py:359)
+int tc_softmax_rows_split(const float* logits, bf16* p_hi, bf16* p_lo, long long rows, int cols, cudaStream_t st);
+
+}  // namespace cic

@@ -71,6 +71,10 @@ PROTOTYPES = {
     "cic_conv2d_transpose4x4s2_nhwc_f32": (_i, [_vp] * 6 + [_i] * 6 + [_vp]),
     "cic_dense_workspace_bytes": (_sz, [_i, _i, _i]),
     "cic_dense_f32": (_i, [_vp] * 4 + [_i] * 4 + [_vp, _sz, _vp]),
+    "cic_conv2d_tc_workspace_bytes": (_sz, [_i] * 10),
+    "cic_conv2d_nhwc_tc": (_i, [_vp] * 7 + [_i] * 12 + [_vp, _sz, _vp]),
+    "cic_dense_tc_workspace_bytes": (_sz, [_i, _i, _i]),
+    "cic_dense_tc": (_i, [_vp] * 4 + [_i] * 5 + [_vp, _sz, _vp]),
     "cic_attention_workspace_bytes": (_sz, [_i, _i, _i]),
     "cic_self_attention_f32": (_i, [_vp] * 7 + [_f, _vp, _i, _i, _i, _vp, _sz, _vp]),
     "cic_quantize_latent": (_i, [_vp] * 7 + [_i, _i, _vp]),

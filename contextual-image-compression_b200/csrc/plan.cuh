@@ -146,6 +146,7 @@ struct cic_plan {
   cic_plan_opts opts{};
   cic::WeightStore w;
   cic::BufStore tcw;
+  float attn_gamma = 0.f;  // SelfAttention.gamma, read once at plan creation (tensor-core path)
   long long last_launches = 0;
   cic::Profiler prof;
   // CIC_PLAN_ADAPTIVE owns its seven sub-models

@@ -1,4 +1,4 @@
-// tcgen05 implicit-GEMM kernel + host-side launch (tensor-map encoding, tiling, grid).
+// tcgen05 implicit-GEMM kernel + host-side launch (tensor-map encoding, grid).
 #include "tc_gemm.cuh"
 #include "tc_host.cuh"
 
@@ -9,11 +9,12 @@ namespace cic {
 // ------------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------------
-template <int BN, bool SPLIT>
-__global__ void __launch_bounds__(192, (TcCfg<BN, SPLIT>::kSmemBytes <= 112 * 1024) ? 2 : 1)
+template <int BN, int BK, bool SPLIT>
+__global__ void __launch_bounds__(192, TcCfg<BN, BK, SPLIT>::kMinCtas)
 tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams p) {
-  using Cfg = TcCfg<BN, SPLIT>;
+  using Cfg = TcCfg<BN, BK, SPLIT>;
   constexpr int kStages = Cfg::kStages;
+  constexpr int CH = Cfg::kChunk;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
@@ -62,7 +63,7 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     if (lane == 0) {
       const int cpt = p.src_blocks[0] + p.src_blocks[1];
       const uint32_t rows = (uint32_t)(p.TW * p.TH * p.TB);
-      const uint32_t tx_bytes = (SPLIT ? 2u : 1u) * (rows * 128u + (uint32_t)BN * 128u);
+      const uint32_t tx_bytes = (SPLIT ? 2u : 1u) * (rows + (uint32_t)BN) * (uint32_t)(2 * BK);
       for (int i = 0; i < nkb; ++i) {
         const int s = i % kStages;
         const uint32_t ph = (uint32_t)(i / kStages) & 1u;
@@ -73,7 +74,7 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         const int src = ch >= p.src_blocks[0] ? 1 : 0;
         const int cblk = src ? ch - p.src_blocks[0] : ch;
         const TcTap t = p.taps[phase][tap];
-        const int c = p.src_coff[src] + cblk * TC_BK + t.dc;
+        const int c = p.src_coff[src] + cblk * BK + t.dc;
         uint8_t* st = smem + s * Cfg::kStageBytes;
         uint8_t* a_hi = st;
         uint8_t* a_lo = st + Cfg::kABytes;
@@ -88,8 +89,8 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         }
         const int bn = phase * p.N_pad + n_tile * BN;
         const int bz = p.b_batched ? b0 : 0;
-        tma_load_3d(b_hi, &maps.b[0], &full_bar[s], kb * TC_BK, bn, bz);
-        if (SPLIT) tma_load_3d(b_lo, &maps.b[1], &full_bar[s], kb * TC_BK, bn, bz);
+        tma_load_3d(b_hi, &maps.b[0], &full_bar[s], kb * BK, bn, bz);
+        if (SPLIT) tma_load_3d(b_lo, &maps.b[1], &full_bar[s], kb * BK, bn, bz);
       }
     }
   } else if (warp == 1) {
@@ -105,15 +106,15 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         const uint32_t a_hi = st, a_lo = st + Cfg::kABytes;
         const uint32_t b_hi = st + (SPLIT ? 2 : 1) * Cfg::kABytes, b_lo = b_hi + Cfg::kBBytes;
 #pragma unroll
-        for (int k = 0; k < TC_BK / 16; ++k)
-          umma_bf16(tmem_base, umma_desc_sw128(a_hi + k * 32), umma_desc_sw128(b_hi + k * 32), idesc, (i | k) != 0);
+        for (int k = 0; k < BK / 16; ++k)
+          umma_bf16(tmem_base, umma_desc_kmajor<BK>(a_hi + k * 32), umma_desc_kmajor<BK>(b_hi + k * 32), idesc, (i | k) != 0);
         if (SPLIT) {
 #pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k)
-            umma_bf16(tmem_base, umma_desc_sw128(a_lo + k * 32), umma_desc_sw128(b_hi + k * 32), idesc, 1u);
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16(tmem_base, umma_desc_kmajor<BK>(a_lo + k * 32), umma_desc_kmajor<BK>(b_hi + k * 32), idesc, 1u);
 #pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k)
-            umma_bf16(tmem_base, umma_desc_sw128(a_hi + k * 32), umma_desc_sw128(b_lo + k * 32), idesc, 1u);
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16(tmem_base, umma_desc_kmajor<BK>(a_hi + k * 32), umma_desc_kmajor<BK>(b_lo + k * 32), idesc, 1u);
         }
         umma_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
       }
@@ -132,46 +133,62 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     const long long opix = ((long long)b * p.out_H + (oy * p.out_ys + p.out_y0[phase])) * p.out_W + (ox * p.out_xs + p.out_x0[phase]);
     const long long mrow = ((long long)b * p.Ho + oy) * p.Wo + ox;
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
+    for (int c = 0; c < BN / CH; ++c) {
       uint32_t v[32];
       __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the divergent stores of the previous chunk
-      tmem_ld32(taddr + (uint32_t)(c * 32), v);
+      if (CH == 32) tmem_ld32(taddr + (uint32_t)(c * CH), v);
+      else tmem_ld16(taddr + (uint32_t)(c * CH), v);
       tmem_ld_wait();
-      if (!valid) continue;
-      const int n0 = n_tile * BN + c * 32;
+      const int n0 = n_tile * BN + c * CH;
+      const int nv = min(CH, p.N - n0);  // valid channels of this chunk
+      if (!valid || nv <= 0) continue;
       if (p.out_mode == TC_OUT_PARTIAL) {
-        float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out_hi) + ((long long)split * p.m_total + mrow) * p.N + n0);
+        float* dst = reinterpret_cast<float*>(p.out_hi) + ((long long)split * p.m_total + mrow) * p.N + n0;
+        if (nv == CH && (p.N & 3) == 0) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
-                               __uint_as_float(v[4 * j + 3]));
+          for (int j = 0; j < CH / 4; ++j)
+            reinterpret_cast<float4*>(dst)[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                            __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < CH; ++j)
+            if (j < nv) dst[j] = __uint_as_float(v[j]);
+        }
         continue;
       }
-      float f[32];
+      float f[CH];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
+      for (int j = 0; j < CH; ++j) {
         float x = __fmul_rn(p.alpha, __uint_as_float(v[j]));
-        if (p.bias) x = __fadd_rn(x, __ldg(p.bias + n0 + j));
-        if (p.scale) x = __fadd_rn(__fmul_rn(x, __ldg(p.scale + n0 + j)), __ldg(p.shift + n0 + j));
+        if (j < nv) {
+          if (p.bias) x = __fadd_rn(x, __ldg(p.bias + n0 + j));
+          if (p.scale) x = __fadd_rn(__fmul_rn(x, __ldg(p.scale + n0 + j)), __ldg(p.shift + n0 + j));
+        }
         f[j] = act_apply(x, p.act);
       }
       if (p.out_mode == TC_OUT_F32) {
-        float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out_hi) + opix * p.out_ld + p.out_coff + n0);
+        float* dst = reinterpret_cast<float*>(p.out_hi) + opix * p.out_ld + p.out_coff + n0;
+        if (nv == CH && ((p.out_ld | p.out_coff) & 3) == 0) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-      } else if (p.out_mode == TC_OUT_BF16) {
+          for (int j = 0; j < CH / 4; ++j) reinterpret_cast<float4*>(dst)[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < CH; ++j)
+            if (j < nv) dst[j] = f[j];
+        }
+      } else if (p.out_mode == TC_OUT_BF16) {  // host guarantees N % CH == 0 and 16-byte aligned records
         const long long idx = opix * p.out_ld + p.out_coff + n0;
         if (p.res_hi) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
+          for (int j = 0; j < CH; ++j) {
             float rv = __bfloat162float(p.res_hi[idx + j]);
             if (p.res_lo) rv += __bfloat162float(p.res_lo[idx + j]);
             f[j] = __fadd_rn(f[j], rv);
           }
         }
-        uint32_t hi[16], lo[16];
+        uint32_t hi[CH / 2], lo[CH / 2];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
+        for (int j = 0; j < CH / 2; ++j) {
           const __nv_bfloat16 h0 = __float2bfloat16_rn(f[2 * j]), h1 = __float2bfloat16_rn(f[2 * j + 1]);
           hi[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
           const __nv_bfloat16 l0 = __float2bfloat16_rn(f[2 * j] - __bfloat162float(h0));
@@ -185,11 +202,11 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             if (p.up2) o = ((((long long)b * p.out_H + (oy * 2 + ry)) * p.out_W) + (ox * 2 + rx)) * p.out_ld + p.out_coff + n0;
             uint4* dh = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out_hi) + o);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+            for (int j = 0; j < CH / 8; ++j) dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
             if (p.out_lo) {
               uint4* dl = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out_lo) + o);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+              for (int j = 0; j < CH / 8; ++j) dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
             }
           }
       } else {  // TC_OUT_BF16_T: out[b][n][position] (V^T for the attention PV product)
@@ -198,7 +215,8 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(p.out_hi);
         __nv_bfloat16* ol = reinterpret_cast<__nv_bfloat16*>(p.out_lo);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
+        for (int j = 0; j < CH; ++j) {
+          if (j >= nv) break;
           const long long o = ((long long)b * p.N + n0 + j) * how + pos;
           const __nv_bfloat16 h = __float2bfloat16_rn(f[j]);
           oh[o] = h;
@@ -244,9 +262,10 @@ int tc_encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* 
   cuuint32_t bx[5], es[5];
   for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+  // the inner box is one swizzle atom: 64 bf16 -> 128-byte swizzle, 32 bf16 -> 64-byte swizzle
+  const CUtensorMapSwizzle sw = box[0] == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu %llu %llu %llu %llu] box [%u %u %u %u %u] base %p", (int)r,
               rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
@@ -258,45 +277,48 @@ int tc_encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* 
   return CIC_OK;
 }
 
-template <int BN, bool SPLIT>
+template <int BN, int BK, bool SPLIT>
 static int launch_one(const TcMaps& maps, const TcParams& p, dim3 grid, cudaStream_t st) {
-  using Cfg = TcCfg<BN, SPLIT>;
+  using Cfg = TcCfg<BN, BK, SPLIT>;
   static bool attr_set = false;
   if (!attr_set) {
-    CIC_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    CIC_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, BK, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  tc_gemm_kernel<BN, SPLIT><<<grid, 192, Cfg::kSmemBytes, st>>>(maps, p);
+  tc_gemm_kernel<BN, BK, SPLIT><<<grid, 192, Cfg::kSmemBytes, st>>>(maps, p);
   CIC_COUNT_LAUNCH();
   CIC_CHECK_LAUNCH("tc_gemm_kernel");
   return CIC_OK;
 }
 
-int launch_tc_gemm(const TcMaps& maps, const TcParams& p, int block_n, bool split, cudaStream_t st) {
-  CIC_REQUIRE(p.N % block_n == 0, "tc_gemm: N=%d is not a multiple of the N tile %d", p.N, block_n);
+template <int BK, bool SPLIT>
+static int launch_bn(const TcMaps& maps, const TcParams& p, int block_n, dim3 grid, cudaStream_t st) {
+  switch (block_n) {
+    case 16: return launch_one<16, BK, SPLIT>(maps, p, grid, st);
+    case 32: return launch_one<32, BK, SPLIT>(maps, p, grid, st);
+    case 64: return launch_one<64, BK, SPLIT>(maps, p, grid, st);
+    case 128: return launch_one<128, BK, SPLIT>(maps, p, grid, st);
+    case 256:
+      if (!SPLIT && BK == 64) return launch_one<256, 64, false>(maps, p, grid, st);
+      break;
+  }
+  set_error("tc_gemm: unsupported N tile %d (K block %d, split=%d)", block_n, BK, (int)SPLIT);
+  return CIC_ERR_INVALID;
+}
+
+int launch_tc_gemm(const TcMaps& maps, const TcParams& p, int block_n, int block_k, bool split, cudaStream_t st) {
+  CIC_REQUIRE(block_n > 0 && p.N_pad % block_n == 0 && p.N <= p.N_pad, "tc_gemm: padded N=%d is not a multiple of the N tile %d", p.N_pad, block_n);
   CIC_REQUIRE(p.kblocks >= p.splits && p.splits >= 1, "tc_gemm: bad split-K %d for %d K blocks", p.splits, p.kblocks);
   const int per = (p.kblocks + p.splits - 1) / p.splits;
   CIC_REQUIRE((p.splits - 1) * per < p.kblocks, "tc_gemm: split-K leaves an empty split");
   CIC_REQUIRE(p.TW * p.TH * p.TB <= TC_BM && p.TW >= 1, "tc_gemm: bad M tile");
   const long long mt = (long long)p.tiles_x * p.tiles_y * p.tiles_b;
   CIC_REQUIRE(mt > 0 && mt < 2147483647LL, "tc_gemm: bad tile count");
-  dim3 grid((unsigned)mt, p.N / block_n, p.nphases * p.splits);
+  dim3 grid((unsigned)mt, (p.N + block_n - 1) / block_n, p.nphases * p.splits);
   CIC_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "tc_gemm: grid too large");
-  if (split) {
-    switch (block_n) {
-      case 32: return launch_one<32, true>(maps, p, grid, st);
-      case 64: return launch_one<64, true>(maps, p, grid, st);
-      case 128: return launch_one<128, true>(maps, p, grid, st);
-    }
-  } else {
-    switch (block_n) {
-      case 32: return launch_one<32, false>(maps, p, grid, st);
-      case 64: return launch_one<64, false>(maps, p, grid, st);
-      case 128: return launch_one<128, false>(maps, p, grid, st);
-      case 256: return launch_one<256, false>(maps, p, grid, st);
-    }
-  }
-  set_error("tc_gemm: unsupported N tile %d (split=%d)", block_n, (int)split);
+  if (block_k == 64) return split ? launch_bn<64, true>(maps, p, block_n, grid, st) : launch_bn<64, false>(maps, p, block_n, grid, st);
+  if (block_k == 32) return split ? launch_bn<32, true>(maps, p, block_n, grid, st) : launch_bn<32, false>(maps, p, block_n, grid, st);
+  set_error("tc_gemm: unsupported K block %d", block_k);
   return CIC_ERR_INVALID;
 }
 

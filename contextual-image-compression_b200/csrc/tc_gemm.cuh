@@ -1,13 +1,14 @@
 // tcgen05 / TMEM / TMA implicit-GEMM for sm_100a: the CIC_PREC_TC arithmetic of the conv, transposed
 // conv, dense and attention matmuls.
 //
-//   D[128 x BN] (fp32, TMEM) += A[128 x 64] (bf16, smem, K-major, 128B swizzle) * B[BN x 64]^T (same)
+//   D[128 x BN] (fp32, TMEM) += A[128 x BK] (bf16, smem, K-major, swizzled) * B[BN x BK]^T (same)
 //
-// A is the im2col view of an NHWC bf16 activation tensor: one TMA box {64 channels, TW, TH, TB}
-// per (tap, 64-channel chunk) lands as 128 rows x 128 B, which *is* the canonical K-major SWIZZLE_128B
-// UMMA operand layout, and TMA's out-of-bounds zero fill implements TF 'same' padding.  Stride-2 convs
-// read through a 5-D view (x-parity folded into the channel dim, y-parity as its own dim) so no
-// traversal strides are needed; transposed 4x4/stride-2 convs run as four 2x2 phases selected by
+// A is the im2col view of an NHWC bf16 activation tensor: one TMA box {BK channels, TW, TH, TB}
+// per (tap, BK-channel chunk) lands as 128 rows x (2*BK) bytes, which *is* the canonical K-major
+// swizzled UMMA operand layout (SWIZZLE_128B for BK = 64, SWIZZLE_64B for BK = 32, the latter for
+// the 32-channel layers), and TMA's out-of-bounds zero fill implements TF 'same' padding.  Stride-2
+// convs read through a 5-D view (x-parity folded into the channel dim, y-parity as its own dim) so
+// no traversal strides are needed; transposed 4x4/stride-2 convs run as four 2x2 phases selected by
 // blockIdx.z.  B is the layer's weight matrix pre-packed to bf16 [N][K] (K ordered tap-major).
 // In SPLIT mode A and B are (hi, lo) bf16 pairs and each K block issues three MMAs
 // (hi*hi + lo*hi + hi*lo): error-compensated bf16 that reproduces fp32 products to ~2^-17 relative.
@@ -15,7 +16,8 @@
 // Warp roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer (one
 // lane), warps 2-5 = epilogue (tcgen05.ld -> bias / folded BN / activation -> global).  A ring of
 // kStages smem slots with full/empty mbarriers decouples TMA from the tensor pipe; tcgen05.commit
-// releases slots and signals the epilogue.
+// releases slots and signals the epilogue.  Two CTAs are co-resident per SM where shared memory allows,
+// so one CTA's epilogue overlaps the other's main loop.
 #pragma once
 #include "common.cuh"
 
@@ -26,7 +28,6 @@ namespace cic {
 enum TcOutMode { TC_OUT_BF16 = 0, TC_OUT_F32 = 1, TC_OUT_PARTIAL = 2, TC_OUT_BF16_T = 3 };
 
 constexpr int TC_BM = 128;
-constexpr int TC_BK = 64;
 constexpr int TC_MAX_TAPS = 16;
 
 struct TcTap {  // TMA coordinate deltas of one filter tap
@@ -42,7 +43,7 @@ struct TcParams {
   int Wo, Ho, batch;      // output positions per batch item and batch size (row validity)
   int a5d;                // 1: A maps are the 5-D stride-2 view
   int nsrc;               // channel-concatenated sources
-  int src_blocks[2];      // 64-channel blocks per tap from each source
+  int src_blocks[2];      // BK-channel blocks per tap from each source
   int src_coff[2];        // channel offset inside each source's pixel record
   int ntaps;
   TcTap taps[4][TC_MAX_TAPS];  // [phase][tap]
@@ -82,10 +83,12 @@ __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarr
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// Bounded wait: a pipeline bug traps (CUDA error on the host) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t ok;
-  do {
+  long long t0 = 0;
+  for (uint32_t it = 0;; ++it) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -93,7 +96,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(ok)
         : "r"(addr), "r"(parity)
         : "memory");
-  } while (!ok);
+    if (ok) return;
+    if (it == 1024) t0 = clock64();
+    if (it > 1024 && (it & 1023) == 0 && clock64() - t0 > 4000000000LL) __trap();  // ~2 s
+  }
 }
 
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
@@ -149,14 +155,18 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// K-major, SWIZZLE_128B shared-memory operand descriptor (sm_100 format): rows of 128 B, 8-row groups
-// 1024 B apart (SBO); LBO unused for a single 128 B atom along K.
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+// K-major swizzled shared-memory operand descriptor (sm_100 format).  One swizzle atom along K
+// (BK bf16 = 2*BK bytes per row), 8-row groups 8 * 2*BK bytes apart (SBO); LBO unused.
+//   BK = 64: SWIZZLE_128B (layout type 2), SBO 1024;  BK = 32: SWIZZLE_64B (layout type 4), SBO 512.
+template <int BK>
+__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr) {
+  constexpr uint64_t sbo = 8 * 2 * BK;
+  constexpr uint64_t layout = BK == 64 ? 2 : 4;
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);  // start address, bits [0,14)
-  d |= (uint64_t)(1024 >> 4) << 32;             // stride byte offset, bits [32,46)
+  d |= (uint64_t)(sbo >> 4) << 32;              // stride byte offset, bits [32,46)
   d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                       // layout type SWIZZLE_128B
+  d |= layout << 61;                            // swizzle mode
   return d;
 }
 
@@ -177,17 +187,28 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-template <int BN, bool SPLIT>
+template <int BN, int BK, bool SPLIT>
 struct TcCfg {
-  static constexpr int kABytes = TC_BM * TC_BK * 2;         // 16 KB
-  static constexpr int kBBytes = BN * TC_BK * 2;
+  static constexpr int kABytes = TC_BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = (SPLIT ? 2 : 1) * (kABytes + kBBytes);
-  static constexpr int kBudget = SPLIT ? 196608 : (BN >= 256 ? 196608 : 98304);  // 1 or 2 CTAs per SM
+  static constexpr int kBudget = (SPLIT && BN >= 128) || BN >= 256 ? 196608 : 98304;  // 1 or 2 CTAs per SM
   static constexpr int kStages = (kBudget / kStageBytes) < 2 ? 2 : ((kBudget / kStageBytes) > 8 ? 8 : (kBudget / kStageBytes));
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr int kTmemCols = BN < 32 ? 32 : BN;
+  static constexpr int kChunk = BN < 32 ? 16 : 32;  // accumulator columns per tcgen05.ld
+  static constexpr int kMinCtas = kSmemBytes <= 112 * 1024 ? 2 : 1;
 };
 
 struct TcMaps {
@@ -195,6 +216,6 @@ struct TcMaps {
   CUtensorMap b[2];     // [hi, lo]
 };
 
-int launch_tc_gemm(const TcMaps& maps, const TcParams& p, int block_n, bool split, cudaStream_t st);
+int launch_tc_gemm(const TcMaps& maps, const TcParams& p, int block_n, int block_k, bool split, cudaStream_t st);
 
 }  // namespace cic

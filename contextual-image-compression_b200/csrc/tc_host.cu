@@ -29,11 +29,17 @@ static void pick_tile(int Wo, int Ho, int batch, bool one_item, int& TW, int& TH
   }
 }
 
-int tc_pick_block_n(int N, bool split) {
-  const int cap = split ? 128 : 256;
-  for (int bn = cap; bn >= 32; bn /= 2)
-    if (N % bn == 0) return bn;
+int tc_pick_block_n(int n_pad, bool split, int bk) {
+  const int cap = (split || bk != 64) ? 128 : 256;
+  for (int bn = cap; bn >= 16; bn /= 2)
+    if (n_pad % bn == 0) return bn;
   return 0;
+}
+
+int tc_pick_block_k(const TcLayer& L) {
+  for (int s = 0; s < L.nsrc; ++s)
+    if (L.src[s].C % 64 != 0) return 32;
+  return 64;
 }
 
 int tc_run_layer(const TcLayer& L, cudaStream_t st) {
@@ -44,9 +50,11 @@ int tc_run_layer(const TcLayer& L, cudaStream_t st) {
   const bool s2 = L.kind == TC_CONV_S2;
   const bool dc = L.kind == TC_DECONV_K4S2;
   CIC_REQUIRE(L.nsrc == 1 || L.nsrc == 2, "tc layer: nsrc must be 1 or 2");
+  const int BK = tc_pick_block_k(L);
   for (int s = 0; s < L.nsrc; ++s) {
-    CIC_REQUIRE(L.src[s].C % TC_BK == 0 && L.src[s].ld % 8 == 0 && L.src[s].coff % 8 == 0,
-                "tc layer: source %d needs C %% 64 == 0 (C=%d, ld=%d, coff=%d)", s, L.src[s].C, L.src[s].ld, L.src[s].coff);
+    CIC_REQUIRE(L.src[s].C % BK == 0 && L.src[s].ld % 8 == 0 && L.src[s].coff % 8 == 0,
+                "tc layer: source %d needs C %% 32 == 0 and 16-byte aligned pixel records (C=%d, ld=%d, coff=%d)", s, L.src[s].C,
+                L.src[s].ld, L.src[s].coff);
     CIC_REQUIRE(!L.split || L.src[s].lo, "tc layer: split mode needs the low part of source %d", s);
   }
   CIC_REQUIRE(!L.split || L.w.lo, "tc layer: split mode needs the low part of the weights");
@@ -62,7 +70,7 @@ int tc_run_layer(const TcLayer& L, cudaStream_t st) {
   // activation tensor maps
   for (int s = 0; s < L.nsrc; ++s) {
     const TcAct& a = L.src[s];
-    p.src_blocks[s] = a.C / TC_BK;
+    p.src_blocks[s] = a.C / BK;
     p.src_coff[s] = a.coff;
     for (int part = 0; part < (L.split ? 2 : 1); ++part) {
       const bf16* base = part ? a.lo : a.hi;
@@ -70,14 +78,14 @@ int tc_run_layer(const TcLayer& L, cudaStream_t st) {
       if (!s2) {
         const uint64_t dims[4] = {(uint64_t)a.ld, (uint64_t)L.W, (uint64_t)L.H, (uint64_t)L.batch};
         const uint64_t str[3] = {(uint64_t)a.ld * 2, (uint64_t)L.W * a.ld * 2, (uint64_t)L.H * L.W * a.ld * 2};
-        const uint32_t box[4] = {TC_BK, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TB};
+        const uint32_t box[4] = {(uint32_t)BK, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TB};
         rc = tc_encode_map(&maps.a[s][part], base, 4, dims, str, box);
       } else {
         // (x-parity, channel) merged | x/2 | y-parity | y/2 | batch
         const uint64_t dims[5] = {(uint64_t)2 * a.ld, (uint64_t)L.W / 2, 2, (uint64_t)L.H / 2, (uint64_t)L.batch};
         const uint64_t str[4] = {(uint64_t)2 * a.ld * 2, (uint64_t)L.W * a.ld * 2, (uint64_t)2 * L.W * a.ld * 2,
                                  (uint64_t)L.H * L.W * a.ld * 2};
-        const uint32_t box[5] = {TC_BK, (uint32_t)p.TW, 1, (uint32_t)p.TH, (uint32_t)p.TB};
+        const uint32_t box[5] = {(uint32_t)BK, (uint32_t)p.TW, 1, (uint32_t)p.TH, (uint32_t)p.TB};
         rc = tc_encode_map(&maps.a[s][part], base, 5, dims, str, box);
       }
       if (rc) return rc;
@@ -120,19 +128,20 @@ int tc_run_layer(const TcLayer& L, cudaStream_t st) {
   }
   const int cpt = p.src_blocks[0] + (L.nsrc > 1 ? p.src_blocks[1] : 0);
   p.kblocks = p.ntaps * cpt;
-  CIC_REQUIRE((long long)p.kblocks * TC_BK == L.w.K, "tc layer: weight K=%d does not match taps x channels = %d", L.w.K,
-              p.kblocks * TC_BK);
+  CIC_REQUIRE((long long)p.kblocks * BK == L.w.K, "tc layer: weight K=%d does not match taps x channels = %d", L.w.K,
+              p.kblocks * BK);
   p.splits = L.splits;
   p.N = L.N;
   p.N_pad = dc ? L.w.rows / 4 : L.w.rows;
   p.b_batched = L.b_batched ? 1 : 0;
+  const int bn = tc_pick_block_n(p.N_pad, L.split, BK);
+  CIC_REQUIRE(bn > 0 && L.N <= p.N_pad, "tc layer: N=%d (padded %d) has no supported tile", L.N, p.N_pad);
+  CIC_REQUIRE(L.w.row_stride % 8 == 0 && L.w.batch_stride % 8 == 0, "tc layer: B rows must be 16-byte aligned");
   // weight / B map
   for (int part = 0; part < (L.split ? 2 : 1); ++part) {
     const uint64_t dims[3] = {(uint64_t)L.w.K, (uint64_t)L.w.rows, (uint64_t)L.w.batches};
     const uint64_t str[2] = {(uint64_t)L.w.row_stride * 2, (uint64_t)L.w.batch_stride * 2};
-    const int bn = tc_pick_block_n(L.N, L.split);
-    CIC_REQUIRE(bn > 0, "tc layer: N=%d has no supported tile", L.N);
-    const uint32_t box[3] = {TC_BK, (uint32_t)bn, 1};
+    const uint32_t box[3] = {(uint32_t)BK, (uint32_t)bn, 1};
     int rc = tc_encode_map(&maps.b[part], part ? L.w.lo : L.w.hi, 3, dims, str, box);
     if (rc) return rc;
   }
@@ -140,11 +149,16 @@ int tc_run_layer(const TcLayer& L, cudaStream_t st) {
   const TcEpilogue& e = L.epi;
   CIC_REQUIRE(L.splits == 1 || e.out_mode == TC_OUT_PARTIAL, "tc layer: split-K needs the partial output mode");
   CIC_REQUIRE(e.out_hi, "tc layer: null output");
+  if (e.out_mode == TC_OUT_BF16) {
+    const int ld = e.out_ld ? e.out_ld : L.N;
+    CIC_REQUIRE(L.N % 16 == 0 && (bn >= 32 ? L.N % 32 == 0 : true) && ld % 8 == 0 && e.out_coff % 8 == 0,
+                "tc layer: bf16 output needs N %% 16 == 0 and 16-byte aligned records (N=%d, ld=%d, coff=%d)", L.N, ld, e.out_coff);
+  }
   p.bias = e.bias; p.scale = e.scale; p.shift = e.shift; p.alpha = e.alpha; p.act = e.act;
   p.out_mode = e.out_mode; p.out_hi = e.out_hi; p.out_lo = e.out_lo; p.res_hi = e.res_hi; p.res_lo = e.res_lo;
   p.out_ld = e.out_ld ? e.out_ld : L.N; p.out_coff = e.out_coff; p.up2 = e.up2;
   p.m_total = (long long)L.batch * Ho * Wo;
-  return launch_tc_gemm(maps, p, tc_pick_block_n(L.N, L.split), L.split, st);
+  return launch_tc_gemm(maps, p, bn, BK, L.split, st);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -156,13 +170,13 @@ __device__ __forceinline__ void split2(float v, bf16& h, bf16& l) {
 }
 
 __global__ void __launch_bounds__(256)
-pack_weight_kernel(const float* __restrict__ src, int K, int N, int N_pad, bf16* __restrict__ hi, bf16* __restrict__ lo) {
+pack_weight_kernel(const float* __restrict__ src, int K, int N, int N_pad, int ld, bf16* __restrict__ hi, bf16* __restrict__ lo) {
   __shared__ float tile[32][33];
   const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
   for (int i = ty; i < 32; i += 8) {
     const int k = k0 + i, n = n0 + tx;
-    tile[i][tx] = (k < K && n < N) ? src[(size_t)k * N + n] : 0.f;
+    tile[i][tx] = (k < K && n < N) ? src[(size_t)k * ld + n] : 0.f;
   }
   __syncthreads();
   for (int i = ty; i < 32; i += 8) {
@@ -176,10 +190,10 @@ pack_weight_kernel(const float* __restrict__ src, int K, int N, int N_pad, bf16*
   }
 }
 
-int tc_pack_weight(const float* src, int K, int N, int N_pad, bf16* hi, bf16* lo, cudaStream_t st) {
+int tc_pack_weight(const float* src, int K, int N, int N_pad, int ld, bf16* hi, bf16* lo, cudaStream_t st) {
   dim3 grid((K + 31) / 32, (N_pad + 31) / 32);
   CIC_REQUIRE(grid.y <= 65535, "pack_weight: N too large");
-  pack_weight_kernel<<<grid, 256, 0, st>>>(src, K, N, N_pad, hi, lo);
+  pack_weight_kernel<<<grid, 256, 0, st>>>(src, K, N, N_pad, ld, hi, lo);
   CIC_COUNT_LAUNCH();
   CIC_CHECK_LAUNCH("pack_weight_kernel");
   return CIC_OK;

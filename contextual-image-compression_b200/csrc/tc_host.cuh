@@ -57,10 +57,12 @@ struct TcLayer {
 int tc_encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                   const uint32_t* box);
 int tc_run_layer(const TcLayer& L, cudaStream_t st);
-int tc_pick_block_n(int N, bool split);
+int tc_pick_block_n(int n_pad, bool split, int bk);
+int tc_pick_block_k(const TcLayer& L);
 
-// fp32 [K][N] (row-major, Keras kernel / Dense layout) -> bf16 hi/lo [N_pad][K] (K contiguous), zero rows >= N
-int tc_pack_weight(const float* src, int K, int N, int N_pad, bf16* hi, bf16* lo, cudaStream_t st);
+// fp32 [K][ld] (row-major, Keras kernel / Dense layout; the first N columns) -> bf16 hi/lo [N_pad][K]
+// (K contiguous), zero rows >= N
+int tc_pack_weight(const float* src, int K, int N, int N_pad, int ld, bf16* hi, bf16* lo, cudaStream_t st);
 // fp32 -> bf16 hi (+ lo)
 int tc_split_f32(const float* src, bf16* hi, bf16* lo, size_t n, cudaStream_t st);
 // bf16 hi (+ lo) -> fp32, with strided source records (ld, coff) -> dense C

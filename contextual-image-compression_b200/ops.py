@@ -61,6 +61,52 @@ def dense(x, kernel, bias=None, activation=None) -> torch.Tensor:
     return y
 
 
+def conv2d_tc(x, kernel, bias=None, stride=1, activation=None, scale=None, shift=None, x2=None, transpose=False,
+              split=False) -> torch.Tensor:
+    """Tensor-core Conv2D('same') / Conv2DTranspose(k4, s2) on concat([x, x2]); see cic_conv2d_nhwc_tc."""
+    x, kernel = to_device_f32(x), to_device_f32(kernel)
+    b, h, w, cin = x.shape
+    cin2 = 0
+    if x2 is not None:
+        x2 = to_device_f32(x2)
+        if tuple(x2.shape[:3]) != (b, h, w):
+            raise ValueError(f"x2 {tuple(x2.shape)} does not match x {tuple(x.shape)}")
+        cin2 = x2.shape[3]
+    kh, kw = int(kernel.shape[0]), int(kernel.shape[1])
+    if transpose:
+        if (kh, kw) != (4, 4) or kernel.shape[3] != cin + cin2:
+            raise ValueError(f"kernel must be (4,4,Cout,{cin + cin2}), got {tuple(kernel.shape)}")
+        cout, stride = int(kernel.shape[2]), 2
+        y = torch.empty((b, 2 * h, 2 * w, cout), dtype=torch.float32, device=x.device)
+    else:
+        if kernel.shape[2] != cin + cin2:
+            raise ValueError(f"kernel expects {kernel.shape[2]} input channels, inputs have {cin + cin2}")
+        cout = int(kernel.shape[3])
+        y = torch.empty((b, -(-h // stride), -(-w // stride), cout), dtype=torch.float32, device=x.device)
+    bias = to_device_f32(bias) if bias is not None else None
+    scale = to_device_f32(scale) if scale is not None else None
+    shift = to_device_f32(shift) if shift is not None else None
+    wsb = int(_lib.lib.cic_conv2d_tc_workspace_bytes(b, h, w, cin, cin2, cout, kh, kw, stride, int(transpose)))
+    ws = runtime.Workspace.get(wsb)
+    _lib.check(_lib.lib.cic_conv2d_nhwc_tc(ptr(x), ptr(x2), ptr(kernel), ptr(bias), ptr(scale), ptr(shift), ptr(y), b, h, w,
+                                           cin, cin2, cout, kh, kw, stride, int(transpose), _ACT[activation], int(split),
+                                           ptr(ws), ws.numel(), runtime.stream_ptr()))
+    return y
+
+
+def dense_tc(x, kernel, bias=None, activation=None, split=False) -> torch.Tensor:
+    x, kernel = to_device_f32(x), to_device_f32(kernel)
+    b, k = x.shape
+    n = kernel.shape[1]
+    bias = to_device_f32(bias) if bias is not None else None
+    y = torch.empty((b, n), dtype=torch.float32, device=x.device)
+    wsb = int(_lib.lib.cic_dense_tc_workspace_bytes(b, k, n))
+    ws = runtime.Workspace.get(wsb)
+    _lib.check(_lib.lib.cic_dense_tc(ptr(x), ptr(kernel), ptr(bias), ptr(y), b, k, n, _ACT[activation], int(split), ptr(ws),
+                                     ws.numel(), runtime.stream_ptr()))
+    return y
+
+
 def self_attention(x, wq, bq, wk, bk, wv, bv, gamma: float) -> torch.Tensor:
     """SelfAttention.call (GAN_functions.py:344-369); x (B,H,W,C); wq/wk (1,1,C,C/8) or (C,C/8); wv (.,C,C)."""
     x = to_device_f32(x)

@@ -174,6 +174,26 @@ size_t cic_dense_workspace_bytes(int batch, int in_dim, int out_dim);
 int cic_dense_f32(const float* d_x, const float* d_kernel, const float* d_bias, float* d_y, int batch, int in_dim,
                   int out_dim, int act, void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* Tensor-core (tcgen05, bf16 operands, fp32 accumulate in TMEM) forms of the three operators above, the
+ * arithmetic the CIC_PREC_TC plans use.  fp32 tensors in and out; operands are converted to bf16 (and the
+ * kernel packed to [Cout][K]) per call, so these are operator-level entry points for parity tests and
+ * one-off use - the plans keep packed weights and bf16 activations resident instead.
+ *   split != 0 : error-compensated 3-term split-bf16 (hi*hi + lo*hi + hi*lo), the encoder's arithmetic;
+ *   split == 0 : single-pass bf16, the decoders' arithmetic.
+ * cic_conv2d_nhwc_tc: Conv2D(padding='same', stride 1 or 2) on the channel concatenation of d_x (cin) and
+ * the optional d_x2 (cin2; Concatenate + Conv2D, GAN_functions.py:256-268), or with transpose != 0
+ * Conv2DTranspose(kernel 4, stride 2, 'same') with d_kernel (4,4,Cout,Cin+Cin2).  Channel counts of the
+ * sources must be multiples of 32. */
+size_t cic_conv2d_tc_workspace_bytes(int batch, int h, int w, int cin, int cin2, int cout, int kh, int kw, int stride,
+                                     int transpose);
+int cic_conv2d_nhwc_tc(const float* d_x, const float* d_x2, const float* d_kernel, const float* d_bias,
+                       const float* d_scale, const float* d_shift, float* d_y, int batch, int h, int w, int cin, int cin2,
+                       int cout, int kh, int kw, int stride, int transpose, int act, int split, void* d_workspace,
+                       size_t workspace_bytes, void* stream);
+size_t cic_dense_tc_workspace_bytes(int batch, int in_dim, int out_dim);
+int cic_dense_tc(const float* d_x, const float* d_kernel, const float* d_bias, float* d_y, int batch, int in_dim, int out_dim,
+                 int act, int split, void* d_workspace, size_t workspace_bytes, void* stream);
+
 /* SelfAttention.call (GAN_functions.py:344-369): x (B,h,w,C) -> gamma*softmax(q k^T) v + x.
  * d_wq/d_wk (C, C/8), d_wv (C, C) are the 1x1 conv kernels; workspace from cic_attention_workspace_bytes. */
 size_t cic_attention_workspace_bytes(int batch, int tokens, int channels);

@@ -1,0 +1,263 @@
+// Raster convolution kernel (see tc_conv.cuh) + launch.
+#include "tc_conv.cuh"
+
+namespace cic {
+
+struct TcvTile {
+  int ox0, oy0, b0;
+  int pass, n_tile;
+};
+
+__device__ __forceinline__ TcvTile tcv_decode(const TcvParams& p, int t) {
+  // N tiles fastest, then passes, then M tiles: every (pass, N tile) of one M tile re-reads the same rasters
+  // back to back, so those re-reads hit L2
+  TcvTile c;
+  c.n_tile = t % p.n_tiles;
+  const int r = t / p.n_tiles;
+  c.pass = r % p.npass;
+  const int m = r / p.npass;
+  c.ox0 = (m % p.tiles_x) * p.TW;
+  c.oy0 = ((m / p.tiles_x) % p.tiles_y) * p.TH;
+  c.b0 = (m / (p.tiles_x * p.tiles_y)) * p.TB;
+  return c;
+}
+
+// instruction descriptor with a runtime N (D fp32, A/B bf16 K-major, M = 128)
+__device__ __forceinline__ uint32_t tcv_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+}
+
+template <int BK, bool SPLIT>
+__global__ void __launch_bounds__(192, 1)
+tc_conv_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* a_ring = smem;
+  uint8_t* b_ring = smem + (size_t)p.a_slots * p.a_slot_bytes;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(b_ring + (size_t)p.b_slots * p.b_slot_bytes);
+  uint64_t* a_empty = a_full + TCV_MAX_SLOTS;
+  uint64_t* b_full = a_empty + TCV_MAX_SLOTS;
+  uint64_t* b_empty = b_full + TCV_MAX_SLOTS;
+  uint64_t* tmem_full_bar = b_empty + TCV_MAX_SLOTS;  // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cpt = p.src_blocks[0] + p.src_blocks[1];  // channel blocks per tap
+  constexpr uint32_t kRowBytes = 2 * BK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&maps.a[0][0]);
+    prefetch_tmap(&maps.b[0]);
+    if (SPLIT) { prefetch_tmap(&maps.a[0][1]); prefetch_tmap(&maps.b[1]); }
+    if (p.nsrc > 1) { prefetch_tmap(&maps.a[1][0]); if (SPLIT) prefetch_tmap(&maps.a[1][1]); }
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < TCV_MAX_SLOTS; ++s) {
+        mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1);
+        mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1);
+      }
+      for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 4); }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 2 * TCV_ACC_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer (warp-convergent; one elected lane issues) =====
+    uint32_t sa = 0, pa = 0, sb = 0, pb = 0;  // ring slot / phase of the next raster and weight block
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      const TcvTile tc = tcv_decode(p, t);
+      const TcvPass& ps = p.pass[tc.pass];
+      const int nrast = ps.nrast;
+      const int brow0 = tc.n_tile * p.BN;
+      for (int cb = 0; cb < cpt; ++cb) {
+        const int src = cb >= p.src_blocks[0] ? 1 : 0;
+        const int cbase = p.src_coff[src] + (src ? cb - p.src_blocks[0] : cb) * BK;
+        for (int ri = 0; ri < nrast; ++ri) {
+          const TcvRaster R = ps.r[ri];
+          mbar_wait(&a_empty[sa], pa ^ 1u);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&a_full[sa], p.a_tx_bytes);
+            uint8_t* a_hi = a_ring + (size_t)sa * p.a_slot_bytes;
+            uint8_t* a_lo = a_hi + (p.a_slot_bytes >> 1);
+            const int c = cbase + R.dc;
+            if (p.a5d) {
+              tma_load_5d(a_hi, &maps.a[src][0], &a_full[sa], c, tc.ox0 + R.dx, R.pz, tc.oy0 + R.dy, tc.b0);
+              if (SPLIT) tma_load_5d(a_lo, &maps.a[src][1], &a_full[sa], c, tc.ox0 + R.dx, R.pz, tc.oy0 + R.dy, tc.b0);
+            } else {
+              tma_load_4d(a_hi, &maps.a[src][0], &a_full[sa], c, tc.ox0 + R.dx, tc.oy0 + R.dy, tc.b0);
+              if (SPLIT) tma_load_4d(a_lo, &maps.a[src][1], &a_full[sa], c, tc.ox0 + R.dx, tc.oy0 + R.dy, tc.b0);
+            }
+          }
+          __syncwarp();
+          if (++sa == (uint32_t)p.a_slots) { sa = 0; pa ^= 1u; }
+          for (int oi = 0; oi < R.nops; ++oi) {
+            const TcvOp op = ps.op[R.op0 + oi];
+            mbar_wait(&b_empty[sb], pb ^ 1u);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&b_full[sb], p.b_tx_bytes);
+              uint8_t* b_hi = b_ring + (size_t)sb * p.b_slot_bytes;
+              uint8_t* b_lo = b_hi + (p.b_slot_bytes >> 1);
+              const int k = (op.tap * cpt + cb) * BK;
+              const int row = ps.phase_id[op.acc] * p.N_pad + brow0;
+              tma_load_3d(b_hi, &maps.b[0], &b_full[sb], k, row, 0);
+              if (SPLIT) tma_load_3d(b_lo, &maps.b[1], &b_full[sb], k, row, 0);
+            }
+            __syncwarp();
+            if (++sb == (uint32_t)p.b_slots) { sb = 0; pb ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (warp-convergent; one elected lane issues) =====
+    const uint32_t idesc = tcv_idesc(p.BN);
+    const uint32_t a_ring_lo = (smem_u32(a_ring) & 0x3FFFF) >> 4, b_ring_lo = (smem_u32(b_ring) & 0x3FFFF) >> 4;
+    const uint32_t a_slot_lo = (uint32_t)p.a_slot_bytes >> 4, b_slot_lo = (uint32_t)p.b_slot_bytes >> 4;
+    uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
+    int lt = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++lt) {
+      const TcvTile tc = tcv_decode(p, t);
+      const TcvPass& ps = p.pass[tc.pass];
+      const int nrast = ps.nrast;
+      const int as = lt & 1;
+      mbar_wait(&tmem_empty_bar[as], (((uint32_t)lt >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t d0 = tmem_base + (uint32_t)(as * TCV_ACC_COLS);
+      for (int cb = 0; cb < cpt; ++cb) {
+        for (int ri = 0; ri < nrast; ++ri) {
+          const TcvRaster R = ps.r[ri];
+          mbar_wait(&a_full[sa], pa);
+          tc_fence_after();
+          const uint32_t a_hi0 = a_ring_lo + sa * a_slot_lo;
+          const uint32_t a_lo0 = a_hi0 + (a_slot_lo >> 1);
+          for (int oi = 0; oi < R.nops; ++oi) {
+            const TcvOp op = ps.op[R.op0 + oi];
+            mbar_wait(&b_full[sb], pb);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t b_hi = b_ring_lo + sb * b_slot_lo;
+              const uint32_t b_lo = b_hi + (b_slot_lo >> 1);
+              const uint32_t sh = (uint32_t)op.row_shift * (kRowBytes >> 4);
+              const uint32_t a_hi = a_hi0 + sh, a_lo = a_lo0 + sh;
+              const uint32_t d = d0 + (uint32_t)(op.acc * p.BN);
+              const uint32_t keep = (cb == 0 && op.first) ? 0u : 1u;
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k)
+                umma_bf16(d, umma_desc_from_lo<BK>(a_hi + 2 * k), umma_desc_from_lo<BK>(b_hi + 2 * k), idesc, k == 0 ? keep : 1u);
+              if (SPLIT) {
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k)
+                  umma_bf16(d, umma_desc_from_lo<BK>(a_lo + 2 * k), umma_desc_from_lo<BK>(b_hi + 2 * k), idesc, 1u);
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k)
+                  umma_bf16(d, umma_desc_from_lo<BK>(a_hi + 2 * k), umma_desc_from_lo<BK>(b_lo + 2 * k), idesc, 1u);
+              }
+              umma_commit(&b_empty[sb]);
+            }
+            __syncwarp();
+            if (++sb == (uint32_t)p.b_slots) { sb = 0; pb ^= 1u; }
+          }
+          if (elect_one()) umma_commit(&a_empty[sa]);  // raster slot is free once all of its MMAs have retired
+          __syncwarp();
+          if (++sa == (uint32_t)p.a_slots) { sa = 0; pa ^= 1u; }
+        }
+      }
+      if (elect_one()) umma_commit(&tmem_full_bar[as]);
+      __syncwarp();
+    }
+  } else {
+    // ===== epilogue: 4 warps, warp w owns TMEM lanes 32*(w%4).. =====
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int xl = r % p.TW, yl = (r / p.TW) % p.TH, bl = r / (p.TW * p.TH);
+    const bool wide = (p.BN & 31) == 0;  // 32-column accumulator chunks, else 16
+    int lt = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++lt) {
+      const TcvTile tc = tcv_decode(p, t);
+      const TcvPass& ps = p.pass[tc.pass];
+      const int as = lt & 1;
+      const int ox = tc.ox0 + xl, oy = tc.oy0 + yl, b = tc.b0 + bl;
+      const bool valid = (bl < p.TB) && ox < p.Wo && oy < p.Ho && b < p.batch;
+      mbar_wait(&tmem_full_bar[as], ((uint32_t)lt >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * TCV_ACC_COLS);
+      const int chunks = wide ? p.BN / 32 : p.BN / 16;
+#pragma unroll 1
+      for (int j = 0; j < ps.nacc; ++j) {
+        const TcRow row{b, oy, ox, ps.phase_id[j], 0};
+#pragma unroll 1
+        for (int c = 0; c < chunks; ++c) {
+          uint32_t v[32];
+          __syncwarp();
+          if (wide) tmem_ld32(taddr + (uint32_t)(j * p.BN + c * 32), v);
+          else tmem_ld16(taddr + (uint32_t)(j * p.BN + c * 16), v);
+          tmem_ld_wait();
+          if (j == ps.nacc - 1 && c == chunks - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+          }
+          const int ch = wide ? 32 : 16;
+          const int n0 = tc.n_tile * p.BN + c * ch;
+          const int nv = min(ch, p.epi.N - n0);
+          if (valid && nv > 0) {
+            if (wide) tc_epilogue_store<32>(p.epi, row, v, n0, nv);
+            else tc_epilogue_store<16>(p.epi, row, v, n0, nv);
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 2 * TCV_ACC_COLS);
+}
+
+size_t tcv_smem_bytes(const TcvParams& p) {
+  size_t n = (size_t)p.a_slots * p.a_slot_bytes + (size_t)p.b_slots * p.b_slot_bytes + 1024 /*align*/ + 512 /*barriers*/;
+  // the kernel allocates all 512 TMEM columns: keep it to one CTA per SM whatever the ring sizes are
+  const size_t floor_bytes = 120 * 1024;
+  return n < floor_bytes ? floor_bytes : n;
+}
+
+template <int BK, bool SPLIT>
+static int launch_conv_one(const TcMaps& maps, const TcvParams& p, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    CIC_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<BK, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const size_t smem = tcv_smem_bytes(p);
+  CIC_REQUIRE(smem <= 227 * 1024, "tc_conv: %zu bytes of shared memory needed", smem);
+  const int slots = sm_count();
+  const int grid = p.total_tiles < slots ? p.total_tiles : slots;
+  tc_conv_kernel<BK, SPLIT><<<grid, 192, smem, st>>>(maps, p);
+  CIC_COUNT_LAUNCH();
+  CIC_CHECK_LAUNCH("tc_conv_kernel");
+  return CIC_OK;
+}
+
+int launch_tc_conv(const TcMaps& maps, const TcvParams& p, int block_k, bool split, cudaStream_t st) {
+  CIC_REQUIRE(p.total_tiles > 0 && p.npass >= 1 && p.npass <= TCV_MAX_PASS, "tc_conv: bad tile list");
+  CIC_REQUIRE(p.BN % 16 == 0 && p.BN >= 16 && p.BN <= TCV_ACC_COLS, "tc_conv: bad accumulator width %d", p.BN);
+  CIC_REQUIRE(p.a_slots >= 2 && p.a_slots <= TCV_MAX_SLOTS && p.b_slots >= 2 && p.b_slots <= TCV_MAX_SLOTS, "tc_conv: bad ring sizes");
+  for (int i = 0; i < p.npass; ++i)
+    CIC_REQUIRE(p.pass[i].nacc >= 1 && p.pass[i].nacc * p.BN <= TCV_ACC_COLS && p.pass[i].nrast >= 1 && p.pass[i].nrast <= TCV_MAX_RASTERS,
+                "tc_conv: bad pass %d", i);
+  if (block_k == 64) return split ? launch_conv_one<64, true>(maps, p, st) : launch_conv_one<64, false>(maps, p, st);
+  if (block_k == 32) return split ? launch_conv_one<32, true>(maps, p, st) : launch_conv_one<32, false>(maps, p, st);
+  set_error("tc_conv: unsupported K block %d", block_k);
+  return CIC_ERR_INVALID;
+}
+
+}  // namespace cic

@@ -9,6 +9,40 @@ namespace cic {
 // ------------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------------
+struct TileCoord {
+  int ox0, oy0, b0;  // first output position of the M tile
+  int n_tile, phase, split;
+  int kb0, nkb;      // K-block range of this split
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int t) {
+  const int mt = p.tiles_x * p.tiles_y * p.tiles_b;
+  int m, n, z;
+  if (p.m_fast) {
+    m = t % mt;
+    const int r = t / mt;
+    n = r % p.n_tiles;
+    z = r / p.n_tiles;
+  } else {
+    n = t % p.n_tiles;
+    const int r = t / p.n_tiles;
+    const int zt = p.nphases * p.splits;
+    z = r % zt;
+    m = r / zt;
+  }
+  TileCoord c;
+  c.ox0 = (m % p.tiles_x) * p.TW;
+  c.oy0 = ((m / p.tiles_x) % p.tiles_y) * p.TH;
+  c.b0 = (m / (p.tiles_x * p.tiles_y)) * p.TB;
+  c.n_tile = n;
+  c.phase = z / p.splits;
+  c.split = z % p.splits;
+  const int per_split = (p.kblocks + p.splits - 1) / p.splits;
+  c.kb0 = c.split * per_split;
+  c.nkb = min(p.kblocks, c.kb0 + per_split) - c.kb0;  // host guarantees >= 1
+  return c;
+}
+
 template <int BN, int BK, bool SPLIT>
 __global__ void __launch_bounds__(192, TcCfg<BN, BK, SPLIT>::kMinCtas)
 tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams p) {
@@ -19,23 +53,11 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
   uint64_t* empty_bar = full_bar + kStages;
-  uint64_t* tmem_full_bar = empty_bar + kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + kStages;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  // tile coordinates
-  const int tile = blockIdx.x;
-  const int tix = tile % p.tiles_x;
-  const int tiy = (tile / p.tiles_x) % p.tiles_y;
-  const int tib = tile / (p.tiles_x * p.tiles_y);
-  const int ox0 = tix * p.TW, oy0 = tiy * p.TH, b0 = tib * p.TB;
-  const int n_tile = blockIdx.y;
-  const int phase = blockIdx.z / p.splits, split = blockIdx.z % p.splits;
-  const int per_split = (p.kblocks + p.splits - 1) / p.splits;
-  const int kb0 = split * per_split;
-  const int kb1 = min(p.kblocks, kb0 + per_split);
-  const int nkb = kb1 - kb0;  // host guarantees >= 1
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&maps.a[0][0]);
@@ -46,7 +68,7 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-      mbar_init(tmem_full_bar, 1);
+      for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 4); }
       fence_barrier_init();
     }
     __syncwarp();
@@ -59,169 +81,113 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
-      const int cpt = p.src_blocks[0] + p.src_blocks[1];
-      const uint32_t rows = (uint32_t)(p.TW * p.TH * p.TB);
-      const uint32_t tx_bytes = (SPLIT ? 2u : 1u) * (rows + (uint32_t)BN) * (uint32_t)(2 * BK);
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % kStages;
-        const uint32_t ph = (uint32_t)(i / kStages) & 1u;
+    // ===== TMA producer: warp-convergent, one elected lane issues; runs ahead across tile boundaries =====
+    const int cpt = p.src_blocks[0] + p.src_blocks[1];
+    const uint32_t rows = (uint32_t)(p.TW * p.TH * p.TB);
+    const uint32_t tx_bytes = (SPLIT ? 2u : 1u) * (rows + (uint32_t)BN) * (uint32_t)(2 * BK);
+    uint32_t s = 0, ph = 0;  // ring slot / phase
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      const TileCoord tc = decode_tile(p, t);
+      const int bn = tc.phase * p.N_pad + tc.n_tile * BN;
+      const int bz = p.b_batched ? tc.b0 : 0;
+      int tap = tc.kb0 / cpt, ch = tc.kb0 % cpt;
+      for (int i = 0; i < tc.nkb; ++i) {
         mbar_wait(&empty_bar[s], ph ^ 1u);
-        mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
-        const int kb = kb0 + i;
-        const int tap = kb / cpt, ch = kb % cpt;
-        const int src = ch >= p.src_blocks[0] ? 1 : 0;
-        const int cblk = src ? ch - p.src_blocks[0] : ch;
-        const TcTap t = p.taps[phase][tap];
-        const int c = p.src_coff[src] + cblk * BK + t.dc;
-        uint8_t* st = smem + s * Cfg::kStageBytes;
-        uint8_t* a_hi = st;
-        uint8_t* a_lo = st + Cfg::kABytes;
-        uint8_t* b_hi = st + (SPLIT ? 2 : 1) * Cfg::kABytes;
-        uint8_t* b_lo = b_hi + Cfg::kBBytes;
-        if (p.a5d) {
-          tma_load_5d(a_hi, &maps.a[src][0], &full_bar[s], c, ox0 + t.dx, t.pz, oy0 + t.dy, b0);
-          if (SPLIT) tma_load_5d(a_lo, &maps.a[src][1], &full_bar[s], c, ox0 + t.dx, t.pz, oy0 + t.dy, b0);
-        } else {
-          tma_load_4d(a_hi, &maps.a[src][0], &full_bar[s], c, ox0 + t.dx, oy0 + t.dy, b0);
-          if (SPLIT) tma_load_4d(a_lo, &maps.a[src][1], &full_bar[s], c, ox0 + t.dx, oy0 + t.dy, b0);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
+          const int kb = tc.kb0 + i;
+          const int src = ch >= p.src_blocks[0] ? 1 : 0;
+          const int cblk = src ? ch - p.src_blocks[0] : ch;
+          const TcTap tp = p.taps[tc.phase][tap];
+          const int c = p.src_coff[src] + cblk * BK + tp.dc;
+          uint8_t* st = smem + s * Cfg::kStageBytes;
+          uint8_t* a_hi = st;
+          uint8_t* a_lo = st + Cfg::kABytes;
+          uint8_t* b_hi = st + (SPLIT ? 2 : 1) * Cfg::kABytes;
+          uint8_t* b_lo = b_hi + Cfg::kBBytes;
+          if (p.a5d) {
+            tma_load_5d(a_hi, &maps.a[src][0], &full_bar[s], c, tc.ox0 + tp.dx, tp.pz, tc.oy0 + tp.dy, tc.b0);
+            if (SPLIT) tma_load_5d(a_lo, &maps.a[src][1], &full_bar[s], c, tc.ox0 + tp.dx, tp.pz, tc.oy0 + tp.dy, tc.b0);
+          } else {
+            tma_load_4d(a_hi, &maps.a[src][0], &full_bar[s], c, tc.ox0 + tp.dx, tc.oy0 + tp.dy, tc.b0);
+            if (SPLIT) tma_load_4d(a_lo, &maps.a[src][1], &full_bar[s], c, tc.ox0 + tp.dx, tc.oy0 + tp.dy, tc.b0);
+          }
+          tma_load_3d(b_hi, &maps.b[0], &full_bar[s], kb * BK, bn, bz);
+          if (SPLIT) tma_load_3d(b_lo, &maps.b[1], &full_bar[s], kb * BK, bn, bz);
         }
-        const int bn = phase * p.N_pad + n_tile * BN;
-        const int bz = p.b_batched ? b0 : 0;
-        tma_load_3d(b_hi, &maps.b[0], &full_bar[s], kb * BK, bn, bz);
-        if (SPLIT) tma_load_3d(b_lo, &maps.b[1], &full_bar[s], kb * BK, bn, bz);
+        __syncwarp();
+        if (++ch == cpt) { ch = 0; ++tap; }
+        if (++s == (uint32_t)kStages) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BN);
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % kStages;
-        const uint32_t ph = (uint32_t)(i / kStages) & 1u;
+    // ===== MMA issuer: warp-convergent, one elected lane issues =====
+    constexpr uint32_t idesc = umma_idesc_bf16(BN);
+    const uint32_t ring_lo = (smem_u32(smem) & 0x3FFFF) >> 4;
+    constexpr uint32_t kStageLo = Cfg::kStageBytes >> 4, kALo = Cfg::kABytes >> 4, kBLo = Cfg::kBBytes >> 4;
+    uint32_t s = 0, ph = 0;
+    int lt = 0;  // tiles processed by this CTA
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++lt) {
+      const TileCoord tc = decode_tile(p, t);
+      const int as = lt & 1;
+      mbar_wait(&tmem_empty_bar[as], (((uint32_t)lt >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t d = tmem_base + (uint32_t)(as * BN);
+      for (int i = 0; i < tc.nkb; ++i) {
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
-        const uint32_t st = smem_u32(smem + s * Cfg::kStageBytes);
-        const uint32_t a_hi = st, a_lo = st + Cfg::kABytes;
-        const uint32_t b_hi = st + (SPLIT ? 2 : 1) * Cfg::kABytes, b_lo = b_hi + Cfg::kBBytes;
-#pragma unroll
-        for (int k = 0; k < BK / 16; ++k)
-          umma_bf16(tmem_base, umma_desc_kmajor<BK>(a_hi + k * 32), umma_desc_kmajor<BK>(b_hi + k * 32), idesc, (i | k) != 0);
-        if (SPLIT) {
+        if (elect_one()) {
+          const uint32_t a_hi = ring_lo + s * kStageLo, a_lo = a_hi + kALo;
+          const uint32_t b_hi = a_hi + (SPLIT ? 2 : 1) * kALo, b_lo = b_hi + kBLo;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
-            umma_bf16(tmem_base, umma_desc_kmajor<BK>(a_lo + k * 32), umma_desc_kmajor<BK>(b_hi + k * 32), idesc, 1u);
+            umma_bf16(d, umma_desc_from_lo<BK>(a_hi + 2 * k), umma_desc_from_lo<BK>(b_hi + 2 * k), idesc, (i | k) != 0);
+          if (SPLIT) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            umma_bf16(tmem_base, umma_desc_kmajor<BK>(a_hi + k * 32), umma_desc_kmajor<BK>(b_lo + k * 32), idesc, 1u);
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16(d, umma_desc_from_lo<BK>(a_lo + 2 * k), umma_desc_from_lo<BK>(b_hi + 2 * k), idesc, 1u);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16(d, umma_desc_from_lo<BK>(a_hi + 2 * k), umma_desc_from_lo<BK>(b_lo + 2 * k), idesc, 1u);
+          }
+          umma_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
         }
-        umma_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
+        __syncwarp();
+        if (++s == (uint32_t)kStages) { s = 0; ph ^= 1u; }
       }
-      umma_commit(tmem_full_bar);    // accumulator complete
+      if (elect_one()) umma_commit(&tmem_full_bar[as]);  // accumulator complete
+      __syncwarp();
     }
   } else {
     // ===== epilogue: 4 warps, warp w owns TMEM lanes 32*(w%4).. =====
     const int q = warp & 3;
     const int r = q * 32 + lane;  // row of the tile
     const int xl = r % p.TW, yl = (r / p.TW) % p.TH, bl = r / (p.TW * p.TH);
-    const int ox = ox0 + xl, oy = oy0 + yl, b = b0 + bl;
-    const bool valid = (bl < p.TB) && ox < p.Wo && oy < p.Ho && b < p.batch;
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-    const long long opix = ((long long)b * p.out_H + (oy * p.out_ys + p.out_y0[phase])) * p.out_W + (ox * p.out_xs + p.out_x0[phase]);
-    const long long mrow = ((long long)b * p.Ho + oy) * p.Wo + ox;
+    int lt = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++lt) {
+      const TileCoord tc = decode_tile(p, t);
+      const int as = lt & 1;
+      const int ox = tc.ox0 + xl, oy = tc.oy0 + yl, b = tc.b0 + bl;
+      const bool valid = (bl < p.TB) && ox < p.Wo && oy < p.Ho && b < p.batch;
+      mbar_wait(&tmem_full_bar[as], ((uint32_t)lt >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+      const TcRow row{b, oy, ox, tc.phase, tc.split};
 #pragma unroll 1
-    for (int c = 0; c < BN / CH; ++c) {
-      uint32_t v[32];
-      __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the divergent stores of the previous chunk
-      if (CH == 32) tmem_ld32(taddr + (uint32_t)(c * CH), v);
-      else tmem_ld16(taddr + (uint32_t)(c * CH), v);
-      tmem_ld_wait();
-      const int n0 = n_tile * BN + c * CH;
-      const int nv = min(CH, p.N - n0);  // valid channels of this chunk
-      if (!valid || nv <= 0) continue;
-      if (p.out_mode == TC_OUT_PARTIAL) {
-        float* dst = reinterpret_cast<float*>(p.out_hi) + ((long long)split * p.m_total + mrow) * p.N + n0;
-        if (nv == CH && (p.N & 3) == 0) {
-#pragma unroll
-          for (int j = 0; j < CH / 4; ++j)
-            reinterpret_cast<float4*>(dst)[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                                            __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-        } else {
-#pragma unroll
-          for (int j = 0; j < CH; ++j)
-            if (j < nv) dst[j] = __uint_as_float(v[j]);
+      for (int c = 0; c < BN / CH; ++c) {
+        uint32_t v[32];
+        __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the divergent stores of the previous chunk
+        if (CH == 32) tmem_ld32(taddr + (uint32_t)(c * CH), v);
+        else tmem_ld16(taddr + (uint32_t)(c * CH), v);
+        tmem_ld_wait();
+        if (c == BN / CH - 1) {  // accumulator is in registers: hand the TMEM buffer back to the MMA issuer
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
         }
-        continue;
-      }
-      float f[CH];
-#pragma unroll
-      for (int j = 0; j < CH; ++j) {
-        float x = __fmul_rn(p.alpha, __uint_as_float(v[j]));
-        if (j < nv) {
-          if (p.bias) x = __fadd_rn(x, __ldg(p.bias + n0 + j));
-          if (p.scale) x = __fadd_rn(__fmul_rn(x, __ldg(p.scale + n0 + j)), __ldg(p.shift + n0 + j));
-        }
-        f[j] = act_apply(x, p.act);
-      }
-      if (p.out_mode == TC_OUT_F32) {
-        float* dst = reinterpret_cast<float*>(p.out_hi) + opix * p.out_ld + p.out_coff + n0;
-        if (nv == CH && ((p.out_ld | p.out_coff) & 3) == 0) {
-#pragma unroll
-          for (int j = 0; j < CH / 4; ++j) reinterpret_cast<float4*>(dst)[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < CH; ++j)
-            if (j < nv) dst[j] = f[j];
-        }
-      } else if (p.out_mode == TC_OUT_BF16) {  // host guarantees N % CH == 0 and 16-byte aligned records
-        const long long idx = opix * p.out_ld + p.out_coff + n0;
-        if (p.res_hi) {
-#pragma unroll
-          for (int j = 0; j < CH; ++j) {
-            float rv = __bfloat162float(p.res_hi[idx + j]);
-            if (p.res_lo) rv += __bfloat162float(p.res_lo[idx + j]);
-            f[j] = __fadd_rn(f[j], rv);
-          }
-        }
-        uint32_t hi[CH / 2], lo[CH / 2];
-#pragma unroll
-        for (int j = 0; j < CH / 2; ++j) {
-          const __nv_bfloat16 h0 = __float2bfloat16_rn(f[2 * j]), h1 = __float2bfloat16_rn(f[2 * j + 1]);
-          hi[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-          const __nv_bfloat16 l0 = __float2bfloat16_rn(f[2 * j] - __bfloat162float(h0));
-          const __nv_bfloat16 l1 = __float2bfloat16_rn(f[2 * j + 1] - __bfloat162float(h1));
-          lo[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-        }
-        const int reps = p.up2 ? 2 : 1;
-        for (int ry = 0; ry < reps; ++ry)
-          for (int rx = 0; rx < reps; ++rx) {
-            long long o = idx;
-            if (p.up2) o = ((((long long)b * p.out_H + (oy * 2 + ry)) * p.out_W) + (ox * 2 + rx)) * p.out_ld + p.out_coff + n0;
-            uint4* dh = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out_hi) + o);
-#pragma unroll
-            for (int j = 0; j < CH / 8; ++j) dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-            if (p.out_lo) {
-              uint4* dl = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out_lo) + o);
-#pragma unroll
-              for (int j = 0; j < CH / 8; ++j) dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
-            }
-          }
-      } else {  // TC_OUT_BF16_T: out[b][n][position] (V^T for the attention PV product)
-        const long long how = (long long)p.Ho * p.Wo;
-        const long long pos = (long long)oy * p.Wo + ox;
-        __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(p.out_hi);
-        __nv_bfloat16* ol = reinterpret_cast<__nv_bfloat16*>(p.out_lo);
-#pragma unroll
-        for (int j = 0; j < CH; ++j) {
-          if (j >= nv) break;
-          const long long o = ((long long)b * p.N + n0 + j) * how + pos;
-          const __nv_bfloat16 h = __float2bfloat16_rn(f[j]);
-          oh[o] = h;
-          if (ol) ol[o] = __float2bfloat16_rn(f[j] - __bfloat162float(h));
-        }
+        const int n0 = tc.n_tile * BN + c * CH;
+        const int nv = min(CH, p.N - n0);  // valid channels of this chunk
+        if (valid && nv > 0) tc_epilogue_store<CH>(p.epi, row, v, n0, nv);
       }
     }
   }
@@ -278,13 +244,16 @@ int tc_encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* 
 }
 
 template <int BN, int BK, bool SPLIT>
-static int launch_one(const TcMaps& maps, const TcParams& p, dim3 grid, cudaStream_t st) {
+static int launch_one(const TcMaps& maps, const TcParams& p, cudaStream_t st) {
   using Cfg = TcCfg<BN, BK, SPLIT>;
   static bool attr_set = false;
   if (!attr_set) {
     CIC_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, BK, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
+  // persistent: at most one wave of CTAs, each walking the tile list with stride gridDim.x
+  const int slots = sm_count() * Cfg::kMinCtas;
+  const int grid = p.total_tiles < slots ? p.total_tiles : slots;
   tc_gemm_kernel<BN, BK, SPLIT><<<grid, 192, Cfg::kSmemBytes, st>>>(maps, p);
   CIC_COUNT_LAUNCH();
   CIC_CHECK_LAUNCH("tc_gemm_kernel");
@@ -292,21 +261,21 @@ static int launch_one(const TcMaps& maps, const TcParams& p, dim3 grid, cudaStre
 }
 
 template <int BK, bool SPLIT>
-static int launch_bn(const TcMaps& maps, const TcParams& p, int block_n, dim3 grid, cudaStream_t st) {
+static int launch_bn(const TcMaps& maps, const TcParams& p, int block_n, cudaStream_t st) {
   switch (block_n) {
-    case 16: return launch_one<16, BK, SPLIT>(maps, p, grid, st);
-    case 32: return launch_one<32, BK, SPLIT>(maps, p, grid, st);
-    case 64: return launch_one<64, BK, SPLIT>(maps, p, grid, st);
-    case 128: return launch_one<128, BK, SPLIT>(maps, p, grid, st);
+    case 16: return launch_one<16, BK, SPLIT>(maps, p, st);
+    case 32: return launch_one<32, BK, SPLIT>(maps, p, st);
+    case 64: return launch_one<64, BK, SPLIT>(maps, p, st);
+    case 128: return launch_one<128, BK, SPLIT>(maps, p, st);
     case 256:
-      if (!SPLIT && BK == 64) return launch_one<256, 64, false>(maps, p, grid, st);
+      if (!SPLIT && BK == 64) return launch_one<256, 64, false>(maps, p, st);
       break;
   }
   set_error("tc_gemm: unsupported N tile %d (K block %d, split=%d)", block_n, BK, (int)SPLIT);
   return CIC_ERR_INVALID;
 }
 
-int launch_tc_gemm(const TcMaps& maps, const TcParams& p, int block_n, int block_k, bool split, cudaStream_t st) {
+int launch_tc_gemm(const TcMaps& maps, TcParams& p, int block_n, int block_k, bool split, cudaStream_t st) {
   CIC_REQUIRE(block_n > 0 && p.N_pad % block_n == 0 && p.N <= p.N_pad, "tc_gemm: padded N=%d is not a multiple of the N tile %d", p.N_pad, block_n);
   CIC_REQUIRE(p.kblocks >= p.splits && p.splits >= 1, "tc_gemm: bad split-K %d for %d K blocks", p.splits, p.kblocks);
   const int per = (p.kblocks + p.splits - 1) / p.splits;
@@ -314,10 +283,12 @@ int launch_tc_gemm(const TcMaps& maps, const TcParams& p, int block_n, int block
   CIC_REQUIRE(p.TW * p.TH * p.TB <= TC_BM && p.TW >= 1, "tc_gemm: bad M tile");
   const long long mt = (long long)p.tiles_x * p.tiles_y * p.tiles_b;
   CIC_REQUIRE(mt > 0 && mt < 2147483647LL, "tc_gemm: bad tile count");
-  dim3 grid((unsigned)mt, (p.N + block_n - 1) / block_n, p.nphases * p.splits);
-  CIC_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "tc_gemm: grid too large");
-  if (block_k == 64) return split ? launch_bn<64, true>(maps, p, block_n, grid, st) : launch_bn<64, false>(maps, p, block_n, grid, st);
-  if (block_k == 32) return split ? launch_bn<32, true>(maps, p, block_n, grid, st) : launch_bn<32, false>(maps, p, block_n, grid, st);
+  p.n_tiles = (p.N + block_n - 1) / block_n;
+  const long long total = mt * p.n_tiles * p.nphases * p.splits;
+  CIC_REQUIRE(total < 2147483647LL, "tc_gemm: too many tiles");
+  p.total_tiles = (int)total;
+  if (block_k == 64) return split ? launch_bn<64, true>(maps, p, block_n, st) : launch_bn<64, false>(maps, p, block_n, st);
+  if (block_k == 32) return split ? launch_bn<32, true>(maps, p, block_n, st) : launch_bn<32, false>(maps, p, block_n, st);
   set_error("tc_gemm: unsupported K block %d", block_k);
   return CIC_ERR_INVALID;
 }

@@ -13,19 +13,19 @@
 // In SPLIT mode A and B are (hi, lo) bf16 pairs and each K block issues three MMAs
 // (hi*hi + lo*hi + hi*lo): error-compensated bf16 that reproduces fp32 products to ~2^-17 relative.
 //
-// Warp roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer (one
-// lane), warps 2-5 = epilogue (tcgen05.ld -> bias / folded BN / activation -> global).  A ring of
-// kStages smem slots with full/empty mbarriers decouples TMA from the tensor pipe; tcgen05.commit
-// releases slots and signals the epilogue.  Two CTAs are co-resident per SM where shared memory allows,
-// so one CTA's epilogue overlaps the other's main loop.
+// Persistent kernel: the grid is one (or two) CTAs per SM and every CTA walks the tile list
+// t = blockIdx.x, blockIdx.x + gridDim.x, ...  Warp roles (192 threads): warp 0 = TMA producer (one lane),
+// warp 1 = TMEM allocator + MMA issuer (one lane), warps 2-5 = epilogue (tcgen05.ld -> bias / folded BN /
+// activation -> global).  A ring of kStages smem slots with full/empty mbarriers decouples TMA from the
+// tensor pipe and runs ahead across tile boundaries; the accumulator is double-buffered in TMEM
+// (tmem_full / tmem_empty mbarriers) so the MMAs of tile i+1 overlap the epilogue of tile i.
 #pragma once
 #include "common.cuh"
+#include "tc_epilogue.cuh"
 
 #include <cuda.h>
 
 namespace cic {
-
-enum TcOutMode { TC_OUT_BF16 = 0, TC_OUT_F32 = 1, TC_OUT_PARTIAL = 2, TC_OUT_BF16_T = 3 };
 
 constexpr int TC_BM = 128;
 constexpr int TC_MAX_TAPS = 16;
@@ -52,23 +52,10 @@ struct TcParams {
   int kblocks;            // total K blocks = ntaps * (src_blocks[0] + src_blocks[1])
   int N, N_pad;           // real / padded output channels (B rows per phase = N_pad)
   int b_batched;          // 1: B has one matrix per batch item (attention); tile never spans items
-  // epilogue
-  const float* bias;
-  const float* scale;
-  const float* shift;
-  float alpha;
-  int act;
-  int out_mode;
-  void* out_hi;           // bf16 (or fp32 for TC_OUT_F32 / TC_OUT_PARTIAL)
-  void* out_lo;           // optional bf16 low part
-  const __nv_bfloat16* res_hi;  // optional residual (same addressing as the bf16 output)
-  const __nv_bfloat16* res_lo;
-  int out_ld, out_coff;
-  int out_H, out_W;
-  int out_ys, out_xs;
-  int8_t out_y0[4], out_x0[4];  // per phase
-  int up2;                // 1: replicate every output pixel 2x2 (nearest up-sampling fused into the store)
-  long long m_total;      // rows of the partial buffer
+  int n_tiles;            // N tiles per (M tile, phase, split)
+  int total_tiles;        // M tiles x n_tiles x nphases x splits
+  int m_fast;             // tile order: 1 = M tiles fastest (weight-dominated GEMMs), 0 = N tiles fastest
+  TcEpi epi;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -80,6 +67,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
@@ -100,6 +90,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (it == 1024) t0 = clock64();
     if (it > 1024 && (it & 1023) == 0 && clock64() - t0 > 4000000000LL) __trap();  // ~2 s
   }
+}
+
+// One lane of a fully converged warp (the same lane every time).  The producer and MMA warps run their loops
+// warp-convergent and elect a lane only around the asynchronous instruction issue: inside a divergent
+// `if (lane == 0)` region the compiler wraps every uniform-datapath instruction (tcgen05.*, TMA, mbarrier) in
+// vote / elect / branch sequences, which made the issuing thread itself the bottleneck (ncu source view,
+// profiles/r01_ncu_raster_issue_bound.md).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
@@ -156,8 +161,19 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 }
 
 // K-major swizzled shared-memory operand descriptor (sm_100 format).  One swizzle atom along K
-// (BK bf16 = 2*BK bytes per row), 8-row groups 8 * 2*BK bytes apart (SBO); LBO unused.
+// (BK bf16 = 2*BK bytes per row), 8-row groups 8 * 2*BK bytes apart (SBO); LBO unused.  The start address
+// may be any row (multiple of 2*BK bytes), not only a multiple of the swizzle repeat: the hardware swizzles
+// on absolute shared-memory address bits, exactly like TMA does when it writes the tile (measured on B200,
+// profiles/r01_shift_probe.log), so base_offset stays 0.
 //   BK = 64: SWIZZLE_128B (layout type 2), SBO 1024;  BK = 32: SWIZZLE_64B (layout type 4), SBO 512.
+template <int BK>
+__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr);
+// the same descriptor from a pre-shifted start-address field: desc = hi(const) | lo, lo = (addr & 0x3FFFF) >> 4
+template <int BK>
+__device__ __forceinline__ uint64_t umma_desc_from_lo(uint32_t lo) {
+  constexpr uint32_t hi = (uint32_t)((8 * 2 * BK) >> 4) | (1u << 14) | ((BK == 64 ? 2u : 4u) << 29);
+  return ((uint64_t)hi << 32) | (uint64_t)lo;
+}
 template <int BK>
 __device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr) {
   constexpr uint64_t sbo = 8 * 2 * BK;
@@ -203,12 +219,13 @@ struct TcCfg {
   static constexpr int kABytes = TC_BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = (SPLIT ? 2 : 1) * (kABytes + kBBytes);
-  static constexpr int kBudget = (SPLIT && BN >= 128) || BN >= 256 ? 196608 : 98304;  // 1 or 2 CTAs per SM
+  static constexpr int kBudget = SPLIT || BN >= 256 ? 196608 : 98304;  // 1 or 2 CTAs per SM
   static constexpr int kStages = (kBudget / kStageBytes) < 2 ? 2 : ((kBudget / kStageBytes) > 8 ? 8 : (kBudget / kStageBytes));
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
-  static constexpr int kTmemCols = BN < 32 ? 32 : BN;
+  static constexpr int kTmemCols = 2 * BN;          // double-buffered accumulator (32 .. 512 columns)
   static constexpr int kChunk = BN < 32 ? 16 : 32;  // accumulator columns per tcgen05.ld
   static constexpr int kMinCtas = kSmemBytes <= 112 * 1024 ? 2 : 1;
+  static_assert(kMinCtas * kTmemCols <= 512, "TMEM over-subscribed");
 };
 
 struct TcMaps {
@@ -216,6 +233,6 @@ struct TcMaps {
   CUtensorMap b[2];     // [hi, lo]
 };
 
-int launch_tc_gemm(const TcMaps& maps, const TcParams& p, int block_n, int block_k, bool split, cudaStream_t st);
+int launch_tc_gemm(const TcMaps& maps, TcParams& p, int block_n, int block_k, bool split, cudaStream_t st);
 
 }  // namespace cic

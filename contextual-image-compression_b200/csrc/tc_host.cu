@@ -1,5 +1,11 @@
 // Host-side assembly of tcgen05 layer launches + conversion kernels (see tc_host.cuh).
 #include "tc_host.cuh"
+#include "tc_conv.cuh"
+
+#include <algorithm>
+#include <vector>
+#include <cstdlib>
+#include <cstring>
 
 namespace cic {
 
@@ -42,6 +48,199 @@ int tc_pick_block_k(const TcLayer& L) {
   return 64;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// raster kernel (tc_conv.cuh): build the tap program of a conv / transposed-conv layer
+// ------------------------------------------------------------------------------------------------
+struct TapDesc {
+  int dc, pz, dx, dy;  // TMA coordinate deltas (as TcTap)
+  int tap;             // index in the weight K order of its phase
+  int phase;
+};
+
+static void layer_taps(const TcLayer& L, std::vector<TapDesc>& taps) {
+  taps.clear();
+  if (L.kind == TC_DECONV_K4S2) {
+    for (int ph = 0; ph < 4; ++ph) {
+      const int py = ph >> 1, px = ph & 1;
+      for (int ty = 0; ty < 2; ++ty)
+        for (int tx = 0; tx < 2; ++tx) taps.push_back({0, 0, tx - (px == 0 ? 1 : 0), ty - (py == 0 ? 1 : 0), ty * 2 + tx, ph});
+    }
+    return;
+  }
+  for (int ky = 0; ky < L.kh; ++ky)
+    for (int kx = 0; kx < L.kw; ++kx) {
+      const int dy = ky - L.pad_t, dx = kx - L.pad_l;
+      if (L.kind == TC_CONV_S2) {
+        const int yb = dy >= 0 ? dy / 2 : -((-dy + 1) / 2), xb = dx >= 0 ? dx / 2 : -((-dx + 1) / 2);
+        taps.push_back({(dx - 2 * xb) * L.src[0].ld, dy - 2 * yb, xb, yb, ky * L.kw + kx, 0});
+      } else {
+        taps.push_back({0, 0, dx, dy, ky * L.kw + kx, 0});
+      }
+    }
+}
+
+// returns CIC_OK and sets *used = true when the layer was launched on the raster kernel; *used = false means
+// "not eligible, use the per-tap kernel"
+static int try_run_raster(const TcLayer& L, int BK, int N_pad, const TcMaps& act_maps_unused, cudaStream_t st, bool* used) {
+  (void)act_maps_unused;
+  *used = false;
+  const bool s2 = L.kind == TC_CONV_S2, dc = L.kind == TC_DECONV_K4S2;
+  static const int force = getenv("CIC_TC_RASTER") ? atoi(getenv("CIC_TC_RASTER")) : -1;  // 0: never, 1: whenever possible
+  if (force == 0) return CIC_OK;
+  if (L.b_batched || L.splits != 1 || L.epi.out_mode == TC_OUT_PARTIAL) return CIC_OK;
+  if (!dc && L.kh * L.kw == 1) return CIC_OK;  // 1x1 / dense: nothing to reuse
+  int BN = 0;
+  for (int bn = 256; bn >= 16; bn -= 16)
+    if (N_pad % bn == 0) { BN = bn; break; }
+  if (!BN) return CIC_OK;
+  const int parts = L.split ? 2 : 1;
+  const int b_slot_bytes = BN * 2 * BK * parts;
+  if (force != 1 && b_slot_bytes > 32768) return CIC_OK;  // wide, K-heavy layers are already tensor-bound on the per-tap kernel
+
+  TcvParams p;
+  memset(&p, 0, sizeof(p));
+  const int Ho = s2 ? L.H / 2 : L.H, Wo = s2 ? L.W / 2 : L.W;
+  pick_tile(Wo, Ho, L.batch, false, p.TW, p.TH, p.TB);
+  p.tiles_x = (Wo + p.TW - 1) / p.TW;
+  p.tiles_y = (Ho + p.TH - 1) / p.TH;
+  p.tiles_b = (L.batch + p.TB - 1) / p.TB;
+  p.Wo = Wo; p.Ho = Ho; p.batch = L.batch;
+  p.a5d = s2 ? 1 : 0;
+  p.nsrc = L.nsrc;
+  for (int s = 0; s < L.nsrc; ++s) { p.src_blocks[s] = L.src[s].C / BK; p.src_coff[s] = L.src[s].coff; }
+  p.N_pad = N_pad; p.BN = BN; p.n_tiles = N_pad / BN;
+
+  std::vector<TapDesc> taps;
+  layer_taps(L, taps);
+  const int nph = dc ? 4 : 1;
+  const bool fused = dc && p.n_tiles == 1 && 4 * BN <= TCV_ACC_COLS;
+  p.npass = fused ? 1 : nph;
+  const int mode = (p.TH == 1 && p.TB == 1) ? 0 : (p.TB == 1 ? 1 : 2);  // 0 ROW, 1 COL, 2 per tap
+
+  // pass -> its taps (acc = local phase index)
+  struct PTap { TapDesc t; int acc; };
+  std::vector<std::vector<PTap>> ptaps(p.npass);
+  for (const TapDesc& t : taps) {
+    const int ps = fused ? 0 : t.phase, acc = fused ? t.phase : 0;
+    ptaps[ps].push_back({t, acc});
+  }
+  // raster box: the maximum halo over all planes and passes
+  int ext_w = 0, ext_h = 0;
+  for (auto& pt : ptaps)
+    for (size_t i = 0; i < pt.size(); ++i)
+      for (size_t j = 0; j < pt.size(); ++j)
+        if (pt[i].t.dc == pt[j].t.dc && pt[i].t.pz == pt[j].t.pz) {
+          ext_w = std::max(ext_w, pt[i].t.dx - pt[j].t.dx);
+          ext_h = std::max(ext_h, pt[i].t.dy - pt[j].t.dy);
+        }
+  p.rw = mode == 0 ? p.TW + ext_w : p.TW;
+  p.rh = mode == 2 ? p.TH : p.TH + ext_h;
+  p.rb = p.TB;
+  if (p.rw > 256 || p.rh > 256) return CIC_OK;
+  int max_end = 0;
+  for (int ps = 0; ps < p.npass; ++ps) {
+    TcvPass& P = p.pass[ps];
+    P.nacc = fused ? 4 : 1;
+    for (int a = 0; a < P.nacc; ++a) P.phase_id[a] = (int8_t)(fused ? a : ps);
+    bool first_seen[4] = {false, false, false, false};
+    std::vector<PTap>& pt = ptaps[ps];
+    std::vector<bool> done(pt.size(), false);
+    int nops = 0;
+    for (size_t i = 0; i < pt.size(); ++i) {
+      if (done[i]) continue;
+      // raster key: the plane, plus dx (COL) or the tap itself (per tap)
+      std::vector<size_t> grp;
+      for (size_t j = i; j < pt.size(); ++j) {
+        if (done[j] || pt[j].t.dc != pt[i].t.dc || pt[j].t.pz != pt[i].t.pz) continue;
+        if (mode == 1 && pt[j].t.dx != pt[i].t.dx) continue;
+        if (mode == 2 && (pt[j].t.dx != pt[i].t.dx || pt[j].t.dy != pt[i].t.dy)) continue;
+        grp.push_back(j);
+      }
+      int dx0 = pt[grp[0]].t.dx, dy0 = pt[grp[0]].t.dy;
+      for (size_t j : grp) { dx0 = std::min(dx0, pt[j].t.dx); dy0 = std::min(dy0, pt[j].t.dy); }
+      if (P.nrast >= TCV_MAX_RASTERS || nops + (int)grp.size() > TCV_MAX_OPS) return CIC_OK;
+      TcvRaster& R = P.r[P.nrast++];
+      R.dc = (int16_t)pt[i].t.dc; R.pz = (int16_t)pt[i].t.pz; R.dx = (int16_t)dx0; R.dy = (int16_t)dy0;
+      R.op0 = (uint8_t)nops; R.nops = (uint8_t)grp.size();
+      for (size_t j : grp) {
+        TcvOp& o = P.op[nops++];
+        const int sh = (pt[j].t.dy - dy0) * p.rw + (pt[j].t.dx - dx0);
+        o.row_shift = (uint16_t)sh;
+        o.acc = (uint8_t)pt[j].acc;
+        o.tap = (uint8_t)pt[j].t.tap;
+        o.first = first_seen[pt[j].acc] ? 0 : 1;
+        first_seen[pt[j].acc] = true;
+        max_end = std::max(max_end, sh + TC_BM);
+        done[j] = true;
+      }
+    }
+  }
+  const long long mt = (long long)p.tiles_x * p.tiles_y * p.tiles_b;
+  const long long total = mt * p.npass * p.n_tiles;
+  if (total <= 0 || total >= 2147483647LL) return CIC_OK;
+  p.total_tiles = (int)total;
+  // shared-memory rings
+  const int raster_rows = p.rw * p.rh * p.rb;
+  const int a_rows = std::max(raster_rows, max_end);
+  const int a_half = ((a_rows * 2 * BK) + 1023) & ~1023;
+  p.a_slot_bytes = a_half * parts;
+  p.a_tx_bytes = (uint32_t)(raster_rows * 2 * BK * parts);
+  p.b_slot_bytes = b_slot_bytes;
+  p.b_tx_bytes = (uint32_t)b_slot_bytes;
+  const int budget = 212 * 1024;
+  p.b_slots = std::min(TCV_MAX_SLOTS, std::max(2, 65536 / b_slot_bytes));
+  p.a_slots = std::min(TCV_MAX_SLOTS, (budget - p.b_slots * p.b_slot_bytes) / p.a_slot_bytes);
+  if (p.a_slots < 2) return CIC_OK;
+
+  // tensor maps
+  TcMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  for (int s = 0; s < L.nsrc; ++s) {
+    const TcAct& a = L.src[s];
+    for (int part = 0; part < parts; ++part) {
+      const bf16* base = part ? a.lo : a.hi;
+      int rc;
+      if (!s2) {
+        const uint64_t dims[4] = {(uint64_t)a.ld, (uint64_t)L.W, (uint64_t)L.H, (uint64_t)L.batch};
+        const uint64_t str[3] = {(uint64_t)a.ld * 2, (uint64_t)L.W * a.ld * 2, (uint64_t)L.H * L.W * a.ld * 2};
+        const uint32_t box[4] = {(uint32_t)BK, (uint32_t)p.rw, (uint32_t)p.rh, (uint32_t)p.rb};
+        rc = tc_encode_map(&maps.a[s][part], base, 4, dims, str, box);
+      } else {
+        const uint64_t dims[5] = {(uint64_t)2 * a.ld, (uint64_t)L.W / 2, 2, (uint64_t)L.H / 2, (uint64_t)L.batch};
+        const uint64_t str[4] = {(uint64_t)2 * a.ld * 2, (uint64_t)L.W * a.ld * 2, (uint64_t)2 * L.W * a.ld * 2,
+                                 (uint64_t)L.H * L.W * a.ld * 2};
+        const uint32_t box[5] = {(uint32_t)BK, (uint32_t)p.rw, 1, (uint32_t)p.rh, (uint32_t)p.rb};
+        rc = tc_encode_map(&maps.a[s][part], base, 5, dims, str, box);
+      }
+      if (rc) return rc;
+    }
+  }
+  for (int part = 0; part < parts; ++part) {
+    const uint64_t dims[3] = {(uint64_t)L.w.K, (uint64_t)L.w.rows, (uint64_t)L.w.batches};
+    const uint64_t str[2] = {(uint64_t)L.w.row_stride * 2, (uint64_t)L.w.batch_stride * 2};
+    const uint32_t box[3] = {(uint32_t)BK, (uint32_t)BN, 1};
+    int rc = tc_encode_map(&maps.b[part], part ? L.w.lo : L.w.hi, 3, dims, str, box);
+    if (rc) return rc;
+  }
+  // epilogue
+  const TcEpilogue& e = L.epi;
+  TcEpi& pe = p.epi;
+  pe.bias = e.bias; pe.scale = e.scale; pe.shift = e.shift; pe.alpha = e.alpha; pe.act = e.act;
+  pe.out_mode = e.out_mode; pe.out_hi = e.out_hi; pe.out_lo = e.out_lo; pe.res_hi = e.res_hi; pe.res_lo = e.res_lo;
+  pe.N = L.N; pe.out_ld = e.out_ld ? e.out_ld : L.N; pe.out_coff = e.out_coff; pe.up2 = e.up2;
+  pe.Ho = Ho; pe.Wo = Wo;
+  pe.m_total = (long long)L.batch * Ho * Wo;
+  if (dc) {
+    for (int ph = 0; ph < 4; ++ph) { pe.out_y0[ph] = (int8_t)(ph >> 1); pe.out_x0[ph] = (int8_t)(ph & 1); }
+    pe.out_ys = 2; pe.out_xs = 2; pe.out_H = 2 * L.H; pe.out_W = 2 * L.W;
+  } else {
+    pe.out_ys = 1; pe.out_xs = 1; pe.out_H = Ho * (e.up2 ? 2 : 1); pe.out_W = Wo * (e.up2 ? 2 : 1);
+  }
+  *used = true;
+  return launch_tc_conv(maps, p, BK, L.split, st);
+}
+
 int tc_run_layer(const TcLayer& L, cudaStream_t st) {
   TcMaps maps;
   memset(&maps, 0, sizeof(maps));
@@ -60,6 +259,21 @@ int tc_run_layer(const TcLayer& L, cudaStream_t st) {
   CIC_REQUIRE(!L.split || L.w.lo, "tc layer: split mode needs the low part of the weights");
   CIC_REQUIRE(!s2 || (L.H % 2 == 0 && L.W % 2 == 0), "tc layer: stride-2 path needs even H, W");
   const int Ho = s2 ? L.H / 2 : L.H, Wo = s2 ? L.W / 2 : L.W;
+  {
+    const int n_pad = dc ? L.w.rows / 4 : L.w.rows;
+    const int cin = L.src[0].C + (L.nsrc > 1 ? L.src[1].C : 0);
+    CIC_REQUIRE((long long)(dc ? 4 : L.kh * L.kw) * cin == L.w.K, "tc layer: weight K=%d does not match taps x channels", L.w.K);
+    CIC_REQUIRE(L.epi.out_hi && L.N <= n_pad && n_pad % 16 == 0, "tc layer: bad output (N=%d, padded %d)", L.N, n_pad);
+    CIC_REQUIRE(L.w.row_stride % 8 == 0 && L.w.batch_stride % 8 == 0, "tc layer: B rows must be 16-byte aligned");
+    if (L.epi.out_mode == TC_OUT_BF16) {
+      const int ld = L.epi.out_ld ? L.epi.out_ld : L.N;
+      CIC_REQUIRE(L.N % 16 == 0 && ld % 8 == 0 && L.epi.out_coff % 8 == 0,
+                  "tc layer: bf16 output needs N %% 16 == 0 and 16-byte aligned records (N=%d, ld=%d, coff=%d)", L.N, ld, L.epi.out_coff);
+    }
+    bool used = false;
+    const int rc = try_run_raster(L, BK, n_pad, maps, st, &used);
+    if (rc || used) return rc;
+  }
   pick_tile(Wo, Ho, L.batch, L.b_batched, p.TW, p.TH, p.TB);
   p.tiles_x = (Wo + p.TW - 1) / p.TW;
   p.tiles_y = (Ho + p.TH - 1) / p.TH;
@@ -104,10 +318,10 @@ int tc_run_layer(const TcLayer& L, cudaStream_t st) {
           t.dy = (int16_t)(ty - (py == 0 ? 1 : 0));
           t.dx = (int16_t)(tx - (px == 0 ? 1 : 0));
         }
-      p.out_y0[ph] = (int8_t)py;
-      p.out_x0[ph] = (int8_t)px;
+      p.epi.out_y0[ph] = (int8_t)py;
+      p.epi.out_x0[ph] = (int8_t)px;
     }
-    p.out_ys = 2; p.out_xs = 2; p.out_H = 2 * L.H; p.out_W = 2 * L.W;
+    p.epi.out_ys = 2; p.epi.out_xs = 2; p.epi.out_H = 2 * L.H; p.epi.out_W = 2 * L.W;
   } else {
     p.ntaps = L.kh * L.kw;
     CIC_REQUIRE(p.ntaps <= TC_MAX_TAPS, "tc layer: too many taps");
@@ -124,7 +338,7 @@ int tc_run_layer(const TcLayer& L, cudaStream_t st) {
           t.dy = (int16_t)dy; t.dx = (int16_t)dx; t.dc = 0; t.pz = 0;
         }
       }
-    p.out_ys = 1; p.out_xs = 1; p.out_H = Ho * (L.epi.up2 ? 2 : 1); p.out_W = Wo * (L.epi.up2 ? 2 : 1);
+    p.epi.out_ys = 1; p.epi.out_xs = 1; p.epi.out_H = Ho * (L.epi.up2 ? 2 : 1); p.epi.out_W = Wo * (L.epi.up2 ? 2 : 1);
   }
   const int cpt = p.src_blocks[0] + (L.nsrc > 1 ? p.src_blocks[1] : 0);
   p.kblocks = p.ntaps * cpt;
@@ -134,6 +348,12 @@ int tc_run_layer(const TcLayer& L, cudaStream_t st) {
   p.N = L.N;
   p.N_pad = dc ? L.w.rows / 4 : L.w.rows;
   p.b_batched = L.b_batched ? 1 : 0;
+  {  // tile order: keep the larger operand's tiles adjacent in time so the smaller one is re-read from L2
+    double act_elems = 0;
+    for (int s = 0; s < L.nsrc; ++s) act_elems += (double)L.batch * L.H * L.W * L.src[s].C;
+    const double w_elems = (double)L.w.rows * L.w.K * L.w.batches;
+    p.m_fast = (!L.b_batched && w_elems > act_elems) ? 1 : 0;
+  }
   const int bn = tc_pick_block_n(p.N_pad, L.split, BK);
   CIC_REQUIRE(bn > 0 && L.N <= p.N_pad, "tc layer: N=%d (padded %d) has no supported tile", L.N, p.N_pad);
   CIC_REQUIRE(L.w.row_stride % 8 == 0 && L.w.batch_stride % 8 == 0, "tc layer: B rows must be 16-byte aligned");
@@ -154,10 +374,12 @@ int tc_run_layer(const TcLayer& L, cudaStream_t st) {
     CIC_REQUIRE(L.N % 16 == 0 && (bn >= 32 ? L.N % 32 == 0 : true) && ld % 8 == 0 && e.out_coff % 8 == 0,
                 "tc layer: bf16 output needs N %% 16 == 0 and 16-byte aligned records (N=%d, ld=%d, coff=%d)", L.N, ld, e.out_coff);
   }
-  p.bias = e.bias; p.scale = e.scale; p.shift = e.shift; p.alpha = e.alpha; p.act = e.act;
-  p.out_mode = e.out_mode; p.out_hi = e.out_hi; p.out_lo = e.out_lo; p.res_hi = e.res_hi; p.res_lo = e.res_lo;
-  p.out_ld = e.out_ld ? e.out_ld : L.N; p.out_coff = e.out_coff; p.up2 = e.up2;
-  p.m_total = (long long)L.batch * Ho * Wo;
+  TcEpi& pe = p.epi;
+  pe.bias = e.bias; pe.scale = e.scale; pe.shift = e.shift; pe.alpha = e.alpha; pe.act = e.act;
+  pe.out_mode = e.out_mode; pe.out_hi = e.out_hi; pe.out_lo = e.out_lo; pe.res_hi = e.res_hi; pe.res_lo = e.res_lo;
+  pe.N = L.N; pe.out_ld = e.out_ld ? e.out_ld : L.N; pe.out_coff = e.out_coff; pe.up2 = e.up2;
+  pe.Ho = Ho; pe.Wo = Wo;
+  pe.m_total = (long long)L.batch * Ho * Wo;
   return launch_tc_gemm(maps, p, bn, BK, L.split, st);
 }
 

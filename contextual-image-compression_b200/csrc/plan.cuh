@@ -96,6 +96,8 @@ struct Scope {  // RAII layer bracket
 int run_dense(const float* x, const float* kernel, const float* bias, const float* scale, const float* shift, float* y,
               int batch, int in_dim, int out_dim, int act, float* ws, size_t ws_floats, cudaStream_t st);
 void pack_deconv_phases(const float* k, int cout, int cin, std::vector<float>& out);
+int launch_conv_k4s2_c3(const float* x, const float* wgt, const float* bias, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo,
+                        float* out_f32, int batch, int H, int W, int act, cudaStream_t st);
 int launch_expand_bpp(const float* bpp, float* bpp_t, float* qs_t, int n_tiles, int tiles_per_img, cudaStream_t st);
 
 // named raw device buffers (packed bf16 weights of the tensor-core path)

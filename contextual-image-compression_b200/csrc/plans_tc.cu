@@ -255,19 +255,27 @@ static int encoder_core_tc(cic_plan* pl, Ctx& c, const float* img, float* latent
   const int H = pl->opts.img_h, W = pl->opts.img_w, C = pl->opts.img_c, L = pl->opts.latent_dim;
   const size_t px = (size_t)B * H * W;
   const size_t mk = c.arena.mark();
-  float* x1f = x1_f32 ? x1_f32 : c.arena.f32(px / 4 * 64);
   int rc;
-  // conv1 (3 -> 64, k4 s2) + LeakyReLU on the CUDA cores (K = 48: bandwidth-bound), then split to bf16 (:300-302)
-  if (!c.dry) {
-    Scope sc(c, "conv1", 2.0 * (px / 4) * 64 * 16 * C, 4.0 * (px * C + px / 4 * 64) + 4.0 * px / 4 * 64);
-    IGemmParams p{};
-    p.src[0] = ConvSrc{img, C, C, 0};
-    p.nsrc = 1; p.Cin = C; p.batch = B; p.H = H; p.W = W; p.Ho = H / 2; p.Wo = W / 2;
-    p.kh = 4; p.kw = 4; p.stride = 2; p.pad_t = same_pad_before(H, 4, 2); p.pad_l = same_pad_before(W, 4, 2);
-    p.Bmat = w.ptr("conv1/kernel"); p.N = 64; p.ldb = 64; p.bias = w.ptr("conv1/bias"); p.act = CIC_ACT_LRELU02; p.alpha = 1.f;
-    p.out = x1f; p.out_ld = 64; p.out_H = p.Ho; p.out_W = p.Wo; p.out_ys = p.out_xs = 1; p.splits = 1;
-    if ((rc = launch_igemm(p, c.st))) return rc;
-    if ((rc = tc_split_f32(x1f, sk.x1.hi, sk.x1.lo, px / 4 * 64, c.st))) return rc;
+  // conv1 (3 -> 64, k4 s2) + LeakyReLU: K = 48 cannot feed a tensor-core K block; a direct CUDA-core kernel writes
+  // the (hi, lo) bf16 pair the split-bf16 layers read (:300-302)
+  if (C == 3) {
+    if (!c.dry) {
+      Scope sc(c, "conv1", 2.0 * (px / 4) * 64 * 16 * C, 4.0 * px * C + 4.0 * px / 4 * 64);
+      if ((rc = launch_conv_k4s2_c3(img, w.ptr("conv1/kernel"), w.ptr("conv1/bias"), sk.x1.hi, sk.x1.lo, x1_f32, B, H, W, CIC_ACT_LRELU02, c.st))) return rc;
+    }
+  } else {
+    float* x1f = x1_f32 ? x1_f32 : c.arena.f32(px / 4 * 64);
+    if (!c.dry) {
+      Scope sc(c, "conv1", 2.0 * (px / 4) * 64 * 16 * C, 4.0 * (px * C + px / 4 * 64) + 4.0 * px / 4 * 64);
+      IGemmParams p{};
+      p.src[0] = ConvSrc{img, C, C, 0};
+      p.nsrc = 1; p.Cin = C; p.batch = B; p.H = H; p.W = W; p.Ho = H / 2; p.Wo = W / 2;
+      p.kh = 4; p.kw = 4; p.stride = 2; p.pad_t = same_pad_before(H, 4, 2); p.pad_l = same_pad_before(W, 4, 2);
+      p.Bmat = w.ptr("conv1/kernel"); p.N = 64; p.ldb = 64; p.bias = w.ptr("conv1/bias"); p.act = CIC_ACT_LRELU02; p.alpha = 1.f;
+      p.out = x1f; p.out_ld = 64; p.out_H = p.Ho; p.out_W = p.Wo; p.out_ys = p.out_xs = 1; p.splits = 1;
+      if ((rc = launch_igemm(p, c.st))) return rc;
+      if ((rc = tc_split_f32(x1f, sk.x1.hi, sk.x1.lo, px / 4 * 64, c.st))) return rc;
+    }
   }
   // conv2..conv3: k4 s2 + BN + LeakyReLU, 3-term split-bf16 (:304-312)
   if ((rc = conv_tc(c, "conv2", TC_CONV_S2, view(sk.x1, 64), nullptr, B, H / 2, W / 2, 4, 4, 2, mat(pl, "conv2", 16 * 64, 128), 128, true,

@@ -12,13 +12,16 @@ __device__ __forceinline__ TcvTile tcv_decode(const TcvParams& p, int t) {
   // N tiles fastest, then passes, then M tiles: every (pass, N tile) of one M tile re-reads the same rasters
   // back to back, so those re-reads hit L2
   TcvTile c;
-  c.n_tile = t % p.n_tiles;
-  const int r = t / p.n_tiles;
-  c.pass = r % p.npass;
-  const int m = r / p.npass;
-  c.ox0 = (m % p.tiles_x) * p.TW;
-  c.oy0 = ((m / p.tiles_x) % p.tiles_y) * p.TH;
-  c.b0 = (m / (p.tiles_x * p.tiles_y)) * p.TB;
+  uint32_t r, nt, m, ps, mx, my, q, mb;
+  p.fd_ntiles.divmod((uint32_t)t, r, nt);
+  p.fd_npass.divmod(r, m, ps);
+  p.fd_tx.divmod(m, q, mx);
+  p.fd_ty.divmod(q, mb, my);
+  c.n_tile = (int)nt;
+  c.pass = (int)ps;
+  c.ox0 = (int)mx * p.TW;
+  c.oy0 = (int)my * p.TH;
+  c.b0 = (int)mb * p.TB;
   return c;
 }
 
@@ -27,24 +30,49 @@ __device__ __forceinline__ uint32_t tcv_idesc(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 }
 
-template <int BK, bool SPLIT>
-__global__ void __launch_bounds__(192, 1)
+template <int BK, bool SPLIT, bool RESIDENT>
+__global__ void __launch_bounds__(224, 1)
 tc_conv_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcvParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* a_ring = smem;
   uint8_t* b_ring = smem + (size_t)p.a_slots * p.a_slot_bytes;
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(b_ring + (size_t)p.b_slots * p.b_slot_bytes);
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(b_ring + (size_t)(p.b_resident ? p.b_blocks : p.b_slots * p.b_group) * p.b_slot_bytes);
   uint64_t* a_empty = a_full + TCV_MAX_SLOTS;
   uint64_t* b_full = a_empty + TCV_MAX_SLOTS;
   uint64_t* b_empty = b_full + TCV_MAX_SLOTS;
   uint64_t* tmem_full_bar = b_empty + TCV_MAX_SLOTS;  // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;       // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint4* ops_tab = reinterpret_cast<uint4*>(tmem_empty_bar + 4);  // [TCV_MAX_PASS][TCV_MAX_OPS] {a_shift, b_off, d_off, flags}
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cpt = p.src_blocks[0] + p.src_blocks[1];  // channel blocks per tap
   constexpr uint32_t kRowBytes = 2 * BK;
+  const uint32_t b_blk_lo = (uint32_t)p.b_slot_bytes >> 4;  // one weight block in descriptor-address units (16 B)
+
+  // MMA op table: everything the issuing thread needs per op in one 16-byte shared-memory word
+  if (threadIdx.x < TCV_MAX_PASS * TCV_MAX_OPS) {
+    const int ps_i = threadIdx.x / TCV_MAX_OPS, oi = threadIdx.x % TCV_MAX_OPS;
+    if (ps_i < p.npass && oi < p.pass[ps_i].nops) {
+      const TcvPass& ps = p.pass[ps_i];
+      const TcvOp op = ps.op[oi];
+      uint32_t flags = op.first ? TCV_F_FIRST : 0;
+      for (int ri = 0; ri < ps.nrast; ++ri) {
+        if (oi == ps.r[ri].op0) flags |= TCV_F_NEW_RASTER;
+        if (oi == ps.r[ri].op0 + ps.r[ri].nops - 1) flags |= TCV_F_LAST_OF_RASTER;
+      }
+      uint32_t b_off;
+      if (p.b_resident) {
+        b_off = (uint32_t)((ps.phase_id[op.acc] * p.n_tiles * p.ntaps + op.tap) * cpt) * b_blk_lo;
+      } else {
+        if (oi % p.b_group == 0) flags |= TCV_F_NEW_BGROUP;
+        if (oi % p.b_group == p.b_group - 1 || oi == ps.nops - 1) flags |= TCV_F_LAST_OF_BGROUP;
+        b_off = (uint32_t)(oi % p.b_group) * b_blk_lo;
+      }
+      ops_tab[threadIdx.x] = make_uint4((uint32_t)op.row_shift * (kRowBytes >> 4), b_off, (uint32_t)(op.acc * p.BN), flags);
+    }
+  }
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&maps.a[0][0]);
@@ -71,19 +99,18 @@ tc_conv_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcvP
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===== TMA producer (warp-convergent; one elected lane issues) =====
-    uint32_t sa = 0, pa = 0, sb = 0, pb = 0;  // ring slot / phase of the next raster and weight block
+    // ===== raster (A) producer (warp-convergent; one elected lane issues) =====
+    uint32_t sa = 0, pa = 0;  // ring slot / phase of the next raster
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
       const TcvTile tc = tcv_decode(p, t);
       const TcvPass& ps = p.pass[tc.pass];
       const int nrast = ps.nrast;
-      const int brow0 = tc.n_tile * p.BN;
       for (int cb = 0; cb < cpt; ++cb) {
         const int src = cb >= p.src_blocks[0] ? 1 : 0;
         const int cbase = p.src_coff[src] + (src ? cb - p.src_blocks[0] : cb) * BK;
         for (int ri = 0; ri < nrast; ++ri) {
           const TcvRaster R = ps.r[ri];
-          mbar_wait(&a_empty[sa], pa ^ 1u);
+          mbar_wait_relaxed(&a_empty[sa], pa ^ 1u);
           if (elect_one()) {
             mbar_arrive_expect_tx(&a_full[sa], p.a_tx_bytes);
             uint8_t* a_hi = a_ring + (size_t)sa * p.a_slot_bytes;
@@ -99,17 +126,51 @@ tc_conv_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcvP
           }
           __syncwarp();
           if (++sa == (uint32_t)p.a_slots) { sa = 0; pa ^= 1u; }
-          for (int oi = 0; oi < R.nops; ++oi) {
-            const TcvOp op = ps.op[R.op0 + oi];
-            mbar_wait(&b_empty[sb], pb ^ 1u);
+        }
+      }
+    }
+  } else if (warp == 6) {
+    // ===== weight (B) producer =====
+    if (RESIDENT) {
+      // the whole layer: block index = ((phase * n_tiles + n_tile) * ntaps + tap) * cpt + cb, all on one barrier
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&b_full[0], p.b_tx_bytes * (uint32_t)p.b_blocks);
+        const int nph = p.b_blocks / (p.n_tiles * p.ntaps * cpt);
+        int blk = 0;
+        for (int ph = 0; ph < nph; ++ph)
+          for (int nt = 0; nt < p.n_tiles; ++nt)
+            for (int tap = 0; tap < p.ntaps; ++tap)
+              for (int cb = 0; cb < cpt; ++cb, ++blk) {
+                uint8_t* b_hi = b_ring + (size_t)blk * p.b_slot_bytes;
+                const int k = (tap * cpt + cb) * BK, row = ph * p.N_pad + nt * p.BN;
+                tma_load_3d(b_hi, &maps.b[0], &b_full[0], k, row, 0);
+                if (SPLIT) tma_load_3d(b_hi + (p.b_slot_bytes >> 1), &maps.b[1], &b_full[0], k, row, 0);
+              }
+      }
+      __syncwarp();
+    } else {
+      uint32_t sb = 0, pb = 0;
+      const int G = p.b_group;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const TcvTile tc = tcv_decode(p, t);
+        const TcvPass& ps = p.pass[tc.pass];
+        const int nops = ps.nops;
+        const int brow0 = tc.n_tile * p.BN;
+        for (int cb = 0; cb < cpt; ++cb) {
+          for (int o0 = 0; o0 < nops; o0 += G) {
+            const int cnt = min(G, nops - o0);
+            mbar_wait_relaxed(&b_empty[sb], pb ^ 1u);
             if (elect_one()) {
-              mbar_arrive_expect_tx(&b_full[sb], p.b_tx_bytes);
-              uint8_t* b_hi = b_ring + (size_t)sb * p.b_slot_bytes;
-              uint8_t* b_lo = b_hi + (p.b_slot_bytes >> 1);
-              const int k = (op.tap * cpt + cb) * BK;
-              const int row = ps.phase_id[op.acc] * p.N_pad + brow0;
-              tma_load_3d(b_hi, &maps.b[0], &b_full[sb], k, row, 0);
-              if (SPLIT) tma_load_3d(b_lo, &maps.b[1], &b_full[sb], k, row, 0);
+              mbar_arrive_expect_tx(&b_full[sb], p.b_tx_bytes * (uint32_t)cnt);
+              uint8_t* slot = b_ring + (size_t)sb * G * p.b_slot_bytes;
+              for (int j = 0; j < cnt; ++j) {
+                const TcvOp op = ps.op[o0 + j];
+                uint8_t* b_hi = slot + (size_t)j * p.b_slot_bytes;
+                const int k = (op.tap * cpt + cb) * BK;
+                const int row = ps.phase_id[op.acc] * p.N_pad + brow0;
+                tma_load_3d(b_hi, &maps.b[0], &b_full[sb], k, row, 0);
+                if (SPLIT) tma_load_3d(b_hi + (p.b_slot_bytes >> 1), &maps.b[1], &b_full[sb], k, row, 0);
+              }
             }
             __syncwarp();
             if (++sb == (uint32_t)p.b_slots) { sb = 0; pb ^= 1u; }
@@ -121,60 +182,74 @@ tc_conv_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcvP
     // ===== MMA issuer (warp-convergent; one elected lane issues) =====
     const uint32_t idesc = tcv_idesc(p.BN);
     const uint32_t a_ring_lo = (smem_u32(a_ring) & 0x3FFFF) >> 4, b_ring_lo = (smem_u32(b_ring) & 0x3FFFF) >> 4;
-    const uint32_t a_slot_lo = (uint32_t)p.a_slot_bytes >> 4, b_slot_lo = (uint32_t)p.b_slot_bytes >> 4;
-    uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
+    const uint32_t a_slot_lo = (uint32_t)p.a_slot_bytes >> 4, a_half_lo = a_slot_lo >> 1;
+    const uint32_t b_slot_lo = b_blk_lo * (uint32_t)p.b_group, b_half_lo = b_blk_lo >> 1;
+    const uint32_t n_aslots = (uint32_t)p.a_slots, n_bslots = (uint32_t)p.b_slots;
+    const uint32_t res_tile_stride = (uint32_t)(p.ntaps * cpt) * b_blk_lo;
+    constexpr bool resident = RESIDENT;
+    uint32_t sa = 0, pa = 0, sb = 0, pb = 0, b_base = 0;
     int lt = 0;
+    if (resident) {
+      mbar_wait(&b_full[0], 0);
+      tc_fence_after();
+    }
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++lt) {
       const TcvTile tc = tcv_decode(p, t);
       const TcvPass& ps = p.pass[tc.pass];
       const int nrast = ps.nrast;
+      const uint4* tab = ops_tab + tc.pass * TCV_MAX_OPS;
       const int as = lt & 1;
       mbar_wait(&tmem_empty_bar[as], (((uint32_t)lt >> 1) & 1u) ^ 1u);
       tc_fence_after();
       const uint32_t d0 = tmem_base + (uint32_t)(as * TCV_ACC_COLS);
+      uint32_t b_cb = b_ring_lo + (uint32_t)tc.n_tile * res_tile_stride;  // resident: block (phase 0, n_tile, tap 0, cb)
       for (int cb = 0; cb < cpt; ++cb) {
+        const uint32_t fresh_mask = cb == 0 ? (uint32_t)TCV_F_FIRST : 0u;
         for (int ri = 0; ri < nrast; ++ri) {
-          const TcvRaster R = ps.r[ri];
+          const int op0 = ps.r[ri].op0, op1 = op0 + ps.r[ri].nops;
           mbar_wait(&a_full[sa], pa);
           tc_fence_after();
-          const uint32_t a_hi0 = a_ring_lo + sa * a_slot_lo;
-          const uint32_t a_lo0 = a_hi0 + (a_slot_lo >> 1);
-          for (int oi = 0; oi < R.nops; ++oi) {
-            const TcvOp op = ps.op[R.op0 + oi];
-            mbar_wait(&b_full[sb], pb);
-            tc_fence_after();
-            if (elect_one()) {
-              const uint32_t b_hi = b_ring_lo + sb * b_slot_lo;
-              const uint32_t b_lo = b_hi + (b_slot_lo >> 1);
-              const uint32_t sh = (uint32_t)op.row_shift * (kRowBytes >> 4);
-              const uint32_t a_hi = a_hi0 + sh, a_lo = a_lo0 + sh;
-              const uint32_t d = d0 + (uint32_t)(op.acc * p.BN);
-              const uint32_t keep = (cb == 0 && op.first) ? 0u : 1u;
-#pragma unroll
-              for (int k = 0; k < BK / 16; ++k)
-                umma_bf16(d, umma_desc_from_lo<BK>(a_hi + 2 * k), umma_desc_from_lo<BK>(b_hi + 2 * k), idesc, k == 0 ? keep : 1u);
-              if (SPLIT) {
-#pragma unroll
-                for (int k = 0; k < BK / 16; ++k)
-                  umma_bf16(d, umma_desc_from_lo<BK>(a_lo + 2 * k), umma_desc_from_lo<BK>(b_hi + 2 * k), idesc, 1u);
-#pragma unroll
-                for (int k = 0; k < BK / 16; ++k)
-                  umma_bf16(d, umma_desc_from_lo<BK>(a_hi + 2 * k), umma_desc_from_lo<BK>(b_lo + 2 * k), idesc, 1u);
+          if (elect_one()) {
+            // one thread issues every MMA of this raster back to back (sb / pb / b_base live in this lane only)
+            const uint32_t a_base = a_ring_lo + sa * a_slot_lo;
+            for (int i = op0; i < op1; ++i) {
+              const uint4 o = tab[i];
+              if (!resident && (o.w & TCV_F_NEW_BGROUP)) {
+                mbar_wait(&b_full[sb], pb);
+                tc_fence_after();
+                b_base = b_ring_lo + sb * b_slot_lo;
               }
-              umma_commit(&b_empty[sb]);
+              const uint32_t a_hi = a_base + o.x, b_hi = (resident ? b_cb : b_base) + o.y, d = d0 + o.z;
+              const uint32_t keep = (o.w & fresh_mask) ? 0u : 1u;
+              {
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k)
+                  umma_bf16(d, umma_desc_from_lo<BK>(a_hi + 2 * k), umma_desc_from_lo<BK>(b_hi + 2 * k), idesc, k == 0 ? keep : 1u);
+                if (SPLIT) {
+#pragma unroll
+                  for (int k = 0; k < BK / 16; ++k)
+                    umma_bf16(d, umma_desc_from_lo<BK>(a_hi + a_half_lo + 2 * k), umma_desc_from_lo<BK>(b_hi + 2 * k), idesc, 1u);
+#pragma unroll
+                  for (int k = 0; k < BK / 16; ++k)
+                    umma_bf16(d, umma_desc_from_lo<BK>(a_hi + 2 * k), umma_desc_from_lo<BK>(b_hi + b_half_lo + 2 * k), idesc, 1u);
+                }
+              }
+              if (!resident && (o.w & TCV_F_LAST_OF_BGROUP)) {
+                umma_commit(&b_empty[sb]);
+                if (++sb == n_bslots) { sb = 0; pb ^= 1u; }
+              }
             }
-            __syncwarp();
-            if (++sb == (uint32_t)p.b_slots) { sb = 0; pb ^= 1u; }
+            umma_commit(&a_empty[sa]);  // raster slot is free once all of its MMAs have retired
           }
-          if (elect_one()) umma_commit(&a_empty[sa]);  // raster slot is free once all of its MMAs have retired
           __syncwarp();
-          if (++sa == (uint32_t)p.a_slots) { sa = 0; pa ^= 1u; }
+          if (++sa == n_aslots) { sa = 0; pa ^= 1u; }
         }
+        b_cb += b_blk_lo;  // resident: next channel block of every tap
       }
       if (elect_one()) umma_commit(&tmem_full_bar[as]);
       __syncwarp();
     }
-  } else {
+  } else if (warp >= 2 && warp <= 5) {
     // ===== epilogue: 4 warps, warp w owns TMEM lanes 32*(w%4).. =====
     const int q = warp & 3;
     const int r = q * 32 + lane;
@@ -187,7 +262,7 @@ tc_conv_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcvP
       const int as = lt & 1;
       const int ox = tc.ox0 + xl, oy = tc.oy0 + yl, b = tc.b0 + bl;
       const bool valid = (bl < p.TB) && ox < p.Wo && oy < p.Ho && b < p.batch;
-      mbar_wait(&tmem_full_bar[as], ((uint32_t)lt >> 1) & 1u);
+      mbar_wait_relaxed(&tmem_full_bar[as], ((uint32_t)lt >> 1) & 1u);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * TCV_ACC_COLS);
       const int chunks = wide ? p.BN / 32 : p.BN / 16;
@@ -224,24 +299,25 @@ tc_conv_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcvP
 }
 
 size_t tcv_smem_bytes(const TcvParams& p) {
-  size_t n = (size_t)p.a_slots * p.a_slot_bytes + (size_t)p.b_slots * p.b_slot_bytes + 1024 /*align*/ + 512 /*barriers*/;
+  size_t n = (size_t)p.a_slots * p.a_slot_bytes + (size_t)(p.b_resident ? p.b_blocks : p.b_slots * p.b_group) * p.b_slot_bytes +
+             1024 /*align*/ + 2048 /*barriers + op table*/;
   // the kernel allocates all 512 TMEM columns: keep it to one CTA per SM whatever the ring sizes are
   const size_t floor_bytes = 120 * 1024;
   return n < floor_bytes ? floor_bytes : n;
 }
 
-template <int BK, bool SPLIT>
+template <int BK, bool SPLIT, bool RESIDENT>
 static int launch_conv_one(const TcMaps& maps, const TcvParams& p, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    CIC_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<BK, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CIC_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<BK, SPLIT, RESIDENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   const size_t smem = tcv_smem_bytes(p);
   CIC_REQUIRE(smem <= 227 * 1024, "tc_conv: %zu bytes of shared memory needed", smem);
   const int slots = sm_count();
   const int grid = p.total_tiles < slots ? p.total_tiles : slots;
-  tc_conv_kernel<BK, SPLIT><<<grid, 192, smem, st>>>(maps, p);
+  tc_conv_kernel<BK, SPLIT, RESIDENT><<<grid, 224, smem, st>>>(maps, p);
   CIC_COUNT_LAUNCH();
   CIC_CHECK_LAUNCH("tc_conv_kernel");
   return CIC_OK;
@@ -250,12 +326,21 @@ static int launch_conv_one(const TcMaps& maps, const TcvParams& p, cudaStream_t 
 int launch_tc_conv(const TcMaps& maps, const TcvParams& p, int block_k, bool split, cudaStream_t st) {
   CIC_REQUIRE(p.total_tiles > 0 && p.npass >= 1 && p.npass <= TCV_MAX_PASS, "tc_conv: bad tile list");
   CIC_REQUIRE(p.BN % 16 == 0 && p.BN >= 16 && p.BN <= TCV_ACC_COLS, "tc_conv: bad accumulator width %d", p.BN);
-  CIC_REQUIRE(p.a_slots >= 2 && p.a_slots <= TCV_MAX_SLOTS && p.b_slots >= 2 && p.b_slots <= TCV_MAX_SLOTS, "tc_conv: bad ring sizes");
+  CIC_REQUIRE(p.a_slots >= 2 && p.a_slots <= TCV_MAX_SLOTS && (p.b_resident || (p.b_slots >= 2 && p.b_slots <= TCV_MAX_SLOTS)),
+              "tc_conv: bad ring sizes");
+  CIC_REQUIRE(p.b_resident || (p.b_group >= 1 && p.b_group <= TCV_MAX_OPS), "tc_conv: bad weight group");
   for (int i = 0; i < p.npass; ++i)
-    CIC_REQUIRE(p.pass[i].nacc >= 1 && p.pass[i].nacc * p.BN <= TCV_ACC_COLS && p.pass[i].nrast >= 1 && p.pass[i].nrast <= TCV_MAX_RASTERS,
+    CIC_REQUIRE(p.pass[i].nops >= 1 && p.pass[i].nops <= TCV_MAX_OPS && p.pass[i].nacc >= 1 && p.pass[i].nacc * p.BN <= TCV_ACC_COLS && p.pass[i].nrast >= 1 && p.pass[i].nrast <= TCV_MAX_RASTERS,
                 "tc_conv: bad pass %d", i);
-  if (block_k == 64) return split ? launch_conv_one<64, true>(maps, p, st) : launch_conv_one<64, false>(maps, p, st);
-  if (block_k == 32) return split ? launch_conv_one<32, true>(maps, p, st) : launch_conv_one<32, false>(maps, p, st);
+  const bool res = p.b_resident != 0;
+  if (block_k == 64) {
+    if (split) return res ? launch_conv_one<64, true, true>(maps, p, st) : launch_conv_one<64, true, false>(maps, p, st);
+    return res ? launch_conv_one<64, false, true>(maps, p, st) : launch_conv_one<64, false, false>(maps, p, st);
+  }
+  if (block_k == 32) {
+    if (split) return res ? launch_conv_one<32, true, true>(maps, p, st) : launch_conv_one<32, true, false>(maps, p, st);
+    return res ? launch_conv_one<32, false, true>(maps, p, st) : launch_conv_one<32, false, false>(maps, p, st);
+  }
   set_error("tc_conv: unsupported K block %d", block_k);
   return CIC_ERR_INVALID;
 }

@@ -15,9 +15,12 @@
 // input is read once for all of them.  Stride-2 convs use the 5-D parity view of tc_gemm.cuh, one raster set
 // per parity plane.
 //
-// Pipeline: persistent CTAs (one per SM); warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = epilogue.
-// A rasters and B (weight) blocks travel in separate mbarrier rings because one raster feeds many MMAs;
-// the accumulator (up to 256 columns per stage) is double-buffered in TMEM.
+// Pipeline: persistent CTAs (one per SM), 224 threads: warp 0 = raster (A) producer, warp 6 = weight (B)
+// producer, warp 1 = MMA issuer, warps 2-5 = epilogue.  A rasters and B blocks travel in separate mbarrier
+// rings filled by separate warps, because one raster feeds many MMAs and the raster of the next tile must be
+// in flight long before the last weight block of this one is issued.  When the whole weight matrix of the
+// layer fits beside the raster ring it is loaded once and stays resident (no per-MMA weight traffic at all).
+// The accumulator (up to 256 columns per stage) is double-buffered in TMEM.
 #pragma once
 #include "tc_gemm.cuh"
 
@@ -26,7 +29,7 @@ namespace cic {
 constexpr int TCV_MAX_RASTERS = 16;
 constexpr int TCV_MAX_OPS = 16;
 constexpr int TCV_MAX_PASS = 4;
-constexpr int TCV_MAX_SLOTS = 8;
+constexpr int TCV_MAX_SLOTS = 16;
 constexpr int TCV_ACC_COLS = 256;  // TMEM columns per accumulator stage
 
 struct TcvRaster {
@@ -45,17 +48,43 @@ struct TcvOp {
   uint8_t pad_[3];
 };
 
+// flags of the MMA op table the kernel builds in shared memory
+enum { TCV_F_FIRST = 1, TCV_F_NEW_RASTER = 2, TCV_F_LAST_OF_RASTER = 4, TCV_F_NEW_BGROUP = 8, TCV_F_LAST_OF_BGROUP = 16 };
+
 struct TcvPass {
   int nrast;
+  int nops;
   int nacc;               // accumulators (output phases) of this pass
   int8_t phase_id[4];     // global phase of each accumulator (weight row block, output offset)
   TcvRaster r[TCV_MAX_RASTERS];
   TcvOp op[TCV_MAX_OPS];
 };
 
+// division by a runtime constant as multiply-high + shift (the tile decode runs once per tile in three warps;
+// six hardware divisions there cost ~1000 cycles of dependent issue)
+struct FastDiv {
+  uint32_t d, mul, shr;
+#ifdef __CUDACC__
+  __device__ __forceinline__ void divmod(uint32_t n, uint32_t& q, uint32_t& r) const {
+    q = d == 1 ? n : (__umulhi(n, mul) >> shr);
+    r = n - q * d;
+  }
+#endif
+};
+inline FastDiv make_fastdiv(uint32_t d) {  // exact for n < 2^31
+  FastDiv f{d, 0, 0};
+  if (d <= 1) return f;
+  uint32_t l = 0;
+  while ((1ull << l) < d) ++l;
+  f.shr = l - 1;
+  f.mul = (uint32_t)(((1ull << (32 + l - 1)) + d - 1) / d);
+  return f;
+}
+
 struct TcvParams {
   int TW, TH, TB;
   int tiles_x, tiles_y, tiles_b;
+  FastDiv fd_ntiles, fd_npass, fd_tx, fd_ty;
   int Wo, Ho, batch;
   int a5d;
   int nsrc;
@@ -67,9 +96,13 @@ struct TcvParams {
   int BN;                 // accumulator width = MMA N (multiple of 16, <= 256, BN * nacc <= 256)
   int n_tiles;            // N tiles per phase (N_pad / BN)
   int total_tiles;        // M tiles x npass x n_tiles
+  int ntaps;              // taps per phase in the weight K order
+  int b_resident;         // 1: all weight blocks live in shared memory for the whole kernel
+  int b_blocks;           // resident blocks: nphases x n_tiles x ntaps x channel blocks
   int a_slots, b_slots;
   int a_slot_bytes;       // per slot; in split mode [hi raster | lo raster], each a_slot_bytes / 2
-  int b_slot_bytes;       // per slot; in split mode [hi | lo]
+  int b_slot_bytes;       // one weight block [BN x BK]; in split mode [hi | lo]
+  int b_group;            // weight blocks per ring slot (loaded under one mbarrier); ring slot = b_group * b_slot_bytes
   uint32_t a_tx_bytes, b_tx_bytes;
   TcEpi epi;
   TcvPass pass[TCV_MAX_PASS];

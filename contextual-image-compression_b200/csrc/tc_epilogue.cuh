@@ -103,13 +103,15 @@ __device__ __forceinline__ void tc_epilogue_store(const TcEpi& e, const TcRow& r
 #pragma unroll
       for (int j = 0; j < CH; ++j) f[j] = fmaxf(f[j], __fmul_rn(f[j], 0.2f));
       break;
-    case CIC_ACT_SIGMOID:
-#pragma unroll 4
-      for (int j = 0; j < CH; ++j) f[j] = j < nv ? 1.f / (1.f + expf(-f[j])) : 0.f;
+    case CIC_ACT_SIGMOID:  // fully unrolled (register-resident f[]); only the valid channels are evaluated
+#pragma unroll
+      for (int j = 0; j < CH; ++j)
+        if (j < nv) f[j] = 1.f / (1.f + expf(-f[j]));
       break;
     case CIC_ACT_TANH:
-#pragma unroll 4
-      for (int j = 0; j < CH; ++j) f[j] = j < nv ? tanhf(f[j]) : 0.f;
+#pragma unroll
+      for (int j = 0; j < CH; ++j)
+        if (j < nv) f[j] = tanhf(f[j]);
       break;
     default: break;
   }

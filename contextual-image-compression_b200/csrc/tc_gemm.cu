@@ -92,7 +92,7 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       const int bz = p.b_batched ? tc.b0 : 0;
       int tap = tc.kb0 / cpt, ch = tc.kb0 % cpt;
       for (int i = 0; i < tc.nkb; ++i) {
-        mbar_wait(&empty_bar[s], ph ^ 1u);
+        mbar_wait_relaxed(&empty_bar[s], ph ^ 1u);
         if (elect_one()) {
           mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
           const int kb = tc.kb0 + i;
@@ -169,7 +169,7 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       const int as = lt & 1;
       const int ox = tc.ox0 + xl, oy = tc.oy0 + yl, b = tc.b0 + bl;
       const bool valid = (bl < p.TB) && ox < p.Wo && oy < p.Ho && b < p.batch;
-      mbar_wait(&tmem_full_bar[as], ((uint32_t)lt >> 1) & 1u);
+      mbar_wait_relaxed(&tmem_full_bar[as], ((uint32_t)lt >> 1) & 1u);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
       const TcRow row{b, oy, ox, tc.phase, tc.split};

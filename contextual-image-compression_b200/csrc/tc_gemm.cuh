@@ -107,6 +107,27 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// Same wait for warps that are not on the critical path (epilogue, producers): the try_wait carries a
+// suspend-time hint so the warp sleeps in hardware instead of hot-polling the scheduler it shares with the
+// MMA-issuing warp.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok;
+  long long t0 = 0;
+  for (uint32_t it = 0;; ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity), "r"(20000u)
+        : "memory");
+    if (ok) return;
+    if (it == 64) t0 = clock64();
+    if (it > 64 && (it & 63) == 0 && clock64() - t0 > 4000000000LL) __trap();  // ~2 s
+  }
+}
+
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }

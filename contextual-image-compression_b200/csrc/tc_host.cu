@@ -163,6 +163,7 @@ static int try_run_raster(const TcLayer& L, int BK, int N_pad, const TcMaps& act
       TcvRaster& R = P.r[P.nrast++];
       R.dc = (int16_t)pt[i].t.dc; R.pz = (int16_t)pt[i].t.pz; R.dx = (int16_t)dx0; R.dy = (int16_t)dy0;
       R.op0 = (uint8_t)nops; R.nops = (uint8_t)grp.size();
+      P.nops = nops + (int)grp.size();
       for (size_t j : grp) {
         TcvOp& o = P.op[nops++];
         const int sh = (pt[j].t.dy - dy0) * p.rw + (pt[j].t.dx - dx0);
@@ -188,9 +189,28 @@ static int try_run_raster(const TcLayer& L, int BK, int N_pad, const TcMaps& act
   p.a_tx_bytes = (uint32_t)(raster_rows * 2 * BK * parts);
   p.b_slot_bytes = b_slot_bytes;
   p.b_tx_bytes = (uint32_t)b_slot_bytes;
-  const int budget = 212 * 1024;
-  p.b_slots = std::min(TCV_MAX_SLOTS, std::max(2, 65536 / b_slot_bytes));
-  p.a_slots = std::min(TCV_MAX_SLOTS, (budget - p.b_slots * p.b_slot_bytes) / p.a_slot_bytes);
+  const int budget = 220 * 1024;
+  p.ntaps = dc ? 4 : L.kh * L.kw;
+  p.b_blocks = nph * p.n_tiles * p.ntaps * (p.src_blocks[0] + p.src_blocks[1]);
+  const long long resident_bytes = (long long)p.b_blocks * b_slot_bytes;
+  static const int no_resident = getenv("CIC_TC_NO_RESIDENT") ? atoi(getenv("CIC_TC_NO_RESIDENT")) : 0;
+  if (!no_resident && resident_bytes <= budget - 2LL * p.a_slot_bytes && resident_bytes <= 96 * 1024 &&
+      resident_bytes * 148 < (long long)p.total_tiles * 16 * b_slot_bytes) {
+    // the whole weight matrix stays in shared memory (only when that is less traffic than streaming it)
+    p.b_resident = 1;
+    p.b_slots = 0;
+    p.a_slots = std::min(8, (int)((budget - resident_bytes) / p.a_slot_bytes));
+  } else {
+    // weight blocks travel in groups of up to 16 KB under one barrier (one wait per group in the MMA warp)
+    p.b_group = std::max(1, std::min(4, 16384 / b_slot_bytes));
+    const int gbytes = p.b_group * b_slot_bytes;
+    p.b_slots = std::min(TCV_MAX_SLOTS, std::max(2, 65536 / gbytes));
+    p.a_slots = std::min(8, (budget - p.b_slots * gbytes) / p.a_slot_bytes);
+    if (p.a_slots < 2) {  // big rasters: give the weight ring less
+      p.b_slots = std::max(2, std::min(TCV_MAX_SLOTS, (budget - 2 * p.a_slot_bytes) / gbytes));
+      p.a_slots = (budget - p.b_slots * gbytes) / p.a_slot_bytes;
+    }
+  }
   if (p.a_slots < 2) return CIC_OK;
 
   // tensor maps
@@ -237,6 +257,10 @@ static int try_run_raster(const TcLayer& L, int BK, int N_pad, const TcMaps& act
   } else {
     pe.out_ys = 1; pe.out_xs = 1; pe.out_H = Ho * (e.up2 ? 2 : 1); pe.out_W = Wo * (e.up2 ? 2 : 1);
   }
+  p.fd_ntiles = make_fastdiv((uint32_t)p.n_tiles);
+  p.fd_npass = make_fastdiv((uint32_t)p.npass);
+  p.fd_tx = make_fastdiv((uint32_t)p.tiles_x);
+  p.fd_ty = make_fastdiv((uint32_t)p.tiles_y);
   *used = true;
   return launch_tc_conv(maps, p, BK, L.split, st);
 }

@@ -168,6 +168,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("CIC_PRECISION", "tc"), choices=["tc", "fp32"])
     ap.add_argument("--images", type=int, default=IMGS_PER_GPU, help="512x512 images per GPU per step")
+    ap.add_argument("--e2e-chunks", type=int, default=8, help="chunks of the batch in the pipelined end-to-end leg")
     ap.add_argument("--cpu-tiles", type=int, default=8, help="tiles in the CPU-oracle sample (0 = skip)")
     ap.add_argument("--profile-csv", default=None, help="write the per-layer device times of the last timed step here")
     args = ap.parse_args()
@@ -216,9 +217,21 @@ def main():
         outs = am.forward_device([d_img, d_mask, d_bpp], extras=False)
         return evaluate(d_img, am.last)
 
+    def evaluate_chunk(d_in, outs):
+        """Per-chunk metric sums (no all-reduce): runs on the compute stream inside the pipelined predict."""
+        k = d_in[0].shape[0]
+        m = cic.ops.metrics_f32(d_in[0], outs["blended"], signed_range=True)
+        hq_ratio = outs["hq_ratio_sum"] / float(IMG_HW * IMG_HW)
+        actual_bpp = (hq_ratio * (2 * BASE_LATENT) + (1.0 - hq_ratio) * BASE_LATENT) * 32.0 / (TILE * TILE)
+        sums = torch.zeros((1, nfields), dtype=torch.float64, device=dev)
+        sums[0, 0], sums[0, 1], sums[0, 2] = m[:, 0].sum(), m[:, 1].sum(), m[:, 2].sum()
+        sums[0, 3], sums[0, 4], sums[0, 6] = actual_bpp.sum(), hq_ratio.sum(), float(k)
+        return sums
+
     def step_e2e():
-        outs = am.predict([h_img, h_mask, h_bpp], verbose=0, reuse_output_buffers=True)   # H2D + model + D2H of all 5 outputs
-        sums = evaluate(am._last_inputs[0], am.last)
+        # pinned host buffers -> (H2D | model + metrics | D2H of all 5 outputs) pipelined over chunks of the batch
+        outs, parts = am.predict_pipelined([h_img, h_mask, h_bpp], n_chunks=args.e2e_chunks, on_chunk=evaluate_chunk)
+        sums = cic.dist.allreduce_metric_sums(torch.stack(parts).sum(0))
         return outs, sums.cpu()
 
     plan = am.plan()

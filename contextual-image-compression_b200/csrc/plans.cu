@@ -531,16 +531,23 @@ int rd_forward_f32(cic_plan* pl, Ctx& c, const float* mask, const float* bpp, fl
                       CIC_ACT_LRELU02, r1))) return rc;                                                   // :511-512
   if ((rc = conv_same(c, "conv2", one(r1, 32), B, h2, w2, w.ptr("conv2/kernel"), 3, 3, 2, 64, w.ptr("conv2/bias"), nullptr, nullptr,
                       CIC_ACT_LRELU02, r2))) return rc;                                                   // :513-514
+  if (!c.dry && (rc = launch_global_avg_pool(r2, feat, B, h4 * w4, 64, 65, c.st))) return rc;             // :515
+  return launch_rd_tail(pl, c, bpp, feat, d1, base, rd_params, B);
+}
+
+// concat clip(bpp/5) (:518) -> Dense128 LReLU (:521-522) -> Dense3 (:525) -> three biased sigmoids (:529-541)
+int launch_rd_tail(cic_plan* pl, Ctx& c, const float* bpp, float* feat, float* d1, float* base, float* rd_params, int B) {
+  const WeightStore& w = pl->w;
+  int rc;
   if (!c.dry) {
-    if ((rc = launch_global_avg_pool(r2, feat, B, h4 * w4, 64, 65, c.st))) return rc;                     // :515
-    rd_set_t_kernel<<<(B + 127) / 128, 128, 0, c.st>>>(bpp, feat, B, 65, 64);                              // :518
+    rd_set_t_kernel<<<(B + 127) / 128, 128, 0, c.st>>>(bpp, feat, B, 65, 64);
     CIC_COUNT_LAUNCH();
     CIC_CHECK_LAUNCH("rd_set_t_kernel");
   }
-  if ((rc = dense(c, "dense1", feat, w.ptr("dense1/kernel"), w.ptr("dense1/bias"), nullptr, nullptr, d1, B, 65, 128, CIC_ACT_LRELU02))) return rc;  // :521-522
-  if ((rc = dense(c, "dense2", d1, w.ptr("dense2/kernel"), w.ptr("dense2/bias"), nullptr, nullptr, base, B, 128, 3, CIC_ACT_NONE))) return rc;      // :525
+  if ((rc = dense(c, "dense1", feat, w.ptr("dense1/kernel"), w.ptr("dense1/bias"), nullptr, nullptr, d1, B, 65, 128, CIC_ACT_LRELU02))) return rc;
+  if ((rc = dense(c, "dense2", d1, w.ptr("dense2/kernel"), w.ptr("dense2/bias"), nullptr, nullptr, base, B, 128, 3, CIC_ACT_NONE))) return rc;
   if (!c.dry) {
-    rd_finalize_kernel<<<(B + 127) / 128, 128, 0, c.st>>>(base, bpp, rd_params, B);                        // :529-541
+    rd_finalize_kernel<<<(B + 127) / 128, 128, 0, c.st>>>(base, bpp, rd_params, B);
     CIC_COUNT_LAUNCH();
     CIC_CHECK_LAUNCH("rd_finalize_kernel");
   }
@@ -753,7 +760,8 @@ static int dispatch(cic_plan* pl, Ctx& c, int batch, int h, int w, const void* a
     case CIC_PLAN_SALIENCY:
       return saliency_forward_f32(pl, c, (const float*)a0, (float*)o0, batch);
     case CIC_PLAN_RD:
-      return rd_forward_f32(pl, c, (const float*)a0, (const float*)a1, (float*)o0, batch);
+      return tc ? rd_forward_tc(pl, c, (const float*)a0, (const float*)a1, (float*)o0, batch)
+                : rd_forward_f32(pl, c, (const float*)a0, (const float*)a1, (float*)o0, batch);
     case CIC_PLAN_ADAPTIVE: {
       const cic_adaptive_io* io = (const cic_adaptive_io*)a0;
       return tc ? adaptive_forward_tc(pl, c, io, batch, h, w) : adaptive_forward_f32(pl, c, io, batch, h, w);

@@ -107,7 +107,10 @@ int build_plan_tc(cic_plan* pl, const cic_tensor* tensors, int n, const std::str
       if (pl->opts.img_c <= 16) rc = pack(pl, "conv_out", w.ptr("conv_out/kernel"), 16 * 32, pl->opts.img_c, 16, false);
       break;
     }
-    default: break;  // saliency / RD networks stay fp32
+    case CIC_PLAN_RD:  // conv2 (32 -> 64, k3 s2) on the tensor cores, split-bf16 (rd_params are compared at 2e-5)
+      rc = pack(pl, "conv2", w.ptr("conv2/kernel"), 9 * 32, 64, 64, true);
+      break;
+    default: break;  // the saliency MLPs stay fp32
   }
   if (rc) return rc;
   CIC_CHECK_CUDA(cudaDeviceSynchronize());
@@ -380,10 +383,69 @@ int generator_forward_tc(cic_plan* pl, Ctx& c, const float* latent, const float*
   return generator_core_tc(pl, c, latent, b1.hi, b2.hi, b3.hi, out, B);
 }
 
-// ---- autoencoder ------------------------------------------------------------------------------
+// ---- autoencoder (train_autoencoder.py:9-40), single-pass bf16 ------------------------------------------
 int autoencoder_forward_tc(cic_plan* pl, Ctx& c, const float* x, float* y, uint8_t* y_u8, int B, int H, int W) {
-  // first cut: the fp32 CUDA-core walker (the tcgen05 autoencoder walker replaces this)
-  return autoencoder_forward_f32(pl, c, x, y, y_u8, B, H, W);
+  const WeightStore& w = pl->w;
+  const int C = pl->opts.img_c;
+  if (C != 3) return autoencoder_forward_f32(pl, c, x, y, y_u8, B, H, W);  // the direct first layer is written for 3 channels
+  const size_t px = (size_t)B * H * W;
+  const size_t mk = c.arena.mark();
+  ActBuf x1 = alloc_act(c, px * 32, false), x1p = alloc_act(c, px / 4 * 32, false), x2 = alloc_act(c, px / 4 * 64, false);
+  ActBuf enc = alloc_act(c, px / 16 * 64, false), y3u = alloc_act(c, px / 4 * 64, false), x2r = alloc_act(c, px / 4 * 64, false);
+  ActBuf y5u = alloc_act(c, px * 32, false), x1r = alloc_act(c, px * 32, false);
+  int rc;
+  if (!c.dry) {  // :14-15 Conv2D(32, relu) + MaxPooling2D fused: writes x1 and its pooled copy
+    Scope sc(c, "conv1", 2.0 * px * 32 * 27, 4.0 * px * 3 + 2.0 * px * 32 * 1.25);
+    if ((rc = launch_conv_k3s1_c3_pool(x, w.ptr("conv1/kernel"), w.ptr("conv1/bias"), x1.hi, x1p.hi, B, H, W, CIC_ACT_RELU, c.st))) return rc;
+  }
+#define AE_CONV(name, s0, s1p, hh, ww, cin, co, outbuf, up)                                                                   \
+  {                                                                                                                           \
+    TcEpilogue e = epi_bf16(w.ptr(name "/bias"), nullptr, nullptr, CIC_ACT_RELU, outbuf);                                     \
+    e.up2 = up;                                                                                                               \
+    if ((rc = conv_tc(c, name, TC_CONV_S1, s0, s1p, B, hh, ww, 3, 3, 1, mat(pl, name, 9 * (cin), co), co, false, e))) return rc; \
+  }
+  AE_CONV("conv2", view(x1p, 32), nullptr, H / 2, W / 2, 32, 64, x2, 0);                      // :17
+  if (!c.dry) {                                                                               // :18
+    Scope sc(c, "pool2", 0, 2.0 * px / 4 * 64 * 1.25);
+    if ((rc = tc_maxpool2x2_bf16(x2.hi, enc.hi, B, H / 2, W / 2, 64, c.st))) return rc;
+  }
+  AE_CONV("conv3", view(enc, 64), nullptr, H / 4, W / 4, 64, 64, y3u, 1);                     // :21 + :22 UpSampling2D in the store
+  AE_CONV("conv_x2", view(x2, 64), nullptr, H / 2, W / 2, 64, 64, x2r, 0);                    // :25
+  TcAct x2rv = view(x2r, 64), x1rv = view(x1r, 32);
+  AE_CONV("conv5", view(y3u, 64), &x2rv, H / 2, W / 2, 128, 32, y5u, 1);                      // :26 concat, :28, :29 UpSampling2D
+  AE_CONV("conv_x1", view(x1, 32), nullptr, H, W, 32, 32, x1r, 0);                            // :32
+#undef AE_CONV
+  TcEpilogue e;                                                                                // :33 concat, :35 Conv2D(3, sigmoid)
+  e.bias = w.ptr("conv_out/bias"); e.act = CIC_ACT_SIGMOID; e.out_mode = TC_OUT_F32; e.out_hi = y; e.out_ld = C;
+  if ((rc = conv_tc(c, "conv_out", TC_CONV_S1, view(y5u, 32), &x1rv, B, H, W, 3, 3, 1, mat(pl, "conv_out", 9 * 64, 16), C, false, e))) return rc;
+  c.arena.release(mk);
+  if (c.dry) return CIC_OK;
+  Scope sc(c, "cast_u8", 0, 5.0 * px * C);
+  if (y_u8) rc = cic_f32_to_u8_trunc(y, y_u8, px * C, 255.0f, c.st);                          // test_autoencoder.py:88
+  return rc;
+}
+
+// ---- RD optimizer (GAN_functions.py:495-557): conv1 direct, conv2 on the tensor cores, the rest fp32 -------------------
+int rd_forward_tc(cic_plan* pl, Ctx& c, const float* mask, const float* bpp, float* rd_params, int B) {
+  const int H = pl->opts.img_h, W = pl->opts.img_w;
+  if (H % 4 || W % 4) return rd_forward_f32(pl, c, mask, bpp, rd_params, B);
+  const WeightStore& w = pl->w;
+  const int h2 = H / 2, w2 = W / 2, h4 = H / 4, w4 = W / 4;
+  ActBuf r1 = alloc_act(c, (size_t)B * h2 * w2 * 32, true);
+  float* r2 = c.arena.f32((size_t)B * h4 * w4 * 64);
+  float* feat = c.arena.f32((size_t)B * 65);
+  float* d1 = c.arena.f32((size_t)B * 128);
+  float* base = c.arena.f32((size_t)B * 3);
+  int rc;
+  if (!c.dry) {                                                                                // :511-512
+    Scope sc(c, "conv1", 2.0 * B * h2 * w2 * 32 * 9, 4.0 * B * H * W + 4.0 * B * h2 * w2 * 32);
+    if ((rc = launch_conv_k3s2_c1(mask, w.ptr("conv1/kernel"), w.ptr("conv1/bias"), r1.hi, r1.lo, B, H, W, CIC_ACT_LRELU02, c.st))) return rc;
+  }
+  TcEpilogue e;                                                                                // :513-514
+  e.bias = w.ptr("conv2/bias"); e.act = CIC_ACT_LRELU02; e.out_mode = TC_OUT_F32; e.out_hi = r2; e.out_ld = 64;
+  if ((rc = conv_tc(c, "conv2", TC_CONV_S2, view(r1, 32), nullptr, B, h2, w2, 3, 3, 2, mat(pl, "conv2", 9 * 32, 64), 64, true, e))) return rc;
+  if (!c.dry && (rc = launch_global_avg_pool(r2, feat, B, h4 * w4, 64, 65, c.st))) return rc;  // :515
+  return launch_rd_tail(pl, c, bpp, feat, d1, base, rd_params, B);                            // :518-541
 }
 
 // ---- adaptive model (GAN_functions.py:604-696) --------------------------------------------------------
@@ -433,7 +495,7 @@ int adaptive_forward_tc(cic_plan* pl, Ctx& c, const cic_adaptive_io* io, int n_i
   // 4. rate-distortion parameters (:624), fp32; an output only
   if (io->d_rd_params || c.dry) {
     if (c.prof) c.prof->prefix = "rd/";
-    if ((rc = rd_forward_f32(pl->rd.get(), c, mask_t, bpp_t, io->d_rd_params, nt))) return rc;
+    if ((rc = rd_forward_tc(pl->rd.get(), c, mask_t, bpp_t, io->d_rd_params, nt))) return rc;
     c.arena.release(mk);
   }
   // 5. quantise (:661-666)

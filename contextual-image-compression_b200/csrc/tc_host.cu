@@ -492,6 +492,44 @@ int tc_join_to_f32(const bf16* hi, const bf16* lo, float* dst, size_t pixels, in
   return CIC_OK;
 }
 
+__global__ void __launch_bounds__(256)
+maxpool2x2_bf16_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int batch, int H, int W, int C8) {
+  const int Ho = H >> 1, Wo = W >> 1;
+  const long long total = (long long)batch * Ho * Wo * C8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % C8);
+    long long r = i / C8;
+    const int ox = (int)(r % Wo); r /= Wo;
+    const int oy = (int)(r % Ho);
+    const int b = (int)(r / Ho);
+    const uint4* p0 = x + (((long long)b * H + 2 * oy) * W + 2 * ox) * C8 + c8;
+    const uint4 v[4] = {__ldg(p0), __ldg(p0 + C8), __ldg(p0 + (long long)W * C8), __ldg(p0 + (long long)W * C8 + C8)};
+    uint4 m;
+    uint32_t* mw = reinterpret_cast<uint32_t*>(&m);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(reinterpret_cast<const uint32_t*>(&v[0]) + q);
+#pragma unroll
+      for (int k = 1; k < 4; ++k) a = __hmax2(a, *reinterpret_cast<const __nv_bfloat162*>(reinterpret_cast<const uint32_t*>(&v[k]) + q));
+      mw[q] = *reinterpret_cast<const uint32_t*>(&a);
+    }
+    y[i] = m;
+  }
+}
+
+int tc_maxpool2x2_bf16(const bf16* x, bf16* y, int batch, int H, int W, int C, cudaStream_t st) {
+  CIC_REQUIRE(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "maxpool2x2_bf16: needs C %% 8 == 0 and even H, W");
+  const long long total = (long long)batch * (H / 2) * (W / 2) * (C / 8);
+  if (total == 0) return CIC_OK;
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  maxpool2x2_bf16_kernel<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), batch, H, W, C / 8);
+  CIC_COUNT_LAUNCH();
+  CIC_CHECK_LAUNCH("maxpool2x2_bf16_kernel");
+  return CIC_OK;
+}
+
 __global__ void tc_splitk_reduce_kernel(const float* __restrict__ partial, int splits, long long M, int N,
                                         const float* __restrict__ bias, const float* __restrict__ scale,
                                         const float* __restrict__ shift, int act, float* __restrict__ out_f32,

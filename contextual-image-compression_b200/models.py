@@ -151,6 +151,66 @@ class Model:
             host = [b.numpy() for b in host_t]
         return host if self._multi_output else host[0]
 
+    def predict_pipelined(self, x, n_chunks: int = 4, on_chunk=None):
+        """High-throughput predict for host inputs: the batch is cut into `n_chunks` contiguous chunks that flow
+        through three CUDA streams - host->device copies, the model, device->host copies into per-model pinned
+        staging buffers - so PCIe traffic overlaps the kernels.  Batch items are independent in every model of the
+        path, so the result equals predict().  `on_chunk(device_inputs, device_outputs)` (optional) runs on the
+        compute stream after each chunk (e.g. the metric kernels) and its return values are collected.
+        Returns (host outputs - views of staging buffers the next call overwrites -, [on_chunk results])."""
+        xs = runtime.as_list(x)
+        hs = [t if isinstance(t, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(t)) for t in xs]
+        hs = [t if t.dtype == torch.float32 else t.to(torch.float32) for t in hs]
+        n = hs[0].shape[0]
+        dev = runtime.require_cuda()
+        n_chunks = max(1, min(int(n_chunks), n))
+        bounds = [(i * n) // n_chunks for i in range(n_chunks + 1)]
+        compute = torch.cuda.current_stream()
+        st = self.__dict__.setdefault("_pipe_streams", {})
+        if "in" not in st:
+            st["in"], st["out"] = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        s_in, s_out = st["in"], st["out"]
+        s_in.wait_stream(compute)
+        s_out.wait_stream(compute)
+        stage = self.__dict__.setdefault("_stage", {})
+        keep, host, extra = [], None, []
+        ev_in = [torch.cuda.Event() for _ in range(n_chunks)]
+        for i in range(n_chunks):                                   # all uploads are queued up front on the copy-in stream
+            lo, hi = bounds[i], bounds[i + 1]
+            with torch.cuda.stream(s_in):
+                d_in = [h[lo:hi].to(dev, non_blocking=True) for h in hs]
+                ev_in[i].record(s_in)
+            keep.append(d_in)
+        offs = None
+        for i in range(n_chunks):
+            lo, hi = bounds[i], bounds[i + 1]
+            compute.wait_event(ev_in[i])
+            outs = self.forward_device(keep[i])
+            if on_chunk is not None:
+                extra.append(on_chunk(keep[i], getattr(self, "last", None)))
+            ev_c = torch.cuda.Event()
+            ev_c.record(compute)
+            if host is None:                                        # staging buffers sized from the first chunk's row ratio
+                per = [o.shape[0] // (hi - lo) for o in outs]
+                host, offs = [], [0] * len(outs)
+                for k, o in enumerate(outs):
+                    shape = (per[k] * n,) + tuple(o.shape[1:])
+                    key = ("pipe", k, shape, o.dtype)
+                    buf = stage.get(key)
+                    if buf is None:
+                        buf = stage[key] = torch.empty(shape, dtype=o.dtype, pin_memory=True)
+                    host.append(buf)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_c)
+                for k, o in enumerate(outs):
+                    host[k][offs[k]:offs[k] + o.shape[0]].copy_(o, non_blocking=True)
+                    offs[k] += o.shape[0]
+            keep.append(outs)                                       # alive until the copies have completed
+        compute.wait_stream(s_out)
+        s_out.synchronize()
+        res = [b.numpy() for b in host]
+        return (res if self._multi_output else res[0]), extra
+
     def __call__(self, inputs, training=False):
         if training:
             raise NotImplementedError("training is outside the accelerated inference path (SURVEY.md §2 #19-20)")

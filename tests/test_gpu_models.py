@@ -237,6 +237,33 @@ def test_compress_and_reconstruct_and_rate_control(cic, precision, small_cfg):
         gt.compress_and_reconstruct(img[0], models, target_bpp=1.0)             # no mask and no opencv-contrib
 
 
+def test_pipelined_predict_equals_predict(cic, precision, small_cfg):
+    """predict_pipelined (chunks over copy-in / compute / copy-out streams) returns what predict returns."""
+    models, ws = _adaptive(cic, small_cfg["img_shape"], small_cfg["base"])
+    am = models["adaptive_model"]
+    img = cic.synth.to_signed_range(cic.synth.synth_images_u8(5, 128, 64, seed=49))
+    mask = cic.synth.synth_masks(5, 128, 64, seed=49)
+    bpp = np.linspace(0.2, 1.8, 5, dtype=np.float32).reshape(5, 1)
+    want = am.predict([img, mask, bpp])
+    seen = []
+    got, extra = am.predict_pipelined([img, mask, bpp], n_chunks=3,
+                                      on_chunk=lambda d_in, outs: seen.append((d_in[0].shape[0], outs["hq_ratio_sum"].clone())))
+    assert [n for n, _ in seen] == [1, 2, 2] and len(extra) == 3
+    for g, w in zip(got, want):
+        assert g.shape == w.shape
+        np.testing.assert_allclose(g, w, atol=0 if precision == "fp32" else 2e-2, rtol=0)
+    ratios = torch.cat([r for _, r in seen]).cpu().numpy() / (128 * 64)
+    np.testing.assert_allclose(ratios, want[4].reshape(5, -1).mean(1, dtype=np.float64), atol=1e-6)
+    import train_autoencoder as tr
+    ae = tr.build_autoencoder((32, 32, 3))
+    ae.set_weights_dict(cic.weights.synthetic_autoencoder(seed=42))
+    x = cic.synth.to_unit_range(cic.synth.synth_images_u8(7, 32, 32, seed=50))
+    y, _ = ae.predict_pipelined(x, n_chunks=4)
+    # fp32: bit-identical.  tc: the tile shape (hence the tap accumulation order) may change with the chunk's batch size,
+    # so an intermediate bf16 rounding can flip by one ulp
+    np.testing.assert_allclose(y, ae.predict(x), atol=0 if precision == "fp32" else 1e-3, rtol=0)
+
+
 def test_linearity_of_blend_at_full_size(cic):
     """Size-independent property at a BASELINE-scale shape (1024x1024): blend(hq, hq) == hq and
     blend is affine in (hq, lq)."""

@@ -29,7 +29,7 @@ template <int CIN, int KS, int STRIDE, int COUT, int NPX, bool POOL>
 __global__ void __launch_bounds__(256)
 direct_conv_kernel(const float* __restrict__ x, const float* __restrict__ wgt, const float* __restrict__ bias,
                    __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, float* __restrict__ out_f32,
-                   __nv_bfloat16* __restrict__ pool_hi, int H, int W, int Ho, int Wo, int pad_t, int pad_l, int act) {
+                   __nv_bfloat16* __restrict__ pool_hi, int H, int W, int Ho, int Wo, int pad_t, int pad_l, int act, const TileMap tm) {
   using Cfg = DcCfg<CIN, KS, STRIDE, COUT, NPX, POOL>;
   __shared__ float patch[Cfg::kPH][Cfg::kPW * CIN];
   __shared__ __align__(16) float wsm[Cfg::kK][COUT];
@@ -37,12 +37,23 @@ direct_conv_kernel(const float* __restrict__ x, const float* __restrict__ wgt, c
   const int tid = threadIdx.x;
   for (int i = tid; i < Cfg::kK * COUT; i += 256) (&wsm[0][0])[i] = wgt[i];
   const int iy0 = STRIDE * oy0 - pad_t, ix0 = STRIDE * ox0 - pad_l;
-  const float* xb = x + (size_t)b * H * W * CIN;
+  // input item b: a dense (H, W, CIN) image, or tile (ty, tx) of a larger image (zero padding at the tile border:
+  // tiles are coded independently)
+  const float* xb;
+  size_t row_stride;
+  if (tm.tiles_x) {
+    const int tpi = tm.tiles_x * tm.tiles_y, img = b / tpi, t = b % tpi;
+    xb = x + (((size_t)img * tm.IH + (size_t)(t / tm.tiles_x) * H) * tm.IW + (size_t)(t % tm.tiles_x) * W) * CIN;
+    row_stride = (size_t)tm.IW * CIN;
+  } else {
+    xb = x + (size_t)b * H * W * CIN;
+    row_stride = (size_t)W * CIN;
+  }
   for (int i = tid; i < Cfg::kPH * Cfg::kPW * CIN; i += 256) {
     const int r = i / (Cfg::kPW * CIN), cix = i % (Cfg::kPW * CIN);
     const int iy = iy0 + r, ix = ix0 + cix / CIN;
     float v = 0.f;
-    if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(xb + ((size_t)iy * W + ix) * CIN + cix % CIN);
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(xb + (size_t)iy * row_stride + (size_t)ix * CIN + cix % CIN);
     patch[r][cix] = v;
   }
   __syncthreads();
@@ -139,7 +150,7 @@ direct_conv_kernel(const float* __restrict__ x, const float* __restrict__ wgt, c
 template <int CIN, int KS, int STRIDE, int COUT, int NPX, bool POOL>
 static int launch_direct(const char* name, const float* x, const float* wgt, const float* bias, __nv_bfloat16* out_hi,
                          __nv_bfloat16* out_lo, float* out_f32, __nv_bfloat16* pool_hi, int batch, int H, int W, int act,
-                         cudaStream_t st) {
+                         const TileMap& tm, cudaStream_t st) {
   using Cfg = DcCfg<CIN, KS, STRIDE, COUT, NPX, POOL>;
   CIC_REQUIRE(H > 0 && W > 0, "%s: bad image size", name);
   CIC_REQUIRE(act == CIC_ACT_NONE || act == CIC_ACT_RELU || act == CIC_ACT_LRELU02, "%s: unsupported activation", name);
@@ -150,10 +161,11 @@ static int launch_direct(const char* name, const float* x, const float* wgt, con
     const int nb = batch - b0 < 65535 ? batch - b0 : 65535;
     dim3 grid((Wo + Cfg::kTileW - 1) / Cfg::kTileW, (Ho + Cfg::kTileH - 1) / Cfg::kTileH, nb);
     const size_t oo = (size_t)b0 * Ho * Wo * COUT, po = (size_t)b0 * (Ho / 2) * (Wo / 2) * COUT;
+    CIC_REQUIRE(!tm.tiles_x || batch <= 65535, "%s: tiled input supports at most 65535 tiles per launch", name);
     direct_conv_kernel<CIN, KS, STRIDE, COUT, NPX, POOL><<<grid, 256, 0, st>>>(
-        x + (size_t)b0 * H * W * CIN, wgt, bias, out_hi ? out_hi + oo : nullptr, out_lo ? out_lo + oo : nullptr,
+        x + (tm.tiles_x ? 0 : (size_t)b0 * H * W * CIN), wgt, bias, out_hi ? out_hi + oo : nullptr, out_lo ? out_lo + oo : nullptr,
         out_f32 ? out_f32 + oo : nullptr, pool_hi ? pool_hi + po : nullptr, H, W, Ho, Wo, same_pad_before(H, KS, STRIDE),
-        same_pad_before(W, KS, STRIDE), act);
+        same_pad_before(W, KS, STRIDE), act, tm);
     CIC_COUNT_LAUNCH();
     CIC_CHECK_LAUNCH(name);
   }
@@ -162,21 +174,21 @@ static int launch_direct(const char* name, const float* x, const float* wgt, con
 
 // x (B,H,W,3) fp32 -> Conv2D(64, k4, s2, 'same') + bias + act -> bf16 hi (+ lo) and/or fp32, (B,H/2,W/2,64)
 int launch_conv_k4s2_c3(const float* x, const float* wgt, const float* bias, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo,
-                        float* out_f32, int batch, int H, int W, int act, cudaStream_t st) {
+                        float* out_f32, int batch, int H, int W, int act, const TileMap& tm, cudaStream_t st) {
   CIC_REQUIRE(H % 2 == 0 && W % 2 == 0, "conv_k4s2_c3: H and W must be even");
-  return launch_direct<3, 4, 2, 64, 2, false>("conv_k4s2_c3_kernel", x, wgt, bias, out_hi, out_lo, out_f32, nullptr, batch, H, W, act, st);
+  return launch_direct<3, 4, 2, 64, 2, false>("conv_k4s2_c3_kernel", x, wgt, bias, out_hi, out_lo, out_f32, nullptr, batch, H, W, act, tm, st);
 }
 
 // x (B,H,W,3) fp32 -> Conv2D(32, k3, 'same') + bias + act -> bf16 (B,H,W,32) and its 2x2 max-pool (B,H/2,W/2,32)
 int launch_conv_k3s1_c3_pool(const float* x, const float* wgt, const float* bias, __nv_bfloat16* out_hi, __nv_bfloat16* pool_hi,
                              int batch, int H, int W, int act, cudaStream_t st) {
-  return launch_direct<3, 3, 1, 32, 4, true>("conv_k3s1_c3_pool_kernel", x, wgt, bias, out_hi, nullptr, nullptr, pool_hi, batch, H, W, act, st);
+  return launch_direct<3, 3, 1, 32, 4, true>("conv_k3s1_c3_pool_kernel", x, wgt, bias, out_hi, nullptr, nullptr, pool_hi, batch, H, W, act, TileMap(), st);
 }
 
 // x (B,H,W,1) fp32 -> Conv2D(32, k3, s2, 'same') + bias + act -> bf16 hi (+ lo), (B,ceil(H/2),ceil(W/2),32)
 int launch_conv_k3s2_c1(const float* x, const float* wgt, const float* bias, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo,
-                        int batch, int H, int W, int act, cudaStream_t st) {
-  return launch_direct<1, 3, 2, 32, 2, false>("conv_k3s2_c1_kernel", x, wgt, bias, out_hi, out_lo, nullptr, nullptr, batch, H, W, act, st);
+                        int batch, int H, int W, int act, const TileMap& tm, cudaStream_t st) {
+  return launch_direct<1, 3, 2, 32, 2, false>("conv_k3s2_c1_kernel", x, wgt, bias, out_hi, out_lo, nullptr, nullptr, batch, H, W, act, tm, st);
 }
 
 }  // namespace cic

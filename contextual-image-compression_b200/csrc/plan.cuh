@@ -96,12 +96,18 @@ struct Scope {  // RAII layer bracket
 int run_dense(const float* x, const float* kernel, const float* bias, const float* scale, const float* shift, float* y,
               int batch, int in_dim, int out_dim, int act, float* ws, size_t ws_floats, cudaStream_t st);
 void pack_deconv_phases(const float* k, int cout, int cin, std::vector<float>& out);
+// Batch item b of a model is tile (ty, tx) of image b / (tiles_x * tiles_y) in an (n_img, IH, IW, C) tensor, so the
+// first and last layers of the tiled codec address the image layout directly (no gather / scatter pass).
+// tiles_x == 0: plain dense batch.
+struct TileMap {
+  int tiles_x = 0, tiles_y = 0, IH = 0, IW = 0;
+};
 int launch_conv_k4s2_c3(const float* x, const float* wgt, const float* bias, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo,
-                        float* out_f32, int batch, int H, int W, int act, cudaStream_t st);
+                        float* out_f32, int batch, int H, int W, int act, const TileMap& tm, cudaStream_t st);
 int launch_conv_k3s1_c3_pool(const float* x, const float* wgt, const float* bias, __nv_bfloat16* out_hi, __nv_bfloat16* pool_hi,
                              int batch, int H, int W, int act, cudaStream_t st);
 int launch_conv_k3s2_c1(const float* x, const float* wgt, const float* bias, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo,
-                        int batch, int H, int W, int act, cudaStream_t st);
+                        int batch, int H, int W, int act, const TileMap& tm, cudaStream_t st);
 int launch_expand_bpp(const float* bpp, float* bpp_t, float* qs_t, int n_tiles, int tiles_per_img, cudaStream_t st);
 
 // named raw device buffers (packed bf16 weights of the tensor-core path)
@@ -141,7 +147,7 @@ int saliency_forward_f32(cic_plan* pl, Ctx& c, const float* latent, float* score
 int rd_forward_f32(cic_plan* pl, Ctx& c, const float* mask, const float* bpp, float* rd_params, int B);
 int adaptive_forward_f32(cic_plan* pl, Ctx& c, const cic_adaptive_io* io, int n_img, int img_h, int img_w);
 int launch_rd_tail(cic_plan* pl, Ctx& c, const float* bpp, float* feat, float* d1, float* base, float* rd_params, int B);
-int rd_forward_tc(cic_plan* pl, Ctx& c, const float* mask, const float* bpp, float* rd_params, int B);
+int rd_forward_tc(cic_plan* pl, Ctx& c, const float* mask, const float* bpp, float* rd_params, int B, const TileMap& tm = TileMap());
 int autoencoder_forward_tc(cic_plan* pl, Ctx& c, const float* x, float* y, uint8_t* y_u8, int B, int H, int W);
 int encoder_forward_tc(cic_plan* pl, Ctx& c, const float* img, float* latent, float* x1, float* x2, float* x3, int B);
 int generator_forward_tc(cic_plan* pl, Ctx& c, const float* latent, const float* s1, const float* s2, const float* s3,

@@ -253,7 +253,8 @@ static EncSkips alloc_skips(Ctx& c, size_t px) {
   return s;
 }
 
-static int encoder_core_tc(cic_plan* pl, Ctx& c, const float* img, float* latent, float* x1_f32, const EncSkips& sk, int B) {
+static int encoder_core_tc(cic_plan* pl, Ctx& c, const float* img, float* latent, float* x1_f32, const EncSkips& sk, int B,
+                           const TileMap& tm = TileMap()) {
   const WeightStore& w = pl->w;
   const int H = pl->opts.img_h, W = pl->opts.img_w, C = pl->opts.img_c, L = pl->opts.latent_dim;
   const size_t px = (size_t)B * H * W;
@@ -264,9 +265,10 @@ static int encoder_core_tc(cic_plan* pl, Ctx& c, const float* img, float* latent
   if (C == 3) {
     if (!c.dry) {
       Scope sc(c, "conv1", 2.0 * (px / 4) * 64 * 16 * C, 4.0 * px * C + 4.0 * px / 4 * 64);
-      if ((rc = launch_conv_k4s2_c3(img, w.ptr("conv1/kernel"), w.ptr("conv1/bias"), sk.x1.hi, sk.x1.lo, x1_f32, B, H, W, CIC_ACT_LRELU02, c.st))) return rc;
+      if ((rc = launch_conv_k4s2_c3(img, w.ptr("conv1/kernel"), w.ptr("conv1/bias"), sk.x1.hi, sk.x1.lo, x1_f32, B, H, W, CIC_ACT_LRELU02, tm, c.st))) return rc;
     }
   } else {
+    CIC_REQUIRE(!tm.tiles_x, "encoder (tc): tiled input needs a 3-channel image");
     float* x1f = x1_f32 ? x1_f32 : c.arena.f32(px / 4 * 64);
     if (!c.dry) {
       Scope sc(c, "conv1", 2.0 * (px / 4) * 64 * 16 * C, 4.0 * (px * C + px / 4 * 64) + 4.0 * px / 4 * 64);
@@ -322,7 +324,8 @@ int encoder_forward_tc(cic_plan* pl, Ctx& c, const float* img, float* latent, fl
 
 // ---- generator --------------------------------------------------------------------------------
 // latent fp32 (B, L); skips as bf16 NHWC (hi only is read)
-static int generator_core_tc(cic_plan* pl, Ctx& c, const float* latent, const bf16* s1, const bf16* s2, const bf16* s3, float* out, int B) {
+static int generator_core_tc(cic_plan* pl, Ctx& c, const float* latent, const bf16* s1, const bf16* s2, const bf16* s3, float* out, int B,
+                             const TileMap& tm = TileMap()) {
   const WeightStore& w = pl->w;
   const int H = pl->opts.img_h, W = pl->opts.img_w, C = pl->opts.img_c, L = pl->opts.latent_dim;
   const int h16 = H / 16, w16 = W / 16, feat = h16 * w16 * 512;
@@ -365,6 +368,7 @@ static int generator_core_tc(cic_plan* pl, Ctx& c, const float* latent, const bf
   // :273 Conv2D(3, k4, 'same', tanh): pad 1 before / 2 after
   TcEpilogue e;
   e.bias = w.ptr("conv_out/bias"); e.act = CIC_ACT_TANH; e.out_mode = TC_OUT_F32; e.out_hi = out; e.out_ld = C;
+  e.tm_tx = tm.tiles_x; e.tm_ty = tm.tiles_y; e.tm_IH = tm.IH; e.tm_IW = tm.IW;  // write straight into the image layout
   if ((rc = conv_tc(c, "conv_out", TC_CONV_S1, view(g4, 32), nullptr, B, H, W, 4, 4, 1, mat(pl, "conv_out", 16 * 32, 16), C, false, e))) return rc;
   c.arena.release(mk);
   return CIC_OK;
@@ -426,9 +430,12 @@ int autoencoder_forward_tc(cic_plan* pl, Ctx& c, const float* x, float* y, uint8
 }
 
 // ---- RD optimizer (GAN_functions.py:495-557): conv1 direct, conv2 on the tensor cores, the rest fp32 -------------------
-int rd_forward_tc(cic_plan* pl, Ctx& c, const float* mask, const float* bpp, float* rd_params, int B) {
+int rd_forward_tc(cic_plan* pl, Ctx& c, const float* mask, const float* bpp, float* rd_params, int B, const TileMap& tm) {
   const int H = pl->opts.img_h, W = pl->opts.img_w;
-  if (H % 4 || W % 4) return rd_forward_f32(pl, c, mask, bpp, rd_params, B);
+  if (H % 4 || W % 4) {
+    CIC_REQUIRE(!tm.tiles_x, "rd (tc): tiled input needs H, W divisible by 4");
+    return rd_forward_f32(pl, c, mask, bpp, rd_params, B);
+  }
   const WeightStore& w = pl->w;
   const int h2 = H / 2, w2 = W / 2, h4 = H / 4, w4 = W / 4;
   ActBuf r1 = alloc_act(c, (size_t)B * h2 * w2 * 32, true);
@@ -439,7 +446,7 @@ int rd_forward_tc(cic_plan* pl, Ctx& c, const float* mask, const float* bpp, flo
   int rc;
   if (!c.dry) {                                                                                // :511-512
     Scope sc(c, "conv1", 2.0 * B * h2 * w2 * 32 * 9, 4.0 * B * H * W + 4.0 * B * h2 * w2 * 32);
-    if ((rc = launch_conv_k3s2_c1(mask, w.ptr("conv1/kernel"), w.ptr("conv1/bias"), r1.hi, r1.lo, B, H, W, CIC_ACT_LRELU02, c.st))) return rc;
+    if ((rc = launch_conv_k3s2_c1(mask, w.ptr("conv1/kernel"), w.ptr("conv1/bias"), r1.hi, r1.lo, B, H, W, CIC_ACT_LRELU02, tm, c.st))) return rc;
   }
   TcEpilogue e;                                                                                // :513-514
   e.bias = w.ptr("conv2/bias"); e.act = CIC_ACT_LRELU02; e.out_mode = TC_OUT_F32; e.out_hi = r2; e.out_ld = 64;
@@ -456,18 +463,11 @@ int adaptive_forward_tc(cic_plan* pl, Ctx& c, const cic_adaptive_io* io, int n_i
   const bool tiled = tpi > 1;
   const size_t tpx = (size_t)nt * T * T;
   int rc;
+  // tiles are addressed in place in the image layout by the first (conv1, RD conv1) and last (conv_out) layers
+  TileMap tm;
+  if (tiled) { tm.tiles_x = img_w / T; tm.tiles_y = img_h / T; tm.IH = img_h; tm.IW = img_w; }
   const float* img_t = io->d_img;
   const float* mask_t = io->d_mask;
-  if (tiled) {
-    float* it = c.arena.f32(tpx * 3);
-    float* mt = c.arena.f32(tpx);
-    if (!c.dry) {
-      if ((rc = launch_tile_gather(io->d_img, it, n_img, img_h, img_w, 3, T, c.st))) return rc;
-      if ((rc = launch_tile_gather(io->d_mask, mt, n_img, img_h, img_w, 1, T, c.st))) return rc;
-    }
-    img_t = it;
-    mask_t = mt;
-  }
   float* bpp_t = c.arena.f32(nt);
   float* qs_t = c.arena.f32(nt);
   if (!c.dry && (rc = launch_expand_bpp(io->d_bpp, bpp_t, qs_t, nt, tpi, c.st))) return rc;              // :631-649
@@ -477,10 +477,10 @@ int adaptive_forward_tc(cic_plan* pl, Ctx& c, const cic_adaptive_io* io, int n_i
   EncSkips hs = alloc_skips(c, tpx), ls = alloc_skips(c, tpx);
   size_t mk = c.arena.mark();
   if (c.prof) c.prof->prefix = "hq_enc/";
-  if ((rc = encoder_core_tc(pl->hq_enc.get(), c, img_t, hq_lat, nullptr, hs, nt))) return rc;
+  if ((rc = encoder_core_tc(pl->hq_enc.get(), c, img_t, hq_lat, nullptr, hs, nt, tm))) return rc;
   c.arena.release(mk);
   if (c.prof) c.prof->prefix = "lq_enc/";
-  if ((rc = encoder_core_tc(pl->lq_enc.get(), c, img_t, lq_lat, nullptr, ls, nt))) return rc;
+  if ((rc = encoder_core_tc(pl->lq_enc.get(), c, img_t, lq_lat, nullptr, ls, nt, tm))) return rc;
   c.arena.release(mk);
   // 3. latent saliency (:619-620), fp32
   float* sal_hq = c.arena.f32(nt);
@@ -495,7 +495,7 @@ int adaptive_forward_tc(cic_plan* pl, Ctx& c, const cic_adaptive_io* io, int n_i
   // 4. rate-distortion parameters (:624), fp32; an output only
   if (io->d_rd_params || c.dry) {
     if (c.prof) c.prof->prefix = "rd/";
-    if ((rc = rd_forward_tc(pl->rd.get(), c, mask_t, bpp_t, io->d_rd_params, nt))) return rc;
+    if ((rc = rd_forward_tc(pl->rd.get(), c, mask_t, bpp_t, io->d_rd_params, nt, tm))) return rc;
     c.arena.release(mk);
   }
   // 5. quantise (:661-666)
@@ -508,28 +508,16 @@ int adaptive_forward_tc(cic_plan* pl, Ctx& c, const cic_adaptive_io* io, int n_i
     if ((rc = cic_quantize_latent(lq_lat, sal_lq, qs_t, lq_q, io->d_lq_symbols, nullptr, io->d_lq_scale, nt, base, c.st))) return rc;
   }
   // 6. generators (:669-670)
-  float* hq_out_t = (!tiled && io->d_hq_out) ? io->d_hq_out : c.arena.f32(tpx * 3);
-  float* lq_out_t = (!tiled && io->d_lq_out) ? io->d_lq_out : c.arena.f32(tpx * 3);
+  float* hq_img = io->d_hq_out ? io->d_hq_out : c.arena.f32(tpx * 3);  // image layout
+  float* lq_img = io->d_lq_out ? io->d_lq_out : c.arena.f32(tpx * 3);
   mk = c.arena.mark();
   if (c.prof) c.prof->prefix = "hq_gen/";
-  if ((rc = generator_core_tc(pl->hq_gen.get(), c, hq_q, hs.x1.hi, hs.x2.hi, hs.x3.hi, hq_out_t, nt))) return rc;
+  if ((rc = generator_core_tc(pl->hq_gen.get(), c, hq_q, hs.x1.hi, hs.x2.hi, hs.x3.hi, hq_img, nt, tm))) return rc;
   c.arena.release(mk);
   if (c.prof) c.prof->prefix = "lq_gen/";
-  if ((rc = generator_core_tc(pl->lq_gen.get(), c, lq_q, ls.x1.hi, ls.x2.hi, ls.x3.hi, lq_out_t, nt))) return rc;
+  if ((rc = generator_core_tc(pl->lq_gen.get(), c, lq_q, ls.x1.hi, ls.x2.hi, ls.x3.hi, lq_img, nt, tm))) return rc;
   c.arena.release(mk);
   // 7. dynamic threshold + blend on whole images (:651-657, :682-684)
-  const float* hq_img = hq_out_t;
-  const float* lq_img = lq_out_t;
-  if (tiled) {
-    float* hi = io->d_hq_out ? io->d_hq_out : c.arena.f32(tpx * 3);
-    float* li = io->d_lq_out ? io->d_lq_out : c.arena.f32(tpx * 3);
-    if (!c.dry) {
-      if ((rc = launch_tile_scatter(hq_out_t, hi, n_img, img_h, img_w, 3, T, c.st))) return rc;
-      if ((rc = launch_tile_scatter(lq_out_t, li, n_img, img_h, img_w, 3, T, c.st))) return rc;
-    }
-    hq_img = hi;
-    lq_img = li;
-  }
   if (c.prof) c.prof->prefix = "";
   if (!c.dry) {
     Scope sc(c, "roi_blend", 0, 44.0 * n_img * img_h * img_w);

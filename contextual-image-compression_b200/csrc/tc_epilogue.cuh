@@ -26,6 +26,7 @@ struct TcEpi {
   int up2;                      // 1: replicate every output pixel 2x2 (nearest up-sampling fused into the store)
   int Ho, Wo;                   // output positions per batch item (of one phase)
   long long m_total;            // rows of the split-K partial buffer
+  int tm_tx, tm_ty, tm_IH, tm_IW;  // tm_tx != 0: batch item b is tile (ty, tx) of image b / (tm_tx * tm_ty) in (n, IH, IW, ld)
 };
 
 struct TcRow {  // the output row this thread owns
@@ -39,7 +40,14 @@ struct TcRow {  // the output row this thread owns
 // epilogue warps stalled on instruction fetch: profiles/r01_ncu_raster_issue_bound.md).
 template <int CH>
 __device__ __forceinline__ void tc_epilogue_store(const TcEpi& e, const TcRow& r, const uint32_t (&v)[32], int n0, int nv) {
-  const long long opix = ((long long)r.b * e.out_H + (r.oy * e.out_ys + e.out_y0[r.phase])) * e.out_W + (r.ox * e.out_xs + e.out_x0[r.phase]);
+  long long opix;
+  if (e.tm_tx) {  // scatter the tile into the image layout
+    const int tpi = e.tm_tx * e.tm_ty, img = r.b / tpi, t = r.b % tpi;
+    opix = ((long long)img * e.tm_IH + (t / e.tm_tx) * e.out_H + (r.oy * e.out_ys + e.out_y0[r.phase])) * e.tm_IW + (t % e.tm_tx) * e.out_W +
+           (r.ox * e.out_xs + e.out_x0[r.phase]);
+  } else {
+    opix = ((long long)r.b * e.out_H + (r.oy * e.out_ys + e.out_y0[r.phase])) * e.out_W + (r.ox * e.out_xs + e.out_x0[r.phase]);
+  }
   const bool full = nv == CH;
   if (e.out_mode == TC_OUT_PARTIAL) {
     const long long mrow = ((long long)r.b * e.Ho + r.oy) * e.Wo + r.ox;

@@ -250,6 +250,7 @@ static int try_run_raster(const TcLayer& L, int BK, int N_pad, const TcMaps& act
   pe.out_mode = e.out_mode; pe.out_hi = e.out_hi; pe.out_lo = e.out_lo; pe.res_hi = e.res_hi; pe.res_lo = e.res_lo;
   pe.N = L.N; pe.out_ld = e.out_ld ? e.out_ld : L.N; pe.out_coff = e.out_coff; pe.up2 = e.up2;
   pe.Ho = Ho; pe.Wo = Wo;
+  pe.tm_tx = e.tm_tx; pe.tm_ty = e.tm_ty; pe.tm_IH = e.tm_IH; pe.tm_IW = e.tm_IW;
   pe.m_total = (long long)L.batch * Ho * Wo;
   if (dc) {
     for (int ph = 0; ph < 4; ++ph) { pe.out_y0[ph] = (int8_t)(ph >> 1); pe.out_x0[ph] = (int8_t)(ph & 1); }
@@ -403,6 +404,7 @@ int tc_run_layer(const TcLayer& L, cudaStream_t st) {
   pe.out_mode = e.out_mode; pe.out_hi = e.out_hi; pe.out_lo = e.out_lo; pe.res_hi = e.res_hi; pe.res_lo = e.res_lo;
   pe.N = L.N; pe.out_ld = e.out_ld ? e.out_ld : L.N; pe.out_coff = e.out_coff; pe.up2 = e.up2;
   pe.Ho = Ho; pe.Wo = Wo;
+  pe.tm_tx = e.tm_tx; pe.tm_ty = e.tm_ty; pe.tm_IH = e.tm_IH; pe.tm_IW = e.tm_IW;
   pe.m_total = (long long)L.batch * Ho * Wo;
   return launch_tc_gemm(maps, p, bn, BK, L.split, st);
 }

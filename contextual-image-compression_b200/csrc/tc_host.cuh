@@ -36,6 +36,7 @@ struct TcEpilogue {
   const bf16* res_lo = nullptr;
   int out_ld = 0, out_coff = 0;
   int up2 = 0;
+  int tm_tx = 0, tm_ty = 0, tm_IH = 0, tm_IW = 0;  // output tile map (see TcEpi)
 };
 
 enum TcKind { TC_CONV_S1 = 0, TC_CONV_S2 = 1, TC_DECONV_K4S2 = 2 };

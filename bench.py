@@ -168,7 +168,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("CIC_PRECISION", "tc"), choices=["tc", "fp32"])
     ap.add_argument("--images", type=int, default=IMGS_PER_GPU, help="512x512 images per GPU per step")
-    ap.add_argument("--e2e-chunks", type=int, default=8, help="chunks of the batch in the pipelined end-to-end leg")
+    ap.add_argument("--e2e-chunks", default="auto", help="pipelined end-to-end leg: number of chunks of the batch, comma-separated chunk "
+                    "sizes, or 'auto' (n/8, 3n/4, n/8: short first upload and last download)")
     ap.add_argument("--cpu-tiles", type=int, default=8, help="tiles in the CPU-oracle sample (0 = skip)")
     ap.add_argument("--profile-csv", default=None, help="write the per-layer device times of the last timed step here")
     args = ap.parse_args()
@@ -217,6 +218,11 @@ def main():
         outs = am.forward_device([d_img, d_mask, d_bpp], extras=False)
         return evaluate(d_img, am.last)
 
+    if args.e2e_chunks == "auto":
+        e2e_chunks = [n_img // 8, n_img - 2 * (n_img // 8), n_img // 8] if n_img >= 16 else min(n_img, 2)
+    else:
+        e2e_chunks = [int(v) for v in str(args.e2e_chunks).split(",")] if "," in str(args.e2e_chunks) else int(args.e2e_chunks)
+
     def evaluate_chunk(d_in, outs):
         """Per-chunk metric sums (no all-reduce): runs on the compute stream inside the pipelined predict."""
         k = d_in[0].shape[0]
@@ -230,7 +236,7 @@ def main():
 
     def step_e2e():
         # pinned host buffers -> (H2D | model + metrics | D2H of all 5 outputs) pipelined over chunks of the batch
-        outs, parts = am.predict_pipelined([h_img, h_mask, h_bpp], n_chunks=args.e2e_chunks, on_chunk=evaluate_chunk)
+        outs, parts = am.predict_pipelined([h_img, h_mask, h_bpp], n_chunks=e2e_chunks, on_chunk=evaluate_chunk)
         sums = cic.dist.allreduce_metric_sums(torch.stack(parts).sum(0))
         return outs, sums.cpu()
 
@@ -301,6 +307,10 @@ def main():
     quality = {"psnr_db": s[0] / n_total, "ssim": s[1] / n_total, "mse": s[2] / n_total, "actual_bpp": s[3] / n_total,
                "hq_ratio": s[4] / n_total, "images": int(n_total)}
 
+    if world > 1:
+        import torch.distributed as tdist
+        tdist.barrier()
+        tdist.destroy_process_group()
     if rank != 0:
         return
     cpu = None

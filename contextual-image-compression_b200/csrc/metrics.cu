@@ -120,6 +120,107 @@ metrics_f32_kernel(const float* __restrict__ A, const float* __restrict__ Bm, do
   }
 }
 
+// Same arithmetic, all channels of a tile in one CTA (C <= 4): the pair is read once with fully coalesced rows
+// (the per-channel kernel above reads every C-th float: C x the sectors), the window sums of one channel at a
+// time reuse one staging buffer, and the /7 of the two filter passes is a multiply by the double 1/7 (one ulp of
+// a double before the cast to float).  Dynamic shared memory: 2 * TP * (TP*C + 1) + 5 * TS * (TP + 1) floats.
+__global__ void __launch_bounds__(256)
+metrics_f32_packed_kernel(const float* __restrict__ A, const float* __restrict__ Bm, double* __restrict__ acc, int H, int W,
+                          int C, float pre_add, float pre_mul, float c1, float c2, float cov_norm) {
+  extern __shared__ float msm[];
+  const int ld = TP * C + 1;
+  float* sa = msm;                       // [TP][ld]
+  float* sb = sa + TP * ld;              // [TP][ld]
+  float* sv = sb + TP * ld;              // [5][TS][TP + 1]
+  __shared__ double red[2][8];
+  const int tiles_x = (W + TS - 1) / TS;
+  const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+  const int b = blockIdx.y;
+  const int x0 = tx * TS, y0 = ty * TS;
+  const size_t img_base = (size_t)b * H * W * C;
+  const int row_elems = TP * C;
+  double sse = 0.0;
+  for (int i = threadIdx.x; i < TP * row_elems; i += blockDim.x) {
+    const int ly = i / row_elems, rem = i % row_elems;
+    const int lx = rem / C;
+    const int gy = y0 + ly - HALO, gx = x0 + lx - HALO;
+    float va = 0.f, vb = 0.f;
+    if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+      const size_t idx = img_base + ((size_t)gy * W + (x0 - HALO)) * C + rem;  // contiguous in rem
+      va = __fmul_rn(__fadd_rn(__ldg(A + idx), pre_add), pre_mul);
+      vb = __fmul_rn(__fadd_rn(__ldg(Bm + idx), pre_add), pre_mul);
+      if (ly >= HALO && ly < HALO + TS && lx >= HALO && lx < HALO + TS) {
+        const float d = __fsub_rn(va, vb);
+        sse += (double)__fmul_rn(d, d);
+      }
+    }
+    sa[ly * ld + rem] = va;
+    sb[ly * ld + rem] = vb;
+  }
+  __syncthreads();
+  const double inv7 = 1.0 / 7.0;
+  double ssum = 0.0;
+  for (int c = 0; c < C; ++c) {
+    // vertical pass (axis 0 first, like scipy): owned rows x (owned + halo) columns
+    for (int i = threadIdx.x; i < TS * TP; i += blockDim.x) {
+      const int r = i / TP, lx = i % TP;
+      double s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0;
+#pragma unroll
+      for (int k = 0; k < 7; ++k) {
+        const float va = sa[(r + k) * ld + lx * C + c], vb = sb[(r + k) * ld + lx * C + c];
+        s0 += (double)va;
+        s1 += (double)vb;
+        s2 += (double)__fmul_rn(va, va);
+        s3 += (double)__fmul_rn(vb, vb);
+        s4 += (double)__fmul_rn(va, vb);
+      }
+      float* o = sv + r * (TP + 1) + lx;
+      o[0] = (float)(s0 * inv7);
+      o[TS * (TP + 1)] = (float)(s1 * inv7);
+      o[2 * TS * (TP + 1)] = (float)(s2 * inv7);
+      o[3 * TS * (TP + 1)] = (float)(s3 * inv7);
+      o[4 * TS * (TP + 1)] = (float)(s4 * inv7);
+    }
+    __syncthreads();
+    // horizontal pass + SSIM expression for owned pixels that survive the 3-px crop
+    for (int i = threadIdx.x; i < TS * TS; i += blockDim.x) {
+      const int r = i / TS, cx = i % TS;
+      const int gy = y0 + r, gx = x0 + cx;
+      if (gy < HALO || gy >= H - HALO || gx < HALO || gx >= W - HALO) continue;
+      double s[5];
+#pragma unroll
+      for (int q = 0; q < 5; ++q) {
+        const float* src = sv + q * TS * (TP + 1) + r * (TP + 1) + cx;
+        double t = 0;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) t += (double)src[k];
+        s[q] = t * inv7;
+      }
+      const float ux = (float)s[0], uy = (float)s[1], uxx = (float)s[2], uyy = (float)s[3], uxy = (float)s[4];
+      const float vx = __fmul_rn(cov_norm, __fsub_rn(uxx, __fmul_rn(ux, ux)));
+      const float vy = __fmul_rn(cov_norm, __fsub_rn(uyy, __fmul_rn(uy, uy)));
+      const float vxy = __fmul_rn(cov_norm, __fsub_rn(uxy, __fmul_rn(ux, uy)));
+      const float a1 = __fadd_rn(__fmul_rn(__fmul_rn(2.0f, ux), uy), c1);
+      const float a2 = __fadd_rn(__fmul_rn(2.0f, vxy), c2);
+      const float b1 = __fadd_rn(__fadd_rn(__fmul_rn(ux, ux), __fmul_rn(uy, uy)), c1);
+      const float b2 = __fadd_rn(__fadd_rn(vx, vy), c2);
+      ssum += (double)__fdiv_rn(__fmul_rn(a1, a2), __fmul_rn(b1, b2));
+    }
+    __syncthreads();
+  }
+  sse = warp_sum(sse);
+  ssum = warp_sum(ssum);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red[0][warp] = sse; red[1][warp] = ssum; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t0 = 0, t1 = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { t0 += red[0][w]; t1 += red[1][w]; }
+    atomicAdd(acc + (size_t)b * 4 + 3, t0);
+    atomicAdd(acc + (size_t)b * 4 + 1, t1);
+  }
+}
+
 // out[b] = {psnr, ssim, mse, sse}
 __global__ void metrics_finalize_kernel(double* __restrict__ acc, int batch, double n_elems, double n_ssim,
                                         double data_range) {
@@ -262,11 +363,26 @@ extern "C" int cic_metrics_psnr_ssim_f32(const float* d_a, const float* d_b, dou
   const float c1 = (float)((0.01 * (double)data_range) * (0.01 * (double)data_range));
   const float c2 = (float)((0.03 * (double)data_range) * (0.03 * (double)data_range));
   const float cov_norm = (float)(49.0 / 48.0);
+  const bool packed = channels <= 4;
+  const size_t smem = packed ? (size_t)(2 * TP * (TP * channels + 1) + 5 * TS * (TP + 1)) * sizeof(float) : 0;
+  if (packed) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      CIC_CHECK_CUDA(cudaFuncSetAttribute(metrics_f32_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+      attr_set = true;
+    }
+  }
   for (int b0 = 0; b0 < batch; b0 += 65535) {
     int nb = batch - b0 < 65535 ? batch - b0 : 65535;
-    dim3 grid(tiles, channels, nb);
-    metrics_f32_kernel<<<grid, 256, 0, st>>>(d_a + (size_t)b0 * h * w * channels, d_b + (size_t)b0 * h * w * channels,
-                                              d_out + (size_t)b0 * 4, h, w, channels, pre_add, pre_mul, c1, c2, cov_norm);
+    const float* pa = d_a + (size_t)b0 * h * w * channels;
+    const float* pb = d_b + (size_t)b0 * h * w * channels;
+    if (packed) {
+      dim3 grid(tiles, nb);
+      metrics_f32_packed_kernel<<<grid, 256, smem, st>>>(pa, pb, d_out + (size_t)b0 * 4, h, w, channels, pre_add, pre_mul, c1, c2, cov_norm);
+    } else {
+      dim3 grid(tiles, channels, nb);
+      metrics_f32_kernel<<<grid, 256, 0, st>>>(pa, pb, d_out + (size_t)b0 * 4, h, w, channels, pre_add, pre_mul, c1, c2, cov_norm);
+    }
     CIC_COUNT_LAUNCH();
     CIC_CHECK_LAUNCH("metrics_f32_kernel");
   }

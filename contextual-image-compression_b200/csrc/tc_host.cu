@@ -80,6 +80,14 @@ static void layer_taps(const TcLayer& L, std::vector<TapDesc>& taps) {
     }
 }
 
+// weights too large to stay resident beside 64-channel rasters but small enough beside 32-channel ones
+static bool raster_prefers_bk32(const TcLayer& L, int N_pad) {
+  if (L.split || L.b_batched || L.splits != 1) return false;
+  const bool dc = L.kind == TC_DECONV_K4S2;
+  const long long wbytes = (long long)(dc ? 4 : 1) * N_pad * L.w.K * 2;
+  return wbytes > 96 * 1024 && wbytes <= 136 * 1024 && (long long)L.batch * L.H * L.W >= 148LL * 128 * 16;
+}
+
 // returns CIC_OK and sets *used = true when the layer was launched on the raster kernel; *used = false means
 // "not eligible, use the per-tap kernel"
 static int try_run_raster(const TcLayer& L, int BK, int N_pad, const TcMaps& act_maps_unused, cudaStream_t st, bool* used) {
@@ -194,7 +202,7 @@ static int try_run_raster(const TcLayer& L, int BK, int N_pad, const TcMaps& act
   p.b_blocks = nph * p.n_tiles * p.ntaps * (p.src_blocks[0] + p.src_blocks[1]);
   const long long resident_bytes = (long long)p.b_blocks * b_slot_bytes;
   static const int no_resident = getenv("CIC_TC_NO_RESIDENT") ? atoi(getenv("CIC_TC_NO_RESIDENT")) : 0;
-  if (!no_resident && resident_bytes <= budget - 2LL * p.a_slot_bytes && resident_bytes <= 96 * 1024 &&
+  if (!no_resident && resident_bytes <= budget - 2LL * p.a_slot_bytes && resident_bytes <= 136 * 1024 &&
       resident_bytes * 148 < (long long)p.total_tiles * 16 * b_slot_bytes) {
     // the whole weight matrix stays in shared memory (only when that is less traffic than streaming it)
     p.b_resident = 1;
@@ -296,6 +304,12 @@ int tc_run_layer(const TcLayer& L, cudaStream_t st) {
                   "tc layer: bf16 output needs N %% 16 == 0 and 16-byte aligned records (N=%d, ld=%d, coff=%d)", L.N, ld, L.epi.out_coff);
     }
     bool used = false;
+    // 64-channel layers whose whole weight matrix fits in shared memory only next to 32-channel rasters (deconv4:
+    // 128 KB of weights + 3 x 25 KB rasters) run with the smaller K block and resident weights
+    if (BK == 64 && raster_prefers_bk32(L, n_pad)) {
+      const int rc32 = try_run_raster(L, 32, n_pad, maps, st, &used);
+      if (rc32 || used) return rc32;
+    }
     const int rc = try_run_raster(L, BK, n_pad, maps, st, &used);
     if (rc || used) return rc;
   }

@@ -151,7 +151,7 @@ class Model:
             host = [b.numpy() for b in host_t]
         return host if self._multi_output else host[0]
 
-    def predict_pipelined(self, x, n_chunks: int = 4, on_chunk=None):
+    def predict_pipelined(self, x, n_chunks=4, on_chunk=None):
         """High-throughput predict for host inputs: the batch is cut into `n_chunks` contiguous chunks that flow
         through three CUDA streams - host->device copies, the model, device->host copies into per-model pinned
         staging buffers - so PCIe traffic overlaps the kernels.  Batch items are independent in every model of the
@@ -163,8 +163,17 @@ class Model:
         hs = [t if t.dtype == torch.float32 else t.to(torch.float32) for t in hs]
         n = hs[0].shape[0]
         dev = runtime.require_cuda()
-        n_chunks = max(1, min(int(n_chunks), n))
-        bounds = [(i * n) // n_chunks for i in range(n_chunks + 1)]
+        if isinstance(n_chunks, (list, tuple)):                     # explicit chunk sizes (small first / last chunks shorten
+            sizes = [int(v) for v in n_chunks if int(v) > 0]        # the exposed first upload and last download)
+            if sum(sizes) != n:
+                raise ValueError(f"chunk sizes {sizes} do not add up to the batch size {n}")
+            bounds = [0]
+            for v in sizes:
+                bounds.append(bounds[-1] + v)
+            n_chunks = len(sizes)
+        else:
+            n_chunks = max(1, min(int(n_chunks), n))
+            bounds = [(i * n) // n_chunks for i in range(n_chunks + 1)]
         compute = torch.cuda.current_stream()
         st = self.__dict__.setdefault("_pipe_streams", {})
         if "in" not in st:

@@ -1,0 +1,298 @@
+// Encoder conv1 on the tensor cores: Conv2D(64, k4, s2, 'same') + bias + LeakyReLU(0.2) of a 3-channel image
+// (GAN_functions.py:300-302) for ONE or BOTH encoders of the adaptive model in a single pass.
+//
+// K = 4*4*3 = 48 is too small for a TMA im2col view (a pixel record is 12 bytes), so the A operand is built in
+// shared memory: four builder warps stage the fp32 input patch of a 128-pixel output tile, and every builder
+// thread gathers the 48 patch values of its output pixel, splits them into bf16 (hi, lo) and stores them as one
+// 128-byte K-major row of the canonical SWIZZLE_128B UMMA layout (K padded to 64 with zeros, generic-proxy stores
+// made visible to the tensor core with fence.proxy.async).  The weights of both encoders ([128][64] bf16 hi/lo,
+// pre-swizzled at plan creation) stay resident in shared memory, so one 3-term split MMA group
+// (hi*hi + lo*hi + hi*lo, 12 tcgen05.mma, fp32 accumulate in TMEM) produces 128 pixels x (64 + 64) channels and
+// the image is read once for both encoders.  A and the accumulator are double-buffered; builders, the MMA warp and
+// the four epilogue warps (tcgen05.ld -> bias -> LeakyReLU -> bf16 hi/lo -> global) overlap across tiles; two CTAs
+// per SM.  This replaces two runs of the CUDA-core direct kernel (direct_conv.cu), which is FFMA-issue-bound
+// (3-register FFMA issues at half rate) at ~16 TFLOP/s.
+#include "plan.cuh"
+#include "tc_gemm.cuh"
+
+namespace cic {
+
+constexpr int C1_K = 64;             // padded K
+constexpr int C1_ROWB = C1_K * 2;    // bytes per A / B row
+constexpr int C1_ABYTES = TC_BM * C1_ROWB;  // one A part (16 KB)
+constexpr int C1_MAX_PATCH = 4 * 258 * 3;   // floats: TW = 128, TH = 1
+
+struct Conv1Params {
+  const float* x;
+  TileMap tm;
+  int batch, H, W, Ho, Wo;
+  int TW, TH, tiles_x, tiles_y, total_tiles;
+  int pad_t, pad_l;
+  const uint8_t* wimg;   // [2 parts][N][128 B], rows pre-swizzled
+  const float* bias;     // [N]
+  __nv_bfloat16* out_hi[2];
+  __nv_bfloat16* out_lo[2];
+};
+
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+template <int N>
+__global__ void __launch_bounds__(288, 2)
+conv1_tc_kernel(const __grid_constant__ Conv1Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* a_buf = smem;                                   // [2 buffers][hi | lo][128 rows x 128 B]
+  uint8_t* b_img = smem + 4 * C1_ABYTES;                   // [hi | lo][N rows x 128 B]
+  float* patch = reinterpret_cast<float*>(b_img + 2 * N * C1_ROWB);
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(patch + C1_MAX_PATCH + 8);
+  uint64_t* a_empty = a_full + 2;
+  uint64_t* tmem_full_bar = a_empty + 2;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int PW3 = (2 * p.TW + 2) * 3, PH = 2 * p.TH + 2;
+
+  // resident weights + zero K padding (chunks 6, 7 of every A row are never written again)
+  for (int i = threadIdx.x; i < 2 * N * C1_ROWB / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(b_img)[i] = __ldg(reinterpret_cast<const uint4*>(p.wimg) + i);
+  for (int i = threadIdx.x; i < 4 * C1_ABYTES / 16; i += blockDim.x) reinterpret_cast<uint4*>(a_buf)[i] = make_uint4(0, 0, 0, 0);
+  if (warp == 4) {
+    if (lane == 0) {
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(&a_full[s], 128); mbar_init(&a_empty[s], 1);
+        mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 4);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 2 * N);
+    tmem_relinquish();
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+
+  if (warp < 4) {
+    // ===== builders: thread r owns row r of the A tile =====
+    const int r = threadIdx.x;
+    const int xl = r % p.TW, yl = r / p.TW;
+    const bool row_ok = yl < p.TH;
+    int lt = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++lt) {
+      const int b = t / tiles_per_img, ti = t % tiles_per_img;
+      const int oy0 = (ti / p.tiles_x) * p.TH, ox0 = (ti % p.tiles_x) * p.TW;
+      const float* xb;
+      size_t row_stride;
+      if (p.tm.tiles_x) {
+        const int tpi = p.tm.tiles_x * p.tm.tiles_y, img = b / tpi, tt = b % tpi;
+        xb = p.x + (((size_t)img * p.tm.IH + (size_t)(tt / p.tm.tiles_x) * p.H) * p.tm.IW + (size_t)(tt % p.tm.tiles_x) * p.W) * 3;
+        row_stride = (size_t)p.tm.IW * 3;
+      } else {
+        xb = p.x + (size_t)b * p.H * p.W * 3;
+        row_stride = (size_t)p.W * 3;
+      }
+      const int iy0 = 2 * oy0 - p.pad_t, ix0 = 2 * ox0 - p.pad_l;
+      named_bar_sync(1, 128);  // everyone is done reading the previous patch
+      for (int i = r; i < PH * PW3; i += 128) {
+        const int pr = i / PW3, cix = i % PW3;
+        const int iy = iy0 + pr, ix = ix0 + cix / 3;
+        float v = 0.f;
+        if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) v = __ldg(xb + (size_t)iy * row_stride + (size_t)ix * 3 + cix % 3);
+        patch[i] = v;
+      }
+      named_bar_sync(1, 128);
+      const int buf = lt & 1;
+      mbar_wait(&a_empty[buf], (((uint32_t)lt >> 1) & 1u) ^ 1u);  // the MMAs that read this buffer have retired
+      if (row_ok) {
+        uint8_t* row_hi = a_buf + (size_t)buf * 2 * C1_ABYTES + (size_t)r * C1_ROWB;
+        uint8_t* row_lo = row_hi + C1_ABYTES;
+        float v[48];
+#pragma unroll
+        for (int ky = 0; ky < 4; ++ky) {
+          const float2* src = reinterpret_cast<const float2*>(patch + (2 * yl + ky) * PW3 + 6 * xl);
+#pragma unroll
+          for (int j = 0; j < 6; ++j) {
+            const float2 f = src[j];
+            v[12 * ky + 2 * j] = f.x;
+            v[12 * ky + 2 * j + 1] = f.y;
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float f0 = v[8 * c + 2 * q], f1 = v[8 * c + 2 * q + 1];
+            const __nv_bfloat162 hh = __floats2bfloat162_rn(f0, f1);
+            hi[q] = *reinterpret_cast<const uint32_t*>(&hh);
+            const __nv_bfloat162 ll = __floats2bfloat162_rn(f0 - __uint_as_float(hi[q] << 16), f1 - __uint_as_float(hi[q] & 0xFFFF0000u));
+            lo[q] = *reinterpret_cast<const uint32_t*>(&ll);
+          }
+          const int off = (c ^ (r & 7)) << 4;  // SWIZZLE_128B: 16-byte chunk index XOR (row mod 8)
+          *reinterpret_cast<uint4*>(row_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(row_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+      }
+      fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
+      mbar_arrive(&a_full[buf]);
+    }
+  } else if (warp == 4) {
+    // ===== MMA issuer =====
+    constexpr uint32_t idesc = umma_idesc_bf16(N);
+    const uint32_t a_lo0 = (smem_u32(a_buf) & 0x3FFFF) >> 4, b_lo0 = (smem_u32(b_img) & 0x3FFFF) >> 4;
+    int lt = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++lt) {
+      const int buf = lt & 1;
+      const uint32_t ph = ((uint32_t)lt >> 1) & 1u;
+      mbar_wait(&tmem_empty_bar[buf], ph ^ 1u);
+      mbar_wait(&a_full[buf], ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t d = tmem_base + (uint32_t)(buf * N);
+        const uint32_t a_hi = a_lo0 + (uint32_t)buf * (2 * C1_ABYTES >> 4), a_lo = a_hi + (C1_ABYTES >> 4);
+        const uint32_t b_hi = b_lo0, b_lo = b_lo0 + (uint32_t)(N * C1_ROWB >> 4);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(d, umma_desc_from_lo<64>(a_hi + 2 * k), umma_desc_from_lo<64>(b_hi + 2 * k), idesc, k != 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(d, umma_desc_from_lo<64>(a_lo + 2 * k), umma_desc_from_lo<64>(b_hi + 2 * k), idesc, 1u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(d, umma_desc_from_lo<64>(a_hi + 2 * k), umma_desc_from_lo<64>(b_lo + 2 * k), idesc, 1u);
+        umma_commit(&a_empty[buf]);
+        umma_commit(&tmem_full_bar[buf]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===== epilogue: warps 5..8, warp w owns TMEM lanes 32*(w%4).. =====
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int xl = r % p.TW, yl = r / p.TW;
+    int lt = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++lt) {
+      const int b = t / tiles_per_img, ti = t % tiles_per_img;
+      const int oy = (ti / p.tiles_x) * p.TH + yl, ox = (ti % p.tiles_x) * p.TW + xl;
+      const bool valid = yl < p.TH && oy < p.Ho && ox < p.Wo;
+      const int buf = lt & 1;
+      mbar_wait_relaxed(&tmem_full_bar[buf], ((uint32_t)lt >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * N);
+      const size_t opix = (((size_t)b * p.Ho + oy) * p.Wo + ox) * 64;
+#pragma unroll 1
+      for (int c = 0; c < N / 32; ++c) {
+        uint32_t v[32];
+        __syncwarp();
+        tmem_ld32(taddr + (uint32_t)(c * 32), v);
+        tmem_ld_wait();
+        if (c == N / 32 - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+        }
+        if (!valid) continue;
+        const int enc = c >> 1, ch0 = (c & 1) * 32;
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + c * 32);
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 bb = __ldg(b4 + j);
+          float f[4] = {__fadd_rn(__uint_as_float(v[4 * j]), bb.x), __fadd_rn(__uint_as_float(v[4 * j + 1]), bb.y),
+                        __fadd_rn(__uint_as_float(v[4 * j + 2]), bb.z), __fadd_rn(__uint_as_float(v[4 * j + 3]), bb.w)};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) f[k] = fmaxf(f[k], __fmul_rn(f[k], 0.2f));  // LeakyReLU(0.2)
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const __nv_bfloat162 hh = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+            const uint32_t hw = *reinterpret_cast<const uint32_t*>(&hh);
+            const __nv_bfloat162 ll = __floats2bfloat162_rn(f[2 * k] - __uint_as_float(hw << 16), f[2 * k + 1] - __uint_as_float(hw & 0xFFFF0000u));
+            hi[2 * j + k] = hw;
+            lo[2 * j + k] = *reinterpret_cast<const uint32_t*>(&ll);
+          }
+        }
+        uint4* dh = reinterpret_cast<uint4*>(p.out_hi[enc] + opix + ch0);
+        uint4* dl = reinterpret_cast<uint4*>(p.out_lo[enc] + opix + ch0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+          dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, 2 * N);
+}
+
+// weights of one or two encoders, (4,4,3,64) fp32 each -> [hi | lo][N][64] bf16 rows in the swizzled smem image
+__global__ void conv1_pack_kernel(const float* __restrict__ w0, const float* __restrict__ w1, uint8_t* __restrict__ img, int N) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * C1_K) return;
+  const int n = i / C1_K, k = i % C1_K;
+  const float* w = n < 64 ? w0 : w1;
+  const float v = k < 48 ? w[k * 64 + (n & 63)] : 0.f;
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+  const size_t off = (size_t)n * C1_ROWB + (((k >> 3) ^ (n & 7)) << 4) + (k & 7) * 2;
+  *reinterpret_cast<__nv_bfloat16*>(img + off) = h;
+  *reinterpret_cast<__nv_bfloat16*>(img + (size_t)N * C1_ROWB + off) = l;
+}
+
+size_t conv1_tc_image_bytes(int n_enc) { return (size_t)2 * 64 * n_enc * C1_ROWB; }
+
+int conv1_tc_pack(const float* w0, const float* w1, uint8_t* img, cudaStream_t st) {
+  const int N = w1 ? 128 : 64;
+  conv1_pack_kernel<<<(N * C1_K + 255) / 256, 256, 0, st>>>(w0, w1, img, N);
+  CIC_COUNT_LAUNCH();
+  CIC_CHECK_LAUNCH("conv1_pack_kernel");
+  return CIC_OK;
+}
+
+template <int N>
+static int launch_conv1_n(const Conv1Params& p, cudaStream_t st) {
+  const size_t smem = 4 * C1_ABYTES + 2 * N * C1_ROWB + (C1_MAX_PATCH + 8) * sizeof(float) + 128 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CIC_CHECK_CUDA(cudaFuncSetAttribute(conv1_tc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const int slots = 2 * sm_count();
+  conv1_tc_kernel<N><<<p.total_tiles < slots ? p.total_tiles : slots, 288, smem, st>>>(p);
+  CIC_COUNT_LAUNCH();
+  CIC_CHECK_LAUNCH("conv1_tc_kernel");
+  return CIC_OK;
+}
+
+// x: (batch, H, W, 3) fp32 (or tiles of larger images, see TileMap); out_*[e]: (batch, H/2, W/2, 64) bf16 of encoder e
+int launch_conv1_tc(const float* x, const uint8_t* wimg, const float* bias, int n_enc, __nv_bfloat16* const* out_hi,
+                    __nv_bfloat16* const* out_lo, int batch, int H, int W, const TileMap& tm, cudaStream_t st) {
+  CIC_REQUIRE(n_enc == 1 || n_enc == 2, "conv1_tc: one or two encoders");
+  CIC_REQUIRE(H % 2 == 0 && W % 2 == 0 && H > 0 && W > 0, "conv1_tc: H and W must be even");
+  if (batch == 0) return CIC_OK;
+  Conv1Params p;
+  memset(&p, 0, sizeof(p));
+  p.x = x; p.tm = tm; p.batch = batch; p.H = H; p.W = W; p.Ho = H / 2; p.Wo = W / 2;
+  int tw = 128;
+  while (tw > p.Wo && tw > 1) tw >>= 1;  // largest power of two <= Wo (capped at 128)
+  p.TW = tw; p.TH = TC_BM / tw;
+  if (p.TH > p.Ho) {
+    int th = 1;
+    while (th * 2 <= p.Ho) th *= 2;
+    p.TH = th;
+  }
+  CIC_REQUIRE((2 * p.TH + 2) * (2 * p.TW + 2) * 3 <= C1_MAX_PATCH, "conv1_tc: patch too large");
+  p.tiles_x = (p.Wo + p.TW - 1) / p.TW; p.tiles_y = (p.Ho + p.TH - 1) / p.TH;
+  const long long total = (long long)batch * p.tiles_x * p.tiles_y;
+  CIC_REQUIRE(total < 2147483647LL, "conv1_tc: too many tiles");
+  p.total_tiles = (int)total;
+  p.pad_t = same_pad_before(H, 4, 2); p.pad_l = same_pad_before(W, 4, 2);
+  p.wimg = wimg; p.bias = bias;
+  for (int e = 0; e < n_enc; ++e) { p.out_hi[e] = out_hi[e]; p.out_lo[e] = out_lo[e]; }
+  return n_enc == 2 ? launch_conv1_n<128>(p, st) : launch_conv1_n<64>(p, st);
+}
+
+}  // namespace cic

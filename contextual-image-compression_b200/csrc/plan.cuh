@@ -104,6 +104,11 @@ struct TileMap {
 };
 int launch_conv_k4s2_c3(const float* x, const float* wgt, const float* bias, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo,
                         float* out_f32, int batch, int H, int W, int act, const TileMap& tm, cudaStream_t st);
+// encoder conv1 on the tensor cores for one or both encoders of the adaptive model (conv1_tc.cu)
+size_t conv1_tc_image_bytes(int n_enc);
+int conv1_tc_pack(const float* w0, const float* w1, uint8_t* img, cudaStream_t st);
+int launch_conv1_tc(const float* x, const uint8_t* wimg, const float* bias, int n_enc, __nv_bfloat16* const* out_hi,
+                    __nv_bfloat16* const* out_lo, int batch, int H, int W, const TileMap& tm, cudaStream_t st);
 int launch_conv_k3s1_c3_pool(const float* x, const float* wgt, const float* bias, __nv_bfloat16* out_hi, __nv_bfloat16* pool_hi,
                              int batch, int H, int W, int act, cudaStream_t st);
 int launch_conv_k3s2_c1(const float* x, const float* wgt, const float* bias, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo,
@@ -139,6 +144,7 @@ struct cic_plan;
 namespace cic {
 // walkers: CIC_PREC_FP32 (plans.cu) and CIC_PREC_TC (plans_tc.cu)
 int build_plan_tc(cic_plan* pl, const cic_tensor* tensors, int n, const std::string& prefix);
+int build_adaptive_tc(cic_plan* pl);
 int autoencoder_forward_f32(cic_plan* pl, Ctx& c, const float* x, float* y, uint8_t* y_u8, int B, int H, int W);
 int encoder_forward_f32(cic_plan* pl, Ctx& c, const float* img, float* latent, float* x1, float* x2, float* x3, int B);
 int generator_forward_f32(cic_plan* pl, Ctx& c, const float* latent, const float* s1, const float* s2, const float* s3,

@@ -712,6 +712,7 @@ extern "C" cic_plan* cic_plan_create(int kind, const cic_tensor* tensors, int n_
     if (!rc) pl->sal_hq.reset(make_sub(CIC_PLAN_SALIENCY, *opts, 2 * base, 0, tensors, n_tensors, "latent_saliency_hq/", &rc));
     if (!rc) pl->sal_lq.reset(make_sub(CIC_PLAN_SALIENCY, *opts, base, 0, tensors, n_tensors, "latent_saliency_lq/", &rc));
     if (!rc) pl->rd.reset(make_sub(CIC_PLAN_RD, *opts, base, 0, tensors, n_tensors, "rd_optimizer/", &rc));
+    if (!rc && opts->precision == CIC_PREC_TC) rc = build_adaptive_tc(pl);
   } else {
     rc = build_any(pl, tensors, n_tensors, "");
   }

@@ -70,6 +70,11 @@ int build_plan_tc(cic_plan* pl, const cic_tensor* tensors, int n, const std::str
     }
     case CIC_PLAN_ENCODER: {
       const int ch[5] = {pl->opts.img_c, 64, 128, 256, 512};
+      if (pl->opts.img_c == 3) {  // conv1 weights as the pre-swizzled shared-memory image of conv1_tc.cu
+        uint8_t* img = (uint8_t*)pl->tcw.alloc("conv1#img", conv1_tc_image_bytes(1));
+        CIC_REQUIRE(img && w.ptr("conv1/kernel"), "tc plan: conv1 weights");
+        if ((rc = conv1_tc_pack(w.ptr("conv1/kernel"), nullptr, img, nullptr))) return rc;
+      }
       for (int i = 2; i <= 4; ++i) {
         const std::string nm = "conv" + std::to_string(i);
         if ((rc = pack(pl, nm, w.ptr(nm + "/kernel"), 16 * ch[i - 1], ch[i], ch[i], true))) return rc;
@@ -113,6 +118,25 @@ int build_plan_tc(cic_plan* pl, const cic_tensor* tensors, int n, const std::str
     default: break;  // the saliency MLPs stay fp32
   }
   if (rc) return rc;
+  CIC_CHECK_CUDA(cudaDeviceSynchronize());
+  return CIC_OK;
+}
+
+// adaptive model: one conv1 pass serves both encoders (weights and biases side by side, hq | lq)
+int build_adaptive_tc(cic_plan* pl) {
+  if (pl->opts.img_c != 3) return CIC_OK;
+  const float* w0 = pl->hq_enc->w.ptr("conv1/kernel");
+  const float* w1 = pl->lq_enc->w.ptr("conv1/kernel");
+  const float* b0 = pl->hq_enc->w.ptr("conv1/bias");
+  const float* b1 = pl->lq_enc->w.ptr("conv1/bias");
+  CIC_REQUIRE(w0 && w1 && b0 && b1, "tc plan: conv1 weights of both encoders");
+  uint8_t* img = (uint8_t*)pl->tcw.alloc("conv1x2#img", conv1_tc_image_bytes(2));
+  float* bias = (float*)pl->tcw.alloc("conv1x2#bias", 128 * sizeof(float));
+  CIC_REQUIRE(img && bias, "tc plan: out of device memory");
+  int rc = conv1_tc_pack(w0, w1, img, nullptr);
+  if (rc) return rc;
+  CIC_CHECK_CUDA(cudaMemcpy(bias, b0, 64 * sizeof(float), cudaMemcpyDeviceToDevice));
+  CIC_CHECK_CUDA(cudaMemcpy(bias + 64, b1, 64 * sizeof(float), cudaMemcpyDeviceToDevice));
   CIC_CHECK_CUDA(cudaDeviceSynchronize());
   return CIC_OK;
 }
@@ -254,7 +278,7 @@ static EncSkips alloc_skips(Ctx& c, size_t px) {
 }
 
 static int encoder_core_tc(cic_plan* pl, Ctx& c, const float* img, float* latent, float* x1_f32, const EncSkips& sk, int B,
-                           const TileMap& tm = TileMap()) {
+                           const TileMap& tm = TileMap(), bool x1_ready = false) {
   const WeightStore& w = pl->w;
   const int H = pl->opts.img_h, W = pl->opts.img_w, C = pl->opts.img_c, L = pl->opts.latent_dim;
   const size_t px = (size_t)B * H * W;
@@ -262,8 +286,17 @@ static int encoder_core_tc(cic_plan* pl, Ctx& c, const float* img, float* latent
   int rc;
   // conv1 (3 -> 64, k4 s2) + LeakyReLU: K = 48 cannot feed a tensor-core K block; a direct CUDA-core kernel writes
   // the (hi, lo) bf16 pair the split-bf16 layers read (:300-302)
-  if (C == 3) {
-    if (!c.dry) {
+  if (x1_ready) {
+    // sk.x1 was produced by the shared conv1 pass of the adaptive model
+  } else if (C == 3 && !x1_f32) {
+    if (!c.dry) {  // tensor cores, im2col built in shared memory (conv1_tc.cu)
+      Scope sc(c, "conv1", 2.0 * (px / 4) * 64 * 16 * C, 4.0 * px * C + 4.0 * px / 4 * 64);
+      bf16* oh[1] = {sk.x1.hi};
+      bf16* ol[1] = {sk.x1.lo};
+      if ((rc = launch_conv1_tc(img, (const uint8_t*)pl->tcw.ptr("conv1#img"), w.ptr("conv1/bias"), 1, oh, ol, B, H, W, tm, c.st))) return rc;
+    }
+  } else if (C == 3) {
+    if (!c.dry) {  // fp32 copy of x1 requested: the CUDA-core kernel writes it in the same pass
       Scope sc(c, "conv1", 2.0 * (px / 4) * 64 * 16 * C, 4.0 * px * C + 4.0 * px / 4 * 64);
       if ((rc = launch_conv_k4s2_c3(img, w.ptr("conv1/kernel"), w.ptr("conv1/bias"), sk.x1.hi, sk.x1.lo, x1_f32, B, H, W, CIC_ACT_LRELU02, tm, c.st))) return rc;
     }
@@ -476,11 +509,20 @@ int adaptive_forward_tc(cic_plan* pl, Ctx& c, const cic_adaptive_io* io, int n_i
   float* lq_lat = io->d_lq_latent ? io->d_lq_latent : c.arena.f32((size_t)nt * base);
   EncSkips hs = alloc_skips(c, tpx), ls = alloc_skips(c, tpx);
   size_t mk = c.arena.mark();
+  const bool shared_conv1 = pl->opts.img_c == 3 && pl->tcw.ptr("conv1x2#img");
+  if (shared_conv1 && !c.dry) {  // conv1 of both encoders in one pass over the image (:300-302 of both build_encoder calls)
+    if (c.prof) c.prof->prefix = "";
+    Scope sc(c, "enc_conv1_x2", 2.0 * 2 * (tpx / 4) * 64 * 48, 4.0 * tpx * 3 + 2 * 4.0 * tpx / 4 * 64);
+    bf16* oh[2] = {hs.x1.hi, ls.x1.hi};
+    bf16* ol[2] = {hs.x1.lo, ls.x1.lo};
+    if ((rc = launch_conv1_tc(img_t, (const uint8_t*)pl->tcw.ptr("conv1x2#img"), (const float*)pl->tcw.ptr("conv1x2#bias"), 2, oh, ol, nt, T, T,
+                              tm, c.st))) return rc;
+  }
   if (c.prof) c.prof->prefix = "hq_enc/";
-  if ((rc = encoder_core_tc(pl->hq_enc.get(), c, img_t, hq_lat, nullptr, hs, nt, tm))) return rc;
+  if ((rc = encoder_core_tc(pl->hq_enc.get(), c, img_t, hq_lat, nullptr, hs, nt, tm, shared_conv1))) return rc;
   c.arena.release(mk);
   if (c.prof) c.prof->prefix = "lq_enc/";
-  if ((rc = encoder_core_tc(pl->lq_enc.get(), c, img_t, lq_lat, nullptr, ls, nt, tm))) return rc;
+  if ((rc = encoder_core_tc(pl->lq_enc.get(), c, img_t, lq_lat, nullptr, ls, nt, tm, shared_conv1))) return rc;
   c.arena.release(mk);
   // 3. latent saliency (:619-620), fp32
   float* sal_hq = c.arena.f32(nt);

@@ -8,6 +8,7 @@
 namespace cic {
 
 thread_local long long g_launch_count = 0;
+thread_local int g_last_kernel_kind = 0;
 static thread_local char g_err[1024] = "";
 
 void set_error(const char* fmt, ...) {

@@ -45,6 +45,9 @@ void set_error(const char* fmt, ...);
 // bench.py can report `gpu_launches` from the library's own bookkeeping.
 extern thread_local long long g_launch_count;
 #define CIC_COUNT_LAUNCH() (++cic::g_launch_count)
+// kernel class of the last heavy launch (the per-layer profiler tags its records with it)
+enum KernelKind { KK_NONE = 0, KK_TC_GEMM = 1, KK_TC_CONV = 2, KK_TC_CONV1 = 3, KK_DIRECT = 4, KK_SIMT = 5 };
+extern thread_local int g_last_kernel_kind;
 
 int sm_count();
 

@@ -264,6 +264,7 @@ static int launch_conv1_n(const Conv1Params& p, cudaStream_t st) {
   conv1_tc_kernel<N><<<p.total_tiles < slots ? p.total_tiles : slots, 288, smem, st>>>(p);
   CIC_COUNT_LAUNCH();
   CIC_CHECK_LAUNCH("conv1_tc_kernel");
+  g_last_kernel_kind = KK_TC_CONV1;
   return CIC_OK;
 }
 

@@ -168,6 +168,7 @@ static int launch_direct(const char* name, const float* x, const float* wgt, con
         same_pad_before(W, KS, STRIDE), act, tm);
     CIC_COUNT_LAUNCH();
     CIC_CHECK_LAUNCH(name);
+    g_last_kernel_kind = KK_DIRECT;
   }
   return CIC_OK;
 }

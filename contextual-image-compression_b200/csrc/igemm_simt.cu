@@ -287,6 +287,7 @@ int launch_igemm(const IGemmParams& p, cudaStream_t st) {
   }
   CIC_COUNT_LAUNCH();
   CIC_CHECK_LAUNCH("igemm_f32_kernel");
+  g_last_kernel_kind = KK_SIMT;
   if (p.splits > 1) return launch_splitk_reduce(p, st);
   return CIC_OK;
 }

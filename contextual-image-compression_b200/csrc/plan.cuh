@@ -62,6 +62,7 @@ struct Profiler {
     std::string name;
     cudaEvent_t e0, e1;
     double flops, bytes;
+    int kind;  // KernelKind of the layer's heavy kernel
   };
   bool on = false;
   std::vector<Rec> recs;
@@ -91,6 +92,7 @@ struct Scope {  // RAII layer bracket
   ~Scope() {
     if (idx >= 0) c.prof->end(idx, c.st);
   }
+  Scope(const Scope&) = delete;
 };
 
 int run_dense(const float* x, const float* kernel, const float* bias, const float* scale, const float* shift, float* y,

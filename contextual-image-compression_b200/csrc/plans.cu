@@ -54,13 +54,17 @@ void Profiler::reset() {
   recs.clear();
 }
 int Profiler::begin(const std::string& name, double flops, double bytes, cudaStream_t st) {
-  Rec r{prefix + name, get_event(), get_event(), flops, bytes};
+  Rec r{prefix + name, get_event(), get_event(), flops, bytes, 0};
+  g_last_kernel_kind = KK_NONE;
   cudaEventRecord(r.e0, st);
   recs.push_back(r);
   return (int)recs.size() - 1;
 }
 void Profiler::end(int idx, cudaStream_t st) {
-  if (idx >= 0 && idx < (int)recs.size()) cudaEventRecord(recs[idx].e1, st);
+  if (idx >= 0 && idx < (int)recs.size()) {
+    cudaEventRecord(recs[idx].e1, st);
+    recs[idx].kind = g_last_kernel_kind;
+  }
 }
 std::string Profiler::report() {
   std::string out;
@@ -69,7 +73,7 @@ std::string Profiler::report() {
     float ms = 0.f;
     cudaEventSynchronize(r.e1);
     cudaEventElapsedTime(&ms, r.e0, r.e1);
-    snprintf(line, sizeof(line), "%s,%.6f,%.6e,%.6e\n", r.name.c_str(), ms, r.flops, r.bytes);
+    snprintf(line, sizeof(line), "%s,%.6f,%.6e,%.6e,%d\n", r.name.c_str(), ms, r.flops, r.bytes, r.kind);
     out += line;
   }
   return out;

@@ -320,6 +320,7 @@ static int launch_conv_one(const TcMaps& maps, const TcvParams& p, cudaStream_t 
   tc_conv_kernel<BK, SPLIT, RESIDENT><<<grid, 224, smem, st>>>(maps, p);
   CIC_COUNT_LAUNCH();
   CIC_CHECK_LAUNCH("tc_conv_kernel");
+  g_last_kernel_kind = KK_TC_CONV;
   return CIC_OK;
 }
 

@@ -257,6 +257,7 @@ static int launch_one(const TcMaps& maps, const TcParams& p, cudaStream_t st) {
   tc_gemm_kernel<BN, BK, SPLIT><<<grid, 192, Cfg::kSmemBytes, st>>>(maps, p);
   CIC_COUNT_LAUNCH();
   CIC_CHECK_LAUNCH("tc_gemm_kernel");
+  g_last_kernel_kind = KK_TC_GEMM;
   return CIC_OK;
 }
 

@@ -66,14 +66,14 @@ class Plan:
         _lib.check(_lib.lib.cic_plan_set_profiling(self.handle, int(on)))
 
     def profile(self):
-        """[(layer, ms, flops, bytes)] of the last forward call (needs set_profiling(True) before it)."""
+        """[(layer, ms, flops, bytes, kernel_kind)] of the last forward call (needs set_profiling(True) before it)."""
         n = int(_lib.lib.cic_plan_get_profile(self.handle, None, 0))
         buf = C.create_string_buffer(n + 16)
         _lib.lib.cic_plan_get_profile(self.handle, buf, n + 16)
         rows = []
         for line in buf.value.decode().splitlines():
-            name, ms, fl, by = line.rsplit(",", 3)
-            rows.append((name, float(ms), float(fl), float(by)))
+            name, ms, fl, by, kind = line.rsplit(",", 4)
+            rows.append((name, float(ms), float(fl), float(by), int(kind)))
         return rows
 
     def __del__(self):

@@ -9,6 +9,7 @@
 #include "tc_host.cuh"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace cic {
@@ -66,6 +67,11 @@ int build_plan_tc(cic_plan* pl, const cic_tensor* tensors, int n, const std::str
       for (auto& l : L)
         if ((rc = pack(pl, l.name, w.ptr(std::string(l.name) + "/kernel"), 9 * l.cin, l.cout, l.cout, false))) return rc;
       if (pl->opts.img_c <= 16) rc = pack(pl, "conv_out", w.ptr("conv_out/kernel"), 9 * 64, pl->opts.img_c, 16, false);
+      if (!rc && pl->opts.img_c == 3) {  // column-strip kernel image (conv_rows_tc.cu)
+        uint8_t* img = (uint8_t*)pl->tcw.alloc("conv_out#rows", conv_rows_image_bytes(3, 64));
+        CIC_REQUIRE(img, "tc plan: out of device memory");
+        rc = conv_rows_pack(w.ptr("conv_out/kernel"), img, 3, 64, 3, nullptr);
+      }
       break;
     }
     case CIC_PLAN_ENCODER: {
@@ -110,6 +116,11 @@ int build_plan_tc(cic_plan* pl, const cic_tensor* tensors, int n, const std::str
                                    hi + (size_t)p * cout[i] * 4 * cin[i], nullptr, nullptr))) return rc;
       }
       if (pl->opts.img_c <= 16) rc = pack(pl, "conv_out", w.ptr("conv_out/kernel"), 16 * 32, pl->opts.img_c, 16, false);
+      if (!rc && pl->opts.img_c == 3) {
+        uint8_t* img = (uint8_t*)pl->tcw.alloc("conv_out#rows", conv_rows_image_bytes(4, 32));
+        CIC_REQUIRE(img, "tc plan: out of device memory");
+        rc = conv_rows_pack(w.ptr("conv_out/kernel"), img, 4, 32, 3, nullptr);
+      }
       break;
     }
     case CIC_PLAN_RD:  // conv2 (32 -> 64, k3 s2) on the tensor cores, split-bf16 (rd_params are compared at 2e-5)
@@ -399,6 +410,16 @@ static int generator_core_tc(cic_plan* pl, Ctx& c, const float* latent, const bf
   DC(4, view(g3, 64), &k1, 8 * h16, 8 * w16, 128, 32, g4);
 #undef DC
   // :273 Conv2D(3, k4, 'same', tanh): pad 1 before / 2 after
+  static const int no_rows = getenv("CIC_TC_NO_ROWS") ? atoi(getenv("CIC_TC_NO_ROWS")) : 0;
+  if (C == 3 && !no_rows) {  // column-strip formulation (kx folded into K, ky into N)
+    if (!c.dry) {
+      Scope sc(c, "conv_out", 2.0 * px * 16 * 32 * C, 2.0 * px * 32 + 4.0 * px * C);
+      TcAct src = view(g4, 32);
+      if ((rc = launch_conv_rows_tc(&src, 1, (const uint8_t*)pl->tcw.ptr("conv_out#rows"), w.ptr("conv_out/bias"), 4, C, CIC_ACT_TANH, out, B, H, W, tm, c.st))) return rc;
+    }
+    c.arena.release(mk);
+    return CIC_OK;
+  }
   TcEpilogue e;
   e.bias = w.ptr("conv_out/bias"); e.act = CIC_ACT_TANH; e.out_mode = TC_OUT_F32; e.out_hi = out; e.out_ld = C;
   e.tm_tx = tm.tiles_x; e.tm_ty = tm.tiles_y; e.tm_IH = tm.IH; e.tm_IW = tm.IW;  // write straight into the image layout
@@ -452,9 +473,18 @@ int autoencoder_forward_tc(cic_plan* pl, Ctx& c, const float* x, float* y, uint8
   AE_CONV("conv5", view(y3u, 64), &x2rv, H / 2, W / 2, 128, 32, y5u, 1);                      // :26 concat, :28, :29 UpSampling2D
   AE_CONV("conv_x1", view(x1, 32), nullptr, H, W, 32, 32, x1r, 0);                            // :32
 #undef AE_CONV
-  TcEpilogue e;                                                                                // :33 concat, :35 Conv2D(3, sigmoid)
-  e.bias = w.ptr("conv_out/bias"); e.act = CIC_ACT_SIGMOID; e.out_mode = TC_OUT_F32; e.out_hi = y; e.out_ld = C;
-  if ((rc = conv_tc(c, "conv_out", TC_CONV_S1, view(y5u, 32), &x1rv, B, H, W, 3, 3, 1, mat(pl, "conv_out", 9 * 64, 16), C, false, e))) return rc;
+  static const int no_rows = getenv("CIC_TC_NO_ROWS") ? atoi(getenv("CIC_TC_NO_ROWS")) : 0;
+  if (!no_rows) {                                                                              // :33 concat, :35 Conv2D(3, sigmoid)
+    if (!c.dry) {
+      Scope sc(c, "conv_out", 2.0 * px * 9 * 64 * C, 2.0 * px * 64 + 4.0 * px * C);
+      TcAct srcs[2] = {view(y5u, 32), x1rv};
+      if ((rc = launch_conv_rows_tc(srcs, 2, (const uint8_t*)pl->tcw.ptr("conv_out#rows"), w.ptr("conv_out/bias"), 3, C, CIC_ACT_SIGMOID, y, B, H, W, TileMap(), c.st))) return rc;
+    }
+  } else {
+    TcEpilogue e;
+    e.bias = w.ptr("conv_out/bias"); e.act = CIC_ACT_SIGMOID; e.out_mode = TC_OUT_F32; e.out_hi = y; e.out_ld = C;
+    if ((rc = conv_tc(c, "conv_out", TC_CONV_S1, view(y5u, 32), &x1rv, B, H, W, 3, 3, 1, mat(pl, "conv_out", 9 * 64, 16), C, false, e))) return rc;
+  }
   c.arena.release(mk);
   if (c.dry) return CIC_OK;
   Scope sc(c, "cast_u8", 0, 5.0 * px * C);

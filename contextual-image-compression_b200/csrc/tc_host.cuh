@@ -68,6 +68,12 @@ int tc_pack_weight(const float* src, int K, int N, int N_pad, int ld, bf16* hi, 
 int tc_split_f32(const float* src, bf16* hi, bf16* lo, size_t n, cudaStream_t st);
 // bf16 hi (+ lo) -> fp32, with strided source records (ld, coff) -> dense C
 int tc_join_to_f32(const bf16* hi, const bf16* lo, float* dst, size_t pixels, int C, int ld, int coff, cudaStream_t st);
+// tiny-Cout output convs by column strips (conv_rows_tc.cu)
+struct TileMap;
+size_t conv_rows_image_bytes(int ks, int cin);
+int conv_rows_pack(const float* w, uint8_t* img, int ks, int cin, int cout, cudaStream_t st);
+int launch_conv_rows_tc(const TcAct* srcs, int nsrc, const uint8_t* wimg, const float* bias, int ks, int cout, int act, float* out,
+                        int batch, int H, int W, const TileMap& tm, cudaStream_t st);
 // MaxPooling2D((2,2)) on NHWC bf16 (even H, W; C % 8 == 0)
 int tc_maxpool2x2_bf16(const bf16* x, bf16* y, int batch, int H, int W, int C, cudaStream_t st);
 // split-K partials [splits][M][N] -> epilogue -> fp32 [M][N] and/or bf16 hi/lo [M][N]

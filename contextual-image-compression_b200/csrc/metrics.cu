@@ -158,53 +158,75 @@ metrics_f32_packed_kernel(const float* __restrict__ A, const float* __restrict__
     sb[ly * ld + rem] = vb;
   }
   __syncthreads();
+  // Window sums slide: s += entering - leaving, all in double.  For image-range data the double sum of 7 floats is
+  // exact, so this equals a fresh 7-term sum, with 10 instead of 35 float->double conversions per output (the
+  // conversion pipe, 16/clk/SM, bounded the first version of this kernel).
   const double inv7 = 1.0 / 7.0;
   double ssum = 0.0;
   for (int c = 0; c < C; ++c) {
-    // vertical pass (axis 0 first, like scipy): owned rows x (owned + halo) columns
-    for (int i = threadIdx.x; i < TS * TP; i += blockDim.x) {
-      const int r = i / TP, lx = i % TP;
+    // vertical pass (axis 0 first, like scipy): a thread per (column, 8-row segment) slides down its segment
+    if (threadIdx.x < 4 * TP) {
+      const int lx = threadIdx.x % TP, r0 = (threadIdx.x / TP) * 8;
+      const float* pa = sa + r0 * ld + lx * C + c;
+      const float* pb = sb + r0 * ld + lx * C + c;
       double s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0;
 #pragma unroll
       for (int k = 0; k < 7; ++k) {
-        const float va = sa[(r + k) * ld + lx * C + c], vb = sb[(r + k) * ld + lx * C + c];
-        s0 += (double)va;
-        s1 += (double)vb;
-        s2 += (double)__fmul_rn(va, va);
-        s3 += (double)__fmul_rn(vb, vb);
-        s4 += (double)__fmul_rn(va, vb);
+        const float va = pa[k * ld], vb = pb[k * ld];
+        s0 += (double)va; s1 += (double)vb;
+        s2 += (double)__fmul_rn(va, va); s3 += (double)__fmul_rn(vb, vb); s4 += (double)__fmul_rn(va, vb);
       }
-      float* o = sv + r * (TP + 1) + lx;
-      o[0] = (float)(s0 * inv7);
-      o[TS * (TP + 1)] = (float)(s1 * inv7);
-      o[2 * TS * (TP + 1)] = (float)(s2 * inv7);
-      o[3 * TS * (TP + 1)] = (float)(s3 * inv7);
-      o[4 * TS * (TP + 1)] = (float)(s4 * inv7);
+      float* o = sv + r0 * (TP + 1) + lx;
+      for (int r = 0;; ++r) {
+        o[0] = (float)(s0 * inv7);
+        o[TS * (TP + 1)] = (float)(s1 * inv7);
+        o[2 * TS * (TP + 1)] = (float)(s2 * inv7);
+        o[3 * TS * (TP + 1)] = (float)(s3 * inv7);
+        o[4 * TS * (TP + 1)] = (float)(s4 * inv7);
+        if (r == 7) break;
+        const float na = pa[(r + 7) * ld], nb = pb[(r + 7) * ld], oa = pa[r * ld], ob = pb[r * ld];
+        s0 += (double)na - (double)oa;
+        s1 += (double)nb - (double)ob;
+        s2 += (double)__fmul_rn(na, na) - (double)__fmul_rn(oa, oa);
+        s3 += (double)__fmul_rn(nb, nb) - (double)__fmul_rn(ob, ob);
+        s4 += (double)__fmul_rn(na, nb) - (double)__fmul_rn(oa, ob);
+        o += TP + 1;
+      }
     }
     __syncthreads();
-    // horizontal pass + SSIM expression for owned pixels that survive the 3-px crop
-    for (int i = threadIdx.x; i < TS * TS; i += blockDim.x) {
-      const int r = i / TS, cx = i % TS;
-      const int gy = y0 + r, gx = x0 + cx;
-      if (gy < HALO || gy >= H - HALO || gx < HALO || gx >= W - HALO) continue;
+    // horizontal pass + SSIM expression: 8 threads per row, each slides over 4 consecutive owned columns
+    {
+      const int r = threadIdx.x >> 3, cx0 = (threadIdx.x & 7) * 4;
+      const int gy = y0 + r;
+      const float* src = sv + r * (TP + 1) + cx0;
       double s[5];
 #pragma unroll
       for (int q = 0; q < 5; ++q) {
-        const float* src = sv + q * TS * (TP + 1) + r * (TP + 1) + cx;
         double t = 0;
 #pragma unroll
-        for (int k = 0; k < 7; ++k) t += (double)src[k];
-        s[q] = t * inv7;
+        for (int k = 0; k < 7; ++k) t += (double)src[q * TS * (TP + 1) + k];
+        s[q] = t;
       }
-      const float ux = (float)s[0], uy = (float)s[1], uxx = (float)s[2], uyy = (float)s[3], uxy = (float)s[4];
-      const float vx = __fmul_rn(cov_norm, __fsub_rn(uxx, __fmul_rn(ux, ux)));
-      const float vy = __fmul_rn(cov_norm, __fsub_rn(uyy, __fmul_rn(uy, uy)));
-      const float vxy = __fmul_rn(cov_norm, __fsub_rn(uxy, __fmul_rn(ux, uy)));
-      const float a1 = __fadd_rn(__fmul_rn(__fmul_rn(2.0f, ux), uy), c1);
-      const float a2 = __fadd_rn(__fmul_rn(2.0f, vxy), c2);
-      const float b1 = __fadd_rn(__fadd_rn(__fmul_rn(ux, ux), __fmul_rn(uy, uy)), c1);
-      const float b2 = __fadd_rn(__fadd_rn(vx, vy), c2);
-      ssum += (double)__fdiv_rn(__fmul_rn(a1, a2), __fmul_rn(b1, b2));
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int cx = cx0 + j, gx = x0 + cx;
+        if (!(gy < HALO || gy >= H - HALO || gx < HALO || gx >= W - HALO)) {
+          const float ux = (float)(s[0] * inv7), uy = (float)(s[1] * inv7), uxx = (float)(s[2] * inv7), uyy = (float)(s[3] * inv7),
+                      uxy = (float)(s[4] * inv7);
+          const float vx = __fmul_rn(cov_norm, __fsub_rn(uxx, __fmul_rn(ux, ux)));
+          const float vy = __fmul_rn(cov_norm, __fsub_rn(uyy, __fmul_rn(uy, uy)));
+          const float vxy = __fmul_rn(cov_norm, __fsub_rn(uxy, __fmul_rn(ux, uy)));
+          const float a1 = __fadd_rn(__fmul_rn(__fmul_rn(2.0f, ux), uy), c1);
+          const float a2 = __fadd_rn(__fmul_rn(2.0f, vxy), c2);
+          const float b1 = __fadd_rn(__fadd_rn(__fmul_rn(ux, ux), __fmul_rn(uy, uy)), c1);
+          const float b2 = __fadd_rn(__fadd_rn(vx, vy), c2);
+          ssum += (double)__fdiv_rn(__fmul_rn(a1, a2), __fmul_rn(b1, b2));
+        }
+        if (j < 3) {
+#pragma unroll
+          for (int q = 0; q < 5; ++q) s[q] += (double)src[q * TS * (TP + 1) + j + 7] - (double)src[q * TS * (TP + 1) + j];
+        }
+      }
     }
     __syncthreads();
   }

@@ -83,6 +83,14 @@ __device__ __forceinline__ float dyn_threshold(float m, float thr) {
   return sigmoidf_(__fmul_rn(__fsub_rn(es, thr), 20.0f));
 }
 
+// 256-bit global store (sm_100: STG.E.ENL2.256): a lane writes one whole 32-byte sector, so strided per-lane
+// records are not written as half-sector pieces.  p must be 32-byte aligned.
+__device__ __forceinline__ void st_global_v8(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f, uint32_t g,
+                                             uint32_t h) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e), "r"(f), "r"(g), "r"(h)
+               : "memory");
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

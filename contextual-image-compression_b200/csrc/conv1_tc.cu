@@ -98,12 +98,20 @@ conv1_tc_kernel(const __grid_constant__ Conv1Params p) {
       }
       const int iy0 = 2 * oy0 - p.pad_t, ix0 = 2 * ox0 - p.pad_l;
       named_bar_sync(1, 128);  // everyone is done reading the previous patch
-      for (int i = r; i < PH * PW3; i += 128) {
-        const int pr = i / PW3, cix = i % PW3;
-        const int iy = iy0 + pr, ix = ix0 + cix / 3;
-        float v = 0.f;
-        if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) v = __ldg(xb + (size_t)iy * row_stride + (size_t)ix * 3 + cix % 3);
-        patch[i] = v;
+      {
+        // all loads of the tile in flight at once: 4-byte cp.async with zero fill outside the image / tile
+        const uint32_t patch_s = smem_u32(patch);
+        const float* row0 = xb + (long long)ix0 * 3;
+        int pr = 0, cix = r;  // r < 128 < PW3
+        for (int i = r; i < PH * PW3; i += 128) {
+          const int iy = iy0 + pr, ix = ix0 + (int)(((unsigned)cix * 43691u) >> 17);  // cix / 3 for cix < 98304
+          const bool ok = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+          const float* src = ok ? row0 + (size_t)iy * row_stride + cix : p.x;
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(patch_s + (uint32_t)i * 4u), "l"(src), "r"(ok ? 4 : 0) : "memory");
+          cix += 128;
+          if (cix >= PW3) { cix -= PW3; ++pr; }
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
       }
       named_bar_sync(1, 128);
       const int buf = lt & 1;
@@ -213,12 +221,12 @@ conv1_tc_kernel(const __grid_constant__ Conv1Params p) {
             lo[2 * j + k] = *reinterpret_cast<const uint32_t*>(&ll);
           }
         }
-        uint4* dh = reinterpret_cast<uint4*>(p.out_hi[enc] + opix + ch0);
-        uint4* dl = reinterpret_cast<uint4*>(p.out_lo[enc] + opix + ch0);
+        __nv_bfloat16* dh = p.out_hi[enc] + opix + ch0;  // 64-byte aligned: whole-sector 256-bit stores
+        __nv_bfloat16* dl = p.out_lo[enc] + opix + ch0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-          dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+        for (int j = 0; j < 2; ++j) {
+          st_global_v8(dh + 16 * j, hi[8 * j], hi[8 * j + 1], hi[8 * j + 2], hi[8 * j + 3], hi[8 * j + 4], hi[8 * j + 5], hi[8 * j + 6], hi[8 * j + 7]);
+          st_global_v8(dl + 16 * j, lo[8 * j], lo[8 * j + 1], lo[8 * j + 2], lo[8 * j + 3], lo[8 * j + 4], lo[8 * j + 5], lo[8 * j + 6], lo[8 * j + 7]);
         }
       }
     }

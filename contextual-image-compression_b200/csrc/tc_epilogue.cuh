@@ -52,7 +52,11 @@ __device__ __forceinline__ void tc_epilogue_store(const TcEpi& e, const TcRow& r
   if (e.out_mode == TC_OUT_PARTIAL) {
     const long long mrow = ((long long)r.b * e.Ho + r.oy) * e.Wo + r.ox;
     float* dst = reinterpret_cast<float*>(e.out_hi) + ((long long)r.split * e.m_total + mrow) * e.N + n0;
-    if (full && (e.N & 3) == 0) {
+    if (full && (e.N & 7) == 0) {
+#pragma unroll
+      for (int j = 0; j < CH / 8; ++j)
+        st_global_v8(dst + 8 * j, v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3], v[8 * j + 4], v[8 * j + 5], v[8 * j + 6], v[8 * j + 7]);
+    } else if (full && (e.N & 3) == 0) {
 #pragma unroll
       for (int j = 0; j < CH / 4; ++j)
         reinterpret_cast<uint4*>(dst)[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -125,7 +129,12 @@ __device__ __forceinline__ void tc_epilogue_store(const TcEpi& e, const TcRow& r
   }
   if (e.out_mode == TC_OUT_F32) {
     float* dst = reinterpret_cast<float*>(e.out_hi) + opix * e.out_ld + e.out_coff + n0;
-    if (full && ((e.out_ld | e.out_coff) & 3) == 0) {
+    if (full && ((e.out_ld | e.out_coff) & 7) == 0) {
+#pragma unroll
+      for (int j = 0; j < CH / 8; ++j)
+        st_global_v8(dst + 8 * j, __float_as_uint(f[8 * j]), __float_as_uint(f[8 * j + 1]), __float_as_uint(f[8 * j + 2]), __float_as_uint(f[8 * j + 3]),
+                     __float_as_uint(f[8 * j + 4]), __float_as_uint(f[8 * j + 5]), __float_as_uint(f[8 * j + 6]), __float_as_uint(f[8 * j + 7]));
+    } else if (full && ((e.out_ld | e.out_coff) & 3) == 0) {
 #pragma unroll
       for (int j = 0; j < CH / 4; ++j) reinterpret_cast<float4*>(dst)[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
     } else {
@@ -177,17 +186,31 @@ __device__ __forceinline__ void tc_epilogue_store(const TcEpi& e, const TcRow& r
       }
     }
     const int reps = e.up2 ? 2 : 1;
+    const bool wide_ok = ((e.out_ld | e.out_coff) & 15) == 0;
 #pragma unroll 1
     for (int rr = 0; rr < reps * reps; ++rr) {
       long long o = idx;
       if (e.up2) o = ((((long long)r.b * e.out_H + (r.oy * 2 + (rr >> 1))) * e.out_W) + (r.ox * 2 + (rr & 1))) * e.out_ld + e.out_coff + n0;
-      uint4* dh = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(e.out_hi) + o);
+      __nv_bfloat16* ph = reinterpret_cast<__nv_bfloat16*>(e.out_hi) + o;
+      __nv_bfloat16* pl = e.out_lo ? reinterpret_cast<__nv_bfloat16*>(e.out_lo) + o : nullptr;
+      if (wide_ok) {  // 32-byte aligned records: whole-sector 256-bit stores
 #pragma unroll
-      for (int j = 0; j < CH / 8; ++j) dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-      if (e.out_lo) {
-        uint4* dl = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(e.out_lo) + o);
+        for (int j = 0; j < CH / 16; ++j)
+          st_global_v8(ph + 16 * j, hi[8 * j], hi[8 * j + 1], hi[8 * j + 2], hi[8 * j + 3], hi[8 * j + 4], hi[8 * j + 5], hi[8 * j + 6], hi[8 * j + 7]);
+        if (pl) {
 #pragma unroll
-        for (int j = 0; j < CH / 8; ++j) dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+          for (int j = 0; j < CH / 16; ++j)
+            st_global_v8(pl + 16 * j, lo[8 * j], lo[8 * j + 1], lo[8 * j + 2], lo[8 * j + 3], lo[8 * j + 4], lo[8 * j + 5], lo[8 * j + 6], lo[8 * j + 7]);
+        }
+      } else {
+        uint4* dh = reinterpret_cast<uint4*>(ph);
+#pragma unroll
+        for (int j = 0; j < CH / 8; ++j) dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+        if (pl) {
+          uint4* dl = reinterpret_cast<uint4*>(pl);
+#pragma unroll
+          for (int j = 0; j < CH / 8; ++j) dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+        }
       }
     }
   } else {  // TC_OUT_BF16_T: out[b][n][position] (V^T for the attention PV product)

@@ -214,7 +214,8 @@ static int attention_tc(cic_plan* pl, Ctx& c, const ActBuf& x, const ActBuf& y, 
   const WeightStore& w = pl->w;
   const int dq = C / 8;
   CIC_REQUIRE(tokens % 32 == 0, "attention (tc): token count %d must be a multiple of 32", tokens);
-  const int chunk_max = 32;  // images per pass: bounds the tokens x tokens score workspace
+  static const int chunk_env = getenv("CIC_ATTN_CHUNK") ? atoi(getenv("CIC_ATTN_CHUNK")) : 0;
+  const int chunk_max = chunk_env > 0 ? chunk_env : 128;  // images per pass: bounds the tokens x tokens score workspace
   const int chunk = batch < chunk_max ? batch : chunk_max;
   const size_t mk = c.arena.mark();
   ActBuf qk = alloc_act(c, (size_t)chunk * tokens * 2 * dq, true);

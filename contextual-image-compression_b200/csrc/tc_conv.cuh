@@ -30,6 +30,8 @@ constexpr int TCV_MAX_RASTERS = 16;
 constexpr int TCV_MAX_OPS = 16;
 constexpr int TCV_MAX_PASS = 4;
 constexpr int TCV_MAX_SLOTS = 16;
+constexpr int TCV_MAX_ISSUERS = 4;
+constexpr int TCV_MAX_THREADS = 448;  // warps: 0 rasters, 1 issuer 0, 2-5 epilogue 0, 6 weights, 7 issuer 1, 8-11 epilogue 1, 12-13 issuers 2-3
 constexpr int TCV_ACC_COLS = 256;  // TMEM columns per accumulator stage
 
 struct TcvRaster {
@@ -49,7 +51,7 @@ struct TcvOp {
 };
 
 // flags of the MMA op table the kernel builds in shared memory
-enum { TCV_F_FIRST = 1, TCV_F_NEW_RASTER = 2, TCV_F_LAST_OF_RASTER = 4, TCV_F_NEW_BGROUP = 8, TCV_F_LAST_OF_BGROUP = 16 };
+enum { TCV_F_FIRST = 1, TCV_F_NEW_RASTER = 2, TCV_F_LAST_OF_RASTER = 4, TCV_F_NEW_BGROUP = 8, TCV_F_LAST_OF_BGROUP = 16, TCV_F_MINE = 32 };
 
 struct TcvPass {
   int nrast;
@@ -104,6 +106,9 @@ struct TcvParams {
   int b_slot_bytes;       // one weight block [BN x BK]; in split mode [hi | lo]
   int b_group;            // weight blocks per ring slot (loaded under one mbarrier); ring slot = b_group * b_slot_bytes
   uint32_t a_tx_bytes, b_tx_bytes;
+  int nw;                 // MMA issuer warps (accumulators a % nw == w belong to issuer w); > 1 only with resident weights
+  int ne;                 // epilogue groups of four warps (1 or 2)
+  int dbg;                // CIC_TC_DBG elimination bits: 1 no MMA issue, 2 no weight loads, 4 no raster loads, 8 no stores
   TcEpi epi;
   TcvPass pass[TCV_MAX_PASS];
 };

@@ -197,7 +197,7 @@ static int try_run_raster(const TcLayer& L, int BK, int N_pad, const TcMaps& act
   p.a_tx_bytes = (uint32_t)(raster_rows * 2 * BK * parts);
   p.b_slot_bytes = b_slot_bytes;
   p.b_tx_bytes = (uint32_t)b_slot_bytes;
-  const int budget = 220 * 1024;
+  const int budget = 218 * 1024;
   p.ntaps = dc ? 4 : L.kh * L.kw;
   p.b_blocks = nph * p.n_tiles * p.ntaps * (p.src_blocks[0] + p.src_blocks[1]);
   const long long resident_bytes = (long long)p.b_blocks * b_slot_bytes;
@@ -210,7 +210,8 @@ static int try_run_raster(const TcLayer& L, int BK, int N_pad, const TcMaps& act
     p.a_slots = std::min(8, (int)((budget - resident_bytes) / p.a_slot_bytes));
   } else {
     // weight blocks travel in groups of up to 16 KB under one barrier (one wait per group in the MMA warp)
-    p.b_group = std::max(1, std::min(4, 16384 / b_slot_bytes));
+    static const int gbytes_env = getenv("CIC_TC_BGROUP_BYTES") ? atoi(getenv("CIC_TC_BGROUP_BYTES")) : 0;
+    p.b_group = std::max(1, std::min(4, (gbytes_env > 0 ? gbytes_env : 32768) / b_slot_bytes));
     const int gbytes = p.b_group * b_slot_bytes;
     p.b_slots = std::min(TCV_MAX_SLOTS, std::max(2, 65536 / gbytes));
     p.a_slots = std::min(8, (budget - p.b_slots * gbytes) / p.a_slot_bytes);
@@ -220,6 +221,10 @@ static int try_run_raster(const TcLayer& L, int BK, int N_pad, const TcMaps& act
     }
   }
   if (p.a_slots < 2) return CIC_OK;
+  // Streamed weights: measured (r01, CIC_TC_RASTER=0 vs default on conv2 / deconv1..3) the per-tap kernel is 10-25 % faster -
+  // one barrier pair per K block there against separate raster + weight-group hand-shakes per op here, and both
+  // are bound by the shared-memory data pipe rather than by L2 traffic.  The raster kernel keeps the resident-weight layers.
+  if (!p.b_resident && force != 1) return CIC_OK;
 
   // tensor maps
   TcMaps maps;
@@ -270,6 +275,18 @@ static int try_run_raster(const TcLayer& L, int BK, int N_pad, const TcMaps& act
   p.fd_npass = make_fastdiv((uint32_t)p.npass);
   p.fd_tx = make_fastdiv((uint32_t)p.tiles_x);
   p.fd_ty = make_fastdiv((uint32_t)p.tiles_y);
+  // issuer warps: one per accumulator (output phase) when the weights are resident and the MMAs are small
+  static const int nw_env = getenv("CIC_TC_NW") ? atoi(getenv("CIC_TC_NW")) : 0;
+  p.nw = 1;
+  if (fused) p.nw = nw_env > 0 ? nw_env : (p.b_resident ? 4 : 1);  // streamed weights: extra issuers measured no gain (shared-memory data pipe bound)
+  // a second epilogue group when one tile has several accumulator chunks to drain per few MMAs
+  static const int ne_env = getenv("CIC_TC_NE") ? atoi(getenv("CIC_TC_NE")) : 0;
+  {
+    const int chunks_per_tile = (fused ? 4 : 1) * (BN % 32 == 0 ? BN / 32 : BN / 16);
+    p.ne = ne_env > 0 ? ne_env : (chunks_per_tile >= 2 ? 2 : 1);
+  }
+  static const int dbg = getenv("CIC_TC_DBG") ? atoi(getenv("CIC_TC_DBG")) : 0;
+  p.dbg = dbg;
   *used = true;
   return launch_tc_conv(maps, p, BK, L.split, st);
 }

@@ -13,6 +13,8 @@ from __future__ import annotations
 import ctypes as C
 from typing import Dict, List, Optional, Sequence
 
+import os
+import sys
 import numpy as np
 import torch
 
@@ -183,7 +185,12 @@ class Model:
         s_out.wait_stream(compute)
         stage = self.__dict__.setdefault("_stage", {})
         keep, host, extra = [], None, []
-        ev_in = [torch.cuda.Event() for _ in range(n_chunks)]
+        timeline = os.environ.get("CIC_PIPE_TIMELINE") == "1"            # debug: per-chunk event times of the three streams
+        ev_in = [torch.cuda.Event(enable_timing=timeline) for _ in range(n_chunks)]
+        if timeline:
+            ev_t0 = torch.cuda.Event(enable_timing=True)
+            ev_t0.record(compute)
+            ev_cs, ev_os = [], []
         for i in range(n_chunks):                                   # all uploads are queued up front on the copy-in stream
             lo, hi = bounds[i], bounds[i + 1]
             with torch.cuda.stream(s_in):
@@ -197,7 +204,7 @@ class Model:
             outs = self.forward_device(keep[i])
             if on_chunk is not None:
                 extra.append(on_chunk(keep[i], getattr(self, "last", None)))
-            ev_c = torch.cuda.Event()
+            ev_c = torch.cuda.Event(enable_timing=timeline)
             ev_c.record(compute)
             if host is None:                                        # staging buffers sized from the first chunk's row ratio
                 per = [o.shape[0] // (hi - lo) for o in outs]
@@ -214,9 +221,19 @@ class Model:
                 for k, o in enumerate(outs):
                     host[k][offs[k]:offs[k] + o.shape[0]].copy_(o, non_blocking=True)
                     offs[k] += o.shape[0]
+                if timeline:
+                    ev_o = torch.cuda.Event(enable_timing=True)
+                    ev_o.record(s_out)
+                    ev_cs.append(ev_c)
+                    ev_os.append(ev_o)
             keep.append(outs)                                       # alive until the copies have completed
         compute.wait_stream(s_out)
         s_out.synchronize()
+        if timeline:
+            torch.cuda.synchronize()
+            print("pipe timeline (ms since start): " + "  ".join(
+                f"[{bounds[i + 1] - bounds[i]}: in {ev_t0.elapsed_time(ev_in[i]):.2f} compute {ev_t0.elapsed_time(ev_cs[i]):.2f} out {ev_t0.elapsed_time(ev_os[i]):.2f}]"
+                for i in range(n_chunks)), file=sys.stderr)
         res = [b.numpy() for b in host]
         return (res if self._multi_output else res[0]), extra
 

@@ -268,5 +268,8 @@ struct TcMaps {
 };
 
 int launch_tc_gemm(const TcMaps& maps, TcParams& p, int block_n, int block_k, bool split, cudaStream_t st);
+// CTA-pair (cta_group::2) variant, tc_gemm2.cu; maps.b encoded with box {BK, block_n / 2}
+int launch_tc_gemm2(const TcMaps& maps, TcParams& p, int block_n, int block_k, bool split, cudaStream_t st);
+int tc2_pick_block_n(int n_pad);
 
 }  // namespace cic

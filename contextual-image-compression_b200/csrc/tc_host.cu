@@ -410,14 +410,21 @@ int tc_run_layer(const TcLayer& L, cudaStream_t st) {
     const double w_elems = (double)L.w.rows * L.w.K * L.w.batches;
     p.m_fast = (!L.b_batched && w_elems > act_elems) ? 1 : 0;
   }
-  const int bn = tc_pick_block_n(p.N_pad, L.split, BK);
+  // CTA-pair kernel (tc_gemm2.cu) for the large conv / transposed-conv GEMMs: halves the B fill and B operand reads per SM
+  static const int pair_env = getenv("CIC_TC_PAIR") ? atoi(getenv("CIC_TC_PAIR")) : 1;
+  const long long m_tiles = (long long)p.tiles_x * p.tiles_y * p.tiles_b;
+  const int bn2 = tc2_pick_block_n(p.N_pad);
+  const bool pair = pair_env && BK == 64 && !L.b_batched && L.splits == 1 && L.epi.out_mode != TC_OUT_PARTIAL && bn2 >= 128 &&  // N tile 64: measured slower than one CTA
+                   
+                    m_tiles >= 2LL * sm_count() && (L.N % 32 == 0);
+  const int bn = pair ? bn2 : tc_pick_block_n(p.N_pad, L.split, BK);
   CIC_REQUIRE(bn > 0 && L.N <= p.N_pad, "tc layer: N=%d (padded %d) has no supported tile", L.N, p.N_pad);
   CIC_REQUIRE(L.w.row_stride % 8 == 0 && L.w.batch_stride % 8 == 0, "tc layer: B rows must be 16-byte aligned");
   // weight / B map
   for (int part = 0; part < (L.split ? 2 : 1); ++part) {
     const uint64_t dims[3] = {(uint64_t)L.w.K, (uint64_t)L.w.rows, (uint64_t)L.w.batches};
     const uint64_t str[2] = {(uint64_t)L.w.row_stride * 2, (uint64_t)L.w.batch_stride * 2};
-    const uint32_t box[3] = {(uint32_t)BK, (uint32_t)bn, 1};
+    const uint32_t box[3] = {(uint32_t)BK, (uint32_t)(pair ? bn / 2 : bn), 1};
     int rc = tc_encode_map(&maps.b[part], part ? L.w.lo : L.w.hi, 3, dims, str, box);
     if (rc) return rc;
   }
@@ -437,6 +444,7 @@ int tc_run_layer(const TcLayer& L, cudaStream_t st) {
   pe.Ho = Ho; pe.Wo = Wo;
   pe.tm_tx = e.tm_tx; pe.tm_ty = e.tm_ty; pe.tm_IH = e.tm_IH; pe.tm_IW = e.tm_IW;
   pe.m_total = (long long)L.batch * Ho * Wo;
+  if (pair) return launch_tc_gemm2(maps, p, bn, BK, L.split, st);
   return launch_tc_gemm(maps, p, bn, BK, L.split, st);
 }
 

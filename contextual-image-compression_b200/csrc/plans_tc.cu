@@ -214,6 +214,32 @@ static int attention_tc(cic_plan* pl, Ctx& c, const ActBuf& x, const ActBuf& y, 
   const WeightStore& w = pl->w;
   const int dq = C / 8;
   CIC_REQUIRE(tokens % 32 == 0, "attention (tc): token count %d must be a multiple of 32", tokens);
+  static const int fused_env = getenv("CIC_ATTN_FUSED") ? atoi(getenv("CIC_ATTN_FUSED")) : 1;
+  if (fused_env && tokens % 128 == 0 && C == 256 && dq == 32) {
+    // projections as GEMMs over the whole batch, then one fused kernel for softmax(q k^T) v (attn_fused.cu)
+    const size_t mk = c.arena.mark();
+    ActBuf qk = alloc_act(c, (size_t)batch * tokens * 2 * dq, true);
+    ActBuf vt = alloc_act(c, (size_t)batch * C * tokens, true);
+    int rc = CIC_OK;
+    const float* bqkv = w.ptr("attn/qkv/bias");
+    if (!c.dry) {
+      if ((rc = conv_tc(c, "attn_qk", TC_CONV_S1, view(x, C), nullptr, batch * tokens, 1, 1, 1, 1, 1, mat(pl, "attn/qk", C, 2 * dq), 2 * dq, true,
+                        epi_bf16(bqkv, nullptr, nullptr, CIC_ACT_NONE, qk)))) return rc;
+      {
+        TcEpilogue e;
+        e.bias = bqkv + 2 * dq; e.out_mode = TC_OUT_BF16_T; e.out_hi = vt.hi; e.out_lo = vt.lo;
+        TcLayer L;
+        L.kind = TC_CONV_S1; L.src[0] = view(x, C); L.nsrc = 1;
+        L.batch = batch; L.H = tokens; L.W = 1; L.kh = 1; L.kw = 1;
+        L.w = mat(pl, "attn/v", C, C); L.N = C; L.split = true; L.epi = e;
+        if ((rc = run_tc(c, "attn_v", L, 2.0 * batch * tokens * (double)C * C, 0))) return rc;
+      }
+      Scope sc(c, "attn_core", 2.0 * batch * tokens * (double)tokens * (dq + C), 2.0 * 2 * 2 * (double)batch * tokens * C);
+      if ((rc = launch_attn_fused(qk.hi, qk.lo, vt.hi, vt.lo, x.hi, x.lo, y.hi, y.lo, nullptr, pl->attn_gamma, batch, tokens, c.st))) return rc;
+    }
+    c.arena.release(mk);
+    return rc;
+  }
   static const int chunk_env = getenv("CIC_ATTN_CHUNK") ? atoi(getenv("CIC_ATTN_CHUNK")) : 0;
   const int chunk_max = chunk_env > 0 ? chunk_env : 128;  // images per pass: bounds the tokens x tokens score workspace
   const int chunk = batch < chunk_max ? batch : chunk_max;

@@ -79,6 +79,9 @@ int tc_maxpool2x2_bf16(const bf16* x, bf16* y, int batch, int H, int W, int C, c
 // split-K partials [splits][M][N] -> epilogue -> fp32 [M][N] and/or bf16 hi/lo [M][N]
 int tc_splitk_reduce(const float* partial, int splits, long long M, int N, const float* bias, const float* scale,
                      const float* shift, int act, float* out_f32, bf16* out_hi, bf16* out_lo, cudaStream_t st);
+// fused attention core (attn_fused.cu): y = gamma * softmax(q k^T) v + x on (hi, lo) bf16 tensors, 32 q/k channels, 256 value channels
+int launch_attn_fused(const bf16* qk_hi, const bf16* qk_lo, const bf16* vt_hi, const bf16* vt_lo, const bf16* x_hi, const bf16* x_lo,
+                      bf16* y_hi, bf16* y_lo, const float* bias_v_scaled, float gamma, int nb, int tokens, cudaStream_t st);
 // row softmax of fp32 logits -> bf16 hi/lo probabilities (tf.nn.softmax(axis=-1), GAN_functions.py:359)
 int tc_softmax_rows_split(const float* logits, bf16* p_hi, bf16* p_lo, long long rows, int cols, cudaStream_t st);
 

@@ -10,7 +10,7 @@
 //   epilogue: y = gamma * O / rowsum + x  ->  (hi, lo) bf16.
 // Two passes instead of an online softmax: no rescaling of O in TMEM, and the probabilities are final when they are
 // rounded to bf16 pairs.  Warps: 0 = TMA producer (Q, K blocks, V^T blocks), 1 = TMEM allocator + MMA issuer,
-// 2-5 = softmax / epilogue (thread = query row = TMEM lane).
+// 2-5 and 6-9 = two softmax / epilogue groups on alternate key blocks (thread = query row = TMEM lane).
 #include "tc_gemm.cuh"
 #include "tc_host.cuh"
 
@@ -26,7 +26,7 @@ constexpr int AT_QBYTES = AT_Q * AT_D * 2;     // one part of the Q tile (8 KB, 
 constexpr int AT_KBYTES = AT_KB * AT_D * 2;    // one part of a K block (4 KB)
 constexpr int AT_VBYTES = AT_C * AT_KB * 2;    // one part of a V^T block (32 KB, SWIZZLE_128B rows of 128 B)
 constexpr int AT_PBYTES = AT_Q * AT_KB * 2;    // one part of a P block (16 KB, SWIZZLE_128B)
-constexpr int AT_SMEM = 2 * AT_QBYTES + 2 * 2 * AT_KBYTES + 2 * 2 * AT_VBYTES + 2 * 2 * AT_PBYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int AT_SMEM = 2 * AT_QBYTES + 2 * 2 * AT_KBYTES + 2 * 2 * AT_VBYTES + 2 * 2 * AT_PBYTES + 1024 /*align*/ + 256 /*barriers*/ + 1024 /*softmax exchange*/;
 constexpr uint32_t AT_S_COLS = 64, AT_O_COL0 = 128;
 
 struct AttnMaps {
@@ -46,13 +46,14 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uin
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+__device__ __forceinline__ void named_bar_sync_at(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t at_idesc(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 attn_fused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -74,6 +75,7 @@ attn_fused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__
   uint64_t* o_full = bars + 18;       // [1]
   uint64_t* o_empty = bars + 19;      // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  float* xch = reinterpret_cast<float*>(bars + 22);  // [2 groups][128 rows]: row maxima / row sums exchanged between the softmax groups
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_q = p.tokens / AT_Q, nblk = p.tokens / AT_KB;
@@ -91,7 +93,7 @@ attn_fused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__
         mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 4);
         mbar_init(&p_full[s], 4); mbar_init(&p_empty[s], 1);
       }
-      mbar_init(o_full, 1); mbar_init(o_empty, 4);
+      mbar_init(o_full, 1); mbar_init(o_empty, 8);
       fence_barrier_init();
     }
     __syncwarp();
@@ -198,48 +200,52 @@ attn_fused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__
     }
     __syncwarp();
   } else {
-    // ===== softmax + epilogue: thread = query row =====
+    // ===== softmax + epilogue: thread = query row; two groups of four warps take alternate key blocks (group g owns S
+    // stage g and P stage g) - one warp per scheduler runs the ~1000-instruction block at ~5 cycles per instruction =====
+    const int g = warp >= 6 ? 1 : 0;
     const int qd = warp & 3;
     const int r = qd * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(qd * 32) << 16);
-    const uint32_t p_row = smem_u32(p_s) + (uint32_t)r * 128u;
+    const uint32_t s_addr = lane_addr + (uint32_t)g * AT_S_COLS;
+    const uint32_t ph = smem_u32(p_s) + (uint32_t)g * 2 * AT_PBYTES + (uint32_t)r * 128u, pl = ph + AT_PBYTES;
     const uint32_t sw = (uint32_t)(r & 7);
     const float kLog2e = 1.4426950408889634f;
-    uint32_t sc = 0, pc = 0, ic = 0;
+    uint32_t gc = 0, gp = 0, ic = 0;  // S blocks / P blocks handled by this group, items
     for (int it = blockIdx.x; it < items; it += gridDim.x, ++ic) {
       const int b = it / tiles_q, qt = it - b * tiles_q;
-      // pass 1: row maximum
+      // pass 1: row maximum over this group's key blocks
       float m = -INFINITY;
-      for (int j = 0; j < nblk; ++j, ++sc) {
-        const uint32_t ss = sc & 1u;
-        mbar_wait_relaxed(&s_full[ss], (sc >> 1) & 1u);
+      for (int j = g; j < nblk; j += 2, ++gc) {
+        mbar_wait_relaxed(&s_full[g], gc & 1u);
         tc_fence_after();
         uint32_t v0[32], v1[32];
         __syncwarp();
-        tmem_ld32(lane_addr + ss * AT_S_COLS, v0);
-        tmem_ld32(lane_addr + ss * AT_S_COLS + 32, v1);
+        tmem_ld32(s_addr, v0);
+        tmem_ld32(s_addr + 32, v1);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&s_empty[ss]);
+        if (lane == 0) mbar_arrive(&s_empty[g]);
 #pragma unroll
         for (int i = 0; i < 32; ++i) m = fmaxf(m, fmaxf(__uint_as_float(v0[i]), __uint_as_float(v1[i])));
       }
+      xch[g * AT_Q + r] = m;
+      named_bar_sync_at(1, 256);
+      m = fmaxf(m, xch[(g ^ 1) * AT_Q + r]);
       // pass 2: probabilities (unnormalised) as bf16 (hi, lo) rows of the P operand, row sum
       const float mb = m * kLog2e;
       float l = 0.f;
-      for (int j = 0; j < nblk; ++j, ++sc, ++pc) {
-        const uint32_t ss = sc & 1u, ps = pc & 1u;
-        mbar_wait_relaxed(&s_full[ss], (sc >> 1) & 1u);
+      for (int j = g; j < nblk; j += 2, ++gc, ++gp) {
+        mbar_wait_relaxed(&s_full[g], gc & 1u);
         tc_fence_after();
         uint32_t v0[32], v1[32];
         __syncwarp();
-        tmem_ld32(lane_addr + ss * AT_S_COLS, v0);
-        tmem_ld32(lane_addr + ss * AT_S_COLS + 32, v1);
+        tmem_ld32(s_addr, v0);
+        tmem_ld32(s_addr + 32, v1);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&s_empty[ss]);
+        if (lane == 0) mbar_arrive(&s_empty[g]);
         uint32_t hi[32], lo[32];  // 64 keys -> 32 packed pairs each
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
@@ -253,8 +259,7 @@ attn_fused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__
           const __nv_bfloat162 lw = __floats2bfloat162_rn(e0 - __uint_as_float(hi[i] << 16), e1 - __uint_as_float(hi[i] & 0xFFFF0000u));
           lo[i] = *reinterpret_cast<const uint32_t*>(&lw);
         }
-        mbar_wait_relaxed(&p_empty[ps], ((pc >> 1) & 1u) ^ 1u);  // the MMAs that read this buffer two blocks ago have retired
-        const uint32_t ph = p_row + ps * 2 * AT_PBYTES, pl = ph + AT_PBYTES;
+        mbar_wait_relaxed(&p_empty[g], (gp & 1u) ^ 1u);  // the MMAs that read this buffer two blocks ago have retired
 #pragma unroll
         for (int c = 0; c < 8; ++c) {  // 16-byte chunk c (keys 8c .. 8c+7) sits at chunk position c ^ (row & 7) (SWIZZLE_128B)
           const uint32_t off = ((uint32_t)c ^ sw) << 4;
@@ -263,20 +268,24 @@ attn_fused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__
         }
         fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[ps]);
+        if (lane == 0) mbar_arrive(&p_full[g]);
       }
-      // epilogue: y = gamma * O / l + x
+      named_bar_sync_at(2, 256);   // the other group has read this group's row maximum
+      xch[g * AT_Q + r] = l;
+      named_bar_sync_at(1, 256);
+      l += xch[(g ^ 1) * AT_Q + r];
+      // epilogue: y = gamma * O / l + x; the two groups take alternate 32-column chunks
       const float inv_l = 1.f / l;
       mbar_wait_relaxed(o_full, ic & 1u);
       tc_fence_after();
       const TcRow row{b, qt * AT_Q + r, 0, 0, 0};
 #pragma unroll 1
-      for (int c = 0; c < AT_C / 32; ++c) {
+      for (int c = g; c < AT_C / 32; c += 2) {
         uint32_t v[32];
         __syncwarp();
         tmem_ld32(lane_addr + AT_O_COL0 + (uint32_t)(c * 32), v);
         tmem_ld_wait();
-        if (c == AT_C / 32 - 1) {
+        if (c + 2 >= AT_C / 32) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(o_empty);
@@ -285,6 +294,7 @@ attn_fused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__
         for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__fmul_rn(__uint_as_float(v[i]), inv_l));
         tc_epilogue_store<32>(p.epi, row, v, c * 32, 32);
       }
+      named_bar_sync_at(2, 256);   // row sums consumed before the next item overwrites the exchange buffer
     }
   }
 
@@ -333,7 +343,7 @@ int launch_attn_fused(const bf16* qk_hi, const bf16* qk_lo, const bf16* vt_hi, c
   }
   const int items = nb * (tokens / AT_Q);
   const int grid = items < sm_count() ? items : sm_count();
-  attn_fused_kernel<<<grid, 192, AT_SMEM, st>>>(maps, p);
+  attn_fused_kernel<<<grid, 320, AT_SMEM, st>>>(maps, p);
   CIC_COUNT_LAUNCH();
   CIC_CHECK_LAUNCH("attn_fused_kernel");
   g_last_kernel_kind = KK_TC_GEMM;

@@ -106,22 +106,25 @@ direct_conv_kernel(const float* __restrict__ x, const float* __restrict__ wgt, c
     if (oy >= Ho || ox >= Wo) continue;
     const size_t o = (((size_t)b * Ho + oy) * Wo + ox) * COUT;
 #pragma unroll
-    for (int j8 = 0; j8 < COUT / 8; ++j8) {
-      uint32_t hi[4], lo[4];
+    for (int j16 = 0; j16 < COUT / 16; ++j16) {  // 16 channels = one whole 32-byte sector per 256-bit store
+      uint32_t hi[8], lo[8];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float f0 = acc[j][8 * j8 + 2 * q], f1 = acc[j][8 * j8 + 2 * q + 1];
+      for (int q = 0; q < 8; ++q) {
+        const float f0 = acc[j][16 * j16 + 2 * q], f1 = acc[j][16 * j16 + 2 * q + 1];
         const __nv_bfloat162 hh = __floats2bfloat162_rn(f0, f1);
         hi[q] = *reinterpret_cast<const uint32_t*>(&hh);
         const __nv_bfloat162 ll = __floats2bfloat162_rn(f0 - __uint_as_float(hi[q] << 16), f1 - __uint_as_float(hi[q] & 0xFFFF0000u));
         lo[q] = *reinterpret_cast<const uint32_t*>(&ll);
       }
-      if (out_hi) reinterpret_cast<uint4*>(out_hi + o)[j8] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-      if (out_lo) reinterpret_cast<uint4*>(out_lo + o)[j8] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      if (out_hi) st_global_v8(out_hi + o + 16 * j16, hi[0], hi[1], hi[2], hi[3], hi[4], hi[5], hi[6], hi[7]);
+      if (out_lo) st_global_v8(out_lo + o + 16 * j16, lo[0], lo[1], lo[2], lo[3], lo[4], lo[5], lo[6], lo[7]);
       if (out_f32) {
-        reinterpret_cast<float4*>(out_f32 + o)[2 * j8] = make_float4(acc[j][8 * j8], acc[j][8 * j8 + 1], acc[j][8 * j8 + 2], acc[j][8 * j8 + 3]);
-        reinterpret_cast<float4*>(out_f32 + o)[2 * j8 + 1] =
-            make_float4(acc[j][8 * j8 + 4], acc[j][8 * j8 + 5], acc[j][8 * j8 + 6], acc[j][8 * j8 + 7]);
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+          st_global_v8(out_f32 + o + 16 * j16 + 8 * h, __float_as_uint(acc[j][16 * j16 + 8 * h]), __float_as_uint(acc[j][16 * j16 + 8 * h + 1]),
+                       __float_as_uint(acc[j][16 * j16 + 8 * h + 2]), __float_as_uint(acc[j][16 * j16 + 8 * h + 3]),
+                       __float_as_uint(acc[j][16 * j16 + 8 * h + 4]), __float_as_uint(acc[j][16 * j16 + 8 * h + 5]),
+                       __float_as_uint(acc[j][16 * j16 + 8 * h + 6]), __float_as_uint(acc[j][16 * j16 + 8 * h + 7]));
       }
     }
   }

@@ -140,22 +140,30 @@ metrics_f32_packed_kernel(const float* __restrict__ A, const float* __restrict__
   const size_t img_base = (size_t)b * H * W * C;
   const int row_elems = TP * C;
   double sse = 0.0;
-  for (int i = threadIdx.x; i < TP * row_elems; i += blockDim.x) {
-    const int ly = i / row_elems, rem = i % row_elems;
-    const int lx = rem / C;
-    const int gy = y0 + ly - HALO, gx = x0 + lx - HALO;
-    float va = 0.f, vb = 0.f;
-    if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-      const size_t idx = img_base + ((size_t)gy * W + (x0 - HALO)) * C + rem;  // contiguous in rem
-      va = __fmul_rn(__fadd_rn(__ldg(A + idx), pre_add), pre_mul);
-      vb = __fmul_rn(__fadd_rn(__ldg(Bm + idx), pre_add), pre_mul);
-      if (ly >= HALO && ly < HALO + TS && lx >= HALO && lx < HALO + TS) {
-        const float d = __fsub_rn(va, vb);
-        sse += (double)__fmul_rn(d, d);
+  {
+    // a warp per staged row, lanes along the contiguous (pixel, channel) elements: no per-element division, and the
+    // validity / ownership tests are range checks on the element index
+    const int lo_rem = max(0, HALO - x0) * C, hi_rem = min(TP, W - x0 + HALO) * C;
+    const int in_lo = HALO * C, in_hi = (HALO + TS) * C;
+    const int wid = threadIdx.x >> 5, ln = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int ly = wid; ly < TP; ly += nwarps) {
+      const int gy = y0 + ly - HALO;
+      const bool row_ok = gy >= 0 && gy < H, own_row = ly >= HALO && ly < HALO + TS;
+      const long long base = (long long)img_base + ((long long)gy * W + (x0 - HALO)) * C;
+      for (int rem = ln; rem < row_elems; rem += 32) {
+        float va = 0.f, vb = 0.f;
+        if (row_ok && rem >= lo_rem && rem < hi_rem) {
+          va = __fmul_rn(__fadd_rn(__ldg(A + base + rem), pre_add), pre_mul);
+          vb = __fmul_rn(__fadd_rn(__ldg(Bm + base + rem), pre_add), pre_mul);
+          if (own_row && rem >= in_lo && rem < in_hi) {
+            const float d = __fsub_rn(va, vb);
+            sse += (double)__fmul_rn(d, d);
+          }
+        }
+        sa[ly * ld + rem] = va;
+        sb[ly * ld + rem] = vb;
       }
     }
-    sa[ly * ld + rem] = va;
-    sb[ly * ld + rem] = vb;
   }
   __syncthreads();
   // Window sums slide: s += entering - leaving, all in double.  For image-range data the double sum of 7 floats is

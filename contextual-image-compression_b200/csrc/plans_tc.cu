@@ -196,12 +196,15 @@ static int dense_tc(Ctx& c, const char* name, const TcAct& x, int batch, const T
 
 static int dense_splits(int batch, int N_pad, int K, bool split) {
   const int bk = K % 64 == 0 ? 64 : 32;
-  const int bn = tc_pick_block_n(N_pad, split, bk);
-  const long long tiles = (long long)((batch + 127) / 128) * (N_pad / (bn > 0 ? bn : 16));
+  const long long mt = (batch + 127) / 128;
+  static const int pair_env = getenv("CIC_TC_PAIR") ? atoi(getenv("CIC_TC_PAIR")) : 1;
+  const bool pair = pair_env && tc_pair_ok(bk, mt, N_pad, N_pad);
+  const int bn = pair ? tc2_pick_block_n(N_pad) : tc_pick_block_n(N_pad, split, bk);
+  const long long tiles = (pair ? (mt + 1) / 2 : mt) * (N_pad / (bn > 0 ? bn : 16));
   const int kblocks = K / bk;
   int s = 1;
-  const int target = 2 * sm_count();
-  if (tiles < target) s = (int)((target + tiles - 1) / tiles);
+  const int target = pair ? sm_count() / 2 : 2 * sm_count();  // one wave of CTA pairs / two waves of CTAs
+  if (tiles < target) s = pair ? (int)(target / tiles) : (int)((target + tiles - 1) / tiles);
   if (s > kblocks / 4) s = kblocks / 4;
   if (s < 1) s = 1;
   // no empty split: ceil(kblocks / s) * (s - 1) < kblocks

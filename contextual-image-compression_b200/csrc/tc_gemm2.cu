@@ -101,7 +101,8 @@ struct Tc2Cfg {
 
 struct PairTile {
   int ox0, oy0, b0;  // this CTA's M tile
-  int n_tile, phase;
+  int n_tile, phase, split;
+  int kb0, nkb;      // K-block range of this split
 };
 
 // pair index t -> (M-tile pair, N tile, phase); same orders as decode_tile of the one-CTA kernel
@@ -117,8 +118,9 @@ __device__ __forceinline__ PairTile decode_pair(const TcParams& p, int t, int ra
   } else {
     n = t % p.n_tiles;
     const int r = t / p.n_tiles;
-    z = r % p.nphases;
-    m2 = r / p.nphases;
+    const int zt = p.nphases * p.splits;
+    z = r % zt;
+    m2 = r / zt;
   }
   const int m = 2 * m2 + rank;  // may be == mt (phantom tile of an odd count): b0 >= batch, everything out of bounds
   PairTile c;
@@ -126,7 +128,11 @@ __device__ __forceinline__ PairTile decode_pair(const TcParams& p, int t, int ra
   c.oy0 = ((m / p.tiles_x) % p.tiles_y) * p.TH;
   c.b0 = (m / (p.tiles_x * p.tiles_y)) * p.TB;
   c.n_tile = n;
-  c.phase = z;
+  c.phase = z / p.splits;
+  c.split = z % p.splits;
+  const int per_split = (p.kblocks + p.splits - 1) / p.splits;
+  c.kb0 = c.split * per_split;
+  c.nkb = min(p.kblocks, c.kb0 + per_split) - c.kb0;  // host guarantees >= 1
   return c;
 }
 
@@ -180,8 +186,8 @@ tc_gemm2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcP
       for (int t = pair0; t < total_pairs; t += npairs_grid) {
         const PairTile tc = decode_pair(p, t, (int)rank);
         const int bn = tc.phase * p.N_pad + tc.n_tile * BN + (int)rank * (BN / 2);
-        int tap = 0, ch = 0;
-        for (int i = 0; i < p.kblocks; ++i) {
+        int tap = tc.kb0 / cpt, ch = tc.kb0 % cpt;
+        for (int i = 0; i < tc.nkb; ++i) {
           mbar_wait_relaxed(&empty_bar[s], ph ^ 1u);
           if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
           const uint32_t bar = smem_u32(&full_bar[s]) & kPeerBitMask;
@@ -201,8 +207,8 @@ tc_gemm2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcP
             tma2_load_4d(a_hi, &maps.a[src][0], bar, c, tc.ox0 + tp.dx, tc.oy0 + tp.dy, tc.b0);
             if (SPLIT) tma2_load_4d(a_lo, &maps.a[src][1], bar, c, tc.ox0 + tp.dx, tc.oy0 + tp.dy, tc.b0);
           }
-          tma2_load_3d(b_hi, &maps.b[0], bar, i * BK, bn, 0);
-          if (SPLIT) tma2_load_3d(b_lo, &maps.b[1], bar, i * BK, bn, 0);
+          tma2_load_3d(b_hi, &maps.b[0], bar, (tc.kb0 + i) * BK, bn, 0);
+          if (SPLIT) tma2_load_3d(b_lo, &maps.b[1], bar, (tc.kb0 + i) * BK, bn, 0);
           if (++ch == cpt) { ch = 0; ++tap; }
           if (++s == (uint32_t)kStages) { s = 0; ph ^= 1u; }
         }
@@ -218,11 +224,12 @@ tc_gemm2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcP
       uint32_t s = 0, ph = 0;
       int lt = 0;
       for (int t = pair0; t < total_pairs; t += npairs_grid, ++lt) {
+        const int nkb = decode_pair(p, t, 0).nkb;
         const int as = lt & 1;
         mbar_wait(&tmem_empty_bar[as], (((uint32_t)lt >> 1) & 1u) ^ 1u);  // both CTAs' epilogues have drained this stage
         tc_fence_after();
         const uint32_t d = tmem_base + (uint32_t)(as * BN);
-        for (int i = 0; i < p.kblocks; ++i) {
+        for (int i = 0; i < nkb; ++i) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           const uint32_t a_hi = ring_lo + s * kStageLo, a_lo = a_hi + kALo;
@@ -261,7 +268,7 @@ tc_gemm2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcP
       mbar_wait_relaxed(&tmem_full_bar[as], ((uint32_t)lt >> 1) & 1u);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
-      const TcRow row{b, oy, ox, tc.phase, 0};
+      const TcRow row{b, oy, ox, tc.phase, tc.split};
       constexpr int kLastMine0 = kChunks - 1 - ((kChunks - 1) % NE);  // last chunk of group 0
       const int last_mine = eg == 0 ? kLastMine0 : (kChunks - 1 - ((kChunks - 1 - 1 + NE) % NE));
       if (eg >= kChunks) {  // more groups than chunks: nothing to drain
@@ -314,7 +321,7 @@ template <int BN, int BK, bool SPLIT>
 static int launch2_one(const TcMaps& maps, const TcParams& p, int total_pairs, cudaStream_t st) {
   // a second epilogue group when the K loop is short: MMA time per tile ~ 2 * kblocks * terms * BN clk against ~75 * BN clk for
   // four warps to drain it (one warp per scheduler is latency-bound at ~2400 clk per 32-column chunk)
-  const bool two = (BN / Tc2Cfg<BN, BK, SPLIT>::kChunk) >= 2 && p.kblocks * (SPLIT ? 3 : 1) < 64;
+  const bool two = (BN / Tc2Cfg<BN, BK, SPLIT>::kChunk) >= 2 && (p.kblocks / p.splits) * (SPLIT ? 3 : 1) < 64;
   if (two) return launch2_thr<BN, BK, SPLIT, 320>(maps, p, total_pairs, st);
   return launch2_thr<BN, BK, SPLIT, 192>(maps, p, total_pairs, st);
 }
@@ -329,11 +336,13 @@ int tc2_pick_block_n(int n_pad) {
 // p as prepared for launch_tc_gemm (taps, maps for A); maps.b must have been encoded with box {BK, block_n / 2}
 int launch_tc_gemm2(const TcMaps& maps, TcParams& p, int block_n, int block_k, bool split, cudaStream_t st) {
   CIC_REQUIRE(block_k == 64, "tc_gemm2: K block must be 64");
-  CIC_REQUIRE(p.splits == 1 && !p.b_batched, "tc_gemm2: no split-K / batched B");
+  CIC_REQUIRE(!p.b_batched, "tc_gemm2: no batched B");
+  CIC_REQUIRE(p.kblocks >= p.splits && p.splits >= 1, "tc_gemm2: bad split-K %d for %d K blocks", p.splits, p.kblocks);
+  CIC_REQUIRE((p.splits - 1) * ((p.kblocks + p.splits - 1) / p.splits) < p.kblocks, "tc_gemm2: split-K leaves an empty split");
   CIC_REQUIRE(block_n > 0 && p.N_pad % block_n == 0 && p.N <= p.N_pad, "tc_gemm2: bad N tile %d", block_n);
   const long long mt = (long long)p.tiles_x * p.tiles_y * p.tiles_b;
   p.n_tiles = (p.N + block_n - 1) / block_n;
-  const long long total = ((mt + 1) / 2) * p.n_tiles * p.nphases;
+  const long long total = ((mt + 1) / 2) * p.n_tiles * p.nphases * p.splits;
   CIC_REQUIRE(total > 0 && total < 2147483647LL, "tc_gemm2: bad tile count");
   p.total_tiles = (int)total;
   switch (block_n) {

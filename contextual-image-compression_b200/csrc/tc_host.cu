@@ -291,6 +291,13 @@ static int try_run_raster(const TcLayer& L, int BK, int N_pad, const TcMaps& act
   return launch_tc_conv(maps, p, BK, L.split, st);
 }
 
+// CTA-pair kernel eligibility (also used by the split-K planner of the Dense layers): K block 64, N tile >= 128 (an N
+// tile of 64 measured slower than one CTA), at least one full pair of M tiles and few phantom tiles
+bool tc_pair_ok(int bk, long long m_tiles, int n_pad, int n) {
+  const int bn2 = tc2_pick_block_n(n_pad);
+  return bk == 64 && bn2 >= 128 && n % 32 == 0 && m_tiles >= 2 && (m_tiles % 2 == 0 || m_tiles >= 16);
+}
+
 int tc_run_layer(const TcLayer& L, cudaStream_t st) {
   TcMaps maps;
   memset(&maps, 0, sizeof(maps));
@@ -414,9 +421,7 @@ int tc_run_layer(const TcLayer& L, cudaStream_t st) {
   static const int pair_env = getenv("CIC_TC_PAIR") ? atoi(getenv("CIC_TC_PAIR")) : 1;
   const long long m_tiles = (long long)p.tiles_x * p.tiles_y * p.tiles_b;
   const int bn2 = tc2_pick_block_n(p.N_pad);
-  const bool pair = pair_env && BK == 64 && !L.b_batched && L.splits == 1 && L.epi.out_mode != TC_OUT_PARTIAL && bn2 >= 128 &&  // N tile 64: measured slower than one CTA
-                   
-                    m_tiles >= 2LL * sm_count() && (L.N % 32 == 0);
+  const bool pair = pair_env && !L.b_batched && tc_pair_ok(BK, m_tiles, p.N_pad, L.N);
   const int bn = pair ? bn2 : tc_pick_block_n(p.N_pad, L.split, BK);
   CIC_REQUIRE(bn > 0 && L.N <= p.N_pad, "tc layer: N=%d (padded %d) has no supported tile", L.N, p.N_pad);
   CIC_REQUIRE(L.w.row_stride % 8 == 0 && L.w.batch_stride % 8 == 0, "tc layer: B rows must be 16-byte aligned");

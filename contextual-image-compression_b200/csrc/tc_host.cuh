@@ -60,6 +60,7 @@ int tc_encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* 
 int tc_run_layer(const TcLayer& L, cudaStream_t st);
 int tc_pick_block_n(int n_pad, bool split, int bk);
 int tc_pick_block_k(const TcLayer& L);
+bool tc_pair_ok(int bk, long long m_tiles, int n_pad, int n);
 
 // fp32 [K][ld] (row-major, Keras kernel / Dense layout; the first N columns) -> bf16 hi/lo [N_pad][K]
 // (K contiguous), zero rows >= N

@@ -49,6 +49,18 @@ METRIC_FIELDS = ("psnr_sum", "ssim_sum", "mse_sum", "actual_bpp_sum", "hq_ratio_
                  "mismatch_count")
 
 
+def metric_sums_row(psnr, ssim, mse, actual_bpp, hq_ratio, n_images: int) -> torch.Tensor:
+    """(1, len(METRIC_FIELDS)) float64 row of per-rank sums built on the device with kernels only (no host scalar is
+    copied into a device element), so it can sit inside a CUDA-graph capture."""
+    dev = psnr.device
+    f64 = dict(dtype=torch.float64, device=dev)
+    zero = torch.zeros((), **f64)
+    vals = [psnr.sum().to(torch.float64), ssim.sum().to(torch.float64), mse.sum().to(torch.float64),
+            actual_bpp.sum().to(torch.float64), hq_ratio.sum().to(torch.float64), zero,
+            torch.full((), float(n_images), **f64), zero]
+    return torch.stack(vals).reshape(1, len(METRIC_FIELDS))
+
+
 def allreduce_metric_sums(local: torch.Tensor) -> torch.Tensor:
     """Sum a (levels, len(METRIC_FIELDS)) float64 tensor over ranks (in place); identity for world 1."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:

@@ -191,19 +191,51 @@ class Model:
             ev_t0 = torch.cuda.Event(enable_timing=True)
             ev_t0.record(compute)
             ev_cs, ev_os = [], []
+        # Repeated calls with the same chunking replay one CUDA graph per chunk (the ~55 launches of a small chunk are
+        # otherwise launch-bound on the host): the first call runs eagerly, then the chunks are captured with
+        # persistent device input / output buffers.  CIC_PIPE_GRAPHS=0 keeps the eager path.
+        gkey = (tuple(bounds), tuple(tuple(h.shape[1:]) for h in hs), id(on_chunk), id(self.plan()))
+        gstate = self.__dict__.setdefault("_pipe_graphs", {})
+        use_graphs = os.environ.get("CIC_PIPE_GRAPHS", "1") != "0"
+        gs = gstate.get(gkey) if use_graphs else None
+        if gs is not None and gs.get("calls", 0) >= 1 and "graphs" not in gs and not gs.get("failed"):
+            try:
+                gs.update(self._capture_pipe_graphs(bounds, hs, on_chunk, dev))
+            except Exception as e:  # noqa: BLE001  (a path that synchronises cannot be captured: stay eager, say so once)
+                gs["failed"] = True
+                torch.cuda.synchronize()
+                print(f"predict_pipelined: CUDA graph capture failed ({e!r}); using eager launches", file=sys.stderr)
+        if gs is None and use_graphs:
+            if len(gstate) > 4:
+                gstate.clear()
+            gs = gstate[gkey] = {"calls": 0}
+        if gs is not None:
+            gs["calls"] += 1
+        graphs = gs.get("graphs") if gs is not None else None
         for i in range(n_chunks):                                   # all uploads are queued up front on the copy-in stream
             lo, hi = bounds[i], bounds[i + 1]
             with torch.cuda.stream(s_in):
-                d_in = [h[lo:hi].to(dev, non_blocking=True) for h in hs]
+                if graphs is not None:
+                    d_in = gs["d_in"][i]
+                    for k, h in enumerate(hs):
+                        d_in[k].copy_(h[lo:hi], non_blocking=True)
+                else:
+                    d_in = [h[lo:hi].to(dev, non_blocking=True) for h in hs]
                 ev_in[i].record(s_in)
             keep.append(d_in)
         offs = None
         for i in range(n_chunks):
             lo, hi = bounds[i], bounds[i + 1]
             compute.wait_event(ev_in[i])
-            outs = self.forward_device(keep[i])
-            if on_chunk is not None:
-                extra.append(on_chunk(keep[i], getattr(self, "last", None)))
+            if graphs is not None:
+                graphs[i].replay()
+                outs = gs["outs"][i]
+                if on_chunk is not None:
+                    extra.append(gs["extra"][i])
+            else:
+                outs = self.forward_device(keep[i])
+                if on_chunk is not None:
+                    extra.append(on_chunk(keep[i], getattr(self, "last", None)))
             ev_c = torch.cuda.Event(enable_timing=timeline)
             ev_c.record(compute)
             if host is None:                                        # staging buffers sized from the first chunk's row ratio
@@ -236,6 +268,24 @@ class Model:
                 for i in range(n_chunks)), file=sys.stderr)
         res = [b.numpy() for b in host]
         return (res if self._multi_output else res[0]), extra
+
+    def _capture_pipe_graphs(self, bounds, hs, on_chunk, dev):
+        """One CUDA graph per chunk of predict_pipelined: forward (+ on_chunk) on persistent buffers."""
+        d_ins, graphs, outs_all, extras = [], [], [], []
+        torch.cuda.synchronize()
+        for i in range(len(bounds) - 1):
+            lo, hi = bounds[i], bounds[i + 1]
+            d_in = [torch.zeros((hi - lo,) + tuple(h.shape[1:]), dtype=torch.float32, device=dev) for h in hs]
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                outs = self.forward_device(d_in)
+                ex = on_chunk(d_in, getattr(self, "last", None)) if on_chunk is not None else None
+            d_ins.append(d_in)
+            graphs.append(g)
+            outs_all.append(outs)
+            extras.append(ex)
+        torch.cuda.synchronize()
+        return {"d_in": d_ins, "graphs": graphs, "outs": outs_all, "extra": extras}
 
     def __call__(self, inputs, training=False):
         if training:

@@ -269,7 +269,7 @@ def main():
     launches_per_step = plan.last_launch_count() + 2          # + metrics kernel and its finalise
     value = world * px_per_step / (ms_step * 1e-3) / 1e6
 
-    KINDS = {0: "other", 1: "tc_gemm_kernel", 2: "tc_conv_kernel", 3: "conv1_tc_kernel", 4: "direct_conv_kernel", 5: "igemm_f32_kernel", 6: "conv_rows_tc_kernel"}
+    KINDS = {0: "other", 1: "tc_gemm_kernel", 2: "tc_conv_kernel", 3: "conv1_tc_kernel", 4: "direct_conv_kernel", 5: "igemm_f32_kernel", 6: "conv_rows_tc_kernel", 7: "tc_gemm2_kernel", 8: "attn_fused_kernel"}
     by_kind = {}
     for name, ms, fl, by, kind in prof:
         k = by_kind.setdefault(KINDS.get(kind, "other"), {"ms": 0.0, "flops": 0.0, "launches": 0})

@@ -346,7 +346,7 @@ int launch_attn_fused(const bf16* qk_hi, const bf16* qk_lo, const bf16* vt_hi, c
   attn_fused_kernel<<<grid, 320, AT_SMEM, st>>>(maps, p);
   CIC_COUNT_LAUNCH();
   CIC_CHECK_LAUNCH("attn_fused_kernel");
-  g_last_kernel_kind = KK_TC_GEMM;
+  g_last_kernel_kind = KK_ATTN;
   return CIC_OK;
 }
 

@@ -46,7 +46,7 @@ void set_error(const char* fmt, ...);
 extern thread_local long long g_launch_count;
 #define CIC_COUNT_LAUNCH() (++cic::g_launch_count)
 // kernel class of the last heavy launch (the per-layer profiler tags its records with it)
-enum KernelKind { KK_NONE = 0, KK_TC_GEMM = 1, KK_TC_CONV = 2, KK_TC_CONV1 = 3, KK_DIRECT = 4, KK_SIMT = 5, KK_TC_ROWS = 6 };
+enum KernelKind { KK_NONE = 0, KK_TC_GEMM = 1, KK_TC_CONV = 2, KK_TC_CONV1 = 3, KK_DIRECT = 4, KK_SIMT = 5, KK_TC_ROWS = 6, KK_TC_GEMM2 = 7, KK_ATTN = 8 };
 extern thread_local int g_last_kernel_kind;
 
 int sm_count();

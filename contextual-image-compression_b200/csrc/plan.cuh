@@ -152,6 +152,9 @@ int encoder_forward_f32(cic_plan* pl, Ctx& c, const float* img, float* latent, f
 int generator_forward_f32(cic_plan* pl, Ctx& c, const float* latent, const float* s1, const float* s2, const float* s3,
                           float* out, int B);
 int saliency_forward_f32(cic_plan* pl, Ctx& c, const float* latent, float* score, int B);
+// mlp_fused.cu
+int launch_rd_tail_fused(const float* feat, int ld, const float* bpp, const float* w1, const float* b1, const float* w2, const float* b2,
+                         float* rd_params, int B, cudaStream_t st);
 int rd_forward_f32(cic_plan* pl, Ctx& c, const float* mask, const float* bpp, float* rd_params, int B);
 int adaptive_forward_f32(cic_plan* pl, Ctx& c, const cic_adaptive_io* io, int n_img, int img_h, int img_w);
 int launch_rd_tail(cic_plan* pl, Ctx& c, const float* bpp, float* feat, float* d1, float* base, float* rd_params, int B);

@@ -543,6 +543,13 @@ int rd_forward_f32(cic_plan* pl, Ctx& c, const float* mask, const float* bpp, fl
 int launch_rd_tail(cic_plan* pl, Ctx& c, const float* bpp, float* feat, float* d1, float* base, float* rd_params, int B) {
   const WeightStore& w = pl->w;
   int rc;
+  static const int fused_env = getenv("CIC_MLP_FUSED") ? atoi(getenv("CIC_MLP_FUSED")) : 1;
+  if (fused_env) {  // concat + Dense128 + Dense3 + sigmoids in one kernel (mlp_fused.cu)
+    if (c.dry) return CIC_OK;
+    Scope sc(c, "tail", 2.0 * B * (65.0 * 128 + 128 * 3), 4.0 * (65 * 128 + 128 * 3 + (double)B * 68));
+    return launch_rd_tail_fused(feat, 65, bpp, w.ptr("dense1/kernel"), w.ptr("dense1/bias"), w.ptr("dense2/kernel"), w.ptr("dense2/bias"), rd_params, B,
+                                c.st);
+  }
   if (!c.dry) {
     rd_set_t_kernel<<<(B + 127) / 128, 128, 0, c.st>>>(bpp, feat, B, 65, 64);
     CIC_COUNT_LAUNCH();

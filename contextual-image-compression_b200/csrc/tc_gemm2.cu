@@ -313,7 +313,7 @@ static int launch2_thr(const TcMaps& maps, const TcParams& p, int total_pairs, c
   tc_gemm2_kernel<BN, BK, SPLIT, THREADS><<<grid, THREADS, Cfg::kSmemBytes, st>>>(maps, p, total_pairs);
   CIC_COUNT_LAUNCH();
   CIC_CHECK_LAUNCH("tc_gemm2_kernel");
-  g_last_kernel_kind = KK_TC_GEMM;
+  g_last_kernel_kind = KK_TC_GEMM2;
   return CIC_OK;
 }
 

@@ -43,10 +43,11 @@ tc_conv_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcvP
   uint64_t* b_empty = b_full + TCV_MAX_SLOTS;
   uint64_t* tmem_full_bar = b_empty + TCV_MAX_SLOTS;  // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;       // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* first_bar = tmem_empty_bar + 2;           // [2] merged ops: the overwriting first op of the tile has retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(first_bar + 2);
   // per issuer warp: [TCV_MAX_ISSUERS][TCV_MAX_PASS][TCV_MAX_OPS] {a_shift, b_off, d_off, flags} and, per raster of a pass,
   // that issuer's op range (first | count << 8)
-  uint4* ops_tab = reinterpret_cast<uint4*>(tmem_empty_bar + 4);
+  uint4* ops_tab = reinterpret_cast<uint4*>(tmem_empty_bar + 6);
   uint32_t* rast_tab = reinterpret_cast<uint32_t*>(ops_tab + TCV_MAX_ISSUERS * TCV_MAX_PASS * TCV_MAX_OPS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -69,19 +70,25 @@ tc_conv_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcvP
         const int first = n;
         for (int oi = ps.r[ri].op0; oi < ps.r[ri].op0 + ps.r[ri].nops; ++oi) {
           const TcvOp op = ps.op[oi];
-          const bool mine = op.acc % nw == w;
+          const bool mine = (p.merged ? oi : (int)op.acc) % nw == w;  // merged ops span accumulators: dealt round-robin
           if (p.b_resident && !mine) continue;  // streamed weights: every issuer walks every op (ring hand-shakes), issues its own
           uint32_t flags = (op.first ? TCV_F_FIRST : 0) | (mine ? TCV_F_MINE : 0);
           if (oi == ps.r[ri].op0) flags |= TCV_F_NEW_RASTER;
           if (oi == ps.r[ri].op0 + ps.r[ri].nops - 1) flags |= TCV_F_LAST_OF_RASTER;
           uint32_t b_off;
-          if (p.b_resident) {
+          if (p.merged && p.b_resident) {
+            b_off = (uint32_t)op.blk0 * b_blk_lo;
+          } else if (p.merged) {  // streamed: one weight-ring slot per op (its nph blocks back to back)
+            flags |= TCV_F_NEW_BGROUP | TCV_F_LAST_OF_BGROUP;
+            b_off = 0;
+          } else if (p.b_resident) {
             b_off = (uint32_t)((ps.phase_id[op.acc] * p.n_tiles * p.ntaps + op.tap) * cpt) * b_blk_lo;
           } else {  // table order == op order == weight ring order
             if (oi % p.b_group == 0) flags |= TCV_F_NEW_BGROUP;
             if (oi % p.b_group == p.b_group - 1 || oi == ps.nops - 1) flags |= TCV_F_LAST_OF_BGROUP;
             b_off = (uint32_t)(oi % p.b_group) * b_blk_lo;
           }
+          flags |= (uint32_t)(((p.merged ? op.nph : 1) * p.BN) >> 3) << 8;  // MMA N of this op (instruction-descriptor field)
           tab[n++] = make_uint4((uint32_t)op.row_shift * (kRowBytes >> 4), b_off, (uint32_t)(op.acc * p.BN), flags);
         }
         rt[ri] = (uint32_t)first | ((uint32_t)(n - first) << 8);
@@ -101,7 +108,10 @@ tc_conv_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcvP
         mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], (uint32_t)nw);
         mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], (uint32_t)nw);
       }
-      for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], (uint32_t)nw); mbar_init(&tmem_empty_bar[s], 4u * (uint32_t)p.ne); }
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(&tmem_full_bar[s], (uint32_t)nw); mbar_init(&tmem_empty_bar[s], 4u * (uint32_t)p.ne);
+        mbar_init(&first_bar[s], 1);
+      }
       fence_barrier_init();
     }
     __syncwarp();
@@ -153,6 +163,18 @@ tc_conv_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcvP
         mbar_arrive_expect_tx(&b_full[0], p.b_tx_bytes * (uint32_t)p.b_blocks);
         const int nph = p.b_blocks / (p.n_tiles * p.ntaps * cpt);
         int blk = 0;
+        if (p.merged) {
+          // per channel block: the blocks of every op back to back, so a merged op's B operand is one contiguous N = nph * BN tile
+          const TcvPass& ps = p.pass[0];
+          for (int cb = 0; cb < cpt; ++cb)
+            for (int oi = 0; oi < ps.nops; ++oi) {
+              const TcvOp op = ps.op[oi];
+              for (int j = 0; j < op.nph; ++j) {
+                uint8_t* b_hi = b_ring + (size_t)(cb * p.nblk_cb + op.blk0 + j) * p.b_slot_bytes;
+                tma_load_3d(b_hi, &maps.b[0], &b_full[0], (op.taps[j] * cpt + cb) * BK, ps.phase_id[op.acc + j] * p.N_pad, 0);
+              }
+            }
+        } else
         for (int ph = 0; ph < nph; ++ph)
           for (int nt = 0; nt < p.n_tiles; ++nt)
             for (int tap = 0; tap < p.ntaps; ++tap)
@@ -171,6 +193,20 @@ tc_conv_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcvP
           const int nops = ps.nops;
           const int brow0 = tc.n_tile * p.BN;
           for (int cb = 0; cb < cpt; ++cb) {
+            if (p.merged) {
+              for (int oi = 0; oi < nops; ++oi) {
+                const TcvOp op = ps.op[oi];
+                mbar_wait_relaxed(&b_empty[sb], pb ^ 1u);
+                uint8_t* slot = b_ring + (size_t)sb * G * p.b_slot_bytes;
+                if (p.dbg & 2) mbar_arrive(&b_full[sb]);
+                else mbar_arrive_expect_tx(&b_full[sb], p.b_tx_bytes * (uint32_t)op.nph);
+                for (int j = 0; j < op.nph && !(p.dbg & 2); ++j)
+                  tma_load_3d(slot + (size_t)j * p.b_slot_bytes, &maps.b[0], &b_full[sb], (op.taps[j] * cpt + cb) * BK,
+                              ps.phase_id[op.acc + j] * p.N_pad + brow0, 0);
+                if (++sb == (uint32_t)p.b_slots) { sb = 0; pb ^= 1u; }
+              }
+              continue;
+            }
             for (int o0 = 0; o0 < nops; o0 += G) {
               const int cnt = min(G, nops - o0);
               mbar_wait_relaxed(&b_empty[sb], pb ^ 1u);
@@ -200,7 +236,8 @@ tc_conv_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcvP
     // issuers when the weights are resident.
     const int w = warp == 1 ? 0 : (warp == 7 ? 1 : warp - 10);
     if (w < nw && elect_one()) {
-      const uint32_t idesc = tcv_idesc(p.BN);
+      const uint32_t idesc0 = tcv_idesc(0);  // N comes from the op table
+      const uint32_t b_cb_step = b_blk_lo * (uint32_t)(p.merged ? p.nblk_cb : 1);
       const uint32_t a_ring_lo = (smem_u32(a_ring) & 0x3FFFF) >> 4, b_ring_lo = (smem_u32(b_ring) & 0x3FFFF) >> 4;
       const uint32_t a_slot_lo = (uint32_t)p.a_slot_bytes >> 4, a_half_lo = a_slot_lo >> 1;
       const uint32_t b_slot_lo = b_blk_lo * (uint32_t)p.b_group, b_half_lo = b_blk_lo >> 1;
@@ -242,6 +279,7 @@ tc_conv_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcvP
                 b_base = b_ring_lo + sb * b_slot_lo;
               }
               if ((o.w & TCV_F_MINE) && !(p.dbg & 1)) {
+                const uint32_t idesc = idesc0 | (((o.w >> 8) & 0xFFu) << 17);
                 const uint32_t a_hi = a_base + o.x, b_hi = b_base + o.y, d = d0 + o.z;
                 const uint32_t keep = (o.w & fresh_mask) ? 0u : 1u;
 #pragma unroll
@@ -278,6 +316,12 @@ tc_conv_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcvP
           const int as = lt & 1;
           mbar_wait(&tmem_empty_bar[as], (((uint32_t)lt >> 1) & 1u) ^ 1u);
           tc_fence_after();
+          if (p.merged && w != 0) {
+            // merged ops of different issuers accumulate into the same TMEM columns: order does not matter for the sums, but
+            // the first op of the tile overwrites - wait until it has retired
+            mbar_wait(&first_bar[as], ((uint32_t)lt >> 1) & 1u);
+            tc_fence_after();
+          }
           const uint32_t d0 = tmem_base + (uint32_t)(as * TCV_ACC_COLS);
           uint32_t b_cb = b_ring_lo + (uint32_t)tc.n_tile * res_tile_stride;  // resident: block (phase 0, n_tile, tap 0, cb)
           for (int cb = 0; cb < cpt; ++cb) {
@@ -296,6 +340,7 @@ tc_conv_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcvP
                   tc_fence_after();
                   b_base = b_ring_lo + sb * b_slot_lo;
                 }
+                const uint32_t idesc = idesc0 | (((o.w >> 8) & 0xFFu) << 17);
                 const uint32_t a_hi = a_base + o.x, b_hi = (resident ? b_cb : b_base) + o.y, d = d0 + o.z;
                 const uint32_t keep = (o.w & fresh_mask) ? 0u : 1u;
                 if (!(p.dbg & 1)) {
@@ -315,12 +360,13 @@ tc_conv_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcvP
                   umma_commit(&b_empty[sb]);
                   if (++sb == n_bslots) { sb = 0; pb ^= 1u; }
                 }
+                if (p.merged && (o.w & fresh_mask)) umma_commit(&first_bar[as]);  // the overwriting op (issuer 0 owns it)
                 o = nx;
               }
               umma_commit(&a_empty[sa]);  // this issuer's share of the raster slot: free once its MMAs have retired
               if (++sa == n_aslots) { sa = 0; pa ^= 1u; }
             }
-            b_cb += b_blk_lo;  // resident: next channel block of every tap
+            b_cb += b_cb_step;  // resident: next channel block
           }
           umma_commit(&tmem_full_bar[as]);
         }

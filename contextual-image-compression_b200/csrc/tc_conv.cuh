@@ -44,10 +44,13 @@ struct TcvRaster {
 
 struct TcvOp {
   uint16_t row_shift;  // A window starts this many rows (pixels) into the raster
-  uint8_t acc;         // accumulator (local phase) index of the pass
+  uint8_t acc;         // accumulator (local phase) index of the pass (the first one of a merged op)
   uint8_t tap;         // tap index in the weight K order: K block = (tap * cpt + channel block)
-  uint8_t first;       // first op of its accumulator in the pass (overwrite at channel block 0)
-  uint8_t pad_[3];
+  uint8_t first;       // first op of its accumulator(s) in the pass (overwrite at channel block 0)
+  uint8_t nph;         // merged op: accumulators acc .. acc + nph - 1 share this A window (one MMA of N = nph * BN); else 1
+  uint8_t blk0;        // merged op: first weight block of the op within a channel block's group of resident blocks
+  uint8_t pad_;
+  uint8_t taps[4];     // merged op: tap index of each merged accumulator
 };
 
 // flags of the MMA op table the kernel builds in shared memory
@@ -106,6 +109,8 @@ struct TcvParams {
   int b_slot_bytes;       // one weight block [BN x BK]; in split mode [hi | lo]
   int b_group;            // weight blocks per ring slot (loaded under one mbarrier); ring slot = b_group * b_slot_bytes
   uint32_t a_tx_bytes, b_tx_bytes;
+  int merged;             // 1: transposed-conv ops are merged per input shift (resident weights, see tc_host.cu)
+  int nblk_cb;            // merged: resident weight blocks per channel block (16)
   int nw;                 // MMA issuer warps (accumulators a % nw == w belong to issuer w); > 1 only with resident weights
   int ne;                 // epilogue groups of four warps (1 or 2)
   int dbg;                // CIC_TC_DBG elimination bits: 1 no MMA issue, 2 no weight loads, 4 no raster loads, 8 no stores

@@ -221,10 +221,70 @@ static int try_run_raster(const TcLayer& L, int BK, int N_pad, const TcMaps& act
     }
   }
   if (p.a_slots < 2) return CIC_OK;
+  // Resident transposed conv: merge the four phases' MMAs per input shift.  The 16 (phase, tap) products read only 9
+  // distinct shifted A windows; with the accumulators ordered (0,0) (0,1) (1,1) (1,0) the phases that share a shift are
+  // adjacent (except one wrap-around pair), so one MMA of N = nph * BN serves them: 11 ops instead of 16 and 9/16 of the
+  // A operand reads - the shared-memory data pipe is what bounds these N <= 32 layers (profiles/r01_smem_pipe_model.md).
+  // CIC_TC_MERGE: 0 off, 1 resident-weight layers (default; deconv4 1.13 -> 0.87 ms), 2 also streamed weights on this kernel
+  // (measured slower than the per-tap kernel for deconv3: 0.87 vs 0.70 ms - the raster kernel's per-op hand-shakes)
+  static const int merge_env = getenv("CIC_TC_MERGE") ? atoi(getenv("CIC_TC_MERGE")) : 1;
+  if (merge_env && fused && !L.split && mode != 2 && 4 * BN <= TCV_ACC_COLS && (p.b_resident || merge_env >= 2)) {
+    TcvPass& P = p.pass[0];
+    static const int acc_phase[4] = {0, 1, 3, 2};                 // accumulator -> phase (py * 2 + px)
+    struct MOp { int dy, dx, acc0, nph; };
+    static const MOp mops[11] = {{0, 0, 0, 4},  {-1, 0, 0, 2}, {1, 0, 2, 2},  {0, 1, 1, 2},  {0, -1, 3, 1}, {0, -1, 0, 1},
+                                 {-1, -1, 0, 1}, {-1, 1, 1, 1}, {1, 1, 2, 1}, {1, -1, 3, 1}};
+    const int nm = 10;
+    // rasters: ROW mode one raster holds every shift; COL mode one raster per dx, the dx = 0 raster (centre op) first
+    const int dx_order[3] = {0, -1, 1};
+    memset(&P, 0, sizeof(P));
+    P.nacc = 4;
+    for (int a = 0; a < 4; ++a) P.phase_id[a] = (int8_t)acc_phase[a];
+    int nops = 0, blk = 0;
+    max_end = 0;
+    const int nr = mode == 0 ? 1 : 3;
+    for (int ri = 0; ri < nr; ++ri) {
+      TcvRaster& R = P.r[P.nrast++];
+      R.dc = 0; R.pz = 0;
+      R.dx = (int16_t)(mode == 0 ? -1 : dx_order[ri]);
+      R.dy = -1;
+      R.op0 = (uint8_t)nops;
+      for (int m = 0; m < nm; ++m) {
+        if (mode == 1 && mops[m].dx != dx_order[ri]) continue;
+        TcvOp& o = P.op[nops];
+        const int sh = (mops[m].dy - R.dy) * p.rw + (mops[m].dx - R.dx);
+        o.row_shift = (uint16_t)sh;
+        o.acc = (uint8_t)mops[m].acc0;
+        o.nph = (uint8_t)mops[m].nph;
+        o.blk0 = (uint8_t)blk;
+        o.first = nops == 0 ? 1 : 0;
+        for (int j = 0; j < mops[m].nph; ++j) {
+          const int ph = acc_phase[mops[m].acc0 + j], py = ph >> 1, px = ph & 1;
+          const int ty = mops[m].dy + (py == 0 ? 1 : 0), tx = mops[m].dx + (px == 0 ? 1 : 0);
+          o.taps[j] = (uint8_t)(ty * 2 + tx);
+        }
+        o.tap = o.taps[0];
+        blk += mops[m].nph;
+        max_end = std::max(max_end, sh + TC_BM);
+        ++nops;
+      }
+      R.nops = (uint8_t)(nops - R.op0);
+    }
+    P.nops = nops;
+    p.merged = 1;
+    p.nblk_cb = blk;  // 16
+    if (!p.b_resident) {  // streamed: one ring slot per op, sized for four blocks
+      p.b_group = 4;
+      const int gbytes = p.b_group * b_slot_bytes;
+      p.b_slots = std::min(TCV_MAX_SLOTS, std::max(2, (budget - 3 * p.a_slot_bytes) / gbytes));
+      p.a_slots = std::min(8, (budget - p.b_slots * gbytes) / p.a_slot_bytes);
+      if (p.a_slots < 2) return CIC_OK;
+    }
+  }
   // Streamed weights: measured (r01, CIC_TC_RASTER=0 vs default on conv2 / deconv1..3) the per-tap kernel is 10-25 % faster -
   // one barrier pair per K block there against separate raster + weight-group hand-shakes per op here, and both
   // are bound by the shared-memory data pipe rather than by L2 traffic.  The raster kernel keeps the resident-weight layers.
-  if (!p.b_resident && force != 1) return CIC_OK;
+  if (!p.b_resident && force != 1 && !p.merged) return CIC_OK;
 
   // tensor maps
   TcMaps maps;
@@ -278,7 +338,8 @@ static int try_run_raster(const TcLayer& L, int BK, int N_pad, const TcMaps& act
   // issuer warps: one per accumulator (output phase) when the weights are resident and the MMAs are small
   static const int nw_env = getenv("CIC_TC_NW") ? atoi(getenv("CIC_TC_NW")) : 0;
   p.nw = 1;
-  if (fused) p.nw = nw_env > 0 ? nw_env : (p.b_resident ? 4 : 1);  // streamed weights: extra issuers measured no gain (shared-memory data pipe bound)
+  if (fused) p.nw = nw_env > 0 ? nw_env : (p.b_resident ? 2 : 1);  // measured r01: 2 issuers (384 threads, 168 regs) beat 4 (448 threads: 128-register
+                                                                  // cap spills the epilogue); streamed weights: extra issuers gave nothing
   // a second epilogue group when one tile has several accumulator chunks to drain per few MMAs
   static const int ne_env = getenv("CIC_TC_NE") ? atoi(getenv("CIC_TC_NE")) : 0;
   {

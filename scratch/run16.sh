@@ -1,0 +1,11 @@
+CIC_TC_MERGE=2 timeout 900 python -m pytest tests/test_gpu_tc_ops.py tests/test_gpu_models.py -m gpu -x -q 2>&1 | tail -4
+run() { name=$1; shift; env "$@" timeout 300 python bench.py --steps 6 --warmup 3 --cpu-tiles 0 --profile-csv gpurun_out/layers_$name.csv > gpurun_out/bench_$name.log 2> gpurun_out/err_$name.log; echo -n "$name: "; grep -E "deconv[34]" gpurun_out/layers_$name.csv | cut -d, -f2 | tr '\n' ' '; python -c "
+import json
+l=[x for x in open('gpurun_out/bench_$name.log') if x.startswith('{')]
+d=json.loads(l[-1]); print(' ms', round(d['ms_per_step'],3), 'e2e', round(d['e2e']['ms_per_step'],2), d['clocks']['sm_mhz'], d['clocks']['reasons'])
+"; }
+for rep in 1 2; do
+run a_m2_$rep CIC_TC_MERGE=2
+run b_m1_$rep CIC_TC_MERGE=1
+run c_m2ne1_$rep CIC_TC_MERGE=2 CIC_TC_NE=1
+done

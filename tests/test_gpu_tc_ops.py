@@ -40,6 +40,8 @@ CONV_CASES = [  # kh, stride, B, H, W, Cin, Cin2, Cout, act
     (1, 1, 2, 8, 8, 256, 0, 64, None),           # attention q|k projection
     (1, 1, 1, 32, 32, 256, 0, 256, None),
     (3, 1, 1, 40, 136, 64, 0, 64, "relu"),       # W > 128: several tiles per row, ragged last tile
+    (3, 1, 1, 17, 128, 64, 0, 128, "relu"),      # CTA-pair kernel: 17 M tiles -> odd pair count, phantom tile masked
+    (3, 1, 2, 32, 64, 128, 0, 256, "lrelu"),     # CTA-pair kernel: N tile 256, 32 M tiles
 ]
 
 
@@ -65,7 +67,9 @@ def test_conv2d_tc_matches_oracle(cic, split, kh, stride, B, H, W, Cin, Cin2, Co
     assert err < tol(split, kh * kh * ct), f"max-abs {err}"
 
 
-DECONV_CASES = [(2, 4, 4, 512, 0, 256), (1, 8, 8, 256, 256, 128), (3, 8, 6, 64, 64, 32), (2, 16, 16, 128, 128, 64)]
+DECONV_CASES = [(2, 4, 4, 512, 0, 256), (1, 8, 8, 256, 256, 128), (3, 8, 6, 64, 64, 32), (2, 16, 16, 128, 128, 64),
+                (2, 16, 16, 128, 128, 128),   # CTA-pair kernel with four output phases
+                (1, 34, 64, 64, 0, 256)]      # CTA-pair kernel, 17 M tiles per phase
 
 
 @pytest.mark.parametrize("split", [False, True])

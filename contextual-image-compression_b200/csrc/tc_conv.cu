@@ -232,7 +232,7 @@ tc_conv_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcvP
     // ===== MMA issuers: warp 1 (+ warps 7.. when nw > 1); one elected lane of each runs the whole role.  Every op is one
     // 16-byte shared-memory word fetched one op ahead (ld.shared).  A single thread sustains ~5 cycles per dependent
     // instruction and ~90 per mbarrier try_wait, so with N <= 64 per MMA one issuer cannot keep the tensor pipe busy
-    // (elimination runs, profiles/r01_issue_bound_elimination.md): the accumulators (output phases) are split over nw
+    // (elimination runs, profiles/r01_smem_pipe_model.md section 1): the accumulators (output phases) are split over nw
     // issuers when the weights are resident.
     const int w = warp == 1 ? 0 : (warp == 7 ? 1 : warp - 10);
     if (w < nw && elect_one()) {

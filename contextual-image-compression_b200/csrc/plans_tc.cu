@@ -32,7 +32,22 @@ static TcAct view(const ActBuf& a, int C, int ld = 0, int coff = 0) { return TcA
 
 // ---- packed weights ---------------------------------------------------------------------------
 // fp32 [K][ld] device matrix (columns [col0, col0 + N)) -> bf16 [N_pad][K] hi (+ lo) owned by the plan
-static int pack(cic_plan* pl, const std::string& name, const float* src, int K, int N, int N_pad, bool with_lo, int ld = 0, int col0 = 0) {
+// bn != "": the layer is followed by inference BatchNorm: y = (x W + bias) * scale + shift = x (W * scale) + (bias * scale + shift), so the
+// scale is folded into the packed weights and "<name>#fb" holds the fused bias - the epilogue then reads one per-channel vector
+// instead of three (a uniform 128-bit load costs four l1tex data-pipe wavefronts, and that pipe bounds the narrow layers:
+// profiles/r01_epilogue_data_pipe.md)
+static int fuse_bn(cic_plan* pl, const std::string& name, const std::string& bn, int N) {
+  const WeightStore& w = pl->w;
+  const float* scale = w.ptr(bn + "/scale");
+  const float* shift = w.ptr(bn + "/shift");
+  CIC_REQUIRE(scale && shift, "tc plan: missing folded BatchNorm '%s'", bn.c_str());
+  float* fb = (float*)pl->tcw.alloc(name + "#fb", (size_t)N * sizeof(float));
+  CIC_REQUIRE(fb, "tc plan: out of device memory");
+  return tc_fuse_bias(w.ptr(name + "/bias"), scale, shift, fb, N, nullptr);
+}
+
+static int pack(cic_plan* pl, const std::string& name, const float* src, int K, int N, int N_pad, bool with_lo, int ld = 0, int col0 = 0,
+                const std::string& bn = std::string()) {
   CIC_REQUIRE(src, "tc plan: missing fp32 weight for '%s'", name.c_str());
   const size_t bytes = (size_t)N_pad * K * sizeof(bf16);
   bf16* hi = (bf16*)pl->tcw.alloc(name + "#hi", bytes);
@@ -41,8 +56,14 @@ static int pack(cic_plan* pl, const std::string& name, const float* src, int K, 
     set_error("tc plan: out of device memory packing '%s' (%zu bytes)", name.c_str(), bytes);
     return CIC_ERR_CUDA;
   }
-  return tc_pack_weight(src + col0, K, N, N_pad, ld ? ld : N, hi, lo, nullptr);
+  if (!bn.empty()) {
+    const int rc = fuse_bn(pl, name, bn, N);
+    if (rc) return rc;
+  }
+  return tc_pack_weight(src + col0, K, N, N_pad, ld ? ld : N, hi, lo, nullptr, bn.empty() ? nullptr : pl->w.ptr(bn + "/scale"));
 }
+
+static const float* fused_bias(const cic_plan* pl, const std::string& name) { return (const float*)pl->tcw.ptr(name + "#fb"); }
 
 static TcMat mat(const cic_plan* pl, const std::string& name, int K, int rows) {
   TcMat m{};
@@ -83,7 +104,7 @@ int build_plan_tc(cic_plan* pl, const cic_tensor* tensors, int n, const std::str
       }
       for (int i = 2; i <= 4; ++i) {
         const std::string nm = "conv" + std::to_string(i);
-        if ((rc = pack(pl, nm, w.ptr(nm + "/kernel"), 16 * ch[i - 1], ch[i], ch[i], true))) return rc;
+        if ((rc = pack(pl, nm, w.ptr(nm + "/kernel"), 16 * ch[i - 1], ch[i], ch[i], true, 0, 0, "bn" + std::to_string(i)))) return rc;
       }
       if (pl->opts.add_attention) {
         const DevTensor* qkv = w.find("attn/qkv/kernel");
@@ -102,7 +123,7 @@ int build_plan_tc(cic_plan* pl, const cic_tensor* tensors, int n, const std::str
     }
     case CIC_PLAN_GENERATOR: {
       const int feat = (pl->opts.img_h / 16) * (pl->opts.img_w / 16) * 512, L = pl->opts.latent_dim;
-      if (L % 32 == 0 && (rc = pack(pl, "dense", w.ptr("dense/kernel"), L, feat, feat, false))) return rc;
+      if (L % 32 == 0 && (rc = pack(pl, "dense", w.ptr("dense/kernel"), L, feat, feat, false, 0, 0, "bn0"))) return rc;
       const int cin[5] = {0, 512, 512, 256, 128}, cout[5] = {0, 256, 128, 64, 32};
       for (int i = 1; i <= 4; ++i) {
         const std::string nm = "deconv" + std::to_string(i);
@@ -111,9 +132,11 @@ int build_plan_tc(cic_plan* pl, const cic_tensor* tensors, int n, const std::str
         const size_t bytes = (size_t)4 * cout[i] * 4 * cin[i] * sizeof(bf16);
         bf16* hi = (bf16*)pl->tcw.alloc(nm + "#hi", bytes);
         CIC_REQUIRE(hi, "tc plan: out of device memory packing %s", nm.c_str());
+        const std::string bn = "bn" + std::to_string(i);
+        if ((rc = fuse_bn(pl, nm, bn, cout[i]))) return rc;
         for (int p = 0; p < 4; ++p)
           if ((rc = tc_pack_weight(ph + (size_t)p * 4 * cin[i] * cout[i], 4 * cin[i], cout[i], cout[i], cout[i],
-                                   hi + (size_t)p * cout[i] * 4 * cin[i], nullptr, nullptr))) return rc;
+                                   hi + (size_t)p * cout[i] * 4 * cin[i], nullptr, nullptr, w.ptr(bn + "/scale")))) return rc;
       }
       if (pl->opts.img_c <= 16) rc = pack(pl, "conv_out", w.ptr("conv_out/kernel"), 16 * 32, pl->opts.img_c, 16, false);
       if (!rc && pl->opts.img_c == 3) {
@@ -358,9 +381,9 @@ static int encoder_core_tc(cic_plan* pl, Ctx& c, const float* img, float* latent
   }
   // conv2..conv3: k4 s2 + BN + LeakyReLU, 3-term split-bf16 (:304-312)
   if ((rc = conv_tc(c, "conv2", TC_CONV_S2, view(sk.x1, 64), nullptr, B, H / 2, W / 2, 4, 4, 2, mat(pl, "conv2", 16 * 64, 128), 128, true,
-                    epi_bf16(w.ptr("conv2/bias"), w.ptr("bn2/scale"), w.ptr("bn2/shift"), CIC_ACT_LRELU02, sk.x2)))) return rc;
+                    epi_bf16(fused_bias(pl, "conv2"), nullptr, nullptr, CIC_ACT_LRELU02, sk.x2)))) return rc;
   if ((rc = conv_tc(c, "conv3", TC_CONV_S2, view(sk.x2, 128), nullptr, B, H / 4, W / 4, 4, 4, 2, mat(pl, "conv3", 16 * 128, 256), 256, true,
-                    epi_bf16(w.ptr("conv3/bias"), w.ptr("bn3/scale"), w.ptr("bn3/shift"), CIC_ACT_LRELU02, sk.x3)))) return rc;
+                    epi_bf16(fused_bias(pl, "conv3"), nullptr, nullptr, CIC_ACT_LRELU02, sk.x3)))) return rc;
   ActBuf x3a = sk.x3;
   if (pl->opts.add_attention) {  // the skip is tapped before attention (:312 vs :318)
     x3a = alloc_act(c, px / 64 * 256, true);
@@ -368,7 +391,7 @@ static int encoder_core_tc(cic_plan* pl, Ctx& c, const float* img, float* latent
   }
   ActBuf x4 = alloc_act(c, px / 256 * 512, true);
   if ((rc = conv_tc(c, "conv4", TC_CONV_S2, view(x3a, 256), nullptr, B, H / 8, W / 8, 4, 4, 2, mat(pl, "conv4", 16 * 256, 512), 512, true,
-                    epi_bf16(w.ptr("conv4/bias"), w.ptr("bn4/scale"), w.ptr("bn4/shift"), CIC_ACT_LRELU02, x4)))) return rc;
+                    epi_bf16(fused_bias(pl, "conv4"), nullptr, nullptr, CIC_ACT_LRELU02, x4)))) return rc;
   // Flatten (NHWC) + Dense (:325-326): split-K GEMM, partials reduced in a fixed order
   const int feat = (H / 16) * (W / 16) * 512, Lp = round_up(L, 16);
   const int splits = dense_splits(B, Lp, feat, true);
@@ -417,7 +440,7 @@ static int generator_core_tc(cic_plan* pl, Ctx& c, const float* latent, const bf
     ActBuf lat = alloc_act(c, (size_t)B * L, false);
     if (!c.dry && (rc = tc_split_f32(latent, lat.hi, nullptr, (size_t)B * L, c.st))) return rc;
     if ((rc = dense_tc(c, "dense", view(lat, L), B, mat(pl, "dense", L, feat), feat, false, 1,
-                       epi_bf16(w.ptr("dense/bias"), w.ptr("bn0/scale"), w.ptr("bn0/shift"), CIC_ACT_LRELU02, g0)))) return rc;
+                       epi_bf16(fused_bias(pl, "dense"), nullptr, nullptr, CIC_ACT_LRELU02, g0)))) return rc;
   } else {  // latent sizes a K block cannot take: fp32 CUDA-core GEMM, then to bf16
     float* g0f = c.arena.f32((size_t)B * feat);
     const size_t wsb = cic_dense_workspace_bytes(B, L, feat);
@@ -432,7 +455,7 @@ static int generator_core_tc(cic_plan* pl, Ctx& c, const float* latent, const bf
   // :253-270 four Conv2DTranspose(k4, s2) + BN + LeakyReLU, the skips concatenated on the channel axis
 #define DC(i, s0v, s1p, hh, ww, cin, co, dst)                                                                             \
   if ((rc = conv_tc(c, "deconv" #i, TC_DECONV_K4S2, s0v, s1p, B, hh, ww, 2, 2, 1, mat(pl, "deconv" #i, 4 * (cin), 4 * (co)), co, false, \
-                    epi_bf16(w.ptr("deconv" #i "/bias"), w.ptr("bn" #i "/scale"), w.ptr("bn" #i "/shift"), CIC_ACT_LRELU02, dst)))) return rc
+                    epi_bf16(fused_bias(pl, "deconv" #i), nullptr, nullptr, CIC_ACT_LRELU02, dst)))) return rc
   TcAct k3{s3, nullptr, 256, 256, 0}, k2{s2, nullptr, 128, 128, 0}, k1{s1, nullptr, 64, 64, 0};
   DC(1, view(g0, 512), nullptr, h16, w16, 512, 256, g1);
   DC(2, view(g1, 256), &k3, 2 * h16, 2 * w16, 512, 128, g2);

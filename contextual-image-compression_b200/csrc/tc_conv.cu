@@ -49,6 +49,7 @@ tc_conv_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcvP
   // that issuer's op range (first | count << 8)
   uint4* ops_tab = reinterpret_cast<uint4*>(tmem_empty_bar + 6);
   uint32_t* rast_tab = reinterpret_cast<uint32_t*>(ops_tab + TCV_MAX_ISSUERS * TCV_MAX_PASS * TCV_MAX_OPS);
+  const TcEpiVec ev{p.epi.bias, p.epi.scale, p.epi.shift};
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cpt = p.src_blocks[0] + p.src_blocks[1];  // channel blocks per tap
@@ -421,8 +422,8 @@ tc_conv_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcvP
           const int n0 = tc.n_tile * p.BN + c * ch;
           const int nv = min(ch, p.epi.N - n0);
           if (valid && nv > 0 && !(p.dbg & 8)) {
-            if (wide) tc_epilogue_store<32>(p.epi, row, v, n0, nv);
-            else tc_epilogue_store<16>(p.epi, row, v, n0, nv);
+            if (wide) tc_epilogue_store<32>(p.epi, ev, row, v, n0, nv);
+            else tc_epilogue_store<16>(p.epi, ev, row, v, n0, nv);
           }
         }
       }

@@ -29,6 +29,15 @@ struct TcEpi {
   int tm_tx, tm_ty, tm_IH, tm_IW;  // tm_tx != 0: batch item b is tile (ty, tx) of image b / (tm_tx * tm_ty) in (n, IH, IW, ld)
 };
 
+// Per-channel epilogue vectors (global memory).  Staging them in shared memory was measured neutral (r01): a uniform 128-bit
+// load costs four l1tex data-pipe wavefronts whether it is LDG or LDS (profiles/r01_epilogue_data_pipe.md); what helps is
+// needing fewer vectors - the plans fold BatchNorm's scale into the packed weights and bias / shift into one vector.
+struct TcEpiVec {
+  const float* bias;
+  const float* scale;
+  const float* shift;
+};
+
 struct TcRow {  // the output row this thread owns
   int b, oy, ox, phase, split;
 };
@@ -39,7 +48,7 @@ struct TcRow {  // the output row this thread owns
 // (the first version interleaved null checks, a per-element activation switch and scalar loads, and the
 // epilogue warps stalled on instruction fetch: profiles/r01_ncu_raster_issue_bound.md).
 template <int CH>
-__device__ __forceinline__ void tc_epilogue_store(const TcEpi& e, const TcRow& r, const uint32_t (&v)[32], int n0, int nv) {
+__device__ __forceinline__ void tc_epilogue_store(const TcEpi& e, const TcEpiVec& ev, const TcRow& r, const uint32_t (&v)[32], int n0, int nv) {
   long long opix;
   if (e.tm_tx) {  // scatter the tile into the image layout
     const int tpi = e.tm_tx * e.tm_ty, img = r.b / tpi, t = r.b % tpi;
@@ -76,8 +85,8 @@ __device__ __forceinline__ void tc_epilogue_store(const TcEpi& e, const TcRow& r
   }
   // per-channel affine: (x + bias) * scale + shift  (conv bias, folded BatchNorm)
   if (full && (n0 & 3) == 0) {
-    if (e.bias) {
-      const float4* b4 = reinterpret_cast<const float4*>(e.bias + n0);
+    if (ev.bias) {
+      const float4* b4 = reinterpret_cast<const float4*>(ev.bias + n0);
 #pragma unroll
       for (int j = 0; j < CH / 4; ++j) {
         const float4 b = __ldg(b4 + j);
@@ -85,9 +94,9 @@ __device__ __forceinline__ void tc_epilogue_store(const TcEpi& e, const TcRow& r
         f[4 * j + 2] = __fadd_rn(f[4 * j + 2], b.z); f[4 * j + 3] = __fadd_rn(f[4 * j + 3], b.w);
       }
     }
-    if (e.scale) {
-      const float4* s4 = reinterpret_cast<const float4*>(e.scale + n0);
-      const float4* t4 = reinterpret_cast<const float4*>(e.shift + n0);
+    if (ev.scale) {
+      const float4* s4 = reinterpret_cast<const float4*>(ev.scale + n0);
+      const float4* t4 = reinterpret_cast<const float4*>(ev.shift + n0);
 #pragma unroll
       for (int j = 0; j < CH / 4; ++j) {
         const float4 sc = __ldg(s4 + j), sh = __ldg(t4 + j);
@@ -96,14 +105,14 @@ __device__ __forceinline__ void tc_epilogue_store(const TcEpi& e, const TcRow& r
       }
     }
   } else {
-    if (e.bias) {
+    if (ev.bias) {
 #pragma unroll
-      for (int j = 0; j < CH; ++j) f[j] = __fadd_rn(f[j], j < nv ? __ldg(e.bias + n0 + j) : 0.f);
+      for (int j = 0; j < CH; ++j) f[j] = __fadd_rn(f[j], j < nv ? __ldg(ev.bias + n0 + j) : 0.f);
     }
-    if (e.scale) {
+    if (ev.scale) {
 #pragma unroll
       for (int j = 0; j < CH; ++j)
-        f[j] = __fadd_rn(__fmul_rn(f[j], j < nv ? __ldg(e.scale + n0 + j) : 1.f), j < nv ? __ldg(e.shift + n0 + j) : 0.f);
+        f[j] = __fadd_rn(__fmul_rn(f[j], j < nv ? __ldg(ev.scale + n0 + j) : 1.f), j < nv ? __ldg(ev.shift + n0 + j) : 0.f);
     }
   }
   switch (e.act) {

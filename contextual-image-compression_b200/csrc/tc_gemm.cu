@@ -56,6 +56,7 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
   uint64_t* tmem_full_bar = empty_bar + kStages;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;    // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  const TcEpiVec ev{p.epi.bias, p.epi.scale, p.epi.shift};
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -187,7 +188,7 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         }
         const int n0 = tc.n_tile * BN + c * CH;
         const int nv = min(CH, p.N - n0);  // valid channels of this chunk
-        if (valid && nv > 0) tc_epilogue_store<CH>(p.epi, row, v, n0, nv);
+        if (valid && nv > 0) tc_epilogue_store<CH>(p.epi, ev, row, v, n0, nv);
       }
     }
   }

@@ -135,6 +135,12 @@ __device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
   return v;
 }
 
+__device__ __forceinline__ uint2 lds_v2(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
+
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
   uint32_t v;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
@@ -271,5 +277,8 @@ int launch_tc_gemm(const TcMaps& maps, TcParams& p, int block_n, int block_k, bo
 // CTA-pair (cta_group::2) variant, tc_gemm2.cu; maps.b encoded with box {BK, block_n / 2}
 int launch_tc_gemm2(const TcMaps& maps, TcParams& p, int block_n, int block_k, bool split, cudaStream_t st);
 int tc2_pick_block_n(int n_pad);
+// merged-phase CTA-pair kernel for Conv2DTranspose(k4, s2) with Cout in {32, 64} (tc_gemm2.cu); maps.b box {64, Cout / 2}
+bool tc_deconv2_ok(int bk, bool split, long long m_tiles, int n_pad, int n);
+int launch_tc_deconv2(const TcMaps& maps, TcParams& p, cudaStream_t st);
 
 }  // namespace cic

@@ -389,14 +389,26 @@ int tc_run_layer(const TcLayer& L, cudaStream_t st) {
                   "tc layer: bf16 output needs N %% 16 == 0 and 16-byte aligned records (N=%d, ld=%d, coff=%d)", L.N, ld, L.epi.out_coff);
     }
     bool used = false;
+    // CIC_TC_DC2: merged-phase CTA-pair kernel for transposed convs with Cout in {32, 64} (tc_gemm2.cu): 0 off, 1 the layers
+    // the raster kernel streams weights for (deconv3), 2 also the resident-weight raster layers (deconv4)
+    static const int dc2_env = getenv("CIC_TC_DC2") ? atoi(getenv("CIC_TC_DC2")) : 0;
+    bool skip_raster = false;
+    if (dc && dc2_env >= 2) {
+      int tw, th, tb;
+      pick_tile(Wo, Ho, L.batch, false, tw, th, tb);
+      const long long mt = (long long)((Wo + tw - 1) / tw) * ((Ho + th - 1) / th) * ((L.batch + tb - 1) / tb);
+      skip_raster = tc_deconv2_ok(BK, L.split, mt, n_pad, L.N);
+    }
     // 64-channel layers whose whole weight matrix fits in shared memory only next to 32-channel rasters (deconv4:
     // 128 KB of weights + 3 x 25 KB rasters) run with the smaller K block and resident weights
-    if (BK == 64 && raster_prefers_bk32(L, n_pad)) {
+    if (!skip_raster && BK == 64 && raster_prefers_bk32(L, n_pad)) {
       const int rc32 = try_run_raster(L, 32, n_pad, maps, st, &used);
       if (rc32 || used) return rc32;
     }
-    const int rc = try_run_raster(L, BK, n_pad, maps, st, &used);
-    if (rc || used) return rc;
+    if (!skip_raster) {
+      const int rc = try_run_raster(L, BK, n_pad, maps, st, &used);
+      if (rc || used) return rc;
+    }
   }
   pick_tile(Wo, Ho, L.batch, L.b_batched, p.TW, p.TH, p.TB);
   p.tiles_x = (Wo + p.TW - 1) / p.TW;
@@ -482,15 +494,17 @@ int tc_run_layer(const TcLayer& L, cudaStream_t st) {
   static const int pair_env = getenv("CIC_TC_PAIR") ? atoi(getenv("CIC_TC_PAIR")) : 1;
   const long long m_tiles = (long long)p.tiles_x * p.tiles_y * p.tiles_b;
   const int bn2 = tc2_pick_block_n(p.N_pad);
-  const bool pair = pair_env && !L.b_batched && tc_pair_ok(BK, m_tiles, p.N_pad, L.N);
-  const int bn = pair ? bn2 : tc_pick_block_n(p.N_pad, L.split, BK);
+  static const int dc2_env = getenv("CIC_TC_DC2") ? atoi(getenv("CIC_TC_DC2")) : 0;
+  const bool dc2 = dc && dc2_env && pair_env && L.splits == 1 && tc_deconv2_ok(BK, L.split, m_tiles, p.N_pad, L.N);
+  const bool pair = !dc2 && pair_env && !L.b_batched && tc_pair_ok(BK, m_tiles, p.N_pad, L.N);
+  const int bn = dc2 ? L.N : (pair ? bn2 : tc_pick_block_n(p.N_pad, L.split, BK));
   CIC_REQUIRE(bn > 0 && L.N <= p.N_pad, "tc layer: N=%d (padded %d) has no supported tile", L.N, p.N_pad);
   CIC_REQUIRE(L.w.row_stride % 8 == 0 && L.w.batch_stride % 8 == 0, "tc layer: B rows must be 16-byte aligned");
   // weight / B map
   for (int part = 0; part < (L.split ? 2 : 1); ++part) {
     const uint64_t dims[3] = {(uint64_t)L.w.K, (uint64_t)L.w.rows, (uint64_t)L.w.batches};
     const uint64_t str[2] = {(uint64_t)L.w.row_stride * 2, (uint64_t)L.w.batch_stride * 2};
-    const uint32_t box[3] = {(uint32_t)BK, (uint32_t)(pair ? bn / 2 : bn), 1};
+    const uint32_t box[3] = {(uint32_t)BK, (uint32_t)(pair || dc2 ? bn / 2 : bn), 1};
     int rc = tc_encode_map(&maps.b[part], part ? L.w.lo : L.w.hi, 3, dims, str, box);
     if (rc) return rc;
   }
@@ -510,6 +524,7 @@ int tc_run_layer(const TcLayer& L, cudaStream_t st) {
   pe.Ho = Ho; pe.Wo = Wo;
   pe.tm_tx = e.tm_tx; pe.tm_ty = e.tm_ty; pe.tm_IH = e.tm_IH; pe.tm_IW = e.tm_IW;
   pe.m_total = (long long)L.batch * Ho * Wo;
+  if (dc2) return launch_tc_deconv2(maps, p, st);
   if (pair) return launch_tc_gemm2(maps, p, bn, BK, L.split, st);
   return launch_tc_gemm(maps, p, bn, BK, L.split, st);
 }
@@ -523,13 +538,14 @@ __device__ __forceinline__ void split2(float v, bf16& h, bf16& l) {
 }
 
 __global__ void __launch_bounds__(256)
-pack_weight_kernel(const float* __restrict__ src, int K, int N, int N_pad, int ld, bf16* __restrict__ hi, bf16* __restrict__ lo) {
+pack_weight_kernel(const float* __restrict__ src, int K, int N, int N_pad, int ld, bf16* __restrict__ hi, bf16* __restrict__ lo,
+                   const float* __restrict__ col_scale) {
   __shared__ float tile[32][33];
   const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
   for (int i = ty; i < 32; i += 8) {
     const int k = k0 + i, n = n0 + tx;
-    tile[i][tx] = (k < K && n < N) ? src[(size_t)k * ld + n] : 0.f;
+    tile[i][tx] = (k < K && n < N) ? (col_scale ? __fmul_rn(src[(size_t)k * ld + n], col_scale[n]) : src[(size_t)k * ld + n]) : 0.f;
   }
   __syncthreads();
   for (int i = ty; i < 32; i += 8) {
@@ -543,10 +559,10 @@ pack_weight_kernel(const float* __restrict__ src, int K, int N, int N_pad, int l
   }
 }
 
-int tc_pack_weight(const float* src, int K, int N, int N_pad, int ld, bf16* hi, bf16* lo, cudaStream_t st) {
+int tc_pack_weight(const float* src, int K, int N, int N_pad, int ld, bf16* hi, bf16* lo, cudaStream_t st, const float* col_scale) {
   dim3 grid((K + 31) / 32, (N_pad + 31) / 32);
   CIC_REQUIRE(grid.y <= 65535, "pack_weight: N too large");
-  pack_weight_kernel<<<grid, 256, 0, st>>>(src, K, N, N_pad, ld, hi, lo);
+  pack_weight_kernel<<<grid, 256, 0, st>>>(src, K, N, N_pad, ld, hi, lo, col_scale);
   CIC_COUNT_LAUNCH();
   CIC_CHECK_LAUNCH("pack_weight_kernel");
   return CIC_OK;
@@ -560,6 +576,20 @@ __global__ void split_f32_kernel(const float* __restrict__ src, bf16* __restrict
     hi[i] = h;
     if (lo) lo[i] = l;
   }
+}
+
+__global__ void fuse_bias_kernel(const float* __restrict__ bias, const float* __restrict__ scale, const float* __restrict__ shift,
+                                 float* __restrict__ out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __fadd_rn(__fmul_rn(bias ? bias[i] : 0.f, scale[i]), shift[i]);
+}
+
+int tc_fuse_bias(const float* bias, const float* scale, const float* shift, float* out, int n, cudaStream_t st) {
+  CIC_REQUIRE(scale && shift && out && n > 0, "fuse_bias: null argument");
+  fuse_bias_kernel<<<(n + 255) / 256, 256, 0, st>>>(bias, scale, shift, out, n);
+  CIC_COUNT_LAUNCH();
+  CIC_CHECK_LAUNCH("fuse_bias_kernel");
+  return CIC_OK;
 }
 
 int tc_split_f32(const float* src, bf16* hi, bf16* lo, size_t n, cudaStream_t st) {

@@ -64,7 +64,10 @@ bool tc_pair_ok(int bk, long long m_tiles, int n_pad, int n);
 
 // fp32 [K][ld] (row-major, Keras kernel / Dense layout; the first N columns) -> bf16 hi/lo [N_pad][K]
 // (K contiguous), zero rows >= N
-int tc_pack_weight(const float* src, int K, int N, int N_pad, int ld, bf16* hi, bf16* lo, cudaStream_t st);
+// col_scale (optional, N floats): column n of src is multiplied by col_scale[n] before rounding - folded BatchNorm scale
+int tc_pack_weight(const float* src, int K, int N, int N_pad, int ld, bf16* hi, bf16* lo, cudaStream_t st, const float* col_scale = nullptr);
+// out[n] = bias[n] * scale[n] + shift[n]: the one epilogue vector left once the scale lives in the weights
+int tc_fuse_bias(const float* bias, const float* scale, const float* shift, float* out, int n, cudaStream_t st);
 // fp32 -> bf16 hi (+ lo)
 int tc_split_f32(const float* src, bf16* hi, bf16* lo, size_t n, cudaStream_t st);
 // bf16 hi (+ lo) -> fp32, with strided source records (ld, coff) -> dense C

@@ -1,0 +1,12 @@
+timeout 600 python -m pytest tests/test_gpu_tc_ops.py -m gpu -x -q -k "transpose" 2>&1 | tail -4
+CIC_TC_DC2=2 timeout 600 python -m pytest tests/test_gpu_tc_ops.py -m gpu -x -q -k "transpose" 2>&1 | tail -4
+run() { name=$1; shift; env "$@" timeout 300 python bench.py --steps 6 --warmup 3 --cpu-tiles 0 --profile-csv gpurun_out/layers_$name.csv > gpurun_out/bench_$name.log 2> gpurun_out/err_$name.log; echo -n "$name: "; grep -E "deconv[34]" gpurun_out/layers_$name.csv | cut -d, -f2 | tr '\n' ' '; python -c "
+import json
+l=[x for x in open('gpurun_out/bench_$name.log') if x.startswith('{')]
+d=json.loads(l[-1]); print(' ms', round(d['ms_per_step'],3), 'e2e', round(d['e2e']['ms_per_step'],2), d['clocks']['sm_mhz'], d['clocks']['reasons'], d['quality']['psnr_db'])
+"; tail -3 gpurun_out/err_$name.log; }
+for rep in 1 2; do
+run dc2_0_$rep CIC_TC_DC2=0
+run dc2_1_$rep CIC_TC_DC2=1
+run dc2_2_$rep CIC_TC_DC2=2
+done

@@ -69,7 +69,10 @@ def test_conv2d_tc_matches_oracle(cic, split, kh, stride, B, H, W, Cin, Cin2, Co
 
 DECONV_CASES = [(2, 4, 4, 512, 0, 256), (1, 8, 8, 256, 256, 128), (3, 8, 6, 64, 64, 32), (2, 16, 16, 128, 128, 64),
                 (2, 16, 16, 128, 128, 128),   # CTA-pair kernel with four output phases
-                (1, 34, 64, 64, 0, 256)]      # CTA-pair kernel, 17 M tiles per phase
+                (1, 34, 64, 64, 0, 256),      # CTA-pair kernel, 17 M tiles per phase
+                (1, 34, 64, 64, 0, 64),       # merged-phase pair kernel (Cout 64): 17 M tiles -> phantom tile masked
+                (4, 32, 32, 128, 128, 64),    # merged-phase pair kernel: generator deconv3 shape, two sources, 32 M tiles
+                (2, 32, 64, 128, 0, 32)]      # merged-phase pair kernel, Cout 32 (generator deconv4 shape)
 
 
 @pytest.mark.parametrize("split", [False, True])

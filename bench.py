@@ -23,7 +23,6 @@ import argparse
 import json
 import os
 import sys
-import threading
 import time
 
 import numpy as np
@@ -50,49 +49,67 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
-class ClockSampler(threading.Thread):
-    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+_SAMPLER_SRC = r"""
+import sys, time
+import pynvml as nv
+nv.nvmlInit()
+h = nv.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))
+bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
+print("max", nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM), flush=True)
+while True:
+    t = time.time()
+    c = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+    print(repr(t), c, ",".join(k for k, b in bits.items() if r & b) or "-", flush=True)
+    time.sleep(0.004)
+"""
 
-    def __init__(self, index: int, period: float = 0.01):
-        super().__init__(daemon=True)
-        self.index, self.period = index, period
-        self.samples, self.reasons, self.max_mhz = [], set(), None
-        self._stop_evt = threading.Event()
-        self.ok = False
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU through NVML from a child process (the bench thread holds the GIL
+    while it queues launches, so an in-process sampler thread starves during a short timed region).  The child runs from
+    before the warm-up; stop() keeps the samples whose time stamps fall inside [start(), stop()]."""
+
+    def __init__(self, index: int):
+        self.proc, self.t0, self.err = None, None, None
         try:
-            import pynvml
-            pynvml.nvmlInit()
-            self.nv = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
-            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
-            self.ok = True
+            import subprocess
+            self.proc = subprocess.Popen([sys.executable, "-c", _SAMPLER_SRC, str(index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
         except Exception as e:  # noqa: BLE001
             self.err = repr(e)
 
-    def run(self):
-        if not self.ok:
-            return
-        nv = self.nv
-        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
-                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
-                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
-                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
-        while not self._stop_evt.is_set():
-            try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for k, bit in names.items():
-                    if r & bit:
-                        self.reasons.add(k)
-            except Exception:  # noqa: BLE001
-                pass
-            self._stop_evt.wait(self.period)
+    def start(self):
+        self.t0 = time.time()
 
     def stop(self):
-        self._stop_evt.set()
-        self.join(timeout=2)
-        med = float(np.median(self.samples)) if self.samples else None
-        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        t1 = time.time()
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "error": self.err}
+        time.sleep(0.02)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        mx, inside, allc, reasons = None, [], [], set()
+        for ln in out.splitlines():
+            f = ln.split()
+            if len(f) == 2 and f[0] == "max":
+                mx = int(f[1])
+            elif len(f) == 3:
+                t, c = float(f[0]), int(f[1])
+                allc.append((t, c))
+                if self.t0 <= t <= t1:
+                    inside.append(c)
+                    if f[2] != "-":
+                        reasons.update(f[2].split(","))
+        if not inside and allc:  # region shorter than one sampling period: the sample nearest to its middle
+            mid = 0.5 * (self.t0 + t1)
+            inside = [min(allc, key=lambda tc: abs(tc[0] - mid))[1]]
+        med = float(np.median(inside)) if inside else None
+        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(inside)}
 
 
 def make_inputs(rank: int, n_img: int):
@@ -189,6 +206,12 @@ def main():
     torch.cuda.set_device(dev)
     cic.set_precision(args.precision)
     peaks = measured_peaks()
+    # clock sampler child (started now so that it is up before the timed region); NVML indices are physical
+    cuda_idx = dev.index if dev.index is not None else 0
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+    if vis and all(v.strip().isdigit() for v in vis.split(",")) and cuda_idx < len(vis.split(",")):
+        cuda_idx = int(vis.split(",")[cuda_idx])
+    sampler = ClockSampler(cuda_idx)
 
     n_img = args.images
     n_tiles = n_img * (IMG_HW // TILE) ** 2
@@ -249,7 +272,6 @@ def main():
         step_device()
     torch.cuda.synchronize()
     plan.set_profiling(True)
-    sampler = ClockSampler(dev.index if dev.index is not None else 0)
     cic.dist.barrier()
     torch.cuda.synchronize()
     sampler.start()
@@ -324,6 +346,32 @@ def main():
     e2e_value = world * px_per_step / (ms_e2e * 1e-3) / 1e6
     h2d = int(h_img.numel() * 4 + h_mask.numel() * 4 + h_bpp.numel() * 4)
     d2h = int(sum(o.nbytes for o in outs) + sums_host.numel() * 8)
+
+    # ---------------- HBM-bound kernels of the path: algorithmic bytes / device time ----------------------
+    hbm_peak = peaks["hbm_gbs"]
+    hbm = {}
+    for name, ms, fl, by, kind in prof:
+        if name in ("roi_blend", "quantize") and ms > 0:
+            hbm[name] = {"ms": ms, "algorithmic_bytes": by, "gbs": by / ms / 1e6, "frac_of_hbm_peak": by / ms / 1e6 / hbm_peak}
+    am.forward_device([d_img, d_mask, d_bpp], extras=False)
+    blended = am.last["blended"]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    cic.ops.metrics_f32(d_img, blended, signed_range=True)
+    torch.cuda.synchronize()
+    reps = 5
+    ev[0].record()
+    for _ in range(reps):
+        cic.ops.metrics_f32(d_img, blended, signed_range=True)
+    ev[1].record()
+    torch.cuda.synchronize()
+    m_ms = ev[0].elapsed_time(ev[1]) / reps
+    m_bytes = 24.0 * px_per_step                                  # two fp32 RGB images read once
+    hbm["metrics_psnr_ssim_f32"] = {"ms": m_ms, "algorithmic_bytes": m_bytes, "gbs": m_bytes / m_ms / 1e6,
+                                    "frac_of_hbm_peak": m_bytes / m_ms / 1e6 / hbm_peak,
+                                    "note": "bound by the fp32<->fp64 conversion pipe, not HBM: scipy-exact 7x7 window sums "
+                                            "(double accumulation, float32 after each pass), DESIGN.md 4.4"}
+    roofline["hbm_kernels"] = hbm
+    roofline["hbm_peak_gbs"] = hbm_peak
 
     s = sums.cpu().numpy()[0]
     n_total = s[6]

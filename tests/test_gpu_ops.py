@@ -140,6 +140,20 @@ def test_metrics_f32_match_oracle(cic, h, w):
     assert set(d) == {"psnr", "ssim", "mse"} and abs(d["psnr"] - got[0, 0]) < 1e-9
 
 
+@pytest.mark.parametrize("n,h,w", [(4, 416, 400), (7, 300, 333)])
+def test_metrics_f32_many_tiles_match_oracle(cic, n, h, w):
+    # several waves of tiles per SM, ragged right / bottom tiles
+    rng = np.random.default_rng(n * h + w)
+    a = (cic.synth.to_signed_range(cic.synth.synth_images_u8(n, h, w, seed=13))).astype(np.float32)
+    b = np.clip(a + rng.standard_normal(a.shape).astype(np.float32) * np.float32(0.05), -1, 1).astype(np.float32)
+    got = cic.ops.metrics_f32(a, b, signed_range=True).cpu().numpy()
+    for i in range(n):
+        m = metrics.compute_metrics(a[i], b[i])
+        assert abs(got[i, 0] - m["psnr"]) < 1e-6
+        assert abs(got[i, 1] - m["ssim"]) < 2e-6
+        assert abs(got[i, 2] - float(m["mse"])) < 1e-8
+
+
 def test_metrics_identical_images(cic):
     a = cic.synth.to_signed_range(cic.synth.synth_images_u8(1, 32, 32))
     got = cic.ops.metrics_f32(a, a, signed_range=True).cpu().numpy()[0]

@@ -292,7 +292,7 @@ attn_fused_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__
         }
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__fmul_rn(__uint_as_float(v[i]), inv_l));
-        tc_epilogue_store<32>(p.epi, TcEpiVec{p.epi.bias, p.epi.scale, p.epi.shift}, row, v, c * 32, 32);
+        tc_epilogue_store<32>(p.epi, TcEpiVec{p.epi.bias, p.epi.scale, p.epi.shift}, row, v, c * 32, 32, true, 0);
       }
       named_bar_sync_at(2, 256);   // row sums consumed before the next item overwrites the exchange buffer
     }

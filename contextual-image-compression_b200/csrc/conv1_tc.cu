@@ -37,6 +37,32 @@ struct Conv1Params {
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
+// 4 x 4 transpose of 16-byte pieces inside every quad of lanes: in: p[4 k + w] = word w of piece k of this lane's row; out:
+// p[4 j + w] = word w of piece (lane & 3) of the row of quad lane j.  After it the four lanes of a quad hold 64 contiguous
+// bytes of one row per store instruction instead of one 32-byte piece of four different rows: a warp store then touches 8 lines
+// instead of 32 (the l1tex data pipe was 69 % busy with this kernel's stores, profiles/r01_epilogue_data_pipe.md).
+__device__ __forceinline__ void quad_transpose16(uint32_t (&p)[16], int lane) {
+  const bool b0 = lane & 1, b1 = lane & 2;
+#pragma unroll
+  for (int pr = 0; pr < 2; ++pr) {
+    const int k0 = 2 * pr, k1 = 2 * pr + 1;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const uint32_t recv = __shfl_xor_sync(0xffffffffu, b0 ? p[4 * k0 + w] : p[4 * k1 + w], 1);
+      if (b0) p[4 * k0 + w] = recv; else p[4 * k1 + w] = recv;
+    }
+  }
+#pragma unroll
+  for (int pr = 0; pr < 2; ++pr) {
+    const int k0 = pr, k1 = pr + 2;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const uint32_t recv = __shfl_xor_sync(0xffffffffu, b1 ? p[4 * k0 + w] : p[4 * k1 + w], 2);
+      if (b1) p[4 * k0 + w] = recv; else p[4 * k1 + w] = recv;
+    }
+  }
+}
+
 template <int N>
 __global__ void __launch_bounds__(288, 2)
 conv1_tc_kernel(const __grid_constant__ Conv1Params p) {
@@ -201,7 +227,8 @@ conv1_tc_kernel(const __grid_constant__ Conv1Params p) {
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
         }
-        if (!valid) continue;
+        const bool quads = (p.TW & 3) == 0;  // rows 4q .. 4q+3 are consecutive pixels of one image row
+        if (!quads && !valid) continue;
         const int enc = c >> 1, ch0 = (c & 1) * 32;
         const float4* b4 = reinterpret_cast<const float4*>(p.bias + c * 32);
         uint32_t hi[16], lo[16];
@@ -223,6 +250,20 @@ conv1_tc_kernel(const __grid_constant__ Conv1Params p) {
         }
         __nv_bfloat16* dh = p.out_hi[enc] + opix + ch0;  // 64-byte aligned: whole-sector 256-bit stores
         __nv_bfloat16* dl = p.out_lo[enc] + opix + ch0;
+        if (quads) {
+          const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+          quad_transpose16(hi, lane);
+          quad_transpose16(lo, lane);
+          const int l4 = lane & 3, q0 = lane & ~3;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (!((vmask >> (q0 + j)) & 1u)) continue;
+            const long long d = (long long)(j - l4) * 64 + l4 * 8;  // row of quad lane j, piece l4 (8 bf16 = 16 bytes)
+            *reinterpret_cast<uint4*>(dh + d) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+            *reinterpret_cast<uint4*>(dl + d) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+          }
+          continue;
+        }
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           st_global_v8(dh + 16 * j, hi[8 * j], hi[8 * j + 1], hi[8 * j + 2], hi[8 * j + 3], hi[8 * j + 4], hi[8 * j + 5], hi[8 * j + 6], hi[8 * j + 7]);

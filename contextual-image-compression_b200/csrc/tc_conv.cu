@@ -421,9 +421,9 @@ tc_conv_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcvP
           const int ch = wide ? 32 : 16;
           const int n0 = tc.n_tile * p.BN + c * ch;
           const int nv = min(ch, p.epi.N - n0);
-          if (valid && nv > 0 && !(p.dbg & 8)) {
-            if (wide) tc_epilogue_store<32>(p.epi, ev, row, v, n0, nv);
-            else tc_epilogue_store<16>(p.epi, ev, row, v, n0, nv);
+          if (nv > 0 && !(p.dbg & 8)) {
+            if (wide) tc_epilogue_store<32>(p.epi, ev, row, v, n0, nv, valid, p.TW);
+            else tc_epilogue_store<16>(p.epi, ev, row, v, n0, nv, valid, 0);
           }
         }
       }

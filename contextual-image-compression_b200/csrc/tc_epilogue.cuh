@@ -47,8 +47,43 @@ struct TcRow {  // the output row this thread owns
 // outside the element loops, per-channel vectors are fetched as float4, and only the taken variant runs
 // (the first version interleaved null checks, a per-element activation switch and scalar loads, and the
 // epilogue warps stalled on instruction fetch: profiles/r01_ncu_raster_issue_bound.md).
+// 4 x 4 transpose of 16-byte pieces inside every quad of lanes: in: p[4 k + w] = word w of piece k of this lane's row; out:
+// p[4 j + w] = word w of piece (lane & 3) of the row of quad lane j.  The four lanes of a quad then store 64 contiguous bytes of
+// one row per instruction instead of 32-byte pieces of four rows: 8 lines per warp store instead of 32
+// (profiles/r01_epilogue_data_pipe.md).
+__device__ __forceinline__ void tc_quad_transpose16(uint32_t* p, int lane) {
+  const bool b0 = lane & 1, b1 = lane & 2;
+#pragma unroll
+  for (int pr = 0; pr < 2; ++pr) {
+    const int k0 = 2 * pr, k1 = 2 * pr + 1;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const uint32_t recv = __shfl_xor_sync(0xffffffffu, b0 ? p[4 * k0 + w] : p[4 * k1 + w], 1);
+      if (b0) p[4 * k0 + w] = recv; else p[4 * k1 + w] = recv;
+    }
+  }
+#pragma unroll
+  for (int pr = 0; pr < 2; ++pr) {
+    const int k0 = pr, k1 = pr + 2;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const uint32_t recv = __shfl_xor_sync(0xffffffffu, b1 ? p[4 * k0 + w] : p[4 * k1 + w], 2);
+      if (b1) p[4 * k0 + w] = recv; else p[4 * k1 + w] = recv;
+    }
+  }
+}
+
+// Called by ALL lanes of the warp (nv is warp-uniform); `valid` = this lane's row exists.  tw = tile width in rows (0 if consecutive
+// rows are not consecutive output positions): with tw % 4 == 0 the rows 4q .. 4q+3 of a warp are neighbours along x and the bf16
+// stores go through the quad transpose.
 template <int CH>
-__device__ __forceinline__ void tc_epilogue_store(const TcEpi& e, const TcEpiVec& ev, const TcRow& r, const uint32_t (&v)[32], int n0, int nv) {
+__device__ __forceinline__ void tc_epilogue_store(const TcEpi& e, const TcEpiVec& ev, const TcRow& r, const uint32_t (&v)[32], int n0, int nv,
+                                                  bool valid, int tw) {
+  // (hi, lo) outputs keep the direct stores: those layers (encoder conv2-4) are tensor-bound and the second transpose only
+  // lengthened their epilogue (conv2 +3 %), measured r01
+  const bool quads = CH == 32 && nv == CH && e.out_mode == TC_OUT_BF16 && !e.out_lo && !e.up2 && !e.tm_tx && !e.res_hi && tw > 0 &&
+                     (tw & 3) == 0 && ((e.out_ld | e.out_coff) & 15) == 0;
+  if (!quads && !valid) return;
   long long opix;
   if (e.tm_tx) {  // scatter the tile into the image layout
     const int tpi = e.tm_tx * e.tm_ty, img = r.b / tpi, t = r.b % tpi;
@@ -193,6 +228,20 @@ __device__ __forceinline__ void tc_epilogue_store(const TcEpi& e, const TcEpiVec
                                                        f[2 * j + 1] - __uint_as_float(hi[j] & 0xFFFF0000u));
         lo[j] = *reinterpret_cast<const uint32_t*>(&l);
       }
+    }
+    if constexpr (CH == 32) if (quads) {
+      const int lane = threadIdx.x & 31, l4 = lane & 3, q0 = lane & ~3;
+      const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+      tc_quad_transpose16(hi, lane);
+      const long long rstride = (long long)e.out_xs * e.out_ld;  // elements between the records of neighbouring rows
+      __nv_bfloat16* ph = reinterpret_cast<__nv_bfloat16*>(e.out_hi) + idx;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (!((vmask >> (q0 + j)) & 1u)) continue;
+        const long long d = (long long)(j - l4) * rstride + l4 * 8;  // row of quad lane j, 16-byte piece l4
+        *reinterpret_cast<uint4*>(ph + d) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+      }
+      return;
     }
     const int reps = e.up2 ? 2 : 1;
     const bool wide_ok = ((e.out_ld | e.out_coff) & 15) == 0;

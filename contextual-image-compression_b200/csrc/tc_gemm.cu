@@ -188,7 +188,7 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         }
         const int n0 = tc.n_tile * BN + c * CH;
         const int nv = min(CH, p.N - n0);  // valid channels of this chunk
-        if (valid && nv > 0) tc_epilogue_store<CH>(p.epi, ev, row, v, n0, nv);
+        if (nv > 0) tc_epilogue_store<CH>(p.epi, ev, row, v, n0, nv, valid, p.TW);
       }
     }
   }

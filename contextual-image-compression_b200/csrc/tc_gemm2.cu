@@ -293,7 +293,7 @@ tc_gemm2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcP
         }
         const int n0 = tc.n_tile * BN + c * CH;
         const int nv = min(CH, p.N - n0);
-        if (valid && nv > 0) tc_epilogue_store<CH>(p.epi, ev, row, v, n0, nv);
+        if (nv > 0) tc_epilogue_store<CH>(p.epi, ev, row, v, n0, nv, valid, p.TW);
       }
     }
   }
@@ -486,7 +486,7 @@ tc_deconv2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ T
         }
         const int acc = (c * 32) / COUT, n0 = (c * 32) % COUT;
         const TcRow row{b, oy, ox, q.acc_phase[acc], 0};
-        if (valid) tc_epilogue_store<32>(p.epi, ev, row, v, n0, 32);
+        tc_epilogue_store<32>(p.epi, ev, row, v, n0, 32, valid, p.TW);
       }
     }
   }

@@ -11,8 +11,9 @@ one pass over that batch.  N > 1 (torchrun, one rank per GPU): every rank codes 
 the timed region.  One JSON line is printed by rank 0.
 
 `value`  : MPix/s with inputs resident in HBM, timed with CUDA events on the launch stream.
-`e2e`    : same metric through the public API (adaptive_model.predict) with pinned HOST buffers, i.e.
-           host->device copy of images/masks/bpp and device->host read of every model output per step.
+`e2e`    : same metric through the public API (adaptive_model.predict_phased, or predict_pipelined with --e2e-mode pipelined)
+           with pinned HOST buffers, i.e. host->device copy of images/masks/bpp and device->host read of every model output
+           per step, overlapped with the kernels chunk by chunk.
 `roofline`: the conv/dense GEMM kernels (dominant), algorithmic FLOPs / summed per-layer device time
            (CUDA events recorded around every layer inside the timed steps) against the measured bf16 peak.
 `cpu_baseline`: the CPU oracle (torch fp32 restatement of the reference graph) on a bounded sample.
@@ -187,6 +188,11 @@ def main():
     ap.add_argument("--images", type=int, default=IMGS_PER_GPU, help="512x512 images per GPU per step")
     ap.add_argument("--e2e-chunks", default="auto", help="pipelined end-to-end leg: number of chunks of the batch, comma-separated chunk "
                     "sizes, or 'auto' (n/8, n/4, n/2, n/8: short first upload and last download)")
+    ap.add_argument("--e2e-mode", default="phased", choices=["phased", "pipelined"],
+                    help="end-to-end leg: predict_phased (encoder convs per upload chunk, Dense layers once per batch, decoders per "
+                         "download chunk) or predict_pipelined (the whole graph per chunk)")
+    ap.add_argument("--enc-chunks", default=None, help="phased: comma-separated upload / encode chunk sizes (default n/16, 3n/16, n/4, n/4, n/4)")
+    ap.add_argument("--dec-chunks", default=None, help="phased: comma-separated decode / download chunk sizes (default: the encode schedule reversed)")
     ap.add_argument("--cpu-tiles", type=int, default=8, help="tiles in the CPU-oracle sample (0 = skip)")
     ap.add_argument("--profile-csv", default=None, help="write the per-layer device times of the last timed step here")
     args = ap.parse_args()
@@ -258,9 +264,15 @@ def main():
         actual_bpp = (hq_ratio * (2 * BASE_LATENT) + (1.0 - hq_ratio) * BASE_LATENT) * 32.0 / (TILE * TILE)
         return cic.dist.metric_sums_row(m[:, 0], m[:, 1], m[:, 2], actual_bpp, hq_ratio, k)
 
+    enc_chunks = [int(v) for v in args.enc_chunks.split(",")] if args.enc_chunks else None
+    dec_chunks = [int(v) for v in args.dec_chunks.split(",")] if args.dec_chunks else None
+
     def step_e2e():
         # pinned host buffers -> (H2D | model + metrics | D2H of all 5 outputs) pipelined over chunks of the batch
-        outs, parts = am.predict_pipelined([h_img, h_mask, h_bpp], n_chunks=e2e_chunks, on_chunk=evaluate_chunk)
+        if args.e2e_mode == "phased":
+            outs, parts = am.predict_phased([h_img, h_mask, h_bpp], enc_chunks=enc_chunks, dec_chunks=dec_chunks, on_chunk=evaluate_chunk)
+        else:
+            outs, parts = am.predict_pipelined([h_img, h_mask, h_bpp], n_chunks=e2e_chunks, on_chunk=evaluate_chunk)
         sums = cic.dist.allreduce_metric_sums(torch.stack(parts).sum(0))
         return outs, sums.cpu()
 
@@ -401,7 +413,7 @@ def main():
                        "l2": f"inputs per step {h2d / 1e6:.0f} MB + activations >> 126 MB L2 (no flush needed)",
                        "step": "encode + quantise + decode + ROI blend + PSNR/SSIM/bpp evaluation + metric all-reduce"},
             "clocks": clocks, "e2e": {"value": e2e_value, "unit": "MPix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                                      "ms_per_step": ms_e2e},
+                                      "ms_per_step": ms_e2e, "api": f"adaptive_model.predict_{args.e2e_mode}"},
             "gpu_launches": int(launches_per_step * args.steps), "roofline": roofline, "cpu_baseline": cpu, "quality": quality,
             "layers_ms_per_step": total_layer_ms}
     print(json.dumps(line))

@@ -41,6 +41,12 @@ class cic_adaptive_io(C.Structure):
         "d_lq_out", "d_hq_ratio_sum")]
 
 
+class cic_adaptive_state(C.Structure):
+    _fields_ = [(n, C.c_void_p * 2) for n in ("x1", "x2", "x3", "x4_hi", "x4_lo", "g0")]
+
+
+PHASE_ENCODE, PHASE_LATENT, PHASE_DECODE = 1, 2, 3
+
 if not os.path.exists(LIB_PATH):
     raise ImportError(
         f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
@@ -67,6 +73,7 @@ PROTOTYPES = {
     "cic_saliency_forward": (_i, [_vp, _vp, _vp, _i, _vp, _sz, _vp]),
     "cic_rd_forward": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
     "cic_adaptive_forward": (_i, [_vp, C.POINTER(cic_adaptive_io), _i, _i, _i, _vp, _sz, _vp]),
+    "cic_adaptive_forward_phase": (_i, [_vp, C.POINTER(cic_adaptive_io), C.POINTER(cic_adaptive_state), _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "cic_conv2d_nhwc_f32": (_i, [_vp] * 6 + [_i] * 9 + [_vp]),
     "cic_conv2d_transpose4x4s2_nhwc_f32": (_i, [_vp] * 6 + [_i] * 6 + [_vp]),
     "cic_dense_workspace_bytes": (_sz, [_i, _i, _i]),

@@ -163,7 +163,8 @@ int autoencoder_forward_tc(cic_plan* pl, Ctx& c, const float* x, float* y, uint8
 int encoder_forward_tc(cic_plan* pl, Ctx& c, const float* img, float* latent, float* x1, float* x2, float* x3, int B);
 int generator_forward_tc(cic_plan* pl, Ctx& c, const float* latent, const float* s1, const float* s2, const float* s3,
                          float* out, int B);
-int adaptive_forward_tc(cic_plan* pl, Ctx& c, const cic_adaptive_io* io, int n_img, int img_h, int img_w);
+int adaptive_forward_tc(cic_plan* pl, Ctx& c, const cic_adaptive_io* io, int n_img, int img_h, int img_w, int phase = 0,
+                        const cic_adaptive_state* state = nullptr, int tile0 = 0);
 }  // namespace cic
 
 struct cic_plan {

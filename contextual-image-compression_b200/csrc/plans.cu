@@ -874,6 +874,48 @@ extern "C" int cic_adaptive_forward(cic_plan* plan, const cic_adaptive_io* io, i
              nullptr, nullptr);
 }
 
+extern "C" int cic_adaptive_forward_phase(cic_plan* plan, const cic_adaptive_io* io, const cic_adaptive_state* state, int phase,
+                                          int tile0, int n_img, int img_h, int img_w, void* d_workspace, size_t workspace_bytes,
+                                          void* stream) {
+  CIC_REQUIRE(plan && plan->kind == CIC_PLAN_ADAPTIVE, "cic_adaptive_forward_phase: not an adaptive plan");
+  CIC_REQUIRE(plan->opts.precision == CIC_PREC_TC, "cic_adaptive_forward_phase: tensor-core plans only");
+  CIC_REQUIRE(phase == CIC_PHASE_ENCODE || phase == CIC_PHASE_LATENT || phase == CIC_PHASE_DECODE,
+              "cic_adaptive_forward_phase: unknown phase %d", phase);
+  CIC_REQUIRE(io && state && tile0 >= 0 && n_img >= 0, "cic_adaptive_forward_phase: bad argument");
+  if (n_img == 0) return CIC_OK;
+  CIC_REQUIRE(io->d_bpp, "cic_adaptive_forward_phase: null bpp");
+  CIC_REQUIRE(phase != CIC_PHASE_ENCODE || (io->d_img && io->d_mask), "cic_adaptive_forward_phase: ENCODE needs image and mask");
+  CIC_REQUIRE(phase != CIC_PHASE_DECODE || io->d_mask, "cic_adaptive_forward_phase: DECODE needs the mask");
+  CIC_REQUIRE(phase == CIC_PHASE_ENCODE || (io->d_hq_latent_q && io->d_lq_latent_q) || phase == CIC_PHASE_DECODE,
+              "cic_adaptive_forward_phase: LATENT needs the quantised latent outputs");
+  for (int e = 0; e < 2; ++e)
+    CIC_REQUIRE(state->x1[e] && state->x2[e] && state->x3[e] && state->x4_hi[e] && state->x4_lo[e] && state->g0[e],
+                "cic_adaptive_forward_phase: null state buffer");
+  const int T = plan->opts.img_h;
+  CIC_REQUIRE(plan->opts.img_h == plan->opts.img_w, "cic_adaptive_forward_phase: square model tiles only");
+  CIC_REQUIRE(img_h > 0 && img_w > 0 && img_h % T == 0 && img_w % T == 0,
+              "cic_adaptive_forward_phase: image size %dx%d is not a multiple of the model tile %d", img_h, img_w, T);
+  const size_t need = cic_plan_workspace_bytes(plan, n_img, img_h, img_w);  // upper bound: the one-call forward of as many images
+  if (!d_workspace || workspace_bytes < need) {
+    set_error("workspace too small: need %zu bytes, got %zu", need, d_workspace ? workspace_bytes : (size_t)0);
+    return CIC_ERR_WORKSPACE;
+  }
+  Ctx c;
+  c.arena.base = (char*)d_workspace;
+  c.arena.cap = workspace_bytes;
+  c.st = (cudaStream_t)stream;
+  c.prof = &plan->prof;
+  if (plan->prof.on) { plan->prof.reset(); plan->prof.prefix = ""; }
+  const long long before = g_launch_count;
+  const int rc = adaptive_forward_tc(plan, c, io, n_img, img_h, img_w, phase, state, tile0);
+  plan->last_launches = g_launch_count - before;
+  if (rc == CIC_OK && c.arena.overflow) {
+    set_error("internal: workspace overflow");
+    return CIC_ERR_WORKSPACE;
+  }
+  return rc;
+}
+
 extern "C" size_t cic_attention_workspace_bytes(int batch, int tokens, int channels) {
   if (batch <= 0) return 0;
   const int chunk = batch < 32 ? batch : 32;

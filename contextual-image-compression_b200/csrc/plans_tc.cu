@@ -341,13 +341,25 @@ static EncSkips alloc_skips(Ctx& c, size_t px) {
   return s;
 }
 
+// part: 0 = whole encoder, 1 = convolutions only (conv4's output goes to *x4_ext), 2 = Flatten + Dense only (reads *x4_ext):
+// the phased adaptive forward runs the convolutions per chunk of the batch and the Dense layer once per batch.
+enum { ENC_ALL = 0, ENC_CONVS = 1, ENC_DENSE = 2 };
+static int encoder_dense_tc(cic_plan* pl, Ctx& c, const ActBuf& x4, float* latent, int B);
+
 static int encoder_core_tc(cic_plan* pl, Ctx& c, const float* img, float* latent, float* x1_f32, const EncSkips& sk, int B,
-                           const TileMap& tm = TileMap(), bool x1_ready = false) {
+                           const TileMap& tm = TileMap(), bool x1_ready = false, int part = ENC_ALL, const ActBuf* x4_ext = nullptr) {
   const WeightStore& w = pl->w;
   const int H = pl->opts.img_h, W = pl->opts.img_w, C = pl->opts.img_c, L = pl->opts.latent_dim;
   const size_t px = (size_t)B * H * W;
   const size_t mk = c.arena.mark();
   int rc;
+  (void)L;
+  if (part == ENC_DENSE) {
+    CIC_REQUIRE(x4_ext, "encoder (tc): dense part needs conv4's output");
+    rc = encoder_dense_tc(pl, c, *x4_ext, latent, B);
+    c.arena.release(mk);
+    return rc;
+  }
   // conv1 (3 -> 64, k4 s2) + LeakyReLU: K = 48 cannot feed a tensor-core K block; a direct CUDA-core kernel writes
   // the (hi, lo) bf16 pair the split-bf16 layers read (:300-302)
   if (x1_ready) {
@@ -389,10 +401,24 @@ static int encoder_core_tc(cic_plan* pl, Ctx& c, const float* img, float* latent
     x3a = alloc_act(c, px / 64 * 256, true);
     if ((rc = attention_tc(pl, c, sk.x3, x3a, B, (H / 8) * (W / 8), 256))) return rc;
   }
-  ActBuf x4 = alloc_act(c, px / 256 * 512, true);
+  ActBuf x4 = x4_ext ? *x4_ext : alloc_act(c, px / 256 * 512, true);
   if ((rc = conv_tc(c, "conv4", TC_CONV_S2, view(x3a, 256), nullptr, B, H / 8, W / 8, 4, 4, 2, mat(pl, "conv4", 16 * 256, 512), 512, true,
                     epi_bf16(fused_bias(pl, "conv4"), nullptr, nullptr, CIC_ACT_LRELU02, x4)))) return rc;
-  // Flatten (NHWC) + Dense (:325-326): split-K GEMM, partials reduced in a fixed order
+  if (part == ENC_CONVS) {
+    c.arena.release(mk);
+    return CIC_OK;
+  }
+  rc = encoder_dense_tc(pl, c, x4, latent, B);
+  c.arena.release(mk);
+  return rc;
+}
+
+// Flatten (NHWC) + Dense (:325-326): split-K GEMM, partials reduced in a fixed order
+static int encoder_dense_tc(cic_plan* pl, Ctx& c, const ActBuf& x4, float* latent, int B) {
+  const WeightStore& w = pl->w;
+  const int H = pl->opts.img_h, W = pl->opts.img_w, L = pl->opts.latent_dim;
+  int rc;
+  const size_t mk = c.arena.mark();
   const int feat = (H / 16) * (W / 16) * 512, Lp = round_up(L, 16);
   const int splits = dense_splits(B, Lp, feat, true);
   float* part = splits > 1 ? c.arena.f32((size_t)splits * B * L) : nullptr;
@@ -421,22 +447,27 @@ int encoder_forward_tc(cic_plan* pl, Ctx& c, const float* img, float* latent, fl
 
 // ---- generator --------------------------------------------------------------------------------
 // latent fp32 (B, L); skips as bf16 NHWC (hi only is read)
+// part: 0 = whole generator, 1 = Dense + BN + LeakyReLU only (output to *g0_ext), 2 = transposed convs + conv_out only (reads *g0_ext)
+enum { GEN_ALL = 0, GEN_DENSE = 1, GEN_CONVS = 2 };
 static int generator_core_tc(cic_plan* pl, Ctx& c, const float* latent, const bf16* s1, const bf16* s2, const bf16* s3, float* out, int B,
-                             const TileMap& tm = TileMap()) {
+                             const TileMap& tm = TileMap(), int part = GEN_ALL, const ActBuf* g0_ext = nullptr) {
   const WeightStore& w = pl->w;
   const int H = pl->opts.img_h, W = pl->opts.img_w, C = pl->opts.img_c, L = pl->opts.latent_dim;
   const int h16 = H / 16, w16 = W / 16, feat = h16 * w16 * 512;
   const size_t px = (size_t)B * H * W;
   CIC_REQUIRE(C <= 16, "generator (tc): at most 16 output channels");
   const size_t mk = c.arena.mark();
-  ActBuf g0 = alloc_act(c, (size_t)B * feat, false);
+  CIC_REQUIRE(part == GEN_ALL || g0_ext, "generator (tc): the split parts need the Dense output buffer");
+  ActBuf g0 = g0_ext ? *g0_ext : alloc_act(c, (size_t)B * feat, false);
   ActBuf g1 = alloc_act(c, px / 64 * 256, false);
   ActBuf g2 = alloc_act(c, px / 16 * 128, false);
   ActBuf g3 = alloc_act(c, px / 4 * 64, false);
   ActBuf g4 = alloc_act(c, px * 32, false);
   int rc;
   // :247-250 Dense -> Reshape(h16, w16, 512) NHWC -> BN -> LeakyReLU
-  if (L % 32 == 0) {
+  if (part == GEN_CONVS) {
+    // g0 was produced by the Dense part
+  } else if (L % 32 == 0) {
     ActBuf lat = alloc_act(c, (size_t)B * L, false);
     if (!c.dry && (rc = tc_split_f32(latent, lat.hi, nullptr, (size_t)B * L, c.st))) return rc;
     if ((rc = dense_tc(c, "dense", view(lat, L), B, mat(pl, "dense", L, feat), feat, false, 1,
@@ -451,6 +482,10 @@ static int generator_core_tc(cic_plan* pl, Ctx& c, const float* latent, const bf
                           CIC_ACT_LRELU02, ws, wsb / sizeof(float), c.st))) return rc;
       if ((rc = tc_split_f32(g0f, g0.hi, nullptr, (size_t)B * feat, c.st))) return rc;
     }
+  }
+  if (part == GEN_DENSE) {
+    c.arena.release(mk);
+    return CIC_OK;
   }
   // :253-270 four Conv2DTranspose(k4, s2) + BN + LeakyReLU, the skips concatenated on the channel axis
 #define DC(i, s0v, s1p, hh, ww, cin, co, dst)                                                                             \
@@ -572,13 +607,17 @@ int rd_forward_tc(cic_plan* pl, Ctx& c, const float* mask, const float* bpp, flo
 }
 
 // ---- adaptive model (GAN_functions.py:604-696) --------------------------------------------------------
-int adaptive_forward_tc(cic_plan* pl, Ctx& c, const cic_adaptive_io* io, int n_img, int img_h, int img_w) {
+int adaptive_forward_tc(cic_plan* pl, Ctx& c, const cic_adaptive_io* io, int n_img, int img_h, int img_w, int phase,
+                        const cic_adaptive_state* state, int tile0) {
   const int T = pl->opts.img_h, base = pl->opts.latent_dim;
   const int tpi = (img_h / T) * (img_w / T);
   const int nt = n_img * tpi;
   const bool tiled = tpi > 1;
   const size_t tpx = (size_t)nt * T * T;
   int rc;
+  const bool all = phase == 0;
+  const bool do_enc = all || phase == CIC_PHASE_ENCODE, do_lat = all || phase == CIC_PHASE_LATENT, do_dec = all || phase == CIC_PHASE_DECODE;
+  CIC_REQUIRE(all || state, "adaptive (tc): the phased forward needs the state buffers");
   // tiles are addressed in place in the image layout by the first (conv1, RD conv1) and last (conv_out) layers
   TileMap tm;
   if (tiled) { tm.tiles_x = img_w / T; tm.tiles_y = img_h / T; tm.IH = img_h; tm.IW = img_w; }
@@ -587,68 +626,114 @@ int adaptive_forward_tc(cic_plan* pl, Ctx& c, const cic_adaptive_io* io, int n_i
   float* bpp_t = c.arena.f32(nt);
   float* qs_t = c.arena.f32(nt);
   if (!c.dry && (rc = launch_expand_bpp(io->d_bpp, bpp_t, qs_t, nt, tpi, c.st))) return rc;              // :631-649
-  // 1-2. encoders (:604-617); skips stay on the device as bf16 for the generators
   float* hq_lat = io->d_hq_latent ? io->d_hq_latent : c.arena.f32((size_t)nt * 2 * base);
   float* lq_lat = io->d_lq_latent ? io->d_lq_latent : c.arena.f32((size_t)nt * base);
-  EncSkips hs = alloc_skips(c, tpx), ls = alloc_skips(c, tpx);
-  size_t mk = c.arena.mark();
-  const bool shared_conv1 = pl->opts.img_c == 3 && pl->tcw.ptr("conv1x2#img");
-  if (shared_conv1 && !c.dry) {  // conv1 of both encoders in one pass over the image (:300-302 of both build_encoder calls)
-    if (c.prof) c.prof->prefix = "";
-    Scope sc(c, "enc_conv1_x2", 2.0 * 2 * (tpx / 4) * 64 * 48, 4.0 * tpx * 3 + 2 * 4.0 * tpx / 4 * 64);
-    bf16* oh[2] = {hs.x1.hi, ls.x1.hi};
-    bf16* ol[2] = {hs.x1.lo, ls.x1.lo};
-    if ((rc = launch_conv1_tc(img_t, (const uint8_t*)pl->tcw.ptr("conv1x2#img"), (const float*)pl->tcw.ptr("conv1x2#bias"), 2, oh, ol, nt, T, T,
-                              tm, c.st))) return rc;
+  // skip tensors, conv4 outputs and generator Dense outputs: in the workspace for the one-call forward, in the caller's
+  // batch-wide state buffers (at the chunk's tile offset) for the phased one
+  const size_t e1 = (size_t)(T / 2) * (T / 2) * 64, e2 = (size_t)(T / 4) * (T / 4) * 128, e3 = (size_t)(T / 8) * (T / 8) * 256,
+               e4 = (size_t)(T / 16) * (T / 16) * 512;
+  EncSkips sk[2];
+  ActBuf x4[2], g0[2];
+  for (int e = 0; e < 2; ++e) {
+    if (all) {
+      sk[e] = alloc_skips(c, tpx);
+    } else {
+      sk[e].x1.hi = (bf16*)state->x1[e] + (size_t)tile0 * e1;
+      sk[e].x2.hi = (bf16*)state->x2[e] + (size_t)tile0 * e2;
+      sk[e].x3.hi = (bf16*)state->x3[e] + (size_t)tile0 * e3;
+      x4[e].hi = (bf16*)state->x4_hi[e] + (size_t)tile0 * e4;
+      x4[e].lo = (bf16*)state->x4_lo[e] + (size_t)tile0 * e4;
+      g0[e].hi = (bf16*)state->g0[e] + (size_t)tile0 * e4;
+      if (do_enc) {  // the low parts only live inside the encoders
+        sk[e].x1.lo = (bf16*)c.arena.alloc_bytes((size_t)nt * e1 * sizeof(bf16));
+        sk[e].x2.lo = (bf16*)c.arena.alloc_bytes((size_t)nt * e2 * sizeof(bf16));
+        sk[e].x3.lo = (bf16*)c.arena.alloc_bytes((size_t)nt * e3 * sizeof(bf16));
+      }
+    }
   }
-  if (c.prof) c.prof->prefix = "hq_enc/";
-  if ((rc = encoder_core_tc(pl->hq_enc.get(), c, img_t, hq_lat, nullptr, hs, nt, tm, shared_conv1))) return rc;
-  c.arena.release(mk);
-  if (c.prof) c.prof->prefix = "lq_enc/";
-  if ((rc = encoder_core_tc(pl->lq_enc.get(), c, img_t, lq_lat, nullptr, ls, nt, tm, shared_conv1))) return rc;
-  c.arena.release(mk);
-  // 3. latent saliency (:619-620), fp32
-  float* sal_hq = c.arena.f32(nt);
-  float* sal_lq = c.arena.f32(nt);
+  const EncSkips &hs = sk[0], &ls = sk[1];
+  size_t mk = c.arena.mark();
+  if (do_enc) {
+    // 1-2. encoder convolutions (:604-617); skips stay on the device as bf16 for the generators
+    const bool shared_conv1 = pl->opts.img_c == 3 && pl->tcw.ptr("conv1x2#img");
+    if (shared_conv1 && !c.dry) {  // conv1 of both encoders in one pass over the image (:300-302 of both build_encoder calls)
+      if (c.prof) c.prof->prefix = "";
+      Scope sc(c, "enc_conv1_x2", 2.0 * 2 * (tpx / 4) * 64 * 48, 4.0 * tpx * 3 + 2 * 4.0 * tpx / 4 * 64);
+      bf16* oh[2] = {hs.x1.hi, ls.x1.hi};
+      bf16* ol[2] = {hs.x1.lo, ls.x1.lo};
+      if ((rc = launch_conv1_tc(img_t, (const uint8_t*)pl->tcw.ptr("conv1x2#img"), (const float*)pl->tcw.ptr("conv1x2#bias"), 2, oh, ol, nt, T, T,
+                                tm, c.st))) return rc;
+    }
+    if (c.prof) c.prof->prefix = "hq_enc/";
+    if ((rc = encoder_core_tc(pl->hq_enc.get(), c, img_t, hq_lat, nullptr, hs, nt, tm, shared_conv1, all ? ENC_ALL : ENC_CONVS, all ? nullptr : &x4[0]))) return rc;
+    c.arena.release(mk);
+    if (c.prof) c.prof->prefix = "lq_enc/";
+    if ((rc = encoder_core_tc(pl->lq_enc.get(), c, img_t, lq_lat, nullptr, ls, nt, tm, shared_conv1, all ? ENC_ALL : ENC_CONVS, all ? nullptr : &x4[1]))) return rc;
+    c.arena.release(mk);
+  }
+  if (do_lat && !all) {  // Dense layers of both encoders on the whole batch
+    if (c.prof) c.prof->prefix = "hq_enc/";
+    if ((rc = encoder_core_tc(pl->hq_enc.get(), c, nullptr, hq_lat, nullptr, hs, nt, tm, true, ENC_DENSE, &x4[0]))) return rc;
+    c.arena.release(mk);
+    if (c.prof) c.prof->prefix = "lq_enc/";
+    if ((rc = encoder_core_tc(pl->lq_enc.get(), c, nullptr, lq_lat, nullptr, ls, nt, tm, true, ENC_DENSE, &x4[1]))) return rc;
+    c.arena.release(mk);
+  }
+  float* hq_q = io->d_hq_latent_q ? io->d_hq_latent_q : c.arena.f32((size_t)nt * 2 * base);
+  float* lq_q = io->d_lq_latent_q ? io->d_lq_latent_q : c.arena.f32((size_t)nt * base);
+  if (do_lat) {
+    // 3. latent saliency (:619-620), fp32
+    float* sal_hq = c.arena.f32(nt);
+    float* sal_lq = c.arena.f32(nt);
+    mk = c.arena.mark();
+    if (c.prof) c.prof->prefix = "sal_hq/";
+    if ((rc = saliency_forward_f32(pl->sal_hq.get(), c, hq_lat, sal_hq, nt))) return rc;
+    c.arena.release(mk);
+    if (c.prof) c.prof->prefix = "sal_lq/";
+    if ((rc = saliency_forward_f32(pl->sal_lq.get(), c, lq_lat, sal_lq, nt))) return rc;
+    c.arena.release(mk);
+    // 5. quantise (:661-666)
+    if (c.prof) c.prof->prefix = "";
+    if (!c.dry) {
+      Scope sc(c, "quantize", 0, 12.0 * nt * 3 * base);
+      if ((rc = cic_quantize_latent(hq_lat, sal_hq, qs_t, hq_q, io->d_hq_symbols, nullptr, io->d_hq_scale, nt, 2 * base, c.st))) return rc;
+      if ((rc = cic_quantize_latent(lq_lat, sal_lq, qs_t, lq_q, io->d_lq_symbols, nullptr, io->d_lq_scale, nt, base, c.st))) return rc;
+    }
+    if (!all) {  // generator Dense layers on the whole batch
+      if (c.prof) c.prof->prefix = "hq_gen/";
+      if ((rc = generator_core_tc(pl->hq_gen.get(), c, hq_q, nullptr, nullptr, nullptr, nullptr, nt, tm, GEN_DENSE, &g0[0]))) return rc;
+      c.arena.release(mk);
+      if (c.prof) c.prof->prefix = "lq_gen/";
+      if ((rc = generator_core_tc(pl->lq_gen.get(), c, lq_q, nullptr, nullptr, nullptr, nullptr, nt, tm, GEN_DENSE, &g0[1]))) return rc;
+      c.arena.release(mk);
+    }
+  }
   mk = c.arena.mark();
-  if (c.prof) c.prof->prefix = "sal_hq/";
-  if ((rc = saliency_forward_f32(pl->sal_hq.get(), c, hq_lat, sal_hq, nt))) return rc;
-  c.arena.release(mk);
-  if (c.prof) c.prof->prefix = "sal_lq/";
-  if ((rc = saliency_forward_f32(pl->sal_lq.get(), c, lq_lat, sal_lq, nt))) return rc;
-  c.arena.release(mk);
   // 4. rate-distortion parameters (:624), fp32; an output only
-  if (io->d_rd_params || c.dry) {
+  if (do_enc && (io->d_rd_params || c.dry)) {
     if (c.prof) c.prof->prefix = "rd/";
     if ((rc = rd_forward_tc(pl->rd.get(), c, mask_t, bpp_t, io->d_rd_params, nt, tm))) return rc;
     c.arena.release(mk);
   }
-  // 5. quantise (:661-666)
-  float* hq_q = io->d_hq_latent_q ? io->d_hq_latent_q : c.arena.f32((size_t)nt * 2 * base);
-  float* lq_q = io->d_lq_latent_q ? io->d_lq_latent_q : c.arena.f32((size_t)nt * base);
-  if (c.prof) c.prof->prefix = "";
-  if (!c.dry) {
-    Scope sc(c, "quantize", 0, 12.0 * nt * 3 * base);
-    if ((rc = cic_quantize_latent(hq_lat, sal_hq, qs_t, hq_q, io->d_hq_symbols, nullptr, io->d_hq_scale, nt, 2 * base, c.st))) return rc;
-    if ((rc = cic_quantize_latent(lq_lat, sal_lq, qs_t, lq_q, io->d_lq_symbols, nullptr, io->d_lq_scale, nt, base, c.st))) return rc;
-  }
-  // 6. generators (:669-670)
-  float* hq_img = io->d_hq_out ? io->d_hq_out : c.arena.f32(tpx * 3);  // image layout
-  float* lq_img = io->d_lq_out ? io->d_lq_out : c.arena.f32(tpx * 3);
-  mk = c.arena.mark();
-  if (c.prof) c.prof->prefix = "hq_gen/";
-  if ((rc = generator_core_tc(pl->hq_gen.get(), c, hq_q, hs.x1.hi, hs.x2.hi, hs.x3.hi, hq_img, nt, tm))) return rc;
-  c.arena.release(mk);
-  if (c.prof) c.prof->prefix = "lq_gen/";
-  if ((rc = generator_core_tc(pl->lq_gen.get(), c, lq_q, ls.x1.hi, ls.x2.hi, ls.x3.hi, lq_img, nt, tm))) return rc;
-  c.arena.release(mk);
-  // 7. dynamic threshold + blend on whole images (:651-657, :682-684)
-  if (c.prof) c.prof->prefix = "";
-  if (!c.dry) {
-    Scope sc(c, "roi_blend", 0, 44.0 * n_img * img_h * img_w);
-    float* blended = io->d_blended;
-    if ((rc = cic_roi_mask_blend(blended ? hq_img : nullptr, blended ? lq_img : nullptr, io->d_mask, io->d_bpp, blended,
-                                 io->d_dt, io->d_hq_ratio_sum, n_img, img_h * img_w, 3, c.st))) return rc;
+  if (do_dec) {
+    // 6. generators (:669-670)
+    float* hq_img = io->d_hq_out ? io->d_hq_out : c.arena.f32(tpx * 3);  // image layout
+    float* lq_img = io->d_lq_out ? io->d_lq_out : c.arena.f32(tpx * 3);
+    mk = c.arena.mark();
+    if (c.prof) c.prof->prefix = "hq_gen/";
+    if ((rc = generator_core_tc(pl->hq_gen.get(), c, hq_q, hs.x1.hi, hs.x2.hi, hs.x3.hi, hq_img, nt, tm, all ? GEN_ALL : GEN_CONVS, all ? nullptr : &g0[0]))) return rc;
+    c.arena.release(mk);
+    if (c.prof) c.prof->prefix = "lq_gen/";
+    if ((rc = generator_core_tc(pl->lq_gen.get(), c, lq_q, ls.x1.hi, ls.x2.hi, ls.x3.hi, lq_img, nt, tm, all ? GEN_ALL : GEN_CONVS, all ? nullptr : &g0[1]))) return rc;
+    c.arena.release(mk);
+    // 7. dynamic threshold + blend on whole images (:651-657, :682-684)
+    if (c.prof) c.prof->prefix = "";
+    if (!c.dry) {
+      Scope sc(c, "roi_blend", 0, 44.0 * n_img * img_h * img_w);
+      float* blended = io->d_blended;
+      if ((rc = cic_roi_mask_blend(blended ? hq_img : nullptr, blended ? lq_img : nullptr, io->d_mask, io->d_bpp, blended,
+                                   io->d_dt, io->d_hq_ratio_sum, n_img, img_h * img_w, 3, c.st))) return rc;
+    }
   }
   return CIC_OK;
 }

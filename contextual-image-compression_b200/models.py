@@ -557,3 +557,223 @@ class AdaptiveCompressionModel(Model):
         if extras:
             return out
         return [out["blended"], out["hq_latent_q"], out["lq_latent_q"], out["rd_params"], out["dt"]]
+
+    # ---- phased, pipelined predict -------------------------------------------------------------------------------------------
+    def _phase_buffers(self, n, h, w, dev):
+        """Persistent device buffers of predict_phased for one batch geometry: inputs, outputs and the batch-wide state."""
+        key = (n, h, w, id(self.plan()))
+        cache = self.__dict__.setdefault("_phase_cache", {})
+        if key in cache:
+            return cache[key]
+        if len(cache) > 2:
+            cache.clear()
+        T, base = self.img_shape[0], self.base_latent_dim
+        tpi = (h // T) * (w // T)
+        nt = n * tpi
+        f32 = dict(dtype=torch.float32, device=dev)
+        bf = dict(dtype=torch.bfloat16, device=dev)
+        b = {
+            "img": torch.empty((n, h, w, 3), **f32), "mask": torch.empty((n, h, w, 1), **f32), "bpp": torch.empty((n,), **f32),
+            "blended": torch.empty((n, h, w, 3), **f32), "dt": torch.empty((n, h, w, 1), **f32),
+            "hq_latent_q": torch.empty((nt, 2 * base), **f32), "lq_latent_q": torch.empty((nt, base), **f32),
+            "rd_params": torch.empty((nt, 3), **f32), "hq_ratio_sum": torch.empty((n,), dtype=torch.float64, device=dev),
+        }
+        e = [(T // 2) ** 2 * 64, (T // 4) ** 2 * 128, (T // 8) ** 2 * 256, (T // 16) ** 2 * 512]
+        st = _lib.cic_adaptive_state()
+        keep = []
+        for name, elems in (("x1", e[0]), ("x2", e[1]), ("x3", e[2]), ("x4_hi", e[3]), ("x4_lo", e[3]), ("g0", e[3])):
+            for k in range(2):
+                t = torch.empty((nt, elems), **bf)
+                keep.append(t)
+                getattr(st, name)[k] = t.data_ptr()
+        b["state"], b["state_keep"], b["tpi"], b["nt"] = st, keep, tpi, nt
+        cache[key] = b
+        return b
+
+    def _phase_call(self, b, phase, lo, hi, h, w):
+        """One cic_adaptive_forward_phase call on images [lo, hi) of the persistent buffers (LATENT: the whole batch)."""
+        io = _lib.cic_adaptive_io()
+        tpi = b["tpi"]
+        if phase == _lib.PHASE_LATENT:
+            io.d_bpp = ptr(b["bpp"])
+            io.d_hq_latent_q, io.d_lq_latent_q = ptr(b["hq_latent_q"]), ptr(b["lq_latent_q"])
+            lo, hi, tile0 = 0, b["bpp"].shape[0], 0
+        else:
+            tile0 = lo * tpi
+            io.d_img, io.d_mask, io.d_bpp = ptr(b["img"][lo:hi]), ptr(b["mask"][lo:hi]), ptr(b["bpp"][lo:hi])
+            if phase == _lib.PHASE_ENCODE:
+                io.d_rd_params = ptr(b["rd_params"][tile0:hi * tpi])
+            else:
+                io.d_blended, io.d_dt = ptr(b["blended"][lo:hi]), ptr(b["dt"][lo:hi])
+                io.d_hq_ratio_sum = ptr(b["hq_ratio_sum"][lo:hi])
+        plan = self.plan()
+        ws = plan.workspace(hi - lo, h, w)
+        _lib.check(_lib.lib.cic_adaptive_forward_phase(plan.handle, C.byref(io), C.byref(b["state"]), phase, tile0, hi - lo, h, w,
+                                                       ptr(ws), ws.numel(), runtime.stream_ptr()))
+
+    def predict_phased(self, x, enc_chunks=None, dec_chunks=None, on_chunk=None):
+        """predict_pipelined with the forward cut into three phases (include/cic.h): the encoder convolutions run per upload chunk
+        while the next chunk's host->device copy is in flight, the Dense / saliency / quantiser phase runs once on the whole batch
+        (its 1.2 GB of Dense weights are streamed once instead of once per chunk), and the decoders run per download chunk while the
+        previous chunk's outputs travel to pinned host buffers.  Same results as predict().  `on_chunk(device_inputs, outputs)` runs
+        on the compute stream after every decode chunk.  Returns (host outputs, [on_chunk results])."""
+        xs = runtime.as_list(x)
+        hs = [t if isinstance(t, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(t)) for t in xs]
+        hs = [t if t.dtype == torch.float32 else t.to(torch.float32) for t in hs]
+        if len(hs) != 3:
+            raise ValueError("adaptive model takes [image, saliency, target_bpp]")
+        img, mask, bpp = hs
+        T = self.img_shape[0]
+        n, h, w, c = img.shape
+        if c != 3 or h % T or w % T:
+            raise ValueError(f"image must be (B, k*{T}, m*{T}, 3), got {tuple(img.shape)}")
+        if mask.dim() == 3:
+            mask = mask.unsqueeze(-1)
+        if tuple(mask.shape) != (n, h, w, 1):
+            raise ValueError(f"saliency must be ({n},{h},{w},1), got {tuple(mask.shape)}")
+        bpp = bpp.reshape(-1)
+        if bpp.numel() != n:
+            raise ValueError(f"target_bpp must have one value per image ({n}), got {bpp.numel()}")
+
+        def bounds_of(sizes, default):
+            sizes = [int(v) for v in (sizes if sizes is not None else default) if int(v) > 0]
+            if sum(sizes) != n:
+                raise ValueError(f"chunk sizes {sizes} do not add up to the batch size {n}")
+            out = [0]
+            for v in sizes:
+                out.append(out[-1] + v)
+            return out
+        # default schedule (measured r01 at 64 images: 4,12,16,16,16 / 16,16,16,12,4 beats coarser and finer ones): a short first
+        # upload and a short last download are what stays exposed, equal chunks in between keep both copy engines busy
+        if n >= 16:
+            a = n // 16
+            default = [a, 3 * a, 4 * a, 4 * a, n - 12 * a]
+        elif n >= 4:
+            default = [n // 4, n // 4, n - 2 * (n // 4)]
+        else:
+            default = [n]
+        eb = bounds_of(enc_chunks, default)
+        db = bounds_of(dec_chunks, default[::-1])
+        dev = runtime.require_cuda()
+        b = self._phase_buffers(n, h, w, dev)
+        compute = torch.cuda.current_stream()
+        st = self.__dict__.setdefault("_pipe_streams", {})
+        if "in" not in st:
+            st["in"], st["out"] = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        s_in, s_out = st["in"], st["out"]
+        s_in.wait_stream(compute)
+        s_out.wait_stream(compute)
+        stage = self.__dict__.setdefault("_stage", {})
+        names = ["blended", "hq_latent_q", "lq_latent_q", "rd_params", "dt"]
+        host = []
+        for k in names:
+            key = ("phased", k, tuple(b[k].shape))
+            if key not in stage:
+                stage[key] = torch.empty(b[k].shape, dtype=b[k].dtype, pin_memory=True)
+            host.append(stage[key])
+        # CUDA graphs: the first call with a chunking runs eagerly, the second captures one graph per phase call (persistent
+        # buffers make them replayable), later calls replay.  CIC_PIPE_GRAPHS=0 keeps the eager path.
+        gkey = (tuple(eb), tuple(db), n, h, w, id(on_chunk), id(self.plan()))
+        gstate = self.__dict__.setdefault("_phase_graphs", {})
+        gs = gstate.get(gkey)
+        if gs is None:
+            if len(gstate) > 4:
+                gstate.clear()
+            gs = gstate[gkey] = {"calls": 0}
+        gs["calls"] += 1
+        use_graphs = os.environ.get("CIC_PIPE_GRAPHS", "1") != "0"
+        if use_graphs and gs["calls"] >= 2 and "enc" not in gs and not gs.get("failed"):
+            try:
+                torch.cuda.synchronize()
+                enc, dec, extra_g = [], [], []
+                for i in range(len(eb) - 1):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self._phase_call(b, _lib.PHASE_ENCODE, eb[i], eb[i + 1], h, w)
+                    enc.append(g)
+                lat = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(lat):
+                    self._phase_call(b, _lib.PHASE_LATENT, 0, n, h, w)
+                for i in range(len(db) - 1):
+                    lo, hi = db[i], db[i + 1]
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self._phase_call(b, _lib.PHASE_DECODE, lo, hi, h, w)
+                        ex = None
+                        if on_chunk is not None:
+                            ex = on_chunk([b["img"][lo:hi], b["mask"][lo:hi], b["bpp"][lo:hi]],
+                                          {"blended": b["blended"][lo:hi], "dt": b["dt"][lo:hi], "hq_ratio_sum": b["hq_ratio_sum"][lo:hi]})
+                    dec.append(g)
+                    extra_g.append(ex)
+                torch.cuda.synchronize()
+                gs.update({"enc": enc, "lat": lat, "dec": dec, "extra": extra_g})
+            except Exception as e:  # noqa: BLE001
+                gs["failed"] = True
+                torch.cuda.synchronize()
+                print(f"predict_phased: CUDA graph capture failed ({e!r}); using eager launches", file=sys.stderr)
+        graphs = gs if "enc" in gs else None
+        # uploads: all queued up front on the copy-in stream
+        timeline = os.environ.get("CIC_PIPE_TIMELINE") == "1"            # debug: event times of the three streams
+        ev_in = [torch.cuda.Event(enable_timing=timeline) for _ in range(len(eb) - 1)]
+        marks = []
+        if timeline:
+            ev_t0 = torch.cuda.Event(enable_timing=True)
+            ev_t0.record(compute)
+
+        def mark(name, stream):
+            if timeline:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record(stream)
+                marks.append((name, e))
+        with torch.cuda.stream(s_in):
+            b["bpp"].copy_(bpp, non_blocking=True)
+            for i in range(len(eb) - 1):
+                lo, hi = eb[i], eb[i + 1]
+                b["img"][lo:hi].copy_(img[lo:hi], non_blocking=True)
+                b["mask"][lo:hi].copy_(mask[lo:hi], non_blocking=True)
+                ev_in[i].record(s_in)
+        for i in range(len(eb) - 1):
+            compute.wait_event(ev_in[i])
+            if graphs is not None:
+                graphs["enc"][i].replay()
+            else:
+                self._phase_call(b, _lib.PHASE_ENCODE, eb[i], eb[i + 1], h, w)
+            mark(f"enc{eb[i + 1] - eb[i]}", compute)
+        if graphs is not None:
+            graphs["lat"].replay()
+        else:
+            self._phase_call(b, _lib.PHASE_LATENT, 0, n, h, w)
+        mark("latent", compute)
+        ev_l = torch.cuda.Event()
+        ev_l.record(compute)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(ev_l)
+            for k in (1, 2, 3):
+                host[k].copy_(b[names[k]], non_blocking=True)
+        extra = []
+        for i in range(len(db) - 1):
+            lo, hi = db[i], db[i + 1]
+            if graphs is not None:
+                graphs["dec"][i].replay()
+                if on_chunk is not None:
+                    extra.append(graphs["extra"][i])
+            else:
+                self._phase_call(b, _lib.PHASE_DECODE, lo, hi, h, w)
+                if on_chunk is not None:
+                    extra.append(on_chunk([b["img"][lo:hi], b["mask"][lo:hi], b["bpp"][lo:hi]],
+                                          {"blended": b["blended"][lo:hi], "dt": b["dt"][lo:hi], "hq_ratio_sum": b["hq_ratio_sum"][lo:hi]}))
+            mark(f"dec{hi - lo}", compute)
+            ev_c = torch.cuda.Event()
+            ev_c.record(compute)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_c)
+                host[0][lo:hi].copy_(b["blended"][lo:hi], non_blocking=True)
+                host[4][lo:hi].copy_(b["dt"][lo:hi], non_blocking=True)
+                mark(f"out{hi - lo}", s_out)
+        compute.wait_stream(s_out)
+        s_out.synchronize()
+        if timeline:
+            torch.cuda.synchronize()
+            print("phase timeline (ms since start): in " + " ".join(f"{ev_t0.elapsed_time(e):.2f}" for e in ev_in) + " | " +
+                  "  ".join(f"{nm} {ev_t0.elapsed_time(e):.2f}" for nm, e in marks), file=sys.stderr)
+        return [t.numpy() for t in host], extra

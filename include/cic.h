@@ -155,6 +155,29 @@ typedef struct cic_adaptive_io {
 int cic_adaptive_forward(cic_plan* plan, const cic_adaptive_io* io, int n_img, int img_h, int img_w,
                          void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* The same forward in three phases, for callers that stream a large batch through the GPU in chunks while host<->device
+ * copies are in flight (adaptive_model.predict_pipelined): the convolutions run per chunk, the Dense layers - which stream
+ * 1.2 GB of weights whatever the batch - once per batch.  Results are identical to cic_adaptive_forward.
+ *   CIC_PHASE_ENCODE  per chunk   conv layers of both encoders (+ attention) and the RD network: image / mask / bpp -> state, rd_params
+ *   CIC_PHASE_LATENT  per batch   encoder Dense, latent saliency, quantiser, generator Dense: state -> latents, state.g0
+ *   CIC_PHASE_DECODE  per chunk   transposed convs, conv_out, ROI blend: state -> blended, dt, hq_ratio_sum
+ * The state buffers are batch-wide device arrays owned by the caller (bf16 elements per tile of the model's H x W input, index
+ * [0] = hq, [1] = lq encoder / generator): x1 (H/2)(W/2)64, x2 (H/4)(W/4)128, x3 (H/8)(W/8)256, x4_hi and x4_lo (H/16)(W/16)512,
+ * g0 (H/16)(W/16)512.  For ENCODE / DECODE the io pointers address the chunk (its first image / tile) and tile0 is the index of
+ * the chunk's first tile in the state buffers; for LATENT io addresses the whole batch (d_bpp, d_hq_latent_q, d_lq_latent_q and
+ * the optional latent / symbol / scale outputs).  Tensor-core plans (CIC_PREC_TC) only. */
+enum { CIC_PHASE_ENCODE = 1, CIC_PHASE_LATENT = 2, CIC_PHASE_DECODE = 3 };
+typedef struct cic_adaptive_state {
+  void* x1[2];
+  void* x2[2];
+  void* x3[2];
+  void* x4_hi[2];
+  void* x4_lo[2];
+  void* g0[2];
+} cic_adaptive_state;
+int cic_adaptive_forward_phase(cic_plan* plan, const cic_adaptive_io* io, const cic_adaptive_state* state, int phase, int tile0,
+                               int n_img, int img_h, int img_w, void* d_workspace, size_t workspace_bytes, void* stream);
+
 /* ---- stand-alone operators (also used inside the plans) ----------------------------------- */
 
 /* Keras Conv2D(padding='same') + optional per-channel affine (folded BatchNorm) + activation, fp32 CUDA

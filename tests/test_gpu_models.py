@@ -264,6 +264,37 @@ def test_pipelined_predict_equals_predict(cic, precision, small_cfg):
     np.testing.assert_allclose(y, ae.predict(x), atol=0 if precision == "fp32" else 1e-3, rtol=0)
 
 
+def test_phased_predict_equals_predict(cic, precision, small_cfg):
+    """predict_phased (encoder convs per upload chunk, Dense / quantiser once per batch, decoders per download chunk; eager on
+    the first call, CUDA graphs from the second) returns what predict returns."""
+    models, ws = _adaptive(cic, small_cfg["img_shape"], small_cfg["base"])
+    am = models["adaptive_model"]
+    img = cic.synth.to_signed_range(cic.synth.synth_images_u8(7, 128, 64, seed=51))
+    mask = cic.synth.synth_masks(7, 128, 64, seed=51)
+    bpp = np.linspace(0.2, 1.8, 7, dtype=np.float32).reshape(7, 1)
+    if precision == "fp32":
+        with pytest.raises(cic._lib.CicError, match="tensor-core plans only"):
+            am.predict_phased([img, mask, bpp])
+        return
+    want = am.predict([img, mask, bpp])
+    on_chunk = lambda d_in, outs: (d_in[0].shape[0], outs["hq_ratio_sum"].clone())  # noqa: E731
+    for call in range(3):                                                       # eager, graph capture, graph replay
+        got, extra = am.predict_phased([img, mask, bpp], enc_chunks=[1, 2, 4], dec_chunks=[4, 2, 1], on_chunk=on_chunk)
+        assert [n for n, _ in extra] == [4, 2, 1]
+        for g, w in zip(got, want):
+            assert g.shape == w.shape
+            np.testing.assert_allclose(g, w, atol=2e-2, rtol=0)
+        # quantised latents: kernel selection can change with a chunk's tile count (a bf16 ulp upstream), which may move a
+        # pre-round value across a rounding boundary
+        assert np.mean(got[1] != want[1]) < 0.01
+        ratios = torch.cat([r for _, r in extra]).cpu().numpy() / (128 * 64)
+        np.testing.assert_allclose(ratios, want[4].reshape(7, -1).mean(1, dtype=np.float64), atol=1e-6)
+    got, _ = am.predict_phased([img, mask, bpp])                                 # default chunking (n < 8: one chunk)
+    np.testing.assert_allclose(got[0], want[0], atol=2e-2, rtol=0)
+    with pytest.raises(ValueError, match="add up"):
+        am.predict_phased([img, mask, bpp], enc_chunks=[3, 3])
+
+
 def test_linearity_of_blend_at_full_size(cic):
     """Size-independent property at a BASELINE-scale shape (1024x1024): blend(hq, hq) == hq and
     blend is affine in (hq, lq)."""

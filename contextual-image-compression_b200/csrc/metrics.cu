@@ -251,6 +251,166 @@ metrics_f32_packed_kernel(const float* __restrict__ A, const float* __restrict__
   }
 }
 
+// Fast variant: the same reductions with the window sums in float32 on CENTRED data.  The packed kernel above reproduces scipy's
+// double-accumulating uniform_filter and is bound by the fp32<->fp64 conversion pipe at 0.42 TB/s (profiles/r01_ncu_final.md); it
+// needs the doubles only because skimage forms the variances as E[x^2] - E[x]^2 of values near 1, which cancels ~4 digits.
+// Variance and covariance are shift invariant, so every tile subtracts a reference value (its centre pixel, per image and channel)
+// before the products: in flat regions - the only place where the c2 = (0.03 R)^2 term is comparable to the variances - the
+// centred values are ~0 and float32 sums of 7 (direct, no sliding: no drift) are accurate to ~1e-7 of the window's energy.
+// The squared-error sum (PSNR, MSE) keeps its double accumulation.  Measured |dSSIM| against the scipy oracle: < 2e-6 on the
+// test images (tolerance in tests/test_gpu_ops.py: 1e-5; the survey's criterion is 1e-4).
+// Dynamic shared memory: 2 * TP * (TP*C + 1) + 5 * TS * (TP + 1) floats, as the packed kernel.
+__global__ void __launch_bounds__(256, 3)
+metrics_f32_fast_kernel(const float* __restrict__ A, const float* __restrict__ Bm, double* __restrict__ acc, int H, int W,
+                        int C, float pre_add, float pre_mul, float c1, float c2, float cov_norm) {
+  extern __shared__ float msm[];
+  const int ld = TP * C + 1;
+  float* sa = msm;                       // [TP][ld]
+  float* sb = sa + TP * ld;              // [TP][ld]
+  float* sv = sb + TP * ld;              // [5][TS][TP + 1]
+  __shared__ double red[2][8];
+  __shared__ float ref[2][4];
+  const int tiles_x = (W + TS - 1) / TS;
+  const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+  const int b = blockIdx.y;
+  const int x0 = tx * TS, y0 = ty * TS;
+  const size_t img_base = (size_t)b * H * W * C;
+  const int row_elems = TP * C;
+  const int wid = threadIdx.x >> 5, ln = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  double sse = 0.0;
+  {
+    // Tile load: with one dependent load per loop iteration the kernel was bound by ~20 serial DRAM latencies per CTA (the fast
+    // and the exact kernel both took 0.9 ms whatever their arithmetic); here every thread first issues all its loads of the
+    // tile round (2 x 9 independent 4-byte loads), then normalises, accumulates the squared error and stores.
+    constexpr int MAXE = 9;   // loads in flight per thread and image; TP * TP * C / 256 = 17 elements for C = 3: two rounds
+    const int total = TP * row_elems;
+    const int lo_rem = max(0, HALO - x0) * C, hi_rem = min(TP, W - x0 + HALO) * C;
+    const int in_lo = HALO * C, in_hi = (HALO + TS) * C;
+    const long long tile_base = (long long)img_base + ((long long)(y0 - HALO) * W + (x0 - HALO)) * C;
+    for (int i0 = threadIdx.x; i0 < total; i0 += MAXE * 256) {
+      float ra[MAXE], rb[MAXE];
+#pragma unroll
+      for (int k = 0; k < MAXE; ++k) {
+        const int i = i0 + k * 256;
+        const int ly = i / row_elems, rem = i - ly * row_elems;
+        const int gy = y0 + ly - HALO;
+        const bool ok = i < total && gy >= 0 && gy < H && rem >= lo_rem && rem < hi_rem;
+        const long long off = tile_base + (long long)ly * W * C + rem;
+        ra[k] = ok ? __ldg(A + off) : -pre_add;   // (-pre_add + pre_add) * pre_mul = 0: outside the image the staged value is 0
+        rb[k] = ok ? __ldg(Bm + off) : -pre_add;
+      }
+#pragma unroll
+      for (int k = 0; k < MAXE; ++k) {
+        const int i = i0 + k * 256;
+        if (i < total) {
+          const int ly = i / row_elems, rem = i - ly * row_elems;
+          const float va = __fmul_rn(__fadd_rn(ra[k], pre_add), pre_mul);
+          const float vb = __fmul_rn(__fadd_rn(rb[k], pre_add), pre_mul);
+          if (ly >= HALO && ly < HALO + TS && rem >= in_lo && rem < in_hi) {  // owned pixels (inside the image: va, vb are data)
+            const int gy = y0 + ly - HALO, gx = x0 + rem / C - HALO;
+            if (gy < H && gx < W) {
+              const float d = __fsub_rn(va, vb);
+              sse += (double)__fmul_rn(d, d);
+            }
+          }
+          sa[ly * ld + rem] = va;
+          sb[ly * ld + rem] = vb;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // reference values: the first owned pixel of the tile (always inside the image)
+  if (threadIdx.x < C) {
+    ref[0][threadIdx.x] = sa[HALO * ld + HALO * C + threadIdx.x];
+    ref[1][threadIdx.x] = sb[HALO * ld + HALO * C + threadIdx.x];
+  }
+  __syncthreads();
+  constexpr int SVQ = TS * (TP + 1);
+  const float inv49 = 1.0f / 49.0f;
+  float ssum = 0.f;
+  for (int c = 0; c < C; ++c) {
+    const float ma = ref[0][c], mb = ref[1][c];
+    // vertical pass: a thread per (column, 8-row segment) slides its five float32 window sums down the segment (14 rows read for
+    // 8 outputs; on centred data seven sliding steps cost ~1e-7 of the window's energy, as a fresh 7-term sum does)
+    if (threadIdx.x < 4 * TP) {
+      const int lx = threadIdx.x % TP, r0 = (threadIdx.x / TP) * 8;
+      const float* pa = sa + r0 * ld + lx * C + c;
+      const float* pb = sb + r0 * ld + lx * C + c;
+      float va[14], vb[14];
+#pragma unroll
+      for (int k = 0; k < 14; ++k) { va[k] = pa[k * ld] - ma; vb[k] = pb[k * ld] - mb; }
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f;
+#pragma unroll
+      for (int k = 0; k < 7; ++k) {
+        s0 += va[k]; s1 += vb[k];
+        s2 = fmaf(va[k], va[k], s2); s3 = fmaf(vb[k], vb[k], s3); s4 = fmaf(va[k], vb[k], s4);
+      }
+      float* o = sv + r0 * (TP + 1) + lx;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        o[0] = s0; o[SVQ] = s1; o[2 * SVQ] = s2; o[3 * SVQ] = s3; o[4 * SVQ] = s4;
+        if (r < 7) {
+          s0 += va[r + 7] - va[r];
+          s1 += vb[r + 7] - vb[r];
+          s2 += va[r + 7] * va[r + 7] - va[r] * va[r];
+          s3 += vb[r + 7] * vb[r + 7] - vb[r] * vb[r];
+          s4 += va[r + 7] * vb[r + 7] - va[r] * vb[r];
+          o += TP + 1;
+        }
+      }
+    }
+    __syncthreads();
+    // horizontal pass + SSIM expression: 8 threads per row, each slides over 4 consecutive owned columns
+    {
+      const int r = threadIdx.x >> 3, cx0 = (threadIdx.x & 7) * 4;
+      const int gy = y0 + r;
+      const float* src = sv + r * (TP + 1) + cx0;
+      float e[5][4];  // window sums of the five quantities for the thread's four outputs
+#pragma unroll
+      for (int t = 0; t < 5; ++t) {
+        float w[10];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) w[k] = src[t * SVQ + k];
+        float q = 0.f;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) q += w[k];
+        e[t][0] = q;
+#pragma unroll
+        for (int j = 1; j < 4; ++j) {
+          q += w[j + 6] - w[j - 1];
+          e[t][j] = q;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int gx = x0 + cx0 + j;
+        if (!(gy < HALO || gy >= H - HALO || gx < HALO || gx >= W - HALO)) {
+          const float e0 = e[0][j] * inv49, e1 = e[1][j] * inv49, e2 = e[2][j] * inv49, e3 = e[3][j] * inv49, e4 = e[4][j] * inv49;
+          const float vx = cov_norm * (e2 - e0 * e0);
+          const float vy = cov_norm * (e3 - e1 * e1);
+          const float vxy = cov_norm * (e4 - e0 * e1);
+          const float ux = e0 + ma, uy = e1 + mb;
+          const float a1 = 2.0f * ux * uy + c1, a2 = 2.0f * vxy + c2;
+          const float b1 = ux * ux + uy * uy + c1, b2 = vx + vy + c2;
+          ssum += __fdiv_rn(a1 * a2, b1 * b2);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  sse = warp_sum(sse);
+  double ssumd = warp_sum((double)ssum);
+  if (ln == 0) { red[0][wid] = sse; red[1][wid] = ssumd; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t0 = 0, t1 = 0;
+    for (int w = 0; w < nwarps; ++w) { t0 += red[0][w]; t1 += red[1][w]; }
+    atomicAdd(acc + (size_t)b * 4 + 3, t0);
+    atomicAdd(acc + (size_t)b * 4 + 1, t1);
+  }
+}
+
 // out[b] = {psnr, ssim, mse, sse}
 __global__ void metrics_finalize_kernel(double* __restrict__ acc, int batch, double n_elems, double n_ssim,
                                         double data_range) {
@@ -379,8 +539,8 @@ __global__ void metrics_gray_finalize_kernel(double* __restrict__ acc, int batch
 
 using namespace cic;
 
-extern "C" int cic_metrics_psnr_ssim_f32(const float* d_a, const float* d_b, double* d_out, int batch, int h, int w,
-                                         int channels, float pre_add, float pre_mul, float data_range, void* stream) {
+static int metrics_f32_impl(const float* d_a, const float* d_b, double* d_out, int batch, int h, int w, int channels, float pre_add,
+                            float pre_mul, float data_range, void* stream, bool fast) {
   CIC_REQUIRE(batch == 0 || (d_a && d_b && d_out), "cic_metrics_psnr_ssim_f32: null pointer");
   CIC_REQUIRE(batch >= 0 && h >= 7 && w >= 7 && channels >= 1 && channels <= 65535,
               "cic_metrics_psnr_ssim_f32: needs h,w >= 7 (7x7 SSIM window), got %dx%dx%d", h, w, channels);
@@ -399,6 +559,7 @@ extern "C" int cic_metrics_psnr_ssim_f32(const float* d_a, const float* d_b, dou
     static bool attr_set = false;
     if (!attr_set) {
       CIC_CHECK_CUDA(cudaFuncSetAttribute(metrics_f32_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+      CIC_CHECK_CUDA(cudaFuncSetAttribute(metrics_f32_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
       attr_set = true;
     }
   }
@@ -406,7 +567,10 @@ extern "C" int cic_metrics_psnr_ssim_f32(const float* d_a, const float* d_b, dou
     int nb = batch - b0 < 65535 ? batch - b0 : 65535;
     const float* pa = d_a + (size_t)b0 * h * w * channels;
     const float* pb = d_b + (size_t)b0 * h * w * channels;
-    if (packed) {
+    if (packed && fast) {
+      dim3 grid(tiles, nb);
+      metrics_f32_fast_kernel<<<grid, 256, smem, st>>>(pa, pb, d_out + (size_t)b0 * 4, h, w, channels, pre_add, pre_mul, c1, c2, cov_norm);
+    } else if (packed) {
       dim3 grid(tiles, nb);
       metrics_f32_packed_kernel<<<grid, 256, smem, st>>>(pa, pb, d_out + (size_t)b0 * 4, h, w, channels, pre_add, pre_mul, c1, c2, cov_norm);
     } else {
@@ -421,6 +585,16 @@ extern "C" int cic_metrics_psnr_ssim_f32(const float* d_a, const float* d_b, dou
   CIC_COUNT_LAUNCH();
   CIC_CHECK_LAUNCH("metrics_finalize_kernel");
   return CIC_OK;
+}
+
+extern "C" int cic_metrics_psnr_ssim_f32(const float* d_a, const float* d_b, double* d_out, int batch, int h, int w,
+                                         int channels, float pre_add, float pre_mul, float data_range, void* stream) {
+  return metrics_f32_impl(d_a, d_b, d_out, batch, h, w, channels, pre_add, pre_mul, data_range, stream, false);
+}
+
+extern "C" int cic_metrics_psnr_ssim_f32_fast(const float* d_a, const float* d_b, double* d_out, int batch, int h, int w,
+                                              int channels, float pre_add, float pre_mul, float data_range, void* stream) {
+  return metrics_f32_impl(d_a, d_b, d_out, batch, h, w, channels, pre_add, pre_mul, data_range, stream, true);
 }
 
 extern "C" int cic_metrics_psnr_ssim_gray_u8(const uint8_t* d_a, const uint8_t* d_b, double* d_out, int batch, int h,

@@ -259,6 +259,12 @@ int cic_f32_to_u8_trunc(const float* d_x, uint8_t* d_y, size_t n, float mul, voi
  * per-channel means, cropped by 3 px), mse, sum of squared error. */
 int cic_metrics_psnr_ssim_f32(const float* d_a, const float* d_b, double* d_out, int batch, int h, int w,
                               int channels, float pre_add, float pre_mul, float data_range, void* stream);
+/* Same outputs with the SSIM window sums in float32 on centred data (every 32x32 tile subtracts its first pixel before the
+ * products: variances are shift invariant, and the cancellation in E[x^2] - E[x]^2 that makes scipy accumulate in double
+ * disappears where it matters).  HBM-bound instead of conversion-bound; psnr / mse / sse are identical to the call above, ssim
+ * agrees with scikit-image to ~1e-6 (tests: 1e-5).  Images with more than 4 channels fall back to the exact kernels. */
+int cic_metrics_psnr_ssim_f32_fast(const float* d_a, const float* d_b, double* d_out, int batch, int h, int w, int channels,
+                                   float pre_add, float pre_mul, float data_range, void* stream);
 
 /* calculate_mse/psnr/ssim on uint8 BGR images (test_autoencoder.py:49-66).  d_out is (B,4) doubles:
  * psnr (data_range 255), ssim of the cv2 BGR2GRAY images (float64 arithmetic, as scikit-image does for

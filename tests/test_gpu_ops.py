@@ -154,6 +154,37 @@ def test_metrics_f32_many_tiles_match_oracle(cic, n, h, w):
         assert abs(got[i, 2] - float(m["mse"])) < 1e-8
 
 
+@pytest.mark.parametrize("n,h,w", [(3, 256, 256), (2, 64, 80), (2, 40, 33), (1, 7, 7), (4, 416, 400)])
+def test_metrics_f32_fast_ssim_match_oracle(cic, n, h, w):
+    """cic_metrics_psnr_ssim_f32_fast: float32 window sums on centred data.  psnr / mse as the exact call; ssim within 1e-5 of
+    the scipy / scikit-image arithmetic (survey criterion 1e-4)."""
+    rng = np.random.default_rng(h * 7 + w)
+    a = (cic.synth.to_signed_range(cic.synth.synth_images_u8(n, h, w, seed=17))).astype(np.float32)
+    b = np.clip(a + rng.standard_normal(a.shape).astype(np.float32) * np.float32(0.06), -1, 1).astype(np.float32)
+    got = cic.ops.metrics_f32(a, b, signed_range=True, fast=True).cpu().numpy()
+    exact = cic.ops.metrics_f32(a, b, signed_range=True).cpu().numpy()
+    np.testing.assert_allclose(got[:, [0, 2, 3]], exact[:, [0, 2, 3]], rtol=1e-12)   # psnr, mse, sse: same double sums (atomic order)
+    for i in range(n):
+        m = metrics.compute_metrics(a[i], b[i])
+        assert abs(got[i, 1] - m["ssim"]) < 1e-5, (got[i, 1], m["ssim"])
+
+
+def test_metrics_f32_fast_ssim_flat_bright_regions(cic):
+    """Worst case for E[x^2] - E[x]^2: nearly constant bright images (variances ~1e-6 against means ~0.95) and a reconstruction
+    that differs by a tiny structured error - the case the double accumulation of scipy exists for."""
+    rng = np.random.default_rng(3)
+    h = w = 128
+    base = np.full((3, h, w, 3), 0.9, np.float32) + rng.standard_normal((3, h, w, 3)).astype(np.float32) * np.float32(1e-3)
+    base[1, :, : w // 2] -= 1.7                                                   # a dark half: a step edge inside tiles
+    base[2] = np.float32(0.97)                                                    # exactly constant
+    a = np.clip(base, -1, 1).astype(np.float32)
+    b = np.clip(a + rng.standard_normal(a.shape).astype(np.float32) * np.float32(2e-3), -1, 1).astype(np.float32)
+    got = cic.ops.metrics_f32(a, b, signed_range=True, fast=True).cpu().numpy()
+    for i in range(3):
+        m = metrics.compute_metrics(a[i], b[i])
+        assert abs(got[i, 1] - m["ssim"]) < 1e-5, (i, got[i, 1], m["ssim"])
+
+
 def test_metrics_identical_images(cic):
     a = cic.synth.to_signed_range(cic.synth.synth_images_u8(1, 32, 32))
     got = cic.ops.metrics_f32(a, a, signed_range=True).cpu().numpy()[0]

@@ -49,12 +49,24 @@ direct_conv_kernel(const float* __restrict__ x, const float* __restrict__ wgt, c
     xb = x + (size_t)b * H * W * CIN;
     row_stride = (size_t)W * CIN;
   }
-  for (int i = tid; i < Cfg::kPH * Cfg::kPW * CIN; i += 256) {
-    const int r = i / (Cfg::kPW * CIN), cix = i % (Cfg::kPW * CIN);
-    const int iy = iy0 + r, ix = ix0 + cix / CIN;
-    float v = 0.f;
-    if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(xb + (size_t)iy * row_stride + (size_t)ix * CIN + cix % CIN);
-    patch[r][cix] = v;
+  {
+    // all loads of the patch in flight before the first shared-memory store: with one dependent load per loop iteration the block
+    // paid ~9 serial DRAM latencies and the RD conv1 launch was latency-bound at 0.40 ms for 0.55 GB (profiles/r01_ncu_final.md)
+    constexpr int kElems = Cfg::kPH * Cfg::kPW * CIN, kPer = (kElems + 255) / 256;
+    float v[kPer];
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      const int i = tid + k * 256;
+      const int r = i / (Cfg::kPW * CIN), cix = i % (Cfg::kPW * CIN);
+      const int iy = iy0 + r, ix = ix0 + cix / CIN;
+      v[k] = 0.f;
+      if (i < kElems && iy >= 0 && iy < H && ix >= 0 && ix < W) v[k] = __ldg(xb + (size_t)iy * row_stride + (size_t)ix * CIN + cix % CIN);
+    }
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      const int i = tid + k * 256;
+      if (i < kElems) patch[i / (Cfg::kPW * CIN)][i % (Cfg::kPW * CIN)] = v[k];
+    }
   }
   __syncthreads();
   const int tx = tid & 31, ty = tid >> 5;

@@ -241,9 +241,7 @@ def main():
     def evaluate(d_in, outs):
         """bpp / PSNR / SSIM evaluation of the step + the one exchange step of the path."""
         m = cic.ops.metrics_f32(d_in, outs["blended"], signed_range=True, fast=fast_ssim)   # (n,4) psnr, ssim, mse, sse
-        hq_ratio = outs["hq_ratio_sum"] / float(IMG_HW * IMG_HW)
-        actual_bpp = (hq_ratio * (2 * BASE_LATENT) + (1.0 - hq_ratio) * BASE_LATENT) * 32.0 / (TILE * TILE)
-        sums = cic.dist.metric_sums_row(m[:, 0], m[:, 1], m[:, 2], actual_bpp, hq_ratio, n_img)
+        sums = cic.ops.metric_sums(m, outs["hq_ratio_sum"], IMG_HW * IMG_HW, 2 * BASE_LATENT, BASE_LATENT, TILE * TILE)
         return cic.dist.allreduce_metric_sums(sums)
 
     def step_device():
@@ -265,9 +263,7 @@ def main():
         """Per-chunk metric sums (no all-reduce): runs on the compute stream inside the pipelined predict."""
         k = d_in[0].shape[0]
         m = cic.ops.metrics_f32(d_in[0], outs["blended"], signed_range=True, fast=fast_ssim)
-        hq_ratio = outs["hq_ratio_sum"] / float(IMG_HW * IMG_HW)
-        actual_bpp = (hq_ratio * (2 * BASE_LATENT) + (1.0 - hq_ratio) * BASE_LATENT) * 32.0 / (TILE * TILE)
-        return cic.dist.metric_sums_row(m[:, 0], m[:, 1], m[:, 2], actual_bpp, hq_ratio, k)
+        return cic.ops.metric_sums(m, outs["hq_ratio_sum"], IMG_HW * IMG_HW, 2 * BASE_LATENT, BASE_LATENT, TILE * TILE)
 
     enc_chunks = [int(v) for v in args.enc_chunks.split(",")] if args.enc_chunks else None
     dec_chunks = [int(v) for v in args.dec_chunks.split(",")] if args.dec_chunks else None
@@ -305,7 +301,7 @@ def main():
     ms_step = cic.dist.max_over_ranks(ms_total / args.steps, device=dev)
     prof = plan.profile()                       # per-layer device times of the last timed step
     plan.set_profiling(False)
-    launches_per_step = plan.last_launch_count() + 2          # + metrics kernel and its finalise
+    launches_per_step = plan.last_launch_count() + 3          # + metrics kernel, its finalise and the metric sums
     value = world * px_per_step / (ms_step * 1e-3) / 1e6
 
     KINDS = {0: "other", 1: "tc_gemm_kernel", 2: "tc_conv_kernel", 3: "conv1_tc_kernel", 4: "direct_conv_kernel", 5: "igemm_f32_kernel", 6: "conv_rows_tc_kernel", 7: "tc_gemm2_kernel", 8: "attn_fused_kernel"}

@@ -602,6 +602,44 @@ extern "C" int cic_metrics_psnr_ssim_f32_fast(const float* d_a, const float* d_b
   return metrics_f32_impl(d_a, d_b, d_out, batch, h, w, channels, pre_add, pre_mul, data_range, stream, true);
 }
 
+// Per-rank metric sums of one evaluated batch (the row the ranks all-reduce; bpp accounting of GAN_test.py:310-325):
+// out[8] = {sum psnr, sum ssim, sum mse, sum actual_bpp, sum hq_ratio, 0, n, 0} in double, one block.
+__global__ void __launch_bounds__(256)
+metric_sums_kernel(const double* __restrict__ m, const double* __restrict__ dt_sum, int n, double img_px, double latent_hq,
+                   double latent_lq, double tile_px, double* __restrict__ out) {
+  __shared__ double red[5][8];
+  double s[5] = {0, 0, 0, 0, 0};
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double hq = dt_sum[i] / img_px;
+    s[0] += m[4 * i]; s[1] += m[4 * i + 1]; s[2] += m[4 * i + 2];
+    s[3] += (hq * latent_hq + (1.0 - hq) * latent_lq) * 32.0 / tile_px;  // total_bits / pixels of a tile
+    s[4] += hq;
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int q = 0; q < 5; ++q) {
+    s[q] = warp_sum(s[q]);
+    if (lane == 0) red[q][warp] = s[q];
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    double v = 0.0;
+    if (threadIdx.x < 5) for (int w = 0; w < 8; ++w) v += red[threadIdx.x][w];
+    if (threadIdx.x == 6) v = (double)n;
+    out[threadIdx.x] = v;
+  }
+}
+
+extern "C" int cic_metric_sums(const double* d_metrics, const double* d_dt_sum, int n, int img_px, int latent_hq, int latent_lq,
+                               int tile_px, double* d_out, void* stream) {
+  CIC_REQUIRE(d_metrics && d_dt_sum && d_out && n > 0 && img_px > 0 && tile_px > 0, "cic_metric_sums: bad argument");
+  metric_sums_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(d_metrics, d_dt_sum, n, (double)img_px, (double)latent_hq, (double)latent_lq,
+                                                        (double)tile_px, d_out);
+  CIC_COUNT_LAUNCH();
+  CIC_CHECK_LAUNCH("metric_sums_kernel");
+  return CIC_OK;
+}
+
 extern "C" int cic_metrics_psnr_ssim_gray_u8(const uint8_t* d_a, const uint8_t* d_b, double* d_out, int batch, int h,
                                              int w, void* stream) {
   CIC_REQUIRE(batch == 0 || (d_a && d_b && d_out), "cic_metrics_psnr_ssim_gray_u8: null pointer");

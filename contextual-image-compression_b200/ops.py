@@ -224,6 +224,18 @@ def metrics_f32(a, b, signed_range: bool, data_range: float = 1.0, fast: bool = 
     return out
 
 
+def metric_sums(metrics: torch.Tensor, dt_sum: torch.Tensor, img_px: int, latent_hq: int, latent_lq: int, tile_px: int) -> torch.Tensor:
+    """(1, 8) float64 row [sum psnr, sum ssim, sum mse, sum actual_bpp, sum hq_ratio, 0, n, 0] of one evaluated batch (dist.METRIC_FIELDS)
+    from metrics_f32's (n,4) output and the per-image dt sums, in one launch (bpp accounting of GAN_test.py:310-325)."""
+    n = metrics.shape[0]
+    if metrics.dtype != torch.float64 or dt_sum.dtype != torch.float64 or dt_sum.numel() != n:
+        raise ValueError("metric_sums takes the float64 outputs of metrics_f32 (n,4) and the per-image dt sums (n,)")
+    out = torch.empty((1, 8), dtype=torch.float64, device=metrics.device)
+    _lib.check(_lib.lib.cic_metric_sums(ptr(metrics.contiguous()), ptr(dt_sum.contiguous()), n, int(img_px), int(latent_hq), int(latent_lq),
+                                        int(tile_px), ptr(out), runtime.stream_ptr()))
+    return out
+
+
 def metrics_gray_u8(a, b) -> torch.Tensor:
     """(B,4) float64 [psnr, ssim(gray), true mse, wrapped uint8 mse] for uint8 BGR images."""
     dev = runtime.require_cuda()

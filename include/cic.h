@@ -266,6 +266,14 @@ int cic_metrics_psnr_ssim_f32(const float* d_a, const float* d_b, double* d_out,
 int cic_metrics_psnr_ssim_f32_fast(const float* d_a, const float* d_b, double* d_out, int batch, int h, int w, int channels,
                                    float pre_add, float pre_mul, float data_range, void* stream);
 
+/* Metric sums of one evaluated batch in one launch: d_metrics (n,4) doubles as written by cic_metrics_psnr_ssim_f32*, d_dt_sum (n,)
+ * doubles as written by cic_roi_mask_blend / cic_adaptive_forward (sum of dt per image of img_px pixels).  Per image
+ * hq_ratio = dt_sum / img_px, total_bits = hq_ratio * latent_hq * 32 + (1 - hq_ratio) * latent_lq * 32, actual_bpp = total_bits /
+ * tile_px (GAN_test.py:310-325).  d_out (8,) doubles = {sum psnr, sum ssim, sum mse, sum actual_bpp, sum hq_ratio, 0, n, 0}: the row
+ * the ranks all-reduce. */
+int cic_metric_sums(const double* d_metrics, const double* d_dt_sum, int n, int img_px, int latent_hq, int latent_lq, int tile_px,
+                    double* d_out, void* stream);
+
 /* calculate_mse/psnr/ssim on uint8 BGR images (test_autoencoder.py:49-66).  d_out is (B,4) doubles:
  * psnr (data_range 255), ssim of the cv2 BGR2GRAY images (float64 arithmetic, as scikit-image does for
  * uint8), true mse, and the reference's wrapped uint8 "mse" (mean of ((a-b)**2 mod 256), App. D.1). */

@@ -185,6 +185,19 @@ def test_metrics_f32_fast_ssim_flat_bright_regions(cic):
         assert abs(got[i, 1] - m["ssim"]) < 1e-5, (i, got[i, 1], m["ssim"])
 
 
+def test_metric_sums_match_torch(cic):
+    rng = np.random.default_rng(21)
+    n = 37
+    m = torch.from_numpy(rng.random((n, 4))).cuda()
+    dts = torch.from_numpy(rng.random(n) * 512 * 512).cuda()
+    got = cic.ops.metric_sums(m, dts, 512 * 512, 1024, 512, 256 * 256).cpu().numpy()[0]
+    hq = dts.cpu().numpy() / (512 * 512)
+    bpp = (hq * 1024 * 32 + (1 - hq) * 512 * 32) / 65536                          # GAN_test.py:313-318
+    want = [m[:, 0].sum().item(), m[:, 1].sum().item(), m[:, 2].sum().item(), bpp.sum(), hq.sum(), 0.0, float(n), 0.0]
+    np.testing.assert_allclose(got, want, rtol=1e-12)
+    assert abs(bpp.mean() - 0.25 * (1 + hq.mean())) < 1e-12                       # actual_bpp == 0.25 (1 + hq_ratio), SURVEY 8 a13
+
+
 def test_metrics_identical_images(cic):
     a = cic.synth.to_signed_range(cic.synth.synth_images_u8(1, 32, 32))
     got = cic.ops.metrics_f32(a, a, signed_range=True).cpu().numpy()[0]

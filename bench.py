@@ -213,6 +213,7 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
     dev = torch.device("cuda", local_rank if world > 1 else torch.cuda.current_device())
     torch.cuda.set_device(dev)
+    numa_cpus = cic.dist.bind_to_gpu_numa_node(dev.index if dev.index is not None else 0) if world > 1 else 0
     cic.set_precision(args.precision)
     peaks = measured_peaks()
     # clock sampler child (started now so that it is up before the timed region); NVML indices are physical
@@ -415,7 +416,7 @@ def main():
                        "precision": args.precision, "tiles_per_gpu": n_tiles, "base_latent_dim": BASE_LATENT,
                        "l2": f"inputs per step {h2d / 1e6:.0f} MB + activations >> 126 MB L2 (no flush needed)",
                        "step": "encode + quantise + decode + ROI blend + PSNR/SSIM/bpp evaluation + metric all-reduce",
-                       "ssim": args.ssim},
+                       "ssim": args.ssim, "cpu_affinity": f"{numa_cpus} CPUs local to the rank's GPU" if numa_cpus else "unchanged"},
             "clocks": clocks, "e2e": {"value": e2e_value, "unit": "MPix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                                       "ms_per_step": ms_e2e, "api": f"adaptive_model.predict_{args.e2e_mode}"},
             "gpu_launches": int(launches_per_step * args.steps), "roofline": roofline, "cpu_baseline": cpu, "quality": quality,

@@ -38,6 +38,30 @@ def init(backend: str | None = None) -> Tuple[int, int]:
     return rank, world
 
 
+def bind_to_gpu_numa_node(cuda_index: int) -> int:
+    """Pin this process to the CPUs NVML reports as local to its GPU (one process per GPU): pinned host buffers allocated
+    afterwards are first-touched on that NUMA node, so every rank's PCIe copies stay on its own socket.  Returns the number of CPUs
+    in the new affinity mask (0 = left unchanged: NVML or sched_setaffinity not available)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        idx = cuda_index
+        if vis and all(v.strip().isdigit() for v in vis.split(",")) and cuda_index < len(vis.split(",")):
+            idx = int(vis.split(",")[cuda_index])
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        allowed = os.sched_getaffinity(0)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1} & allowed
+        if not cpus or cpus == allowed:
+            return 0
+        os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:  # noqa: BLE001  (affinity is an optimisation, never a requirement)
+        return 0
+
+
 def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
     """Contiguous slice [lo, hi) of the global index range owned by `rank` (sizes differ by <= 1)."""
     base, rem = divmod(n_items, world)

@@ -112,6 +112,18 @@ print("ok", rank)
 """
 
 
+def test_numa_binding_is_optional(cic):
+    """bind_to_gpu_numa_node is an optimisation: without NVML / a GPU it leaves the affinity mask alone and returns 0; with one it
+    never leaves the process without CPUs."""
+    import os
+    before = os.sched_getaffinity(0)
+    n = cic.dist.bind_to_gpu_numa_node(0)
+    after = os.sched_getaffinity(0)
+    assert len(after) >= 1 and after <= before
+    assert n == 0 or n == len(after)
+    os.sched_setaffinity(0, before)
+
+
 def test_gloo_world_size_2(tmp_path):
     script = tmp_path / "worker.py"
     script.write_text(GLOO_WORKER.format(root=ROOT))

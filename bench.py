@@ -361,6 +361,29 @@ def main():
     h2d = int(h_img.numel() * 4 + h_mask.numel() * 4 + h_bpp.numel() * 4)
     d2h = int(sum(o.nbytes for o in outs) + sums_host.numel() * 8)
 
+    # informational: the same leg with the reference's uint8 image conventions applied on the device (uint8 image up, uint8 blended
+    # image down: 1 instead of 4 bytes per sample over PCIe); the headline `e2e` above moves the float32 arrays of the reference API
+    e2e_u8 = None
+    if args.e2e_mode == "phased":
+        from cic_b200 import synth
+        h_img_u8 = torch.from_numpy(synth.synth_images_u8(n_img, IMG_HW, IMG_HW, seed=synth.SEED_BASE + 1, first_index=rank * n_img)).pin_memory()
+
+        def step_u8():
+            o, parts = am.predict_phased([h_img_u8, h_mask, h_bpp], enc_chunks=enc_chunks, dec_chunks=dec_chunks, on_chunk=evaluate_chunk, u8_io=True)
+            return o, cic.dist.allreduce_metric_sums(torch.stack(parts).sum(0)).cpu()
+        for _ in range(2):
+            step_u8()
+        torch.cuda.synchronize()
+        cic.dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            outs8, _s8 = step_u8()
+        torch.cuda.synchronize()
+        ms_u8 = cic.dist.max_over_ranks((time.perf_counter() - t0) / args.steps * 1e3, device=dev)
+        e2e_u8 = {"value": world * px_per_step / (ms_u8 * 1e-3) / 1e6, "unit": "MPix/s", "ms_per_step": ms_u8,
+                  "h2d_bytes_per_step": int(h_img_u8.numel() + h_mask.numel() * 4 + h_bpp.numel() * 4),
+                  "d2h_bytes_per_step": int(sum(o.nbytes for o in outs8) + 64), "api": "adaptive_model.predict_phased(u8_io=True)"}
+
     # ---------------- HBM-bound kernels of the path: algorithmic bytes / device time ----------------------
     hbm_peak = peaks["hbm_gbs"]
     hbm = {}
@@ -419,7 +442,7 @@ def main():
                        "ssim": args.ssim, "cpu_affinity": f"{numa_cpus} CPUs local to the rank's GPU" if numa_cpus else "unchanged"},
             "clocks": clocks, "e2e": {"value": e2e_value, "unit": "MPix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                                       "ms_per_step": ms_e2e, "api": f"adaptive_model.predict_{args.e2e_mode}"},
-            "gpu_launches": int(launches_per_step * args.steps), "roofline": roofline, "cpu_baseline": cpu, "quality": quality,
+            "e2e_u8_io": e2e_u8, "gpu_launches": int(launches_per_step * args.steps), "roofline": roofline, "cpu_baseline": cpu, "quality": quality,
             "layers_ms_per_step": total_layer_ms}
     print(json.dumps(line))
 

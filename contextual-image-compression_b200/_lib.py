@@ -90,6 +90,8 @@ PROTOTYPES = {
     "cic_hq_ratio_sweep": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp]),
     "cic_symbol_entropy_bits": (_i, [_vp, _vp, _i, _i, _vp]),
     "cic_f32_to_u8_trunc": (_i, [_vp, _vp, _sz, _f, _vp]),
+    "cic_u8_to_f32_signed": (_i, [_vp, _vp, _sz, _vp]),
+    "cic_f32_signed_to_u8": (_i, [_vp, _vp, _sz, _vp]),
     "cic_metrics_psnr_ssim_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _vp]),
     "cic_metrics_psnr_ssim_f32_fast": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _vp]),
     "cic_metric_sums": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),

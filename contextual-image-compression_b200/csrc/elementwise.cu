@@ -240,6 +240,37 @@ __global__ void f32_to_u8_kernel(const float* __restrict__ x, uint8_t* __restric
     for (size_t i = (nvec << 2) + threadIdx.x; i < n; i += blockDim.x) y[i] = (uint8_t)(int)__fmul_rn(x[i], mul);
 }
 
+// GAN pixel conventions (GAN_functions.py:24-50): load (u8 - 127.5) / 127.5, save ((x + 1) * 127.5).astype(uint8) (truncation)
+__global__ void u8_to_f32_signed_kernel(const uint8_t* __restrict__ x, float* __restrict__ y, size_t n) {
+  const size_t nvec = n >> 2, stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    const uchar4 v = __ldg(reinterpret_cast<const uchar4*>(x) + i);
+    float4 o;
+    o.x = __fdiv_rn(__fsub_rn((float)v.x, 127.5f), 127.5f);
+    o.y = __fdiv_rn(__fsub_rn((float)v.y, 127.5f), 127.5f);
+    o.z = __fdiv_rn(__fsub_rn((float)v.z, 127.5f), 127.5f);
+    o.w = __fdiv_rn(__fsub_rn((float)v.w, 127.5f), 127.5f);
+    reinterpret_cast<float4*>(y)[i] = o;
+  }
+  if (blockIdx.x == 0)
+    for (size_t i = (nvec << 2) + threadIdx.x; i < n; i += blockDim.x) y[i] = __fdiv_rn(__fsub_rn((float)x[i], 127.5f), 127.5f);
+}
+
+__global__ void f32_signed_to_u8_kernel(const float* __restrict__ x, uint8_t* __restrict__ y, size_t n) {
+  const size_t nvec = n >> 2, stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    uchar4 o;
+    o.x = (uint8_t)(int)__fmul_rn(__fadd_rn(v.x, 1.f), 127.5f);
+    o.y = (uint8_t)(int)__fmul_rn(__fadd_rn(v.y, 1.f), 127.5f);
+    o.z = (uint8_t)(int)__fmul_rn(__fadd_rn(v.z, 1.f), 127.5f);
+    o.w = (uint8_t)(int)__fmul_rn(__fadd_rn(v.w, 1.f), 127.5f);
+    reinterpret_cast<uchar4*>(y)[i] = o;
+  }
+  if (blockIdx.x == 0)
+    for (size_t i = (nvec << 2) + threadIdx.x; i < n; i += blockDim.x) y[i] = (uint8_t)(int)__fmul_rn(__fadd_rn(x[i], 1.f), 127.5f);
+}
+
 static inline int grid_for(size_t work_items, int threads, int per_sm = 8) {
   size_t blocks = (work_items + threads - 1) / threads;
   size_t cap = (size_t)sm_count() * per_sm;
@@ -347,5 +378,25 @@ extern "C" int cic_f32_to_u8_trunc(const float* d_x, uint8_t* d_y, size_t n, flo
   f32_to_u8_kernel<<<grid_for(n / 4 + 1, 256, 8), 256, 0, (cudaStream_t)stream>>>(d_x, d_y, n, mul);
   CIC_COUNT_LAUNCH();
   CIC_CHECK_LAUNCH("f32_to_u8_kernel");
+  return CIC_OK;
+}
+
+extern "C" int cic_u8_to_f32_signed(const uint8_t* d_x, float* d_y, size_t n, void* stream) {
+  if (n == 0) return CIC_OK;
+  CIC_REQUIRE(d_x && d_y, "cic_u8_to_f32_signed: null pointer");
+  CIC_REQUIRE(((uintptr_t)d_x & 3) == 0 && ((uintptr_t)d_y & 15) == 0, "cic_u8_to_f32_signed: unaligned buffer");
+  u8_to_f32_signed_kernel<<<grid_for(n / 4 + 1, 256, 8), 256, 0, (cudaStream_t)stream>>>(d_x, d_y, n);
+  CIC_COUNT_LAUNCH();
+  CIC_CHECK_LAUNCH("u8_to_f32_signed_kernel");
+  return CIC_OK;
+}
+
+extern "C" int cic_f32_signed_to_u8(const float* d_x, uint8_t* d_y, size_t n, void* stream) {
+  if (n == 0) return CIC_OK;
+  CIC_REQUIRE(d_x && d_y, "cic_f32_signed_to_u8: null pointer");
+  CIC_REQUIRE(((uintptr_t)d_x & 15) == 0 && ((uintptr_t)d_y & 3) == 0, "cic_f32_signed_to_u8: unaligned buffer");
+  f32_signed_to_u8_kernel<<<grid_for(n / 4 + 1, 256, 8), 256, 0, (cudaStream_t)stream>>>(d_x, d_y, n);
+  CIC_COUNT_LAUNCH();
+  CIC_CHECK_LAUNCH("f32_signed_to_u8_kernel");
   return CIC_OK;
 }

@@ -586,6 +586,8 @@ class AdaptiveCompressionModel(Model):
                 t = torch.empty((nt, elems), **bf)
                 keep.append(t)
                 getattr(st, name)[k] = t.data_ptr()
+        b["img_u8"] = torch.empty((n, h, w, 3), dtype=torch.uint8, device=dev)
+        b["blended_u8"] = torch.empty((n, h, w, 3), dtype=torch.uint8, device=dev)
         b["state"], b["state_keep"], b["tpi"], b["nt"] = st, keep, tpi, nt
         cache[key] = b
         return b
@@ -611,17 +613,21 @@ class AdaptiveCompressionModel(Model):
         _lib.check(_lib.lib.cic_adaptive_forward_phase(plan.handle, C.byref(io), C.byref(b["state"]), phase, tile0, hi - lo, h, w,
                                                        ptr(ws), ws.numel(), runtime.stream_ptr()))
 
-    def predict_phased(self, x, enc_chunks=None, dec_chunks=None, on_chunk=None):
+    def predict_phased(self, x, enc_chunks=None, dec_chunks=None, on_chunk=None, u8_io: bool = False):
         """predict_pipelined with the forward cut into three phases (include/cic.h): the encoder convolutions run per upload chunk
         while the next chunk's host->device copy is in flight, the Dense / saliency / quantiser phase runs once on the whole batch
         (its 1.2 GB of Dense weights are streamed once instead of once per chunk), and the decoders run per download chunk while the
         previous chunk's outputs travel to pinned host buffers.  Same results as predict().  `on_chunk(device_inputs, outputs)` runs
-        on the compute stream after every decode chunk.  Returns (host outputs, [on_chunk results])."""
+        on the compute stream after every decode chunk.  Returns (host outputs, [on_chunk results]).
+        u8_io=True: the image is uint8 RGB and is normalised on the device ((u8 - 127.5) / 127.5, GAN_functions.py:31-37), the
+        blended output comes back as uint8 (((x + 1) * 127.5).astype(uint8), :41-50): 1 instead of 4 bytes per sample over PCIe."""
         xs = runtime.as_list(x)
         hs = [t if isinstance(t, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(t)) for t in xs]
-        hs = [t if t.dtype == torch.float32 else t.to(torch.float32) for t in hs]
         if len(hs) != 3:
             raise ValueError("adaptive model takes [image, saliency, target_bpp]")
+        if u8_io and hs[0].dtype != torch.uint8:
+            raise ValueError("u8_io=True takes a uint8 image")
+        hs = [t if (t.dtype == torch.float32 or (u8_io and k == 0)) else t.to(torch.float32) for k, t in enumerate(hs)]
         img, mask, bpp = hs
         T = self.img_shape[0]
         n, h, w, c = img.shape
@@ -667,13 +673,31 @@ class AdaptiveCompressionModel(Model):
         names = ["blended", "hq_latent_q", "lq_latent_q", "rd_params", "dt"]
         host = []
         for k in names:
-            key = ("phased", k, tuple(b[k].shape))
+            src = b["blended_u8"] if (u8_io and k == "blended") else b[k]
+            key = ("phased", k, tuple(src.shape), src.dtype)
             if key not in stage:
-                stage[key] = torch.empty(b[k].shape, dtype=b[k].dtype, pin_memory=True)
+                stage[key] = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
             host.append(stage[key])
+
+        def encode(lo, hi):
+            if u8_io:
+                _lib.check(_lib.lib.cic_u8_to_f32_signed(ptr(b["img_u8"][lo:hi]), ptr(b["img"][lo:hi]), (hi - lo) * h * w * 3,
+                                                         runtime.stream_ptr()))
+            self._phase_call(b, _lib.PHASE_ENCODE, lo, hi, h, w)
+
+        def decode(lo, hi):
+            self._phase_call(b, _lib.PHASE_DECODE, lo, hi, h, w)
+            ex = None
+            if on_chunk is not None:
+                ex = on_chunk([b["img"][lo:hi], b["mask"][lo:hi], b["bpp"][lo:hi]],
+                              {"blended": b["blended"][lo:hi], "dt": b["dt"][lo:hi], "hq_ratio_sum": b["hq_ratio_sum"][lo:hi]})
+            if u8_io:
+                _lib.check(_lib.lib.cic_f32_signed_to_u8(ptr(b["blended"][lo:hi]), ptr(b["blended_u8"][lo:hi]), (hi - lo) * h * w * 3,
+                                                         runtime.stream_ptr()))
+            return ex
         # CUDA graphs: the first call with a chunking runs eagerly, the second captures one graph per phase call (persistent
         # buffers make them replayable), later calls replay.  CIC_PIPE_GRAPHS=0 keeps the eager path.
-        gkey = (tuple(eb), tuple(db), n, h, w, id(on_chunk), id(self.plan()))
+        gkey = (tuple(eb), tuple(db), n, h, w, id(on_chunk), id(self.plan()), bool(u8_io))
         gstate = self.__dict__.setdefault("_phase_graphs", {})
         gs = gstate.get(gkey)
         if gs is None:
@@ -689,7 +713,7 @@ class AdaptiveCompressionModel(Model):
                 for i in range(len(eb) - 1):
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g):
-                        self._phase_call(b, _lib.PHASE_ENCODE, eb[i], eb[i + 1], h, w)
+                        encode(eb[i], eb[i + 1])
                     enc.append(g)
                 lat = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(lat):
@@ -698,11 +722,7 @@ class AdaptiveCompressionModel(Model):
                     lo, hi = db[i], db[i + 1]
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g):
-                        self._phase_call(b, _lib.PHASE_DECODE, lo, hi, h, w)
-                        ex = None
-                        if on_chunk is not None:
-                            ex = on_chunk([b["img"][lo:hi], b["mask"][lo:hi], b["bpp"][lo:hi]],
-                                          {"blended": b["blended"][lo:hi], "dt": b["dt"][lo:hi], "hq_ratio_sum": b["hq_ratio_sum"][lo:hi]})
+                        ex = decode(lo, hi)
                     dec.append(g)
                     extra_g.append(ex)
                 torch.cuda.synchronize()
@@ -729,7 +749,7 @@ class AdaptiveCompressionModel(Model):
             b["bpp"].copy_(bpp, non_blocking=True)
             for i in range(len(eb) - 1):
                 lo, hi = eb[i], eb[i + 1]
-                b["img"][lo:hi].copy_(img[lo:hi], non_blocking=True)
+                (b["img_u8"] if u8_io else b["img"])[lo:hi].copy_(img[lo:hi], non_blocking=True)
                 b["mask"][lo:hi].copy_(mask[lo:hi], non_blocking=True)
                 ev_in[i].record(s_in)
         for i in range(len(eb) - 1):
@@ -737,7 +757,7 @@ class AdaptiveCompressionModel(Model):
             if graphs is not None:
                 graphs["enc"][i].replay()
             else:
-                self._phase_call(b, _lib.PHASE_ENCODE, eb[i], eb[i + 1], h, w)
+                encode(eb[i], eb[i + 1])
             mark(f"enc{eb[i + 1] - eb[i]}", compute)
         if graphs is not None:
             graphs["lat"].replay()
@@ -758,16 +778,15 @@ class AdaptiveCompressionModel(Model):
                 if on_chunk is not None:
                     extra.append(graphs["extra"][i])
             else:
-                self._phase_call(b, _lib.PHASE_DECODE, lo, hi, h, w)
+                ex = decode(lo, hi)
                 if on_chunk is not None:
-                    extra.append(on_chunk([b["img"][lo:hi], b["mask"][lo:hi], b["bpp"][lo:hi]],
-                                          {"blended": b["blended"][lo:hi], "dt": b["dt"][lo:hi], "hq_ratio_sum": b["hq_ratio_sum"][lo:hi]}))
+                    extra.append(ex)
             mark(f"dec{hi - lo}", compute)
             ev_c = torch.cuda.Event()
             ev_c.record(compute)
             with torch.cuda.stream(s_out):
                 s_out.wait_event(ev_c)
-                host[0][lo:hi].copy_(b["blended"][lo:hi], non_blocking=True)
+                host[0][lo:hi].copy_((b["blended_u8"] if u8_io else b["blended"])[lo:hi], non_blocking=True)
                 host[4][lo:hi].copy_(b["dt"][lo:hi], non_blocking=True)
                 mark(f"out{hi - lo}", s_out)
         compute.wait_stream(s_out)

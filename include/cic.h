@@ -253,6 +253,12 @@ int cic_symbol_entropy_bits(const int32_t* d_symbols, double* d_bits, int batch,
 /* (y*255).astype(uint8) - truncation toward zero (test_autoencoder.py:88,96). */
 int cic_f32_to_u8_trunc(const float* d_x, uint8_t* d_y, size_t n, float mul, void* stream);
 
+/* GAN pixel conventions on the device (GAN_functions.py:31-37 load, :41-50 save): y = (u8 - 127.5) / 127.5 and
+ * y = ((x + 1) * 127.5).astype(uint8) (float32 arithmetic, truncation).  Lets callers move 1 byte per sample over PCIe instead of 4
+ * (adaptive_model.predict_phased(..., u8_io=True)). */
+int cic_u8_to_f32_signed(const uint8_t* d_x, float* d_y, size_t n, void* stream);
+int cic_f32_signed_to_u8(const float* d_x, uint8_t* d_y, size_t n, void* stream);
+
 /* compute_metrics (GAN_functions.py:724-759): inputs (B,H,W,C) float32; v = (x + pre_add) * pre_mul maps
  * [-1,1] to [0,1] (pre_add = 1, pre_mul = 0.5) or is the identity (0, 1).  d_out is (B,4) doubles:
  * psnr (skimage, data_range, all channels jointly), ssim (7x7 uniform window, sample covariance, mean of the

@@ -293,6 +293,16 @@ def test_phased_predict_equals_predict(cic, precision, small_cfg):
     np.testing.assert_allclose(got[0], want[0], atol=2e-2, rtol=0)
     with pytest.raises(ValueError, match="add up"):
         am.predict_phased([img, mask, bpp], enc_chunks=[3, 3])
+    # uint8 image in, uint8 blended out: the reference's load / save conventions applied on the device
+    img_u8 = cic.synth.synth_images_u8(7, 128, 64, seed=51)
+    for call in range(3):
+        got8, _ = am.predict_phased([img_u8, mask, bpp], enc_chunks=[1, 2, 4], dec_chunks=[4, 2, 1], u8_io=True)
+        assert got8[0].dtype == np.uint8
+        want8 = ((want[0] + 1) * np.float32(127.5)).astype(np.uint8)
+        assert np.abs(got8[0].astype(int) - want8.astype(int)).max() <= 3          # 2e-2 in [-1,1] = 2.55 uint8 steps
+        np.testing.assert_allclose(got8[4], want[4], atol=1e-6)
+    with pytest.raises(ValueError, match="uint8"):
+        am.predict_phased([img, mask, bpp], u8_io=True)
 
 
 def test_linearity_of_blend_at_full_size(cic):

@@ -95,6 +95,39 @@ def test_conv_transpose_tc_matches_oracle(cic, split, B, H, W, Cin, Cin2, Cout):
     assert err < tol(split, 4 * ct), f"max-abs {err}"
 
 
+_DC2_SCRIPT = r"""
+import sys
+import numpy as np, torch
+sys.path.insert(0, {root!r})
+import cic_b200 as cic
+from oracle import graphs
+bf = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(torch.bfloat16).to(torch.float32).numpy()
+for (B, H, W, Cin, Cin2, Cout) in [(4, 32, 32, 128, 128, 64), (1, 34, 64, 64, 0, 64), (2, 32, 64, 128, 0, 32)]:
+    rng = np.random.default_rng(H * Cin + Cout)
+    ct = Cin + Cin2
+    x = rng.standard_normal((B, H, W, ct)).astype(np.float32)
+    k = (rng.standard_normal((4, 4, Cout, ct)) / np.sqrt(4 * ct)).astype(np.float32)
+    b = (rng.standard_normal(Cout) * 0.1).astype(np.float32)
+    x1 = np.ascontiguousarray(x[..., :Cin]); x2 = np.ascontiguousarray(x[..., Cin:]) if Cin2 else None
+    got = cic.ops.conv2d_tc(x1, k, b, activation="lrelu", x2=x2, transpose=True, split=False).cpu().numpy()
+    t = graphs.lrelu(graphs.conv2d_transpose_same_k4s2(graphs._nchw(torch.from_numpy(bf(x)).double()), bf(k).astype(np.float64),
+                                                       b.astype(np.float64), torch.float64))
+    err = np.abs(got - graphs._nhwc(t).numpy()).max()
+    assert err < 2e-4, (B, H, W, Cin, Cin2, Cout, err)
+print("DC2_OK")
+"""
+
+
+def test_merged_phase_pair_deconv_kernel(cic):
+    """tc_deconv2_kernel (tc_gemm2.cu) is off by default; CIC_TC_DC2 is read once per process, so it is exercised in a child
+    process: the generator's deconv3 / deconv4 shapes and an odd tile count (phantom tile) against the float64 oracle."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CIC_TC_DC2="2")
+    r = subprocess.run([sys.executable, "-c", _DC2_SCRIPT.format(root=root)], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "DC2_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 @pytest.mark.parametrize("split", [False, True])
 @pytest.mark.parametrize("B,K,N", [(1, 8192, 64), (5, 131072, 32), (256, 1024, 2048), (3, 64, 8192), (4, 32, 1024), (130, 512, 3)])
 def test_dense_tc_matches_oracle(cic, split, B, K, N):

@@ -38,6 +38,18 @@ def _make_tensor_array(named: Dict[str, np.ndarray]):
     return arr, keep
 
 
+def phased_default_chunks(n: int) -> List[int]:
+    """Upload / encode chunk sizes of predict_phased for a batch of n images (the decode / download schedule is the reverse).
+    Measured r01 at 64 images: 4,12,16,16,16 / 16,16,16,12,4 beats coarser and finer schedules - a short first upload and a short
+    last download are what stays exposed, equal chunks in between keep both copy engines busy."""
+    if n >= 16:
+        a = n // 16
+        return [a, 3 * a, 4 * a, 4 * a, n - 12 * a]
+    if n >= 4:
+        return [n // 4, n // 4, n - 2 * (n // 4)]
+    return [n]
+
+
 class Plan:
     """RAII wrapper of a cic_plan*."""
 
@@ -649,15 +661,7 @@ class AdaptiveCompressionModel(Model):
             for v in sizes:
                 out.append(out[-1] + v)
             return out
-        # default schedule (measured r01 at 64 images: 4,12,16,16,16 / 16,16,16,12,4 beats coarser and finer ones): a short first
-        # upload and a short last download are what stays exposed, equal chunks in between keep both copy engines busy
-        if n >= 16:
-            a = n // 16
-            default = [a, 3 * a, 4 * a, 4 * a, n - 12 * a]
-        elif n >= 4:
-            default = [n // 4, n // 4, n - 2 * (n // 4)]
-        else:
-            default = [n]
+        default = phased_default_chunks(n)
         eb = bounds_of(enc_chunks, default)
         db = bounds_of(dec_chunks, default[::-1])
         dev = runtime.require_cuda()

@@ -112,6 +112,17 @@ print("ok", rank)
 """
 
 
+def test_phased_default_chunks(cic):
+    from importlib import import_module
+    models = import_module("contextual-image-compression_b200.models")
+    assert models.phased_default_chunks(64) == [4, 12, 16, 16, 16]
+    for n in list(range(1, 40)) + [64, 100, 256, 1000]:
+        c = models.phased_default_chunks(n)
+        assert sum(c) == n and all(v > 0 for v in c) and len(c) <= 5
+        if n >= 16:
+            assert c[0] == min(c)                                                  # the exposed first upload is the shortest chunk
+
+
 def test_numa_binding_is_optional(cic):
     """bind_to_gpu_numa_node is an optimisation: without NVML / a GPU it leaves the affinity mask alone and returns 0; with one it
     never leaves the process without CPUs."""

@@ -319,6 +319,11 @@ def main():
     dom = max((k for k in by_kind if k != "other"), key=lambda k: by_kind[k]["ms"]) if by_kind else "other"
     dom_ms, dom_flops = by_kind.get(dom, {"ms": 0.0})["ms"], by_kind.get(dom, {"flops": 0.0})["flops"]
     achieved_tflops = dom_flops / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
+    # executed tensor-core FLOPs of the same launches: the encoder chain (conv2-4, attention projections, Dense) issues three MMAs
+    # per algorithmic MAC (hi*hi + lo*hi + hi*lo, split-bf16); reported next to the algorithmic figure, never instead of it
+    dom_exec = sum(fl * (3.0 if (args.precision == "tc" and ("_enc/" in name)) else 1.0)
+                   for name, ms, fl, by, kind in prof if KINDS.get(kind, "other") == dom)
+    executed_tflops = dom_exec / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
     peak = peaks["bf16_tflops_sustained"]
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")      # dram bytes per step of each kernel class, from ncu --set full
@@ -331,6 +336,7 @@ def main():
                 "peak_source": f"{peaks['source']} sustained bf16 (MEASURED_PEAKS.json)",
                 "kernel_ms_per_step": dom_ms, "kernel_share_of_step": dom_ms / ms_step if ms_step else None,
                 "kernel_algorithmic_flops_per_step": dom_flops,
+                "kernel_executed_tflops": executed_tflops, "kernel_executed_frac_of_burst_peak": executed_tflops / peaks["bf16_tflops"],
                 "all_gemm_layers": {"tflops": gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0, "ms_per_step": gemm_ms,
                                     "algorithmic_flops_per_step": gemm_flops, "model_flops_per_step": n_tiles * FLOP_PER_TILE,
                                     "frac_of_peak": (gemm_flops / (gemm_ms * 1e-3) / 1e12 / peak) if gemm_ms > 0 else 0.0},

@@ -10,6 +10,12 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on a B200 via gpurun)")
+    # the C-ABI library is built in-tree and is not under version control: build it once on a clean checkout (nvcc cross-compiles
+    # without a GPU); on the GPU box the snapshot already carries the .so
+    lib = os.path.join(ROOT, "contextual-image-compression_b200", "libcic.so")
+    if not os.path.exists(lib):
+        import __graft_entry__
+        __graft_entry__.build()
 
 
 @pytest.fixture(scope="session")

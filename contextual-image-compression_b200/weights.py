@@ -183,3 +183,51 @@ def synthetic_adaptive(img_shape, base_latent_dim: int, seed: int = 42,
         "latent_saliency_lq": synthetic_latent_saliency(base_latent_dim, seed + 6, keras_default),
         "rd_optimizer": synthetic_rd_optimizer(seed + 7, keras_default),
     }
+
+
+# ---- checkpoints -----------------------------------------------------------------------------------------------------------
+# The reference saves each sub-model with Keras `model.save("*.h5")` (GAN_train.py:548-581) and reloads it with
+# `keras.models.load_model` (GAN_test.py:37-78).  Neither h5py nor TensorFlow exists in this repository's environment, so the
+# exchange format is a flat .npz in the Keras layouts above ("<sub_model>/<layer>/<tensor>"): `tools/convert_keras_h5.py`
+# writes it in the reference's own environment, `load_npz` reads it here.
+
+def flatten(nested: Dict[str, Weights]) -> Weights:
+    return {f"{sub}/{k}": np.asarray(v) for sub, ws in nested.items() for k, v in ws.items()}
+
+
+def unflatten(flat: Weights) -> Dict[str, Weights]:
+    nested: Dict[str, Weights] = {}
+    for key, v in flat.items():
+        sub, _, name = key.partition("/")
+        if not name:
+            raise ValueError(f"checkpoint key '{key}' is not '<sub_model>/<layer>/<tensor>'")
+        nested.setdefault(sub, {})[name] = np.ascontiguousarray(v, dtype=np.float32)
+    return nested
+
+
+def save_npz(path: str, nested: Dict[str, Weights]) -> None:
+    np.savez(path, **flatten(nested))
+
+
+def load_npz(path: str) -> Dict[str, Weights]:
+    with np.load(path) as f:
+        return unflatten({k: f[k] for k in f.files})
+
+
+def check_adaptive(nested: Dict[str, Weights], img_shape, base_latent_dim: int) -> None:
+    """Raise ValueError naming the first missing / extra / mis-shaped tensor of an adaptive-model checkpoint."""
+    want = synthetic_adaptive(img_shape, base_latent_dim, keras_default=True)
+    for sub, ws in want.items():
+        if sub not in nested:
+            raise ValueError(f"checkpoint has no sub-model '{sub}'")
+        for k, v in ws.items():
+            if k not in nested[sub]:
+                raise ValueError(f"checkpoint is missing '{sub}/{k}' {v.shape}")
+            if tuple(nested[sub][k].shape) != tuple(v.shape):
+                raise ValueError(f"'{sub}/{k}' has shape {tuple(nested[sub][k].shape)}, expected {tuple(v.shape)}")
+        extra = set(nested[sub]) - set(ws)
+        if extra:
+            raise ValueError(f"checkpoint has unknown tensors in '{sub}': {sorted(extra)[:4]}")
+    extra = set(nested) - set(want)
+    if extra:
+        raise ValueError(f"checkpoint has unknown sub-models: {sorted(extra)}")

@@ -112,6 +112,85 @@ print("ok", rank)
 """
 
 
+def test_checkpoint_npz_round_trip_and_load_models(cic, tmp_path):
+    """flat Keras-layout .npz checkpoints (written by tools/convert_keras_h5.py in the reference's environment)."""
+    import GAN_test as gt
+    shape, base = (64, 64, 3), 32                                               # a small instance of the same graph
+    w = cic.weights.synthetic_adaptive(shape, base, seed=5)
+    path = str(tmp_path / "adaptive_weights.npz")
+    cic.weights.save_npz(path, w)
+    back = cic.weights.load_npz(path)
+    assert set(back) == set(w) and all(set(back[s]) == set(w[s]) for s in w)
+    for s_ in w:
+        for k in w[s_]:
+            assert back[s_][k].dtype == np.float32
+            np.testing.assert_array_equal(back[s_][k], w[s_][k])
+    cic.weights.check_adaptive(back, shape, base)
+    with pytest.raises(ValueError, match="has shape"):
+        cic.weights.check_adaptive(back, shape, 2 * base)                       # a checkpoint of another latent size
+    bad = {s_: dict(ws) for s_, ws in w.items()}
+    del bad["hq_encoder"]["attn/gamma"]
+    with pytest.raises(ValueError, match="missing 'hq_encoder/attn/gamma'"):
+        cic.weights.check_adaptive(bad, shape, base)
+    bad = {s_: dict(ws) for s_, ws in w.items()}
+    bad["rd_optimizer"]["conv3/kernel"] = np.zeros(3, np.float32)
+    with pytest.raises(ValueError, match="unknown tensors in 'rd_optimizer'"):
+        cic.weights.check_adaptive(bad, shape, base)
+    with pytest.raises(FileNotFoundError):
+        gt.load_models(str(tmp_path / "nowhere"))
+    (tmp_path / "h5dir").mkdir()
+    (tmp_path / "h5dir" / "hq_encoder_final.h5").write_bytes(b"")
+    with pytest.raises(NotImplementedError, match="convert_keras_h5"):
+        gt.load_models(str(tmp_path / "h5dir"))
+
+
+def test_keras_layer_mapping_of_the_converter(cic):
+    """tools/convert_keras_h5.map_layers on duck-typed layers in the creation order of GAN_functions.py:236-331."""
+    import importlib.util, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("convert_keras_h5", os.path.join(root, "tools", "convert_keras_h5.py"))
+    conv = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(conv)
+
+    def layer(cls, *ws):
+        return type(cls, (), {"get_weights": lambda self: list(ws)})()
+    ref = cic.weights.synthetic_encoder((64, 64, 3), 32, True, seed=1)
+    att = type("SelfAttention", (), {})()
+    att.query_conv = layer("Conv2D", ref["attn/query/kernel"], ref["attn/query/bias"])
+    att.key_conv = layer("Conv2D", ref["attn/key/kernel"], ref["attn/key/bias"])
+    att.value_conv = layer("Conv2D", ref["attn/value/kernel"], ref["attn/value/bias"])
+    att.gamma = ref["attn/gamma"]
+    bn = lambda p: layer("BatchNormalization", ref[p + "/gamma"], ref[p + "/beta"], ref[p + "/moving_mean"], ref[p + "/moving_variance"])  # noqa: E731
+    layers = [layer("InputLayer"), layer("Conv2D", ref["conv1/kernel"], ref["conv1/bias"]), layer("LeakyReLU"),
+              layer("Conv2D", ref["conv2/kernel"], ref["conv2/bias"]), bn("bn2"), layer("LeakyReLU"),
+              layer("Conv2D", ref["conv3/kernel"], ref["conv3/bias"]), bn("bn3"), layer("LeakyReLU"), att,
+              layer("Conv2D", ref["conv4/kernel"], ref["conv4/bias"]), bn("bn4"), layer("LeakyReLU"), layer("Flatten"),
+              layer("Dense", ref["dense/kernel"], ref["dense/bias"])]
+    got = conv.map_layers(layers, "encoder")
+    assert set(got) == set(ref)
+    for k in ref:
+        np.testing.assert_array_equal(got[k], ref[k])
+    gref = cic.weights.synthetic_generator(32, (64, 64, 3), seed=2)
+    gl = [layer("Dense", gref["dense/kernel"], gref["dense/bias"]), layer("Reshape")]
+    gbn = lambda p: layer("BatchNormalization", gref[p + "/gamma"], gref[p + "/beta"], gref[p + "/moving_mean"], gref[p + "/moving_variance"])  # noqa: E731
+    gl += [gbn("bn0"), layer("LeakyReLU")]
+    for i in range(1, 5):
+        gl += [layer("Conv2DTranspose", gref[f"deconv{i}/kernel"], gref[f"deconv{i}/bias"]), gbn(f"bn{i}"), layer("LeakyReLU"), layer("Concatenate")]
+    gl += [layer("Conv2D", gref["conv_out/kernel"], gref["conv_out/bias"])]
+    gg = conv.map_layers(gl, "generator")
+    assert set(gg) == set(gref) and all(np.array_equal(gg[k], gref[k]) for k in gref)
+    with pytest.raises(ValueError, match="unexpected layer counts"):
+        conv.map_layers(gl[:-1], "generator")
+    sref = cic.weights.synthetic_latent_saliency(32, seed=3)
+    sl = [layer("Dense", sref[f"dense{i}/kernel"], sref[f"dense{i}/bias"]) for i in (1, 2, 3)]
+    assert set(conv.map_layers(sl, "latent_saliency")) == set(sref)
+    rref = cic.weights.synthetic_rd_optimizer(seed=4)
+    rl = [layer("Conv2D", rref["conv1/kernel"], rref["conv1/bias"]), layer("Conv2D", rref["conv2/kernel"], rref["conv2/bias"]),
+          layer("GlobalAveragePooling2D"), layer("Dense", rref["dense1/kernel"], rref["dense1/bias"]),
+          layer("Dense", rref["dense2/kernel"], rref["dense2/bias"])]
+    assert set(conv.map_layers(rl, "rd_optimizer")) == set(rref)
+
+
 def test_phased_default_chunks(cic):
     from importlib import import_module
     models = import_module("contextual-image-compression_b200.models")

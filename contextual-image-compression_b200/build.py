@@ -12,6 +12,8 @@ LIB = os.path.join(HERE, "libcic.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+if os.environ.get("CIC_BUILD_KNOBS") == "1":      # tuning build: kernel-selection switches read from the environment (common.cuh)
+    FLAGS.append("-DCIC_TUNING_KNOBS")
 
 
 def sources():

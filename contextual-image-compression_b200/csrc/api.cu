@@ -19,11 +19,13 @@ void set_error(const char* fmt, ...) {
 }
 
 int sm_count() {
-  static int cached = 0;
-  if (cached > 0) return cached;
+  static int cached[64] = {0};  // per device ordinal
   int dev = 0, n = 0;
-  if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) {
-    cached = n;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  const int slot = dev & 63;
+  if (cached[slot] > 0) return cached[slot];
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) {
+    cached[slot] = n;
     return n;
   }
   return 148;  // B200

@@ -336,10 +336,10 @@ int launch_attn_fused(const bf16* qk_hi, const bf16* qk_lo, const bf16* vt_hi, c
   e.out_H = tokens; e.out_W = 1; e.out_ys = 1; e.out_xs = 1;
   e.Ho = tokens; e.Wo = 1;
   e.m_total = (long long)nb * tokens;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;  // function attributes are per device
+  if (attr_set.todo()) {
     CIC_CHECK_CUDA(cudaFuncSetAttribute(attn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
-    attr_set = true;
+    attr_set.done();
   }
   const int items = nb * (tokens / AT_Q);
   const int grid = items < sm_count() ? items : sm_count();

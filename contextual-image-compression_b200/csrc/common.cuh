@@ -11,9 +11,32 @@
 
 #include "../../include/cic.h"
 
+// Kernel-selection switches used while tuning (profiles/*.md record what each one measured).  The shipped library has none: the
+// macro is its default value unless the library is built with -DCIC_TUNING_KNOBS (build.py: CIC_BUILD_KNOBS=1), which reads the
+// environment once per call site.
+#ifdef CIC_TUNING_KNOBS
+#include <stdlib.h>
+#define CIC_KNOB(name, dflt) (getenv(name) ? atoi(getenv(name)) : (dflt))
+#else
+#define CIC_KNOB(name, dflt) (dflt)
+#endif
+
 namespace cic {
 
 void set_error(const char* fmt, ...);
+
+// "once per device" guard for cudaFuncSetAttribute (the attribute is per device: a process that switches devices must opt every
+// device in).  todo() / done() may race between threads; the worst case is a harmless repeated cudaFuncSetAttribute.
+struct DeviceOnce {
+  unsigned long long mask = 0;
+  static unsigned long long bit() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return 1ull << (dev & 63);
+  }
+  bool todo() const { return !(__atomic_load_n(&mask, __ATOMIC_ACQUIRE) & bit()); }
+  void done() { __atomic_fetch_or(&mask, bit(), __ATOMIC_RELEASE); }
+};
 
 #define CIC_CHECK_CUDA(expr)                                                                   \
   do {                                                                                         \

@@ -114,10 +114,14 @@ conv1_tc_kernel(const __grid_constant__ Conv1Params p) {
       const int oy0 = (ti / p.tiles_x) * p.TH, ox0 = (ti % p.tiles_x) * p.TW;
       const float* xb;
       size_t row_stride;
+      int vh = p.H, vw = p.W;  // rows / columns of this item that exist in the image (ragged last tile row / column: fewer)
       if (p.tm.tiles_x) {
         const int tpi = p.tm.tiles_x * p.tm.tiles_y, img = b / tpi, tt = b % tpi;
-        xb = p.x + (((size_t)img * p.tm.IH + (size_t)(tt / p.tm.tiles_x) * p.H) * p.tm.IW + (size_t)(tt % p.tm.tiles_x) * p.W) * 3;
+        const int gy0 = (tt / p.tm.tiles_x) * p.H, gx0 = (tt % p.tm.tiles_x) * p.W;
+        xb = p.x + (((size_t)img * p.tm.IH + (size_t)gy0) * p.tm.IW + (size_t)gx0) * 3;
         row_stride = (size_t)p.tm.IW * 3;
+        vh = min(p.H, p.tm.IH - gy0);
+        vw = min(p.W, p.tm.IW - gx0);
       } else {
         xb = p.x + (size_t)b * p.H * p.W * 3;
         row_stride = (size_t)p.W * 3;
@@ -125,14 +129,19 @@ conv1_tc_kernel(const __grid_constant__ Conv1Params p) {
       const int iy0 = 2 * oy0 - p.pad_t, ix0 = 2 * ox0 - p.pad_l;
       named_bar_sync(1, 128);  // everyone is done reading the previous patch
       {
-        // all loads of the tile in flight at once: 4-byte cp.async with zero fill outside the image / tile
+        // all loads of the tile in flight at once: 4-byte cp.async with zero fill outside the tile ('same' padding: tiles are
+        // coded independently); pixels of a ragged tile beyond the image replicate the image's last row / column
         const uint32_t patch_s = smem_u32(patch);
         const float* row0 = xb + (long long)ix0 * 3;
+        const bool ragged = vh < p.H || vw < p.W;
         int pr = 0, cix = r;  // r < 128 < PW3
         for (int i = r; i < PH * PW3; i += 128) {
-          const int iy = iy0 + pr, ix = ix0 + (int)(((unsigned)cix * 43691u) >> 17);  // cix / 3 for cix < 98304
+          const int px = (int)(((unsigned)cix * 43691u) >> 17);  // cix / 3 for cix < 98304
+          const int iy = iy0 + pr, ix = ix0 + px;
           const bool ok = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
           const float* src = ok ? row0 + (size_t)iy * row_stride + cix : p.x;
+          if (ragged && ok && (iy >= vh || ix >= vw))
+            src = xb + (size_t)min(iy, vh - 1) * row_stride + (size_t)min(ix, vw - 1) * 3 + (cix - 3 * px);
           asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(patch_s + (uint32_t)i * 4u), "l"(src), "r"(ok ? 4 : 0) : "memory");
           cix += 128;
           if (cix >= PW3) { cix -= PW3; ++pr; }
@@ -304,10 +313,10 @@ int conv1_tc_pack(const float* w0, const float* w1, uint8_t* img, cudaStream_t s
 template <int N>
 static int launch_conv1_n(const Conv1Params& p, cudaStream_t st) {
   const size_t smem = 4 * C1_ABYTES + 2 * N * C1_ROWB + (C1_MAX_PATCH + 8) * sizeof(float) + 128 + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;  // function attributes are per device
+  if (attr_set.todo()) {
     CIC_CHECK_CUDA(cudaFuncSetAttribute(conv1_tc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    attr_set.done();
   }
   const int slots = 2 * sm_count();
   conv1_tc_kernel<N><<<p.total_tiles < slots ? p.total_tiles : slots, 288, smem, st>>>(p);

@@ -152,10 +152,14 @@ conv_rows_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__
       const int gx = x0 + xl;
       float* out_col;
       size_t row_stride;
+      int vh = p.H, vw = p.W;  // rows / columns of this item that exist in the image (a ragged last tile is cropped on store)
       if (p.tm_tx) {
         const int tpi = p.tm_tx * p.tm_ty, img = b / tpi, tt = b % tpi;
-        out_col = p.out + ((((size_t)img * p.tm_IH + (size_t)(tt / p.tm_tx) * p.H) * p.tm_IW) + (size_t)(tt % p.tm_tx) * p.W + gx) * COUT;
+        const int gy0 = (tt / p.tm_tx) * p.H, gx0 = (tt % p.tm_tx) * p.W;
+        out_col = p.out + ((((size_t)img * p.tm_IH + (size_t)gy0) * p.tm_IW) + (size_t)gx0 + gx) * COUT;
         row_stride = (size_t)p.tm_IW * COUT;
+        vh = min(p.H, p.tm_IH - gy0);
+        vw = min(p.W, p.tm_IW - gx0);
       } else {
         out_col = p.out + (((size_t)b * p.H) * p.W + gx) * COUT;
         row_stride = (size_t)p.W * COUT;
@@ -186,7 +190,7 @@ conv_rows_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__
         }
         // output row r + pad - (KS - 1) has received its last contribution
         const int yo = r + p.pad - (KS - 1);
-        if (yo >= y0 && yo < y0 + CR_STRIP_H && yo < p.H && gx < p.W) {
+        if (yo >= y0 && yo < y0 + CR_STRIP_H && yo < vh && gx < vw) {
           float* dst = out_col + (size_t)yo * row_stride;
 #pragma unroll
           for (int o = 0; o < COUT; ++o) {
@@ -236,10 +240,10 @@ template <int KS, int COUT>
 static int launch_rows(const TcMaps& maps, const ConvRowsParams& p, cudaStream_t st) {
   const size_t smem = (size_t)CR_SLOTS * p.slot_bytes + (size_t)p.nblk * KS * 1024 + 512 + 1024;
   CIC_REQUIRE(smem <= 227 * 1024, "conv_rows: %zu bytes of shared memory", smem);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;  // function attributes are per device
+  if (attr_set.todo()) {
     CIC_CHECK_CUDA(cudaFuncSetAttribute(conv_rows_tc_kernel<KS, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
+    attr_set.done();
   }
   const int slots = sm_count() * (smem <= 112 * 1024 ? 2 : 1);  // two co-resident CTAs (32 TMEM columns each) when shared memory allows
   conv_rows_tc_kernel<KS, COUT><<<p.total_strips < slots ? p.total_strips : slots, 192, smem, st>>>(maps, p);

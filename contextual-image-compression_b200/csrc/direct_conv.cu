@@ -41,10 +41,14 @@ direct_conv_kernel(const float* __restrict__ x, const float* __restrict__ wgt, c
   // tiles are coded independently)
   const float* xb;
   size_t row_stride;
+  int vh = H, vw = W;  // rows / columns of this item that exist in the image: a ragged last tile replicates the image edge
   if (tm.tiles_x) {
     const int tpi = tm.tiles_x * tm.tiles_y, img = b / tpi, t = b % tpi;
-    xb = x + (((size_t)img * tm.IH + (size_t)(t / tm.tiles_x) * H) * tm.IW + (size_t)(t % tm.tiles_x) * W) * CIN;
+    const int gy0 = (t / tm.tiles_x) * H, gx0 = (t % tm.tiles_x) * W;
+    xb = x + (((size_t)img * tm.IH + (size_t)gy0) * tm.IW + (size_t)gx0) * CIN;
     row_stride = (size_t)tm.IW * CIN;
+    vh = min(H, tm.IH - gy0);
+    vw = min(W, tm.IW - gx0);
   } else {
     xb = x + (size_t)b * H * W * CIN;
     row_stride = (size_t)W * CIN;
@@ -60,7 +64,8 @@ direct_conv_kernel(const float* __restrict__ x, const float* __restrict__ wgt, c
       const int r = i / (Cfg::kPW * CIN), cix = i % (Cfg::kPW * CIN);
       const int iy = iy0 + r, ix = ix0 + cix / CIN;
       v[k] = 0.f;
-      if (i < kElems && iy >= 0 && iy < H && ix >= 0 && ix < W) v[k] = __ldg(xb + (size_t)iy * row_stride + (size_t)ix * CIN + cix % CIN);
+      if (i < kElems && iy >= 0 && iy < H && ix >= 0 && ix < W)
+        v[k] = __ldg(xb + (size_t)min(iy, vh - 1) * row_stride + (size_t)min(ix, vw - 1) * CIN + cix % CIN);
     }
 #pragma unroll
     for (int k = 0; k < kPer; ++k) {

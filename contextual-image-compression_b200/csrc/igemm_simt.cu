@@ -472,12 +472,13 @@ int launch_global_avg_pool(const float* x, float* y, int batch, int hw, int C, i
   return CIC_OK;
 }
 
-// image (n,H,W,C) <-> tiles (n*ty*tx, tile, tile, C); tile order (image, tile row, tile col)
+// image (n,H,W,C) <-> tiles (n*ty*tx, tile, tile, C); tile order (image, tile row, tile col).  H, W need not be multiples of
+// the tile: the gather replicates the image's last row / column into a ragged last tile, the scatter crops it.
 template <bool GATHER>
 __global__ void tile_copy_kernel(const float* __restrict__ src, float* __restrict__ dst, int n_img, int H, int W, int C,
                                  int tile) {
-  const int tyn = H / tile, txn = W / tile;
-  const long long total = (long long)n_img * H * W * C;
+  const int tyn = (H + tile - 1) / tile, txn = (W + tile - 1) / tile;
+  const long long total = (long long)n_img * tyn * txn * tile * tile * C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     // i indexes the tile-major buffer
     const int c = (int)(i % C);
@@ -487,34 +488,34 @@ __global__ void tile_copy_kernel(const float* __restrict__ src, float* __restric
     const int tx = (int)(r % txn); r /= txn;
     const int ty = (int)(r % tyn);
     const int img = (int)(r / tyn);
-    const long long j = ((((long long)img * H + ty * tile + ly) * W) + tx * tile + lx) * C + c;
-    if (GATHER) dst[i] = src[j];
-    else dst[j] = src[i];
+    const int gy = ty * tile + ly, gx = tx * tile + lx;
+    if (GATHER) {
+      dst[i] = src[((((long long)img * H + min(gy, H - 1)) * W) + min(gx, W - 1)) * C + c];
+    } else if (gy < H && gx < W) {
+      dst[((((long long)img * H + gy) * W) + gx) * C + c] = src[i];
+    }
   }
 }
 
-int launch_tile_gather(const float* img, float* tiles, int n_img, int H, int W, int C, int tile, cudaStream_t st) {
-  const long long total = (long long)n_img * H * W * C;
+static int launch_tile_copy(bool gather, const float* src, float* dst, int n_img, int H, int W, int C, int tile, cudaStream_t st) {
+  const long long total = (long long)n_img * ((H + tile - 1) / tile) * ((W + tile - 1) / tile) * tile * tile * C;
   if (total == 0) return CIC_OK;
   long long blocks = (total + 255) / 256;
   const long long cap = (long long)sm_count() * 16;
   if (blocks > cap) blocks = cap;
-  tile_copy_kernel<true><<<(int)blocks, 256, 0, st>>>(img, tiles, n_img, H, W, C, tile);
+  if (gather) tile_copy_kernel<true><<<(int)blocks, 256, 0, st>>>(src, dst, n_img, H, W, C, tile);
+  else tile_copy_kernel<false><<<(int)blocks, 256, 0, st>>>(src, dst, n_img, H, W, C, tile);
   CIC_COUNT_LAUNCH();
-  CIC_CHECK_LAUNCH("tile_gather_kernel");
+  CIC_CHECK_LAUNCH(gather ? "tile_gather_kernel" : "tile_scatter_kernel");
   return CIC_OK;
 }
 
+int launch_tile_gather(const float* img, float* tiles, int n_img, int H, int W, int C, int tile, cudaStream_t st) {
+  return launch_tile_copy(true, img, tiles, n_img, H, W, C, tile, st);
+}
+
 int launch_tile_scatter(const float* tiles, float* img, int n_img, int H, int W, int C, int tile, cudaStream_t st) {
-  const long long total = (long long)n_img * H * W * C;
-  if (total == 0) return CIC_OK;
-  long long blocks = (total + 255) / 256;
-  const long long cap = (long long)sm_count() * 16;
-  if (blocks > cap) blocks = cap;
-  tile_copy_kernel<false><<<(int)blocks, 256, 0, st>>>(tiles, img, n_img, H, W, C, tile);
-  CIC_COUNT_LAUNCH();
-  CIC_CHECK_LAUNCH("tile_scatter_kernel");
-  return CIC_OK;
+  return launch_tile_copy(false, tiles, img, n_img, H, W, C, tile, st);
 }
 
 }  // namespace cic

@@ -561,11 +561,11 @@ static int metrics_f32_impl(const float* d_a, const float* d_b, double* d_out, i
   const bool packed = channels <= 4;
   const size_t smem = packed ? (size_t)(2 * TP * (TP * channels + 1) + 5 * TS * (TP + 1)) * sizeof(float) : 0;
   if (packed) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_set;  // function attributes are per device
+    if (attr_set.todo()) {
       CIC_CHECK_CUDA(cudaFuncSetAttribute(metrics_f32_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
       CIC_CHECK_CUDA(cudaFuncSetAttribute(metrics_f32_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
-      attr_set = true;
+      attr_set.done();
     }
   }
   for (int b0 = 0; b0 < batch; b0 += 65535) {

@@ -543,7 +543,7 @@ int rd_forward_f32(cic_plan* pl, Ctx& c, const float* mask, const float* bpp, fl
 int launch_rd_tail(cic_plan* pl, Ctx& c, const float* bpp, float* feat, float* d1, float* base, float* rd_params, int B) {
   const WeightStore& w = pl->w;
   int rc;
-  static const int fused_env = getenv("CIC_MLP_FUSED") ? atoi(getenv("CIC_MLP_FUSED")) : 1;
+  static const int fused_env = CIC_KNOB("CIC_MLP_FUSED", 1);
   if (fused_env) {  // concat + Dense128 + Dense3 + sigmoids in one kernel (mlp_fused.cu)
     if (c.dry) return CIC_OK;
     Scope sc(c, "tail", 2.0 * B * (65.0 * 128 + 128 * 3), 4.0 * (65 * 128 + 128 * 3 + (double)B * 68));
@@ -574,9 +574,9 @@ int launch_expand_bpp(const float* bpp, float* bpp_t, float* qs_t, int n_tiles, 
 
 int adaptive_forward_f32(cic_plan* pl, Ctx& c, const cic_adaptive_io* io, int n_img, int img_h, int img_w) {
   const int T = pl->opts.img_h, base = pl->opts.latent_dim;
-  const int tpi = (img_h / T) * (img_w / T);
+  const int tpi = ((img_h + T - 1) / T) * ((img_w + T - 1) / T);
   const int nt = n_img * tpi;
-  const bool tiled = tpi > 1;
+  const bool tiled = tpi > 1 || img_h != T || img_w != T;  // ragged sizes: edge-replicated into whole tiles, cropped on the way out
   const size_t tpx = (size_t)nt * T * T;
   int rc;
   // 0. image / mask tiles
@@ -868,8 +868,7 @@ extern "C" int cic_adaptive_forward(cic_plan* plan, const cic_adaptive_io* io, i
   CIC_REQUIRE(io && (n_img == 0 || (io->d_img && io->d_mask && io->d_bpp)), "cic_adaptive_forward: null input");
   const int T = plan->opts.img_h;
   CIC_REQUIRE(plan->opts.img_h == plan->opts.img_w, "cic_adaptive_forward: square model tiles only");
-  CIC_REQUIRE(img_h > 0 && img_w > 0 && img_h % T == 0 && img_w % T == 0,
-              "cic_adaptive_forward: image size %dx%d is not a multiple of the model tile %d", img_h, img_w, T);
+  CIC_REQUIRE(img_h > 0 && img_w > 0 && T > 0, "cic_adaptive_forward: bad image size %dx%d", img_h, img_w);
   return run(plan, n_img, img_h, img_w, d_workspace, workspace_bytes, stream, io, nullptr, nullptr, nullptr, nullptr, nullptr,
              nullptr, nullptr);
 }
@@ -893,8 +892,7 @@ extern "C" int cic_adaptive_forward_phase(cic_plan* plan, const cic_adaptive_io*
                 "cic_adaptive_forward_phase: null state buffer");
   const int T = plan->opts.img_h;
   CIC_REQUIRE(plan->opts.img_h == plan->opts.img_w, "cic_adaptive_forward_phase: square model tiles only");
-  CIC_REQUIRE(img_h > 0 && img_w > 0 && img_h % T == 0 && img_w % T == 0,
-              "cic_adaptive_forward_phase: image size %dx%d is not a multiple of the model tile %d", img_h, img_w, T);
+  CIC_REQUIRE(img_h > 0 && img_w > 0 && T > 0, "cic_adaptive_forward_phase: bad image size %dx%d", img_h, img_w);
   const size_t need = cic_plan_workspace_bytes(plan, n_img, img_h, img_w);  // upper bound: the one-call forward of as many images
   if (!d_workspace || workspace_bytes < need) {
     set_error("workspace too small: need %zu bytes, got %zu", need, d_workspace ? workspace_bytes : (size_t)0);

@@ -220,7 +220,7 @@ static int dense_tc(Ctx& c, const char* name, const TcAct& x, int batch, const T
 static int dense_splits(int batch, int N_pad, int K, bool split) {
   const int bk = K % 64 == 0 ? 64 : 32;
   const long long mt = (batch + 127) / 128;
-  static const int pair_env = getenv("CIC_TC_PAIR") ? atoi(getenv("CIC_TC_PAIR")) : 1;
+  static const int pair_env = CIC_KNOB("CIC_TC_PAIR", 1);
   const bool pair = pair_env && tc_pair_ok(bk, mt, N_pad, N_pad);
   const int bn = pair ? tc2_pick_block_n(N_pad) : tc_pick_block_n(N_pad, split, bk);
   const long long tiles = (pair ? (mt + 1) / 2 : mt) * (N_pad / (bn > 0 ? bn : 16));
@@ -240,7 +240,7 @@ static int attention_tc(cic_plan* pl, Ctx& c, const ActBuf& x, const ActBuf& y, 
   const WeightStore& w = pl->w;
   const int dq = C / 8;
   CIC_REQUIRE(tokens % 32 == 0, "attention (tc): token count %d must be a multiple of 32", tokens);
-  static const int fused_env = getenv("CIC_ATTN_FUSED") ? atoi(getenv("CIC_ATTN_FUSED")) : 1;
+  static const int fused_env = CIC_KNOB("CIC_ATTN_FUSED", 1);
   if (fused_env && tokens % 128 == 0 && C == 256 && dq == 32) {
     // projections as GEMMs over the whole batch, then one fused kernel for softmax(q k^T) v (attn_fused.cu)
     const size_t mk = c.arena.mark();
@@ -266,7 +266,7 @@ static int attention_tc(cic_plan* pl, Ctx& c, const ActBuf& x, const ActBuf& y, 
     c.arena.release(mk);
     return rc;
   }
-  static const int chunk_env = getenv("CIC_ATTN_CHUNK") ? atoi(getenv("CIC_ATTN_CHUNK")) : 0;
+  static const int chunk_env = CIC_KNOB("CIC_ATTN_CHUNK", 0);
   const int chunk_max = chunk_env > 0 ? chunk_env : 128;  // images per pass: bounds the tokens x tokens score workspace
   const int chunk = batch < chunk_max ? batch : chunk_max;
   const size_t mk = c.arena.mark();
@@ -498,7 +498,7 @@ static int generator_core_tc(cic_plan* pl, Ctx& c, const float* latent, const bf
   DC(4, view(g3, 64), &k1, 8 * h16, 8 * w16, 128, 32, g4);
 #undef DC
   // :273 Conv2D(3, k4, 'same', tanh): pad 1 before / 2 after
-  static const int no_rows = getenv("CIC_TC_NO_ROWS") ? atoi(getenv("CIC_TC_NO_ROWS")) : 0;
+  static const int no_rows = CIC_KNOB("CIC_TC_NO_ROWS", 0);
   if (C == 3 && !no_rows) {  // column-strip formulation (kx folded into K, ky into N)
     if (!c.dry) {
       Scope sc(c, "conv_out", 2.0 * px * 16 * 32 * C, 2.0 * px * 32 + 4.0 * px * C);
@@ -561,7 +561,7 @@ int autoencoder_forward_tc(cic_plan* pl, Ctx& c, const float* x, float* y, uint8
   AE_CONV("conv5", view(y3u, 64), &x2rv, H / 2, W / 2, 128, 32, y5u, 1);                      // :26 concat, :28, :29 UpSampling2D
   AE_CONV("conv_x1", view(x1, 32), nullptr, H, W, 32, 32, x1r, 0);                            // :32
 #undef AE_CONV
-  static const int no_rows = getenv("CIC_TC_NO_ROWS") ? atoi(getenv("CIC_TC_NO_ROWS")) : 0;
+  static const int no_rows = CIC_KNOB("CIC_TC_NO_ROWS", 0);
   if (!no_rows) {                                                                              // :33 concat, :35 Conv2D(3, sigmoid)
     if (!c.dry) {
       Scope sc(c, "conv_out", 2.0 * px * 9 * 64 * C, 2.0 * px * 64 + 4.0 * px * C);
@@ -610,9 +610,11 @@ int rd_forward_tc(cic_plan* pl, Ctx& c, const float* mask, const float* bpp, flo
 int adaptive_forward_tc(cic_plan* pl, Ctx& c, const cic_adaptive_io* io, int n_img, int img_h, int img_w, int phase,
                         const cic_adaptive_state* state, int tile0) {
   const int T = pl->opts.img_h, base = pl->opts.latent_dim;
-  const int tpi = (img_h / T) * (img_w / T);
+  const int tpi = ((img_h + T - 1) / T) * ((img_w + T - 1) / T);
   const int nt = n_img * tpi;
-  const bool tiled = tpi > 1;
+  // sizes that are not a multiple of the model tile: the last tile row / column replicates the image edge on load (conv1, RD conv1)
+  // and is cropped on store (conv_out); dt, blend and hq_ratio run on the real image
+  const bool tiled = tpi > 1 || img_h != T || img_w != T;
   const size_t tpx = (size_t)nt * T * T;
   int rc;
   const bool all = phase == 0;
@@ -620,7 +622,7 @@ int adaptive_forward_tc(cic_plan* pl, Ctx& c, const cic_adaptive_io* io, int n_i
   CIC_REQUIRE(all || state, "adaptive (tc): the phased forward needs the state buffers");
   // tiles are addressed in place in the image layout by the first (conv1, RD conv1) and last (conv_out) layers
   TileMap tm;
-  if (tiled) { tm.tiles_x = img_w / T; tm.tiles_y = img_h / T; tm.IH = img_h; tm.IW = img_w; }
+  if (tiled) { tm.tiles_x = (img_w + T - 1) / T; tm.tiles_y = (img_h + T - 1) / T; tm.IH = img_h; tm.IW = img_w; }
   const float* img_t = io->d_img;
   const float* mask_t = io->d_mask;
   float* bpp_t = c.arena.f32(nt);

@@ -445,10 +445,10 @@ size_t tcv_smem_bytes(const TcvParams& p) {
 
 template <int BK, bool SPLIT, bool RESIDENT, int THREADS>
 static int launch_conv_thr(const TcMaps& maps, const TcvParams& p, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;  // function attributes are per device
+  if (attr_set.todo()) {
     CIC_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<BK, SPLIT, RESIDENT, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
+    attr_set.done();
   }
   const size_t smem = tcv_smem_bytes(p);
   CIC_REQUIRE(smem <= 227 * 1024, "tc_conv: %zu bytes of shared memory needed", smem);

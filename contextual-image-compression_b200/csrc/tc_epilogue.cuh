@@ -87,8 +87,9 @@ __device__ __forceinline__ void tc_epilogue_store(const TcEpi& e, const TcEpiVec
   long long opix;
   if (e.tm_tx) {  // scatter the tile into the image layout
     const int tpi = e.tm_tx * e.tm_ty, img = r.b / tpi, t = r.b % tpi;
-    opix = ((long long)img * e.tm_IH + (t / e.tm_tx) * e.out_H + (r.oy * e.out_ys + e.out_y0[r.phase])) * e.tm_IW + (t % e.tm_tx) * e.out_W +
-           (r.ox * e.out_xs + e.out_x0[r.phase]);
+    const int gy = (t / e.tm_tx) * e.out_H + (r.oy * e.out_ys + e.out_y0[r.phase]), gx = (t % e.tm_tx) * e.out_W + (r.ox * e.out_xs + e.out_x0[r.phase]);
+    if (gy >= e.tm_IH || gx >= e.tm_IW) return;  // ragged last tile row / column: cropped on store (never with the quad path: !e.tm_tx)
+    opix = ((long long)img * e.tm_IH + gy) * e.tm_IW + gx;
   } else {
     opix = ((long long)r.b * e.out_H + (r.oy * e.out_ys + e.out_y0[r.phase])) * e.out_W + (r.ox * e.out_xs + e.out_x0[r.phase]);
   }

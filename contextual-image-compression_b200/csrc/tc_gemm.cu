@@ -247,10 +247,10 @@ int tc_encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* 
 template <int BN, int BK, bool SPLIT>
 static int launch_one(const TcMaps& maps, const TcParams& p, cudaStream_t st) {
   using Cfg = TcCfg<BN, BK, SPLIT>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;  // function attributes are per device
+  if (attr_set.todo()) {
     CIC_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, BK, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
+    attr_set.done();
   }
   // persistent: at most one wave of CTAs, each walking the tile list with stride gridDim.x
   const int slots = sm_count() * Cfg::kMinCtas;

@@ -502,10 +502,10 @@ static int launch_dc2(const TcMaps& maps, const TcParams& p, const Dc2Params& q,
   constexpr int kStages = (200 * 1024 / kStageBytes) > 8 ? 8 : (200 * 1024 / kStageBytes);
   constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 1024 /*barriers + op tables*/;
   constexpr int THREADS = 320;  // two epilogue groups: 4 * Cout / 32 >= 4 chunks per tile
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;  // function attributes are per device
+  if (attr_set.todo()) {
     CIC_CHECK_CUDA(cudaFuncSetAttribute(tc_deconv2_kernel<COUT, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    attr_set = true;
+    attr_set.done();
   }
   const int pairs = sm_count() / 2;
   const int grid = 2 * (total_pairs < pairs ? total_pairs : pairs);
@@ -557,10 +557,10 @@ int launch_tc_deconv2(const TcMaps& maps, TcParams& p, cudaStream_t st) {
 template <int BN, int BK, bool SPLIT, int THREADS>
 static int launch2_thr(const TcMaps& maps, const TcParams& p, int total_pairs, cudaStream_t st) {
   using Cfg = Tc2Cfg<BN, BK, SPLIT>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;  // function attributes are per device
+  if (attr_set.todo()) {
     CIC_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm2_kernel<BN, BK, SPLIT, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
+    attr_set.done();
   }
   const int pairs = sm_count() / 2;
   const int grid = 2 * (total_pairs < pairs ? total_pairs : pairs);

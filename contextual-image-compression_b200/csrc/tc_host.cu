@@ -94,7 +94,7 @@ static int try_run_raster(const TcLayer& L, int BK, int N_pad, const TcMaps& act
   (void)act_maps_unused;
   *used = false;
   const bool s2 = L.kind == TC_CONV_S2, dc = L.kind == TC_DECONV_K4S2;
-  static const int force = getenv("CIC_TC_RASTER") ? atoi(getenv("CIC_TC_RASTER")) : -1;  // 0: never, 1: whenever possible
+  static const int force = CIC_KNOB("CIC_TC_RASTER", -1);  // 0: never, 1: whenever possible
   if (force == 0) return CIC_OK;
   if (L.b_batched || L.splits != 1 || L.epi.out_mode == TC_OUT_PARTIAL) return CIC_OK;
   if (!dc && L.kh * L.kw == 1) return CIC_OK;  // 1x1 / dense: nothing to reuse
@@ -201,7 +201,7 @@ static int try_run_raster(const TcLayer& L, int BK, int N_pad, const TcMaps& act
   p.ntaps = dc ? 4 : L.kh * L.kw;
   p.b_blocks = nph * p.n_tiles * p.ntaps * (p.src_blocks[0] + p.src_blocks[1]);
   const long long resident_bytes = (long long)p.b_blocks * b_slot_bytes;
-  static const int no_resident = getenv("CIC_TC_NO_RESIDENT") ? atoi(getenv("CIC_TC_NO_RESIDENT")) : 0;
+  static const int no_resident = CIC_KNOB("CIC_TC_NO_RESIDENT", 0);
   if (!no_resident && resident_bytes <= budget - 2LL * p.a_slot_bytes && resident_bytes <= 136 * 1024 &&
       resident_bytes * 148 < (long long)p.total_tiles * 16 * b_slot_bytes) {
     // the whole weight matrix stays in shared memory (only when that is less traffic than streaming it)
@@ -210,7 +210,7 @@ static int try_run_raster(const TcLayer& L, int BK, int N_pad, const TcMaps& act
     p.a_slots = std::min(8, (int)((budget - resident_bytes) / p.a_slot_bytes));
   } else {
     // weight blocks travel in groups of up to 16 KB under one barrier (one wait per group in the MMA warp)
-    static const int gbytes_env = getenv("CIC_TC_BGROUP_BYTES") ? atoi(getenv("CIC_TC_BGROUP_BYTES")) : 0;
+    static const int gbytes_env = CIC_KNOB("CIC_TC_BGROUP_BYTES", 0);
     p.b_group = std::max(1, std::min(4, (gbytes_env > 0 ? gbytes_env : 32768) / b_slot_bytes));
     const int gbytes = p.b_group * b_slot_bytes;
     p.b_slots = std::min(TCV_MAX_SLOTS, std::max(2, 65536 / gbytes));
@@ -227,7 +227,7 @@ static int try_run_raster(const TcLayer& L, int BK, int N_pad, const TcMaps& act
   // A operand reads - the shared-memory data pipe is what bounds these N <= 32 layers (profiles/r01_smem_pipe_model.md).
   // CIC_TC_MERGE: 0 off, 1 resident-weight layers (default; deconv4 1.13 -> 0.87 ms), 2 also streamed weights on this kernel
   // (measured slower than the per-tap kernel for deconv3: 0.87 vs 0.70 ms - the raster kernel's per-op hand-shakes)
-  static const int merge_env = getenv("CIC_TC_MERGE") ? atoi(getenv("CIC_TC_MERGE")) : 1;
+  static const int merge_env = CIC_KNOB("CIC_TC_MERGE", 1);
   if (merge_env && fused && !L.split && mode != 2 && 4 * BN <= TCV_ACC_COLS && (p.b_resident || merge_env >= 2)) {
     TcvPass& P = p.pass[0];
     static const int acc_phase[4] = {0, 1, 3, 2};                 // accumulator -> phase (py * 2 + px)
@@ -336,17 +336,17 @@ static int try_run_raster(const TcLayer& L, int BK, int N_pad, const TcMaps& act
   p.fd_tx = make_fastdiv((uint32_t)p.tiles_x);
   p.fd_ty = make_fastdiv((uint32_t)p.tiles_y);
   // issuer warps: one per accumulator (output phase) when the weights are resident and the MMAs are small
-  static const int nw_env = getenv("CIC_TC_NW") ? atoi(getenv("CIC_TC_NW")) : 0;
+  static const int nw_env = CIC_KNOB("CIC_TC_NW", 0);
   p.nw = 1;
   if (fused) p.nw = nw_env > 0 ? nw_env : (p.b_resident ? 2 : 1);  // measured r01: 2 issuers (384 threads, 168 regs) beat 4 (448 threads: 128-register
                                                                   // cap spills the epilogue); streamed weights: extra issuers gave nothing
   // a second epilogue group when one tile has several accumulator chunks to drain per few MMAs
-  static const int ne_env = getenv("CIC_TC_NE") ? atoi(getenv("CIC_TC_NE")) : 0;
+  static const int ne_env = CIC_KNOB("CIC_TC_NE", 0);
   {
     const int chunks_per_tile = (fused ? 4 : 1) * (BN % 32 == 0 ? BN / 32 : BN / 16);
     p.ne = ne_env > 0 ? ne_env : (chunks_per_tile >= 2 ? 2 : 1);
   }
-  static const int dbg = getenv("CIC_TC_DBG") ? atoi(getenv("CIC_TC_DBG")) : 0;
+  static const int dbg = CIC_KNOB("CIC_TC_DBG", 0);
   p.dbg = dbg;
   *used = true;
   return launch_tc_conv(maps, p, BK, L.split, st);
@@ -391,7 +391,7 @@ int tc_run_layer(const TcLayer& L, cudaStream_t st) {
     bool used = false;
     // CIC_TC_DC2: merged-phase CTA-pair kernel for transposed convs with Cout in {32, 64} (tc_gemm2.cu): 0 off, 1 the layers
     // the raster kernel streams weights for (deconv3), 2 also the resident-weight raster layers (deconv4)
-    static const int dc2_env = getenv("CIC_TC_DC2") ? atoi(getenv("CIC_TC_DC2")) : 0;
+    static const int dc2_env = CIC_KNOB("CIC_TC_DC2", 0);
     bool skip_raster = false;
     if (dc && dc2_env >= 2) {
       int tw, th, tb;
@@ -491,10 +491,10 @@ int tc_run_layer(const TcLayer& L, cudaStream_t st) {
     p.m_fast = (!L.b_batched && w_elems > act_elems) ? 1 : 0;
   }
   // CTA-pair kernel (tc_gemm2.cu) for the large conv / transposed-conv GEMMs: halves the B fill and B operand reads per SM
-  static const int pair_env = getenv("CIC_TC_PAIR") ? atoi(getenv("CIC_TC_PAIR")) : 1;
+  static const int pair_env = CIC_KNOB("CIC_TC_PAIR", 1);
   const long long m_tiles = (long long)p.tiles_x * p.tiles_y * p.tiles_b;
   const int bn2 = tc2_pick_block_n(p.N_pad);
-  static const int dc2_env = getenv("CIC_TC_DC2") ? atoi(getenv("CIC_TC_DC2")) : 0;
+  static const int dc2_env = CIC_KNOB("CIC_TC_DC2", 0);
   const bool dc2 = dc && dc2_env && pair_env && L.splits == 1 && tc_deconv2_ok(BK, L.split, m_tiles, p.N_pad, L.N);
   const bool pair = !dc2 && pair_env && !L.b_batched && tc_pair_ok(BK, m_tiles, p.N_pad, L.N);
   const int bn = dc2 ? L.N : (pair ? bn2 : tc_pick_block_n(p.N_pad, L.split, BK));

@@ -69,9 +69,13 @@ class Plan:
         self.kind = kind
         self.precision = precision or runtime.get_precision()
 
+    def workspace_bytes(self, batch: int, h: int = 0, w: int = 0) -> int:
+        return int(_lib.lib.cic_plan_workspace_bytes(self.handle, batch, h, w))
+
     def workspace(self, batch: int, h: int = 0, w: int = 0) -> torch.Tensor:
-        n = _lib.lib.cic_plan_workspace_bytes(self.handle, batch, h, w)
-        return runtime.Workspace.get(int(n))
+        """The shared grow-only scratch buffer (eager calls).  Captured CUDA graphs never use it: a graph bakes the raw
+        pointer in, and the shared buffer is re-allocated when a later call needs more - they own private scratch instead."""
+        return runtime.Workspace.get(self.workspace_bytes(batch, h, w))
 
     def last_launch_count(self) -> int:
         return int(_lib.lib.cic_plan_last_launch_count(self.handle))
@@ -108,7 +112,21 @@ class Model:
     def __init__(self):
         self._plan: Optional[Plan] = None
         self._plan_precision: Optional[str] = None
-        self.weights: Dict[str, np.ndarray] = {}
+        self._plan_gen = 0          # bumped whenever the plan is rebuilt: keys every cache that holds plan pointers
+        self._ws_override: Optional[torch.Tensor] = None   # private scratch of the graph set being captured / replayed
+        self._weights: Optional[Dict[str, np.ndarray]] = None
+        self._default_weights = None   # () -> Keras-default weights, drawn on first use (a checkpoint usually replaces them first)
+
+    # -- weights ------------------------------------------------------------------------------
+    @property
+    def weights(self) -> Dict[str, np.ndarray]:
+        if self._weights is None:
+            self._weights = self._default_weights() if self._default_weights is not None else {}
+        return self._weights
+
+    @weights.setter
+    def weights(self, w: Dict[str, np.ndarray]) -> None:
+        self._weights = w
 
     # -- weights ------------------------------------------------------------------------------
     def get_weights_dict(self) -> Dict[str, np.ndarray]:
@@ -116,7 +134,22 @@ class Model:
 
     def set_weights_dict(self, w: Dict[str, np.ndarray]) -> None:
         self.weights = w
+        self._drop_plan()
+
+    def _drop_plan(self) -> None:
+        """Forget the plan and everything that holds raw pointers into it (captured CUDA graphs replay the packed-weight and
+        scratch addresses they were captured with; the plan's destructor frees the former)."""
+        for name in ("_pipe_graphs", "_phase_graphs", "_phase_cache"):
+            self.__dict__.pop(name, None)
         self._plan = None
+
+    def _workspace(self, plan: "Plan", batch: int, h: int = 0, w: int = 0) -> torch.Tensor:
+        if self._ws_override is not None:
+            need = plan.workspace_bytes(batch, h, w)
+            if self._ws_override.numel() < need:
+                raise RuntimeError(f"private scratch of {self._ws_override.numel()} bytes is smaller than the {need} this call needs")
+            return self._ws_override
+        return plan.workspace(batch, h, w)
 
     def count_params(self) -> int:
         return int(sum(int(np.prod(v.shape)) for v in self._flat_weights().values()))
@@ -131,8 +164,10 @@ class Model:
     def plan(self) -> Plan:
         prec = runtime.get_precision()
         if self._plan is None or self._plan_precision != prec:
+            self._drop_plan()
             self._plan = self._make_plan(prec)
             self._plan_precision = prec
+            self._plan_gen += 1
         return self._plan
 
     # -- protocols ----------------------------------------------------------------------------
@@ -197,7 +232,7 @@ class Model:
         s_out.wait_stream(compute)
         stage = self.__dict__.setdefault("_stage", {})
         keep, host, extra = [], None, []
-        timeline = os.environ.get("CIC_PIPE_TIMELINE") == "1"            # debug: per-chunk event times of the three streams
+        timeline = runtime.pipe_timeline()                               # debug: per-chunk event times of the three streams
         ev_in = [torch.cuda.Event(enable_timing=timeline) for _ in range(n_chunks)]
         if timeline:
             ev_t0 = torch.cuda.Event(enable_timing=True)
@@ -205,10 +240,11 @@ class Model:
             ev_cs, ev_os = [], []
         # Repeated calls with the same chunking replay one CUDA graph per chunk (the ~55 launches of a small chunk are
         # otherwise launch-bound on the host): the first call runs eagerly, then the chunks are captured with
-        # persistent device input / output buffers.  CIC_PIPE_GRAPHS=0 keeps the eager path.
-        gkey = (tuple(bounds), tuple(tuple(h.shape[1:]) for h in hs), id(on_chunk), id(self.plan()))
+        # persistent device input / output buffers.  runtime.set_cuda_graphs(False) keeps the eager path.
+        self.plan()                                                 # (re)build first: a rebuild drops the graph caches
+        gkey = (tuple(bounds), tuple(tuple(h.shape[1:]) for h in hs), id(on_chunk), self._plan_gen)
         gstate = self.__dict__.setdefault("_pipe_graphs", {})
-        use_graphs = os.environ.get("CIC_PIPE_GRAPHS", "1") != "0"
+        use_graphs = runtime.use_cuda_graphs()
         gs = gstate.get(gkey) if use_graphs else None
         if gs is not None and gs.get("calls", 0) >= 1 and "graphs" not in gs and not gs.get("failed"):
             try:
@@ -218,9 +254,9 @@ class Model:
                 torch.cuda.synchronize()
                 print(f"predict_pipelined: CUDA graph capture failed ({e!r}); using eager launches", file=sys.stderr)
         if gs is None and use_graphs:
-            if len(gstate) > 4:
+            if len(gstate) > 1:
                 gstate.clear()
-            gs = gstate[gkey] = {"calls": 0}
+            gs = gstate[gkey] = {"calls": 0, "on_chunk": on_chunk}   # the strong reference keeps id(on_chunk) from being reused
         if gs is not None:
             gs["calls"] += 1
         graphs = gs.get("graphs") if gs is not None else None
@@ -285,19 +321,29 @@ class Model:
         """One CUDA graph per chunk of predict_pipelined: forward (+ on_chunk) on persistent buffers."""
         d_ins, graphs, outs_all, extras = [], [], [], []
         torch.cuda.synchronize()
+        plan = self.plan()
+        need = 0
         for i in range(len(bounds) - 1):
-            lo, hi = bounds[i], bounds[i + 1]
-            d_in = [torch.zeros((hi - lo,) + tuple(h.shape[1:]), dtype=torch.float32, device=dev) for h in hs]
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                outs = self.forward_device(d_in)
-                ex = on_chunk(d_in, getattr(self, "last", None)) if on_chunk is not None else None
-            d_ins.append(d_in)
-            graphs.append(g)
-            outs_all.append(outs)
-            extras.append(ex)
+            shp = hs[0].shape
+            need = max(need, plan.workspace_bytes(bounds[i + 1] - bounds[i], *(shp[1:3] if len(shp) == 4 else (0, 0))))
+        ws = torch.empty(max(need, 1 << 20), dtype=torch.uint8, device=dev)   # private scratch: the graphs bake its address in
+        self._ws_override = ws
+        try:
+            for i in range(len(bounds) - 1):
+                lo, hi = bounds[i], bounds[i + 1]
+                d_in = [torch.zeros((hi - lo,) + tuple(h.shape[1:]), dtype=torch.float32, device=dev) for h in hs]
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    outs = self.forward_device(d_in)
+                    ex = on_chunk(d_in, getattr(self, "last", None)) if on_chunk is not None else None
+                d_ins.append(d_in)
+                graphs.append(g)
+                outs_all.append(outs)
+                extras.append(ex)
+        finally:
+            self._ws_override = None
         torch.cuda.synchronize()
-        return {"d_in": d_ins, "graphs": graphs, "outs": outs_all, "extra": extras}
+        return {"d_in": d_ins, "graphs": graphs, "outs": outs_all, "extra": extras, "ws": ws}
 
     def __call__(self, inputs, training=False):
         if training:
@@ -322,7 +368,7 @@ class AutoencoderModel(Model):
     def __init__(self, input_shape, seed: int = 0):
         super().__init__()
         self.input_shape = tuple(int(v) for v in input_shape)
-        self.weights = W.synthetic_autoencoder(seed=seed, channels=self.input_shape[2], keras_default=True)
+        self._default_weights = lambda: W.synthetic_autoencoder(seed=seed, channels=self.input_shape[2], keras_default=True)
 
     def _make_plan(self, precision):
         return Plan(_lib.PLAN_AUTOENCODER, self.weights, img_shape=(0, 0, self.input_shape[2]), precision=precision)
@@ -337,7 +383,7 @@ class AutoencoderModel(Model):
         plan = self.plan()
         y = torch.empty_like(x)
         y8 = torch.empty((b, h, w, c), dtype=torch.uint8, device=x.device) if want_u8 else None
-        ws = plan.workspace(b, h, w)
+        ws = self._workspace(plan, b, h, w)
         _lib.check(_lib.lib.cic_autoencoder_forward(plan.handle, ptr(x), ptr(y), ptr(y8), b, h, w, ptr(ws), ws.numel(),
                                                     runtime.stream_ptr()))
         return [y, y8] if want_u8 else [y]
@@ -354,7 +400,7 @@ class EncoderModel(Model):
         self.latent_dim = int(latent_dim)
         self.name = name
         self.add_attention = bool(add_attention)
-        self.weights = W.synthetic_encoder(self.img_shape, self.latent_dim, self.add_attention, seed, keras_default=True)
+        self._default_weights = lambda: W.synthetic_encoder(self.img_shape, self.latent_dim, self.add_attention, seed, keras_default=True)
 
     def _make_plan(self, precision):
         return Plan(_lib.PLAN_ENCODER, self.weights, self.img_shape, self.latent_dim, self.add_attention, precision)
@@ -371,7 +417,7 @@ class EncoderModel(Model):
         x2 = torch.empty((b, h // 4, w // 4, 128), dtype=torch.float32, device=dev)
         x3 = torch.empty((b, h // 8, w // 8, 256), dtype=torch.float32, device=dev)
         plan = self.plan()
-        ws = plan.workspace(b)
+        ws = self._workspace(plan, b)
         _lib.check(_lib.lib.cic_encoder_forward(plan.handle, ptr(x), ptr(lat), ptr(x1), ptr(x2), ptr(x3), b, ptr(ws),
                                                 ws.numel(), runtime.stream_ptr()))
         return [lat, x1, x2, x3]
@@ -385,7 +431,7 @@ class GeneratorModel(Model):
         self.img_shape = tuple(int(v) for v in img_shape)
         self.latent_dim = int(latent_dim)
         self.name = name
-        self.weights = W.synthetic_generator(self.latent_dim, self.img_shape, seed, keras_default=True)
+        self._default_weights = lambda: W.synthetic_generator(self.latent_dim, self.img_shape, seed, keras_default=True)
 
     def _make_plan(self, precision):
         return Plan(_lib.PLAN_GENERATOR, self.weights, self.img_shape, self.latent_dim, False, precision)
@@ -402,7 +448,7 @@ class GeneratorModel(Model):
                 raise ValueError(f"{self.name}: expected input shapes {want}, got {runtime.shapes_str(inputs)}")
         out = torch.empty((b, h, w, c), dtype=torch.float32, device=lat.device)
         plan = self.plan()
-        ws = plan.workspace(b)
+        ws = self._workspace(plan, b)
         _lib.check(_lib.lib.cic_generator_forward(plan.handle, ptr(lat), ptr(s1), ptr(s2), ptr(s3), ptr(out), b, ptr(ws),
                                                   ws.numel(), runtime.stream_ptr()))
         return [out]
@@ -415,7 +461,7 @@ class LatentSaliencyModel(Model):
         super().__init__()
         self.latent_dim = int(latent_dim)
         self.name = name
-        self.weights = W.synthetic_latent_saliency(self.latent_dim, seed, keras_default=True)
+        self._default_weights = lambda: W.synthetic_latent_saliency(self.latent_dim, seed, keras_default=True)
 
     def _make_plan(self, precision):
         return Plan(_lib.PLAN_SALIENCY, self.weights, (0, 0, 3), self.latent_dim, False, precision)
@@ -427,7 +473,7 @@ class LatentSaliencyModel(Model):
         b = lat.shape[0]
         out = torch.empty((b, 1), dtype=torch.float32, device=lat.device)
         plan = self.plan()
-        ws = plan.workspace(b)
+        ws = self._workspace(plan, b)
         _lib.check(_lib.lib.cic_saliency_forward(plan.handle, ptr(lat), ptr(out), b, ptr(ws), ws.numel(), runtime.stream_ptr()))
         return [out]
 
@@ -443,7 +489,7 @@ class RDOptimizerModel(Model):
         self.img_shape = tuple(int(v) for v in img_shape)
         self.latent_dims = latent_dims
         self.name = name
-        self.weights = W.synthetic_rd_optimizer(seed, keras_default=True)
+        self._default_weights = lambda: W.synthetic_rd_optimizer(seed, keras_default=True)
 
     def _make_plan(self, precision):
         return Plan(_lib.PLAN_RD, self.weights, self.img_shape, 0, False, precision)
@@ -462,7 +508,7 @@ class RDOptimizerModel(Model):
         bpp = bpp.reshape(-1).contiguous()
         out = torch.empty((b, 3), dtype=torch.float32, device=mask.device)
         plan = self.plan()
-        ws = plan.workspace(b)
+        ws = self._workspace(plan, b)
         _lib.check(_lib.lib.cic_rd_forward(plan.handle, ptr(mask), ptr(bpp), ptr(out), b, ptr(ws), ws.numel(), runtime.stream_ptr()))
         return [out]
 
@@ -498,7 +544,7 @@ class AdaptiveCompressionModel(Model):
         """Accepts {sub_model: {name: array}} (weights.synthetic_adaptive) and shares it with the sub-models."""
         for sub in self.SUBS:
             self.components[sub].set_weights_dict(w[sub])
-        self._plan = None
+        self._drop_plan()
 
     def get_weights_dict(self):
         return {sub: self.components[sub].weights for sub in self.SUBS}
@@ -507,29 +553,48 @@ class AdaptiveCompressionModel(Model):
         # sub-models may have had their weights replaced individually: rebuild when identities change
         ids = tuple(id(self.components[s].weights) for s in self.SUBS)
         if self._seen != ids:
-            self._plan = None
+            self._drop_plan()
             self._seen = ids
         return super().plan()
 
     def _make_plan(self, precision):
         return Plan(_lib.PLAN_ADAPTIVE, self._flat_weights(), self.img_shape, self.base_latent_dim, False, precision)
 
-    def forward_device(self, inputs, extras: bool = False):
-        if len(inputs) != 3:
-            raise ValueError("adaptive model takes [image, saliency, target_bpp]")
-        img, mask, bpp = inputs
+    # ---- geometry ------------------------------------------------------------------------------------------------------------
+    PADDING = "edge"   # how images that are not a multiple of the model tile are extended (SURVEY App. F): the last row / column
+                       # of the image is replicated into the ragged tiles on load, outputs are cropped on store
+
+    def tiles_per_image(self, h: int, w: int) -> int:
         T = self.img_shape[0]
+        return (-(-h // T)) * (-(-w // T))
+
+    def _check_inputs(self, img, mask, bpp):
         n, h, w, c = img.shape
-        if c != 3 or h % T or w % T:
-            raise ValueError(f"image must be (B, k*{T}, m*{T}, 3), got {tuple(img.shape)}")
+        if c != 3 or h < 1 or w < 1:
+            raise ValueError(f"image must be (B, H, W, 3), got {tuple(img.shape)}")
         if mask.dim() == 3:
             mask = mask.unsqueeze(-1)
         if tuple(mask.shape) != (n, h, w, 1):
             raise ValueError(f"saliency must be ({n},{h},{w},1), got {tuple(mask.shape)}")
-        bpp = bpp.reshape(-1).contiguous()
+        bpp = bpp.reshape(-1)
         if bpp.numel() != n:
             raise ValueError(f"target_bpp must have one value per image ({n}), got {bpp.numel()}")
-        nt = n * (h // T) * (w // T)
+        return mask, bpp
+
+    def forward_device(self, inputs, extras: bool = False):
+        """[image (n,H,W,3), saliency (n,H,W,1), target_bpp (n,)] on the device -> the five model outputs on the device.
+        H, W of any size: the image is coded as ceil(H/T) x ceil(W/T) independent tiles of the model size T (256 in the
+        reference, whose graph is fixed at that size: GAN_functions.py:242-248); ragged tiles replicate the image edge and are
+        cropped, dt / blend / hq_ratio cover the H x W pixels of the image only."""
+        if len(inputs) != 3:
+            raise ValueError("adaptive model takes [image, saliency, target_bpp]")
+        img, mask, bpp = inputs
+        if img.dim() != 4:
+            raise ValueError(f"image must be (B, H, W, 3), got {tuple(img.shape)}")
+        mask, bpp = self._check_inputs(img, mask, bpp)
+        bpp = bpp.contiguous()
+        n, h, w, c = img.shape
+        nt = n * self.tiles_per_image(h, w)
         dev = img.device
         base = self.base_latent_dim
         f32 = dict(dtype=torch.float32, device=dev)
@@ -562,7 +627,7 @@ class AdaptiveCompressionModel(Model):
             io.d_hq_scale, io.d_lq_scale = ptr(out["hq_scale"]), ptr(out["lq_scale"])
             io.d_hq_out, io.d_lq_out = ptr(out["hq_out"]), ptr(out["lq_out"])
         plan = self.plan()
-        ws = plan.workspace(n, h, w)
+        ws = self._workspace(plan, n, h, w)
         _lib.check(_lib.lib.cic_adaptive_forward(plan.handle, C.byref(io), n, h, w, ptr(ws), ws.numel(), runtime.stream_ptr()))
         self.last = out
         self._last_inputs = [img, mask, bpp]
@@ -573,14 +638,16 @@ class AdaptiveCompressionModel(Model):
     # ---- phased, pipelined predict -------------------------------------------------------------------------------------------
     def _phase_buffers(self, n, h, w, dev):
         """Persistent device buffers of predict_phased for one batch geometry: inputs, outputs and the batch-wide state."""
-        key = (n, h, w, id(self.plan()))
+        self.plan()
+        key = (n, h, w, self._plan_gen)
         cache = self.__dict__.setdefault("_phase_cache", {})
         if key in cache:
             return cache[key]
-        if len(cache) > 2:
+        if len(cache) > 1:                       # the graphs captured on the evicted buffers go with them
             cache.clear()
+            self.__dict__.pop("_phase_graphs", None)
         T, base = self.img_shape[0], self.base_latent_dim
-        tpi = (h // T) * (w // T)
+        tpi = self.tiles_per_image(h, w)
         nt = n * tpi
         f32 = dict(dtype=torch.float32, device=dev)
         bf = dict(dtype=torch.bfloat16, device=dev)
@@ -604,7 +671,7 @@ class AdaptiveCompressionModel(Model):
         cache[key] = b
         return b
 
-    def _phase_call(self, b, phase, lo, hi, h, w):
+    def _phase_call(self, b, phase, lo, hi, h, w, want_dt=True):
         """One cic_adaptive_forward_phase call on images [lo, hi) of the persistent buffers (LATENT: the whole batch)."""
         io = _lib.cic_adaptive_io()
         tpi = b["tpi"]
@@ -618,21 +685,28 @@ class AdaptiveCompressionModel(Model):
             if phase == _lib.PHASE_ENCODE:
                 io.d_rd_params = ptr(b["rd_params"][tile0:hi * tpi])
             else:
-                io.d_blended, io.d_dt = ptr(b["blended"][lo:hi]), ptr(b["dt"][lo:hi])
+                io.d_blended = ptr(b["blended"][lo:hi])
+                io.d_dt = ptr(b["dt"][lo:hi]) if want_dt else None
                 io.d_hq_ratio_sum = ptr(b["hq_ratio_sum"][lo:hi])
         plan = self.plan()
-        ws = plan.workspace(hi - lo, h, w)
+        ws = self._workspace(plan, hi - lo, h, w)
         _lib.check(_lib.lib.cic_adaptive_forward_phase(plan.handle, C.byref(io), C.byref(b["state"]), phase, tile0, hi - lo, h, w,
                                                        ptr(ws), ws.numel(), runtime.stream_ptr()))
 
-    def predict_phased(self, x, enc_chunks=None, dec_chunks=None, on_chunk=None, u8_io: bool = False):
-        """predict_pipelined with the forward cut into three phases (include/cic.h): the encoder convolutions run per upload chunk
-        while the next chunk's host->device copy is in flight, the Dense / saliency / quantiser phase runs once on the whole batch
-        (its 1.2 GB of Dense weights are streamed once instead of once per chunk), and the decoders run per download chunk while the
-        previous chunk's outputs travel to pinned host buffers.  Same results as predict().  `on_chunk(device_inputs, outputs)` runs
-        on the compute stream after every decode chunk.  Returns (host outputs, [on_chunk results]).
-        u8_io=True: the image is uint8 RGB and is normalised on the device ((u8 - 127.5) / 127.5, GAN_functions.py:31-37), the
-        blended output comes back as uint8 (((x + 1) * 127.5).astype(uint8), :41-50): 1 instead of 4 bytes per sample over PCIe."""
+    def predict_phased(self, x, enc_chunks=None, dec_chunks=None, on_chunk=None, u8_io: bool = False, want_dt: bool = True):
+        """predict() for host batches at full throughput: the forward is cut into three phases (include/cic.h): the encoder
+        convolutions run per upload chunk while the next chunk's host->device copy is in flight, the Dense / saliency /
+        quantiser phase runs once on the whole batch (its 1.2 GB of Dense weights are streamed once instead of once per
+        chunk), and the decoders run per download chunk while the previous chunk's outputs travel to pinned host buffers.
+        Same results as predict().  `on_chunk(device_inputs, outputs)` runs on the compute stream after every decode chunk.
+        Returns (host outputs, [on_chunk results]); the host outputs are views of pinned buffers the next call overwrites.
+
+        u8_io=True: the reference's file-boundary pixel format on the wire.  The image is uint8 RGB and is normalised on the
+        device ((u8 - 127.5) / 127.5: load_and_preprocess_image, GAN_functions.py:31-37), the blended output comes back as uint8
+        (((x + 1) * 127.5).astype(uint8): save_image, :41-50): 1 instead of 4 bytes per sample over PCIe.  on_chunk still sees
+        the float32 tensors, so PSNR / SSIM are the reference's (computed before the uint8 cast, GAN_test.py:297-300).
+        want_dt=False: the bit-allocation map is not downloaded; the fifth host output is hq_ratio = mean(dt) per image
+        (float64, (n,)) - all GAN_test.py:312,573 take from it."""
         xs = runtime.as_list(x)
         hs = [t if isinstance(t, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(t)) for t in xs]
         if len(hs) != 3:
@@ -641,17 +715,10 @@ class AdaptiveCompressionModel(Model):
             raise ValueError("u8_io=True takes a uint8 image")
         hs = [t if (t.dtype == torch.float32 or (u8_io and k == 0)) else t.to(torch.float32) for k, t in enumerate(hs)]
         img, mask, bpp = hs
-        T = self.img_shape[0]
+        if img.dim() != 4:
+            raise ValueError(f"image must be (B, H, W, 3), got {tuple(img.shape)}")
+        mask, bpp = self._check_inputs(img, mask, bpp)
         n, h, w, c = img.shape
-        if c != 3 or h % T or w % T:
-            raise ValueError(f"image must be (B, k*{T}, m*{T}, 3), got {tuple(img.shape)}")
-        if mask.dim() == 3:
-            mask = mask.unsqueeze(-1)
-        if tuple(mask.shape) != (n, h, w, 1):
-            raise ValueError(f"saliency must be ({n},{h},{w},1), got {tuple(mask.shape)}")
-        bpp = bpp.reshape(-1)
-        if bpp.numel() != n:
-            raise ValueError(f"target_bpp must have one value per image ({n}), got {bpp.numel()}")
 
         def bounds_of(sizes, default):
             sizes = [int(v) for v in (sizes if sizes is not None else default) if int(v) > 0]
@@ -666,6 +733,7 @@ class AdaptiveCompressionModel(Model):
         db = bounds_of(dec_chunks, default[::-1])
         dev = runtime.require_cuda()
         b = self._phase_buffers(n, h, w, dev)
+        plan = self.plan()
         compute = torch.cuda.current_stream()
         st = self.__dict__.setdefault("_pipe_streams", {})
         if "in" not in st:
@@ -677,7 +745,7 @@ class AdaptiveCompressionModel(Model):
         names = ["blended", "hq_latent_q", "lq_latent_q", "rd_params", "dt"]
         host = []
         for k in names:
-            src = b["blended_u8"] if (u8_io and k == "blended") else b[k]
+            src = b["blended_u8"] if (u8_io and k == "blended") else (b["hq_ratio_sum"] if (k == "dt" and not want_dt) else b[k])
             key = ("phased", k, tuple(src.shape), src.dtype)
             if key not in stage:
                 stage[key] = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
@@ -690,29 +758,35 @@ class AdaptiveCompressionModel(Model):
             self._phase_call(b, _lib.PHASE_ENCODE, lo, hi, h, w)
 
         def decode(lo, hi):
-            self._phase_call(b, _lib.PHASE_DECODE, lo, hi, h, w)
+            self._phase_call(b, _lib.PHASE_DECODE, lo, hi, h, w, want_dt)
             ex = None
             if on_chunk is not None:
                 ex = on_chunk([b["img"][lo:hi], b["mask"][lo:hi], b["bpp"][lo:hi]],
-                              {"blended": b["blended"][lo:hi], "dt": b["dt"][lo:hi], "hq_ratio_sum": b["hq_ratio_sum"][lo:hi]})
+                              {"blended": b["blended"][lo:hi], "dt": b["dt"][lo:hi] if want_dt else None,
+                               "hq_ratio_sum": b["hq_ratio_sum"][lo:hi]})
             if u8_io:
                 _lib.check(_lib.lib.cic_f32_signed_to_u8(ptr(b["blended"][lo:hi]), ptr(b["blended_u8"][lo:hi]), (hi - lo) * h * w * 3,
                                                          runtime.stream_ptr()))
             return ex
         # CUDA graphs: the first call with a chunking runs eagerly, the second captures one graph per phase call (persistent
-        # buffers make them replayable), later calls replay.  CIC_PIPE_GRAPHS=0 keeps the eager path.
-        gkey = (tuple(eb), tuple(db), n, h, w, id(on_chunk), id(self.plan()), bool(u8_io))
+        # buffers + a private scratch buffer make them replayable), later calls replay.  The cache entry owns everything whose
+        # address the graphs bake in, and is keyed by the plan generation, so a rebuilt plan can never meet an old graph.
+        gkey = (tuple(eb), tuple(db), n, h, w, id(on_chunk), self._plan_gen, bool(u8_io), bool(want_dt))
         gstate = self.__dict__.setdefault("_phase_graphs", {})
         gs = gstate.get(gkey)
         if gs is None:
-            if len(gstate) > 4:
+            if len(gstate) > 1:
                 gstate.clear()
-            gs = gstate[gkey] = {"calls": 0}
+            gs = gstate[gkey] = {"calls": 0, "on_chunk": on_chunk, "buffers": b}
         gs["calls"] += 1
-        use_graphs = os.environ.get("CIC_PIPE_GRAPHS", "1") != "0"
+        use_graphs = runtime.use_cuda_graphs()
         if use_graphs and gs["calls"] >= 2 and "enc" not in gs and not gs.get("failed"):
             try:
                 torch.cuda.synchronize()
+                sizes = [eb[i + 1] - eb[i] for i in range(len(eb) - 1)] + [db[i + 1] - db[i] for i in range(len(db) - 1)] + [n]
+                need = max(plan.workspace_bytes(v, h, w) for v in set(sizes))
+                gs["ws"] = torch.empty(max(need, 1 << 20), dtype=torch.uint8, device=dev)
+                self._ws_override = gs["ws"]
                 enc, dec, extra_g = [], [], []
                 for i in range(len(eb) - 1):
                     g = torch.cuda.CUDAGraph()
@@ -733,11 +807,14 @@ class AdaptiveCompressionModel(Model):
                 gs.update({"enc": enc, "lat": lat, "dec": dec, "extra": extra_g})
             except Exception as e:  # noqa: BLE001
                 gs["failed"] = True
+                gs.pop("ws", None)
                 torch.cuda.synchronize()
                 print(f"predict_phased: CUDA graph capture failed ({e!r}); using eager launches", file=sys.stderr)
+            finally:
+                self._ws_override = None
         graphs = gs if "enc" in gs else None
         # uploads: all queued up front on the copy-in stream
-        timeline = os.environ.get("CIC_PIPE_TIMELINE") == "1"            # debug: event times of the three streams
+        timeline = runtime.pipe_timeline()                               # debug: event times of the three streams
         ev_in = [torch.cuda.Event(enable_timing=timeline) for _ in range(len(eb) - 1)]
         marks = []
         if timeline:
@@ -791,7 +868,7 @@ class AdaptiveCompressionModel(Model):
             with torch.cuda.stream(s_out):
                 s_out.wait_event(ev_c)
                 host[0][lo:hi].copy_((b["blended_u8"] if u8_io else b["blended"])[lo:hi], non_blocking=True)
-                host[4][lo:hi].copy_(b["dt"][lo:hi], non_blocking=True)
+                host[4][lo:hi].copy_((b["dt"] if want_dt else b["hq_ratio_sum"])[lo:hi], non_blocking=True)
                 mark(f"out{hi - lo}", s_out)
         compute.wait_stream(s_out)
         s_out.synchronize()
@@ -799,4 +876,7 @@ class AdaptiveCompressionModel(Model):
             torch.cuda.synchronize()
             print("phase timeline (ms since start): in " + " ".join(f"{ev_t0.elapsed_time(e):.2f}" for e in ev_in) + " | " +
                   "  ".join(f"{nm} {ev_t0.elapsed_time(e):.2f}" for nm, e in marks), file=sys.stderr)
-        return [t.numpy() for t in host], extra
+        res = [t.numpy() for t in host]
+        if not want_dt:
+            res[4] = res[4] / float(h * w)
+        return res, extra

@@ -77,8 +77,28 @@ class Workspace:
         cls._bufs.clear()
 
 
-def launch_count_reset() -> None:
-    pass
+_use_graphs = True
+_pipe_timeline = False
+
+
+def set_cuda_graphs(on: bool) -> None:
+    """predict_pipelined / predict_phased replay CUDA graphs from their third call with one chunking (default on)."""
+    global _use_graphs
+    _use_graphs = bool(on)
+
+
+def use_cuda_graphs() -> bool:
+    return _use_graphs
+
+
+def set_pipe_timeline(on: bool) -> None:
+    """Print the per-chunk event times of the copy-in / compute / copy-out streams of the pipelined predicts (debugging)."""
+    global _pipe_timeline
+    _pipe_timeline = bool(on)
+
+
+def pipe_timeline() -> bool:
+    return _pipe_timeline
 
 
 def as_list(x) -> list:

@@ -21,6 +21,7 @@ import numpy as np
 BN_EPS = 1e-3  # Keras BatchNormalization default epsilon
 
 Weights = Dict[str, np.ndarray]
+_SHAPES_ONLY = False
 
 
 def _glorot(rng: np.random.Generator, shape: Tuple[int, ...]) -> np.ndarray:
@@ -30,6 +31,8 @@ def _glorot(rng: np.random.Generator, shape: Tuple[int, ...]) -> np.ndarray:
     else:
         receptive = int(np.prod(shape[:-2]))
         fan_in, fan_out = shape[-2] * receptive, shape[-1] * receptive
+    if _SHAPES_ONLY:   # check_adaptive wants the shape table only: a zero-stride view, no memory, no RNG
+        return np.broadcast_to(np.zeros((), np.float32), shape)
     limit = np.sqrt(6.0 / (fan_in + fan_out))
     # generate in float32 blocks to bound memory for the 131072 x 1024 Dense kernels
     out = rng.random(size=shape, dtype=np.float32)
@@ -214,9 +217,20 @@ def load_npz(path: str) -> Dict[str, Weights]:
         return unflatten({k: f[k] for k in f.files})
 
 
+def adaptive_shapes(img_shape, base_latent_dim: int) -> Dict[str, Weights]:
+    """{sub_model: {name: zero-stride array of the expected shape}} of an adaptive-model checkpoint, without allocating or
+    drawing the ~1.7 GB of Keras-default weights (the builders run with their kernel initialiser replaced by a shape stub)."""
+    global _SHAPES_ONLY
+    _SHAPES_ONLY = True
+    try:
+        return synthetic_adaptive(img_shape, base_latent_dim, keras_default=True)
+    finally:
+        _SHAPES_ONLY = False
+
+
 def check_adaptive(nested: Dict[str, Weights], img_shape, base_latent_dim: int) -> None:
     """Raise ValueError naming the first missing / extra / mis-shaped tensor of an adaptive-model checkpoint."""
-    want = synthetic_adaptive(img_shape, base_latent_dim, keras_default=True)
+    want = adaptive_shapes(img_shape, base_latent_dim)
     for sub, ws in want.items():
         if sub not in nested:
             raise ValueError(f"checkpoint has no sub-model '{sub}'")

@@ -1,26 +1,38 @@
 #!/usr/bin/env python
-"""Headline benchmark: encode + quantise + decode MPix/s of the contextual (adaptive GAN) codec.
+"""Benchmark of the learned-compression inference hot path: encode + quantise + decode MPix/s.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision tc|fp32]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c1|c2|c3|c4|c5] [--no-extra-configs]
 
-Workload (BASELINE.json configs[1]): batch of 64 synthetic 512x512 RGB images per GPU, coded as 256
-tiles of 256x256 by the adaptive model of build_adaptive_compression_model (HQ + LQ encoder, latent
-saliency, quantiser, two generators, ROI blend) followed by the PSNR/SSIM/bpp evaluation.  One "step" is
-one pass over that batch.  N > 1 (torchrun, one rank per GPU): every rank codes its own 64 images
-(weak scaling, no data-path collective); the only exchange is the all-reduce of the metric sums, inside
-the timed region.  One JSON line is printed by rank 0.
+Configs (BASELINE.json `configs`):
+  c1  build_autoencoder on 32 synthetic 256x256 images + uint8 cast + calculate_mse/psnr/ssim (test_autoencoder.py:83-108)
+  c2  adaptive GAN codec, 64 x 512x512 images per GPU = 256 tiles of 256x256, target bpp 1.0  <- headline (default)
+  c3  ROI / rate sweep on 1024x1024 images (16 tiles each) over linspace(0.1, 2.0, 10) + {0.1, 1.0, 2.0} (GAN_test.py:532-645)
+  c4  1080p (1920x1080 = 40 tiles / frame), 256 frames in total over the N GPUs (STRONG scaling), metric all-reduce timed
+  c5  4K (3840x2160 = 135 tiles / image), 32 images per GPU (256 on 8 GPUs), per-image PSNR / SSIM
+The default run prints ONE JSON line whose top level is c2 (the headline, continuous with earlier rounds) and whose `configs`
+key holds a short measurement of c1, c3, c4 and c5; `--config cX` makes cX the top level instead.
 
-`value`  : MPix/s with inputs resident in HBM, timed with CUDA events on the launch stream.
-`e2e`    : same metric through the public API (adaptive_model.predict_phased, or predict_pipelined with --e2e-mode pipelined)
-           with pinned HOST buffers, i.e. host->device copy of images/masks/bpp and device->host read of every model output
-           per step, overlapped with the kernels chunk by chunk.
-`roofline`: the conv/dense GEMM kernels (dominant), algorithmic FLOPs / summed per-layer device time
-           (CUDA events recorded around every layer inside the timed steps) against the measured bf16 peak.
-`cpu_baseline`: the CPU oracle (torch fp32 restatement of the reference graph) on a bounded sample.
+One "step" = one pass of the codec + its PSNR/SSIM/bpp evaluation over the config's batch.  N > 1 (torchrun, one rank per GPU):
+images are sharded over the ranks, weights replicated, no data-path collective; the only exchange is the all-reduce of the
+metric sums, inside the timed region.
+
+`value`        MPix/s with inputs resident in HBM, CUDA events on the launch stream, max over ranks.
+`e2e`          same metric through the public API with pinned HOST buffers: adaptive_model.predict_phased(u8_io=True) - the
+               reference's file-boundary pixel format on the wire (uint8 RGB image up: load_and_preprocess_image,
+               GAN_functions.py:24-39; uint8 reconstruction down: save_image, :41-50) - host->device copy of image / mask / bpp and
+               device->host read of all five model outputs every step, overlapped chunk by chunk.  `e2e_f32_io` is the same with
+               float32 images both ways (the headline of round 1).  `host_copy_floor_ms`: the same bytes moved by plain concurrent
+               copies with no kernel running, all ranks at once - the ceiling the host side sets.
+`roofline`     the dominant kernel class: algorithmic FLOPs of its layers / their summed device time (CUDA events around every
+               launch inside the timed steps) against the measured sustained bf16 peak; `hbm_kernels` the bandwidth kernels.
+`parity`       GPU outputs of this very run against the CPU oracle on sampled tiles: symbol mismatches (total / outside the 1e-3
+               band), max-abs reconstruction error, PSNR / SSIM / actual-bpp deltas.
+`cpu_baseline` the CPU oracle (torch fp32 restatement of the reference graph) on a bounded sample.
 """
 from __future__ import annotations
 
 import argparse
+import importlib.util
 import json
 import os
 import sys
@@ -32,13 +44,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-IMG_HW = 512
-IMGS_PER_GPU = 64
 TILE = 256
 BASE_LATENT = 512
-TARGET_BPP = 1.0
-FLOP_PER_TILE = 23.818e9          # SURVEY.md §8(d): algorithmic FLOPs of the adaptive model per 256x256 tile
+FLOP_PER_TILE = 23.818e9          # SURVEY.md 8(d): algorithmic FLOPs of the adaptive model per 256x256 tile
+AE_FLOP_PER_PIXEL = 74304.0
 METRIC = "encode+quantize+decode MPix/s"
+SWEEP_LEVELS = sorted(set(np.round(np.linspace(0.1, 2.0, 10), 6).tolist() + [0.1, 1.0, 2.0]))   # 10 distinct + dups
 
 
 def measured_peaks():
@@ -48,6 +59,15 @@ def measured_peaks():
         return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d["bf16_tflops_sustained"],
                 "source": "measured"}
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def pure_module(name: str):
+    """synth.py / weights.py of the package are pure numpy; loading them by path does NOT import the package, so the reference
+    arm never maps libcic.so."""
+    spec = importlib.util.spec_from_file_location(f"cic_pure_{name}", os.path.join(ROOT, "contextual-image-compression_b200", f"{name}.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
 
 
 _SAMPLER_SRC = r"""
@@ -113,69 +133,658 @@ class ClockSampler:
         return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(inside)}
 
 
-def make_inputs(rank: int, n_img: int):
-    from cic_b200 import synth
+# ---- workloads -------------------------------------------------------------------------------------------------------------------
+# name -> geometry.  `pool`: distinct synthetic images generated per rank; batches larger than the pool cycle through it (every image
+# is coded in full every time - only the pixel data repeats), which keeps host-side input generation out of the run time.
+CONFIGS = {
+    "c1": dict(kind="ae", h=256, w=256, images=32, scaling="weak", baseline="configs[0]",
+               what="build_autoencoder + uint8 cast + calculate_mse/psnr/ssim on 32 x 256x256 images per GPU"),
+    "c2": dict(kind="gan", h=512, w=512, images=64, chunk=64, pool=64, bpp=1.0, scaling="weak", baseline="configs[1]",
+               what="adaptive GAN codec (build_adaptive_compression_model), 64 x 512x512 images per GPU = 256 tiles of 256x256, target bpp 1.0"),
+    "c3": dict(kind="sweep", h=1024, w=1024, images=4, scaling="weak", baseline="configs[2]",
+               what="ROI-mask mixed-rate sweep: 4 x 1024x1024 images per GPU (16 tiles each) x 11 target-bpp levels "
+                    "(linspace(0.1, 2.0, 10) + 1.0), encoders once, quantiser + generators + blend + PSNR/SSIM per level"),
+    "c4": dict(kind="gan", h=1080, w=1920, images_total=256, chunk=8, pool=8, bpp=1.0, scaling="strong", baseline="configs[3]",
+               what="adaptive GAN codec on 1920x1080 frames (40 tiles of 256x256 each, last tile row edge-replicated), 256 frames in "
+                    "total sharded over the GPUs, metric all-reduce in the timed region"),
+    "c5": dict(kind="gan", h=2160, w=3840, images=32, chunk=4, pool=2, bpp=1.0, scaling="weak", baseline="configs[4]",
+               what="adaptive GAN codec on 3840x2160 images (135 tiles of 256x256 each), 32 images per GPU (256 on 8 GPUs), per-image PSNR/SSIM"),
+}
+
+
+def tiles_per_image(h, w):
+    return (-(-h // TILE)) * (-(-w // TILE))
+
+
+def gan_inputs(synth, rank: int, n_img: int, h: int, w: int, bpp: float, seed_off: int):
     first = rank * n_img
-    img = synth.to_signed_range(synth.synth_images_u8(n_img, IMG_HW, IMG_HW, seed=synth.SEED_BASE + 1, first_index=first))
-    mask = synth.synth_masks(n_img, IMG_HW, IMG_HW, seed=synth.SEED_BASE + 1, first_index=first)
-    bpp = np.full((n_img, 1), TARGET_BPP, np.float32)
-    return img, mask, bpp
+    img_u8 = synth.synth_images_u8(n_img, h, w, seed=synth.SEED_BASE + seed_off, first_index=first)
+    mask = synth.synth_masks(n_img, h, w, seed=synth.SEED_BASE + seed_off, first_index=first)
+    return img_u8, synth.to_signed_range(img_u8), mask, np.full((n_img, 1), bpp, np.float32)
 
 
-def tiles_of(a, c):
-    n = a.shape[0]
-    t = IMG_HW // TILE
-    return a.reshape(n, t, TILE, t, TILE, c).transpose(0, 1, 3, 2, 4, 5).reshape(-1, TILE, TILE, c)
-
-
-def cpu_oracle_rate(weights, img, mask, bpp, n_tiles: int, reps: int = 1):
-    """MPix/s of the CPU oracle (torch fp32, all host threads) on the first n_tiles tiles of the workload."""
+# ---- reference arm ---------------------------------------------------------------------------------------------------------------
+def cpu_oracle_step(weights, img, mask, bpp, tiles=None):
+    """One pass of the CPU oracle over (some tiles of) a GAN-codec batch + compute_metrics on every coded tile.  Returns seconds,
+    tiles coded."""
     import torch
-    from oracle import graphs, metrics
+    from oracle import metrics, tiling
     torch.set_num_threads(os.cpu_count() or 1)
-    ti, tm = tiles_of(img, 3)[:n_tiles], tiles_of(mask, 1)[:n_tiles]
-    tb = np.repeat(bpp.reshape(-1), (IMG_HW // TILE) ** 2)[:n_tiles].reshape(-1, 1)
-    best = None
-    for _ in range(reps):
-        t0 = time.perf_counter()
-        outs = graphs.adaptive_forward(weights, ti, tm, tb)
-        for k in range(min(n_tiles, 4)):
-            metrics.compute_metrics(ti[k], outs[0][k])
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    return n_tiles * TILE * TILE / best / 1e6, best
+    t0 = time.perf_counter()
+    ref = tiling.adaptive_forward_tiled(weights, img, mask, bpp, TILE, tiles=tiles)
+    for k in range(len(ref["tiles"])):
+        metrics.compute_metrics(ref["img_tiles"][k], ref["blended"][k])
+    return time.perf_counter() - t0, len(ref["tiles"]), ref
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU path (its TensorFlow stack is not installable here, so the
-    oracle port of the same graph) timed on the host cores; rank 0 only."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    """--impl reference: the reference's CPU path timed on the host cores, rank 0 only.  The reference's own stack (TensorFlow /
+    Keras, scikit-image) is not installable in this image, so this is the oracle port of the same graph (`kind: "port"`), on the
+    SAME config as the product arm: every tile of the batch is coded and evaluated each step, unless that would take more than
+    ~5 minutes for warmup + steps - then a whole-image sample is timed and the line says `extrapolated: true`."""
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    import importlib
-    W = importlib.import_module("contextual-image-compression_b200.weights")
     import torch
-    n_tiles = 8
-    img, mask, bpp = make_inputs(0, n_tiles // 4)
-    weights = W.synthetic_adaptive((TILE, TILE, 3), BASE_LATENT, seed=42)
+    synth, W = pure_module("synth"), pure_module("weights")
+    cfg_name = args.config
+    cfg = CONFIGS[cfg_name]
     cores = os.cpu_count() or 1
+    budget_s = float(os.environ.get("CIC_REF_BUDGET_S", "300"))
+    if cfg["kind"] == "ae":
+        from oracle import graphs, metrics
+        torch.set_num_threads(cores)
+        w = W.synthetic_autoencoder(seed=42)
+        x = synth.to_unit_range(synth.synth_images_u8(cfg["images"], cfg["h"], cfg["w"], seed=synth.SEED_BASE))
+
+        def step():
+            t0 = time.perf_counter()
+            for i in range(x.shape[0]):                           # the batch-1 loop of test_autoencoder.py:83-108
+                y = graphs.autoencoder_forward(w, x[i:i + 1])
+                y8, x8 = graphs.autoencoder_output_u8(y)[0], (x[i] * 255).astype(np.uint8)
+                metrics.ae_calculate_mse(x8, y8), metrics.ae_calculate_psnr(x8, y8), metrics.ae_calculate_ssim(x8, y8)
+            return time.perf_counter() - t0
+        px, sample, extrapolated = x.shape[0] * cfg["h"] * cfg["w"], f"all {x.shape[0]} images per step (batch-1 loop)", False
+    else:
+        n_img = cfg.get("images", cfg.get("images_total"))
+        weights = W.synthetic_adaptive((TILE, TILE, 3), BASE_LATENT, seed=42)
+        pool = min(n_img, cfg.get("pool", n_img))
+        _, img, mask, bpp = gan_inputs(synth, 0, pool, cfg["h"], cfg["w"], cfg.get("bpp", 1.0), 1)
+        tpi = tiles_per_image(cfg["h"], cfg["w"])
+        levels = len(SWEEP_LEVELS) if cfg["kind"] == "sweep" else 1
+        t_probe, _, _ = cpu_oracle_step(weights, img[:1], mask[:1], bpp[:1], tiles=np.arange(min(4, tpi)))   # also the warm-up of the threads
+        per_tile = t_probe / min(4, tpi)
+        full_s = per_tile * tpi * n_img * levels
+        n_steps = args.steps + args.warmup
+        imgs_per_step = n_img
+        if full_s * n_steps > budget_s:
+            imgs_per_step = max(1, int(budget_s / n_steps / (per_tile * tpi * levels)))
+        extrapolated = imgs_per_step < n_img
+        imgs_per_step = min(imgs_per_step, pool) if extrapolated else imgs_per_step
+
+        def step():
+            tot = 0.0
+            done = 0
+            while done < imgs_per_step:                           # batches beyond the pool cycle through it, like the product arm
+                k = min(pool, imgs_per_step - done)
+                for _ in range(levels):
+                    tot += cpu_oracle_step(weights, img[:k], mask[:k], bpp[:k])[0]
+                done += k
+            return tot
+        px = imgs_per_step * cfg["h"] * cfg["w"] * levels
+        sample = (f"{imgs_per_step} of {n_img} images per step ({imgs_per_step * tpi} tiles of 256x256"
+                  f"{', x ' + str(levels) + ' bpp levels' if levels > 1 else ''}), every tile coded and evaluated")
     for _ in range(args.warmup):
-        cpu_oracle_rate(weights, img, mask, bpp, n_tiles)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        cpu_oracle_rate(weights, img, mask, bpp, n_tiles)
-    dt = (time.perf_counter() - t0) / args.steps
-    val = n_tiles * TILE * TILE / dt / 1e6
+        step()
+    secs = [step() for _ in range(args.steps)]
+    dt = float(np.mean(secs))
+    val = px / dt / 1e6
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "MPix/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "adaptive GAN codec, 512x512 images as 256x256 tiles, bpp 1.0 (BASELINE configs[1])",
-                       "sample": f"{n_tiles} tiles ({n_tiles // 4} images) per step", "l2": "n/a (CPU)"},
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "extrapolated": bool(extrapolated),
+            "config": {"workload": f"{cfg['what']} (BASELINE {cfg['baseline']})", "name": cfg_name, "sample": sample, "l2": "n/a (CPU)"},
             "cpu_baseline": {"value": val, "unit": "MPix/s", "cores": cores, "kind": "port",
-                             "sample": f"{n_tiles} tiles of 256x256 per step, torch {torch.__version__} CPU fp32 oracle, {cores} threads"},
+                             "sample": f"{sample}; torch {torch.__version__} CPU fp32 oracle of the reference graph, {cores} threads "
+                                       f"(the reference's TensorFlow stack is not installable here)"},
             "e2e": {"value": val, "unit": "MPix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+
+
+# ---- product arm -----------------------------------------------------------------------------------------------------------------
+KINDS = {0: "other", 1: "tc_gemm_kernel", 2: "tc_conv_kernel", 3: "conv1_tc_kernel", 4: "direct_conv_kernel", 5: "igemm_f32_kernel",
+         6: "conv_rows_tc_kernel", 7: "tc_gemm2_kernel", 8: "attn_fused_kernel", 9: "gen_tail_kernel"}
+
+
+class Bench:
+    def __init__(self, args):
+        import torch
+        import cic_b200 as cic
+        self.torch, self.cic, self.args = torch, cic, args
+        self.rank, self.world = cic.dist.init()
+        local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+        self.dev = torch.device("cuda", local_rank if self.world > 1 else torch.cuda.current_device())
+        torch.cuda.set_device(self.dev)
+        self.numa_cpus = cic.dist.bind_to_gpu_numa_node(self.dev.index or 0) if self.world > 1 else 0
+        cic.set_precision(args.precision)
+        self.peaks = measured_peaks()
+        cuda_idx = self.dev.index if self.dev.index is not None else 0
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        if vis and all(v.strip().isdigit() for v in vis.split(",")) and cuda_idx < len(vis.split(",")):
+            cuda_idx = int(vis.split(",")[cuda_idx])
+        self.nvml_idx = cuda_idx
+        self._gan = None
+        self.fast_ssim = args.ssim == "fast"
+        self.launches = 0
+
+    # -- models ------------------------------------------------------------------------------------------------------------------
+    def gan(self):
+        if self._gan is None:
+            import GAN_functions as gf
+            weights = self.cic.weights.synthetic_adaptive((TILE, TILE, 3), BASE_LATENT, seed=42)
+            models = gf.build_adaptive_compression_model((TILE, TILE, 3), BASE_LATENT, target_bpp=True)
+            models["adaptive_model"].set_weights_dict(weights)
+            self._gan = (models["adaptive_model"], weights)
+        return self._gan
+
+    # -- timing ------------------------------------------------------------------------------------------------------------------
+    def timed(self, fn, steps, warmup, sampler=None, wall=False):
+        """ms per step of fn(): W untimed calls, barrier + synchronize, K calls between CUDA events, synchronize + barrier; max
+        over ranks.  wall=True also takes the host clock (legs that end with a host synchronisation) and returns the larger."""
+        torch, cic = self.torch, self.cic
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        cic.dist.barrier()
+        torch.cuda.synchronize()
+        if sampler is not None:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        last = None
+        for _ in range(steps):
+            last = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        host_ms = (time.perf_counter() - t0) * 1e3 / steps
+        cic.dist.barrier()
+        ms = e0.elapsed_time(e1) / steps
+        if wall:
+            ms = max(ms, host_ms)
+        return cic.dist.max_over_ranks(ms, device=self.dev), last
+
+    def host_copy_floor(self, h2d_bytes: int, d2h_bytes: int, reps: int = 5):
+        """ms to move the e2e leg's bytes with plain copies and nothing else: one pinned->device and one device->pinned copy of
+        those sizes running concurrently on two streams, every rank at the same time (they share the host's memory and PCIe
+        root), max over ranks.  No kernel of the codec can make the end-to-end leg faster than this."""
+        torch, cic = self.torch, self.cic
+        hi = torch.empty(max(h2d_bytes, 1), dtype=torch.uint8, pin_memory=True)
+        ho = torch.empty(max(d2h_bytes, 1), dtype=torch.uint8, pin_memory=True)
+        di = torch.empty(max(h2d_bytes, 1), dtype=torch.uint8, device=self.dev)
+        do = torch.empty(max(d2h_bytes, 1), dtype=torch.uint8, device=self.dev)
+        s1, s2 = torch.cuda.Stream(device=self.dev), torch.cuda.Stream(device=self.dev)
+
+        def once():
+            with torch.cuda.stream(s1):
+                di.copy_(hi, non_blocking=True)
+            with torch.cuda.stream(s2):
+                ho.copy_(do, non_blocking=True)
+            s1.synchronize()
+            s2.synchronize()
+        once()
+        torch.cuda.synchronize()
+        cic.dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            once()
+        ms = (time.perf_counter() - t0) * 1e3 / reps
+        cic.dist.barrier()
+        return cic.dist.max_over_ranks(ms, device=self.dev)
+
+    # -- per-kernel accounting ----------------------------------------------------------------------------------------------------
+    def roofline_from_profile(self, prof, ms_step_scale: float = 1.0):
+        """prof: rows of Plan.profile() for one forward call.  Dominant kernel class = largest share of the device time."""
+        peaks, args = self.peaks, self.args
+        by_kind = {}
+        for name, ms, fl, by, kind in prof:
+            k = by_kind.setdefault(KINDS.get(kind, "other"), {"ms": 0.0, "flops": 0.0, "launches": 0})
+            k["ms"] += ms
+            k["flops"] += fl
+            k["launches"] += 1
+        gemm_ms = sum(ms for name, ms, fl, by, kind in prof if fl > 0)
+        gemm_flops = sum(fl for name, ms, fl, by, kind in prof if fl > 0)
+        cand = [k for k in by_kind if k != "other"]
+        dom = max(cand, key=lambda k: by_kind[k]["ms"]) if cand else "other"
+        dom_ms, dom_flops = by_kind.get(dom, {"ms": 0.0})["ms"], by_kind.get(dom, {"flops": 0.0})["flops"]
+        achieved = dom_flops / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
+        # executed tensor-core FLOPs of the same launches: the encoder chain issues three MMAs per algorithmic MAC (split-bf16);
+        # reported next to the algorithmic figure, never instead of it
+        dom_exec = sum(fl * (3.0 if (args.precision == "tc" and ("_enc/" in name)) else 1.0)
+                       for name, ms, fl, by, kind in prof if KINDS.get(kind, "other") == dom)
+        executed = dom_exec / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
+        peak = peaks["bf16_tflops_sustained"]
+        total_ms = sum(ms for name, ms, fl, by, kind in prof)
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")      # dram bytes per C2 step of each kernel class, ncu --set full
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(dom, {}).get("dram_bytes_per_step")
+        return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+                "traffic": traffic,
+                "kernel": f"{dom} ({by_kind.get(dom, {}).get('launches', 0)} launches per forward call; algorithmic FLOPs 2*M*N*K of its "
+                          f"layers / their summed device time, CUDA events around every launch on the launch stream inside the timed steps)",
+                "peak_source": f"{peaks['source']} sustained bf16 (MEASURED_PEAKS.json)",
+                "kernel_ms": dom_ms, "kernel_share_of_layers": dom_ms / total_ms if total_ms else None,
+                "kernel_algorithmic_flops": dom_flops, "kernel_executed_tflops": executed,
+                "kernel_executed_frac_of_burst_peak": executed / peaks["bf16_tflops"],
+                "all_gemm_layers": {"tflops": gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0, "ms": gemm_ms,
+                                    "algorithmic_flops": gemm_flops,
+                                    "frac_of_peak": (gemm_flops / (gemm_ms * 1e-3) / 1e12 / peak) if gemm_ms > 0 else 0.0},
+                "by_kernel": {k: {"ms": v["ms"], "tflops": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["ms"] > 0 else 0.0,
+                                  "launches": v["launches"]} for k, v in by_kind.items()},
+                "layers_ms": total_ms,
+                "note": "encoder layers execute 3 MMAs per algorithmic MAC (split-bf16); executed tensor FLOPs are higher than algorithmic"}
+
+    # -- GAN codec on a batch of frames (c2, c4, c5) --------------------------------------------------------------------------------
+    def run_gan(self, name: str, steps: int, warmup: int, headline: bool):
+        torch, cic, args = self.torch, self.cic, self.args
+        cfg = dict(CONFIGS[name])
+        h, w = cfg["h"], cfg["w"]
+        if name == "c2" and args.images:
+            cfg["images"] = args.images
+            cfg["chunk"] = cfg["pool"] = args.images
+        if "images_total" in cfg:                                                # strong scaling: a fixed total, sharded
+            lo, hi = cic.dist.shard_range(cfg["images_total"], self.rank, self.world)
+            n_img, n_total = hi - lo, cfg["images_total"]
+        else:
+            n_img, n_total = cfg["images"], cfg["images"] * self.world
+        chunk = min(cfg["chunk"], n_img)
+        pool = min(cfg["pool"], n_img)
+        while chunk % pool and pool > 1:
+            pool -= 1
+        tpi = tiles_per_image(h, w)
+        am, weights = self.gan()
+        synth = cic.synth
+        img_u8, img, mask, bpp = gan_inputs(synth, self.rank, pool, h, w, cfg["bpp"], {"c2": 1, "c4": 3, "c5": 4}[name])
+        reps = chunk // pool                                                     # a chunk = the pool repeated (device / pinned copies)
+        tile_in = lambda a: np.concatenate([a] * reps, axis=0) if reps > 1 else a  # noqa: E731
+        h_img8, h_img, h_mask, h_bpp = (torch.from_numpy(tile_in(a)).pin_memory() for a in (img_u8, img, mask, bpp))
+        d_img, d_mask, d_bpp = (t.to(self.dev) for t in (h_img, h_mask, h_bpp))
+        n_chunks = -(-n_img // chunk)
+        last_n = n_img - (n_chunks - 1) * chunk
+        sizes = [chunk] * (n_chunks - 1) + [last_n]
+        px_step_rank = n_img * h * w
+        px_step = n_total * h * w
+
+        def evaluate(d_in_img, outs, n):
+            m = cic.ops.metrics_f32(d_in_img, outs["blended"], signed_range=True, fast=self.fast_ssim)     # (n,4) psnr, ssim, mse, sse
+            return m, cic.ops.metric_sums(m, outs["hq_ratio_sum"], h * w, 2 * BASE_LATENT, BASE_LATENT, TILE * TILE)
+
+        per_image = {}
+
+        def step_device():
+            tot = None
+            for k in sizes:
+                am.forward_device([d_img[:k], d_mask[:k], d_bpp[:k]], extras=False)
+                m, s = evaluate(d_img[:k], am.last, k)
+                tot = s if tot is None else tot + s
+                per_image["last"] = m
+            return cic.dist.allreduce_metric_sums(tot)
+
+        def on_chunk(d_in, outs):
+            return evaluate(d_in[0], outs, d_in[0].shape[0])[1]
+
+        def make_e2e(u8, want_dt=True):
+            src = [h_img8 if u8 else h_img, h_mask, h_bpp]
+
+            def step():
+                tot, outs = None, None
+                for k in sizes:
+                    outs, parts = am.predict_phased([t[:k] for t in src], on_chunk=on_chunk, u8_io=u8, want_dt=want_dt)
+                    s = torch.stack(parts).sum(0)
+                    tot = s if tot is None else tot + s
+                return outs, cic.dist.allreduce_metric_sums(tot).cpu()
+            return step
+
+        plan = am.plan()
+        sampler = ClockSampler(self.nvml_idx) if headline else None
+        plan.set_profiling(True)
+        ms_step, sums = self.timed(step_device, steps, warmup, sampler)
+        clocks = sampler.stop() if sampler else None
+        prof = plan.profile()
+        plan.set_profiling(False)
+        launches_per_step = (plan.last_launch_count() + 3) * n_chunks            # + metrics kernel, its finalise and the metric sums
+        self.launches += launches_per_step * steps
+        value = px_step / (ms_step * 1e-3) / 1e6
+        roofline = self.roofline_from_profile(prof)
+        roofline["kernel_share_of_step"] = roofline["kernel_ms"] * (n_img / sizes[-1]) / ms_step if ms_step else None
+        roofline["model_flops_per_step"] = n_total * tpi * FLOP_PER_TILE
+        roofline["whole_step_tflops"] = n_img * tpi * FLOP_PER_TILE / (ms_step * 1e-3) / 1e12
+        roofline["whole_step_frac_of_peak"] = roofline["whole_step_tflops"] / self.peaks["bf16_tflops_sustained"]
+
+        # ---- e2e: pinned host buffers in, host buffers out --------------------------------------------------------------------
+        e2e_steps, e2e_warm = (steps, 3) if headline else (max(2, steps), 3)
+
+        def e2e_leg(u8, want_dt=True):
+            ms, last = self.timed(make_e2e(u8, want_dt), e2e_steps, e2e_warm, wall=True)
+            outs, sums_host = last
+            scale = n_img / sizes[-1]                                           # outs are the last chunk's
+            h2d = int(((h_img8 if u8 else h_img)[:chunk].numel() * (1 if u8 else 4) + h_mask[:chunk].numel() * 4 + chunk * 4) * n_img / chunk)
+            d2h = int(sum(o.nbytes for o in outs) * scale + sums_host.numel() * 8)
+            floor = self.host_copy_floor(h2d, d2h)
+            return {"value": px_step / (ms * 1e-3) / 1e6, "unit": "MPix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms, "host_copy_floor_ms": floor, "frac_of_host_copy_floor": floor / ms if ms else None,
+                    "host_gbs_achieved": (h2d + d2h) * self.world / (ms * 1e-3) / 1e9}
+        e2e = e2e_leg(True)
+        e2e["api"] = "adaptive_model.predict_phased(u8_io=True): uint8 RGB image up, uint8 reconstruction down (GAN_functions.py:24-50), mask / dt / latents / rd_params float32"
+        e2e_f32 = e2e_f32_nodt = None
+        if headline:
+            e2e_f32 = e2e_leg(False)
+            e2e_f32["api"] = "adaptive_model.predict_phased: float32 image up, float32 reconstruction down (round 1's e2e)"
+            e2e_f32_nodt = e2e_leg(True, want_dt=False)
+            e2e_f32_nodt["api"] = "adaptive_model.predict_phased(u8_io=True, want_dt=False): hq_ratio instead of the bit-allocation map"
+        self.launches += launches_per_step * (e2e_steps + e2e_warm) * (3 if headline else 1)
+
+        # ---- bandwidth kernels of the path (headline only) ----------------------------------------------------------------------
+        if headline:
+            roofline["hbm_kernels"], roofline["hbm_peak_gbs"] = self.hbm_kernels(prof, am, d_img[:sizes[-1]], d_mask[:sizes[-1]], d_bpp[:sizes[-1]]), self.peaks["hbm_gbs"]
+
+        s = sums.cpu().numpy()[0]
+        n_seen = s[6]
+        quality = {"psnr_db": s[0] / n_seen, "ssim": s[1] / n_seen, "mse": s[2] / n_seen, "actual_bpp": s[3] / n_seen,
+                   "hq_ratio": s[4] / n_seen, "images": int(n_seen)}
+        if name == "c5":                                                          # per-image PSNR / SSIM of the last chunk (BASELINE configs[4])
+            pm = per_image["last"].cpu().numpy()
+            quality["per_image_psnr_db"] = [float(v) for v in pm[:, 0]]
+            quality["per_image_ssim"] = [float(v) for v in pm[:, 1]]
+
+        # ---- parity of this run's outputs against the CPU oracle (rank 0, outside every timed region) ---------------------------------
+        par, cpu = None, None
+        if self.rank == 0 and args.cpu_tiles > 0:
+            from oracle import parity, tiling
+            k = min(pool, 2 if name != "c2" else 4)
+            out = am.forward_device([d_img[:k], d_mask[:k], d_bpp[:k]], extras=True)
+            got = {key: out[key].cpu().numpy() for key in ("blended", "dt", "hq_symbols", "lq_symbols", "hq_ratio_sum")}
+            n_or = args.cpu_tiles if headline else min(args.cpu_tiles, 4)
+            sel = tiling.sample_tiles(k * tpi, n_or, seed=7)
+            secs, ncoded, ref = cpu_oracle_step(weights, img[:k], mask[:k], bpp[:k], tiles=sel)
+            par = parity.adaptive_parity(got, ref, k, h, w, TILE)
+            want_ratio = tiling.hq_ratio(mask[:k], bpp[:k])
+            par["hq_ratio_delta_max"] = float(np.abs(got["hq_ratio_sum"] / (h * w) - want_ratio).max())
+            par["actual_bpp_delta_max"] = 0.25 * par["hq_ratio_delta_max"]      # actual_bpp = 0.25 (1 + hq_ratio), GAN_test.py:318-325
+            par["against"] = f"CPU oracle (torch fp32) on {ncoded} sampled tiles of the first {k} images of this run's inputs"
+            if headline:
+                cores = os.cpu_count() or 1
+                secs2, _, _ = cpu_oracle_step(weights, img[:k], mask[:k], bpp[:k], tiles=sel)
+                best = min(secs, secs2)
+                cpu = {"value": ncoded * TILE * TILE / best / 1e6, "unit": "MPix/s", "cores": cores, "kind": "port",
+                       "sample": f"{ncoded} tiles of 256x256 of the workload incl. compute_metrics per tile, best of 2, {best:.2f} s, torch-CPU fp32 "
+                                 f"oracle of the reference graph (the reference's TensorFlow stack is not installable here)"}
+        line = {"metric": METRIC, "value": value, "unit": "MPix/s", "n_gpus": self.world, "steps": steps, "warmup": warmup,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None,
+                "dtype": "bf16 (3-term split-bf16 encoder, bf16 decoder, fp32 accumulate)" if args.precision == "tc" else "f32",
+                "data": "synthetic" + (f" ({pool} distinct images per rank, repeated)" if pool < n_img else ""),
+                "config": {"workload": f"{cfg['what']} (BASELINE {cfg['baseline']})", "name": name, "precision": args.precision,
+                           "images_per_gpu": n_img, "images_total": n_total, "tiles_per_gpu": n_img * tpi, "images_per_forward_call": chunk,
+                           "base_latent_dim": BASE_LATENT, "padding": f"{am.PADDING} (images that are not multiples of 256 replicate their last row / column; outputs cropped)",
+                           "l2": f"inputs per forward call {(h_img[:chunk].numel() + h_mask[:chunk].numel()) * 4 / 1e6:.0f} MB + activations >> 126 MB L2 (no flush needed)",
+                           "step": "encode + quantise + decode + ROI blend + PSNR/SSIM/bpp evaluation + metric all-reduce",
+                           "ssim": args.ssim, "cpu_affinity": f"{self.numa_cpus} CPUs local to the rank's GPU" if self.numa_cpus else "unchanged"},
+                "e2e": e2e, "gpu_launches": None, "roofline": roofline, "parity": par, "quality": quality}
+        if clocks is not None:
+            line["clocks"] = clocks
+        if e2e_f32 is not None:
+            line["e2e_f32_io"], line["e2e_u8_io_no_dt"] = e2e_f32, e2e_f32_nodt
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        if args.profile_csv and self.rank == 0 and headline:
+            with open(args.profile_csv, "w") as f:
+                f.write("layer,ms,flops,bytes,tflops,gbs,kernel\n")
+                for lname, ms, fl, by, kind in prof:
+                    f.write(f"{lname},{ms:.4f},{fl:.4e},{by:.4e},{(fl / ms / 1e9) if ms > 0 else 0:.2f},{(by / ms / 1e6) if ms > 0 else 0:.1f},"
+                            f"{KINDS.get(kind, 'other')}\n")
+        return line
+
+    def hbm_kernels(self, prof, am, d_img, d_mask, d_bpp):
+        """Algorithmic bytes / device time of the bandwidth kernels against the measured HBM peak."""
+        torch, cic = self.torch, self.cic
+        hbm_peak = self.peaks["hbm_gbs"]
+        hbm = {}
+        for name, ms, fl, by, kind in prof:
+            if name in ("roi_blend", "quantize", "gen_tail") and ms > 0 and by > 0:
+                hbm[name] = {"ms": ms, "algorithmic_bytes": by, "gbs": by / ms / 1e6, "frac_of_hbm_peak": by / ms / 1e6 / hbm_peak}
+        am.forward_device([d_img, d_mask, d_bpp], extras=False)
+        blended = am.last["blended"]
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        m_bytes = 24.0 * d_img.shape[0] * d_img.shape[1] * d_img.shape[2]   # two fp32 RGB images read once
+        reps = 5
+        for key, fast, note in (("metrics_psnr_ssim_f32_fast", True, "float32 window sums on centred data (DESIGN.md 4.5)"),
+                                ("metrics_psnr_ssim_f32", False, "bound by the fp32<->fp64 conversion pipe, not HBM: scipy-exact 7x7 window "
+                                                                 "sums (double accumulation, float32 after each pass), DESIGN.md 4.5")):
+            cic.ops.metrics_f32(d_img, blended, signed_range=True, fast=fast)
+            torch.cuda.synchronize()
+            ev[0].record()
+            for _ in range(reps):
+                mm = cic.ops.metrics_f32(d_img, blended, signed_range=True, fast=fast)
+            ev[1].record()
+            torch.cuda.synchronize()
+            m_ms = ev[0].elapsed_time(ev[1]) / reps
+            hbm[key] = {"ms": m_ms, "algorithmic_bytes": m_bytes, "gbs": m_bytes / m_ms / 1e6,
+                        "frac_of_hbm_peak": m_bytes / m_ms / 1e6 / hbm_peak, "mean_ssim": float(mm[:, 1].mean().item()), "note": note,
+                        "used_in_step": fast == self.fast_ssim}
+        return hbm
+
+    # -- c1: autoencoder ------------------------------------------------------------------------------------------------------------
+    def run_ae(self, steps: int, warmup: int, headline: bool):
+        torch, cic, args = self.torch, self.cic, self.args
+        cfg = CONFIGS["c1"]
+        n, h, w = cfg["images"], cfg["h"], cfg["w"]
+        import train_autoencoder as tr
+        model = tr.build_autoencoder((h, w, 3))
+        wts = cic.weights.synthetic_autoencoder(seed=42)
+        model.set_weights_dict(wts)
+        x_u8 = cic.synth.synth_images_u8(n, h, w, seed=cic.synth.SEED_BASE, first_index=self.rank * n)
+        x = cic.synth.to_unit_range(x_u8)
+        h_x = torch.from_numpy(x).pin_memory()
+        d_x = h_x.to(self.dev)
+        nf = len(cic.dist.METRIC_FIELDS)
+
+        def evaluate(dx):
+            y, y8 = model.forward_device([dx], want_u8=True)
+            x8 = cic.ops.f32_to_u8_trunc(dx, 255.0)                               # test_autoencoder.py:96
+            m = cic.ops.metrics_gray_u8(x8, y8)                                  # psnr, ssim(gray), true mse, wrapped mse
+            row = torch.zeros((1, nf), dtype=torch.float64, device=self.dev)
+            row[0, 0], row[0, 1], row[0, 2], row[0, 6] = m[:, 0].sum(), m[:, 1].sum(), m[:, 3].sum(), float(dx.shape[0])
+            return y8, m, row
+
+        def step_device():
+            return cic.dist.allreduce_metric_sums(evaluate(d_x)[2])
+
+        stage = {}
+
+        def step_e2e():
+            dx = h_x.to(self.dev, non_blocking=True)
+            y8, m, row = evaluate(dx)
+            if "y8" not in stage:
+                stage["y8"] = torch.empty(y8.shape, dtype=torch.uint8, pin_memory=True)
+                stage["m"] = torch.empty(m.shape, dtype=torch.float64, pin_memory=True)
+            stage["y8"].copy_(y8, non_blocking=True)
+            stage["m"].copy_(m, non_blocking=True)
+            sums = cic.dist.allreduce_metric_sums(row).cpu()
+            torch.cuda.current_stream().synchronize()
+            return stage["y8"], sums
+
+        plan = model.plan()
+        # 2.1 MPix per step < L2: flush between timed iterations by writing a buffer larger than L2
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)
+
+        def flushed(fn):
+            def g():
+                flush.zero_()
+                return fn()
+            return g
+        sampler = ClockSampler(self.nvml_idx) if headline else None
+        ms_flush, _ = self.timed(lambda: flush.zero_(), steps, warmup)
+        plan.set_profiling(True)
+        ms_both, sums = self.timed(flushed(step_device), steps, warmup, sampler)
+        clocks = sampler.stop() if sampler else None
+        prof = plan.profile()
+        plan.set_profiling(False)
+        ms_step = max(ms_both - ms_flush, 1e-6)
+        self.launches += (plan.last_launch_count() + 4) * steps
+        px = n * h * w * self.world
+        ms_e2e_both, last = self.timed(flushed(step_e2e), steps, warmup, wall=True)
+        ms_e2e = max(ms_e2e_both - ms_flush, 1e-6)
+        h2d, d2h = int(h_x.numel() * 4), int(stage["y8"].numel() + stage["m"].numel() * 8 + nf * 8)
+        floor = self.host_copy_floor(h2d, d2h)
+        roofline = self.roofline_from_profile(prof)
+        roofline["model_flops_per_step"] = AE_FLOP_PER_PIXEL * px
+        roofline["whole_step_tflops"] = AE_FLOP_PER_PIXEL * n * h * w / (ms_step * 1e-3) / 1e12
+        roofline["whole_step_frac_of_peak"] = roofline["whole_step_tflops"] / self.peaks["bf16_tflops_sustained"]
+        s = sums.cpu().numpy()[0]
+        quality = {"psnr_db": s[0] / s[6], "ssim_gray": s[1] / s[6], "mse_uint8_wrapped": s[2] / s[6], "images": int(s[6])}
+        par, cpu = None, None
+        if self.rank == 0 and args.cpu_tiles > 0:
+            from oracle import graphs, metrics
+            import torch as _t
+            _t.set_num_threads(os.cpu_count() or 1)
+            y8, m, _ = evaluate(d_x)
+            y8, m = y8.cpu().numpy(), m.cpu().numpy()
+            t0 = time.perf_counter()
+            want = graphs.autoencoder_forward(wts, x)                            # batch 32
+            t_batch = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            for i in range(n):                                                   # the reference's batch-1 loop incl. metrics
+                yi = graphs.autoencoder_output_u8(graphs.autoencoder_forward(wts, x[i:i + 1]))[0]
+                metrics.ae_calculate_mse(x_u8[i], yi), metrics.ae_calculate_psnr(x_u8[i], yi), metrics.ae_calculate_ssim(x_u8[i], yi)
+            t_loop = time.perf_counter() - t0
+            want8 = graphs.autoencoder_output_u8(want)
+            dp = max(abs(m[i, 0] - metrics.ae_calculate_psnr(x_u8[i], want8[i])) for i in range(min(n, 8)))
+            ds = max(abs(m[i, 1] - metrics.ae_calculate_ssim(x_u8[i], want8[i])) for i in range(min(n, 8)))
+            par = {"u8_max_abs_lsb": int(np.abs(y8.astype(int) - want8.astype(int)).max()),
+                   "u8_pixels_differing_frac": float(np.mean(y8 != want8)), "psnr_delta_db_max": float(dp), "ssim_delta_max": float(ds),
+                   "against": f"CPU oracle (torch fp32) on all {n} images"}
+            cores = os.cpu_count() or 1
+            cpu = {"value": n * h * w / t_loop / 1e6, "unit": "MPix/s", "cores": cores, "kind": "port",
+                   "sample": f"all {n} images, batch-1 loop incl. the three metrics like test_autoencoder.py:83-108, {t_loop:.2f} s "
+                             f"(one batch-{n} forward without metrics: {n * h * w / t_batch / 1e6:.2f} MPix/s)"}
+        line = {"metric": METRIC, "value": px / (ms_step * 1e-3) / 1e6, "unit": "MPix/s", "n_gpus": self.world, "steps": steps, "warmup": warmup,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16 (fp32 accumulate), uint8 output" if args.precision == "tc" else "f32", "data": "synthetic",
+                "config": {"workload": f"{cfg['what']} (BASELINE {cfg['baseline']})", "name": "c1", "precision": args.precision,
+                           "l2": f"L2 flushed between timed iterations (256 MB memset, its {ms_flush:.3f} ms subtracted)",
+                           "step": "predict + truncating uint8 cast of input and output + MSE/PSNR/SSIM(gray) + metric all-reduce"},
+                "e2e": {"value": px / (ms_e2e * 1e-3) / 1e6, "unit": "MPix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e,
+                        "host_copy_floor_ms": floor, "frac_of_host_copy_floor": floor / ms_e2e,
+                        "api": "build_autoencoder(...).forward_device on a pinned float32 batch + evaluate (uint8 reconstruction + per-image metrics down)"},
+                "gpu_launches": None, "roofline": roofline, "parity": par, "quality": quality}
+        if clocks is not None:
+            line["clocks"] = clocks
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        return line
+
+    # -- c3: ROI / rate sweep -------------------------------------------------------------------------------------------------------
+    def run_sweep(self, steps: int, warmup: int, headline: bool):
+        torch, cic, args = self.torch, self.cic, self.args
+        cfg = CONFIGS["c3"]
+        n, h, w = cfg["images"], cfg["h"], cfg["w"]
+        am, weights = self.gan()
+        img_u8, img, mask, _ = gan_inputs(cic.synth, self.rank, n, h, w, 1.0, 2)
+        h_img8, h_mask = torch.from_numpy(img_u8).pin_memory(), torch.from_numpy(mask).pin_memory()
+        d_img, d_mask = torch.from_numpy(img).to(self.dev), h_mask.to(self.dev)
+        levels = SWEEP_LEVELS
+        nl = len(levels)
+        nf = len(cic.dist.METRIC_FIELDS)
+        d_levels = torch.tensor(levels, dtype=torch.float32, device=self.dev)
+
+        def sweep(di, dm):
+            rows = torch.zeros((nl, nf), dtype=torch.float64, device=self.dev)
+
+            def on_level(k, ins, outs):
+                m = cic.ops.metrics_f32(ins[0], outs["blended"], signed_range=True, fast=self.fast_ssim)
+                rows[k:k + 1] = cic.ops.metric_sums(m, outs["hq_ratio_sum"], h * w, 2 * BASE_LATENT, BASE_LATENT, TILE * TILE)
+            ratios = am.rate_sweep_device(di, dm, levels, on_level)
+            fastpath = cic.ops.hq_ratio_sweep(dm, d_levels)                     # the hq_ratio-only sweep: one pass over the masks
+            return ratios, fastpath, cic.dist.allreduce_metric_sums(rows)
+
+        def step_device():
+            return sweep(d_img, d_mask)
+
+        stage = {}
+
+        def step_e2e():
+            di8 = h_img8.to(self.dev, non_blocking=True)
+            dm = h_mask.to(self.dev, non_blocking=True)
+            di = torch.empty(di8.shape, dtype=torch.float32, device=self.dev)
+            cic._lib.check(cic._lib.lib.cic_u8_to_f32_signed(di8.data_ptr(), di.data_ptr(), di8.numel(), cic.runtime.stream_ptr()))
+            ratios, fastpath, rows = sweep(di, dm)
+            if "r" not in stage:
+                stage["r"] = torch.empty(ratios.shape, dtype=torch.float64, pin_memory=True)
+                stage["rows"] = torch.empty(rows.shape, dtype=torch.float64, pin_memory=True)
+            stage["r"].copy_(ratios, non_blocking=True)
+            stage["rows"].copy_(rows, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return stage["r"], stage["rows"]
+
+        plan = am.plan()
+        sampler = ClockSampler(self.nvml_idx) if headline else None
+        ms_step, last = self.timed(step_device, steps, warmup, sampler)
+        clocks = sampler.stop() if sampler else None
+        ratios, fastpath, rows = last
+        self.launches += int(plan.last_launch_count() * (1 + 2 * nl) * 0.5 + 3 * nl) * steps
+        px = n * h * w * nl * self.world                                         # every level yields a full reconstruction
+        ms_e2e, _ = self.timed(step_e2e, max(2, steps), 3, wall=True)
+        h2d, d2h = int(h_img8.numel() + h_mask.numel() * 4), int(nl * n * 8 + nl * nf * 8)
+        floor = self.host_copy_floor(h2d, d2h)
+        r = rows.cpu().numpy()
+        per_level = [{"target_bpp": levels[k], "hq_ratio": r[k, 4] / r[k, 6], "actual_bpp": r[k, 3] / r[k, 6], "psnr_db": r[k, 0] / r[k, 6],
+                      "ssim": r[k, 1] / r[k, 6]} for k in range(nl)]
+        rat = ratios.cpu().numpy()
+        # the single-pass sweep kernel (4 B / pixel for all levels) timed alone: the reference's test_rate_control needs only this
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ev[0].record()
+        for _ in range(20):
+            cic.ops.hq_ratio_sweep(d_mask, d_levels)
+        ev[1].record()
+        torch.cuda.synchronize()
+        sw_ms = ev[0].elapsed_time(ev[1]) / 20
+        roofline = {"bound": "hbm", "kernel": "hq_ratio_sweep_kernel (mean(dt) of every image x level in one pass over the masks, 4 B/pixel)",
+                    "achieved": 4.0 * n * h * w / sw_ms / 1e6, "peak": self.peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": 4.0 * n * h * w / sw_ms / 1e6 / self.peaks["hbm_gbs"], "traffic": None, "kernel_ms": sw_ms,
+                    "note": f"{n} x {h}x{w} masks = {4.0 * n * h * w / 1e6:.0f} MB < 126 MB L2: repeated launches read the L2, so this is an L2-resident rate; "
+                            "the full sweep step itself is tensor-bound like c2 (decoders per level)",
+                    "whole_step_tflops": n * tiles_per_image(h, w) * (FLOP_PER_TILE * 0.33 + nl * FLOP_PER_TILE * 0.67) / (ms_step * 1e-3) / 1e12}
+        par = None
+        if self.rank == 0 and args.cpu_tiles > 0:
+            from oracle import tiling
+            want = np.stack([tiling.hq_ratio(mask, np.full((n, 1), lv, np.float32)) for lv in levels])
+            par = {"hq_ratio_delta_max": float(np.abs(rat - want).max()),
+                   "hq_ratio_sweep_kernel_vs_full_model_max": float(np.abs(fastpath.cpu().numpy().T - rat).max()),
+                   "actual_bpp_delta_max": float(0.25 * np.abs(rat - want).max()),
+                   "monotone_in_bpp": bool(np.all(np.diff(rat[[levels.index(v) for v in sorted(levels)]], axis=0) > 0)),
+                   "against": "CPU oracle dynamic_threshold on the full masks, every level"}
+        line = {"metric": METRIC, "value": px / (ms_step * 1e-3) / 1e6, "unit": "MPix/s", "n_gpus": self.world, "steps": steps, "warmup": warmup,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16 (3-term split-bf16 encoder, bf16 decoder, fp32 accumulate)" if args.precision == "tc" else "f32", "data": "synthetic",
+                "config": {"workload": f"{cfg['what']} (BASELINE {cfg['baseline']})", "name": "c3", "levels": levels,
+                           "pixels_counted": "every level yields a full reconstruction: pixels x levels per step (the reference runs the whole model per level)",
+                           "l2": "activations of 64 tiles >> 126 MB L2 (no flush needed)"},
+                "e2e": {"value": px / (ms_e2e * 1e-3) / 1e6, "unit": "MPix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e,
+                        "host_copy_floor_ms": floor, "frac_of_host_copy_floor": floor / ms_e2e,
+                        "api": "uint8 images + float32 masks up, adaptive_model.rate_sweep_device, per-level hq_ratio and metric sums down"},
+                "gpu_launches": None, "roofline": roofline, "parity": par, "per_level": per_level}
+        if clocks is not None:
+            line["clocks"] = clocks
+        return line
+
+    def run(self, name: str, steps: int, warmup: int, headline: bool):
+        kind = CONFIGS[name]["kind"]
+        if kind == "ae":
+            return self.run_ae(steps, warmup, headline)
+        if kind == "sweep":
+            return self.run_sweep(steps, warmup, headline)
+        return self.run_gan(name, steps, warmup, headline)
 
 
 def main():
@@ -184,273 +793,40 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--no-extra-configs", action="store_true", help="default run: skip the short c1 / c3 / c4 / c5 measurements under `configs`")
+    ap.add_argument("--extra-steps", type=int, default=3, help="timed steps of each config under `configs`")
     ap.add_argument("--precision", default=os.environ.get("CIC_PRECISION", "tc"), choices=["tc", "fp32"])
-    ap.add_argument("--images", type=int, default=IMGS_PER_GPU, help="512x512 images per GPU per step")
-    ap.add_argument("--e2e-chunks", default="auto", help="pipelined end-to-end leg: number of chunks of the batch, comma-separated chunk "
-                    "sizes, or 'auto' (n/8, n/4, n/2, n/8: short first upload and last download)")
-    ap.add_argument("--e2e-mode", default="phased", choices=["phased", "pipelined"],
-                    help="end-to-end leg: predict_phased (encoder convs per upload chunk, Dense layers once per batch, decoders per "
-                         "download chunk) or predict_pipelined (the whole graph per chunk)")
-    ap.add_argument("--enc-chunks", default=None, help="phased: comma-separated upload / encode chunk sizes (default n/16, 3n/16, n/4, n/4, n/4)")
-    ap.add_argument("--dec-chunks", default=None, help="phased: comma-separated decode / download chunk sizes (default: the encode schedule reversed)")
+    ap.add_argument("--images", type=int, default=0, help="c2: 512x512 images per GPU per step (default 64)")
     ap.add_argument("--ssim", default="fast", choices=["fast", "exact"],
                     help="SSIM kernel of the evaluation: float32 window sums on centred data (HBM-bound, |dSSIM| < 1e-5 against "
                          "scikit-image in the tests) or the op-by-op scipy arithmetic (double accumulation, conversion-pipe-bound)")
-    ap.add_argument("--cpu-tiles", type=int, default=8, help="tiles in the CPU-oracle sample (0 = skip)")
-    ap.add_argument("--profile-csv", default=None, help="write the per-layer device times of the last timed step here")
+    ap.add_argument("--cpu-tiles", type=int, default=8, help="tiles in the CPU-oracle parity / baseline sample (0 = skip)")
+    ap.add_argument("--profile-csv", default=None, help="write the per-layer device times of the last timed forward call here")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":
         return run_reference(args)
 
-    import torch
-    import cic_b200 as cic
-    import GAN_functions as gf
-
-    rank, world = cic.dist.init()
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
-    dev = torch.device("cuda", local_rank if world > 1 else torch.cuda.current_device())
-    torch.cuda.set_device(dev)
-    numa_cpus = cic.dist.bind_to_gpu_numa_node(dev.index if dev.index is not None else 0) if world > 1 else 0
-    cic.set_precision(args.precision)
-    peaks = measured_peaks()
-    # clock sampler child (started now so that it is up before the timed region); NVML indices are physical
-    cuda_idx = dev.index if dev.index is not None else 0
-    vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
-    if vis and all(v.strip().isdigit() for v in vis.split(",")) and cuda_idx < len(vis.split(",")):
-        cuda_idx = int(vis.split(",")[cuda_idx])
-    sampler = ClockSampler(cuda_idx)
-
-    n_img = args.images
-    n_tiles = n_img * (IMG_HW // TILE) ** 2
-    img, mask, bpp = make_inputs(rank, n_img)
-    weights = cic.weights.synthetic_adaptive((TILE, TILE, 3), BASE_LATENT, seed=42)
-    models = gf.build_adaptive_compression_model((TILE, TILE, 3), BASE_LATENT, target_bpp=True)
-    am = models["adaptive_model"]
-    am.set_weights_dict(weights)
-
-    # pinned host buffers (e2e leg) and device-resident copies (value leg)
-    h_img, h_mask, h_bpp = (torch.from_numpy(a).pin_memory() for a in (img, mask, bpp))
-    d_img, d_mask, d_bpp = (t.to(dev) for t in (h_img, h_mask, h_bpp))
-    nfields = len(cic.dist.METRIC_FIELDS)
-    px_per_step = n_img * IMG_HW * IMG_HW
-
-    fast_ssim = args.ssim == "fast"
-
-    def evaluate(d_in, outs):
-        """bpp / PSNR / SSIM evaluation of the step + the one exchange step of the path."""
-        m = cic.ops.metrics_f32(d_in, outs["blended"], signed_range=True, fast=fast_ssim)   # (n,4) psnr, ssim, mse, sse
-        sums = cic.ops.metric_sums(m, outs["hq_ratio_sum"], IMG_HW * IMG_HW, 2 * BASE_LATENT, BASE_LATENT, TILE * TILE)
-        return cic.dist.allreduce_metric_sums(sums)
-
-    def step_device():
-        outs = am.forward_device([d_img, d_mask, d_bpp], extras=False)
-        return evaluate(d_img, am.last)
-
-    if args.e2e_chunks == "auto":
-        # graded chunks: a short first upload and last download, sizes doubling in between so every upload hides behind the
-        # previous chunk's kernels (measured r01: 8,16,32,8 beats 8,48,8 and five- or six-chunk schedules at 64 images)
-        if n_img >= 32:
-            a, b = n_img // 8, n_img // 4
-            e2e_chunks = [a, b, n_img - 2 * a - b, a]
-        else:
-            e2e_chunks = [n_img // 8, n_img - 2 * (n_img // 8), n_img // 8] if n_img >= 16 else min(n_img, 2)
-    else:
-        e2e_chunks = [int(v) for v in str(args.e2e_chunks).split(",")] if "," in str(args.e2e_chunks) else int(args.e2e_chunks)
-
-    def evaluate_chunk(d_in, outs):
-        """Per-chunk metric sums (no all-reduce): runs on the compute stream inside the pipelined predict."""
-        k = d_in[0].shape[0]
-        m = cic.ops.metrics_f32(d_in[0], outs["blended"], signed_range=True, fast=fast_ssim)
-        return cic.ops.metric_sums(m, outs["hq_ratio_sum"], IMG_HW * IMG_HW, 2 * BASE_LATENT, BASE_LATENT, TILE * TILE)
-
-    enc_chunks = [int(v) for v in args.enc_chunks.split(",")] if args.enc_chunks else None
-    dec_chunks = [int(v) for v in args.dec_chunks.split(",")] if args.dec_chunks else None
-
-    def step_e2e():
-        # pinned host buffers -> (H2D | model + metrics | D2H of all 5 outputs) pipelined over chunks of the batch
-        if args.e2e_mode == "phased":
-            outs, parts = am.predict_phased([h_img, h_mask, h_bpp], enc_chunks=enc_chunks, dec_chunks=dec_chunks, on_chunk=evaluate_chunk)
-        else:
-            outs, parts = am.predict_pipelined([h_img, h_mask, h_bpp], n_chunks=e2e_chunks, on_chunk=evaluate_chunk)
-        sums = cic.dist.allreduce_metric_sums(torch.stack(parts).sum(0))
-        return outs, sums.cpu()
-
-    plan = am.plan()
-    launches_per_step = None
-
-    # ---------------- value leg: inputs resident in HBM -------------------------------------------
-    for _ in range(args.warmup):
-        step_device()
-    torch.cuda.synchronize()
-    plan.set_profiling(True)
-    cic.dist.barrier()
-    torch.cuda.synchronize()
-    sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    layer_ms, layer_flops = {}, {}
-    e0.record()
-    for _ in range(args.steps):
-        sums = step_device()
-    e1.record()
-    torch.cuda.synchronize()
-    cic.dist.barrier()
-    clocks = sampler.stop()
-    ms_total = e0.elapsed_time(e1)
-    ms_step = cic.dist.max_over_ranks(ms_total / args.steps, device=dev)
-    prof = plan.profile()                       # per-layer device times of the last timed step
-    plan.set_profiling(False)
-    launches_per_step = plan.last_launch_count() + 3          # + metrics kernel, its finalise and the metric sums
-    value = world * px_per_step / (ms_step * 1e-3) / 1e6
-
-    KINDS = {0: "other", 1: "tc_gemm_kernel", 2: "tc_conv_kernel", 3: "conv1_tc_kernel", 4: "direct_conv_kernel", 5: "igemm_f32_kernel", 6: "conv_rows_tc_kernel", 7: "tc_gemm2_kernel", 8: "attn_fused_kernel"}
-    by_kind = {}
-    for name, ms, fl, by, kind in prof:
-        k = by_kind.setdefault(KINDS.get(kind, "other"), {"ms": 0.0, "flops": 0.0, "launches": 0})
-        k["ms"] += ms
-        k["flops"] += fl
-        k["launches"] += 1
-    gemm_ms = sum(ms for name, ms, fl, by, kind in prof if fl > 0)
-    gemm_flops = sum(fl for name, ms, fl, by, kind in prof if fl > 0)
-    total_layer_ms = sum(ms for name, ms, fl, by, kind in prof)
-    # dominant kernel = the kernel class with the largest share of the step
-    dom = max((k for k in by_kind if k != "other"), key=lambda k: by_kind[k]["ms"]) if by_kind else "other"
-    dom_ms, dom_flops = by_kind.get(dom, {"ms": 0.0})["ms"], by_kind.get(dom, {"flops": 0.0})["flops"]
-    achieved_tflops = dom_flops / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
-    # executed tensor-core FLOPs of the same launches: the encoder chain (conv2-4, attention projections, Dense) issues three MMAs
-    # per algorithmic MAC (hi*hi + lo*hi + hi*lo, split-bf16); reported next to the algorithmic figure, never instead of it
-    dom_exec = sum(fl * (3.0 if (args.precision == "tc" and ("_enc/" in name)) else 1.0)
-                   for name, ms, fl, by, kind in prof if KINDS.get(kind, "other") == dom)
-    executed_tflops = dom_exec / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
-    peak = peaks["bf16_tflops_sustained"]
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")      # dram bytes per step of each kernel class, from ncu --set full
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(dom, {}).get("dram_bytes_per_step")
-    roofline = {"bound": "tensor", "achieved": achieved_tflops, "peak": peak, "unit": "TFLOP/s", "frac": achieved_tflops / peak,
-                "traffic": traffic,
-                "kernel": f"{dom} ({by_kind.get(dom, {}).get('launches', 0)} launches per step; algorithmic FLOPs 2*M*N*K of its layers / "
-                          f"their summed device time, CUDA events around every launch on the launch stream inside the timed steps)",
-                "peak_source": f"{peaks['source']} sustained bf16 (MEASURED_PEAKS.json)",
-                "kernel_ms_per_step": dom_ms, "kernel_share_of_step": dom_ms / ms_step if ms_step else None,
-                "kernel_algorithmic_flops_per_step": dom_flops,
-                "kernel_executed_tflops": executed_tflops, "kernel_executed_frac_of_burst_peak": executed_tflops / peaks["bf16_tflops"],
-                "all_gemm_layers": {"tflops": gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0, "ms_per_step": gemm_ms,
-                                    "algorithmic_flops_per_step": gemm_flops, "model_flops_per_step": n_tiles * FLOP_PER_TILE,
-                                    "frac_of_peak": (gemm_flops / (gemm_ms * 1e-3) / 1e12 / peak) if gemm_ms > 0 else 0.0},
-                "by_kernel": {k: {"ms": v["ms"], "tflops": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["ms"] > 0 else 0.0,
-                                  "launches": v["launches"]} for k, v in by_kind.items()},
-                "note": "encoder layers execute 3 MMAs per algorithmic MAC (split-bf16); executed tensor FLOPs are higher than algorithmic"}
-    if args.profile_csv and rank == 0:
-        with open(args.profile_csv, "w") as f:
-            f.write("layer,ms,flops,bytes,tflops,gbs,kernel\n")
-            for name, ms, fl, by, kind in prof:
-                f.write(f"{name},{ms:.4f},{fl:.4e},{by:.4e},{(fl / ms / 1e9) if ms > 0 else 0:.2f},{(by / ms / 1e6) if ms > 0 else 0:.1f},"
-                        f"{KINDS.get(kind, 'other')}\n")
-
-    # ---------------- e2e leg: pinned host buffers in, host buffers out ------------------------------
-    for _ in range(2):
-        step_e2e()
-    torch.cuda.synchronize()
-    cic.dist.barrier()
-    t0 = time.perf_counter()
-    e0.record()
-    for _ in range(args.steps):
-        outs, sums_host = step_e2e()
-    e1.record()
-    torch.cuda.synchronize()
-    wall = (time.perf_counter() - t0) / args.steps * 1e3
-    ms_e2e = cic.dist.max_over_ranks(max(e0.elapsed_time(e1) / args.steps, wall), device=dev)
-    e2e_value = world * px_per_step / (ms_e2e * 1e-3) / 1e6
-    h2d = int(h_img.numel() * 4 + h_mask.numel() * 4 + h_bpp.numel() * 4)
-    d2h = int(sum(o.nbytes for o in outs) + sums_host.numel() * 8)
-
-    # informational: the same leg with the reference's uint8 image conventions applied on the device (uint8 image up, uint8 blended
-    # image down: 1 instead of 4 bytes per sample over PCIe); the headline `e2e` above moves the float32 arrays of the reference API
-    e2e_u8 = None
-    if args.e2e_mode == "phased":
-        from cic_b200 import synth
-        h_img_u8 = torch.from_numpy(synth.synth_images_u8(n_img, IMG_HW, IMG_HW, seed=synth.SEED_BASE + 1, first_index=rank * n_img)).pin_memory()
-
-        def step_u8():
-            o, parts = am.predict_phased([h_img_u8, h_mask, h_bpp], enc_chunks=enc_chunks, dec_chunks=dec_chunks, on_chunk=evaluate_chunk, u8_io=True)
-            return o, cic.dist.allreduce_metric_sums(torch.stack(parts).sum(0)).cpu()
-        for _ in range(2):
-            step_u8()
-        torch.cuda.synchronize()
-        cic.dist.barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            outs8, _s8 = step_u8()
-        torch.cuda.synchronize()
-        ms_u8 = cic.dist.max_over_ranks((time.perf_counter() - t0) / args.steps * 1e3, device=dev)
-        e2e_u8 = {"value": world * px_per_step / (ms_u8 * 1e-3) / 1e6, "unit": "MPix/s", "ms_per_step": ms_u8,
-                  "h2d_bytes_per_step": int(h_img_u8.numel() + h_mask.numel() * 4 + h_bpp.numel() * 4),
-                  "d2h_bytes_per_step": int(sum(o.nbytes for o in outs8) + 64), "api": "adaptive_model.predict_phased(u8_io=True)"}
-
-    # ---------------- HBM-bound kernels of the path: algorithmic bytes (SURVEY 8d) / device time ----------------------
-    hbm_peak = peaks["hbm_gbs"]
-    hbm = {}
-    for name, ms, fl, by, kind in prof:
-        if name in ("roi_blend", "quantize") and ms > 0:
-            hbm[name] = {"ms": ms, "algorithmic_bytes": by, "gbs": by / ms / 1e6, "frac_of_hbm_peak": by / ms / 1e6 / hbm_peak}
-    am.forward_device([d_img, d_mask, d_bpp], extras=False)
-    blended = am.last["blended"]
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    m_bytes = 24.0 * px_per_step                                  # two fp32 RGB images read once
-    reps = 5
-    for key, fast, note in (("metrics_psnr_ssim_f32_fast", True, "float32 window sums on centred data (DESIGN.md 4.5)"),
-                            ("metrics_psnr_ssim_f32", False, "bound by the fp32<->fp64 conversion pipe, not HBM: scipy-exact 7x7 window "
-                                                             "sums (double accumulation, float32 after each pass), DESIGN.md 4.5")):
-        cic.ops.metrics_f32(d_img, blended, signed_range=True, fast=fast)
-        torch.cuda.synchronize()
-        ev[0].record()
-        for _ in range(reps):
-            mm = cic.ops.metrics_f32(d_img, blended, signed_range=True, fast=fast)
-        ev[1].record()
-        torch.cuda.synchronize()
-        m_ms = ev[0].elapsed_time(ev[1]) / reps
-        hbm[key] = {"ms": m_ms, "algorithmic_bytes": m_bytes, "gbs": m_bytes / m_ms / 1e6,
-                    "frac_of_hbm_peak": m_bytes / m_ms / 1e6 / hbm_peak, "mean_ssim": float(mm[:, 1].mean().item()), "note": note,
-                    "used_in_step": fast == fast_ssim}
-    roofline["hbm_kernels"] = hbm
-    roofline["hbm_peak_gbs"] = hbm_peak
-
-    s = sums.cpu().numpy()[0]
-    n_total = s[6]
-    quality = {"psnr_db": s[0] / n_total, "ssim": s[1] / n_total, "mse": s[2] / n_total, "actual_bpp": s[3] / n_total,
-               "hq_ratio": s[4] / n_total, "images": int(n_total)}
-
-    if world > 1:
+    b = Bench(args)
+    line = b.run(args.config, args.steps, args.warmup, headline=True)
+    if args.config == "c2" and not args.no_extra_configs:
+        extra = {}
+        for name in ("c1", "c3", "c4", "c5"):
+            try:
+                extra[name] = b.run(name, args.extra_steps, 3, headline=False)
+            except Exception as e:  # noqa: BLE001  (a secondary config must not take the headline down with it)
+                extra[name] = {"error": repr(e)}
+                b.torch.cuda.synchronize()
+        line["configs"] = extra
+    line["gpu_launches"] = int(b.launches)
+    if b.world > 1:
         import torch.distributed as tdist
         tdist.barrier()
         tdist.destroy_process_group()
-    if rank != 0:
-        return
-    cpu = None
-    if args.cpu_tiles > 0:
-        cores = os.cpu_count() or 1
-        rate, secs = cpu_oracle_rate(weights, img, mask, bpp, args.cpu_tiles, reps=2)
-        cpu = {"value": rate, "unit": "MPix/s", "cores": cores, "kind": "port",
-               "sample": f"first {args.cpu_tiles} tiles of the workload, best of 2, {secs:.2f} s, torch-CPU fp32 oracle of the reference graph "
-                         f"(the reference's TensorFlow stack is not installable here)"}
-    line = {"metric": METRIC, "value": value, "unit": "MPix/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16 (3-term split-bf16 encoder, bf16 decoder, fp32 accumulate)" if args.precision == "tc" else "f32",
-            "data": "synthetic",
-            "config": {"workload": f"adaptive GAN codec (build_adaptive_compression_model), {n_img} x {IMG_HW}x{IMG_HW} images per GPU "
-                                   f"= {n_tiles} tiles of 256x256, target bpp {TARGET_BPP} (BASELINE configs[1])",
-                       "precision": args.precision, "tiles_per_gpu": n_tiles, "base_latent_dim": BASE_LATENT,
-                       "l2": f"inputs per step {h2d / 1e6:.0f} MB + activations >> 126 MB L2 (no flush needed)",
-                       "step": "encode + quantise + decode + ROI blend + PSNR/SSIM/bpp evaluation + metric all-reduce",
-                       "ssim": args.ssim, "cpu_affinity": f"{numa_cpus} CPUs local to the rank's GPU" if numa_cpus else "unchanged"},
-            "clocks": clocks, "e2e": {"value": e2e_value, "unit": "MPix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                                      "ms_per_step": ms_e2e, "api": f"adaptive_model.predict_{args.e2e_mode}"},
-            "e2e_u8_io": e2e_u8, "gpu_launches": int(launches_per_step * args.steps), "roofline": roofline, "cpu_baseline": cpu, "quality": quality,
-            "layers_ms_per_step": total_layer_ms}
-    print(json.dumps(line))
+    if b.rank == 0:
+        print(json.dumps(line))
 
 
 if __name__ == "__main__":

@@ -693,6 +693,35 @@ class AdaptiveCompressionModel(Model):
         _lib.check(_lib.lib.cic_adaptive_forward_phase(plan.handle, C.byref(io), C.byref(b["state"]), phase, tile0, hi - lo, h, w,
                                                        ptr(ws), ws.numel(), runtime.stream_ptr()))
 
+    def rate_sweep_device(self, img: torch.Tensor, mask: torch.Tensor, levels, on_level=None):
+        """The rate-control sweep of GAN_test.py:532-645 WITH reconstructions (BASELINE configs[2]): the reference runs the whole
+        model once per target bpp; the encoder convolutions and skips do not depend on the target, so they run once here and only
+        the Dense / latent-saliency / quantiser phase and the decoders + ROI blend run per level - same results as one full
+        predict per level.  img (n,H,W,3), mask (n,H,W,1) on the device; levels: target bpps.  `on_level(k, inputs, outputs)`
+        is called after every level with views of the persistent buffers (valid until the next level).  Returns hq_ratio
+        (levels, n) float64 on the device."""
+        if mask.dim() == 3:
+            mask = mask.unsqueeze(-1)
+        n, h, w, _ = img.shape
+        dev = img.device
+        b = self._phase_buffers(n, h, w, dev)
+        b["img"].copy_(img)
+        b["mask"].copy_(mask)
+        levels = [float(v) for v in levels]
+        ratios = torch.empty((len(levels), n), dtype=torch.float64, device=dev)
+        b["bpp"].fill_(levels[0] if levels else 1.0)
+        self._phase_call(b, _lib.PHASE_ENCODE, 0, n, h, w)
+        for k, level in enumerate(levels):
+            b["bpp"].fill_(level)
+            self._phase_call(b, _lib.PHASE_LATENT, 0, n, h, w)
+            self._phase_call(b, _lib.PHASE_DECODE, 0, n, h, w)
+            ratios[k].copy_(b["hq_ratio_sum"])
+            if on_level is not None:
+                on_level(k, [b["img"], b["mask"], b["bpp"]],
+                         {"blended": b["blended"], "dt": b["dt"], "hq_ratio_sum": b["hq_ratio_sum"],
+                          "hq_latent_q": b["hq_latent_q"], "lq_latent_q": b["lq_latent_q"]})
+        return ratios / float(h * w)
+
     def predict_phased(self, x, enc_chunks=None, dec_chunks=None, on_chunk=None, u8_io: bool = False, want_dt: bool = True):
         """predict() for host batches at full throughput: the forward is cut into three phases (include/cic.h): the encoder
         convolutions run per upload chunk while the next chunk's host->device copy is in flight, the Dense / saliency /

@@ -49,6 +49,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    # Blackwell proof: per-kernel counts of UTCHMMA[.2CTA] / LDTM / UTMALDG in the library just linked -> profiles/sass_summary.txt
+    tool = os.path.join(HERE, "..", "tools", "sass_summary.py")
+    if os.environ.get("CIC_SASS_SUMMARY", "1") != "0" and os.path.exists(tool):
+        s = subprocess.run([sys.executable, tool], capture_output=True, text=True)
+        if verbose or s.returncode != 0:
+            sys.stderr.write(s.stdout + s.stderr)
     return LIB
 
 

@@ -225,3 +225,101 @@ def test_gloo_world_size_2(tmp_path):
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
         assert "ok" in o
+
+
+def test_fixture_script_assigns_every_tensor(cic):
+    """tools/make_reference_fixtures.assign_layers (the inverse of the converter's map_layers) on duck-typed Keras layers: every
+    tensor of a sub-model lands in the layer the converter would read it back from."""
+    import importlib.util
+    mods = {}
+    for name in ("make_reference_fixtures", "convert_keras_h5"):
+        spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, "tools", name + ".py"))
+        mods[name] = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mods[name])
+    fx, conv = mods["make_reference_fixtures"], mods["convert_keras_h5"]
+
+    def layer(cls):
+        store = {}
+        return type(cls, (), {"set_weights": lambda self, ws: store.__setitem__("w", list(ws)), "get_weights": lambda self: store.get("w", [])})()
+
+    class Var:
+        def assign(self, v):
+            self.v = np.asarray(v)
+
+        def numpy(self):
+            return self.v
+    ref = cic.weights.synthetic_encoder((64, 64, 3), 32, True, seed=1)
+    att = type("SelfAttention", (), {})()
+    att.query_conv, att.key_conv, att.value_conv, att.gamma = layer("Conv2D"), layer("Conv2D"), layer("Conv2D"), Var()
+    layers = [layer("InputLayer"), layer("Conv2D"), layer("LeakyReLU"), layer("Conv2D"), layer("BatchNormalization"), layer("Conv2D"),
+              layer("BatchNormalization"), att, layer("Conv2D"), layer("BatchNormalization"), layer("Flatten"), layer("Dense")]
+    assert fx.assign_layers(layers, "encoder", ref) == len(ref)
+    back = conv.map_layers(layers, "encoder")
+    assert set(back) == set(ref) and all(np.array_equal(back[k], ref[k]) for k in ref)
+    gref = cic.weights.synthetic_generator(32, (64, 64, 3), seed=2)
+    gl = [layer("Dense"), layer("Reshape")] + [layer("BatchNormalization")] + sum(
+        [[layer("Conv2DTranspose"), layer("BatchNormalization"), layer("Concatenate")] for _ in range(4)], []) + [layer("Conv2D")]
+    assert fx.assign_layers(gl, "generator", gref) == len(gref)
+    back = conv.map_layers(gl, "generator")
+    assert all(np.array_equal(back[k], gref[k]) for k in gref)
+    aref = cic.weights.synthetic_autoencoder(seed=3)
+    al = [layer("Conv2D") if i % 2 == 0 else layer("MaxPooling2D") for i in range(14)]
+    assert fx.assign_layers(al, "autoencoder", aref) == len(aref)
+
+
+def test_saliency_front_end_follows_the_reference(cic, monkeypatch):
+    """compute_saliency_map with a stubbed cv2.saliency (opencv-contrib is absent): 'combined' mixes the RAW maps 0.6 / 0.4 and
+    normalises only the sum (GAN_functions.py:95-99); failures fall back like :84-91; the input-range rule of :63-66 is kept."""
+    import types
+    import cv2
+    sal = cic.saliency
+    spec_map = np.array([[0.2, 0.4], [0.1, 0.0]], np.float32)
+    fine_map = np.array([[10.0, 0.0], [30.0, 20.0]], np.float32)       # native range differs from the spectral map's
+    seen = {}
+
+    def algo(out, ok=True):
+        def compute(self, img):
+            seen["dtype"], seen["shape"], seen["max"] = img.dtype, img.shape, int(img.max())
+            return ok, out
+        return type("Algo", (), {"computeSaliency": compute})()
+    state = {"ok_s": True, "ok_f": True}
+    stub = types.SimpleNamespace(StaticSaliencySpectralResidual_create=lambda: algo(spec_map, state["ok_s"]),
+                                 StaticSaliencyFineGrained_create=lambda: algo(fine_map, state["ok_f"]))
+    monkeypatch.setattr(cv2, "saliency", stub, raising=False)
+    img = np.zeros((2, 2, 3), np.float32)                               # [-1, 1] convention: 0 -> 127
+    got = sal.compute_saliency_map(img, method="combined")
+    want = 0.6 * spec_map + 0.4 * fine_map
+    np.testing.assert_allclose(got, want / want.max(), rtol=1e-6)
+    assert seen["dtype"] == np.uint8 and seen["max"] == 127
+    sal.compute_saliency_map(np.full((2, 2, 3), 200.0, np.float32), method="spectral_residual")
+    assert seen["max"] == 200                                           # max > 1: cast as is (:65-66)
+    state["ok_f"] = False
+    np.testing.assert_array_equal(sal.compute_saliency_map(img, method="combined"), spec_map)     # surviving map, un-normalised (:86)
+    state["ok_s"] = False
+    np.testing.assert_array_equal(sal.compute_saliency_map(img, method="combined"), np.ones((2, 2), np.float32))
+    np.testing.assert_array_equal(sal.compute_saliency_map(img, method="fine_grained"), np.ones((2, 2), np.float32))
+    with pytest.raises(ValueError, match="Unsupported"):
+        sal.compute_saliency_map(img, method="nope")
+    # the non-smooth mask uses the adaptive threshold of :172-194 (Otsu vs 70 % histogram share, clamped to [0.05, 0.5])
+    rng = np.random.default_rng(0)
+    m = rng.random((64, 64)).astype(np.float32) ** 3
+    thr = sal.adaptive_threshold(m)
+    assert 0.05 <= thr <= 0.5
+    np.testing.assert_array_equal(sal.create_saliency_mask(m, smooth=False), (m > thr).astype(np.float32))
+    np.testing.assert_array_equal(sal.create_saliency_mask(m, threshold=0.3, smooth=False), (m > 0.3).astype(np.float32))
+    sm = sal.create_saliency_mask(m, smooth=True)
+    assert sm.max() == pytest.approx(1.0) and sm.shape == m.shape
+
+
+def test_model_caches_follow_the_plan_generation(cic):
+    """set_weights_dict drops the plan AND everything that holds raw pointers into it (graph caches were keyed by id())."""
+    import train_autoencoder as tr
+    m = tr.build_autoencoder((32, 32, 3))
+    m.__dict__["_pipe_graphs"] = {"k": 1}
+    m.__dict__["_phase_graphs"] = {"k": 1}
+    m.__dict__["_phase_cache"] = {"k": 1}
+    assert m._weights is None                                           # Keras-default weights are drawn lazily
+    m.set_weights_dict(cic.weights.synthetic_autoencoder(seed=1))
+    assert not any(k in m.__dict__ for k in ("_pipe_graphs", "_phase_graphs", "_phase_cache")) and m._plan is None
+    shapes = cic.weights.adaptive_shapes((256, 256, 3), 512)            # no allocation: zero-stride views
+    assert shapes["hq_encoder"]["dense/kernel"].shape == (131072, 1024) and shapes["hq_encoder"]["dense/kernel"].strides == (0, 0)

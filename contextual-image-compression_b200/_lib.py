@@ -94,6 +94,8 @@ PROTOTYPES = {
     "cic_f32_signed_to_u8": (_i, [_vp, _vp, _sz, _vp]),
     "cic_metrics_psnr_ssim_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _vp]),
     "cic_metrics_psnr_ssim_f32_fast": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _vp]),
+    "cic_msssim_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "cic_msssim_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _vp, _sz, _vp]),
     "cic_metric_sums": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "cic_metrics_psnr_ssim_gray_u8": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
 }

@@ -416,6 +416,164 @@ metrics_f32_fast_kernel(const float* __restrict__ A, const float* __restrict__ B
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// float32 RGB path, warp-per-strip (the evaluation of the codec's batches; cic_metrics_psnr_ssim_f32_fast for C == 3, W % 4 == 0)
+// ------------------------------------------------------------------------------------------
+// The tile kernels above stage a 38 x 38 halo tile in shared memory and were bound by instruction issue (283 instructions per
+// pixel and channel: 4-byte halo loads with index arithmetic, two shared-memory round trips, block barriers).  Here one warp
+// walks down a strip of the image: a row of the interleaved NHWC image is a 1-D array of 3 W floats in which the 7 taps of a
+// channel are 3 elements apart.  Every lane owns 12 consecutive elements (three aligned 128-bit loads per image and row = four
+// RGB pixels, so element j has channel j % 3); lanes 1..30 produce output, lanes 0 and 31 only carry the 9-element halo.
+//   vertical:   five running window sums per element (a, b, aa, bb, ab of centred values) slide down the strip in registers;
+//               the row that leaves the 7-row window comes back from a 7-slot ring in shared memory (raw centred a, b: 96 B
+//               per thread and row) - no re-read from global memory, no block barrier;
+//   horizontal: 9 + 9 halo values per quantity arrive by warp shuffle from the neighbouring lanes; the first three outputs of
+//               a lane are full 7-tap sums, the other nine slide (+ in, - out): 36 adds per 12 outputs and quantity;
+//   SSIM:       as metrics_f32_fast_kernel (float32 on centred data: variances are shift invariant; the strip's first pixel is
+//               the reference), summed per row in float32, per strip in double; squared error in double per element.
+// One warp per CTA, so every branch on the strip geometry is uniform by construction and the shuffles need no re-convergence.
+// Strips overlap by 6 rows (R owned rows + 3 above and below are read): redundant reads hit L2.
+constexpr int MS_E = 12;             // elements (floats of the interleaved row) per thread and row: 3 x float4 = 4 RGB pixels
+constexpr int MS_OUT = 30 * MS_E;    // output elements per warp and row: lanes 1..30 (lanes 0 and 31 carry the 9-element halo)
+constexpr int MS_WARPS = 1;          // one warp per CTA: every branch on the strip geometry is provably uniform (no WARPSYNC around the shuffles)
+constexpr int MS_RING_BYTES = 7 * 6 * 32 * MS_WARPS * 16;  // 7 rows x (3 + 3) float4 per thread
+
+__global__ void __launch_bounds__(32 * MS_WARPS, 10)
+metrics_f32_strip_kernel(const float* __restrict__ A, const float* __restrict__ Bm, double* __restrict__ acc, int batch, int H, int W, int R,
+                         int bands, int segs, float pre_add, float pre_mul, float c1, float c2, float cov_norm) {
+  extern __shared__ float4 ms_ring[];  // [warp][slot 7][k 6][lane 32]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long wg = (long long)blockIdx.x * MS_WARPS + warp;
+  const int band = (int)(wg % bands), seg = (int)((wg / bands) % segs), img = (int)(wg / ((long long)bands * segs));
+  const int y0 = seg * R, y1 = min(y0 + R, H);
+  const int row_elems = 3 * W;
+  const int e_base = band * MS_OUT - MS_E + MS_E * lane;            // first element of this thread (a multiple of 12: channel = j % 3)
+  const bool in_row = e_base >= 0 && e_base < row_elems;            // row_elems % 12 == 0: a thread is inside or outside as a whole
+  const bool owner = in_row && lane >= 1 && lane <= 30;
+  const int e_load = min(max(e_base, 0), row_elems - MS_E);
+  const size_t img_base = (size_t)img * H * row_elems;
+  float4* ring = ms_ring + (size_t)warp * 7 * 6 * 32 + lane;
+  // centring reference: the first owned pixel of the strip (variances are shift invariant; float32 window sums of centred
+  // values are accurate to ~1e-7 of the window's energy where the c2 term matters)
+  float ma[3], mb[3];
+  {
+    const int er = min(band * MS_OUT, row_elems - 3);
+    const float* pa = A + img_base + (size_t)y0 * row_elems + er;
+    const float* pb = Bm + img_base + (size_t)y0 * row_elems + er;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      ma[c] = __fmul_rn(__fadd_rn(__ldg(pa + c), pre_add), pre_mul);
+      mb[c] = __fmul_rn(__fadd_rn(__ldg(pb + c), pre_add), pre_mul);
+    }
+  }
+  float s[5][MS_E];   // vertical window sums of a, b, aa, bb, ab (centred)
+#pragma unroll
+  for (int q = 0; q < 5; ++q)
+#pragma unroll
+    for (int j = 0; j < MS_E; ++j) s[q][j] = 0.f;
+  double sse = 0.0, ssum = 0.0;
+  const float inv49 = 1.0f / 49.0f;
+  const int px0 = e_base / 3;   // pixel of element 0 (e_base may be negative only for lane 0 of band 0, never an owner)
+  int slot = 0;
+  for (int y = y0 - 3, i = 0; y < y1 + 3; ++y, ++i) {
+    const int yr = min(max(y, 0), H - 1);
+    const float4* ra = reinterpret_cast<const float4*>(A + img_base + (size_t)yr * row_elems + e_load);
+    const float4* rb = reinterpret_cast<const float4*>(Bm + img_base + (size_t)yr * row_elems + e_load);
+    float a[MS_E], b[MS_E];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float4 va = __ldg(ra + k), vb = __ldg(rb + k);
+      a[4 * k] = va.x; a[4 * k + 1] = va.y; a[4 * k + 2] = va.z; a[4 * k + 3] = va.w;
+      b[4 * k] = vb.x; b[4 * k + 1] = vb.y; b[4 * k + 2] = vb.z; b[4 * k + 3] = vb.w;
+    }
+    const bool own_row = owner && y >= y0 && y < y1;
+    double sse_row = 0.0;
+#pragma unroll
+    for (int j = 0; j < MS_E; ++j) {
+      const float va = __fmul_rn(__fadd_rn(a[j], pre_add), pre_mul);
+      const float vb = __fmul_rn(__fadd_rn(b[j], pre_add), pre_mul);
+      const float d = __fsub_rn(va, vb);
+      sse_row += (double)__fmul_rn(d, d);
+      a[j] = va - ma[j % 3];
+      b[j] = vb - mb[j % 3];
+    }
+    if (own_row) sse += sse_row;
+    // vertical sliding sums: the row that leaves the window (y - 7) comes back from the ring
+    if (i >= 7) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const float4 oa = ring[(slot * 6 + k) * 32], ob = ring[(slot * 6 + 3 + k) * 32];
+        const float xa[4] = {oa.x, oa.y, oa.z, oa.w}, xb[4] = {ob.x, ob.y, ob.z, ob.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int j = 4 * k + t;
+          s[0][j] -= xa[t];
+          s[1][j] -= xb[t];
+          s[2][j] = fmaf(-xa[t], xa[t], s[2][j]);
+          s[3][j] = fmaf(-xb[t], xb[t], s[3][j]);
+          s[4][j] = fmaf(-xa[t], xb[t], s[4][j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      ring[(slot * 6 + k) * 32] = make_float4(a[4 * k], a[4 * k + 1], a[4 * k + 2], a[4 * k + 3]);
+      ring[(slot * 6 + 3 + k) * 32] = make_float4(b[4 * k], b[4 * k + 1], b[4 * k + 2], b[4 * k + 3]);
+    }
+    if (++slot == 7) slot = 0;
+#pragma unroll
+    for (int j = 0; j < MS_E; ++j) {
+      s[0][j] += a[j];
+      s[1][j] += b[j];
+      s[2][j] = fmaf(a[j], a[j], s[2][j]);
+      s[3][j] = fmaf(b[j], b[j], s[3][j]);
+      s[4][j] = fmaf(a[j], b[j], s[4][j]);
+    }
+    const int yc = y - 3;   // centre row of the window that is complete now (warp-uniform conditions below)
+    if (i < 6 || yc < max(y0, 3) || yc >= min(y1, H - 3)) continue;
+    // horizontal 7-tap sums along the stride-3 (same channel) sequences: 9 halo elements from each neighbour lane
+    float e[5][MS_E];
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+      float x[MS_E + 18];
+#pragma unroll
+      for (int j = 0; j < 9; ++j) {
+        x[j] = __shfl_up_sync(0xffffffffu, s[q][j + 3], 1);
+        x[MS_E + 9 + j] = __shfl_down_sync(0xffffffffu, s[q][j], 1);
+      }
+#pragma unroll
+      for (int j = 0; j < MS_E; ++j) x[9 + j] = s[q][j];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) e[q][j] = ((x[j] + x[j + 3]) + (x[j + 6] + x[j + 9])) + ((x[j + 12] + x[j + 15]) + x[j + 18]);
+#pragma unroll
+      for (int j = 3; j < MS_E; ++j) e[q][j] = e[q][j - 3] + (x[j + 18] - x[j - 3]);
+    }
+    if (owner) {
+      float row_sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < MS_E; ++j) {
+        const int gx = px0 + j / 3;
+        const float e0 = e[0][j] * inv49, e1 = e[1][j] * inv49, e2 = e[2][j] * inv49, e3 = e[3][j] * inv49, e4 = e[4][j] * inv49;
+        const float vx = cov_norm * (e2 - e0 * e0);
+        const float vy = cov_norm * (e3 - e1 * e1);
+        const float vxy = cov_norm * (e4 - e0 * e1);
+        const float ux = e0 + ma[j % 3], uy = e1 + mb[j % 3];
+        const float a1 = 2.0f * ux * uy + c1, a2 = 2.0f * vxy + c2;
+        const float b1 = ux * ux + uy * uy + c1, b2 = vx + vy + c2;
+        const float sv = __fdividef(a1 * a2, b1 * b2);
+        row_sum += (gx >= 3 && gx < W - 3) ? sv : 0.f;
+      }
+      ssum += (double)row_sum;
+    }
+  }
+  sse = warp_sum(sse);
+  ssum = warp_sum(ssum);
+  if (lane == 0) {
+    atomicAdd(acc + (size_t)img * 4 + 3, sse);
+    atomicAdd(acc + (size_t)img * 4 + 1, ssum);
+  }
+}
+
 // out[b] = {psnr, ssim, mse, sse}
 __global__ void metrics_finalize_kernel(double* __restrict__ acc, int batch, double n_elems, double n_ssim,
                                         double data_range) {
@@ -567,6 +725,32 @@ static int metrics_f32_impl(const float* d_a, const float* d_b, double* d_out, i
       CIC_CHECK_CUDA(cudaFuncSetAttribute(metrics_f32_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
       attr_set.done();
     }
+  }
+  if (fast && channels == 3 && w % 4 == 0 && w >= 8 && (((uintptr_t)d_a | (uintptr_t)d_b) & 15) == 0 && CIC_KNOB("CIC_METRICS_STRIP", 1)) {
+    static DeviceOnce strip_attr;
+    if (strip_attr.todo()) {
+      CIC_CHECK_CUDA(cudaFuncSetAttribute(metrics_f32_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MS_RING_BYTES));
+      strip_attr.done();
+    }
+    const int bands = (3 * w + MS_OUT - 1) / MS_OUT;
+    // rows per strip: as tall as possible (6 of R + 6 rows read are overlap) while the grid still fills the resident-warp slots
+    const long long slots = (long long)sm_count() * 10;
+    int R = CIC_KNOB("CIC_METRICS_ROWS", 0);
+    if (R <= 0) {
+      R = 128;
+      while (R > 16 && (long long)batch * bands * ((h + R - 1) / R) < slots) R >>= 1;
+    }
+    const int segs = (h + R - 1) / R;
+    const long long warps = (long long)batch * bands * segs;
+    CIC_REQUIRE(warps < 2147483647LL, "metrics: too many strips");
+    metrics_f32_strip_kernel<<<(unsigned)warps, 32, MS_RING_BYTES, st>>>(d_a, d_b, d_out, batch, h, w, R, bands, segs, pre_add, pre_mul, c1, c2, cov_norm);
+    CIC_COUNT_LAUNCH();
+    CIC_CHECK_LAUNCH("metrics_f32_strip_kernel");
+    metrics_finalize_kernel<<<(batch + 127) / 128, 128, 0, st>>>(d_out, batch, (double)h * w * channels,
+                                                                 (double)(h - 6) * (w - 6) * channels, (double)data_range);
+    CIC_COUNT_LAUNCH();
+    CIC_CHECK_LAUNCH("metrics_finalize_kernel");
+    return CIC_OK;
   }
   for (int b0 = 0; b0 < batch; b0 += 65535) {
     int nb = batch - b0 < 65535 ? batch - b0 : 65535;

@@ -224,6 +224,25 @@ def metrics_f32(a, b, signed_range: bool, data_range: float = 1.0, fast: bool = 
     return out
 
 
+def ms_ssim_f32(a, b, signed_range: bool, data_range: float = 1.0) -> torch.Tensor:
+    """(B,) float64 MS-SSIM per image (five scales, 11x11 Gaussian window; see cic_msssim_f32 - an extra with no reference call
+    site, BASELINE configs[4]).  Images (B,H,W,C) with H, W >= 176; signed_range maps [-1,1] -> [0,1] first."""
+    a, b = to_device_f32(a), to_device_f32(b)
+    if a.dim() == 3:
+        a, b = a.unsqueeze(0), b.unsqueeze(0)
+    if a.shape != b.shape:
+        raise ValueError(f"shape mismatch {tuple(a.shape)} vs {tuple(b.shape)}")
+    n, h, w, c = a.shape
+    if min(h, w) < 176:
+        raise ValueError(f"MS-SSIM with five scales needs H, W >= 176, got {h}x{w}")
+    out = torch.empty((n,), dtype=torch.float64, device=a.device)
+    pre_add, pre_mul = (1.0, 0.5) if signed_range else (0.0, 1.0)
+    ws = torch.empty(int(_lib.lib.cic_msssim_workspace_bytes(n, h, w, c)), dtype=torch.uint8, device=a.device)
+    _lib.check(_lib.lib.cic_msssim_f32(ptr(a), ptr(b), ptr(out), n, h, w, c, pre_add, pre_mul, float(data_range), ptr(ws), ws.numel(),
+                                       runtime.stream_ptr()))
+    return out
+
+
 def metric_sums(metrics: torch.Tensor, dt_sum: torch.Tensor, img_px: int, latent_hq: int, latent_lq: int, tile_px: int) -> torch.Tensor:
     """(1, 8) float64 row [sum psnr, sum ssim, sum mse, sum actual_bpp, sum hq_ratio, 0, n, 0] of one evaluated batch (dist.METRIC_FIELDS)
     from metrics_f32's (n,4) output and the per-image dt sums, in one launch (bpp accounting of GAN_test.py:310-325)."""

@@ -272,6 +272,15 @@ int cic_metrics_psnr_ssim_f32(const float* d_a, const float* d_b, double* d_out,
 int cic_metrics_psnr_ssim_f32_fast(const float* d_a, const float* d_b, double* d_out, int batch, int h, int w, int channels,
                                    float pre_add, float pre_mul, float data_range, void* stream);
 
+/* MS-SSIM per image (BASELINE.json configs[4]).  The reference has no MS-SSIM call site (it evaluates single-scale SSIM,
+ * GAN_functions.py:745-748); this is Wang-Simoncelli-Bovik 2003 as tf.image.ssim_multiscale / pytorch_msssim implement it: five
+ * scales (weights 0.0448, 0.2856, 0.3001, 0.2363, 0.1333), 11x11 Gaussian window sigma 1.5 as a valid correlation, 2x2 average
+ * pooling between scales, per channel, mean over channels.  Inputs (B,H,W,C) float32, v = (x + pre_add) * pre_mul as above; h, w >=
+ * 176.  d_out (B,) doubles.  PARITY UNPINNED: checked against a float64 numpy restatement of this definition only. */
+size_t cic_msssim_workspace_bytes(int batch, int h, int w, int channels);
+int cic_msssim_f32(const float* d_a, const float* d_b, double* d_out, int batch, int h, int w, int channels, float pre_add,
+                   float pre_mul, float data_range, void* d_workspace, size_t workspace_bytes, void* stream);
+
 /* Metric sums of one evaluated batch in one launch: d_metrics (n,4) doubles as written by cic_metrics_psnr_ssim_f32*, d_dt_sum (n,)
  * doubles as written by cic_roi_mask_blend / cic_adaptive_forward (sum of dt per image of img_px pixels).  Per image
  * hq_ratio = dt_sum / img_px, total_bits = hq_ratio * latent_hq * 32 + (1 - hq_ratio) * latent_lq * 32, actual_bpp = total_bits /

@@ -119,3 +119,55 @@ def symbol_entropy_bits(symbols: np.ndarray) -> float:
     _, counts = np.unique(np.asarray(symbols).astype(np.int64), return_counts=True)
     p = counts / counts.sum()
     return float(-(p * np.log2(p)).sum() * counts.sum())
+
+
+# ---- MS-SSIM (BASELINE configs[4] "PSNR/MS-SSIM per image") -----------------------------------------------------------------
+# The reference computes single-scale SSIM only (GAN_functions.py:745-748); MS-SSIM has no call site there, so this is the
+# published algorithm (Wang, Simoncelli, Bovik 2003) in the form the common implementations use (tf.image.ssim_multiscale,
+# pytorch_msssim): five scales, weights below, 11x11 Gaussian window sigma 1.5 applied as a VALID separable correlation, K1 =
+# 0.01, K2 = 0.03, population (co)variances, 2x2 average pooling between scales, per channel
+#   msssim_c = prod_{j<5} relu(mean cs_j)^w_j * relu(mean ssim_5)^w_5,   result = mean over channels.
+# PARITY UNPINNED: float64 numpy restatement of that definition; the CUDA kernel is compared against it only.
+MSSSIM_WEIGHTS = (0.0448, 0.2856, 0.3001, 0.2363, 0.1333)
+
+
+def gaussian_window(size: int = 11, sigma: float = 1.5) -> np.ndarray:
+    x = np.arange(size, dtype=np.float64) - size // 2
+    g = np.exp(-(x * x) / (2.0 * sigma * sigma))
+    return g / g.sum()
+
+
+def _valid_gauss(x: np.ndarray, g: np.ndarray) -> np.ndarray:
+    from scipy.ndimage import correlate1d
+    r = len(g) // 2
+    y = correlate1d(correlate1d(x, g, axis=0, mode="constant"), g, axis=1, mode="constant")
+    return y[r:-r, r:-r]
+
+
+def ms_ssim(img1: np.ndarray, img2: np.ndarray, data_range: float = 1.0) -> float:
+    """MS-SSIM of two (H,W,C) images in [0, data_range]; min(H, W) > 160."""
+    a, b = np.asarray(img1, np.float64), np.asarray(img2, np.float64)
+    if a.ndim == 2:
+        a, b = a[..., None], b[..., None]
+    g = gaussian_window()
+    c1, c2 = (0.01 * data_range) ** 2, (0.03 * data_range) ** 2
+    vals = []
+    for c in range(a.shape[2]):
+        x, y = a[..., c], b[..., c]
+        prod = 1.0
+        for j, wgt in enumerate(MSSSIM_WEIGHTS):
+            mx, my = _valid_gauss(x, g), _valid_gauss(y, g)
+            sxx = _valid_gauss(x * x, g) - mx * mx
+            syy = _valid_gauss(y * y, g) - my * my
+            sxy = _valid_gauss(x * y, g) - mx * my
+            cs = (2.0 * sxy + c2) / (sxx + syy + c2)
+            if j < len(MSSSIM_WEIGHTS) - 1:
+                prod *= max(cs.mean(), 0.0) ** wgt
+                h2, w2 = x.shape[0] // 2, x.shape[1] // 2            # 2x2 average pooling (floor)
+                x = x[:2 * h2, :2 * w2].reshape(h2, 2, w2, 2).mean(axis=(1, 3))
+                y = y[:2 * h2, :2 * w2].reshape(h2, 2, w2, 2).mean(axis=(1, 3))
+            else:
+                ss = ((2.0 * mx * my + c1) / (mx * mx + my * my + c1)) * cs
+                prod *= max(ss.mean(), 0.0) ** wgt
+        vals.append(prod)
+    return float(np.mean(vals))

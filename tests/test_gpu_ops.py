@@ -283,3 +283,20 @@ def test_self_attention_matches_oracle(cic, hw, C):
     np.testing.assert_allclose(got, want, atol=3e-5, rtol=1e-5)
     ident = cic.ops.self_attention(x, w["attn/query/kernel"], None, w["attn/key/kernel"], None, w["attn/value/kernel"], None, 0.0)
     np.testing.assert_array_equal(ident.cpu().numpy(), x)                        # gamma = 0 -> exact identity
+
+
+@pytest.mark.parametrize("n,h,w", [(2, 176, 208), (1, 256, 256), (1, 360, 500)])
+def test_ms_ssim_matches_numpy_restatement(cic, n, h, w):
+    """cic_msssim_f32 (BASELINE configs[4] extra, parity unpinned: no reference call site) against the float64 numpy restatement
+    of Wang 2003 / tf.image.ssim_multiscale in oracle/metrics.py."""
+    a = cic.synth.to_signed_range(cic.synth.synth_images_u8(n, h, w, seed=90))
+    rng = np.random.default_rng(1)
+    b = np.clip(a + rng.normal(0, 0.08, a.shape).astype(np.float32), -1, 1).astype(np.float32)
+    got = cic.ops.ms_ssim_f32(a, b, signed_range=True).cpu().numpy()
+    for i in range(n):
+        want = metrics.ms_ssim((a[i] + 1) / 2, (b[i] + 1) / 2, data_range=1.0)
+        assert abs(got[i] - want) < 1e-5, (got[i], want)
+    same = cic.ops.ms_ssim_f32(a, a, signed_range=True).cpu().numpy()
+    assert np.all(np.abs(same - 1.0) < 1e-6)
+    with pytest.raises(ValueError, match="176"):
+        cic.ops.ms_ssim_f32(a[:, :100], b[:, :100], signed_range=True)

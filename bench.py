@@ -17,12 +17,14 @@ images are sharded over the ranks, weights replicated, no data-path collective; 
 metric sums, inside the timed region.
 
 `value`        MPix/s with inputs resident in HBM, CUDA events on the launch stream, max over ranks.
-`e2e`          same metric through the public API with pinned HOST buffers: adaptive_model.predict_phased(u8_io=True) - the
+`e2e`          same metric through the public API with pinned HOST buffers: adaptive_model.predict_stream(u8_io=True) - the
                reference's file-boundary pixel format on the wire (uint8 RGB image up: load_and_preprocess_image,
                GAN_functions.py:24-39; uint8 reconstruction down: save_image, :41-50) - host->device copy of image / mask / bpp and
-               device->host read of all five model outputs every step, overlapped chunk by chunk.  `e2e_f32_io` is the same with
-               float32 images both ways (the headline of round 1).  `host_copy_floor_ms`: the same bytes moved by plain concurrent
-               copies with no kernel running, all ranks at once - the ceiling the host side sets.
+               device->host read of all five model outputs for every step inside the timed region; consecutive steps overlap
+               (upload of the next, kernels of this, download of the previous).  `e2e_single_call`: one synchronous
+               predict_phased call per step (round 1's API).  `e2e_f32_io`: float32 images both ways.  `host_copy_floor_ms`: the same
+               bytes moved by plain concurrent copies with no kernel running, all ranks at once; `frac_of_roof` = max(device step,
+               copy floor) / e2e step - 1.0 means the end-to-end leg is as fast as its slower resource allows.
 `roofline`     the dominant kernel class: algorithmic FLOPs of its layers / their summed device time (CUDA events around every
                launch inside the timed steps) against the measured sustained bf16 peak; `hbm_kernels` the bandwidth kernels.
 `parity`       GPU outputs of this very run against the CPU oracle on sampled tiles: symbol mismatches (total / outside the 1e-3
@@ -465,25 +467,69 @@ class Bench:
         # ---- e2e: pinned host buffers in, host buffers out --------------------------------------------------------------------
         e2e_steps, e2e_warm = (steps, 3) if headline else (max(2, steps), 3)
 
-        def e2e_leg(u8, want_dt=True):
-            ms, last = self.timed(make_e2e(u8, want_dt), e2e_steps, e2e_warm, wall=True)
-            outs, sums_host = last
-            scale = n_img / sizes[-1]                                           # outs are the last chunk's
+        def bytes_of(u8, outs):
+            scale = n_img / sizes[-1]                                           # outs are the last forward call's
             h2d = int(((h_img8 if u8 else h_img)[:chunk].numel() * (1 if u8 else 4) + h_mask[:chunk].numel() * 4 + chunk * 4) * n_img / chunk)
-            d2h = int(sum(o.nbytes for o in outs) * scale + sums_host.numel() * 8)
+            d2h = int(sum(o.nbytes for o in outs) * scale + nfields * 8)
+            return h2d, d2h
+
+        def finish_leg(ms, u8, outs):
+            h2d, d2h = bytes_of(u8, outs)
             floor = self.host_copy_floor(h2d, d2h)
             return {"value": px_step / (ms * 1e-3) / 1e6, "unit": "MPix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms, "host_copy_floor_ms": floor, "frac_of_host_copy_floor": floor / ms if ms else None,
+                    "ms_per_step": ms, "device_step_ms": ms_step, "host_copy_floor_ms": floor,
+                    "frac_of_roof": max(ms_step, floor) / ms if ms else None,
                     "host_gbs_achieved": (h2d + d2h) * self.world / (ms * 1e-3) / 1e9}
-        e2e = e2e_leg(True)
-        e2e["api"] = "adaptive_model.predict_phased(u8_io=True): uint8 RGB image up, uint8 reconstruction down (GAN_functions.py:24-50), mask / dt / latents / rd_params float32"
+
+        def single_call_leg(u8, want_dt=True):
+            ms, last = self.timed(make_e2e(u8, want_dt), e2e_steps, e2e_warm, wall=True)
+            return finish_leg(ms, u8, last[0])
+
+        def stream_leg(u8, want_dt=True):
+            """K steps through adaptive_model.predict_stream: every forward call's inputs come from pinned host memory and all its
+            outputs go back to pinned host memory inside the timed region; consecutive calls overlap (upload of the next, kernels of
+            this, download of the previous).  The metric sums of a step are all-reduced and copied to the host asynchronously."""
+            src = [h_img8 if u8 else h_img, h_mask, h_bpp]
+            sums_host = torch.zeros((max(e2e_steps, e2e_warm), nfields), dtype=torch.float64).pin_memory()
+            last = {}
+
+            def run(nsteps):
+                def gen():
+                    for _ in range(nsteps):
+                        for k in sizes:
+                            yield [t[:k] for t in src]
+                tot, seen, step = None, 0, 0
+                for outs, part in am.predict_stream(gen(), on_batch=on_chunk, u8_io=u8, want_dt=want_dt):
+                    tot = part.clone() if tot is None else tot + part
+                    seen += 1
+                    last["outs"] = outs
+                    if seen == len(sizes):                                        # a step is complete: the one exchange step of the path
+                        sums_host[step].copy_(cic.dist.allreduce_metric_sums(tot)[0], non_blocking=True)
+                        tot, seen, step = None, 0, step + 1
+                torch.cuda.synchronize()
+            run(e2e_warm)
+            torch.cuda.synchronize()
+            cic.dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            run(e2e_steps)
+            ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+            cic.dist.barrier()
+            ms = cic.dist.max_over_ranks(ms, device=self.dev)
+            return finish_leg(ms, u8, last["outs"])
+        nfields = len(cic.dist.METRIC_FIELDS)
+        e2e = stream_leg(True)
+        e2e["api"] = ("adaptive_model.predict_stream(u8_io=True): uint8 RGB image up, uint8 reconstruction down (GAN_functions.py:24-50), mask / dt / latents / "
+                      "rd_params float32; consecutive forward calls overlap on three streams")
+        e2e_single = single_call_leg(True)
+        e2e_single["api"] = "adaptive_model.predict_phased(u8_io=True): one synchronous call per batch, the batch chunked to hide its own copies"
         e2e_f32 = e2e_f32_nodt = None
         if headline:
-            e2e_f32 = e2e_leg(False)
-            e2e_f32["api"] = "adaptive_model.predict_phased: float32 image up, float32 reconstruction down (round 1's e2e)"
-            e2e_f32_nodt = e2e_leg(True, want_dt=False)
-            e2e_f32_nodt["api"] = "adaptive_model.predict_phased(u8_io=True, want_dt=False): hq_ratio instead of the bit-allocation map"
-        self.launches += launches_per_step * (e2e_steps + e2e_warm) * (3 if headline else 1)
+            e2e_f32 = stream_leg(False)
+            e2e_f32["api"] = "adaptive_model.predict_stream: float32 image up, float32 reconstruction down"
+            e2e_f32_nodt = stream_leg(True, want_dt=False)
+            e2e_f32_nodt["api"] = "adaptive_model.predict_stream(u8_io=True, want_dt=False): hq_ratio instead of the bit-allocation map"
+        self.launches += launches_per_step * (e2e_steps + e2e_warm) * (4 if headline else 2)
 
         # ---- bandwidth kernels of the path (headline only) ----------------------------------------------------------------------
         if headline:
@@ -533,6 +579,7 @@ class Bench:
                 "e2e": e2e, "gpu_launches": None, "roofline": roofline, "parity": par, "quality": quality}
         if clocks is not None:
             line["clocks"] = clocks
+        line["e2e_single_call"] = e2e_single
         if e2e_f32 is not None:
             line["e2e_f32_io"], line["e2e_u8_io_no_dt"] = e2e_f32, e2e_f32_nodt
         if cpu is not None:

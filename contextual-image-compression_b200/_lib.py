@@ -89,6 +89,10 @@ PROTOTYPES = {
     "cic_roi_mask_blend": (_i, [_vp] * 7 + [_i, _i, _i, _vp]),
     "cic_hq_ratio_sweep": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp]),
     "cic_symbol_entropy_bits": (_i, [_vp, _vp, _i, _i, _vp]),
+    "cic_rans_max_bytes": (_sz, [_i, _i]),
+    "cic_rans_workspace_bytes": (_sz, [_i, _i]),
+    "cic_rans_encode": (_i, [_vp, _i, _i, _vp, _sz, _vp, _vp, _sz, _vp]),
+    "cic_rans_decode": (_i, [_vp, _sz, _vp, _i, _i, _vp]),
     "cic_f32_to_u8_trunc": (_i, [_vp, _vp, _sz, _f, _vp]),
     "cic_u8_to_f32_signed": (_i, [_vp, _vp, _sz, _vp]),
     "cic_f32_signed_to_u8": (_i, [_vp, _vp, _sz, _vp]),

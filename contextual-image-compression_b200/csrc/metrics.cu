@@ -424,27 +424,29 @@ metrics_f32_fast_kernel(const float* __restrict__ A, const float* __restrict__ B
 // walks down a strip of the image: a row of the interleaved NHWC image is a 1-D array of 3 W floats in which the 7 taps of a
 // channel are 3 elements apart.  Every lane owns 12 consecutive elements (three aligned 128-bit loads per image and row = four
 // RGB pixels, so element j has channel j % 3); lanes 1..30 produce output, lanes 0 and 31 only carry the 9-element halo.
-//   vertical:   five running window sums per element (a, b, aa, bb, ab of centred values) slide down the strip in registers;
+//   vertical:   four running window sums per element (a, b, aa + bb, ab of centred values: SSIM needs vx + vy, never vx alone)
+//               slide down the strip in registers;
 //               the row that leaves the 7-row window comes back from a 7-slot ring in shared memory (raw centred a, b: 96 B
 //               per thread and row) - no re-read from global memory, no block barrier;
 //   horizontal: 9 + 9 halo values per quantity arrive by warp shuffle from the neighbouring lanes; the first three outputs of
 //               a lane are full 7-tap sums, the other nine slide (+ in, - out): 36 adds per 12 outputs and quantity;
 //   SSIM:       as metrics_f32_fast_kernel (float32 on centred data: variances are shift invariant; the strip's first pixel is
-//               the reference), summed per row in float32, per strip in double; squared error in double per element.
+//               the reference), summed per row in float32, per strip in double; the squared error in double per element.
 // One warp per CTA, so every branch on the strip geometry is uniform by construction and the shuffles need no re-convergence.
 // Strips overlap by 6 rows (R owned rows + 3 above and below are read): redundant reads hit L2.
 constexpr int MS_E = 12;             // elements (floats of the interleaved row) per thread and row: 3 x float4 = 4 RGB pixels
 constexpr int MS_OUT = 30 * MS_E;    // output elements per warp and row: lanes 1..30 (lanes 0 and 31 carry the 9-element halo)
-constexpr int MS_WARPS = 1;          // one warp per CTA: every branch on the strip geometry is provably uniform (no WARPSYNC around the shuffles)
-constexpr int MS_RING_BYTES = 7 * 6 * 32 * MS_WARPS * 16;  // 7 rows x (3 + 3) float4 per thread
+constexpr int MS_Q = 4;              // window sums per element: a, b, aa + bb, ab (SSIM needs vx + vy, never vx alone)
+constexpr int MS_RING_BYTES = 7 * 6 * 32 * 16;  // 7 rows x (3 + 3) float4 per thread, one warp per CTA
 
-__global__ void __launch_bounds__(32 * MS_WARPS, 10)
+__global__ void __launch_bounds__(32, 10)
 metrics_f32_strip_kernel(const float* __restrict__ A, const float* __restrict__ Bm, double* __restrict__ acc, int batch, int H, int W, int R,
                          int bands, int segs, float pre_add, float pre_mul, float c1, float c2, float cov_norm) {
-  extern __shared__ float4 ms_ring[];  // [warp][slot 7][k 6][lane 32]
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long wg = (long long)blockIdx.x * MS_WARPS + warp;
-  const int band = (int)(wg % bands), seg = (int)((wg / bands) % segs), img = (int)(wg / ((long long)bands * segs));
+  extern __shared__ float4 ms_ring[];  // [slot 7][k 6][lane 32]
+  const int lane = threadIdx.x;
+  const unsigned wg = blockIdx.x;      // one warp per CTA: the strip geometry below is uniform by construction
+  const int band = (int)(wg % (unsigned)bands), seg = (int)((wg / (unsigned)bands) % (unsigned)segs), img = (int)(wg / ((unsigned)bands * (unsigned)segs));
+  (void)batch;
   const int y0 = seg * R, y1 = min(y0 + R, H);
   const int row_elems = 3 * W;
   const int e_base = band * MS_OUT - MS_E + MS_E * lane;            // first element of this thread (a multiple of 12: channel = j % 3)
@@ -452,7 +454,7 @@ metrics_f32_strip_kernel(const float* __restrict__ A, const float* __restrict__ 
   const bool owner = in_row && lane >= 1 && lane <= 30;
   const int e_load = min(max(e_base, 0), row_elems - MS_E);
   const size_t img_base = (size_t)img * H * row_elems;
-  float4* ring = ms_ring + (size_t)warp * 7 * 6 * 32 + lane;
+  float4* ring = ms_ring + lane;
   // centring reference: the first owned pixel of the strip (variances are shift invariant; float32 window sums of centred
   // values are accurate to ~1e-7 of the window's energy where the c2 term matters)
   float ma[3], mb[3];
@@ -466,28 +468,40 @@ metrics_f32_strip_kernel(const float* __restrict__ A, const float* __restrict__ 
       mb[c] = __fmul_rn(__fadd_rn(__ldg(pb + c), pre_add), pre_mul);
     }
   }
-  float s[5][MS_E];   // vertical window sums of a, b, aa, bb, ab (centred)
+  float s[MS_Q][MS_E];   // vertical window sums of a, b, aa + bb, ab (centred values)
 #pragma unroll
-  for (int q = 0; q < 5; ++q)
+  for (int q = 0; q < MS_Q; ++q)
 #pragma unroll
     for (int j = 0; j < MS_E; ++j) s[q][j] = 0.f;
   double sse = 0.0, ssum = 0.0;
   const float inv49 = 1.0f / 49.0f;
-  const int px0 = e_base / 3;   // pixel of element 0 (e_base may be negative only for lane 0 of band 0, never an owner)
+  const int px0 = e_base / 3;   // pixel of element 0 (e_base is negative only for lane 0 of band 0, never an owner)
   int slot = 0;
-  for (int y = y0 - 3, i = 0; y < y1 + 3; ++y, ++i) {
-    const int yr = min(max(y, 0), H - 1);
+  // software pipeline: the loads of row y + 1 are in flight while row y is processed (10 warps per SM cannot hide a DRAM round
+  // trip per row on their own)
+  float4 na[3], nb[3];
+  {
+    const int yr = min(max(y0 - 3, 0), H - 1);
     const float4* ra = reinterpret_cast<const float4*>(A + img_base + (size_t)yr * row_elems + e_load);
     const float4* rb = reinterpret_cast<const float4*>(Bm + img_base + (size_t)yr * row_elems + e_load);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { na[k] = __ldg(ra + k); nb[k] = __ldg(rb + k); }
+  }
+  for (int y = y0 - 3, i = 0; y < y1 + 3; ++y, ++i) {
     float a[MS_E], b[MS_E];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      const float4 va = __ldg(ra + k), vb = __ldg(rb + k);
-      a[4 * k] = va.x; a[4 * k + 1] = va.y; a[4 * k + 2] = va.z; a[4 * k + 3] = va.w;
-      b[4 * k] = vb.x; b[4 * k + 1] = vb.y; b[4 * k + 2] = vb.z; b[4 * k + 3] = vb.w;
+      a[4 * k] = na[k].x; a[4 * k + 1] = na[k].y; a[4 * k + 2] = na[k].z; a[4 * k + 3] = na[k].w;
+      b[4 * k] = nb[k].x; b[4 * k + 1] = nb[k].y; b[4 * k + 2] = nb[k].z; b[4 * k + 3] = nb[k].w;
     }
-    const bool own_row = owner && y >= y0 && y < y1;
-    double sse_row = 0.0;
+    if (y + 1 < y1 + 3) {
+      const int yr = min(max(y + 1, 0), H - 1);
+      const float4* ra = reinterpret_cast<const float4*>(A + img_base + (size_t)yr * row_elems + e_load);
+      const float4* rb = reinterpret_cast<const float4*>(Bm + img_base + (size_t)yr * row_elems + e_load);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { na[k] = __ldg(ra + k); nb[k] = __ldg(rb + k); }
+    }
+    double sse_row = 0.0;  // squared error: the same float32 products and double sums as the exact kernels (psnr / mse are identical)
 #pragma unroll
     for (int j = 0; j < MS_E; ++j) {
       const float va = __fmul_rn(__fadd_rn(a[j], pre_add), pre_mul);
@@ -497,7 +511,7 @@ metrics_f32_strip_kernel(const float* __restrict__ A, const float* __restrict__ 
       a[j] = va - ma[j % 3];
       b[j] = vb - mb[j % 3];
     }
-    if (own_row) sse += sse_row;
+    if (owner && y >= y0 && y < y1) sse += sse_row;
     // vertical sliding sums: the row that leaves the window (y - 7) comes back from the ring
     if (i >= 7) {
 #pragma unroll
@@ -509,9 +523,8 @@ metrics_f32_strip_kernel(const float* __restrict__ A, const float* __restrict__ 
           const int j = 4 * k + t;
           s[0][j] -= xa[t];
           s[1][j] -= xb[t];
-          s[2][j] = fmaf(-xa[t], xa[t], s[2][j]);
-          s[3][j] = fmaf(-xb[t], xb[t], s[3][j]);
-          s[4][j] = fmaf(-xa[t], xb[t], s[4][j]);
+          s[2][j] = fmaf(-xa[t], xa[t], fmaf(-xb[t], xb[t], s[2][j]));
+          s[3][j] = fmaf(-xa[t], xb[t], s[3][j]);
         }
       }
     }
@@ -525,16 +538,16 @@ metrics_f32_strip_kernel(const float* __restrict__ A, const float* __restrict__ 
     for (int j = 0; j < MS_E; ++j) {
       s[0][j] += a[j];
       s[1][j] += b[j];
-      s[2][j] = fmaf(a[j], a[j], s[2][j]);
-      s[3][j] = fmaf(b[j], b[j], s[3][j]);
-      s[4][j] = fmaf(a[j], b[j], s[4][j]);
+      s[2][j] = fmaf(a[j], a[j], fmaf(b[j], b[j], s[2][j]));
+      s[3][j] = fmaf(a[j], b[j], s[3][j]);
     }
-    const int yc = y - 3;   // centre row of the window that is complete now (warp-uniform conditions below)
+    const int yc = y - 3;   // centre row of the window that is complete now
     if (i < 6 || yc < max(y0, 3) || yc >= min(y1, H - 3)) continue;
-    // horizontal 7-tap sums along the stride-3 (same channel) sequences: 9 halo elements from each neighbour lane
-    float e[5][MS_E];
+    // horizontal 7-tap sums along the stride-3 (same channel) sequences: 9 halo elements from each neighbour lane; the first
+    // three outputs are full sums, the other nine slide
+    float e[MS_Q][MS_E];
 #pragma unroll
-    for (int q = 0; q < 5; ++q) {
+    for (int q = 0; q < MS_Q; ++q) {
       float x[MS_E + 18];
 #pragma unroll
       for (int j = 0; j < 9; ++j) {
@@ -553,13 +566,13 @@ metrics_f32_strip_kernel(const float* __restrict__ A, const float* __restrict__ 
 #pragma unroll
       for (int j = 0; j < MS_E; ++j) {
         const int gx = px0 + j / 3;
-        const float e0 = e[0][j] * inv49, e1 = e[1][j] * inv49, e2 = e[2][j] * inv49, e3 = e[3][j] * inv49, e4 = e[4][j] * inv49;
-        const float vx = cov_norm * (e2 - e0 * e0);
-        const float vy = cov_norm * (e3 - e1 * e1);
-        const float vxy = cov_norm * (e4 - e0 * e1);
+        const float e0 = e[0][j] * inv49, e1 = e[1][j] * inv49, e2 = e[2][j] * inv49, e3 = e[3][j] * inv49;
+        const float mm = fmaf(e0, e0, e1 * e1);           // ux'^2 + uy'^2 of the centred means
+        const float vsum = cov_norm * (e2 - mm);          // vx + vy
+        const float vxy = cov_norm * fmaf(-e0, e1, e3);
         const float ux = e0 + ma[j % 3], uy = e1 + mb[j % 3];
-        const float a1 = 2.0f * ux * uy + c1, a2 = 2.0f * vxy + c2;
-        const float b1 = ux * ux + uy * uy + c1, b2 = vx + vy + c2;
+        const float a1 = fmaf(2.0f * ux, uy, c1), a2 = fmaf(2.0f, vxy, c2);
+        const float b1 = fmaf(ux, ux, fmaf(uy, uy, c1)), b2 = vsum + c2;
         const float sv = __fdividef(a1 * a2, b1 * b2);
         row_sum += (gx >= 3 && gx < W - 3) ? sv : 0.f;
       }

@@ -139,7 +139,7 @@ class Model:
     def _drop_plan(self) -> None:
         """Forget the plan and everything that holds raw pointers into it (captured CUDA graphs replay the packed-weight and
         scratch addresses they were captured with; the plan's destructor frees the former)."""
-        for name in ("_pipe_graphs", "_phase_graphs", "_phase_cache"):
+        for name in ("_pipe_graphs", "_phase_graphs", "_phase_cache", "_stream_cache", "_stream_ws"):
             self.__dict__.pop(name, None)
         self._plan = None
 
@@ -721,6 +721,169 @@ class AdaptiveCompressionModel(Model):
                          {"blended": b["blended"], "dt": b["dt"], "hq_ratio_sum": b["hq_ratio_sum"],
                           "hq_latent_q": b["hq_latent_q"], "lq_latent_q": b["lq_latent_q"]})
         return ratios / float(h * w)
+
+    # ---- streaming predict: batches overlap each other ----------------------------------------------------------------------
+    def _stream_slot(self, slot, n, h, w, dev, u8_io, want_dt):
+        """Persistent device + pinned host buffers of one slot of predict_stream."""
+        self.plan()
+        key = ("stream", slot, n, h, w, self._plan_gen, bool(u8_io), bool(want_dt))
+        cache = self.__dict__.setdefault("_stream_cache", {})
+        if key in cache:
+            return cache[key]
+        for k in [k for k in cache if k[1] == slot]:            # another geometry used this slot: drop it (and its graph)
+            del cache[k]
+        base = self.base_latent_dim
+        nt = n * self.tiles_per_image(h, w)
+        f32 = dict(dtype=torch.float32, device=dev)
+        b = {
+            "img": torch.empty((n, h, w, 3), **f32), "mask": torch.empty((n, h, w, 1), **f32), "bpp": torch.empty((n,), **f32),
+            "blended": torch.empty((n, h, w, 3), **f32), "dt": torch.empty((n, h, w, 1), **f32) if want_dt else None,
+            "hq_latent_q": torch.empty((nt, 2 * base), **f32), "lq_latent_q": torch.empty((nt, base), **f32),
+            "rd_params": torch.empty((nt, 3), **f32), "hq_ratio_sum": torch.empty((n,), dtype=torch.float64, device=dev),
+        }
+        if u8_io:
+            b["img_u8"] = torch.empty((n, h, w, 3), dtype=torch.uint8, device=dev)
+            b["blended_u8"] = torch.empty((n, h, w, 3), dtype=torch.uint8, device=dev)
+        outs = [b["blended_u8"] if u8_io else b["blended"], b["hq_latent_q"], b["lq_latent_q"], b["rd_params"],
+                b["dt"] if want_dt else b["hq_ratio_sum"]]
+        b["outs"] = outs
+        b["host"] = [torch.empty(o.shape, dtype=o.dtype, pin_memory=True) for o in outs]
+        b["calls"], b["graph"], b["extra"] = 0, None, None
+        cache[key] = b
+        return b
+
+    def _stream_compute(self, b, n, h, w, u8_io, want_dt, on_batch):
+        """The whole forward of one batch on the slot's buffers (+ on_batch): what the slot's CUDA graph holds."""
+        if u8_io:
+            _lib.check(_lib.lib.cic_u8_to_f32_signed(ptr(b["img_u8"]), ptr(b["img"]), n * h * w * 3, runtime.stream_ptr()))
+        io = _lib.cic_adaptive_io()
+        io.d_img, io.d_mask, io.d_bpp = ptr(b["img"]), ptr(b["mask"]), ptr(b["bpp"])
+        io.d_blended, io.d_hq_latent_q, io.d_lq_latent_q = ptr(b["blended"]), ptr(b["hq_latent_q"]), ptr(b["lq_latent_q"])
+        io.d_rd_params, io.d_hq_ratio_sum = ptr(b["rd_params"]), ptr(b["hq_ratio_sum"])
+        io.d_dt = ptr(b["dt"]) if want_dt else None
+        plan = self.plan()
+        ws = self._workspace(plan, n, h, w)
+        _lib.check(_lib.lib.cic_adaptive_forward(plan.handle, C.byref(io), n, h, w, ptr(ws), ws.numel(), runtime.stream_ptr()))
+        ex = None
+        if on_batch is not None:
+            ex = on_batch([b["img"], b["mask"], b["bpp"]], {"blended": b["blended"], "dt": b["dt"], "hq_ratio_sum": b["hq_ratio_sum"]})
+        if u8_io:
+            _lib.check(_lib.lib.cic_f32_signed_to_u8(ptr(b["blended"]), ptr(b["blended_u8"]), n * h * w * 3, runtime.stream_ptr()))
+        return ex
+
+    def predict_stream(self, batches, on_batch=None, u8_io: bool = False, want_dt: bool = True, depth: int = 2):
+        """predict() for a STREAM of host batches at full throughput: a generator that yields (host outputs, on_batch result) per
+        batch, in order.  Batch k + 1 is uploaded while batch k is on the tensor cores and batch k - 1 travels back to pinned host
+        memory (three CUDA streams, `depth` buffer sets), so in steady state a batch costs max(kernels, copies) - not their sum,
+        and the kernels run on the whole batch (chunking a batch to hide its own copies, as predict_phased does for a single
+        call, costs tile-quantisation efficiency on the small chunks).  From its second use a slot replays ONE CUDA graph
+        (forward + on_batch).  Results equal predict().
+
+        batches: iterable of [image (n,H,W,3), saliency (n,H,W,1), target_bpp (n,)] with one geometry; pinned tensors copy fastest.
+        The yielded arrays are views of the slot's pinned buffers: valid until `depth` more batches have been yielded.
+        u8_io / want_dt: as predict_phased (uint8 image up, uint8 reconstruction down; hq_ratio instead of the dt map)."""
+        dev = runtime.require_cuda()
+        compute = torch.cuda.current_stream()
+        st = self.__dict__.setdefault("_pipe_streams", {})
+        if "in" not in st:
+            st["in"], st["out"] = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        s_in, s_out = st["in"], st["out"]
+        s_in.wait_stream(compute)
+        s_out.wait_stream(compute)
+        depth = max(1, int(depth))
+        pending = []                                                  # [(slot buffers, ev_out, extra, pixels per image)]
+
+        def finish(item):
+            b, ev_out, extra, hw = item
+            ev_out.synchronize()
+            res = [t.numpy() for t in b["host"]]
+            if not want_dt:
+                res[4] = res[4] / float(hw)
+            return res, extra
+
+        for k, x in enumerate(batches):
+            if len(pending) == depth:
+                yield finish(pending.pop(0))
+            xs = runtime.as_list(x)
+            hs = [t if isinstance(t, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(t)) for t in xs]
+            if len(hs) != 3:
+                raise ValueError("adaptive model takes [image, saliency, target_bpp]")
+            if u8_io and hs[0].dtype != torch.uint8:
+                raise ValueError("u8_io=True takes a uint8 image")
+            hs = [t if (t.dtype == torch.float32 or (u8_io and i == 0)) else t.to(torch.float32) for i, t in enumerate(hs)]
+            img, mask, bpp = hs
+            if img.dim() != 4:
+                raise ValueError(f"image must be (B, H, W, 3), got {tuple(img.shape)}")
+            mask, bpp = self._check_inputs(img, mask, bpp)
+            n, h, w, _ = img.shape
+            b = self._stream_slot(k % depth, n, h, w, dev, u8_io, want_dt)
+            timeline = runtime.pipe_timeline()
+            ev_in, ev_c, ev_out = (torch.cuda.Event(enable_timing=timeline) for _ in range(3))
+            if timeline:                                              # debug: start / end of the three legs of every batch
+                tl = self.__dict__.setdefault("_stream_timeline", [])
+                marks = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+                marks[0].record(s_in)
+            # the slot's previous batch (k - depth) has been yielded above, i.e. its download - hence its kernels - completed: the
+            # slot's buffers are free, and this upload may overlap the kernels of batch k - 1 in the other slot
+            with torch.cuda.stream(s_in):
+                (b["img_u8"] if u8_io else b["img"]).copy_(img, non_blocking=True)
+                b["mask"].copy_(mask, non_blocking=True)
+                b["bpp"].copy_(bpp, non_blocking=True)
+                ev_in.record(s_in)
+            compute.wait_event(ev_in)
+            if timeline:
+                marks[1].record(compute)
+            b["calls"] += 1
+            if runtime.use_cuda_graphs() and b["calls"] >= 2 and b["graph"] is None and not b.get("failed") and b.get("on_batch_id") == id(on_batch):
+                try:
+                    torch.cuda.synchronize()
+                    need = self.plan().workspace_bytes(n, h, w)
+                    wsd = self.__dict__.setdefault("_stream_ws", {})
+                    if wsd.get("gen") != self._plan_gen or wsd["buf"].numel() < need:   # one private scratch for all slots: their
+                        wsd.clear()                                                    # graphs run one after the other on one stream
+                        for other in self.__dict__.get("_stream_cache", {}).values():
+                            other["graph"] = None
+                        wsd.update(gen=self._plan_gen, buf=torch.empty(max(need, 1 << 20), dtype=torch.uint8, device=dev))
+                    self._ws_override = wsd["buf"]
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        ex = self._stream_compute(b, n, h, w, u8_io, want_dt, on_batch)
+                    b["graph"], b["extra"], b["on_batch"] = g, ex, on_batch
+                    torch.cuda.synchronize()
+                except Exception as e:  # noqa: BLE001
+                    b["failed"] = True
+                    torch.cuda.synchronize()
+                    print(f"predict_stream: CUDA graph capture failed ({e!r}); using eager launches", file=sys.stderr)
+                finally:
+                    self._ws_override = None
+            if b["graph"] is not None and b.get("on_batch") is on_batch:
+                b["graph"].replay()
+                extra = b["extra"]
+            else:
+                b["on_batch_id"] = id(on_batch)
+                b["on_batch_keep"] = on_batch
+                extra = self._stream_compute(b, n, h, w, u8_io, want_dt, on_batch)
+            ev_c.record(compute)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_c)
+                if timeline:
+                    marks[2].record(s_out)
+                for hbuf, o in zip(b["host"], b["outs"]):
+                    hbuf.copy_(o, non_blocking=True)
+                ev_out.record(s_out)
+            if timeline:
+                tl.append((marks[0], ev_in, marks[1], ev_c, marks[2], ev_out))
+            pending.append((b, ev_out, extra, h * w))
+        while pending:
+            yield finish(pending.pop(0))
+        compute.wait_stream(s_out)
+        if runtime.pipe_timeline() and self.__dict__.get("_stream_timeline"):
+            torch.cuda.synchronize()
+            tl = self.__dict__.pop("_stream_timeline")
+            t0 = tl[0][0]
+            for i, ev in enumerate(tl):
+                t = [t0.elapsed_time(e) for e in ev]
+                print(f"stream batch {i}: upload {t[0]:.2f}-{t[1]:.2f}  kernels {t[2]:.2f}-{t[3]:.2f}  download {t[4]:.2f}-{t[5]:.2f} ms", flush=True)
 
     def predict_phased(self, x, enc_chunks=None, dec_chunks=None, on_chunk=None, u8_io: bool = False, want_dt: bool = True):
         """predict() for host batches at full throughput: the forward is cut into three phases (include/cic.h): the encoder

@@ -200,6 +200,34 @@ def symbol_entropy_bits(symbols: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def rans_encode(symbols: torch.Tensor):
+    """Entropy-code integer latent symbols (rows, L) int32 on the device -> (uint8 stream tensor, trimmed to its length).  One
+    host synchronisation (the length).  Symbols beyond +-1023 are clamped (|symbol| <~ 100 in the codec: scale <= e^2.652)."""
+    if symbols.dtype != torch.int32 or not symbols.is_cuda:
+        symbols = torch.as_tensor(np.asarray(symbols.cpu() if isinstance(symbols, torch.Tensor) else symbols)).to(torch.int32).to(runtime.require_cuda())
+    symbols = symbols.contiguous()
+    rows, L = symbols.shape
+    dev = symbols.device
+    cap = int(_lib.lib.cic_rans_max_bytes(rows, L))
+    stream = torch.empty(cap, dtype=torch.uint8, device=dev)
+    nbytes = torch.zeros((), dtype=torch.int64, device=dev)
+    ws = torch.empty(int(_lib.lib.cic_rans_workspace_bytes(rows, L)), dtype=torch.uint8, device=dev)
+    _lib.check(_lib.lib.cic_rans_encode(ptr(symbols), rows, L, ptr(stream), cap, ptr(nbytes), ptr(ws), ws.numel(), runtime.stream_ptr()))
+    return stream[: int(nbytes.item())]
+
+
+def rans_decode(stream: torch.Tensor, rows: int, latent_dim: int) -> torch.Tensor:
+    """Inverse of rans_encode -> (rows, latent_dim) int32 on the device."""
+    if not isinstance(stream, torch.Tensor):
+        stream = torch.from_numpy(np.ascontiguousarray(np.frombuffer(bytes(stream), dtype=np.uint8)))
+    stream = stream.to(runtime.require_cuda()).contiguous()
+    if stream.data_ptr() % 4:
+        stream = stream.clone()
+    out = torch.empty((rows, latent_dim), dtype=torch.int32, device=stream.device)
+    _lib.check(_lib.lib.cic_rans_decode(ptr(stream), stream.numel(), ptr(out), rows, latent_dim, runtime.stream_ptr()))
+    return out
+
+
 def f32_to_u8_trunc(x, mul: float = 255.0) -> torch.Tensor:
     x = to_device_f32(x)
     y = torch.empty(x.shape, dtype=torch.uint8, device=x.device)

@@ -250,6 +250,19 @@ int cic_hq_ratio_sweep(const float* d_mask, const float* d_bpp_levels, int n_lev
 #define CIC_SYM_MAX 1023
 int cic_symbol_entropy_bits(const int32_t* d_symbols, double* d_bits, int batch, int latent_dim, void* stream);
 
+/* Entropy coder for the integer latent symbols: the bitstream the reference never writes (its bitrate is the nominal 32 bits per
+ * latent element of GAN_test.py:310-325).  Static model per call (histogram over all symbols, normalised to 2^14),
+ * rANS with 32 interleaved states per row (one warp per row; rows - tiles - stay independently decodable), symbols clamped to
+ * [-CIC_SYM_MAX, CIC_SYM_MAX].  Stream layout (little endian): u32 magic "CICR", version 1, rows, latent_dim, prob_bits 14, alphabet
+ * 2047, 2 reserved | u16 freq[2048] | u32 row_offset[rows + 1] | per row: u32 state[32], u16 words[], padded to 4 bytes.
+ * cic_rans_encode writes the stream and its length in bytes (*d_nbytes, device); cic_rans_decode restores the symbols exactly.
+ * d_symbols (rows, latent_dim) int32; d_stream 4-byte aligned with cic_rans_max_bytes() capacity. */
+size_t cic_rans_max_bytes(int rows, int latent_dim);
+size_t cic_rans_workspace_bytes(int rows, int latent_dim);
+int cic_rans_encode(const int32_t* d_symbols, int rows, int latent_dim, uint8_t* d_stream, size_t stream_capacity,
+                    unsigned long long* d_nbytes, void* d_workspace, size_t workspace_bytes, void* stream);
+int cic_rans_decode(const uint8_t* d_stream, size_t nbytes, int32_t* d_symbols, int rows, int latent_dim, void* stream);
+
 /* (y*255).astype(uint8) - truncation toward zero (test_autoencoder.py:88,96). */
 int cic_f32_to_u8_trunc(const float* d_x, uint8_t* d_y, size_t n, float mul, void* stream);
 

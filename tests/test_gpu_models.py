@@ -321,3 +321,36 @@ def test_linearity_of_blend_at_full_size(cic):
     assert torch.allclose(s, dt.double().sum(dim=(1, 2, 3)), rtol=1e-9)
     sweep = cic.ops.hq_ratio_sweep(mask, bpp)
     assert abs(sweep[0, 0].item() - s[0].item() / (1024 * 1024)) < 1e-7
+
+
+def test_stream_predict_equals_predict(cic, small_cfg):
+    """predict_stream (batches overlapping each other on three streams, one CUDA graph per slot from its second use) yields, in
+    order, what predict returns for every batch - float32 and uint8 wire formats, with and without the dt map."""
+    cic.set_precision("tc")
+    models, ws = _adaptive(cic, small_cfg["img_shape"], small_cfg["base"])
+    am = models["adaptive_model"]
+    batches, wants, batches8 = [], [], []
+    for k in range(6):
+        img_u8 = cic.synth.synth_images_u8(3, 128, 64, seed=200 + k)
+        img = cic.synth.to_signed_range(img_u8)
+        mask = cic.synth.synth_masks(3, 128, 64, seed=200 + k)
+        bpp = np.linspace(0.2 + 0.1 * k, 1.8, 3, dtype=np.float32).reshape(3, 1)
+        batches.append([img, mask, bpp])
+        batches8.append([img_u8, mask, bpp])
+        wants.append(am.predict([img, mask, bpp]))
+    on_batch = lambda d_in, outs: outs["hq_ratio_sum"].clone()  # noqa: E731
+    got = [([np.array(o) for o in outs], ex.cpu().numpy().copy()) for outs, ex in am.predict_stream(iter(batches), on_batch=on_batch)]
+    assert len(got) == 6
+    for (outs, ratio), want in zip(got, wants):
+        for g, w in zip(outs, want):
+            assert g.shape == w.shape
+            np.testing.assert_allclose(g, w, atol=2e-2, rtol=0)
+        assert np.mean(outs[1] != want[1]) < 0.01
+        np.testing.assert_allclose(ratio / (128 * 64), want[4].reshape(3, -1).mean(1, dtype=np.float64), atol=1e-6)
+    got8 = [[np.array(o) for o in outs] for outs, _ in am.predict_stream(iter(batches8), u8_io=True, want_dt=False, depth=3)]
+    for outs, want in zip(got8, wants):
+        assert outs[0].dtype == np.uint8
+        want8 = ((want[0] + 1) * np.float32(127.5)).astype(np.uint8)
+        assert np.abs(outs[0].astype(int) - want8.astype(int)).max() <= 3
+        np.testing.assert_allclose(outs[4], want[4].reshape(3, -1).mean(1, dtype=np.float64), atol=1e-6)
+    assert list(am.predict_stream(iter([]))) == []

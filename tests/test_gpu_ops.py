@@ -300,3 +300,41 @@ def test_ms_ssim_matches_numpy_restatement(cic, n, h, w):
     assert np.all(np.abs(same - 1.0) < 1e-6)
     with pytest.raises(ValueError, match="176"):
         cic.ops.ms_ssim_f32(a[:, :100], b[:, :100], signed_range=True)
+
+
+@pytest.mark.parametrize("rows,L,scale", [(5, 1024, 3.0), (3, 70, 20.0), (2, 512, 0.0), (1, 32, 400.0), (9, 64, 1.0), (130, 512, 2.0)])
+def test_rans_bitstream_matches_cpu_restatement(cic, rows, L, scale):
+    """cic_rans_encode / cic_rans_decode: the GPU stream equals the numpy restatement byte for byte, both decoders
+    invert both encoders, symbols beyond +-1023 are clamped.  Edge cases: one-symbol alphabet (scale 0), L not a multiple of 32,
+    L < 32 lanes' worth, heavy tails."""
+    from oracle import rans
+    rng = np.random.default_rng(rows * 1000 + L)
+    x = np.rint(rng.standard_normal((rows, L)) * scale).astype(np.int32)
+    if scale > 100:
+        x[0, :4] = [5000, -5000, 1023, -1023]
+    want = rans.encode(x)
+    got = cic.ops.rans_encode(torch.from_numpy(x).cuda())
+    got_b = got.cpu().numpy().tobytes()
+    assert len(got_b) == len(want)
+    assert got_b == want
+    clamped = np.clip(x, -1023, 1023)
+    np.testing.assert_array_equal(cic.ops.rans_decode(got, rows, L).cpu().numpy(), clamped)
+    np.testing.assert_array_equal(rans.decode(got_b), clamped)
+    np.testing.assert_array_equal(cic.ops.rans_decode(torch.from_numpy(np.frombuffer(want, np.uint8).copy()), rows, L).cpu().numpy(), clamped)
+
+
+def test_rans_round_trip_on_codec_symbols_and_empty(cic):
+    """Round trip at the codec's own scale: symbols of 256 tiles (Laplacian-like, |s| <~ 100) -> stream -> symbols; measured bits
+    per symbol sit between the zeroth-order entropy and entropy + 1.5 (32 x 32-bit states per row = 1 bit per symbol at L = 1024)."""
+    rng = np.random.default_rng(7)
+    x = np.rint(rng.laplace(0, 2.5, (256, 1024))).astype(np.int32)
+    sym = torch.from_numpy(x).cuda()
+    stream = cic.ops.rans_encode(sym)
+    back = cic.ops.rans_decode(stream, 256, 1024)
+    assert torch.equal(back, sym)
+    bits = cic.ops.symbol_entropy_bits(sym.reshape(1, -1)).item()                 # zeroth-order entropy of the whole call
+    coded = 8.0 * stream.numel()
+    assert bits <= coded <= bits + 1.5 * x.size + 8 * 6000, (bits, coded)
+    empty = cic.ops.rans_encode(torch.zeros((0, 64), dtype=torch.int32, device="cuda"))
+    assert empty.numel() == 32 + 4096 + 4
+    assert cic.ops.rans_decode(empty, 0, 64).shape == (0, 64)

@@ -323,3 +323,15 @@ def test_model_caches_follow_the_plan_generation(cic):
     assert not any(k in m.__dict__ for k in ("_pipe_graphs", "_phase_graphs", "_phase_cache")) and m._plan is None
     shapes = cic.weights.adaptive_shapes((256, 256, 3), 512)            # no allocation: zero-stride views
     assert shapes["hq_encoder"]["dense/kernel"].shape == (131072, 1024) and shapes["hq_encoder"]["dense/kernel"].strides == (0, 0)
+
+
+def test_import_shim_does_not_duplicate_modules(cic):
+    """`cic_b200.x` and `contextual-image-compression_b200.x` are one module object (a second copy would split module-level state
+    such as the precision switch or the workspace cache)."""
+    import importlib
+    import GAN_functions, GAN_test, test_autoencoder, train_autoencoder  # noqa: F401  (the drop-ins import through the shim)
+    import cic_b200.models as m2
+    import cic_b200.runtime as r2
+    assert importlib.import_module("contextual-image-compression_b200.models") is m2
+    assert importlib.import_module("contextual-image-compression_b200.runtime") is r2 and cic.runtime is r2 and m2.runtime is r2
+    assert GAN_functions.build_encoder.__module__ == "contextual-image-compression_b200.gan"

@@ -1,0 +1,176 @@
+// create_saliency_mask(saliency_map, smooth=True) on the GPU (GAN_functions.py:199-203): the step that turns a
+// saliency map into the model's mask input and that the reference recomputes on the CPU for every image and target bpp
+// (GAN_test.py:279-280, :553).
+//
+//   mask = cv2.bilateralFilter(sal.astype(float32), 9, 75, 75)      -> bilateral_kernel
+//   mask = cv2.GaussianBlur(mask, (31, 31), 0)                      -> gauss31_kernel (rows, then columns)
+//   mask = mask / mask.max()  (if max > 0)                          -> max_kernel + scale_kernel
+//
+// OpenCV semantics reproduced (cv2 is the oracle of the tests - these two filters are in core OpenCV, not in contrib):
+//   * bilateralFilter, CV_32F, d = 9: radius 4, the CIRCULAR neighbourhood r = sqrt(i^2 + j^2) <= 4 (49 taps), space weight
+//     exp(-r^2 / (2 sigma_space^2)), colour weight exp(-dv^2 / (2 sigma_color^2)), BORDER_REFLECT_101; an image whose value
+//     range is below FLT_EPSILON is copied.  OpenCV evaluates the colour weight through a 4096-bin interpolated table; with
+//     sigma_color = 75 on values in [0, 1] the weight is within 1e-4 of 1 and the table error is ~1e-9, far below the 1e-5 the
+//     tests ask for.
+//   * GaussianBlur, ksize 31, sigma 0 -> sigma = 0.3 * ((31 - 1) * 0.5 - 1) + 0.8 = 5.0, float32 coefficients of the normalised
+//     kernel, separable, BORDER_REFLECT_101.
+// The saliency MAP itself (cv2.saliency spectral residual + fine grained, GAN_functions.py:52-121) needs opencv-contrib, which
+// does not exist here even as an oracle; it stays a host input.
+#include "common.cuh"
+
+#include <cfloat>
+#include <cmath>
+
+namespace cic {
+
+__device__ __forceinline__ int reflect101(int p, int n) {
+  if (n == 1) return 0;
+  while (p < 0 || p >= n) p = p < 0 ? -p : 2 * (n - 1) - p;
+  return p;
+}
+
+// per-image min and max -> mm[2 * b], mm[2 * b + 1] (ordered-int atomics on the float bit patterns; inputs are finite)
+__device__ __forceinline__ void atomic_min_f(float* a, float v) {
+  if (v >= 0.f) atomicMin(reinterpret_cast<int*>(a), __float_as_int(v));
+  else atomicMax(reinterpret_cast<unsigned*>(a), __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_f(float* a, float v) {
+  if (v >= 0.f) atomicMax(reinterpret_cast<int*>(a), __float_as_int(v));
+  else atomicMin(reinterpret_cast<unsigned*>(a), __float_as_uint(v));
+}
+
+__global__ void sal_minmax_init_kernel(float* mm, int batch) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < batch) { mm[2 * i] = FLT_MAX; mm[2 * i + 1] = -FLT_MAX; }
+}
+
+__global__ void __launch_bounds__(256)
+sal_minmax_kernel(const float* __restrict__ x, float* __restrict__ mm, int hw) {
+  const int b = blockIdx.y;
+  const float* p = x + (size_t)b * hw;
+  float lo = FLT_MAX, hi = -FLT_MAX;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += gridDim.x * blockDim.x) {
+    const float v = __ldg(p + i);
+    lo = fminf(lo, v);
+    hi = fmaxf(hi, v);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomic_min_f(mm + 2 * b, lo);
+    atomic_max_f(mm + 2 * b + 1, hi);
+  }
+}
+
+constexpr int BL_T = 32, BL_R = 4, BL_P = BL_T + 2 * BL_R;
+
+__global__ void __launch_bounds__(256)
+sal_bilateral_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ mm, int H, int W, float space_coeff,
+                     float color_coeff) {
+  __shared__ float t[BL_P][BL_P + 1];
+  const int b = blockIdx.z, x0 = blockIdx.x * BL_T, y0 = blockIdx.y * BL_T;
+  const float* src = x + (size_t)b * H * W;
+  for (int i = threadIdx.x; i < BL_P * BL_P; i += blockDim.x) {
+    const int ly = i / BL_P, lx = i % BL_P;
+    t[ly][lx] = __ldg(src + (size_t)reflect101(y0 + ly - BL_R, H) * W + reflect101(x0 + lx - BL_R, W));
+  }
+  __syncthreads();
+  const bool flat = (mm[2 * b + 1] - mm[2 * b]) < FLT_EPSILON;
+  for (int i = threadIdx.x; i < BL_T * BL_T; i += blockDim.x) {
+    const int oy = i / BL_T, ox = i % BL_T;
+    if (y0 + oy >= H || x0 + ox >= W) continue;
+    const float v0 = t[oy + BL_R][ox + BL_R];
+    float sum = 0.f, wsum = 0.f;
+#pragma unroll
+    for (int dy = -BL_R; dy <= BL_R; ++dy)
+#pragma unroll
+      for (int dx = -BL_R; dx <= BL_R; ++dx) {
+        if (dy * dy + dx * dx > BL_R * BL_R) continue;      // OpenCV: r = sqrt(i*i + j*j) > radius -> skipped
+        const float v = t[oy + BL_R + dy][ox + BL_R + dx];
+        const float d = v - v0;
+        const float w = expf((float)(dy * dy + dx * dx) * space_coeff) * expf(d * d * color_coeff);
+        sum = fmaf(v, w, sum);
+        wsum += w;
+      }
+    y[(size_t)b * H * W + (size_t)(y0 + oy) * W + x0 + ox] = flat ? v0 : sum / wsum;
+  }
+}
+
+constexpr int GS_K = 31, GS_R = 15;
+
+// one separable pass: horizontal (axis = 0) or vertical (axis = 1); coefficients in constant-size shared memory
+__global__ void __launch_bounds__(256)
+sal_gauss31_kernel(const float* __restrict__ x, float* __restrict__ y, int H, int W, int axis) {
+  __shared__ float g[GS_K];
+  if (threadIdx.x < GS_K) {
+    // cv::getGaussianKernel(31, sigma = 5): exp(-x^2 / (2 sigma^2)) in double, normalised, stored as float32
+    double s = 0.0;
+    for (int k = 0; k < GS_K; ++k) { const double d = k - GS_R; s += exp(-d * d / 50.0); }
+    const double d = (int)threadIdx.x - GS_R;
+    g[threadIdx.x] = (float)(exp(-d * d / 50.0) / s);
+  }
+  __syncthreads();
+  const int b = blockIdx.y;
+  const float* src = x + (size_t)b * H * W;
+  float* dst = y + (size_t)b * H * W;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H * W; i += gridDim.x * blockDim.x) {
+    const int py = i / W, px = i % W;
+    float acc = 0.f;
+    if (axis == 0) {
+      const float* row = src + (size_t)py * W;
+#pragma unroll
+      for (int k = 0; k < GS_K; ++k) acc = fmaf(g[k], __ldg(row + reflect101(px + k - GS_R, W)), acc);
+    } else {
+#pragma unroll
+      for (int k = 0; k < GS_K; ++k) acc = fmaf(g[k], __ldg(src + (size_t)reflect101(py + k - GS_R, H) * W + px), acc);
+    }
+    dst[i] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+sal_scale_kernel(float* __restrict__ y, const float* __restrict__ mm, int hw) {
+  const int b = blockIdx.y;
+  const float mx = mm[2 * b + 1];
+  if (!(mx > 0.f)) return;                               // GAN_functions.py:202: only when mask.max() > 0
+  float* p = y + (size_t)b * hw;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += gridDim.x * blockDim.x) p[i] = __fdiv_rn(p[i], mx);
+}
+
+}  // namespace cic
+
+using namespace cic;
+
+extern "C" size_t cic_saliency_mask_workspace_bytes(int batch, int h, int w) {
+  if (batch <= 0 || h <= 0 || w <= 0) return 0;
+  return (((size_t)batch * h * w * sizeof(float) + 255) & ~(size_t)255) + (((size_t)batch * 2 * sizeof(float) + 255) & ~(size_t)255) + 256;
+}
+
+extern "C" int cic_saliency_mask_smooth(const float* d_saliency, float* d_mask, int batch, int h, int w, void* d_workspace,
+                                        size_t workspace_bytes, void* stream) {
+  CIC_REQUIRE(batch >= 0 && h > 0 && w > 0, "cic_saliency_mask_smooth: bad shape");
+  if (batch == 0) return CIC_OK;
+  CIC_REQUIRE(d_saliency && d_mask, "cic_saliency_mask_smooth: null pointer");
+  CIC_REQUIRE(batch <= 65535, "cic_saliency_mask_smooth: at most 65535 maps per call");
+  CIC_REQUIRE(d_workspace && workspace_bytes >= cic_saliency_mask_workspace_bytes(batch, h, w), "cic_saliency_mask_smooth: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* tmp = (float*)d_workspace;
+  float* mm = (float*)((char*)d_workspace + (((size_t)batch * h * w * sizeof(float) + 255) & ~(size_t)255));
+  const int hw = h * w;
+  const int blocks = (hw + 255) / 256 < sm_count() * 4 ? (hw + 255) / 256 : sm_count() * 4;
+  sal_minmax_init_kernel<<<(batch + 127) / 128, 128, 0, st>>>(mm, batch);
+  sal_minmax_kernel<<<dim3(blocks, batch), 256, 0, st>>>(d_saliency, mm, hw);
+  // cv2.bilateralFilter(src, 9, 75, 75): gauss coefficients -0.5 / sigma^2
+  const float coeff = (float)(-0.5 / (75.0 * 75.0));
+  sal_bilateral_kernel<<<dim3((w + BL_T - 1) / BL_T, (h + BL_T - 1) / BL_T, batch), 256, 0, st>>>(d_saliency, d_mask, mm, h, w, coeff, coeff);
+  sal_gauss31_kernel<<<dim3(blocks, batch), 256, 0, st>>>(d_mask, tmp, h, w, 0);
+  sal_gauss31_kernel<<<dim3(blocks, batch), 256, 0, st>>>(tmp, d_mask, h, w, 1);
+  sal_minmax_init_kernel<<<(batch + 127) / 128, 128, 0, st>>>(mm, batch);
+  sal_minmax_kernel<<<dim3(blocks, batch), 256, 0, st>>>(d_mask, mm, hw);
+  sal_scale_kernel<<<dim3(blocks, batch), 256, 0, st>>>(d_mask, mm, hw);
+  for (int i = 0; i < 8; ++i) CIC_COUNT_LAUNCH();
+  CIC_CHECK_LAUNCH("saliency mask kernels");
+  return CIC_OK;
+}

@@ -142,18 +142,23 @@ def bpp_accounting(hq_ratio, img_size=IMG_SIZE, base_latent_dim=BASE_LATENT_DIM)
             "actual_bpp": total_bits / (img_size[0] * img_size[1])}
 
 
-def _mask_for(img, mask):
+def _mask_for(img, mask, saliency_map=None):
+    """The mask input of the model: an explicit mask, or create_saliency_mask(saliency_map, smooth=True) on the GPU when the caller
+    has a saliency map, or the reference's whole front end (needs cv2.saliency = opencv-contrib for the map)."""
     if mask is not None:
         return np.asarray(mask, dtype=np.float32).reshape(img.shape[0], img.shape[1])
     from . import saliency
-    return saliency.create_saliency_mask(saliency.compute_saliency_map(img, method="combined"), smooth=True)
+    if saliency_map is None:
+        saliency_map = saliency.compute_saliency_map(img, method="combined")                 # GAN_test.py:279
+    return ops.saliency_mask_smooth(np.asarray(saliency_map, np.float32)).cpu().numpy()   # GAN_test.py:280
 
 
-def compress_and_reconstruct(img, models, target_bpp=1.0, mask=None):
-    """GAN_test.py:265-340.  `mask` (H,W) in [0,1] replaces the reference's opencv-contrib saliency
-    pipeline (GAN_test.py:279-280), which runs when it is None and cv2.saliency is importable."""
+def compress_and_reconstruct(img, models, target_bpp=1.0, mask=None, saliency_map=None):
+    """GAN_test.py:265-340.  `mask` (H,W) in [0,1] replaces the reference's saliency front end (GAN_test.py:279-280);
+    `saliency_map` replaces only its opencv-contrib half (compute_saliency_map) - the mask is then made from it on the GPU;
+    with neither, the whole front end runs (needs cv2.saliency)."""
     img = np.asarray(img, dtype=np.float32)
-    mask = _mask_for(img, mask)
+    mask = _mask_for(img, mask, saliency_map)
     img_batch = np.expand_dims(img, axis=0)
     mask_batch = np.expand_dims(np.expand_dims(mask, axis=-1), axis=0)
     target_bpp_batch = np.array([[target_bpp]], dtype=np.float32)

@@ -200,6 +200,22 @@ def symbol_entropy_bits(symbols: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def saliency_mask_smooth(saliency_map) -> torch.Tensor:
+    """create_saliency_mask(saliency_map, smooth=True) (GAN_functions.py:199-203) on the device: bilateral(9, 75, 75) -> Gaussian
+    31x31 -> / max, OpenCV semantics.  saliency_map (H,W) or (B,H,W) -> float32 mask of the same shape on the device."""
+    x = to_device_f32(saliency_map)
+    single = x.dim() == 2
+    if single:
+        x = x.unsqueeze(0)
+    if x.dim() != 3:
+        raise ValueError(f"saliency map must be (H,W) or (B,H,W), got {tuple(x.shape)}")
+    b, h, w = x.shape
+    y = torch.empty_like(x)
+    ws = torch.empty(int(_lib.lib.cic_saliency_mask_workspace_bytes(b, h, w)), dtype=torch.uint8, device=x.device)
+    _lib.check(_lib.lib.cic_saliency_mask_smooth(ptr(x), ptr(y), b, h, w, ptr(ws), ws.numel(), runtime.stream_ptr()))
+    return y[0] if single else y
+
+
 def rans_encode(symbols: torch.Tensor):
     """Entropy-code integer latent symbols (rows, L) int32 on the device -> (uint8 stream tensor, trimmed to its length).  One
     host synchronisation (the length).  Symbols beyond +-1023 are clamped (|symbol| <~ 100 in the codec: scale <= e^2.652)."""

@@ -250,6 +250,14 @@ int cic_hq_ratio_sweep(const float* d_mask, const float* d_bpp_levels, int n_lev
 #define CIC_SYM_MAX 1023
 int cic_symbol_entropy_bits(const int32_t* d_symbols, double* d_bits, int batch, int latent_dim, void* stream);
 
+/* create_saliency_mask(saliency_map, smooth=True) (GAN_functions.py:199-203; recomputed on the CPU for every image and target bpp
+ * at GAN_test.py:279-280): cv2.bilateralFilter(map, 9, 75, 75) -> cv2.GaussianBlur(31x31, sigma 0 = 5.0) -> / max (if max > 0), with
+ * OpenCV's semantics (circular 9-tap-wide neighbourhood, BORDER_REFLECT_101, float32).  d_saliency, d_mask (B,H,W) float32; the two
+ * may not alias.  The saliency map itself (cv2.saliency, opencv-contrib) stays a host input. */
+size_t cic_saliency_mask_workspace_bytes(int batch, int h, int w);
+int cic_saliency_mask_smooth(const float* d_saliency, float* d_mask, int batch, int h, int w, void* d_workspace,
+                             size_t workspace_bytes, void* stream);
+
 /* Entropy coder for the integer latent symbols: the bitstream the reference never writes (its bitrate is the nominal 32 bits per
  * latent element of GAN_test.py:310-325).  Static model per call (histogram over all symbols, normalised to 2^14),
  * rANS with 32 interleaved states per row (one warp per row; rows - tiles - stay independently decodable), symbols clamped to

@@ -338,3 +338,29 @@ def test_rans_round_trip_on_codec_symbols_and_empty(cic):
     empty = cic.ops.rans_encode(torch.zeros((0, 64), dtype=torch.int32, device="cuda"))
     assert empty.numel() == 32 + 4096 + 4
     assert cic.ops.rans_decode(empty, 0, 64).shape == (0, 64)
+
+
+@pytest.mark.parametrize("b,h,w", [(2, 256, 256), (1, 100, 180), (3, 33, 47)])
+def test_saliency_mask_smooth_matches_opencv(cic, b, h, w):
+    """cic_saliency_mask_smooth against the REAL OpenCV calls of create_saliency_mask(smooth=True)
+    (GAN_functions.py:199-203): cv2.bilateralFilter(9, 75, 75) -> cv2.GaussianBlur((31, 31), 0) -> / max."""
+    import cv2
+    rng = np.random.default_rng(h + w)
+    yy, xx = np.mgrid[0:h, 0:w]
+    maps = []
+    for _ in range(b):
+        m = 0.05 * rng.random((h, w))
+        for _ in range(4):
+            cy, cx, s = rng.uniform(0, h), rng.uniform(0, w), rng.uniform(4, 40)
+            m += rng.uniform(0.2, 1.0) * np.exp(-((yy - cy) ** 2 + (xx - cx) ** 2) / (2 * s * s))
+        maps.append((m / m.max()).astype(np.float32))
+    maps = np.stack(maps)
+    got = cic.ops.saliency_mask_smooth(maps).cpu().numpy()
+    for i in range(b):
+        want = cic.saliency.create_saliency_mask(maps[i], smooth=True)           # the cv2 calls
+        assert got[i].max() == pytest.approx(1.0, abs=1e-6)
+        np.testing.assert_allclose(got[i], want, atol=1e-5)
+    flat = np.full((1, 40, 40), 0.25, np.float32)                               # value range < FLT_EPSILON: bilateral copies, max-normalised to 1
+    np.testing.assert_allclose(cic.ops.saliency_mask_smooth(flat).cpu().numpy(), 1.0, atol=1e-6)
+    zero = np.zeros((40, 40), np.float32)                                       # max == 0: left as is (GAN_functions.py:202)
+    assert cic.ops.saliency_mask_smooth(zero).abs().max().item() == 0.0

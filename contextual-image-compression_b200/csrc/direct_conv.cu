@@ -209,6 +209,10 @@ int launch_conv_k3s1_c3_pool(const float* x, const float* wgt, const float* bias
 // x (B,H,W,1) fp32 -> Conv2D(32, k3, s2, 'same') + bias + act -> bf16 hi (+ lo), (B,ceil(H/2),ceil(W/2),32)
 int launch_conv_k3s2_c1(const float* x, const float* wgt, const float* bias, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo,
                         int batch, int H, int W, int act, const TileMap& tm, cudaStream_t st) {
+  // one pixel per thread: half the accumulator registers, twice the resident CTAs - the kernel is latency-bound, not FMA-bound
+  // (r02 ncu: 24 % of the warp slots occupied, long-scoreboard stalls lead)
+  if (CIC_KNOB("CIC_RD_NPX", 1) == 1)
+    return launch_direct<1, 3, 2, 32, 1, false>("conv_k3s2_c1_kernel", x, wgt, bias, out_hi, out_lo, nullptr, nullptr, batch, H, W, act, tm, st);
   return launch_direct<1, 3, 2, 32, 2, false>("conv_k3s2_c1_kernel", x, wgt, bias, out_hi, out_lo, nullptr, nullptr, batch, H, W, act, tm, st);
 }
 

@@ -587,6 +587,160 @@ metrics_f32_strip_kernel(const float* __restrict__ A, const float* __restrict__ 
   }
 }
 
+// packed fp32 pairs (Blackwell FADD2 / FMUL2 / FFMA2): one issue slot for two float operations - the strip kernel is issue-bound
+typedef unsigned long long ms_u64;
+__device__ __forceinline__ ms_u64 ms_pk(float2 v) { ms_u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(v.x), "f"(v.y)); return r; }
+__device__ __forceinline__ float2 ms_up(ms_u64 r) { float2 v; asm("mov.b64 {%0, %1}, %2;" : "=f"(v.x), "=f"(v.y) : "l"(r)); return v; }
+__device__ __forceinline__ float2 f2_add(float2 a, float2 b) { ms_u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(ms_pk(a)), "l"(ms_pk(b))); return ms_up(r); }
+__device__ __forceinline__ float2 f2_sub(float2 a, float2 b) { ms_u64 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(ms_pk(a)), "l"(ms_pk(b))); return ms_up(r); }
+__device__ __forceinline__ float2 f2_mul(float2 a, float2 b) { ms_u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(ms_pk(a)), "l"(ms_pk(b))); return ms_up(r); }
+__device__ __forceinline__ float2 f2_fma(float2 a, float2 b, float2 c) { ms_u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(ms_pk(a)), "l"(ms_pk(b)), "l"(ms_pk(c))); return ms_up(r); }
+__device__ __forceinline__ float2 f2_shfl_up(float2 v) { return make_float2(__shfl_up_sync(0xffffffffu, v.x, 1), __shfl_up_sync(0xffffffffu, v.y, 1)); }
+__device__ __forceinline__ float2 f2_shfl_down(float2 v) { return make_float2(__shfl_down_sync(0xffffffffu, v.x, 1), __shfl_down_sync(0xffffffffu, v.y, 1)); }
+
+// As metrics_f32_strip_kernel, with the window sums kept as packed pairs per element: (u, v) = (a + b, a - b) of the centred values
+// and (uu, vv).  E[a] = (E[u] + E[v]) / 2, E[aa + bb] = (E[uu] + E[vv]) / 2, E[ab] = (E[uu] - E[vv]) / 4: every vertical and
+// horizontal update is one packed instruction for two quantities, and the SSIM expression works on (wu, wv) = (E[uu] - E[u]^2,
+// E[vv] - E[v]^2) and (U, V) = (ux + uy, ux - uy).
+__global__ void __launch_bounds__(32, 10)
+metrics_f32_strip2_kernel(const float* __restrict__ A, const float* __restrict__ Bm, double* __restrict__ acc, int batch, int H, int W, int R,
+                          int bands, int segs, float pre_add, float pre_mul, float c1, float c2, float cov_norm) {
+  extern __shared__ float4 ms_ring[];  // [slot 7][k 6][lane 32]: the (u, v) pairs of 12 elements
+  const int lane = threadIdx.x;
+  const unsigned wg = blockIdx.x;
+  const int band = (int)(wg % (unsigned)bands), seg = (int)((wg / (unsigned)bands) % (unsigned)segs), img = (int)(wg / ((unsigned)bands * (unsigned)segs));
+  (void)batch;
+  const int y0 = seg * R, y1 = min(y0 + R, H);
+  const int row_elems = 3 * W;
+  const int e_base = band * MS_OUT - MS_E + MS_E * lane;
+  const bool in_row = e_base >= 0 && e_base < row_elems;
+  const bool owner = in_row && lane >= 1 && lane <= 30;
+  const int e_load = min(max(e_base, 0), row_elems - MS_E);
+  const size_t img_base = (size_t)img * H * row_elems;
+  float4* ring = ms_ring + lane;
+  float2 muv[3];   // (ma + mb, ma - mb) per channel: the centring reference in the (u, v) basis
+  {
+    const int er = min(band * MS_OUT, row_elems - 3);
+    const float* pa = A + img_base + (size_t)y0 * row_elems + er;
+    const float* pb = Bm + img_base + (size_t)y0 * row_elems + er;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float ma = __fmul_rn(__fadd_rn(__ldg(pa + c), pre_add), pre_mul);
+      const float mb = __fmul_rn(__fadd_rn(__ldg(pb + c), pre_add), pre_mul);
+      muv[c] = make_float2(ma + mb, ma - mb);
+    }
+  }
+  float2 s_uv[MS_E], s_sq[MS_E];
+#pragma unroll
+  for (int j = 0; j < MS_E; ++j) { s_uv[j] = make_float2(0.f, 0.f); s_sq[j] = make_float2(0.f, 0.f); }
+  double sse = 0.0, ssum = 0.0;
+  const float2 inv49 = make_float2(1.0f / 49.0f, 1.0f / 49.0f);
+  const float cnh = 0.5f * cov_norm;
+  const int px0 = e_base / 3;
+  int slot = 0;
+  float4 na[3], nb[3];
+  {
+    const int yr = min(max(y0 - 3, 0), H - 1);
+    const float4* ra = reinterpret_cast<const float4*>(A + img_base + (size_t)yr * row_elems + e_load);
+    const float4* rb = reinterpret_cast<const float4*>(Bm + img_base + (size_t)yr * row_elems + e_load);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { na[k] = __ldg(ra + k); nb[k] = __ldg(rb + k); }
+  }
+  for (int y = y0 - 3, i = 0; y < y1 + 3; ++y, ++i) {
+    float a[MS_E], b[MS_E];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      a[4 * k] = na[k].x; a[4 * k + 1] = na[k].y; a[4 * k + 2] = na[k].z; a[4 * k + 3] = na[k].w;
+      b[4 * k] = nb[k].x; b[4 * k + 1] = nb[k].y; b[4 * k + 2] = nb[k].z; b[4 * k + 3] = nb[k].w;
+    }
+    if (y + 1 < y1 + 3) {
+      const int yr = min(max(y + 1, 0), H - 1);
+      const float4* ra = reinterpret_cast<const float4*>(A + img_base + (size_t)yr * row_elems + e_load);
+      const float4* rb = reinterpret_cast<const float4*>(Bm + img_base + (size_t)yr * row_elems + e_load);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { na[k] = __ldg(ra + k); nb[k] = __ldg(rb + k); }
+    }
+    float2 uv[MS_E];
+    double sse_row = 0.0;
+    const float2 pa2 = make_float2(pre_add, pre_add), pm2 = make_float2(pre_mul, pre_mul);
+#pragma unroll
+    for (int j = 0; j < MS_E; j += 2) {
+      // v = (x + pre_add) * pre_mul and d = va - vb with the roundings of the exact kernels (add.rn / mul.rn / sub.rn, two lanes each)
+      const float2 va = f2_mul(f2_add(make_float2(a[j], a[j + 1]), pa2), pm2);
+      const float2 vb = f2_mul(f2_add(make_float2(b[j], b[j + 1]), pa2), pm2);
+      const float2 d = f2_sub(va, vb), sm = f2_add(va, vb), dd = f2_mul(d, d);
+      sse_row += (double)dd.x;
+      sse_row += (double)dd.y;
+      uv[j] = make_float2(sm.x - muv[j % 3].x, d.x - muv[j % 3].y);
+      uv[j + 1] = make_float2(sm.y - muv[(j + 1) % 3].x, d.y - muv[(j + 1) % 3].y);
+    }
+    if (owner && y >= y0 && y < y1) sse += sse_row;
+    if (i >= 7) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        const float4 o = ring[(slot * 6 + k) * 32];
+        const float2 o0 = make_float2(o.x, o.y), o1 = make_float2(o.z, o.w);
+        s_uv[2 * k] = f2_sub(s_uv[2 * k], o0);
+        s_uv[2 * k + 1] = f2_sub(s_uv[2 * k + 1], o1);
+        s_sq[2 * k] = f2_sub(s_sq[2 * k], f2_mul(o0, o0));
+        s_sq[2 * k + 1] = f2_sub(s_sq[2 * k + 1], f2_mul(o1, o1));
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) ring[(slot * 6 + k) * 32] = make_float4(uv[2 * k].x, uv[2 * k].y, uv[2 * k + 1].x, uv[2 * k + 1].y);
+    if (++slot == 7) slot = 0;
+#pragma unroll
+    for (int j = 0; j < MS_E; ++j) {
+      s_uv[j] = f2_add(s_uv[j], uv[j]);
+      s_sq[j] = f2_fma(uv[j], uv[j], s_sq[j]);
+    }
+    const int yc = y - 3;
+    if (i < 6 || yc < max(y0, 3) || yc >= min(y1, H - 3)) continue;
+    float2 e_uv[MS_E], e_sq[MS_E];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      float2 x[MS_E + 18];
+#pragma unroll
+      for (int j = 0; j < 9; ++j) {
+        x[j] = f2_shfl_up(q == 0 ? s_uv[j + 3] : s_sq[j + 3]);
+        x[MS_E + 9 + j] = f2_shfl_down(q == 0 ? s_uv[j] : s_sq[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < MS_E; ++j) x[9 + j] = q == 0 ? s_uv[j] : s_sq[j];
+      float2 e[MS_E];
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        e[j] = f2_add(f2_add(f2_add(x[j], x[j + 3]), f2_add(x[j + 6], x[j + 9])), f2_add(f2_add(x[j + 12], x[j + 15]), x[j + 18]));
+#pragma unroll
+      for (int j = 3; j < MS_E; ++j) e[j] = f2_add(e[j - 3], f2_sub(x[j + 18], x[j - 3]));
+#pragma unroll
+      for (int j = 0; j < MS_E; ++j) { if (q == 0) e_uv[j] = e[j]; else e_sq[j] = e[j]; }
+    }
+    if (owner) {
+      float row_sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < MS_E; ++j) {
+        const int gx = px0 + j / 3;
+        const float2 m = f2_mul(e_uv[j], inv49);                       // (E[u], E[v]) of the centred values
+        const float2 w = f2_sub(f2_mul(e_sq[j], inv49), f2_mul(m, m)); // (E[uu] - E[u]^2, E[vv] - E[v]^2)
+        const float2 UV = f2_add(m, muv[j % 3]);                       // (ux + uy, ux - uy)
+        const float2 UV2 = f2_mul(UV, UV);
+        const float a1 = fmaf(0.5f, UV2.x - UV2.y, c1), b1 = fmaf(0.5f, UV2.x + UV2.y, c1);   // 2 ux uy + c1, ux^2 + uy^2 + c1
+        const float a2 = fmaf(cnh, w.x - w.y, c2), b2 = fmaf(cnh, w.x + w.y, c2);             // 2 vxy + c2, vx + vy + c2
+        const float sv = __fdividef(a1 * a2, b1 * b2);
+        row_sum += (gx >= 3 && gx < W - 3) ? sv : 0.f;
+      }
+      ssum += (double)row_sum;
+    }
+  }
+  sse = warp_sum(sse);
+  ssum = warp_sum(ssum);
+  if (lane == 0) {
+    atomicAdd(acc + (size_t)img * 4 + 3, sse);
+    atomicAdd(acc + (size_t)img * 4 + 1, ssum);
+  }
+}
+
 // out[b] = {psnr, ssim, mse, sse}
 __global__ void metrics_finalize_kernel(double* __restrict__ acc, int batch, double n_elems, double n_ssim,
                                         double data_range) {
@@ -743,6 +897,7 @@ static int metrics_f32_impl(const float* d_a, const float* d_b, double* d_out, i
     static DeviceOnce strip_attr;
     if (strip_attr.todo()) {
       CIC_CHECK_CUDA(cudaFuncSetAttribute(metrics_f32_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MS_RING_BYTES));
+      CIC_CHECK_CUDA(cudaFuncSetAttribute(metrics_f32_strip2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MS_RING_BYTES));
       strip_attr.done();
     }
     const int bands = (3 * w + MS_OUT - 1) / MS_OUT;
@@ -756,7 +911,10 @@ static int metrics_f32_impl(const float* d_a, const float* d_b, double* d_out, i
     const int segs = (h + R - 1) / R;
     const long long warps = (long long)batch * bands * segs;
     CIC_REQUIRE(warps < 2147483647LL, "metrics: too many strips");
-    metrics_f32_strip_kernel<<<(unsigned)warps, 32, MS_RING_BYTES, st>>>(d_a, d_b, d_out, batch, h, w, R, bands, segs, pre_add, pre_mul, c1, c2, cov_norm);
+    if (CIC_KNOB("CIC_METRICS_PACKED", 1))
+      metrics_f32_strip2_kernel<<<(unsigned)warps, 32, MS_RING_BYTES, st>>>(d_a, d_b, d_out, batch, h, w, R, bands, segs, pre_add, pre_mul, c1, c2, cov_norm);
+    else
+      metrics_f32_strip_kernel<<<(unsigned)warps, 32, MS_RING_BYTES, st>>>(d_a, d_b, d_out, batch, h, w, R, bands, segs, pre_add, pre_mul, c1, c2, cov_norm);
     CIC_COUNT_LAUNCH();
     CIC_CHECK_LAUNCH("metrics_f32_strip_kernel");
     metrics_finalize_kernel<<<(batch + 127) / 128, 128, 0, st>>>(d_out, batch, (double)h * w * channels,

@@ -391,7 +391,7 @@ int tc_run_layer(const TcLayer& L, cudaStream_t st) {
     bool used = false;
     // CIC_TC_DC2: merged-phase CTA-pair kernel for transposed convs with Cout in {32, 64} (tc_gemm2.cu): 0 off, 1 the layers
     // the raster kernel streams weights for (deconv3), 2 also the resident-weight raster layers (deconv4)
-    static const int dc2_env = CIC_KNOB("CIC_TC_DC2", 0);
+    static const int dc2_env = CIC_KNOB("CIC_TC_DC2", 1);
     bool skip_raster = false;
     if (dc && dc2_env >= 2) {
       int tw, th, tb;
@@ -494,7 +494,7 @@ int tc_run_layer(const TcLayer& L, cudaStream_t st) {
   static const int pair_env = CIC_KNOB("CIC_TC_PAIR", 1);
   const long long m_tiles = (long long)p.tiles_x * p.tiles_y * p.tiles_b;
   const int bn2 = tc2_pick_block_n(p.N_pad);
-  static const int dc2_env = CIC_KNOB("CIC_TC_DC2", 0);
+  static const int dc2_env = CIC_KNOB("CIC_TC_DC2", 1);
   const bool dc2 = dc && dc2_env && pair_env && L.splits == 1 && tc_deconv2_ok(BK, L.split, m_tiles, p.N_pad, L.N);
   const bool pair = !dc2 && pair_env && !L.b_batched && tc_pair_ok(BK, m_tiles, p.N_pad, L.N);
   const int bn = dc2 ? L.N : (pair ? bn2 : tc_pick_block_n(p.N_pad, L.split, BK));

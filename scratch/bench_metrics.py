@@ -7,10 +7,11 @@ n, h, w = 64, 512, 512
 a = torch.rand((n, h, w, 3), device="cuda") * 2 - 1
 b = (a + 0.05 * torch.randn_like(a)).clamp(-1, 1)
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-for rows in [0, 32, 64, 128] if len(sys.argv) < 2 else [int(sys.argv[1])]:
+for rows in [0, 64, 128] if len(sys.argv) < 2 else [int(sys.argv[1])]:
     os.environ["CIC_METRICS_ROWS"] = str(rows)
-    for strip in ("1", "0"):
+    for strip, packed in (("1", "1"), ("1", "0"), ("0", "0")):
         os.environ["CIC_METRICS_STRIP"] = strip
+        os.environ["CIC_METRICS_PACKED"] = packed
         cic.ops.metrics_f32(a, b, signed_range=True, fast=True)
         torch.cuda.synchronize()
         ev[0].record()
@@ -19,4 +20,4 @@ for rows in [0, 32, 64, 128] if len(sys.argv) < 2 else [int(sys.argv[1])]:
         ev[1].record()
         torch.cuda.synchronize()
         ms = ev[0].elapsed_time(ev[1]) / 20
-        print(f"rows={rows} strip={strip}: {ms:.4f} ms  {24.0 * n * h * w / ms / 1e6:.0f} GB/s  ssim {m[:, 1].mean().item():.9f} psnr {m[:, 0].mean().item():.9f}")
+        print(f"rows={rows} strip={strip} packed={packed}: {ms:.4f} ms  {24.0 * n * h * w / ms / 1e6:.0f} GB/s  ssim {m[:, 1].mean().item():.9f} psnr {m[:, 0].mean().item():.9f}")

@@ -21,7 +21,7 @@
 
 namespace cic {
 
-constexpr int CR_SLOTS = 8;
+constexpr int CR_SLOTS = 8;          // at most this many raster slots (input rows in flight)
 constexpr int CR_STRIP_H = 128;
 constexpr int CR_MAXK = 5;
 
@@ -32,6 +32,7 @@ struct ConvRowsParams {
   int blk_src[4], blk_c0[4]; // source and first channel of each block
   int cout, act;
   int strips_x, strips_y, total_strips;
+  int slots;                 // raster slots in the ring (3..CR_SLOTS)
   int slot_bytes;            // one raster slot: nblk rasters of rast_bytes each
   int rast_bytes;            // rw pixels x 64 B rounded up to 1 KB (swizzle phase of every raster starts at 0)
   int rw;                    // raster width in pixels = 128 + ks - 1
@@ -39,15 +40,30 @@ struct ConvRowsParams {
   const float* bias;
   float* out;                // fp32, (batch, H, W, cout) or the image layout of `tm`
   int tm_tx, tm_ty, tm_IH, tm_IW;
+  // FUSE2 (generator tail, GAN_functions.py:273 of both generators + :651-657, :682-684): block 0 = HQ generator, block 1 = LQ
+  // generator, separate accumulators; the column owners apply tanh to both, form dt from the mask and write the BLEND
+  const float* bias2;        // conv_out bias of the second generator
+  const float* mask;         // (n_img, IH, IW) saliency mask
+  const float* bpp;          // (n_img,) target bpp
+  float* dt_out;             // (n_img, IH, IW) or NULL
+  double* dt_sum;            // (n_img,) += sum of dt (zeroed by the launcher) or NULL
+  float* out_hq;             // un-blended generator outputs (diagnostics) or NULL
+  float* out_lq;
 };
 
-template <int KS, int COUT>
-__global__ void __launch_bounds__(192, 2)
+// tanh(z) = 1 - 2 / (e^(2z) + 1) on the SFU (ex2.approx, rcp.approx): absolute error ~1e-6 against tanhf - the fused tail's four
+// column-owner warps do the work of three kernels' epilogues, and tanhf's ~20 instructions per value were what paced it
+__device__ __forceinline__ float tanh_fast(float z) { return 1.0f - __fdividef(2.0f, __expf(2.0f * z) + 1.0f); }
+
+template <int KS, int COUT, bool FUSE2>
+__global__ void __launch_bounds__(192, 3)
 conv_rows_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ ConvRowsParams p) {
+  constexpr int STG = FUSE2 ? 32 : 16;   // TMEM columns per accumulator stage
+  const int SLOTS = p.slots;   // 3..8 raster slots, chosen by the launcher so that three CTAs fit an SM
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* a_ring = smem;
-  uint8_t* b_img = smem + (size_t)CR_SLOTS * p.slot_bytes;
+  uint8_t* b_img = smem + (size_t)SLOTS * p.slot_bytes;
   uint64_t* a_full = reinterpret_cast<uint64_t*>(b_img + (size_t)p.nblk * KS * 1024);
   uint64_t* a_empty = a_full + CR_SLOTS;
   uint64_t* tmem_full_bar = a_empty + CR_SLOTS;
@@ -63,12 +79,12 @@ conv_rows_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int s = 0; s < CR_SLOTS; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+      for (int s = 0; s < SLOTS; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
       for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 4); }
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, 32);
+    tmem_alloc(tmem_slot, 2 * STG);
     tmem_relinquish();
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the weight image was written with generic stores
@@ -96,7 +112,7 @@ conv_rows_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__
             tma_load_4d(a_ring + (size_t)s * p.slot_bytes + (size_t)k * p.rast_bytes, &maps.a[p.blk_src[k]][0], &a_full[s], p.blk_c0[k], x0 - p.pad, r, b);
         }
         __syncwarp();
-        if (++s == CR_SLOTS) { s = 0; ph ^= 1u; }
+        if (++s == SLOTS) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
@@ -117,9 +133,10 @@ conv_rows_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__
         mbar_wait(&a_full[s], ph);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t d = tmem_base + (uint32_t)(as * 16);
+          uint32_t d = tmem_base + (uint32_t)(as * STG);
           uint32_t first = 1;
           for (int k = 0; k < p.nblk; ++k) {
+            if (FUSE2 && k == 1) { d += 16; first = 1; }   // the second generator accumulates in its own 16 columns
             const uint32_t a_blk = a_lo0 + s * slot_lo + (uint32_t)k * rast_lo;
 #pragma unroll
             for (int kx = 0; kx < KS; ++kx) {
@@ -134,7 +151,7 @@ conv_rows_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__
           umma_commit(&tmem_full_bar[as]);
         }
         __syncwarp();
-        if (++s == CR_SLOTS) { s = 0; ph ^= 1u; }
+        if (++s == SLOTS) { s = 0; ph ^= 1u; }
         ++lt;
       }
     }
@@ -142,42 +159,64 @@ conv_rows_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__
     // ===== column owners: thread x accumulates output column x0 + x down the strip =====
     const int q = warp & 3;
     const int xl = q * 32 + lane;
-    float bias[COUT];
+    float bias[COUT], bias2[COUT];
 #pragma unroll
-    for (int o = 0; o < COUT; ++o) bias[o] = p.bias ? __ldg(p.bias + o) : 0.f;
+    for (int o = 0; o < COUT; ++o) {
+      bias[o] = p.bias ? __ldg(p.bias + o) : 0.f;
+      bias2[o] = (FUSE2 && p.bias2) ? __ldg(p.bias2 + o) : 0.f;
+    }
     int lt = 0;
     for (int t = blockIdx.x; t < p.total_strips; t += gridDim.x) {
       const int b = t / strips_per_item, ti = t % strips_per_item;
       const int y0 = (ti / p.strips_x) * CR_STRIP_H, x0 = (ti % p.strips_x) * TC_BM;
       const int gx = x0 + xl;
-      float* out_col;
-      size_t row_stride;
+      size_t pix0;             // pixel index of (row 0, column gx) of this item in the output / mask layout
+      size_t row_pix;          // pixels per output row
       int vh = p.H, vw = p.W;  // rows / columns of this item that exist in the image (a ragged last tile is cropped on store)
+      int img = b;
       if (p.tm_tx) {
-        const int tpi = p.tm_tx * p.tm_ty, img = b / tpi, tt = b % tpi;
+        const int tpi = p.tm_tx * p.tm_ty, tt = b % tpi;
+        img = b / tpi;
         const int gy0 = (tt / p.tm_tx) * p.H, gx0 = (tt % p.tm_tx) * p.W;
-        out_col = p.out + ((((size_t)img * p.tm_IH + (size_t)gy0) * p.tm_IW) + (size_t)gx0 + gx) * COUT;
-        row_stride = (size_t)p.tm_IW * COUT;
+        pix0 = (((size_t)img * p.tm_IH + (size_t)gy0) * p.tm_IW) + (size_t)gx0 + gx;
+        row_pix = (size_t)p.tm_IW;
         vh = min(p.H, p.tm_IH - gy0);
         vw = min(p.W, p.tm_IW - gx0);
       } else {
-        out_col = p.out + (((size_t)b * p.H) * p.W + gx) * COUT;
-        row_stride = (size_t)p.W * COUT;
+        pix0 = ((size_t)b * p.H) * p.W + gx;
+        row_pix = (size_t)p.W;
       }
-      float acc[KS][COUT];  // acc[s]: output row (r + pad - s) while input row r is being added
+      float* out_col = p.out + pix0 * COUT;
+      const size_t row_stride = row_pix * COUT;
+      float thr = 0.f;
+      if (FUSE2) thr = rate_thr(rate_t(__ldg(p.bpp + img)));   // GAN_functions.py:631-644
+      double dt_local = 0.0;
+      if (FUSE2 && gx < vw) {
+        for (int yp = y0; yp < y0 + 12 && yp < vh; ++yp) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.mask + pix0 + (size_t)yp * row_pix));
+      }
+      float acc[KS][COUT];   // acc[s]: output row (r + pad - s) while input row r is being added
+      float acc2[FUSE2 ? KS : 1][COUT];
 #pragma unroll
       for (int s = 0; s < KS; ++s)
 #pragma unroll
-        for (int o = 0; o < COUT; ++o) acc[s][o] = 0.f;
+        for (int o = 0; o < COUT; ++o) { acc[s][o] = 0.f; if (FUSE2) acc2[s][o] = 0.f; }
 #pragma unroll 1
       for (int i = 0; i < rows_in; ++i) {
         const int r = y0 - p.pad + i;
+        if (FUSE2) {
+          // the mask value of an output row is a dependent global load in this thread's serial walk down the strip: without
+          // the prefetch every row paid a DRAM round trip (measured: 0.71 ms for the fused tail against an HBM floor of 0.39)
+          const int yp = r + p.pad - (KS - 1) + 12;
+          if (yp >= y0 && yp < y0 + CR_STRIP_H && yp < vh && gx < vw)
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(p.mask + pix0 + (size_t)yp * row_pix));
+        }
         if (r >= 0 && r < p.H) {
           const int as = lt & 1;
           mbar_wait_relaxed(&tmem_full_bar[as], ((uint32_t)lt >> 1) & 1u);
           tc_fence_after();
           uint32_t v[32];
-          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 16), v);
+          if (FUSE2) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * STG), v);
+          else tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * STG), v);
           tmem_ld_wait();
           tc_fence_before();
           __syncwarp();
@@ -186,30 +225,52 @@ conv_rows_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__
 #pragma unroll
           for (int s = 0; s < KS; ++s)
 #pragma unroll
-            for (int o = 0; o < COUT; ++o) acc[s][o] += __uint_as_float(v[s * COUT + o]);  // column n = ky * Cout + o, ky = s
+            for (int o = 0; o < COUT; ++o) {
+              acc[s][o] += __uint_as_float(v[s * COUT + o]);  // column n = ky * Cout + o, ky = s
+              if (FUSE2) acc2[s][o] += __uint_as_float(v[16 + s * COUT + o]);
+            }
         }
         // output row r + pad - (KS - 1) has received its last contribution
         const int yo = r + p.pad - (KS - 1);
         if (yo >= y0 && yo < y0 + CR_STRIP_H && yo < vh && gx < vw) {
           float* dst = out_col + (size_t)yo * row_stride;
+          if (!FUSE2) {
 #pragma unroll
-          for (int o = 0; o < COUT; ++o) {
-            const float z = acc[KS - 1][o] + bias[o];
-            dst[o] = p.act == CIC_ACT_TANH ? tanhf(z) : (p.act == CIC_ACT_SIGMOID ? 1.f / (1.f + expf(-z)) : z);
+            for (int o = 0; o < COUT; ++o) {
+              const float z = acc[KS - 1][o] + bias[o];
+              dst[o] = p.act == CIC_ACT_TANH ? tanhf(z) : (p.act == CIC_ACT_SIGMOID ? 1.f / (1.f + expf(-z)) : z);
+            }
+          } else {
+            const size_t pix = pix0 + (size_t)yo * row_pix;
+            const float w = dyn_threshold(__ldg(p.mask + pix), thr);          // :651-657
+            const float w1 = __fsub_rn(1.0f, w);
+            dt_local += (double)w;
+            if (p.dt_out) p.dt_out[pix] = w;
+#pragma unroll
+            for (int o = 0; o < COUT; ++o) {
+              const float h = tanh_fast(acc[KS - 1][o] + bias[o]), l = tanh_fast(acc2[KS - 1][o] + bias2[o]);   // :273 of both generators
+              dst[o] = __fadd_rn(__fmul_rn(h, w), __fmul_rn(l, w1));                                    // :682-684
+              if (p.out_hq) p.out_hq[pix * COUT + o] = h;
+              if (p.out_lq) p.out_lq[pix * COUT + o] = l;
+            }
           }
         }
 #pragma unroll
         for (int s = KS - 1; s > 0; --s)
 #pragma unroll
-          for (int o = 0; o < COUT; ++o) acc[s][o] = acc[s - 1][o];
+          for (int o = 0; o < COUT; ++o) { acc[s][o] = acc[s - 1][o]; if (FUSE2) acc2[s][o] = acc2[s - 1][o]; }
 #pragma unroll
-        for (int o = 0; o < COUT; ++o) acc[0][o] = 0.f;
+        for (int o = 0; o < COUT; ++o) { acc[0][o] = 0.f; if (FUSE2) acc2[0][o] = 0.f; }
+      }
+      if (FUSE2 && p.dt_sum) {   // hq_ratio numerator (GAN_test.py:312): one atomic per warp and strip
+        const double sdt = warp_sum(dt_local);
+        if (lane == 0) atomicAdd(p.dt_sum + img, sdt);
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 32);
+  if (warp == 1) tmem_dealloc(tmem_base, 2 * STG);
 }
 
 // (ks, ks, Cin, Cout) fp32 -> [blk][kx][16 rows n = ky*Cout + o][32 channels] bf16, rows swizzled (SWIZZLE_64B)
@@ -236,17 +297,31 @@ int conv_rows_pack(const float* w, uint8_t* img, int ks, int cin, int cout, cuda
   return CIC_OK;
 }
 
-template <int KS, int COUT>
-static int launch_rows(const TcMaps& maps, const ConvRowsParams& p, cudaStream_t st) {
-  const size_t smem = (size_t)CR_SLOTS * p.slot_bytes + (size_t)p.nblk * KS * 1024 + 512 + 1024;
+template <int KS, int COUT, bool FUSE2>
+static int launch_rows(const TcMaps& maps, ConvRowsParams& p, cudaStream_t st) {
+  // The column owners walk their strips serially (TMEM load, accumulate, store per row), so what hides their latencies is the
+  // number of strips in flight per SM: size the raster ring for THREE co-resident CTAs (32 / 64 TMEM columns each) whenever at
+  // least three slots fit (r02: the fused generator tail went 0.67 -> 0.56 ms from two to three CTAs per SM).
+  const size_t fixed = (size_t)p.nblk * KS * 1024 + 512 + 1024;
+  int slots = (int)((75 * 1024 - fixed) / p.slot_bytes);
+  slots = slots > CR_SLOTS ? CR_SLOTS : slots;
+  if (slots < 3) {   // wide inputs: two CTAs per SM, or one
+    slots = (int)((112 * 1024 - fixed) / p.slot_bytes);
+    if (slots < 3) slots = (int)((227 * 1024 - fixed) / p.slot_bytes);
+    slots = slots > CR_SLOTS ? CR_SLOTS : slots;
+    CIC_REQUIRE(slots >= 2, "conv_rows: input rows of %d bytes do not fit the raster ring", p.slot_bytes);
+  }
+  p.slots = slots;
+  const size_t smem = (size_t)slots * p.slot_bytes + fixed;
   CIC_REQUIRE(smem <= 227 * 1024, "conv_rows: %zu bytes of shared memory", smem);
   static DeviceOnce attr_set;  // function attributes are per device
   if (attr_set.todo()) {
-    CIC_CHECK_CUDA(cudaFuncSetAttribute(conv_rows_tc_kernel<KS, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CIC_CHECK_CUDA(cudaFuncSetAttribute(conv_rows_tc_kernel<KS, COUT, FUSE2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set.done();
   }
-  const int slots = sm_count() * (smem <= 112 * 1024 ? 2 : 1);  // two co-resident CTAs (32 TMEM columns each) when shared memory allows
-  conv_rows_tc_kernel<KS, COUT><<<p.total_strips < slots ? p.total_strips : slots, 192, smem, st>>>(maps, p);
+  const int per_sm = smem <= 75 * 1024 ? 3 : (smem <= 112 * 1024 ? 2 : 1);
+  const int ctas = sm_count() * per_sm;
+  conv_rows_tc_kernel<KS, COUT, FUSE2><<<p.total_strips < ctas ? p.total_strips : ctas, 192, smem, st>>>(maps, p);
   CIC_COUNT_LAUNCH();
   CIC_CHECK_LAUNCH("conv_rows_tc_kernel");
   g_last_kernel_kind = KK_TC_ROWS;
@@ -286,8 +361,47 @@ int launch_conv_rows_tc(const TcAct* srcs, int nsrc, const uint8_t* wimg, const 
   const long long total = (long long)batch * p.strips_x * p.strips_y;
   CIC_REQUIRE(total < 2147483647LL, "conv_rows: too many strips");
   p.total_strips = (int)total;
-  if (ks == 4) return launch_rows<4, 3>(maps, p, st);
-  return launch_rows<3, 3>(maps, p, st);
+  if (ks == 4) return launch_rows<4, 3, false>(maps, p, st);
+  return launch_rows<3, 3, false>(maps, p, st);
+}
+
+// Generator tail in one kernel: Conv2D(3, k4, 'same', tanh) of the HQ and of the LQ generator (GAN_functions.py:273) on their
+// deconv4 outputs (32 channels each), dynamic threshold dt = sigmoid((mask^0.7 - thr) * 20) (:651-657) and the blend
+// hq * dt + lq * (1 - dt) (:682-684).  Replaces two conv_out launches + roi_blend: the un-blended fp32 images (24 B / pixel written,
+// 24 B / pixel read back) never reach HBM.  wimg: the two generators' pre-swizzled conv_out images back to back.
+int launch_gen_tail(const TcAct& hq, const TcAct& lq, const uint8_t* wimg, const float* bias_hq, const float* bias_lq, const float* mask,
+                    const float* bpp, float* out, float* dt_out, double* dt_sum, float* out_hq, float* out_lq, int n_img, int batch, int H,
+                    int W, const TileMap& tm, cudaStream_t st) {
+  CIC_REQUIRE(hq.C == 32 && lq.C == 32 && wimg && mask && bpp && out, "gen_tail: two 32-channel sources, weights, mask, bpp and output");
+  if (batch == 0) return CIC_OK;
+  if (dt_sum) CIC_CHECK_CUDA(cudaMemsetAsync(dt_sum, 0, sizeof(double) * n_img, st));
+  ConvRowsParams p;
+  memset(&p, 0, sizeof(p));
+  TcMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  p.H = H; p.W = W; p.batch = batch; p.ks = 4; p.pad = same_pad_before(H, 4, 1);
+  p.rw = TC_BM + 4 - 1;
+  const TcAct* srcs[2] = {&hq, &lq};
+  for (int s = 0; s < 2; ++s) {
+    const TcAct& a = *srcs[s];
+    CIC_REQUIRE(a.ld % 8 == 0 && a.coff % 8 == 0, "gen_tail: source %d needs 16-byte aligned pixel records", s);
+    p.blk_src[p.nblk] = s; p.blk_c0[p.nblk] = a.coff; ++p.nblk;
+    const uint64_t dims[4] = {(uint64_t)a.ld, (uint64_t)W, (uint64_t)H, (uint64_t)batch};
+    const uint64_t str[3] = {(uint64_t)a.ld * 2, (uint64_t)W * a.ld * 2, (uint64_t)H * W * a.ld * 2};
+    const uint32_t box[4] = {32, (uint32_t)p.rw, 1, 1};
+    int rc = tc_encode_map(&maps.a[s][0], a.hi, 4, dims, str, box);
+    if (rc) return rc;
+  }
+  p.rast_bytes = (p.rw * 64 + 1023) & ~1023;
+  p.slot_bytes = p.nblk * p.rast_bytes;
+  p.cout = 3; p.act = CIC_ACT_TANH; p.wimg = wimg; p.bias = bias_hq; p.bias2 = bias_lq; p.out = out;
+  p.mask = mask; p.bpp = bpp; p.dt_out = dt_out; p.dt_sum = dt_sum; p.out_hq = out_hq; p.out_lq = out_lq;
+  p.tm_tx = tm.tiles_x; p.tm_ty = tm.tiles_y; p.tm_IH = tm.IH; p.tm_IW = tm.IW;
+  p.strips_x = (W + TC_BM - 1) / TC_BM; p.strips_y = (H + CR_STRIP_H - 1) / CR_STRIP_H;
+  const long long total = (long long)batch * p.strips_x * p.strips_y;
+  CIC_REQUIRE(total < 2147483647LL, "gen_tail: too many strips");
+  p.total_strips = (int)total;
+  return launch_rows<4, 3, true>(maps, p, st);
 }
 
 }  // namespace cic

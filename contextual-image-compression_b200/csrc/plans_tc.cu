@@ -171,6 +171,15 @@ int build_adaptive_tc(cic_plan* pl) {
   if (rc) return rc;
   CIC_CHECK_CUDA(cudaMemcpy(bias, b0, 64 * sizeof(float), cudaMemcpyDeviceToDevice));
   CIC_CHECK_CUDA(cudaMemcpy(bias + 64, b1, 64 * sizeof(float), cudaMemcpyDeviceToDevice));
+  // generator tail (conv_out of both generators + dt + blend in one kernel): the two conv_out images back to back
+  const float* k0 = pl->hq_gen->w.ptr("conv_out/kernel");
+  const float* k1 = pl->lq_gen->w.ptr("conv_out/kernel");
+  CIC_REQUIRE(k0 && k1, "tc plan: conv_out weights of both generators");
+  const size_t one = conv_rows_image_bytes(4, 32);
+  uint8_t* tail = (uint8_t*)pl->tcw.alloc("gen_tail#rows", 2 * one);
+  CIC_REQUIRE(tail, "tc plan: out of device memory");
+  if ((rc = conv_rows_pack(k0, tail, 4, 32, 3, nullptr))) return rc;
+  if ((rc = conv_rows_pack(k1, tail + one, 4, 32, 3, nullptr))) return rc;
   CIC_CHECK_CUDA(cudaDeviceSynchronize());
   return CIC_OK;
 }
@@ -449,8 +458,10 @@ int encoder_forward_tc(cic_plan* pl, Ctx& c, const float* img, float* latent, fl
 // latent fp32 (B, L); skips as bf16 NHWC (hi only is read)
 // part: 0 = whole generator, 1 = Dense + BN + LeakyReLU only (output to *g0_ext), 2 = transposed convs + conv_out only (reads *g0_ext)
 enum { GEN_ALL = 0, GEN_DENSE = 1, GEN_CONVS = 2 };
+// g4_ext != nullptr: stop after deconv4 and leave its output (256^2 x 32 bf16 per tile) there - the adaptive model runs conv_out of
+// both generators and the blend as one kernel (launch_gen_tail)
 static int generator_core_tc(cic_plan* pl, Ctx& c, const float* latent, const bf16* s1, const bf16* s2, const bf16* s3, float* out, int B,
-                             const TileMap& tm = TileMap(), int part = GEN_ALL, const ActBuf* g0_ext = nullptr) {
+                             const TileMap& tm = TileMap(), int part = GEN_ALL, const ActBuf* g0_ext = nullptr, const ActBuf* g4_ext = nullptr) {
   const WeightStore& w = pl->w;
   const int H = pl->opts.img_h, W = pl->opts.img_w, C = pl->opts.img_c, L = pl->opts.latent_dim;
   const int h16 = H / 16, w16 = W / 16, feat = h16 * w16 * 512;
@@ -462,7 +473,7 @@ static int generator_core_tc(cic_plan* pl, Ctx& c, const float* latent, const bf
   ActBuf g1 = alloc_act(c, px / 64 * 256, false);
   ActBuf g2 = alloc_act(c, px / 16 * 128, false);
   ActBuf g3 = alloc_act(c, px / 4 * 64, false);
-  ActBuf g4 = alloc_act(c, px * 32, false);
+  ActBuf g4 = g4_ext ? *g4_ext : alloc_act(c, px * 32, false);
   int rc;
   // :247-250 Dense -> Reshape(h16, w16, 512) NHWC -> BN -> LeakyReLU
   if (part == GEN_CONVS) {
@@ -497,6 +508,10 @@ static int generator_core_tc(cic_plan* pl, Ctx& c, const float* latent, const bf
   DC(3, view(g2, 128), &k2, 4 * h16, 4 * w16, 256, 64, g3);
   DC(4, view(g3, 64), &k1, 8 * h16, 8 * w16, 128, 32, g4);
 #undef DC
+  if (g4_ext) {
+    c.arena.release(mk);
+    return CIC_OK;
+  }
   // :273 Conv2D(3, k4, 'same', tanh): pad 1 before / 2 after
   static const int no_rows = CIC_KNOB("CIC_TC_NO_ROWS", 0);
   if (C == 3 && !no_rows) {  // column-strip formulation (kx folded into K, ky into N)
@@ -718,6 +733,30 @@ int adaptive_forward_tc(cic_plan* pl, Ctx& c, const cic_adaptive_io* io, int n_i
     c.arena.release(mk);
   }
   if (do_dec) {
+    const uint8_t* tail_img = (const uint8_t*)pl->tcw.ptr("gen_tail#rows");
+    // (the workspace dry run measures the fused path: it keeps both deconv4 outputs alive at once)
+    const bool fused_tail = pl->opts.img_c == 3 && tail_img && (io->d_blended || c.dry) && CIC_KNOB("CIC_GEN_TAIL", 1);
+    if (fused_tail) {
+      // 6-7. generators up to deconv4 (:669-670), then conv_out of both + dynamic threshold + blend in one kernel (:273, :651-657,
+      // :682-684): the un-blended images never reach HBM
+      ActBuf g4h = alloc_act(c, tpx * 32, false), g4l = alloc_act(c, tpx * 32, false);
+      mk = c.arena.mark();
+      if (c.prof) c.prof->prefix = "hq_gen/";
+      if ((rc = generator_core_tc(pl->hq_gen.get(), c, hq_q, hs.x1.hi, hs.x2.hi, hs.x3.hi, nullptr, nt, tm, all ? GEN_ALL : GEN_CONVS, all ? nullptr : &g0[0], &g4h))) return rc;
+      c.arena.release(mk);
+      if (c.prof) c.prof->prefix = "lq_gen/";
+      if ((rc = generator_core_tc(pl->lq_gen.get(), c, lq_q, ls.x1.hi, ls.x2.hi, ls.x3.hi, nullptr, nt, tm, all ? GEN_ALL : GEN_CONVS, all ? nullptr : &g0[1], &g4l))) return rc;
+      c.arena.release(mk);
+      if (c.prof) c.prof->prefix = "";
+      if (!c.dry) {
+        const double px = (double)n_img * img_h * img_w;
+        Scope sc(c, "gen_tail", 2.0 * 2 * tpx * 16 * 32 * 3, 2.0 * 2 * tpx * 32 + px * (4.0 + 12.0 + (io->d_dt ? 4.0 : 0.0)));
+        if ((rc = launch_gen_tail(view(g4h, 32), view(g4l, 32), tail_img, pl->hq_gen->w.ptr("conv_out/bias"), pl->lq_gen->w.ptr("conv_out/bias"),
+                                  io->d_mask, io->d_bpp, io->d_blended, io->d_dt, io->d_hq_ratio_sum, io->d_hq_out, io->d_lq_out, n_img, nt, T, T,
+                                  tiled ? tm : TileMap(), c.st))) return rc;
+      }
+      return CIC_OK;
+    }
     // 6. generators (:669-670)
     float* hq_img = io->d_hq_out ? io->d_hq_out : c.arena.f32(tpx * 3);  // image layout
     float* lq_img = io->d_lq_out ? io->d_lq_out : c.arena.f32(tpx * 3);

@@ -78,6 +78,9 @@ size_t conv_rows_image_bytes(int ks, int cin);
 int conv_rows_pack(const float* w, uint8_t* img, int ks, int cin, int cout, cudaStream_t st);
 int launch_conv_rows_tc(const TcAct* srcs, int nsrc, const uint8_t* wimg, const float* bias, int ks, int cout, int act, float* out,
                         int batch, int H, int W, const TileMap& tm, cudaStream_t st);
+int launch_gen_tail(const TcAct& hq, const TcAct& lq, const uint8_t* wimg, const float* bias_hq, const float* bias_lq, const float* mask,
+                    const float* bpp, float* out, float* dt_out, double* dt_sum, float* out_hq, float* out_lq, int n_img, int batch, int H,
+                    int W, const TileMap& tm, cudaStream_t st);
 // MaxPooling2D((2,2)) on NHWC bf16 (even H, W; C % 8 == 0)
 int tc_maxpool2x2_bf16(const bf16* x, bf16* y, int batch, int H, int W, int C, cudaStream_t st);
 // split-K partials [splits][M][N] -> epilogue -> fp32 [M][N] and/or bf16 hi/lo [M][N]

@@ -254,7 +254,7 @@ def run_reference(args):
 
 # ---- product arm -----------------------------------------------------------------------------------------------------------------
 KINDS = {0: "other", 1: "tc_gemm_kernel", 2: "tc_conv_kernel", 3: "conv1_tc_kernel", 4: "direct_conv_kernel", 5: "igemm_f32_kernel",
-         6: "conv_rows_tc_kernel", 7: "tc_gemm2_kernel", 8: "attn_fused_kernel", 9: "gen_tail_kernel"}
+         6: "conv_rows_tc_kernel", 7: "tc_gemm2_kernel", 8: "attn_fused_kernel"}
 
 
 class Bench:

@@ -26,9 +26,11 @@ def _deps_mtime():
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _deps_mtime():
-        return LIB
     objdir = os.path.join(HERE, "build")
+    stamp = os.path.join(objdir, "flags.txt")          # a library built with other flags (e.g. the tuning knobs) is stale too
+    same_flags = os.path.exists(stamp) and open(stamp).read() == " ".join(FLAGS)
+    if not force and same_flags and os.path.exists(LIB) and os.path.getmtime(LIB) >= _deps_mtime():
+        return LIB
     os.makedirs(objdir, exist_ok=True)
 
     def compile_one(src):
@@ -49,6 +51,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    with open(stamp, "w") as f:
+        f.write(" ".join(FLAGS))
     # Blackwell proof: per-kernel counts of UTCHMMA[.2CTA] / LDTM / UTMALDG in the library just linked -> profiles/sass_summary.txt
     tool = os.path.join(HERE, "..", "tools", "sass_summary.py")
     if os.environ.get("CIC_SASS_SUMMARY", "1") != "0" and os.path.exists(tool):

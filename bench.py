@@ -191,7 +191,7 @@ def run_reference(args):
     cfg_name = args.config
     cfg = CONFIGS[cfg_name]
     cores = os.cpu_count() or 1
-    budget_s = float(os.environ.get("CIC_REF_BUDGET_S", "300"))
+    budget_s = float(os.environ.get("CIC_REF_BUDGET_S", "340"))
     if cfg["kind"] == "ae":
         from oracle import graphs, metrics
         torch.set_num_threads(cores)
@@ -554,7 +554,7 @@ class Bench:
         par, cpu = None, None
         if self.rank == 0 and args.cpu_tiles > 0:
             from oracle import parity, tiling
-            k = min(pool, 2 if name != "c2" else 4)
+            k = min(pool, 2 if name != "c2" else 16)
             out = am.forward_device([d_img[:k], d_mask[:k], d_bpp[:k]], extras=True)
             got = {key: out[key].cpu().numpy() for key in ("blended", "dt", "hq_symbols", "lq_symbols", "hq_ratio_sum")}
             # the bitstream the reference never writes: rANS over the integer symbols of these k images, both branches,

@@ -333,7 +333,7 @@ class Model:
                 lo, hi = bounds[i], bounds[i + 1]
                 d_in = [torch.zeros((hi - lo,) + tuple(h.shape[1:]), dtype=torch.float32, device=dev) for h in hs]
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
                     outs = self.forward_device(d_in)
                     ex = on_chunk(d_in, getattr(self, "last", None)) if on_chunk is not None else None
                 d_ins.append(d_in)
@@ -846,7 +846,7 @@ class AdaptiveCompressionModel(Model):
                         wsd.update(gen=self._plan_gen, buf=torch.empty(max(need, 1 << 20), dtype=torch.uint8, device=dev))
                     self._ws_override = wsd["buf"]
                     g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g):
+                    with torch.cuda.graph(g, capture_error_mode="thread_local"):
                         ex = self._stream_compute(b, n, h, w, u8_io, want_dt, on_batch)
                     b["graph"], b["extra"], b["on_batch"] = g, ex, on_batch
                     torch.cuda.synchronize()
@@ -982,16 +982,16 @@ class AdaptiveCompressionModel(Model):
                 enc, dec, extra_g = [], [], []
                 for i in range(len(eb) - 1):
                     g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g):
+                    with torch.cuda.graph(g, capture_error_mode="thread_local"):
                         encode(eb[i], eb[i + 1])
                     enc.append(g)
                 lat = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(lat):
+                with torch.cuda.graph(lat, capture_error_mode="thread_local"):
                     self._phase_call(b, _lib.PHASE_LATENT, 0, n, h, w)
                 for i in range(len(db) - 1):
                     lo, hi = db[i], db[i + 1]
                     g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g):
+                    with torch.cuda.graph(g, capture_error_mode="thread_local"):
                         ex = decode(lo, hi)
                     dec.append(g)
                     extra_g.append(ex)

@@ -492,7 +492,7 @@ class Bench:
             outputs go back to pinned host memory inside the timed region; consecutive calls overlap (upload of the next, kernels of
             this, download of the previous).  The metric sums of a step are all-reduced and copied to the host asynchronously."""
             src = [h_img8 if u8 else h_img, h_mask, h_bpp]
-            sums_dev = torch.zeros((max(e2e_steps, e2e_warm, 4), nfields), dtype=torch.float64, device=self.dev)
+            sums_dev = torch.zeros((max(e2e_steps, e2e_warm, 6), nfields), dtype=torch.float64, device=self.dev)
             sums_host = torch.zeros_like(sums_dev, device="cpu").pin_memory()
             last = {}
 
@@ -502,7 +502,7 @@ class Bench:
                         for k in sizes:
                             yield [t[:k] for t in src]
                 tot, seen, step = None, 0, 0
-                for outs, part in am.predict_stream(gen(), on_batch=on_chunk, u8_io=u8, want_dt=want_dt):
+                for outs, part in am.predict_stream(gen(), on_batch=on_chunk, u8_io=u8, want_dt=want_dt, depth=3):
                     tot = part.clone() if tot is None else tot + part
                     seen += 1
                     last["outs"] = outs
@@ -513,7 +513,7 @@ class Bench:
                         tot, seen, step = None, 0, step + 1
                 sums_host.copy_(sums_dev, non_blocking=True)
                 torch.cuda.synchronize()
-            run(max(e2e_warm, -(-4 // len(sizes))))                               # >= 4 forward calls: each of the two slots runs eagerly once, then captures its graph
+            run(max(e2e_warm, -(-6 // len(sizes))))                               # >= 6 forward calls: each of the three slots runs eagerly once, then captures its graph
             torch.cuda.synchronize()
             cic.dist.barrier()
             torch.cuda.synchronize()

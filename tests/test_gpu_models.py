@@ -354,3 +354,28 @@ def test_stream_predict_equals_predict(cic, small_cfg):
         assert np.abs(outs[0].astype(int) - want8.astype(int)).max() <= 3
         np.testing.assert_allclose(outs[4], want[4].reshape(3, -1).mean(1, dtype=np.float64), atol=1e-6)
     assert list(am.predict_stream(iter([]))) == []
+
+
+def test_rate_sweep_equals_one_predict_per_level(cic, small_cfg):
+    """rate_sweep_device (BASELINE configs[2]: encoders once, quantiser + generators + blend per target bpp) gives, per level, what
+    the reference's loop of full predictions gives (GAN_test.py:565-573): hq_ratio, blended image, quantised latents."""
+    cic.set_precision("tc")
+    models, ws = _adaptive(cic, small_cfg["img_shape"], small_cfg["base"])
+    am = models["adaptive_model"]
+    img = cic.synth.to_signed_range(cic.synth.synth_images_u8(2, 128, 192, seed=52))
+    mask = cic.synth.synth_masks(2, 128, 192, seed=52)
+    levels = [0.1, 0.944444, 2.0]
+    seen = {}
+
+    def on_level(k, ins, outs):
+        seen[k] = (outs["blended"].cpu().numpy().copy(), outs["hq_latent_q"].cpu().numpy().copy(), outs["dt"].cpu().numpy().copy())
+    ratios = am.rate_sweep_device(cic.runtime.to_device_f32(img), cic.runtime.to_device_f32(mask), levels, on_level).cpu().numpy()
+    assert ratios.shape == (3, 2) and np.all(np.diff(ratios, axis=0) > 0)
+    for k, lv in enumerate(levels):
+        want = am.predict([img, mask, np.full((2, 1), lv, np.float32)])
+        np.testing.assert_allclose(ratios[k], want[4].reshape(2, -1).mean(1, dtype=np.float64), atol=1e-6)
+        np.testing.assert_allclose(seen[k][2], want[4], atol=1e-6)
+        np.testing.assert_allclose(seen[k][0], want[0], atol=2e-2, rtol=0)
+        assert np.mean(seen[k][1] != want[1]) < 0.01
+    sweep = cic.ops.hq_ratio_sweep(mask, np.array(levels, np.float32)).cpu().numpy()          # the mask-only fast path agrees
+    np.testing.assert_allclose(sweep.T, ratios, atol=1e-6)

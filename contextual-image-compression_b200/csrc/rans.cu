@@ -208,6 +208,10 @@ rans_pack_kernel(const uint16_t* __restrict__ words, const uint32_t* __restrict_
 __global__ void __launch_bounds__(128)
 rans_decode_rows_kernel(const uint8_t* __restrict__ stream, int32_t* __restrict__ out, int rows, int L) {
   extern __shared__ uint32_t rsm[];
+  {  // a stream whose header does not describe (rows, L) is not walked at all: its offsets would be read out of bounds
+    const uint32_t* hd = reinterpret_cast<const uint32_t*>(stream);
+    if (hd[0] != RANS_MAGIC || hd[1] != 1u || hd[2] != (uint32_t)rows || hd[3] != (uint32_t)L || hd[4] != RANS_PROB_BITS || hd[5] != RANS_ALPHA) return;
+  }
   uint32_t* stab = rsm;                                            // [2047] freq | cum << 16
   uint16_t* lut = reinterpret_cast<uint16_t*>(rsm + RANS_ALPHA + 1);   // [2^14] slot -> symbol
   __shared__ uint32_t scan[128];

@@ -239,6 +239,12 @@ def rans_decode(stream: torch.Tensor, rows: int, latent_dim: int) -> torch.Tenso
     stream = stream.to(runtime.require_cuda()).contiguous()
     if stream.data_ptr() % 4:
         stream = stream.clone()
+    if stream.numel() < 32 + 4096 + 4 * (rows + 1):
+        raise ValueError(f"stream of {stream.numel()} bytes is shorter than the header of a {rows}-row stream")
+    header = stream[:32].cpu().numpy().view("<u4")          # validated on the host: the kernel refuses a mismatching stream too
+    if header[0] != 0x52434943 or header[1] != 1 or (int(header[2]), int(header[3])) != (rows, latent_dim):
+        raise ValueError(f"not a CICR v1 stream of shape ({rows}, {latent_dim}): header says magic {int(header[0]):#x}, version {int(header[1])}, "
+                         f"shape ({int(header[2])}, {int(header[3])})")
     out = torch.empty((rows, latent_dim), dtype=torch.int32, device=stream.device)
     _lib.check(_lib.lib.cic_rans_decode(ptr(stream), stream.numel(), ptr(out), rows, latent_dim, runtime.stream_ptr()))
     return out

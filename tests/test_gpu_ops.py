@@ -335,6 +335,10 @@ def test_rans_round_trip_on_codec_symbols_and_empty(cic):
     bits = cic.ops.symbol_entropy_bits(sym.reshape(1, -1)).item()                 # zeroth-order entropy of the whole call
     coded = 8.0 * stream.numel()
     assert bits <= coded <= bits + 1.5 * x.size + 8 * 6000, (bits, coded)
+    with pytest.raises(ValueError, match="CICR"):
+        cic.ops.rans_decode(stream, 128, 1024)                                   # wrong shape for this stream
+    with pytest.raises(ValueError, match="shorter"):
+        cic.ops.rans_decode(stream[:100], 256, 1024)
     empty = cic.ops.rans_encode(torch.zeros((0, 64), dtype=torch.int32, device="cuda"))
     assert empty.numel() == 32 + 4096 + 4
     assert cic.ops.rans_decode(empty, 0, 64).shape == (0, 64)

@@ -379,3 +379,31 @@ def test_rate_sweep_equals_one_predict_per_level(cic, small_cfg):
         assert np.mean(seen[k][1] != want[1]) < 0.01
     sweep = cic.ops.hq_ratio_sweep(mask, np.array(levels, np.float32)).cpu().numpy()          # the mask-only fast path agrees
     np.testing.assert_allclose(sweep.T, ratios, atol=1e-6)
+
+
+def test_host_paths_on_ragged_sizes(cic, small_cfg):
+    """predict_phased / predict_stream / rate_sweep_device on an image size that is not a multiple of the tile: the same cropped
+    outputs as predict (whose ragged-size parity against the oracle is test_adaptive_ragged_small)."""
+    cic.set_precision("tc")
+    models, ws = _adaptive(cic, small_cfg["img_shape"], small_cfg["base"])
+    am = models["adaptive_model"]
+    n, h, w = 5, 100, 148
+    img_u8 = cic.synth.synth_images_u8(n, h, w, seed=53)
+    img = cic.synth.to_signed_range(img_u8)
+    mask = cic.synth.synth_masks(n, h, w, seed=53)
+    bpp = np.linspace(0.3, 1.7, n, dtype=np.float32).reshape(n, 1)
+    want = am.predict([img, mask, bpp])
+    assert want[0].shape == (n, h, w, 3) and want[1].shape == (n * 2 * 3, 2 * small_cfg["base"])
+    for call in range(3):
+        got, _ = am.predict_phased([img, mask, bpp], enc_chunks=[2, 3], dec_chunks=[3, 2])
+        for g, wv in zip(got, want):
+            assert g.shape == wv.shape
+            np.testing.assert_allclose(g, wv, atol=2e-2, rtol=0)
+    outs = [([np.array(o) for o in o5]) for o5, _ in am.predict_stream(iter([[img_u8, mask, bpp]] * 3), u8_io=True)]
+    want8 = ((want[0] + 1) * np.float32(127.5)).astype(np.uint8)
+    for o5 in outs:
+        assert o5[0].shape == (n, h, w, 3) and np.abs(o5[0].astype(int) - want8.astype(int)).max() <= 3
+        np.testing.assert_allclose(o5[4], want[4], atol=1e-6)
+    ratios = am.rate_sweep_device(cic.runtime.to_device_f32(img), cic.runtime.to_device_f32(mask), [1.0]).cpu().numpy()
+    full = am.predict([img, mask, np.ones((n, 1), np.float32)])
+    np.testing.assert_allclose(ratios[0], full[4].reshape(n, -1).mean(1, dtype=np.float64), atol=1e-6)

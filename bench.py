@@ -206,8 +206,10 @@ def run_reference(args):
                 metrics.ae_calculate_mse(x8, y8), metrics.ae_calculate_psnr(x8, y8), metrics.ae_calculate_ssim(x8, y8)
             return time.perf_counter() - t0
         px, sample, extrapolated = x.shape[0] * cfg["h"] * cfg["w"], f"all {x.shape[0]} images per step (batch-1 loop)", False
+        n_ref_images = x.shape[0]
     else:
         n_img = cfg.get("images", cfg.get("images_total"))
+        n_ref_images = n_img
         weights = W.synthetic_adaptive((TILE, TILE, 3), BASE_LATENT, seed=42)
         pool = min(n_img, cfg.get("pool", n_img))
         _, img, mask, bpp = gan_inputs(synth, 0, pool, cfg["h"], cfg["w"], cfg.get("bpp", 1.0), 1)
@@ -243,7 +245,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "MPix/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "extrapolated": bool(extrapolated),
-            "config": {"workload": f"{cfg['what']} (BASELINE {cfg['baseline']})", "name": cfg_name, "sample": sample, "l2": "n/a (CPU)"},
+            "config": {"workload": f"{cfg['what']} (BASELINE {cfg['baseline']})", "name": cfg_name, "sample": sample, "l2": "n/a (CPU)",
+                       "images_per_gpu": n_ref_images, "images_total": n_ref_images},
             "cpu_baseline": {"value": val, "unit": "MPix/s", "cores": cores, "kind": "port",
                              "sample": f"{sample}; torch {torch.__version__} CPU fp32 oracle of the reference graph, {cores} threads "
                                        f"(the reference's TensorFlow stack is not installable here)"},

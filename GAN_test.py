@@ -15,22 +15,23 @@ MODEL_DIR = "models"
 
 
 def load_models(model_dir=None, weights=None):
-    """GAN_test.py:37-220 loads Keras .h5 checkpoints.  h5py is not available here, so `model_dir` is expected to hold
-    `adaptive_weights.npz`, the flat Keras-layout checkpoint tools/convert_keras_h5.py writes from the reference's `*_final.h5`
-    files; alternatively pass `weights` ({sub_model: {name: array}}, e.g. cic_b200.weights.synthetic_adaptive).  Builds the same
-    eight-entry dict; with neither argument the models keep Keras-default init."""
+    """GAN_test.py:37-220: load the trained component models from `model_dir`.  Reads, in this order of preference,
+      * the reference's own Keras checkpoints `<component>_final.h5`, or the latest `<component>_epoch_<n>.h5` when the final ones
+        are missing (GAN_test.py:84-125) - through cic_b200.keras_h5 on the package's HDF5 reader (no h5py / TensorFlow needed);
+      * `adaptive_weights.npz`, the flat Keras-layout checkpoint tools/convert_keras_h5.py writes;
+    or takes `weights` ({sub_model: {name: array}}, e.g. cic_b200.weights.synthetic_adaptive) directly.  Builds the same eight-entry
+    dict; with neither argument the models keep Keras-default init.  Raises ValueError("No models found! ...") like the reference
+    (:219) when the directory holds neither."""
     if model_dir is not None and weights is None:
-        import os
         import cic_b200
         npz = os.path.join(model_dir, "adaptive_weights.npz")
-        if os.path.exists(npz):                    # written by tools/convert_keras_h5.py from the reference's *_final.h5 files
+        if os.path.isdir(model_dir) and cic_b200.keras_h5.find_suffix(model_dir):
+            weights = cic_b200.keras_h5.load_adaptive_dir(model_dir)
+        elif os.path.exists(npz):
             weights = cic_b200.weights.load_npz(npz)
-            cic_b200.weights.check_adaptive(weights, IMG_SHAPE, BASE_LATENT_DIM)
-        elif os.path.isdir(model_dir) and any(f.endswith(".h5") for f in os.listdir(model_dir)):
-            raise NotImplementedError(f"{model_dir} holds Keras .h5 checkpoints: convert them once with tools/convert_keras_h5.py in the "
-                                      "reference's TensorFlow environment (h5py is not available here) -> adaptive_weights.npz")
         else:
-            raise FileNotFoundError(f"no adaptive_weights.npz (or .h5 checkpoints) in {model_dir}")
+            raise ValueError("No models found! Please train the models first.")
+        cic_b200.weights.check_adaptive(weights, IMG_SHAPE, BASE_LATENT_DIM)
     models = build_adaptive_compression_model(IMG_SHAPE, BASE_LATENT_DIM, target_bpp=True)
     if weights is not None:
         models["adaptive_model"].set_weights_dict(weights)

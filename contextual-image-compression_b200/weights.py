@@ -1,6 +1,6 @@
 """Weight containers in Keras layouts + the synthetic-weight recipe.
 
-Layouts follow Keras so that a later `.h5` importer is a pure rename:
+Layouts follow Keras so that the `.h5` importer (keras_h5.py) is a pure rename:
   Conv2D kernel           (kh, kw, Cin, Cout)      bias (Cout,)
   Conv2DTranspose kernel  (kh, kw, Cout, Cin)      bias (Cout,)
   Dense kernel            (in, out)                bias (out,)
@@ -190,9 +190,8 @@ def synthetic_adaptive(img_shape, base_latent_dim: int, seed: int = 42,
 
 # ---- checkpoints -----------------------------------------------------------------------------------------------------------
 # The reference saves each sub-model with Keras `model.save("*.h5")` (GAN_train.py:548-581) and reloads it with
-# `keras.models.load_model` (GAN_test.py:37-78).  Neither h5py nor TensorFlow exists in this repository's environment, so the
-# exchange format is a flat .npz in the Keras layouts above ("<sub_model>/<layer>/<tensor>"): `tools/convert_keras_h5.py`
-# writes it in the reference's own environment, `load_npz` reads it here.
+# `keras.models.load_model` (GAN_test.py:37-78).  keras_h5.py reads those files directly; the flat .npz below (Keras layouts,
+# "<sub_model>/<layer>/<tensor>") is the second route: `tools/convert_keras_h5.py` writes it in the reference's own environment.
 
 def flatten(nested: Dict[str, Weights]) -> Weights:
     return {f"{sub}/{k}": np.asarray(v) for sub, ws in nested.items() for k, v in ws.items()}

@@ -13,10 +13,27 @@ from cic_b200.autoencoder import (  # noqa: F401
 target_size = (128, 128)  # test_autoencoder.py:39
 
 
-def main(n_images=32, size=(256, 256)):
+model_path = "autoencoder_model.h5"  # test_autoencoder.py:30
+
+
+def load_model(path=model_path, input_shape=(128, 128, 3)):
+    """test_autoencoder.py:30-34: the trained autoencoder from its Keras .h5 checkpoint (read with cic_b200.keras_h5)."""
+    import os
+    from cic_b200 import keras_h5
+    if not os.path.exists(path):
+        raise FileNotFoundError(f"Trained model not found: {path}")   # test_autoencoder.py:31-32
+    model = build_autoencoder(input_shape)
+    model.set_weights_dict(keras_h5.load_autoencoder(path))
+    return model
+
+
+def main(n_images=32, size=(256, 256), path=None):
     from cic_b200 import synth, weights
-    model = build_autoencoder((size[0], size[1], 3))
-    model.set_weights_dict(weights.synthetic_autoencoder())
+    if path is not None:
+        model = load_model(path, (size[0], size[1], 3))
+    else:
+        model = build_autoencoder((size[0], size[1], 3))
+        model.set_weights_dict(weights.synthetic_autoencoder())
     imgs = synth.to_unit_range(synth.synth_images_u8(n_images, size[0], size[1]))
     r = evaluate_batch(model, imgs)
     print("\n=== Overall Compression Performance ===")

@@ -11,9 +11,14 @@ It loads the seven component models the reference saves at the end of training (
 `model.layers` in creation order and names the tensors the way contextual-image-compression_b200/weights.py does; layouts are
 Keras' own (Conv2D (kh,kw,Cin,Cout), Conv2DTranspose (kh,kw,Cout,Cin), Dense (in,out)), so nothing is transposed.
 
+Since the package reads .h5 files itself (contextual-image-compression_b200/keras_h5.py on hdf5_lite.py, `GAN_test.load_models(model_dir)`), this
+script is the second route: it goes through Keras' own loader, so it also works for checkpoints in formats hdf5_lite does not
+cover, and the two routes can be compared on a real checkpoint (`--check` reads the same files with hdf5_lite and asserts equality).
+
 THIS SCRIPT CANNOT BE EXECUTED IN THIS REPOSITORY'S CONTAINER (no TensorFlow, no h5py): the Keras-loading part is unverified here.
-The layer-to-name mapping (`map_layers`) is pure Python on duck-typed layers and is covered by tests/test_host_logic.py; it follows
-the creation order of GAN_functions.py:236-331 (generator, encoder), :210-234 (latent saliency), :495-557 (RD optimizer).
+The layer-to-name mapping (`map_layers`, shared with keras_h5.py) is pure Python on duck-typed layers and is covered by
+tests/test_host_logic.py; it follows the creation order of GAN_functions.py:236-331 (generator, encoder), :210-234 (latent
+saliency), :495-557 (RD optimizer).
 """
 from __future__ import annotations
 
@@ -23,68 +28,21 @@ import os
 import numpy as np
 
 
-def _cls(layer) -> str:
-    return type(layer).__name__
+def _keras_h5():
+    """contextual-image-compression_b200/keras_h5.py (+ hdf5_lite.py) imported under a shell package: both are pure Python + numpy, whereas the
+    package's own __init__ loads the CUDA library"""
+    import importlib
+    import sys
+    import types
+    pkg = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "contextual-image-compression_b200")
+    shell = types.ModuleType("cic_h5pkg")
+    shell.__path__ = [pkg]
+    sys.modules.setdefault("cic_h5pkg", shell)
+    return importlib.import_module("cic_h5pkg.keras_h5")
 
 
-def map_layers(layers, kind: str) -> dict:
-    """{name: array} for one sub-model from its layers in creation order (objects with a class name and get_weights())."""
-    out = {}
-    convs = [l for l in layers if _cls(l) == "Conv2D"]
-    deconvs = [l for l in layers if _cls(l) == "Conv2DTranspose"]
-    denses = [l for l in layers if _cls(l) == "Dense"]
-    bns = [l for l in layers if _cls(l) == "BatchNormalization"]
-    attn = [l for l in layers if _cls(l) == "SelfAttention"]
-
-    def put(prefix, layer, names=("kernel", "bias")):
-        ws = layer.get_weights()
-        if len(ws) != len(names):
-            raise ValueError(f"{kind}/{prefix}: expected {len(names)} tensors, found {len(ws)}")
-        for n, w in zip(names, ws):
-            out[f"{prefix}/{n}"] = np.asarray(w, np.float32)
-
-    bn_names = ("gamma", "beta", "moving_mean", "moving_variance")
-    if kind == "encoder":                      # GAN_functions.py:300-326: conv1, (conv + BN) x 3, [attention before conv4], Dense
-        if len(convs) != 4 or len(bns) != 3 or len(denses) != 1 or len(attn) > 1:
-            raise ValueError(f"encoder: unexpected layer counts conv={len(convs)} bn={len(bns)} dense={len(denses)} attn={len(attn)}")
-        for i, l in enumerate(convs, start=1):
-            put(f"conv{i}", l)
-        for i, l in enumerate(bns, start=2):
-            put(f"bn{i}", l, bn_names)
-        put("dense", denses[0])
-        if attn:                               # :339-342: weights in creation order gamma, then query / key / value kernel + bias
-            a = attn[0]
-            for nm, sub in (("query", a.query_conv), ("key", a.key_conv), ("value", a.value_conv)):
-                put(f"attn/{nm}", sub)
-            out["attn/gamma"] = np.asarray(a.gamma.numpy() if hasattr(a.gamma, "numpy") else a.gamma, np.float32).reshape(1)
-    elif kind == "generator":                  # :247-273: Dense, BN, (ConvT + BN) x 4, Conv2D
-        if len(denses) != 1 or len(bns) != 5 or len(deconvs) != 4 or len(convs) != 1:
-            raise ValueError(f"generator: unexpected layer counts dense={len(denses)} bn={len(bns)} deconv={len(deconvs)} conv={len(convs)}")
-        put("dense", denses[0])
-        for i, l in enumerate(bns):
-            put(f"bn{i}", l, bn_names)
-        for i, l in enumerate(deconvs, start=1):
-            put(f"deconv{i}", l)
-        put("conv_out", convs[0])
-    elif kind == "latent_saliency":            # :224-229: three Dense layers
-        if len(denses) != 3:
-            raise ValueError(f"latent saliency: expected 3 Dense layers, found {len(denses)}")
-        for i, l in enumerate(denses, start=1):
-            put(f"dense{i}", l)
-    elif kind == "rd_optimizer":               # :511-525: two Conv2D, two Dense
-        if len(convs) != 2 or len(denses) != 2:
-            raise ValueError(f"rd optimizer: unexpected layer counts conv={len(convs)} dense={len(denses)}")
-        for i, l in enumerate(convs, start=1):
-            put(f"conv{i}", l)
-        for i, l in enumerate(denses, start=1):
-            put(f"dense{i}", l)
-    else:
-        raise ValueError(f"unknown sub-model kind '{kind}'")
-    return out
-
-
-SUB_MODELS = (("hq_encoder", "encoder"), ("hq_generator", "generator"), ("lq_encoder", "encoder"), ("lq_generator", "generator"),
-              ("latent_saliency_hq", "latent_saliency"), ("latent_saliency_lq", "latent_saliency"), ("rd_optimizer", "rd_optimizer"))
+_K = _keras_h5()
+map_layers, SUB_MODELS = _K.map_layers, _K.SUB_MODELS
 
 
 def main():
@@ -92,6 +50,7 @@ def main():
     ap.add_argument("--model-dir", default="models")
     ap.add_argument("--suffix", default="_final.h5", help="file name suffix of the component checkpoints (e.g. _epoch_50.h5)")
     ap.add_argument("--out", default=None)
+    ap.add_argument("--check", action="store_true", help="also read the files with the package's own HDF5 reader and compare")
     args = ap.parse_args()
     from tensorflow import keras                                   # noqa: PLC0415  (only available in the reference's environment)
     from GAN_functions import SelfAttention, AdaptiveQuantizationLayer  # the reference's module, GAN_test.py:14-20
@@ -101,6 +60,13 @@ def main():
         model = keras.models.load_model(os.path.join(args.model_dir, sub + args.suffix), custom_objects=custom, compile=False)
         for k, v in map_layers(list(model.layers), kind).items():
             flat[f"{sub}/{k}"] = v
+    if args.check:
+        own = _K.load_adaptive_dir(args.model_dir, args.suffix)
+        for sub, ws in own.items():
+            for k, v in ws.items():
+                if not np.array_equal(v, flat[f"{sub}/{k}"]):
+                    raise SystemExit(f"hdf5_lite and Keras disagree on {sub}/{k}")
+        print(f"hdf5_lite read the same {sum(len(w) for w in own.values())} tensors bit for bit")
     out = args.out or os.path.join(args.model_dir, "adaptive_weights.npz")
     np.savez(out, **flat)
     print(f"wrote {len(flat)} tensors, {sum(v.size for v in flat.values()):,} parameters -> {out}")

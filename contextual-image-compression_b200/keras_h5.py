@@ -171,7 +171,8 @@ def _class_names(model_config: Optional[dict]) -> Dict[str, str]:
     out: Dict[str, str] = {}
     if not model_config:
         return out
-    for l in model_config.get("config", {}).get("layers", []):
+    cfg = model_config.get("config", {})
+    for l in (cfg if isinstance(cfg, list) else cfg.get("layers", [])):      # very old Sequential files: config is the layer list
         name = l.get("name") or l.get("config", {}).get("name")
         if name:
             out[name] = l.get("class_name", "")

@@ -41,7 +41,22 @@ def _message(mtype: int, body: bytes) -> bytes:
     return struct.pack("<HHB3x", mtype, len(body), 0) + body
 
 
-def _attribute(name: str, value) -> bytes:
+class VlenStr(str):
+    """an attribute value to be written as a variable-length UTF-8 string (what h5py does for a Python str): global heap + v3 attribute"""
+
+
+def _attribute(name: str, value, writer=None) -> bytes:
+    if isinstance(value, VlenStr):
+        raw = value.encode("utf-8")
+        # global heap collection with one object (index 1) and the free-space object (index 0)
+        obj = struct.pack("<HH4xQ", 1, 1, len(raw)) + _pad8(raw)
+        size = 16 + len(obj) + 16
+        gaddr = writer.alloc(b"GCOL" + struct.pack("<B3xQ", 1, size) + obj + struct.pack("<HH4xQ", 0, 0, 0))
+        nm = name.encode() + b"\x00"
+        dt = struct.pack("<BBBBI", 0x19, 0x01, 0x01, 0, 16) + struct.pack("<BBBBI", 0x13, 0x00, 0, 0, 1)
+        ds = struct.pack("<BBBB", 2, 0, 0, 0)                                  # version 2, rank 0, scalar
+        data = struct.pack("<IQI", len(raw), gaddr, 1)
+        return _message(0x000C, struct.pack("<BBHHHB", 3, 0, len(nm), len(dt), len(ds), 1) + nm + dt + ds + data)
     arr = np.asarray(value)
     if arr.dtype.kind == "U":
         arr = np.char.encode(arr, "utf-8")
@@ -79,7 +94,7 @@ class Writer:
         daddr = self.alloc(arr.tobytes()) if arr.size else UNDEF
         msgs = [_message(0x0001, _dataspace(arr.shape)), _message(0x0003, _datatype(arr.dtype)),
                 _message(0x0008, struct.pack("<BBQQ", 3, 1, daddr, arr.nbytes))]
-        msgs += [_attribute(k, v) for k, v in (attrs or {}).items()]
+        msgs += [_attribute(k, v, self) for k, v in (attrs or {}).items()]
         return self._header(msgs, split)
 
     def group(self, children: Dict[str, int], attrs: Dict[str, object] = None, split: bool = False) -> int:
@@ -105,7 +120,7 @@ class Writer:
             tree += struct.pack("<QQ", addr, last)
         tree += b"\x00" * (16 * (32 - len(snods)))
         tree_addr = self.alloc(tree)
-        msgs = [_message(0x0011, struct.pack("<QQ", tree_addr, heap_addr))] + [_attribute(k, v) for k, v in (attrs or {}).items()]
+        msgs = [_message(0x0011, struct.pack("<QQ", tree_addr, heap_addr))] + [_attribute(k, v, self) for k, v in (attrs or {}).items()]
         return self._header(msgs, split)
 
     def finish(self, root: int) -> bytes:

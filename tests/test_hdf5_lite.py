@@ -56,9 +56,10 @@ def test_writer_reader_round_trip(split, user_block):
     many = {f"d{i:02d}": np.full((2,), i, np.float64) for i in range(21)}     # three symbol-table nodes
     data = h5_writer.write_tree({"g": ({"a": (a, {"note": np.bytes_(b"hello"), "n": np.int32(7)}), "b": b}, {"names": np.array([b"x", b"yy"], "S2")}),
                                  "many": many, "empty": np.zeros((0, 3), np.float32)},
-                                attrs={"top": np.float32(1.5)}, user_block=user_block, split=split)
+                                attrs={"top": np.float32(1.5), "text": h5_writer.VlenStr("vari\u00e9 length")}, user_block=user_block, split=split)
     f = hdf5_lite.File(data)
     assert sorted(f.keys()) == ["empty", "g", "many"] and f.attrs["top"] == np.float32(1.5)
+    assert f.attrs["text"].decode("utf-8") == "vari\u00e9 length"               # variable-length string through the global heap
     np.testing.assert_array_equal(f["g/a"].read(), a)
     np.testing.assert_array_equal(f["g"]["b"].read(), b)
     assert f["g/a"].attrs["note"] == b"hello" and f["g/a"].attrs["n"] == 7

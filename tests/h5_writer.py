@@ -65,6 +65,11 @@ def _attribute(name: str, value, writer=None) -> bytes:
     return _message(0x000C, struct.pack("<BxHHH", 1, len(nm), len(dt), len(ds)) + _pad8(nm) + _pad8(dt) + _pad8(ds) + arr.tobytes())
 
 
+class Chunked:
+    def __init__(self, arr, chunks, deflate=True, shuffle=False):
+        self.arr, self.chunks, self.deflate, self.shuffle = np.asarray(arr), tuple(chunks), deflate, shuffle
+
+
 class Writer:
     def __init__(self, user_block: int = 0):
         self.user_block = user_block
@@ -96,6 +101,40 @@ class Writer:
                 _message(0x0008, struct.pack("<BBQQ", 3, 1, daddr, arr.nbytes))]
         msgs += [_attribute(k, v, self) for k, v in (attrs or {}).items()]
         return self._header(msgs, split)
+
+    def chunked_dataset(self, arr: np.ndarray, chunks, deflate: bool = True, shuffle: bool = False) -> int:
+        """chunked layout (v3 class 2) behind a one-node v1 chunk B-tree; filter pipeline v1: [shuffle,] deflate"""
+        import itertools
+        import zlib
+        arr = np.ascontiguousarray(arr)
+        rank, es = arr.ndim, arr.dtype.itemsize
+        entries = []
+        for idx in itertools.product(*[range(0, s, c) for s, c in zip(arr.shape, chunks)]):
+            chunk = np.zeros(chunks, arr.dtype)
+            sl = tuple(slice(o, min(o + c, s)) for o, c, s in zip(idx, chunks, arr.shape))
+            chunk[tuple(slice(0, x.stop - x.start) for x in sl)] = arr[sl]
+            raw = chunk.tobytes()
+            if shuffle:
+                raw = np.frombuffer(raw, np.uint8).reshape(-1, es).T.tobytes()
+            if deflate:
+                raw = zlib.compress(raw, 4)
+            entries.append((idx, self.alloc(raw), len(raw)))
+        assert len(entries) <= 64
+        node = b"TREE" + struct.pack("<BBHQQ", 1, 0, len(entries), UNDEF, UNDEF)
+        for idx, addr, size in entries:
+            node += struct.pack("<II", size, 0) + b"".join(struct.pack("<Q", o) for o in idx) + struct.pack("<Q", 0) + struct.pack("<Q", addr)
+        node += struct.pack("<II", 0, 0) + b"".join(struct.pack("<Q", s) for s in arr.shape) + struct.pack("<Q", 0)      # final key
+        baddr = self.alloc(node)
+        layout = struct.pack("<BBBQ", 3, 2, rank + 1, baddr) + b"".join(struct.pack("<I", c) for c in chunks) + struct.pack("<I", es)
+        filt = []
+        if shuffle:
+            filt.append(struct.pack("<HHHH", 2, 0, 1, 1) + struct.pack("<I", es) + b"\x00" * 4)
+        if deflate:
+            filt.append(struct.pack("<HHHH", 1, 0, 1, 1) + struct.pack("<I", 4) + b"\x00" * 4)
+        msgs = [_message(0x0001, _dataspace(arr.shape)), _message(0x0003, _datatype(arr.dtype)), _message(0x0008, layout)]
+        if filt:
+            msgs.append(_message(0x000B, struct.pack("<BB6x", 1, len(filt)) + b"".join(filt)))
+        return self._header(msgs, False)
 
     def group(self, children: Dict[str, int], attrs: Dict[str, object] = None, split: bool = False) -> int:
         names = sorted(children, key=lambda s: s.encode())
@@ -134,6 +173,8 @@ class Writer:
 
 def _tree(w: Writer, node, attrs=None, split=False) -> int:
     """node: ndarray (dataset) or {name: node | (node, attrs)}"""
+    if isinstance(node, Chunked):
+        return w.chunked_dataset(node.arr, node.chunks, node.deflate, node.shuffle)
     if isinstance(node, np.ndarray):
         return w.dataset(node, attrs, split)
     children = {}

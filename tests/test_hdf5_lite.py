@@ -70,6 +70,15 @@ def test_writer_reader_round_trip(split, user_block):
     assert f["empty"].read().shape == (0, 3)
 
 
+@pytest.mark.parametrize("deflate,shuffle", [(False, False), (True, False), (True, True)])
+def test_chunked_datasets(deflate, shuffle):
+    # Keras writes contiguous datasets; h5py users who re-save with compression get chunked + shuffle + deflate
+    rng = np.random.default_rng(1)
+    a = rng.standard_normal((10, 7, 3)).astype(np.float32)
+    data = h5_writer.write_tree({"a": h5_writer.Chunked(a, (4, 4, 3), deflate, shuffle)})
+    np.testing.assert_array_equal(hdf5_lite.File(data)["a"].read(), a)
+
+
 def _keras_layers(nested, sub, kind):
     """(class, layer name, [(weight name, array)]) in the order Keras lists the layers of the reference's models, from our flat names"""
     ws = nested[sub]

@@ -231,4 +231,5 @@ def test_full_size_h5_directory_drives_the_codec(tmp_path):
     b = GAN_test.compress_and_reconstruct(img, direct, target_bpp=1.0, mask=mask)
     np.testing.assert_array_equal(a["compressed_img"], b["compressed_img"])
     np.testing.assert_array_equal(a["hq_latent"], b["hq_latent"])
-    assert a["actual_bpp"] == b["actual_bpp"] and a["metrics"]["psnr"] == b["metrics"]["psnr"]
+    assert a["actual_bpp"] == b["actual_bpp"]
+    assert a["metrics"]["psnr"] == pytest.approx(b["metrics"]["psnr"], rel=1e-12)      # the metric sums are atomics: order-dependent last bits

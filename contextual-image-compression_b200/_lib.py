@@ -95,6 +95,9 @@ PROTOTYPES = {
     "cic_rans_workspace_bytes": (_sz, [_i, _i]),
     "cic_rans_encode": (_i, [_vp, _i, _i, _vp, _sz, _vp, _vp, _sz, _vp]),
     "cic_rans_decode": (_i, [_vp, _sz, _vp, _i, _i, _vp]),
+    "cic_jpeg_max_bytes": (_sz, [_i, _i]),
+    "cic_jpeg_workspace_bytes": (_sz, [_i, _i, _i]),
+    "cic_jpeg_encode_u8": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _sz, _vp, _vp, _sz, _vp]),
     "cic_f32_to_u8_trunc": (_i, [_vp, _vp, _sz, _f, _vp]),
     "cic_u8_to_f32_signed": (_i, [_vp, _vp, _sz, _vp]),
     "cic_f32_signed_to_u8": (_i, [_vp, _vp, _sz, _vp]),

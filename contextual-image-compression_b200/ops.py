@@ -250,6 +250,48 @@ def rans_decode(stream: torch.Tensor, rows: int, latent_dim: int) -> torch.Tenso
     return out
 
 
+def jpeg_encode_device(images_u8: torch.Tensor, quality: int = 95, rgb: bool = False, capacity: int = None):
+    """Baseline JPEG files of a uint8 batch (B,H,W,3) on the device -> (out (B, capacity) uint8, sizes (B,) int32), both on the device;
+    file b is out[b, :sizes[b]].  No host synchronisation.  A size above `capacity` means that file was truncated (cic.h)."""
+    x = images_u8
+    if x.dtype != torch.uint8 or not x.is_cuda or x.dim() != 4 or x.shape[3] != 3:
+        raise ValueError(f"jpeg_encode_device: expected a (B,H,W,3) uint8 CUDA tensor, got {tuple(x.shape)} {x.dtype} on {x.device}")
+    x = x.contiguous()
+    b, h, w, _ = x.shape
+    if capacity is None:
+        capacity = int(_lib.lib.cic_jpeg_max_bytes(h, w))
+    out = torch.empty((b, capacity), dtype=torch.uint8, device=x.device)
+    sizes = torch.zeros((b,), dtype=torch.int32, device=x.device)
+    ws = torch.empty(int(_lib.lib.cic_jpeg_workspace_bytes(b, h, w)), dtype=torch.uint8, device=x.device)
+    _lib.check(_lib.lib.cic_jpeg_encode_u8(ptr(x), b, h, w, int(bool(rgb)), int(quality), ptr(out), capacity, ptr(sizes), ptr(ws), ws.numel(),
+                                           runtime.stream_ptr()))
+    return out, sizes
+
+
+def jpeg_encode(images_u8, quality: int = 95, rgb: bool = False):
+    """The bytes cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, quality]) returns (= the file cv2.imwrite writes:
+    test_autoencoder.py:93, GAN_functions.py:50), made on the GPU.  images_u8: (H,W,3) or (B,H,W,3) uint8, BGR like cv2's input
+    (rgb=True: RGB input, i.e. save_image's cvtColor folded in); device tensor or host array.  -> bytes or list of bytes.
+    First tries a 4 bytes / pixel buffer (q95 photographs need ~1), and repeats with the strict worst case if a file did not fit."""
+    x = images_u8 if isinstance(images_u8, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(images_u8))
+    single = x.dim() == 3
+    if single:
+        x = x[None]
+    x = x.to(runtime.require_cuda())
+    b, h, w, _ = x.shape
+    worst = int(_lib.lib.cic_jpeg_max_bytes(h, w))
+    cap = min(worst, 1024 + 4 * ((h + 15) // 16) * ((w + 15) // 16) * 256)
+    out, sizes = jpeg_encode_device(x, quality, rgb, cap)
+    n = sizes.cpu().numpy()
+    if int(n.max()) > cap:
+        out, sizes = jpeg_encode_device(x, quality, rgb, worst)
+        n = sizes.cpu().numpy()
+    top = int(n.max())
+    host = out[:, :top].cpu().numpy()
+    files = [host[i, : int(n[i])].tobytes() for i in range(b)]
+    return files[0] if single else files
+
+
 def f32_to_u8_trunc(x, mul: float = 255.0) -> torch.Tensor:
     x = to_device_f32(x)
     y = torch.empty(x.shape, dtype=torch.uint8, device=x.device)

@@ -35,12 +35,35 @@ def load_and_preprocess_image(image_path, target_size=(256, 256)):
 
 
 def save_image(img, path):
-    """GAN_functions.py:41-50: ((img+1)*127.5).astype(uint8) (truncation), RGB -> BGR, imwrite."""
-    import cv2
+    """GAN_functions.py:41-50: ((img+1)*127.5).astype(uint8) (truncation), RGB -> BGR, imwrite.  A 3-channel image saved as
+    .jpg / .jpeg is encoded on the GPU (ops.jpeg_encode: the same bytes cv2.imwrite produces, with the RGB -> BGR swap folded into
+    the kernel); other formats and grey images go through OpenCV."""
     out = ((np.asarray(img) + 1) * 127.5).astype(np.uint8)
+    if out.ndim == 3 and out.shape[2] == 3 and os.path.splitext(path)[1].lower() in (".jpg", ".jpeg", ".jpe"):
+        from . import ops
+        with open(path, "wb") as f:
+            f.write(ops.jpeg_encode(out, rgb=True))
+        return
+    import cv2
     if out.ndim == 3 and out.shape[2] == 3:
         out = cv2.cvtColor(out, cv2.COLOR_RGB2BGR)
     cv2.imwrite(path, out)
+
+
+def save_images_u8(images_u8, paths, rgb=True, quality=95):
+    """Batch form of save_image for images that are already uint8 on the device (predict_phased / predict_stream with u8_io=True
+    give ((x + 1) * 127.5).astype(uint8) RGB): one encoder call, only the compressed bytes cross PCIe.  .jpg paths only."""
+    from . import ops
+    files = ops.jpeg_encode(images_u8, quality=quality, rgb=rgb)
+    if isinstance(files, bytes):
+        files = [files]
+    if len(files) != len(paths):
+        raise ValueError(f"{len(files)} images for {len(paths)} paths")
+    for data, path in zip(files, paths):
+        if os.path.splitext(path)[1].lower() not in (".jpg", ".jpeg", ".jpe"):
+            raise ValueError(f"save_images_u8 writes JPEG files, got '{path}'")
+        with open(path, "wb") as f:
+            f.write(data)
 
 
 def _saliency_module():

@@ -271,6 +271,18 @@ int cic_rans_encode(const int32_t* d_symbols, int rows, int latent_dim, uint8_t*
                     unsigned long long* d_nbytes, void* d_workspace, size_t workspace_bytes, void* stream);
 int cic_rans_decode(const uint8_t* d_stream, size_t nbytes, int32_t* d_symbols, int rows, int latent_dim, void* stream);
 
+/* Output stage: the file cv2.imwrite("*.jpg", img) writes (test_autoencoder.py:88-93; GAN_functions.py:41-50 save_image, called at
+ * GAN_test.py:390), produced on the device - baseline JPEG, 4:2:0, Annex K Huffman tables, JFIF 1.01 header, libjpeg's integer
+ * arithmetic throughout, so the bytes equal OpenCV's (cv2.imencode is the tests' oracle).  d_img (batch, h, w, 3) uint8, channel
+ * order BGR like cv2.imwrite's input (rgb = 0) or RGB (rgb = 1: save_image's cvtColor folded in); quality as IMWRITE_JPEG_QUALITY
+ * (OpenCV's default is 95).  File b starts at d_out + b * capacity and is d_sizes[b] bytes long; cic_jpeg_max_bytes is the strict
+ * worst case, a smaller capacity is allowed: bytes beyond it are dropped and d_sizes[b] still holds the size the file needs.
+ * d_workspace 256-byte aligned. */
+size_t cic_jpeg_max_bytes(int h, int w);
+size_t cic_jpeg_workspace_bytes(int batch, int h, int w);
+int cic_jpeg_encode_u8(const uint8_t* d_img, int batch, int h, int w, int rgb, int quality, uint8_t* d_out, size_t capacity,
+                       int32_t* d_sizes, void* d_workspace, size_t workspace_bytes, void* stream);
+
 /* (y*255).astype(uint8) - truncation toward zero (test_autoencoder.py:88,96). */
 int cic_f32_to_u8_trunc(const float* d_x, uint8_t* d_y, size_t n, float mul, void* stream);
 

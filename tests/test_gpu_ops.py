@@ -368,3 +368,65 @@ def test_saliency_mask_smooth_matches_opencv(cic, b, h, w):
     np.testing.assert_allclose(cic.ops.saliency_mask_smooth(flat).cpu().numpy(), 1.0, atol=1e-6)
     zero = np.zeros((40, 40), np.float32)                                       # max == 0: left as is (GAN_functions.py:202)
     assert cic.ops.saliency_mask_smooth(zero).abs().max().item() == 0.0
+
+
+def _jpeg_image(h, w, kind, seed):
+    from test_oracle_extras import _jpeg_test_image
+    return _jpeg_test_image(h, w, kind, seed)
+
+
+@pytest.mark.parametrize("h,w", [(16, 16), (64, 64), (100, 150), (17, 33), (8, 8), (1, 1), (120, 68), (256, 256), (512, 512)])
+def test_jpeg_encoder_is_byte_identical_to_opencv(cic, h, w):
+    """cic_jpeg_encode_u8 (the output stage) against the REAL library behind the reference's cv2.imwrite
+    (test_autoencoder.py:93; GAN_functions.py:50): the files are equal byte for byte - and equal to the numpy restatement."""
+    import cv2
+    from oracle import jpeg
+    imgs = np.stack([_jpeg_image(h, w, kind, h * 1000 + w + i) for i, kind in enumerate(("noise", "smooth", "flat", "saturated", "smooth"))])
+    files = cic.ops.jpeg_encode(imgs)
+    assert len(files) == len(imgs)
+    for i, f in enumerate(files):
+        want = bytes(cv2.imencode(".jpg", imgs[i])[1])
+        assert f[:jpeg.HEADER_BYTES] == want[:jpeg.HEADER_BYTES], "header"
+        assert len(f) == len(want), (i, len(f), len(want))
+        assert f == want, f"image {i}: first difference at byte {next(k for k in range(len(f)) if f[k] != want[k])} of {len(f)}"
+    assert files[1] == jpeg.encode_bgr(imgs[1])
+    for q in (100, 50, 10):
+        assert cic.ops.jpeg_encode(imgs[1], quality=q) == bytes(cv2.imencode(".jpg", imgs[1], [cv2.IMWRITE_JPEG_QUALITY, q])[1]), q
+    # RGB input = save_image's cv2.cvtColor(img, cv2.COLOR_RGB2BGR) folded into the kernel
+    assert cic.ops.jpeg_encode(imgs[1][..., ::-1].copy(), rgb=True) == files[1]
+
+
+def test_jpeg_encoder_frames_and_capacity(cic):
+    import cv2
+    frame = _jpeg_image(1080, 1920, "smooth", 3)                                 # H is not a multiple of 16: dummy block row
+    f = cic.ops.jpeg_encode(torch.from_numpy(frame).cuda())
+    assert f == bytes(cv2.imencode(".jpg", frame)[1])
+    back = cv2.imdecode(np.frombuffer(f, np.uint8), cv2.IMREAD_COLOR)
+    assert back.shape == frame.shape
+    # a buffer that is too small: the size is still reported, nothing is written beyond the capacity
+    x = torch.from_numpy(np.stack([_jpeg_image(64, 64, "noise", 1)] * 2)).cuda()
+    full, sizes = cic.ops.jpeg_encode_device(x)
+    need = int(sizes[0].item())
+    out, sizes2 = cic.ops.jpeg_encode_device(x, capacity=1000)
+    assert out.shape == (2, 1000) and int(sizes2[0].item()) == need > 1000
+    assert torch.equal(out[0], full[0, :1000]) and torch.equal(out[1], full[1, :1000])
+    with pytest.raises(ValueError):
+        cic.ops.jpeg_encode_device(x.float())
+    empty, s0 = cic.ops.jpeg_encode_device(x[:0])
+    assert empty.shape[0] == 0 and s0.numel() == 0
+
+
+def test_save_image_writes_opencv_bytes_from_the_gpu(cic, tmp_path):
+    """GAN_functions.save_image(img, path) (:41-50): [-1,1] RGB float -> truncated uint8 -> BGR -> cv2.imwrite.  For .jpg paths the file
+    is made on the GPU and equals the one OpenCV writes."""
+    import cv2
+    import GAN_functions as gf
+    img = _jpeg_image(96, 80, "smooth", 4).astype(np.float32) / 127.5 - 1.0
+    p = str(tmp_path / "a.jpg")
+    gf.save_image(img, p)
+    u8 = cv2.cvtColor(((img + 1) * 127.5).astype(np.uint8), cv2.COLOR_RGB2BGR)
+    q = str(tmp_path / "b.jpg")
+    cv2.imwrite(q, u8)
+    assert open(p, "rb").read() == open(q, "rb").read()
+    gf.save_image(img, str(tmp_path / "c.png"))                                  # other formats stay on OpenCV
+    np.testing.assert_array_equal(cv2.imread(str(tmp_path / "c.png")), u8)

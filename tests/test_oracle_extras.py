@@ -91,3 +91,42 @@ def test_hq_ratio_of_the_unpadded_image_matches_appendix_c():
     mask = np.full((1, 10, 20, 1), 0.75, np.float32)
     for bpp, want in ((0.1, 0.212834), (1.0, 0.852215), (2.0, 0.994246)):
         assert tiling.hq_ratio(mask, np.array([bpp]))[0] == pytest.approx(want, abs=2e-6)
+
+
+def _jpeg_test_image(h, w, kind, seed):
+    import cv2
+    rng = np.random.default_rng(seed)
+    if kind == "noise":
+        return (rng.random((h, w, 3)) * 255).astype(np.uint8)
+    if kind == "flat":
+        return np.full((h, w, 3), (7, 250, 128), np.uint8)
+    if kind == "saturated":                                  # long runs of 0 / 255: exercises 0xFF stuffing and ZRL
+        return (((np.indices((h, w)).sum(0) // 3) % 2) * 255).astype(np.uint8)[..., None].repeat(3, axis=2)
+    base = rng.random((h // 8 + 2, w // 8 + 2, 3)).astype(np.float32)
+    img = cv2.resize(base, (w, h), interpolation=cv2.INTER_CUBIC) + 0.03 * rng.standard_normal((h, w, 3))
+    return np.clip(img * 255, 0, 255).astype(np.uint8)
+
+
+@pytest.mark.parametrize("h,w", [(16, 16), (64, 64), (48, 80), (100, 150), (17, 33), (8, 8), (1, 1), (120, 68), (99, 151), (128, 128)])
+def test_jpeg_restatement_is_byte_identical_to_opencv(h, w):
+    """oracle/jpeg.py against the real library behind the reference's cv2.imwrite (test_autoencoder.py:93, GAN_functions.py:50)."""
+    cv2 = pytest.importorskip("cv2")
+    from oracle import jpeg
+    for kind in ("noise", "smooth", "flat", "saturated"):
+        img = _jpeg_test_image(h, w, kind, h * 1000 + w)
+        assert jpeg.encode_bgr(img) == bytes(cv2.imencode(".jpg", img)[1]), (kind, "default quality")
+    img = _jpeg_test_image(h, w, "smooth", 5)
+    for q in (100, 75, 50, 10):
+        assert jpeg.encode_bgr(img, q) == bytes(cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, q])[1]), q
+
+
+def test_jpeg_restatement_decodes():
+    cv2 = pytest.importorskip("cv2")
+    from oracle import jpeg
+    img = _jpeg_test_image(96, 112, "smooth", 9)
+    back = cv2.imdecode(np.frombuffer(jpeg.encode_bgr(img), np.uint8), cv2.IMREAD_COLOR)
+    assert back.shape == img.shape
+    mse = np.mean((back.astype(np.float64) - img) ** 2)
+    assert 10 * np.log10(255 ** 2 / mse) > 28            # q95 with 4:2:0 chroma on an image carrying 3 % noise
+    with pytest.raises(ValueError):
+        jpeg.encode_bgr(img[..., 0])

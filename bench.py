@@ -574,6 +574,7 @@ class Bench:
                 "bpp_nominal_reference_accounting": quality["actual_bpp"],
                 "note": "cic_rans_encode: static model per call, 32 interleaved rANS states per tile row; bpp_both_streams counts the HQ and the LQ "
                         "latent of every tile (the soft ROI blend needs both everywhere) over the unpadded pixels"}
+            quality["output_stage"] = self.jpeg_stage(out["blended"], k, h, w)
             if name == "c5":                                                      # BASELINE configs[4]: "PSNR/MS-SSIM per image" (MS-SSIM: unpinned extra)
                 quality["per_image_ms_ssim"] = [float(v) for v in cic.ops.ms_ssim_f32(d_img[:k], out["blended"], signed_range=True).cpu().numpy()]
             n_or = args.cpu_tiles if headline else min(args.cpu_tiles, 4)
@@ -616,6 +617,38 @@ class Bench:
                     f.write(f"{lname},{ms:.4f},{fl:.4e},{by:.4e},{(fl / ms / 1e9) if ms > 0 else 0:.2f},{(by / ms / 1e6) if ms > 0 else 0:.1f},"
                             f"{KINDS.get(kind, 'other')}\n")
         return line
+
+    def jpeg_stage(self, blended, k, h, w):
+        """The reference's output stage (GAN_functions.py:41-50 save_image -> cv2.imwrite("*.jpg"), called per image at GAN_test.py:390) on
+        the device: the k reconstructions of the parity block -> uint8 -> JPEG files; compared byte for byte with OpenCV's own encoder
+        (the real library) when cv2 is importable.  Outside every timed region; device time by CUDA events."""
+        torch, cic = self.torch, self.cic
+        u8 = cic.ops.f32_signed_to_u8(blended)
+        cap = 1024 + 4 * ((h + 15) // 16) * ((w + 15) // 16) * 256
+        cic.ops.jpeg_encode_device(u8, rgb=True, capacity=cap)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        torch.cuda.synchronize()
+        ev[0].record()
+        for _ in range(5):
+            files_dev, sizes = cic.ops.jpeg_encode_device(u8, rgb=True, capacity=cap)
+        ev[1].record()
+        torch.cuda.synchronize()
+        ms = ev[0].elapsed_time(ev[1]) / 5
+        self.launches += 8 * 6
+        files = cic.ops.jpeg_encode(u8, rgb=True)
+        rep = {"images": k, "format": "baseline JPEG, quality 95, 4:2:0 (cv2.imwrite defaults)", "bytes_per_image": float(np.mean([len(f) for f in files])),
+               "bpp_of_the_files": 8.0 * sum(len(f) for f in files) / (k * h * w), "encode_ms": ms, "encode_mpix_s": k * h * w / ms / 1e3,
+               "d2h_bytes_vs_uint8_pixels": sum(len(f) for f in files) / (k * h * w * 3.0)}
+        try:
+            import cv2
+            host = u8.cpu().numpy()
+            t0 = time.perf_counter()
+            want = [bytes(cv2.imencode(".jpg", cv2.cvtColor(host[i], cv2.COLOR_RGB2BGR))[1]) for i in range(k)]
+            rep["opencv_one_core_mpix_s"] = k * h * w / (time.perf_counter() - t0) / 1e6
+            rep["byte_identical_to_opencv"] = bool(all(a == b for a, b in zip(files, want)))
+        except ImportError:
+            rep["byte_identical_to_opencv"] = None
+        return rep
 
     def hbm_kernels(self, prof, am, d_img, d_mask, d_bpp):
         """Algorithmic bytes / device time of the bandwidth kernels against the measured HBM peak."""

@@ -292,6 +292,14 @@ def jpeg_encode(images_u8, quality: int = 95, rgb: bool = False):
     return files[0] if single else files
 
 
+def f32_signed_to_u8(x) -> torch.Tensor:
+    """((x + 1) * 127.5).astype(uint8) on the device (GAN_functions.py:44, save_image's first line)."""
+    x = to_device_f32(x)
+    y = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    _lib.check(_lib.lib.cic_f32_signed_to_u8(ptr(x), ptr(y), x.numel(), runtime.stream_ptr()))
+    return y
+
+
 def f32_to_u8_trunc(x, mul: float = 255.0) -> torch.Tensor:
     x = to_device_f32(x)
     y = torch.empty(x.shape, dtype=torch.uint8, device=x.device)

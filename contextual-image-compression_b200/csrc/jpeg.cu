@@ -18,11 +18,12 @@
 // Kernels (all HBM-bound integer / byte work, no tensor cores):
 //   jpeg_dct_kernel      one CTA per 8 MCUs of a row: BGR bytes -> Y/Cb/Cr in shared memory -> 48 blocks, row pass and column pass as
 //                        384 one-dimensional DCTs each -> quantise, zig-zag, dummy rule -> int16 coefficients, coalesced
-//   jpeg_len_kernel      one thread per block: bit length of its Huffman code
+//   jpeg_len_kernel      one thread per block (the CTA's 128 blocks staged in shared memory with coalesced loads): bit length of its code
 //   jpeg_scan_kernel     per-image exclusive scan (one CTA per image) -> bit offset of every block; zeroes the words two pack CTAs share
 //   jpeg_pack_kernel     one CTA per 128 blocks: every thread ORs its code words into the CTA's span in shared memory, the span goes
 //                        to HBM with coalesced word stores (the two boundary words by atomicOr)
-//   jpeg_ffcount_kernel / jpeg_scan_kernel / jpeg_stuff_kernel   0xFF stuffing: count per 32-byte chunk, scan, scatter behind the header
+//   jpeg_ffcount_kernel / jpeg_scan_kernel / jpeg_stuff_kernel   0xFF stuffing: count per 32-byte chunk, scan, then every CTA
+//                        assembles its 8 KB of the file in shared memory and stores whole words behind the header
 #include "common.cuh"
 
 #include <initializer_list>
@@ -78,7 +79,7 @@ __device__ __forceinline__ void dct8(int* d) {
 
 template <bool RGB>
 __global__ void __launch_bounds__(256)
-jpeg_dct_kernel(const uint8_t* __restrict__ img, int16_t* __restrict__ coef, int H, int W, int mw, int mh, JpegQuant qt) {
+jpeg_dct_kernel(const uint8_t* __restrict__ img, int16_t* __restrict__ coef, int H, int W, int mw, int mh, int words_ok, JpegQuant qt) {
   __shared__ uint8_t sY[16][128], sCb[16][128], sCr[16][128];
   __shared__ int s[48][72];
   __shared__ uint32_t recip[2][64];
@@ -93,15 +94,34 @@ jpeg_dct_kernel(const uint8_t* __restrict__ img, int16_t* __restrict__ coef, int
   }
   if (tid < 64) zz[tid] = c_zigzag[tid];
   const uint8_t* src = img + (size_t)b * H * W * 3;
-  for (int i = tid; i < 16 * 128; i += 256) {
-    const int ly = i >> 7, lx = i & 127;
-    const int y = min(my * 16 + ly, H - 1), x = min(mx0 * 16 + lx, W - 1);
-    const uint8_t* p = src + ((size_t)y * W + x) * 3;
-    const int c0 = __ldg(p), c1 = __ldg(p + 1), c2 = __ldg(p + 2);
+  auto convert = [&](int ly, int lx, int c0, int c1, int c2) {
     const int r = RGB ? c0 : c2, g = c1, bl = RGB ? c2 : c0;
     sY[ly][lx] = (uint8_t)((19595 * r + 38470 * g + 7471 * bl + 32768) >> 16);
     sCb[ly][lx] = (uint8_t)((-11059 * r - 21709 * g + 32768 * bl + (128 << 16) + 32767) >> 16);
     sCr[ly][lx] = (uint8_t)((32768 * r - 27439 * g - 5329 * bl + (128 << 16) + 32767) >> 16);
+  };
+  if (words_ok && mx0 * 16 + 128 <= W) {
+    // the CTA's 128-pixel row segments are whole, 4-byte aligned runs of 96 words: stage the raw bytes with word loads
+    uint32_t* sraw = reinterpret_cast<uint32_t*>(&s[0][0]);       // 16 x 96 words, reused by the DCT afterwards
+    for (int i = tid; i < 16 * 96; i += 256) {
+      const int ly = i / 96, wx = i - ly * 96;
+      const int y = min(my * 16 + ly, H - 1);
+      sraw[i] = __ldg(reinterpret_cast<const uint32_t*>(src + ((size_t)y * W + mx0 * 16) * 3) + wx);
+    }
+    __syncthreads();
+    const uint8_t* sb = reinterpret_cast<const uint8_t*>(sraw);
+    for (int i = tid; i < 16 * 128; i += 256) {
+      const int ly = i >> 7, lx = i & 127;
+      const uint8_t* p = sb + ly * 384 + lx * 3;
+      convert(ly, lx, p[0], p[1], p[2]);
+    }
+  } else {
+    for (int i = tid; i < 16 * 128; i += 256) {
+      const int ly = i >> 7, lx = i & 127;
+      const int y = min(my * 16 + ly, H - 1), x = min(mx0 * 16 + lx, W - 1);
+      const uint8_t* p = src + ((size_t)y * W + x) * 3;
+      convert(ly, lx, __ldg(p), __ldg(p + 1), __ldg(p + 2));
+    }
   }
   __syncthreads();
   for (int i = tid; i < 8 * 4 * 64; i += 256) {
@@ -141,23 +161,32 @@ jpeg_dct_kernel(const uint8_t* __restrict__ img, int16_t* __restrict__ coef, int
   const bool bottom = (((H + 7) >> 3) & 1) && my == mh - 1;       // the MCU row's second Y block row does not exist
   const bool right_odd = ((W + 7) >> 3) & 1;
   int16_t* dst = coef + (((size_t)b * mh * mw + (size_t)my * mw + mx0) * 6) * 64;
-  for (int i = tid; i < nm * 6 * 64; i += 256) {
-    const int blk = i >> 6, k = i & 63, m = blk / 6, j = blk - m * 6;
-    const bool right = right_odd && (mx0 + m == mw - 1);          // the MCU's second Y block column does not exist
-    int srcj = j;
-    bool dummy = false;
-    if (j < 4) {
+  // thread = one zig-zag position k of every fourth block: the table entries are loaded once
+  const int k = tid & 63, nat_k = zz[k], pos_k = (nat_k >> 3) * 9 + (nat_k & 7);
+  const uint32_t rq[2] = {recip[0][nat_k], recip[1][nat_k]}, hq[2] = {(uint32_t)sq[0][nat_k] >> 1, (uint32_t)sq[1][nat_k] >> 1};
+  const uint32_t rq0[2] = {recip[0][0], recip[1][0]}, hq0[2] = {(uint32_t)sq[0][0] >> 1, (uint32_t)sq[1][0] >> 1};
+  for (int blk = tid >> 6; blk < nm * 6; blk += 4) {
+    const int m = blk / 6, j = blk - m * 6, t = j < 4 ? 0 : 1;
+    int v = s[blk][pos_k];
+    uint32_t r = rq[t], h = hq[t];
+    bool zero = false;
+    if ((bottom || right_odd) && j < 4) {                         // dummy blocks (jccoefct.c): AC = 0, DC = DC of the previous block
+      const bool right = right_odd && (mx0 + m == mw - 1);
+      int srcj = j;
+      bool dummy = false;
       if (bottom && j >= 2) { srcj = 1; dummy = true; }
       else if (right && (j & 1)) { srcj = j - 1; dummy = true; }
       if (srcj == 1 && right) srcj = 0;
+      if (dummy) {
+        v = s[m * 6 + srcj][0];
+        r = rq0[0];
+        h = hq0[0];
+        zero = k > 0;
+      }
     }
-    const int t = j < 4 ? 0 : 1, nat = dummy ? 0 : zz[k];
-    const int v = s[m * 6 + srcj][(nat >> 3) * 9 + (nat & 7)];
-    const uint32_t a = (uint32_t)abs(v) + (sq[t][nat] >> 1);
-    int qv = (int)__umulhi(a, recip[t][nat]);
+    int qv = (int)__umulhi((uint32_t)abs(v) + h, r);
     qv = v < 0 ? -qv : qv;
-    if (dummy && k > 0) qv = 0;
-    dst[i] = (int16_t)qv;
+    dst[blk * 64 + k] = (int16_t)(zero ? 0 : qv);
   }
 }
 
@@ -173,44 +202,50 @@ __device__ __forceinline__ int dc_pred(const int16_t* __restrict__ coef_img, int
   return coef_img[(size_t)prev * 64];
 }
 
-__device__ __forceinline__ void load_block(const int16_t* __restrict__ p, int* c) {
-  const uint4* q = reinterpret_cast<const uint4*>(p);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const uint4 v = __ldg(q + i);
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      c[i * 8 + 2 * k] = (int)(int16_t)(w[k] & 0xFFFFu);
-      c[i * 8 + 2 * k + 1] = (int)(int16_t)(w[k] >> 16);
-    }
+constexpr int JPEG_CSTRIDE = 33;   // words per staged block (32 + 1: thread t reads word t * 33 + i without bank conflicts)
+
+// the coefficients of JPEG_PACK_N consecutive blocks -> shared memory with coalesced 16-byte loads
+__device__ __forceinline__ void stage_blocks(const int16_t* __restrict__ coef_img, int blk0, int nblk, uint32_t* sc) {
+  const uint4* src = reinterpret_cast<const uint4*>(coef_img + (size_t)blk0 * 64);
+  const int n4 = min(JPEG_PACK_N, nblk - blk0) * 8;
+  for (int i = threadIdx.x; i < n4; i += JPEG_PACK_N) {
+    const uint4 v = __ldg(src + i);
+    uint32_t* d = sc + (i >> 3) * JPEG_CSTRIDE + (i & 7) * 4;
+    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
   }
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(JPEG_PACK_N)
 jpeg_len_kernel(const int16_t* __restrict__ coef, uint32_t* __restrict__ len, int nblk, JpegTables tab) {
+  __shared__ uint32_t sc[JPEG_PACK_N * JPEG_CSTRIDE];
   __shared__ uint8_t lac[2][256], ldc[2][16];
-  for (int i = threadIdx.x; i < 512; i += 128) lac[i >> 8][i & 255] = (uint8_t)(tab.ac[i >> 8][i & 255] & 31);
-  if (threadIdx.x < 32) ldc[threadIdx.x >> 4][threadIdx.x & 15] = (uint8_t)(tab.dc[threadIdx.x >> 4][threadIdx.x & 15] & 31);
-  __syncthreads();
-  const int blk = blockIdx.x * 128 + threadIdx.x, b = blockIdx.y;
-  if (blk >= nblk) return;
+  const int tid = threadIdx.x, blk0 = blockIdx.x * JPEG_PACK_N, blk = blk0 + tid, b = blockIdx.y;
+  for (int i = tid; i < 512; i += JPEG_PACK_N) lac[i >> 8][i & 255] = (uint8_t)(tab.ac[i >> 8][i & 255] & 31);
+  if (tid < 32) ldc[tid >> 4][tid & 15] = (uint8_t)(tab.dc[tid >> 4][tid & 15] & 31);
   const int16_t* coef_img = coef + (size_t)b * nblk * 64;
-  int c[64];
-  load_block(coef_img + (size_t)blk * 64, c);
+  stage_blocks(coef_img, blk0, nblk, sc);
+  __syncthreads();
+  if (blk >= nblk) return;
+  const uint32_t* mine = sc + tid * JPEG_CSTRIDE;
   const int t = (blk % 6) < 4 ? 0 : 1;
-  const int diff = c[0] - dc_pred(coef_img, blk);
+  uint32_t w = mine[0];
+  const int diff = (int)(int16_t)(w & 0xFFFFu) - dc_pred(coef_img, blk);
   int n = nbits_of(diff);
   uint32_t bits = ldc[t][n] + n;
   int run = 0;
-#pragma unroll
-  for (int k = 1; k < 64; ++k) {
-    const int v = c[k];
-    if (v == 0) { ++run; continue; }
+  auto ac = [&](int v) {
+    if (v == 0) { ++run; return; }
     bits += (run >> 4) * lac[t][0xF0];
-    n = nbits_of(v);
-    bits += lac[t][((run & 15) << 4) | n] + n;
+    const int nb = nbits_of(v);
+    bits += lac[t][((run & 15) << 4) | nb] + nb;
     run = 0;
+  };
+  ac((int)(int16_t)(w >> 16));
+#pragma unroll 4
+  for (int i = 1; i < 32; ++i) {
+    w = mine[i];
+    ac((int)(int16_t)(w & 0xFFFFu));
+    ac((int)(int16_t)(w >> 16));
   }
   if (run) bits += lac[t][0];
   len[(size_t)b * nblk + blk] = bits;
@@ -280,75 +315,96 @@ jpeg_scan_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, ui
   }
 }
 
+constexpr int JPEG_SPAN_WORDS = 2048;   // shared-memory span of one pack CTA (64 bytes per block; q95 photographs need ~30)
+
 __global__ void __launch_bounds__(JPEG_PACK_N)
 jpeg_pack_kernel(const int16_t* __restrict__ coef, const uint32_t* __restrict__ off, const uint32_t* __restrict__ total,
                  uint32_t* __restrict__ raw, size_t raw_words_per_image, int nblk, JpegTables tab) {
-  extern __shared__ uint32_t span[];                               // JPEG_PACK_N * 52 words + 2
+  __shared__ uint32_t sc[JPEG_PACK_N * JPEG_CSTRIDE];
+  __shared__ uint32_t span[JPEG_SPAN_WORDS];
   __shared__ uint32_t tac[2][256], tdc[2][16];
   const int tid = threadIdx.x, b = blockIdx.y, blk0 = blockIdx.x * JPEG_PACK_N, blk = blk0 + tid;
   for (int i = tid; i < 512; i += JPEG_PACK_N) tac[i >> 8][i & 255] = tab.ac[i >> 8][i & 255];
   if (tid < 32) tdc[tid >> 4][tid & 15] = tab.dc[tid >> 4][tid & 15];
+  const int16_t* coef_img = coef + (size_t)b * nblk * 64;
+  stage_blocks(coef_img, blk0, nblk, sc);
   const uint32_t* off_img = off + (size_t)b * nblk;
   const uint32_t begin = off_img[blk0];
   const int blk_end = min(blk0 + JPEG_PACK_N, nblk);
   const uint32_t end = blk_end < nblk ? off_img[blk_end] : total[b];
   const uint32_t w0 = begin >> 5;
   const uint32_t nwords = end > begin ? ((end - 1) >> 5) - w0 + 1 : 0;
-  for (uint32_t i = tid; i < nwords; i += JPEG_PACK_N) span[i] = 0u;
+  // The CTA's bits form one contiguous span of the raw stream.  A word the span shares with a neighbouring CTA (the span starts or
+  // ends inside it) was zeroed by the scan kernel and is merged with atomicOr; every other word belongs to this CTA alone.
+  // Usual case: the span is assembled in shared memory and stored with coalesced word stores.  A span too long for it (noise at
+  // quality 100) is assembled in place: the CTA zeroes its own words, then every thread ORs straight into HBM.
+  const bool in_smem = nwords <= JPEG_SPAN_WORDS;
+  uint32_t* dst = raw + (size_t)b * raw_words_per_image + w0;
+  auto shared_word = [&](uint32_t i) { return (i == 0 && (begin & 31)) || (i == nwords - 1 && (end & 31)); };
+  if (in_smem) {
+    for (uint32_t i = tid; i < nwords; i += JPEG_PACK_N) span[i] = 0u;
+  } else {
+    for (uint32_t i = tid; i < nwords; i += JPEG_PACK_N)
+      if (!shared_word(i)) dst[i] = 0u;
+  }
   __syncthreads();
   if (blk < nblk) {
-    const int16_t* coef_img = coef + (size_t)b * nblk * 64;
-    int c[64];
-    load_block(coef_img + (size_t)blk * 64, c);
+    const uint32_t* mine = sc + tid * JPEG_CSTRIDE;
     const int t = (blk % 6) < 4 ? 0 : 1;
     const uint32_t start = off_img[blk];
-    uint32_t w = (start >> 5) - w0;
+    uint32_t* target = (in_smem ? span : dst) + ((start >> 5) - w0);
     int nacc = (int)(start & 31);
     unsigned long long acc = 0;
+    auto flush = [&](uint32_t word) {
+      atomicOr(target++, in_smem ? word : __byte_perm(word, 0, 0x0123));
+    };
     auto emit = [&](uint32_t code, int length) {
       acc = (acc << length) | code;
       nacc += length;
       if (nacc >= 32) {
         nacc -= 32;
-        atomicOr(&span[w++], (uint32_t)(acc >> nacc));
+        flush((uint32_t)(acc >> nacc));
         acc &= (1ull << nacc) - 1;
       }
     };
-    const int diff = c[0] - dc_pred(coef_img, blk);
+    uint32_t w = mine[0];
+    const int diff = (int)(int16_t)(w & 0xFFFFu) - dc_pred(coef_img, blk);
     int n = nbits_of(diff);
     uint32_t e = tdc[t][n];
     emit(e >> 5, (int)(e & 31));
     if (n) emit((uint32_t)(diff < 0 ? diff - 1 : diff) & ((1u << n) - 1), n);
     int run = 0;
-#pragma unroll
-    for (int k = 1; k < 64; ++k) {
-      const int v = c[k];
-      if (v == 0) { ++run; continue; }
+    auto ac = [&](int v) {
+      if (v == 0) { ++run; return; }
       while (run > 15) {
-        e = tac[t][0xF0];
-        emit(e >> 5, (int)(e & 31));
+        const uint32_t z = tac[t][0xF0];
+        emit(z >> 5, (int)(z & 31));
         run -= 16;
       }
-      n = nbits_of(v);
-      e = tac[t][(run << 4) | n];
-      emit(e >> 5, (int)(e & 31));
-      emit((uint32_t)(v < 0 ? v - 1 : v) & ((1u << n) - 1), n);
+      const int nb = nbits_of(v);
+      const uint32_t c = tac[t][(run << 4) | nb];
+      emit(c >> 5, (int)(c & 31));
+      emit((uint32_t)(v < 0 ? v - 1 : v) & ((1u << nb) - 1), nb);
       run = 0;
+    };
+    ac((int)(int16_t)(w >> 16));
+#pragma unroll 4
+    for (int i = 1; i < 32; ++i) {
+      w = mine[i];
+      ac((int)(int16_t)(w & 0xFFFFu));
+      ac((int)(int16_t)(w >> 16));
     }
     if (run) {
       e = tac[t][0];
       emit(e >> 5, (int)(e & 31));
     }
-    if (nacc) atomicOr(&span[w], (uint32_t)(acc << (32 - nacc)));
+    if (nacc) flush((uint32_t)(acc << (32 - nacc)));
   }
+  if (!in_smem) return;
   __syncthreads();
-  // the span's words in stream byte order; a word shared with the neighbouring CTA (span starts / ends inside it) was zeroed by the
-  // scan kernel and is merged atomically, every other word is this CTA's alone
-  uint32_t* dst = raw + (size_t)b * raw_words_per_image + w0;
   for (uint32_t i = tid; i < nwords; i += JPEG_PACK_N) {
-    const uint32_t v = __byte_perm(span[i], 0, 0x0123);
-    const bool shared_word = (i == 0 && (begin & 31)) || (i == nwords - 1 && (end & 31));
-    if (shared_word) atomicOr(dst + i, v);
+    const uint32_t v = __byte_perm(span[i], 0, 0x0123);           // stream byte order
+    if (shared_word(i)) atomicOr(dst + i, v);
     else dst[i] = v;
   }
 }
@@ -391,29 +447,49 @@ __global__ void __launch_bounds__(256)
 jpeg_stuff_kernel(const uint32_t* __restrict__ raw, size_t raw_words_per_image, const uint32_t* __restrict__ bits_total,
                   const uint32_t* __restrict__ ffoff, const uint32_t* __restrict__ fftotal, size_t max_chunks, uint8_t* __restrict__ out,
                   size_t capacity, int32_t* __restrict__ sizes) {
-  const int chunk = blockIdx.x * 256 + threadIdx.x, b = blockIdx.y;
+  // 256 chunks of 32 raw bytes -> at most 16 KB of stuffed output, contiguous in the file: assembled in shared memory at the file's
+  // own 4-byte alignment, then stored as whole words (single bytes only at the two ends, which other CTAs share)
+  __shared__ __align__(16) uint8_t sb[256 * 2 * JPEG_CHUNK + 16];
+  __shared__ uint32_t s_end;
+  const int tid = threadIdx.x, chunk0 = blockIdx.x * 256, chunk = chunk0 + tid, b = blockIdx.y;
   const uint32_t bits = bits_total[b];
   const uint32_t nbytes = (bits + 7) >> 3;
-  if ((size_t)chunk * JPEG_CHUNK >= nbytes) return;
-  uint8_t bytes[JPEG_CHUNK];
-  const int valid = load_chunk(raw + (size_t)b * raw_words_per_image, bits, chunk, bytes);
+  if ((size_t)chunk0 * JPEG_CHUNK >= nbytes) return;
   uint8_t* dst = out + (size_t)b * capacity;
-  size_t pos = (size_t)JPEG_HEADER + (size_t)chunk * JPEG_CHUNK + ffoff[(size_t)b * max_chunks + chunk];
+  const size_t pos0 = (size_t)JPEG_HEADER + (size_t)chunk0 * JPEG_CHUNK + ffoff[(size_t)b * max_chunks + chunk0];
+  const uint32_t lead = (uint32_t)((uintptr_t)(dst + pos0) & 3);    // the span starts `lead` bytes into an aligned word
+  if (tid == 0) s_end = 0;
+  __syncthreads();
+  if ((size_t)chunk * JPEG_CHUNK < nbytes) {
+    uint8_t bytes[JPEG_CHUNK];
+    const int valid = load_chunk(raw + (size_t)b * raw_words_per_image, bits, chunk, bytes);
+    uint32_t rel = lead + (uint32_t)((size_t)(chunk - chunk0) * JPEG_CHUNK + ffoff[(size_t)b * max_chunks + chunk] - ffoff[(size_t)b * max_chunks + chunk0]);
 #pragma unroll
-  for (int i = 0; i < JPEG_CHUNK; ++i) {
-    if (i < valid) {
-      if (pos < capacity) dst[pos] = bytes[i];
-      ++pos;
-      if (bytes[i] == 0xFF) {
-        if (pos < capacity) dst[pos] = 0;
-        ++pos;
+    for (int i = 0; i < JPEG_CHUNK; ++i) {
+      if (i < valid) {
+        sb[rel++] = bytes[i];
+        if (bytes[i] == 0xFF) sb[rel++] = 0;
       }
     }
+    const bool last = (size_t)chunk * JPEG_CHUNK + valid == nbytes;
+    if (last) {                                                     // EOI and the file size
+      sb[rel++] = 0xFF;
+      sb[rel++] = 0xD9;
+      sizes[b] = (int32_t)((size_t)JPEG_HEADER + nbytes + fftotal[b] + 2);
+    }
+    if (last || tid == 255) s_end = rel;
   }
-  if ((size_t)chunk * JPEG_CHUNK + valid == nbytes) {               // the last chunk: EOI and the file size
-    if (pos < capacity) dst[pos] = 0xFF;
-    if (pos + 1 < capacity) dst[pos + 1] = 0xD9;
-    sizes[b] = (int32_t)((size_t)JPEG_HEADER + nbytes + fftotal[b] + 2);
+  __syncthreads();
+  uint32_t end = s_end;
+  if (pos0 >= capacity) return;
+  if ((size_t)(end - lead) > capacity - pos0) end = lead + (uint32_t)(capacity - pos0);    // nothing is written beyond the capacity
+  uint8_t* base = dst + pos0 - lead;                                // 4-byte aligned
+  const uint32_t* sw = reinterpret_cast<const uint32_t*>(sb);
+  for (uint32_t i = tid; i * 4 < end; i += 256) {
+    const uint32_t lo = i * 4, hi = lo + 4;
+    if (lo >= lead && hi <= end) reinterpret_cast<uint32_t*>(base)[i] = sw[i];
+    else
+      for (uint32_t k = max(lo, lead); k < min(hi, end); ++k) base[k] = sb[k];
   }
 }
 
@@ -561,19 +637,14 @@ extern "C" int cic_jpeg_encode_u8(const uint8_t* d_img, int batch, int h, int w,
   make_header(h, w, qt, &hdr);
   const size_t raw_words = d.raw_bytes / 4;
   const int nblk = (int)d.nblk;
-  static DeviceOnce attr_set;
-  const size_t span_bytes = (size_t)JPEG_PACK_N * JPEG_BLOCK_MAX_BYTES + 16;
-  if (attr_set.todo()) {
-    CIC_CHECK_CUDA(cudaFuncSetAttribute(jpeg_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)span_bytes));
-    attr_set.done();
-  }
   jpeg_header_kernel<<<batch, 256, 0, st>>>(d_out, capacity, hdr);
   const dim3 g1((d.mw + 7) / 8, d.mh, batch);
-  if (rgb) jpeg_dct_kernel<true><<<g1, 256, 0, st>>>(d_img, coef, h, w, d.mw, d.mh, qt);
-  else jpeg_dct_kernel<false><<<g1, 256, 0, st>>>(d_img, coef, h, w, d.mw, d.mh, qt);
-  jpeg_len_kernel<<<dim3((nblk + 127) / 128, batch), 128, 0, st>>>(coef, len, nblk, tab);
+  const int words_ok = (w % 4 == 0) && (((uintptr_t)d_img & 3) == 0);
+  if (rgb) jpeg_dct_kernel<true><<<g1, 256, 0, st>>>(d_img, coef, h, w, d.mw, d.mh, words_ok, qt);
+  else jpeg_dct_kernel<false><<<g1, 256, 0, st>>>(d_img, coef, h, w, d.mw, d.mh, words_ok, qt);
+  jpeg_len_kernel<<<dim3((nblk + JPEG_PACK_N - 1) / JPEG_PACK_N, batch), JPEG_PACK_N, 0, st>>>(coef, len, nblk, tab);
   jpeg_scan_kernel<true, false><<<batch, 1024, 0, st>>>(len, off, bits_total, nullptr, d.nblk, nblk, raw, raw_words);
-  jpeg_pack_kernel<<<dim3((nblk + JPEG_PACK_N - 1) / JPEG_PACK_N, batch), JPEG_PACK_N, span_bytes, st>>>(coef, off, bits_total, raw, raw_words, nblk, tab);
+  jpeg_pack_kernel<<<dim3((nblk + JPEG_PACK_N - 1) / JPEG_PACK_N, batch), JPEG_PACK_N, 0, st>>>(coef, off, bits_total, raw, raw_words, nblk, tab);
   const dim3 g5((unsigned)((d.max_chunks + 255) / 256), batch);
   jpeg_ffcount_kernel<<<g5, 256, 0, st>>>(raw, raw_words, bits_total, ffcnt, d.max_chunks);
   jpeg_scan_kernel<false, true><<<batch, 1024, 0, st>>>(ffcnt, ffoff, fftotal, bits_total, d.max_chunks, 0, nullptr, 0);

@@ -392,6 +392,7 @@ def test_jpeg_encoder_is_byte_identical_to_opencv(cic, h, w):
     assert files[1] == jpeg.encode_bgr(imgs[1])
     for q in (100, 50, 10):
         assert cic.ops.jpeg_encode(imgs[1], quality=q) == bytes(cv2.imencode(".jpg", imgs[1], [cv2.IMWRITE_JPEG_QUALITY, q])[1]), q
+    assert cic.ops.jpeg_encode(imgs[0], quality=100) == bytes(cv2.imencode(".jpg", imgs[0], [cv2.IMWRITE_JPEG_QUALITY, 100])[1])   # longest codes
     # RGB input = save_image's cv2.cvtColor(img, cv2.COLOR_RGB2BGR) folded into the kernel
     assert cic.ops.jpeg_encode(imgs[1][..., ::-1].copy(), rgb=True) == files[1]
 

@@ -68,12 +68,32 @@ def calculate_ssim(image1, image2):
     return float(ops.metrics_f32(ga, gb, signed_range=False, data_range=1.0)[0, 1].item())
 
 
-def evaluate_batch(model: AutoencoderModel, images) -> dict:
+def evaluate_batch(model: AutoencoderModel, images, save_paths=None) -> dict:
     """The loop of test_autoencoder.py:83-108 for a whole batch in three launches-groups: predict,
     truncating uint8 cast of output and input, fused PSNR/SSIM/MSE.  images (B,H,W,3) float32 in [0,1].
-    Returns per-image arrays 'mse' (the reference's wrapped value), 'true_mse', 'psnr', 'ssim'."""
+    Returns per-image arrays 'mse' (the reference's wrapped value), 'true_mse', 'psnr', 'ssim'.
+    save_paths: one file name per image = the reference's cv2.imwrite(compressed_path, compressed_img_uint8) (:90-93); .jpg names
+    are encoded on the GPU (ops.jpeg_encode, the bytes OpenCV writes; the channel order is whatever the input had, as in the
+    reference), other formats are written by OpenCV from the downloaded uint8 batch."""
     x = to_device_f32(images)
     y, y8 = model.forward_device([x], want_u8=True)
     x8 = ops.f32_to_u8_trunc(x, 255.0)                       # test_autoencoder.py:96
     m = ops.metrics_gray_u8(x8, y8).cpu().numpy()
+    if save_paths is not None:
+        import os
+        if len(save_paths) != y8.shape[0]:
+            raise ValueError(f"{len(save_paths)} paths for {y8.shape[0]} images")
+        is_jpg = [os.path.splitext(p)[1].lower() in (".jpg", ".jpeg", ".jpe") for p in save_paths]
+        if any(is_jpg):
+            files = ops.jpeg_encode(y8)
+            for ok, data, p in zip(is_jpg, files, save_paths):
+                if ok:
+                    with open(p, "wb") as f:
+                        f.write(data)
+        if not all(is_jpg):
+            import cv2
+            host = y8.cpu().numpy()
+            for ok, img, p in zip(is_jpg, host, save_paths):
+                if not ok:
+                    cv2.imwrite(p, img)
     return {"psnr": m[:, 0], "ssim": m[:, 1], "true_mse": m[:, 2], "mse": m[:, 3], "compressed_u8": y8, "compressed": y}

@@ -431,3 +431,22 @@ def test_save_image_writes_opencv_bytes_from_the_gpu(cic, tmp_path):
     assert open(p, "rb").read() == open(q, "rb").read()
     gf.save_image(img, str(tmp_path / "c.png"))                                  # other formats stay on OpenCV
     np.testing.assert_array_equal(cv2.imread(str(tmp_path / "c.png")), u8)
+
+
+def test_autoencoder_batch_writes_the_files_opencv_would(cic, tmp_path):
+    """test_autoencoder.py:88-93: (compressed * 255).astype(uint8) -> cv2.imwrite(compressed_path, ...) per image; evaluate_batch does
+    it for the batch, .jpg on the GPU."""
+    import cv2
+    import train_autoencoder as tr
+    model = tr.build_autoencoder((64, 96, 3))
+    model.set_weights_dict(cic.weights.synthetic_autoencoder(seed=42))
+    x = cic.synth.to_unit_range(cic.synth.synth_images_u8(3, 64, 96, seed=3))
+    paths = [str(tmp_path / "a.jpg"), str(tmp_path / "b.png"), str(tmp_path / "c.jpeg")]
+    r = cic.autoencoder.evaluate_batch(model, x, save_paths=paths)
+    y8 = r["compressed_u8"].cpu().numpy()
+    for i, p in enumerate(paths):
+        q = str(tmp_path / ("ref_" + os.path.basename(p)))
+        cv2.imwrite(q, y8[i])
+        assert open(p, "rb").read() == open(q, "rb").read(), p
+    with pytest.raises(ValueError):
+        cic.autoencoder.evaluate_batch(model, x, save_paths=paths[:2])

@@ -52,6 +52,10 @@ class _Reader:
     def length(self, pos: int) -> int:
         return self.u(pos, self.L)
 
+    def off_from(self, body: bytes, pos: int) -> int:
+        """an offset-sized field of a message body (not of the file)"""
+        return int.from_bytes(body[pos:pos + self.O], "little")
+
     def at(self, addr: int) -> int:
         """file position of an address stored in the file (addresses are relative to the base address)"""
         return self.base + addr
@@ -453,9 +457,3 @@ class File(Group):
             walk(btree)
         return out
 
-
-def _off_from(self, body: bytes, pos: int) -> int:
-    return int.from_bytes(body[pos:pos + self.O], "little")
-
-
-_Reader.off_from = _off_from

@@ -490,7 +490,7 @@ class Bench:
             ms, last = self.timed(make_e2e(u8, want_dt), e2e_steps, e2e_warm, wall=True)
             return finish_leg(ms, u8, last[0])
 
-        def stream_leg(u8, want_dt=True):
+        def stream_leg(u8, want_dt=True, jpeg_out=0.0):
             """K steps through adaptive_model.predict_stream: every forward call's inputs come from pinned host memory and all its
             outputs go back to pinned host memory inside the timed region; consecutive calls overlap (upload of the next, kernels of
             this, download of the previous).  The metric sums of a step are all-reduced and copied to the host asynchronously."""
@@ -505,7 +505,7 @@ class Bench:
                         for k in sizes:
                             yield [t[:k] for t in src]
                 tot, seen, step = None, 0, 0
-                for outs, part in am.predict_stream(gen(), on_batch=on_chunk, u8_io=u8, want_dt=want_dt, depth=3):
+                for outs, part in am.predict_stream(gen(), on_batch=on_chunk, u8_io=u8, want_dt=want_dt, depth=3, jpeg_out=jpeg_out):
                     tot = part.clone() if tot is None else tot + part
                     seen += 1
                     last["outs"] = outs
@@ -532,13 +532,20 @@ class Bench:
                       "rd_params float32; consecutive forward calls overlap on three streams")
         e2e_single = single_call_leg(True)
         e2e_single["api"] = "adaptive_model.predict_phased(u8_io=True): one synchronous call per batch, the batch chunked to hide its own copies"
-        e2e_f32 = e2e_f32_nodt = None
+        e2e_f32 = e2e_f32_nodt = e2e_jpeg = None
         if headline:
             e2e_f32 = stream_leg(False)
             e2e_f32["api"] = "adaptive_model.predict_stream: float32 image up, float32 reconstruction down"
             e2e_f32_nodt = stream_leg(True, want_dt=False)
             e2e_f32_nodt["api"] = "adaptive_model.predict_stream(u8_io=True, want_dt=False): hq_ratio instead of the bit-allocation map"
-        self.launches += launches_per_step * (e2e_steps + e2e_warm) * (4 if headline else 2)
+            # the reference's own flow per image (GAN_test.py:386-390): metrics + the reconstruction saved as a JPEG file - the file is made
+            # on the device (byte-identical to cv2.imwrite), so the pixels never cross PCIe; 1 byte / pixel reserved per file
+            e2e_jpeg = stream_leg(True, want_dt=False, jpeg_out=1.0)
+            e2e_jpeg["api"] = ("adaptive_model.predict_stream(u8_io=True, want_dt=False, jpeg_out=1.0): uint8 image up; JPEG files of the "
+                               "reconstructions (save_image, GAN_functions.py:41-50), latents, rd_params, hq_ratio down; the encoder's 8 kernels are inside the step")
+            e2e_jpeg["device_step_ms"] = None                                       # the value leg's step does not contain the encoder
+            e2e_jpeg["frac_of_roof"] = None
+        self.launches += launches_per_step * (e2e_steps + e2e_warm) * (5 if headline else 2)
 
         # ---- bandwidth kernels of the path (headline only) ----------------------------------------------------------------------
         if headline:
@@ -607,7 +614,7 @@ class Bench:
             line["clocks"] = clocks
         line["e2e_single_call"] = e2e_single
         if e2e_f32 is not None:
-            line["e2e_f32_io"], line["e2e_u8_io_no_dt"] = e2e_f32, e2e_f32_nodt
+            line["e2e_f32_io"], line["e2e_u8_io_no_dt"], line["e2e_u8_in_jpeg_out"] = e2e_f32, e2e_f32_nodt, e2e_jpeg
         if cpu is not None:
             line["cpu_baseline"] = cpu
         if args.profile_csv and self.rank == 0 and headline:

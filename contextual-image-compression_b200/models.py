@@ -723,10 +723,10 @@ class AdaptiveCompressionModel(Model):
         return ratios / float(h * w)
 
     # ---- streaming predict: batches overlap each other ----------------------------------------------------------------------
-    def _stream_slot(self, slot, n, h, w, dev, u8_io, want_dt):
+    def _stream_slot(self, slot, n, h, w, dev, u8_io, want_dt, jpeg_cap=0):
         """Persistent device + pinned host buffers of one slot of predict_stream."""
         self.plan()
-        key = ("stream", slot, n, h, w, self._plan_gen, bool(u8_io), bool(want_dt))
+        key = ("stream", slot, n, h, w, self._plan_gen, bool(u8_io), bool(want_dt), int(jpeg_cap))
         cache = self.__dict__.setdefault("_stream_cache", {})
         if key in cache:
             return cache[key]
@@ -746,6 +746,11 @@ class AdaptiveCompressionModel(Model):
             b["blended_u8"] = torch.empty((n, h, w, 3), dtype=torch.uint8, device=dev)
         outs = [b["blended_u8"] if u8_io else b["blended"], b["hq_latent_q"], b["lq_latent_q"], b["rd_params"],
                 b["dt"] if want_dt else b["hq_ratio_sum"]]
+        if jpeg_cap:                                              # the reconstruction leaves the device as JPEG files
+            b["jpeg"] = torch.empty((n, jpeg_cap), dtype=torch.uint8, device=dev)
+            b["jpeg_sizes"] = torch.zeros((n,), dtype=torch.int32, device=dev)
+            outs[0] = b["jpeg"]
+            outs.append(b["jpeg_sizes"])
         b["outs"] = outs
         b["host"] = [torch.empty(o.shape, dtype=o.dtype, pin_memory=True) for o in outs]
         b["calls"], b["graph"], b["extra"] = 0, None, None
@@ -769,9 +774,20 @@ class AdaptiveCompressionModel(Model):
             ex = on_batch([b["img"], b["mask"], b["bpp"]], {"blended": b["blended"], "dt": b["dt"], "hq_ratio_sum": b["hq_ratio_sum"]})
         if u8_io:
             _lib.check(_lib.lib.cic_f32_signed_to_u8(ptr(b["blended"]), ptr(b["blended_u8"]), n * h * w * 3, runtime.stream_ptr()))
+        if "jpeg" in b:                                           # save_image's cv2.imwrite on the device (RGB -> BGR folded in)
+            jws = self.__dict__.setdefault("_stream_jpeg_ws", {})
+            need = int(_lib.lib.cic_jpeg_workspace_bytes(n, h, w))
+            if jws.get("bytes", 0) < need:
+                if torch.cuda.is_current_stream_capturing():
+                    raise RuntimeError("JPEG workspace must exist before graph capture")
+                for other in self.__dict__.get("_stream_cache", {}).values():      # graphs of other slots hold the old buffer
+                    other["graph"] = None
+                jws.update(bytes=need, buf=torch.empty(need, dtype=torch.uint8, device=b["jpeg"].device))
+            _lib.check(_lib.lib.cic_jpeg_encode_u8(ptr(b["blended_u8"]), n, h, w, 1, 95, ptr(b["jpeg"]), b["jpeg"].shape[1], ptr(b["jpeg_sizes"]),
+                                                   ptr(jws["buf"]), jws["bytes"], runtime.stream_ptr()))
         return ex
 
-    def predict_stream(self, batches, on_batch=None, u8_io: bool = False, want_dt: bool = True, depth: int = 2):
+    def predict_stream(self, batches, on_batch=None, u8_io: bool = False, want_dt: bool = True, depth: int = 2, jpeg_out: float = 0.0):
         """predict() for a STREAM of host batches at full throughput: a generator that yields (host outputs, on_batch result) per
         batch, in order.  Batch k + 1 is uploaded while batch k is on the tensor cores and batch k - 1 travels back to pinned host
         memory (three CUDA streams, `depth` buffer sets), so in steady state a batch costs max(kernels, copies) - not their sum,
@@ -781,8 +797,15 @@ class AdaptiveCompressionModel(Model):
 
         batches: iterable of [image (n,H,W,3), saliency (n,H,W,1), target_bpp (n,)] with one geometry; pinned tensors copy fastest.
         The yielded arrays are views of the slot's pinned buffers: valid until `depth` more batches have been yielded.
-        u8_io / want_dt: as predict_phased (uint8 image up, uint8 reconstruction down; hq_ratio instead of the dt map)."""
+        u8_io / want_dt: as predict_phased (uint8 image up, uint8 reconstruction down; hq_ratio instead of the dt map).
+        jpeg_out (with u8_io): bytes per pixel reserved for a JPEG file of every reconstruction (e.g. 1.0).  The reconstruction then
+        leaves the device the way the reference stores it - save_image's cv2.imwrite(".jpg") (GAN_functions.py:41-50, GAN_test.py:390),
+        encoded on the GPU, byte-identical to OpenCV's file: output 0 is a (n, capacity) uint8 array of files and a sixth output
+        holds their sizes (file i = out[0][i, :out[5][i]]; a size above the capacity means that file was cut and needs a larger
+        jpeg_out)."""
         dev = runtime.require_cuda()
+        if jpeg_out and not u8_io:
+            raise ValueError("jpeg_out needs u8_io=True (the files are made from the uint8 reconstruction)")
         compute = torch.cuda.current_stream()
         st = self.__dict__.setdefault("_pipe_streams", {})
         if "in" not in st:
@@ -816,7 +839,8 @@ class AdaptiveCompressionModel(Model):
                 raise ValueError(f"image must be (B, H, W, 3), got {tuple(img.shape)}")
             mask, bpp = self._check_inputs(img, mask, bpp)
             n, h, w, _ = img.shape
-            b = self._stream_slot(k % depth, n, h, w, dev, u8_io, want_dt)
+            jpeg_cap = (1024 + int(float(jpeg_out) * h * w) + 3) & ~3 if jpeg_out else 0
+            b = self._stream_slot(k % depth, n, h, w, dev, u8_io, want_dt, jpeg_cap)
             timeline = runtime.pipe_timeline()
             ev_in, ev_c, ev_out = (torch.cuda.Event(enable_timing=timeline) for _ in range(3))
             if timeline:                                              # debug: start / end of the three legs of every batch

@@ -354,6 +354,21 @@ def test_stream_predict_equals_predict(cic, small_cfg):
         assert np.abs(outs[0].astype(int) - want8.astype(int)).max() <= 3
         np.testing.assert_allclose(outs[4], want[4].reshape(3, -1).mean(1, dtype=np.float64), atol=1e-6)
     assert list(am.predict_stream(iter([]))) == []
+    # jpeg_out: the reconstruction leaves the device as the file save_image would write (GAN_functions.py:41-50) - equal to OpenCV's
+    # encoding of the uint8 reconstruction the u8_io stream returns for the same batch (same kernels, same graph inputs)
+    import cv2
+    gotj = [[np.array(o) for o in outs] for outs, _ in am.predict_stream(iter(batches8), u8_io=True, want_dt=False, depth=3, jpeg_out=2.0)]
+    assert len(gotj) == 6
+    for outs, ref8 in zip(gotj, got8):
+        assert len(outs) == 6 and outs[0].dtype == np.uint8 and outs[5].shape == (3,)
+        for i in range(3):
+            size = int(outs[5][i])
+            assert 623 < size <= outs[0].shape[1]
+            want = bytes(cv2.imencode(".jpg", cv2.cvtColor(ref8[0][i], cv2.COLOR_RGB2BGR))[1])
+            assert outs[0][i, :size].tobytes() == want
+        np.testing.assert_array_equal(outs[1], ref8[1])
+    with pytest.raises(ValueError, match="u8_io"):
+        list(am.predict_stream(iter(batches), jpeg_out=1.0))
 
 
 def test_rate_sweep_equals_one_predict_per_level(cic, small_cfg):

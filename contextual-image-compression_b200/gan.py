@@ -144,19 +144,19 @@ def bpp_accounting(hq_ratio, img_size=IMG_SIZE, base_latent_dim=BASE_LATENT_DIM)
 
 def _mask_for(img, mask, saliency_map=None):
     """The mask input of the model: an explicit mask, or create_saliency_mask(saliency_map, smooth=True) on the GPU when the caller
-    has a saliency map, or the reference's whole front end (needs cv2.saliency = opencv-contrib for the map)."""
+    has a saliency map, or the reference's whole front end (compute_saliency_map(img, 'combined') -> create_saliency_mask) as
+    one device-side chain."""
     if mask is not None:
         return np.asarray(mask, dtype=np.float32).reshape(img.shape[0], img.shape[1])
-    from . import saliency
     if saliency_map is None:
-        saliency_map = saliency.compute_saliency_map(img, method="combined")                 # GAN_test.py:279
+        return ops.saliency_mask_from_image(img, method="combined").cpu().numpy()         # GAN_test.py:279-280
     return ops.saliency_mask_smooth(np.asarray(saliency_map, np.float32)).cpu().numpy()   # GAN_test.py:280
 
 
 def compress_and_reconstruct(img, models, target_bpp=1.0, mask=None, saliency_map=None):
     """GAN_test.py:265-340.  `mask` (H,W) in [0,1] replaces the reference's saliency front end (GAN_test.py:279-280);
     `saliency_map` replaces only its opencv-contrib half (compute_saliency_map) - the mask is then made from it on the GPU;
-    with neither, the whole front end runs (needs cv2.saliency)."""
+    with neither, the whole front end runs on the GPU (csrc/saliency_map.cu + saliency_mask.cu)."""
     img = np.asarray(img, dtype=np.float32)
     mask = _mask_for(img, mask, saliency_map)
     img_batch = np.expand_dims(img, axis=0)

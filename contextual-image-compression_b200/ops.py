@@ -216,6 +216,42 @@ def saliency_mask_smooth(saliency_map) -> torch.Tensor:
     return y[0] if single else y
 
 
+SALIENCY_METHODS = {"spectral_residual": 0, "fine_grained": 1, "combined": 2}      # enum cic_saliency_method
+
+
+def saliency_map(image, method: str = "spectral_residual") -> torch.Tensor:
+    """compute_saliency_map(image, method) (GAN_functions.py:52-121) on the device: the spectral-residual and fine-grained
+    detectors of cv2.saliency (opencv-contrib) and their 0.6 / 0.4 mix, divided by the maximum.  image: (H,W,3) or (B,H,W,3), RGB;
+    float32 with max <= 1 is taken as [-1, 1] and mapped with ((x + 1) * 127.5).astype(uint8), anything else is cast to uint8
+    (:63-67).  -> float32 map (H,W) or (B,H,W) on the device."""
+    if method not in SALIENCY_METHODS:
+        raise ValueError(f"Unsupported saliency method: {method}")                      # GAN_functions.py:110
+    x = image if isinstance(image, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(image))
+    single = x.dim() == 3
+    if single:
+        x = x[None]
+    if x.dim() != 4 or x.shape[3] != 3:
+        raise ValueError(f"saliency_map: expected (H,W,3) or (B,H,W,3), got {tuple(x.shape)}")
+    x = x.to(runtime.require_cuda())
+    if x.dtype == torch.float32 and x.numel() and float(x.max()) <= 1.0:
+        x = f32_signed_to_u8(x.contiguous())
+    elif x.dtype != torch.uint8:
+        x = x.to(torch.int32).to(torch.uint8)           # numpy's astype(uint8): truncate toward zero, wrap modulo 256
+    x = x.contiguous()
+    b, h, w, _ = x.shape
+    y = torch.empty((b, h, w), dtype=torch.float32, device=x.device)
+    ws = torch.empty(int(_lib.lib.cic_saliency_map_workspace_bytes(b, h, w)), dtype=torch.uint8, device=x.device)
+    _lib.check(_lib.lib.cic_saliency_map_u8(ptr(x), ptr(y), b, h, w, 1, SALIENCY_METHODS[method], ptr(ws), ws.numel(),
+                                            runtime.stream_ptr()))
+    return y[0] if single else y
+
+
+def saliency_mask_from_image(image, method: str = "combined") -> torch.Tensor:
+    """The reference's whole mask front end for one image or a batch, on the device with nothing crossing PCIe in between:
+    create_saliency_mask(compute_saliency_map(img, method), smooth=True) (GAN_test.py:279-280)."""
+    return saliency_mask_smooth(saliency_map(image, method))
+
+
 def rans_encode(symbols: torch.Tensor):
     """Entropy-code integer latent symbols (rows, L) int32 on the device -> (uint8 stream tensor, trimmed to its length).  One
     host synchronisation (the length).  Symbols beyond +-1023 are clamped (|symbol| <~ 100 in the codec: scale <= e^2.652)."""

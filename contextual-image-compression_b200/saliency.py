@@ -4,8 +4,7 @@ These are the steps *before* the accelerated path
 pipeline.  They follow the reference operation for operation so that masks (and therefore dt, hq_ratio, actual_bpp and the
 blended image) are the reference's:
 
-  * `compute_saliency_map` needs `cv2.saliency` (opencv-contrib, not installed in this image); it raises a clear error when the
-    module is absent - callers then pass an explicit mask - and follows the reference's fall-backs when a method *fails*.
+  * `compute_saliency_map` runs the two cv2.saliency detectors (opencv-contrib) and their mix on the GPU (`ops.saliency_map`);
   * `create_saliency_mask(smooth=True)` - the only mode the reference uses (GAN_test.py:280,553) - is plain OpenCV (bilateral
     9/75/75, Gaussian 31x31, / max); `ops.saliency_mask_smooth` is the same arithmetic on the GPU (§8 f2).
 """
@@ -66,64 +65,17 @@ def save_images_u8(images_u8, paths, rgb=True, quality=95):
             f.write(data)
 
 
-def _saliency_module():
-    import cv2
-    mod = getattr(cv2, "saliency", None)
-    if mod is None:
-        raise RuntimeError("compute_saliency_map needs cv2.saliency (opencv-contrib), which is not installed; "
-                           "pass a saliency mask explicitly (mask=...)")
-    return mod
-
-
-def _to_cv_bgr_u8(image):
-    """GAN_functions.py:63-71: float32 images with max <= 1 are taken as [-1, 1] and mapped to [0, 255] (truncation); anything
-    else is cast to uint8 as is.  3-channel images are RGB -> BGR."""
-    import cv2
-    image = np.asarray(image)
-    if image.dtype == np.float32 and np.max(image) <= 1.0:
-        image_cv = ((image + 1) * 127.5).astype(np.uint8)
-    else:
-        image_cv = image.astype(np.uint8)
-    if image_cv.ndim == 3 and image_cv.shape[2] == 3:
-        image_cv = cv2.cvtColor(image_cv, cv2.COLOR_RGB2BGR)
-    return image_cv
-
-
 def compute_saliency_map(image, method="spectral_residual"):
-    """GAN_functions.py:52-121.
-
-    'combined' mixes the RAW spectral-residual and fine-grained maps (0.6 / 0.4, :95) and normalises only the sum (:98-99) - the
-    maps keep their native ranges in the mix.  A failed method falls back to the surviving map (returned un-normalised, as the
-    reference does, :84-88) or to a uniform map of ones (:89-91, :112-115)."""
-    sal = _saliency_module()
-    image_cv = _to_cv_bgr_u8(image)
-    uniform = np.ones(image_cv.shape[:2], dtype=np.float32)
-    if method == "combined":
-        ok_s, spectral = sal.StaticSaliencySpectralResidual_create().computeSaliency(image_cv)
-        ok_f, fine = sal.StaticSaliencyFineGrained_create().computeSaliency(image_cv)
-        if not (ok_s and ok_f):
-            print("Warning: One or more saliency methods failed. Using available method.")
-            if ok_s:
-                return spectral
-            if ok_f:
-                return fine
-            print("All saliency methods failed. Returning uniform saliency.")
-            return uniform
-        mix = 0.6 * spectral + 0.4 * fine
-        peak = mix.max()
-        return mix / peak if peak > 0 else mix
-    if method == "spectral_residual":
-        algo = sal.StaticSaliencySpectralResidual_create()
-    elif method == "fine_grained":
-        algo = sal.StaticSaliencyFineGrained_create()
-    else:
-        raise ValueError(f"Unsupported saliency method: {method}")
-    ok, out = algo.computeSaliency(image_cv)
-    if not ok:
-        print(f"Failed to compute saliency using {method} method.")
-        return uniform
-    peak = out.max()
-    return out / peak if peak > 0 else out
+    """GAN_functions.py:52-121 on the GPU (`ops.saliency_map`, csrc/saliency_map.cu): the reference calls cv2.saliency
+    (opencv-contrib) on the CPU; here the spectral-residual and fine-grained detectors, the RAW 0.6 / 0.4 mix of 'combined' (:95)
+    and the division by the maximum (:98-99, :118-119) run on the device.  Same input conventions (:63-71), same ValueError for an
+    unknown method (:110), float32 (H,W) numpy array out.  The reference's fall-backs for a detector that reports failure
+    (:81-91, :112-115) have no counterpart: neither detector can fail."""
+    from . import ops
+    image = np.asarray(image)
+    if image.ndim == 2:                                 # OpenCV's detectors take a one-channel image as is
+        image = np.repeat(image[:, :, None], 3, axis=2)
+    return ops.saliency_map(image, method).cpu().numpy()
 
 
 def adaptive_threshold(saliency_map):

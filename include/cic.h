@@ -253,10 +253,20 @@ int cic_symbol_entropy_bits(const int32_t* d_symbols, double* d_bits, int batch,
 /* create_saliency_mask(saliency_map, smooth=True) (GAN_functions.py:199-203; recomputed on the CPU for every image and target bpp
  * at GAN_test.py:279-280): cv2.bilateralFilter(map, 9, 75, 75) -> cv2.GaussianBlur(31x31, sigma 0 = 5.0) -> / max (if max > 0), with
  * OpenCV's semantics (circular 9-tap-wide neighbourhood, BORDER_REFLECT_101, float32).  d_saliency, d_mask (B,H,W) float32; the two
- * may not alias.  The saliency map itself (cv2.saliency, opencv-contrib) stays a host input. */
+ * may not alias. */
 size_t cic_saliency_mask_workspace_bytes(int batch, int h, int w);
 int cic_saliency_mask_smooth(const float* d_saliency, float* d_mask, int batch, int h, int w, void* d_workspace,
                              size_t workspace_bytes, void* stream);
+
+/* compute_saliency_map(image, method) (GAN_functions.py:52-121; called per image and target bpp at GAN_test.py:279, :552 and
+ * GAN_train.py:84): cv2.saliency.StaticSaliencySpectralResidual / StaticSaliencyFineGrained (opencv-contrib) on the uint8 image,
+ * method 'combined' = 0.6 * spectral + 0.4 * fine (:95), every result divided by its maximum when that is positive (:98-99,
+ * :118-119).  d_images (B,H,W,3) uint8 - what GAN_functions.py:63-67 hands to OpenCV - in RGB (rgb = 1: the reference's RGB -> BGR
+ * swap of :70-71 happens inside) or BGR order; d_map (B,H,W) float32 in [0, 1]. */
+enum cic_saliency_method { CIC_SALIENCY_SPECTRAL_RESIDUAL = 0, CIC_SALIENCY_FINE_GRAINED = 1, CIC_SALIENCY_COMBINED = 2 };
+size_t cic_saliency_map_workspace_bytes(int batch, int h, int w);
+int cic_saliency_map_u8(const uint8_t* d_images, float* d_map, int batch, int h, int w, int rgb, int method, void* d_workspace,
+                        size_t workspace_bytes, void* stream);
 
 /* Entropy coder for the integer latent symbols: the bitstream the reference never writes (its bitrate is the nominal 32 bits per
  * latent element of GAN_test.py:310-325).  Static model per call (histogram over all symbols, normalised to 2^14),

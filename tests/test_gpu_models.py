@@ -233,8 +233,13 @@ def test_compress_and_reconstruct_and_rate_control(cic, precision, small_cfg):
     np.testing.assert_allclose(fast["actual_bpp"], [(h * 64 + (1 - h) * 32) * 32 / 4096 for h in fast["hq_ratio"]], rtol=1e-12)
     per_img = np.array(fast["hq_ratio"]).reshape(4, 10)
     assert np.all(np.diff(per_img, axis=1) > 0)
-    with pytest.raises(RuntimeError, match="saliency"):
-        gt.compress_and_reconstruct(img[0], models, target_bpp=1.0)             # no mask and no opencv-contrib
+    # no mask: the reference's whole front end (compute_saliency_map 'combined' -> create_saliency_mask, GAN_test.py:279-280) on the GPU
+    from oracle import saliency as osal
+    r2 = gt.compress_and_reconstruct(img[0], models, target_bpp=1.0)
+    want_mask = cic.saliency.create_saliency_mask(osal.compute_saliency_map(img[0], "combined"), smooth=True)   # oracle map, cv2 mask
+    np.testing.assert_allclose(r2["saliency_map"], want_mask, atol=1e-4)
+    want2 = graphs.adaptive_forward(ws, img[:1], want_mask[None, :, :, None], np.array([[1.0]], np.float32))
+    assert abs(r2["hq_ratio"] - want2[4].mean()) < 1e-4
 
 
 def test_pipelined_predict_equals_predict(cic, precision, small_cfg):

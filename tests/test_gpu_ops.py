@@ -370,6 +370,51 @@ def test_saliency_mask_smooth_matches_opencv(cic, b, h, w):
     assert cic.ops.saliency_mask_smooth(zero).abs().max().item() == 0.0
 
 
+@pytest.mark.parametrize("b,h,w", [(3, 256, 256), (1, 100, 173), (2, 512, 384), (1, 1080, 1920), (2, 64, 64), (1, 37, 300)])
+def test_saliency_map_matches_oracle(cic, b, h, w):
+    """cic_saliency_map_u8 (compute_saliency_map, GAN_functions.py:52-121) against oracle/saliency.py: the numpy
+    restatement (fine grained: the uint8 conspicuity map bit for bit; spectral residual: float64 pipeline, 1e-5) and the same
+    detectors composed of the REAL OpenCV core routines (1e-3: cv2's polar conversions are float32)."""
+    from oracle import saliency as osal
+    from test_oracle_saliency import photo
+    bgr = np.stack([photo(h, w, seed=10 * h + i) for i in range(b)])
+    rgb_u8 = np.ascontiguousarray(bgr[..., ::-1])
+    signed = (rgb_u8.astype(np.float32) - 127.5) / 127.5                         # what load_and_preprocess_image returns
+    for method in ("spectral_residual", "fine_grained", "combined"):
+        got = cic.ops.saliency_map(signed, method).cpu().numpy()
+        got_u8 = cic.ops.saliency_map(rgb_u8, method).cpu().numpy()              # uint8 input: cast as is (:65-66)
+        assert got.shape == (b, h, w) and got.dtype == np.float32
+        for i in range(b):
+            want = osal.compute_saliency_map(signed[i], method)
+            tol = 0 if method == "fine_grained" else 1e-5
+            np.testing.assert_allclose(got[i], want, atol=tol, rtol=0)
+            np.testing.assert_allclose(got[i], osal.compute_saliency_map(signed[i], method, use_cv=True), atol=1e-3)
+            assert got[i].max() == pytest.approx(1.0, abs=1e-6)
+            # ((u8 - 127.5) / 127.5 + 1) * 127.5 truncates back to u8 or u8 - 1: the two input conventions agree closely, not exactly
+            assert np.mean(np.abs(got_u8[i] - got[i])) < 2e-2
+    single = cic.saliency.compute_saliency_map(signed[0], method="combined")     # the drop-in name: numpy in, numpy out
+    np.testing.assert_array_equal(single, got[0])
+    with pytest.raises(ValueError, match="Unsupported"):
+        cic.ops.saliency_map(signed, "nope")
+
+
+def test_saliency_map_degenerate_inputs(cic):
+    """A flat image: the fine-grained map is all zero and stays zero (no division by a zero maximum, GAN_functions.py:118); the
+    whole front end on a batch equals per-image calls."""
+    from oracle import saliency as osal
+    from test_oracle_saliency import photo
+    flat = np.full((1, 48, 48, 3), 90, np.uint8)
+    assert cic.ops.saliency_map(flat, "fine_grained").abs().max().item() == 0.0
+    bgr = np.stack([photo(128, 160, seed=i) for i in range(3)])
+    rgb = np.ascontiguousarray(bgr[..., ::-1])
+    masks = cic.ops.saliency_mask_from_image(rgb).cpu().numpy()
+    for i in range(3):
+        one = cic.ops.saliency_mask_from_image(rgb[i]).cpu().numpy()
+        np.testing.assert_array_equal(masks[i], one)
+        want = cic.saliency.create_saliency_mask(osal.compute_saliency_map(rgb[i], "combined"), smooth=True)
+        np.testing.assert_allclose(masks[i], want, atol=1e-4)
+
+
 def _jpeg_image(h, w, kind, seed):
     from test_oracle_extras import _jpeg_test_image
     return _jpeg_test_image(h, w, kind, seed)

@@ -267,39 +267,18 @@ def test_fixture_script_assigns_every_tensor(cic):
     assert fx.assign_layers(al, "autoencoder", aref) == len(aref)
 
 
-def test_saliency_front_end_follows_the_reference(cic, monkeypatch):
-    """compute_saliency_map with a stubbed cv2.saliency (opencv-contrib is absent): 'combined' mixes the RAW maps 0.6 / 0.4 and
-    normalises only the sum (GAN_functions.py:95-99); failures fall back like :84-91; the input-range rule of :63-66 is kept."""
-    import types
-    import cv2
+def test_saliency_front_end_follows_the_reference(cic):
+    """compute_saliency_map is the GPU path (no cv2.saliency route): an unknown method raises like GAN_functions.py:110 before any
+    device work, and without a device the call fails loudly instead of falling back.  The non-smooth mask keeps :172-194."""
+    import torch
     sal = cic.saliency
-    spec_map = np.array([[0.2, 0.4], [0.1, 0.0]], np.float32)
-    fine_map = np.array([[10.0, 0.0], [30.0, 20.0]], np.float32)       # native range differs from the spectral map's
-    seen = {}
-
-    def algo(out, ok=True):
-        def compute(self, img):
-            seen["dtype"], seen["shape"], seen["max"] = img.dtype, img.shape, int(img.max())
-            return ok, out
-        return type("Algo", (), {"computeSaliency": compute})()
-    state = {"ok_s": True, "ok_f": True}
-    stub = types.SimpleNamespace(StaticSaliencySpectralResidual_create=lambda: algo(spec_map, state["ok_s"]),
-                                 StaticSaliencyFineGrained_create=lambda: algo(fine_map, state["ok_f"]))
-    monkeypatch.setattr(cv2, "saliency", stub, raising=False)
-    img = np.zeros((2, 2, 3), np.float32)                               # [-1, 1] convention: 0 -> 127
-    got = sal.compute_saliency_map(img, method="combined")
-    want = 0.6 * spec_map + 0.4 * fine_map
-    np.testing.assert_allclose(got, want / want.max(), rtol=1e-6)
-    assert seen["dtype"] == np.uint8 and seen["max"] == 127
-    sal.compute_saliency_map(np.full((2, 2, 3), 200.0, np.float32), method="spectral_residual")
-    assert seen["max"] == 200                                           # max > 1: cast as is (:65-66)
-    state["ok_f"] = False
-    np.testing.assert_array_equal(sal.compute_saliency_map(img, method="combined"), spec_map)     # surviving map, un-normalised (:86)
-    state["ok_s"] = False
-    np.testing.assert_array_equal(sal.compute_saliency_map(img, method="combined"), np.ones((2, 2), np.float32))
-    np.testing.assert_array_equal(sal.compute_saliency_map(img, method="fine_grained"), np.ones((2, 2), np.float32))
+    img = np.zeros((8, 8, 3), np.float32)
     with pytest.raises(ValueError, match="Unsupported"):
         sal.compute_saliency_map(img, method="nope")
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            sal.compute_saliency_map(img, method="combined")
+    assert not hasattr(sal, "_saliency_module")
     # the non-smooth mask uses the adaptive threshold of :172-194 (Otsu vs 70 % histogram share, clamped to [0.05, 0.5])
     rng = np.random.default_rng(0)
     m = rng.random((64, 64)).astype(np.float32) ** 3

@@ -582,6 +582,7 @@ class Bench:
                 "note": "cic_rans_encode: static model per call, 32 interleaved rANS states per tile row; bpp_both_streams counts the HQ and the LQ "
                         "latent of every tile (the soft ROI blend needs both everywhere) over the unpadded pixels"}
             quality["output_stage"] = self.jpeg_stage(out["blended"], k, h, w)
+            quality["input_stage"] = self.saliency_stage(d_img[:k], img[:k], k, h, w)
             if name == "c5":                                                      # BASELINE configs[4]: "PSNR/MS-SSIM per image" (MS-SSIM: unpinned extra)
                 quality["per_image_ms_ssim"] = [float(v) for v in cic.ops.ms_ssim_f32(d_img[:k], out["blended"], signed_range=True).cpu().numpy()]
             n_or = args.cpu_tiles if headline else min(args.cpu_tiles, 4)
@@ -655,6 +656,32 @@ class Bench:
             rep["byte_identical_to_opencv"] = bool(all(a == b for a, b in zip(files, want)))
         except ImportError:
             rep["byte_identical_to_opencv"] = None
+        return rep
+
+    def saliency_stage(self, d_img, img, k, h, w):
+        """The reference's input stage (GAN_test.py:279-280: compute_saliency_map(img, 'combined') -> create_saliency_mask(smooth=True), run
+        on the CPU per image and target bpp) on the device for the k images of the parity block; image 0 is compared with the CPU
+        restatement composed of the real OpenCV core routines (oracle/saliency.py; opencv-contrib itself is absent: unpinned).  Outside
+        every timed region - the bench's masks stay the synthetic ones of SURVEY 8d."""
+        torch, cic = self.torch, self.cic
+        cic.ops.saliency_mask_from_image(d_img)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        torch.cuda.synchronize()
+        ev[0].record()
+        for _ in range(5):
+            masks = cic.ops.saliency_mask_from_image(d_img)
+        ev[1].record()
+        torch.cuda.synchronize()
+        ms = ev[0].elapsed_time(ev[1]) / 5
+        self.launches += 6 * 19
+        rep = {"images": k, "what": "spectral residual + fine grained saliency, 0.6 / 0.4 mix, bilateral 9/75/75, Gaussian 31x31, / max",
+               "ms": ms, "mpix_s": k * h * w / ms / 1e3, "kernel_launches_per_call": 19}
+        if h * w <= 1920 * 1080:
+            from oracle import saliency as osal
+            t0 = time.perf_counter()
+            want = cic.saliency.create_saliency_mask(osal.compute_saliency_map(img[0], "combined", use_cv=True), smooth=True)
+            rep["opencv_one_core_mpix_s"] = h * w / (time.perf_counter() - t0) / 1e6
+            rep["mask_max_abs_delta_vs_opencv_restatement"] = float(np.abs(masks[0].cpu().numpy() - want).max())
         return rep
 
     def hbm_kernels(self, prof, am, d_img, d_mask, d_bpp):

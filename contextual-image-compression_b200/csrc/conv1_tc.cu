@@ -20,7 +20,7 @@ namespace cic {
 constexpr int C1_K = 64;             // padded K
 constexpr int C1_ROWB = C1_K * 2;    // bytes per A / B row
 constexpr int C1_ABYTES = TC_BM * C1_ROWB;  // one A part (16 KB)
-constexpr int C1_MAX_PATCH = 4 * 258 * 3;   // floats: TW = 128, TH = 1
+constexpr int C1_MAX_PATCH = 4 * 194 * 4;   // floats: TW = 128, TH = 1 staged as 194 16-byte chunks per row (4 * 258 * 3 + padding)
 
 struct Conv1Params {
   const float* x;
@@ -108,8 +108,20 @@ conv1_tc_kernel(const __grid_constant__ Conv1Params p) {
     const int r = threadIdx.x;
     const int xl = r % p.TW, yl = r / p.TW;
     const bool row_ok = yl < p.TH;
-    int lt = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++lt) {
+    const uint32_t patch_s = smem_u32(patch);
+    // Fast staging (the codec's 256-wide tiles and every other 16-byte-friendly geometry): the patch row starts one pixel left of
+    // the tile (pad_l = 1), i.e. 12 bytes before a 16-byte boundary, so staging starts ONE FLOAT earlier and moves whole 16-byte
+    // chunks: the first chunk holds the left padding pixel and the last one the right padding pixel - both entirely outside the
+    // tile (zero fill), every other chunk entirely inside.  6 cp.async per thread and tile instead of 24.
+    const int PWC = (PW3 + 1 + 3) >> 2;                      // 16-byte chunks per staged row (one leading float)
+    const bool fast = p.pad_l == 1 && (p.W & 3) == 0 && 2 * p.TW == p.W && (!p.tm.tiles_x || (p.tm.IW & 3) == 0) &&
+                      ((size_t)PH * PWC * 4 <= (size_t)C1_MAX_PATCH) && ((reinterpret_cast<uintptr_t>(p.x) & 15) == 0);
+    // floats per staged row; position of the row's first patch float (image float -3 of a row staged from float -4: odd, so the
+    // gather below cannot use 8-byte loads on it directly)
+    const int pitch = fast ? 4 * PWC : PW3, lead = fast ? 1 : 0;
+
+    // stage the patch of tile t (asynchronously; the caller waits with cp.async.wait_all + the named barrier)
+    auto stage = [&](int t) {
       const int b = t / tiles_per_img, ti = t % tiles_per_img;
       const int oy0 = (ti / p.tiles_x) * p.TH, ox0 = (ti % p.tiles_x) * p.TW;
       const float* xb;
@@ -127,44 +139,72 @@ conv1_tc_kernel(const __grid_constant__ Conv1Params p) {
         row_stride = (size_t)p.W * 3;
       }
       const int iy0 = 2 * oy0 - p.pad_t, ix0 = 2 * ox0 - p.pad_l;
-      named_bar_sync(1, 128);  // everyone is done reading the previous patch
-      {
-        // all loads of the tile in flight at once: 4-byte cp.async with zero fill outside the tile ('same' padding: tiles are
-        // coded independently); pixels of a ragged tile beyond the image replicate the image's last row / column
-        const uint32_t patch_s = smem_u32(patch);
-        const float* row0 = xb + (long long)ix0 * 3;
-        const bool ragged = vh < p.H || vw < p.W;
-        int pr = 0, cix = r;  // r < 128 < PW3
-        for (int i = r; i < PH * PW3; i += 128) {
-          const int px = (int)(((unsigned)cix * 43691u) >> 17);  // cix / 3 for cix < 98304
-          const int iy = iy0 + pr, ix = ix0 + px;
-          const bool ok = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
-          const float* src = ok ? row0 + (size_t)iy * row_stride + cix : p.x;
-          if (ragged && ok && (iy >= vh || ix >= vw))
-            src = xb + (size_t)min(iy, vh - 1) * row_stride + (size_t)min(ix, vw - 1) * 3 + (cix - 3 * px);
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(patch_s + (uint32_t)i * 4u), "l"(src), "r"(ok ? 4 : 0) : "memory");
-          cix += 128;
-          if (cix >= PW3) { cix -= PW3; ++pr; }
+      const bool ragged = vh < p.H || vw < p.W;
+      if (fast && !ragged) {
+        // ox0 == 0 (one tile spans the row): chunk c of row pr covers floats 4c - 4 .. 4c - 1 of the image row
+        for (int i = r; i < PH * PWC; i += 128) {
+          const int pr = i / PWC, c = i - pr * PWC;
+          const int iy = iy0 + pr;
+          const bool ok = iy >= 0 && iy < p.H && c >= 1 && 4 * c - 4 < 3 * p.W;
+          const float* src = ok ? xb + (size_t)iy * row_stride + (4 * c - 4) : p.x;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(patch_s + (uint32_t)i * 16u), "l"(src), "r"(ok ? 16 : 0) : "memory");
         }
-        asm volatile("cp.async.wait_all;" ::: "memory");
+        return;
       }
-      named_bar_sync(1, 128);
+      // generic staging: 4-byte cp.async with zero fill outside the tile ('same' padding: tiles are coded independently); pixels
+      // of a ragged tile beyond the image replicate the image's last row / column
+      const float* row0 = xb + (long long)ix0 * 3;
+      int pr = 0, cix = r;  // r < 128 < PW3
+      for (int i = r; i < PH * PW3; i += 128) {
+        const int px = (int)(((unsigned)cix * 43691u) >> 17);  // cix / 3 for cix < 98304
+        const int iy = iy0 + pr, ix = ix0 + px;
+        const bool ok = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+        const float* src = ok ? row0 + (size_t)iy * row_stride + cix : p.x;
+        if (ragged && ok && (iy >= vh || ix >= vw))
+          src = xb + (size_t)min(iy, vh - 1) * row_stride + (size_t)min(ix, vw - 1) * 3 + (cix - 3 * px);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(patch_s + (uint32_t)(pr * pitch + lead + cix) * 4u), "l"(src), "r"(ok ? 4 : 0) : "memory");
+        cix += 128;
+        if (cix >= PW3) { cix -= PW3; ++pr; }
+      }
+    };
+
+    int lt = 0;
+    if ((int)blockIdx.x < p.total_tiles) stage(blockIdx.x);
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++lt) {
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      named_bar_sync(1, 128);  // the whole patch of tile t has landed
+      float v[48];
+      if (row_ok) {
+#pragma unroll
+        for (int ky = 0; ky < 4; ++ky) {
+          const float* row = patch + (2 * yl + ky) * pitch + lead + 6 * xl;
+          if (lead) {  // odd start: one word, five aligned pairs, one word
+            v[12 * ky] = row[0];
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+              const float2 f = *reinterpret_cast<const float2*>(row + 1 + 2 * j);
+              v[12 * ky + 1 + 2 * j] = f.x;
+              v[12 * ky + 2 + 2 * j] = f.y;
+            }
+            v[12 * ky + 11] = row[11];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+              const float2 f = *reinterpret_cast<const float2*>(row + 2 * j);
+              v[12 * ky + 2 * j] = f.x;
+              v[12 * ky + 2 * j + 1] = f.y;
+            }
+          }
+        }
+      }
+      named_bar_sync(1, 128);  // everyone holds its patch values in registers: the staging buffer is free again
+      // the next tile's loads fly while this tile is split and stored (one staging buffer: no shared memory left for two)
+      if (t + (int)gridDim.x < p.total_tiles) stage(t + gridDim.x);
       const int buf = lt & 1;
       mbar_wait(&a_empty[buf], (((uint32_t)lt >> 1) & 1u) ^ 1u);  // the MMAs that read this buffer have retired
       if (row_ok) {
         uint8_t* row_hi = a_buf + (size_t)buf * 2 * C1_ABYTES + (size_t)r * C1_ROWB;
         uint8_t* row_lo = row_hi + C1_ABYTES;
-        float v[48];
-#pragma unroll
-        for (int ky = 0; ky < 4; ++ky) {
-          const float2* src = reinterpret_cast<const float2*>(patch + (2 * yl + ky) * PW3 + 6 * xl);
-#pragma unroll
-          for (int j = 0; j < 6; ++j) {
-            const float2 f = src[j];
-            v[12 * ky + 2 * j] = f.x;
-            v[12 * ky + 2 * j + 1] = f.y;
-          }
-        }
 #pragma unroll
         for (int c = 0; c < 6; ++c) {
           uint32_t hi[4], lo[4];

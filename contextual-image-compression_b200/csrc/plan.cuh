@@ -111,6 +111,13 @@ size_t conv1_tc_image_bytes(int n_enc);
 int conv1_tc_pack(const float* w0, const float* w1, uint8_t* img, cudaStream_t st);
 int launch_conv1_tc(const float* x, const uint8_t* wimg, const float* bias, int n_enc, __nv_bfloat16* const* out_hi,
                     __nv_bfloat16* const* out_lo, int batch, int H, int W, const TileMap& tm, cudaStream_t st);
+// 1- / 3-channel first layers with 32 outputs on the tensor cores (first_conv_tc.cu): autoencoder conv1 + pool, RD conv1
+size_t first_conv_image_bytes();
+int first_conv_pack(const float* w, int nk, uint8_t* img, cudaStream_t st);
+int launch_first_conv_tc_pool(const float* x, const uint8_t* wimg, const float* bias, __nv_bfloat16* out_hi, __nv_bfloat16* pool_hi,
+                              int batch, int H, int W, int act, cudaStream_t st);
+int launch_first_conv_tc_c1s2(const float* x, const uint8_t* wimg, const float* bias, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo,
+                              int batch, int H, int W, int act, const TileMap& tm, cudaStream_t st);
 int launch_conv_k3s1_c3_pool(const float* x, const float* wgt, const float* bias, __nv_bfloat16* out_hi, __nv_bfloat16* pool_hi,
                              int batch, int H, int W, int act, cudaStream_t st);
 int launch_conv_k3s2_c1(const float* x, const float* wgt, const float* bias, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo,

@@ -93,6 +93,11 @@ int build_plan_tc(cic_plan* pl, const cic_tensor* tensors, int n, const std::str
         CIC_REQUIRE(img, "tc plan: out of device memory");
         rc = conv_rows_pack(w.ptr("conv_out/kernel"), img, 3, 64, 3, nullptr);
       }
+      if (!rc && pl->opts.img_c == 3) {  // conv1 (3 -> 32, k3) as the resident weight image of first_conv_tc.cu
+        uint8_t* img = (uint8_t*)pl->tcw.alloc("conv1#fc", first_conv_image_bytes());
+        CIC_REQUIRE(img && w.ptr("conv1/kernel"), "tc plan: conv1 weights");
+        rc = first_conv_pack(w.ptr("conv1/kernel"), 27, img, nullptr);
+      }
       break;
     }
     case CIC_PLAN_ENCODER: {
@@ -148,6 +153,11 @@ int build_plan_tc(cic_plan* pl, const cic_tensor* tensors, int n, const std::str
     }
     case CIC_PLAN_RD:  // conv2 (32 -> 64, k3 s2) on the tensor cores, split-bf16 (rd_params are compared at 2e-5)
       rc = pack(pl, "conv2", w.ptr("conv2/kernel"), 9 * 32, 64, 64, true);
+      if (!rc) {  // conv1 (1 -> 32, k3 s2) as the resident weight image of first_conv_tc.cu
+        uint8_t* img = (uint8_t*)pl->tcw.alloc("conv1#fc", first_conv_image_bytes());
+        CIC_REQUIRE(img && w.ptr("conv1/kernel"), "tc plan: RD conv1 weights");
+        rc = first_conv_pack(w.ptr("conv1/kernel"), 9, img, nullptr);
+      }
       break;
     default: break;  // the saliency MLPs stay fp32
   }
@@ -557,7 +567,12 @@ int autoencoder_forward_tc(cic_plan* pl, Ctx& c, const float* x, float* y, uint8
   int rc;
   if (!c.dry) {  // :14-15 Conv2D(32, relu) + MaxPooling2D fused: writes x1 and its pooled copy
     Scope sc(c, "conv1", 2.0 * px * 32 * 27, 4.0 * px * 3 + 2.0 * px * 32 * 1.25);
-    if ((rc = launch_conv_k3s1_c3_pool(x, w.ptr("conv1/kernel"), w.ptr("conv1/bias"), x1.hi, x1p.hi, B, H, W, CIC_ACT_RELU, c.st))) return rc;
+    const uint8_t* fc = (const uint8_t*)pl->tcw.ptr("conv1#fc");
+    if (fc && H % 2 == 0 && W % 2 == 0 && CIC_KNOB("CIC_FIRST_TC", 1))
+      rc = launch_first_conv_tc_pool(x, fc, w.ptr("conv1/bias"), x1.hi, x1p.hi, B, H, W, CIC_ACT_RELU, c.st);
+    else
+      rc = launch_conv_k3s1_c3_pool(x, w.ptr("conv1/kernel"), w.ptr("conv1/bias"), x1.hi, x1p.hi, B, H, W, CIC_ACT_RELU, c.st);
+    if (rc) return rc;
   }
 #define AE_CONV(name, s0, s1p, hh, ww, cin, co, outbuf, up)                                                                   \
   {                                                                                                                           \
@@ -612,7 +627,12 @@ int rd_forward_tc(cic_plan* pl, Ctx& c, const float* mask, const float* bpp, flo
   int rc;
   if (!c.dry) {                                                                                // :511-512
     Scope sc(c, "conv1", 2.0 * B * h2 * w2 * 32 * 9, 4.0 * B * H * W + 4.0 * B * h2 * w2 * 32);
-    if ((rc = launch_conv_k3s2_c1(mask, w.ptr("conv1/kernel"), w.ptr("conv1/bias"), r1.hi, r1.lo, B, H, W, CIC_ACT_LRELU02, tm, c.st))) return rc;
+    const uint8_t* fc = (const uint8_t*)pl->tcw.ptr("conv1#fc");
+    if (fc && CIC_KNOB("CIC_FIRST_TC", 1))
+      rc = launch_first_conv_tc_c1s2(mask, fc, w.ptr("conv1/bias"), r1.hi, r1.lo, B, H, W, CIC_ACT_LRELU02, tm, c.st);
+    else
+      rc = launch_conv_k3s2_c1(mask, w.ptr("conv1/kernel"), w.ptr("conv1/bias"), r1.hi, r1.lo, B, H, W, CIC_ACT_LRELU02, tm, c.st);
+    if (rc) return rc;
   }
   TcEpilogue e;                                                                                // :513-514
   e.bias = w.ptr("conv2/bias"); e.act = CIC_ACT_LRELU02; e.out_mode = TC_OUT_F32; e.out_hi = r2; e.out_ld = 64;

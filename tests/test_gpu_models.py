@@ -53,8 +53,11 @@ def test_autoencoder_matches_oracle(cic, precision, B, H, W):
     err = np.abs(y - want).max()
     assert err < RECON_TOL[precision], f"max-abs {err}"
     # batch-1 loop of test_autoencoder.py:83-85 gives the same pixels as one batch
+    # (fp32: identical.  tc: the tile geometry of the tensor-core layers follows the batch size, so fp32 partial sums are grouped
+    # differently and a bf16 activation can round the other way - isolated 3x3 patches of pixels move by a few 1e-4.)
     y0 = model.predict(np.expand_dims(x[0], axis=0))[0]
-    np.testing.assert_allclose(y0, y[0], atol=1e-6)
+    np.testing.assert_allclose(y0, y[0], atol=1e-6 if precision == "fp32" else 2e-3)
+    assert np.mean(np.abs(y0 - y[0]) > 1e-6) < 0.05
     # uint8 "quantiser": truncation; 1-LSB flips only where y*255 sits next to an integer
     r = cic.autoencoder.evaluate_batch(model, x)
     y8 = r["compressed_u8"].cpu().numpy()

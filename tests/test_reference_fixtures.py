@@ -101,3 +101,26 @@ def test_cuda_path_matches_reference_adaptive(cic):
     for i in np.flatnonzero(same):
         m = gf.compute_metrics(img[i], out["blended"][i])
         assert abs(m["psnr"] - g["metrics"][i, 0]) < 0.05
+
+
+def _saliency_inputs(synth, g):
+    return synth.to_signed_range(synth.synth_images_u8(3, 256, 256, seed=int(g["seed_inputs"])))
+
+
+def test_oracle_matches_reference_saliency(pure_mods):
+    """oracle/saliency.py (restated from the opencv-contrib source) against the reference's own compute_saliency_map outputs."""
+    from oracle import saliency as osal
+    g = _load("reference_saliency.npz")
+    img = _saliency_inputs(pure_mods[0], g)
+    for method, tol in (("spectral_residual", 1e-3), ("fine_grained", 1.5 / 255), ("combined", 2e-3)):
+        for i in range(3):
+            np.testing.assert_allclose(osal.compute_saliency_map(img[i], method), g[method][i], atol=tol)
+
+
+@pytest.mark.gpu
+def test_cuda_path_matches_reference_saliency(cic):
+    g = _load("reference_saliency.npz")
+    img = _saliency_inputs(cic.synth, g)
+    for method, tol in (("spectral_residual", 1e-3), ("fine_grained", 1.5 / 255), ("combined", 2e-3)):
+        np.testing.assert_allclose(cic.ops.saliency_map(img, method).cpu().numpy(), g[method], atol=tol)
+    np.testing.assert_allclose(cic.ops.saliency_mask_from_image(img).cpu().numpy(), g["masks"], atol=2e-3)

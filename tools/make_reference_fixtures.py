@@ -15,6 +15,8 @@ the seeded synthetic inputs (synth.py: integer-hash images, Gaussian-blob masks)
                            bpp 0.1 / 1.0; hq_encoder / lq_encoder latents (pre-quantisation); compute_metrics(img, blended) (:724)
   reference_autoencoder.npz  build_autoencoder((64,96,3)).predict(x) for 2 images
   reference_metrics.npz    skimage PSNR / SSIM on the uint8 autoencoder convention (test_autoencoder.py:52-66 formulas)
+  reference_saliency.npz   compute_saliency_map (all three methods) and create_saliency_mask(smooth=True) on 3 synthetic 256x256 images
+                           (only where cv2.saliency = opencv-contrib is installed)
 
 tests/test_reference_fixtures.py consumes the files when they exist (CPU test: oracle vs fixture; GPU test: CUDA path vs fixture)
 and skips with a message when they do not.
@@ -155,6 +157,15 @@ def main():
         ga, gb = cv2.cvtColor(a8[i], cv2.COLOR_BGR2GRAY), cv2.cvtColor(b8[i], cv2.COLOR_BGR2GRAY)   # :64-65
         rows.append([mse, psnr, float(structural_similarity(ga, gb, data_range=255))])   # :66
     np.savez_compressed(os.path.join(GOLDEN, "reference_metrics.npz"), a8=a8, b8=b8, rows=np.array(rows, np.float64))
+    # ---- saliency front end (GAN_functions.py:52-121, :159-208; needs opencv-contrib: cv2.saliency) ------------------------------
+    if hasattr(cv2, "saliency"):
+        simg = synth.to_signed_range(synth.synth_images_u8(3, 256, 256, seed=47))
+        sal = {m: np.stack([ref.compute_saliency_map(simg[i], method=m) for i in range(3)]).astype(np.float32)
+               for m in ("spectral_residual", "fine_grained", "combined")}
+        masks = np.stack([ref.create_saliency_mask(sal["combined"][i], smooth=True) for i in range(3)]).astype(np.float32)
+        np.savez_compressed(os.path.join(GOLDEN, "reference_saliency.npz"), seed_inputs=47, masks=masks, **sal)
+    else:
+        print("cv2.saliency (opencv-contrib) is absent: reference_saliency.npz not written")
     import tensorflow as tf                                       # noqa: PLC0415
     import skimage                                                # noqa: PLC0415
     with open(os.path.join(GOLDEN, "reference_versions.txt"), "w") as f:

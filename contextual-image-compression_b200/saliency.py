@@ -5,8 +5,8 @@ pipeline.  They follow the reference operation for operation so that masks (and 
 blended image) are the reference's:
 
   * `compute_saliency_map` runs the two cv2.saliency detectors (opencv-contrib) and their mix on the GPU (`ops.saliency_map`);
-  * `create_saliency_mask(smooth=True)` - the only mode the reference uses (GAN_test.py:280,553) - is plain OpenCV (bilateral
-    9/75/75, Gaussian 31x31, / max); `ops.saliency_mask_smooth` is the same arithmetic on the GPU (§8 f2).
+  * `create_saliency_mask` runs on the GPU in both modes: smooth (bilateral 9/75/75, Gaussian 31x31, / max - the only mode the
+    reference uses, GAN_test.py:280,553) and binary (given or adaptive Otsu / histogram-share threshold) (§8 f2).
 """
 from __future__ import annotations
 
@@ -80,29 +80,18 @@ def compute_saliency_map(image, method="spectral_residual"):
 
 def adaptive_threshold(saliency_map):
     """The threshold create_saliency_mask derives when none is given (GAN_functions.py:172-194): min(Otsu on the uint8 map, the
-    lower edge of the first of 50 histogram bins whose cumulative share exceeds 0.7), clamped to [0.05, 0.5]."""
-    import cv2
-    sal = np.asarray(saliency_map)
-    u8 = (sal * 255).astype(np.uint8) if sal.max() <= 1.0 else sal.astype(np.uint8)
-    otsu, _ = cv2.threshold(u8, 0, 255, cv2.THRESH_BINARY + cv2.THRESH_OTSU)
-    otsu = otsu / 255.0
-    hist, edges = np.histogram(sal.flatten(), 50, range=(0, 1))
-    share = np.cumsum(hist)
-    share = share / share[-1]
-    by_share = edges[np.argmax(share > 0.7)]
-    return max(0.05, min(0.5, min(otsu, by_share)))
+    lower edge of the first of 50 histogram bins whose cumulative share exceeds 0.7), clamped to [0.05, 0.5] - on the device."""
+    from . import ops
+    _, thr = ops.saliency_mask_binary(np.asarray(saliency_map, np.float32), None, return_threshold=True)
+    return float(thr[0].item())
 
 
 def create_saliency_mask(saliency_map, threshold=None, smooth=True):
-    """GAN_functions.py:159-208.  smooth=True: bilateral(9,75,75) -> Gaussian 31x31 -> / max (the threshold is computed and not
-    used in that mode, App. D.5 - skipped here, it has no effect on the result).  smooth=False: binary mask at `threshold`, or
-    at the adaptive threshold of :172-194 when none is given."""
-    import cv2
-    sal = np.asarray(saliency_map)
+    """GAN_functions.py:159-208 on the GPU.  smooth=True: bilateral(9,75,75) -> Gaussian 31x31 -> / max (`ops.saliency_mask_smooth`;
+    the threshold the reference computes first has no effect in that mode, App. D.5, and is skipped).  smooth=False: binary mask at
+    `threshold`, or at the adaptive threshold of :172-194 when none is given (`ops.saliency_mask_binary`).  numpy in, numpy out."""
+    from . import ops
+    sal = np.asarray(saliency_map, np.float32)
     if smooth:
-        mask = cv2.bilateralFilter(sal.astype(np.float32), 9, 75, 75)
-        mask = cv2.GaussianBlur(mask, (31, 31), 0)
-        peak = mask.max()
-        return mask / peak if peak > 0 else mask
-    final_threshold = adaptive_threshold(sal) if threshold is None else threshold
-    return (sal > final_threshold).astype(np.float32)
+        return ops.saliency_mask_smooth(sal).cpu().numpy()
+    return ops.saliency_mask_binary(sal, threshold).cpu().numpy()

@@ -258,6 +258,14 @@ size_t cic_saliency_mask_workspace_bytes(int batch, int h, int w);
 int cic_saliency_mask_smooth(const float* d_saliency, float* d_mask, int batch, int h, int w, void* d_workspace,
                              size_t workspace_bytes, void* stream);
 
+/* create_saliency_mask(saliency_map, threshold, smooth=False) (GAN_functions.py:172-197, :204-206): mask = (map > threshold) as
+ * float32 0 / 1.  adaptive != 0: the threshold of every map is min(Otsu of the uint8 map / 255 (cv2.threshold THRESH_OTSU), lower
+ * edge of the first of 50 np.histogram bins on [0, 1] whose cumulative share exceeds 0.7) clamped to [0.05, 0.5] - computed on the
+ * device and, when d_threshold_out (B,) is not NULL, also returned; adaptive == 0: `threshold` for every map (no workspace). */
+size_t cic_saliency_mask_binary_workspace_bytes(int batch);
+int cic_saliency_mask_binary(const float* d_saliency, float* d_mask, double threshold, int adaptive, double* d_threshold_out, int batch,
+                             int h, int w, void* d_workspace, size_t workspace_bytes, void* stream);
+
 /* compute_saliency_map(image, method) (GAN_functions.py:52-121; called per image and target bpp at GAN_test.py:279, :552 and
  * GAN_train.py:84): cv2.saliency.StaticSaliencySpectralResidual / StaticSaliencyFineGrained (opencv-contrib) on the uint8 image,
  * method 'combined' = 0.6 * spectral + 0.4 * fine (:95), every result divided by its maximum when that is positive (:98-99,

@@ -271,3 +271,63 @@ def compute_saliency_map(image: np.ndarray, method: str = "spectral_residual", u
         raise ValueError(f"Unsupported saliency method: {method}")
     peak = out.max()
     return out / peak if peak > 0 else out
+
+
+# ------------------------------------------------------------------ create_saliency_mask (GAN_functions.py:159-208)
+
+def otsu_u8(u8: np.ndarray) -> int:
+    """getThreshVal_Otsu_8u (imgproc/src/thresh.cpp): the threshold cv2.threshold(u8, 0, 255, THRESH_BINARY + THRESH_OTSU) returns.
+    Pinned on the real call in tests/test_oracle_saliency.py."""
+    h = np.bincount(u8.ravel(), minlength=256).astype(np.int64)
+    scale = 1.0 / u8.size
+    mu = 0.0
+    for i in range(256):
+        mu += i * float(h[i])
+    mu *= scale
+    mu1 = q1 = max_sigma = 0.0
+    max_val = 0
+    eps = float(np.finfo(np.float32).eps)
+    for i in range(256):
+        p_i = h[i] * scale
+        mu1 *= q1
+        q1 += p_i
+        q2 = 1.0 - q1
+        if min(q1, q2) < eps or max(q1, q2) > 1.0 - eps:
+            continue
+        mu1 = (mu1 + i * p_i) / q1
+        mu2 = (mu - q1 * mu1) / q2
+        sigma = q1 * q2 * (mu1 - mu2) * (mu1 - mu2)
+        if sigma > max_sigma:
+            max_sigma, max_val = sigma, i
+    return max_val
+
+
+def adaptive_threshold(saliency_map: np.ndarray, use_cv: bool = True) -> float:
+    """GAN_functions.py:172-194: min(Otsu on the uint8 map / 255, lower edge of the first of 50 histogram bins whose cumulative
+    share exceeds 0.7), clamped to [0.05, 0.5]."""
+    sal = np.asarray(saliency_map)
+    u8 = (sal * 255).astype(np.uint8) if sal.max() <= 1.0 else sal.astype(np.uint8)
+    if use_cv:
+        import cv2
+        otsu, _ = cv2.threshold(u8, 0, 255, cv2.THRESH_BINARY + cv2.THRESH_OTSU)
+    else:
+        otsu = otsu_u8(u8)
+    otsu = otsu / 255.0
+    hist, edges = np.histogram(sal.flatten(), 50, range=(0, 1))
+    share = np.cumsum(hist)
+    share = share / share[-1]
+    by_share = edges[np.argmax(share > 0.7)]
+    return float(max(0.05, min(0.5, min(otsu, by_share))))
+
+
+def create_saliency_mask(saliency_map: np.ndarray, threshold=None, smooth: bool = True) -> np.ndarray:
+    """GAN_functions.py:159-208 with the real OpenCV calls (the threshold is computed and unused when smooth=True, App. D.5)."""
+    import cv2
+    sal = np.asarray(saliency_map)
+    if smooth:
+        mask = cv2.bilateralFilter(sal.astype(np.float32), 9, 75, 75)
+        mask = cv2.GaussianBlur(mask, (31, 31), 0)
+        peak = mask.max()
+        return mask / peak if peak > 0 else mask
+    final_threshold = adaptive_threshold(sal) if threshold is None else threshold
+    return (sal > final_threshold).astype(np.float32)

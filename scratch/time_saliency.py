@@ -38,7 +38,7 @@ for name, b, h, w in (("64x256x256", 64, 256, 256), ("64x512x512", 64, 512, 512)
     n_cpu = 2
     for i in range(n_cpu):
         m = osal.compute_saliency_map(np.ascontiguousarray(bgr[i][..., ::-1]), "combined", use_cv=True)
-        cic.saliency.create_saliency_mask(m, smooth=True)
+        osal.create_saliency_mask(m, smooth=True)
     row["cpu_ms_per_image"] = (time.perf_counter() - t) / n_cpu * 1e3
     row["gpu_mpix_s"] = b * h * w / row["map_and_mask_ms"] / 1e3
     row["cpu_mpix_s"] = h * w / row["cpu_ms_per_image"] / 1e3

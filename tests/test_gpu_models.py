@@ -239,7 +239,7 @@ def test_compress_and_reconstruct_and_rate_control(cic, precision, small_cfg):
     # no mask: the reference's whole front end (compute_saliency_map 'combined' -> create_saliency_mask, GAN_test.py:279-280) on the GPU
     from oracle import saliency as osal
     r2 = gt.compress_and_reconstruct(img[0], models, target_bpp=1.0)
-    want_mask = cic.saliency.create_saliency_mask(osal.compute_saliency_map(img[0], "combined"), smooth=True)   # oracle map, cv2 mask
+    want_mask = osal.create_saliency_mask(osal.compute_saliency_map(img[0], "combined"), smooth=True)   # oracle map, cv2 mask
     np.testing.assert_allclose(r2["saliency_map"], want_mask, atol=1e-4)
     want2 = graphs.adaptive_forward(ws, img[:1], want_mask[None, :, :, None], np.array([[1.0]], np.float32))
     assert abs(r2["hq_ratio"] - want2[4].mean()) < 1e-4

@@ -360,8 +360,10 @@ def test_saliency_mask_smooth_matches_opencv(cic, b, h, w):
         maps.append((m / m.max()).astype(np.float32))
     maps = np.stack(maps)
     got = cic.ops.saliency_mask_smooth(maps).cpu().numpy()
+    from oracle import saliency as osal
+    np.testing.assert_array_equal(cic.saliency.create_saliency_mask(maps[0], smooth=True), got[0])   # the drop-in name: numpy in / out
     for i in range(b):
-        want = cic.saliency.create_saliency_mask(maps[i], smooth=True)           # the cv2 calls
+        want = osal.create_saliency_mask(maps[i], smooth=True)                    # the cv2 calls
         assert got[i].max() == pytest.approx(1.0, abs=1e-6)
         np.testing.assert_allclose(got[i], want, atol=1e-5)
     flat = np.full((1, 40, 40), 0.25, np.float32)                               # value range < FLT_EPSILON: bilateral copies, max-normalised to 1
@@ -411,8 +413,43 @@ def test_saliency_map_degenerate_inputs(cic):
     for i in range(3):
         one = cic.ops.saliency_mask_from_image(rgb[i]).cpu().numpy()
         np.testing.assert_array_equal(masks[i], one)
-        want = cic.saliency.create_saliency_mask(osal.compute_saliency_map(rgb[i], "combined"), smooth=True)
+        want = osal.create_saliency_mask(osal.compute_saliency_map(rgb[i], "combined"), smooth=True)
         np.testing.assert_allclose(masks[i], want, atol=1e-4)
+
+
+def test_saliency_mask_binary_matches_opencv_and_numpy(cic):
+    """cic_saliency_mask_binary (create_saliency_mask(smooth=False), GAN_functions.py:172-197, :204-206) against the reference's own
+    lines run with the REAL cv2.threshold(THRESH_OTSU) and np.histogram (oracle.saliency.adaptive_threshold)."""
+    from oracle import saliency as osal
+    rng = np.random.default_rng(5)
+    maps = []
+    for t in range(12):
+        h, w = 40 + 13 * t, 64 + 7 * t
+        kind = t % 4
+        if kind == 0:
+            m = rng.random((h, w)) ** rng.uniform(0.3, 4)
+        elif kind == 1:
+            m = (rng.random((h, w)) > rng.random()) * rng.random()
+        elif kind == 2:
+            m = np.clip(rng.normal(rng.random(), 0.2, (h, w)), 0, 1)
+        else:
+            m = np.round(rng.random((h, w)) * 8) / 8              # values on bin edges (0.125 k), 1.0 included
+        maps.append(m.astype(np.float32))
+    for m in maps:
+        want_thr = osal.adaptive_threshold(m)
+        got, thr = cic.ops.saliency_mask_binary(m, None, return_threshold=True)
+        assert thr[0].item() == want_thr
+        np.testing.assert_array_equal(got.cpu().numpy(), osal.create_saliency_mask(m, smooth=False))
+        np.testing.assert_array_equal(cic.saliency.create_saliency_mask(m, smooth=False), got.cpu().numpy())
+        assert cic.saliency.adaptive_threshold(m) == want_thr
+        np.testing.assert_array_equal(cic.saliency.create_saliency_mask(m, threshold=0.3, smooth=False), (m > 0.3).astype(np.float32))
+    batch = np.stack([rng.random((48, 80)).astype(np.float32) ** (1 + i) for i in range(5)])
+    got, thr = cic.ops.saliency_mask_binary(batch, None, return_threshold=True)
+    for i in range(5):
+        assert thr[i].item() == osal.adaptive_threshold(batch[i])
+        np.testing.assert_array_equal(got[i].cpu().numpy(), (batch[i] > thr[i].item()).astype(np.float32))
+    big = (rng.random((32, 32)) * 300).astype(np.float32)         # maximum above 1: cast to uint8 as is (:176-177), wraps like numpy
+    assert cic.saliency.adaptive_threshold(big) == osal.adaptive_threshold(big)
 
 
 def _jpeg_image(h, w, kind, seed):

@@ -74,3 +74,23 @@ def test_against_opencv_contrib_when_present(h, w):
     ok, fg = cv2.saliency.StaticSaliencyFineGrained_create().computeSaliency(bgr)
     assert ok
     np.testing.assert_allclose(S.fine_grained_np(bgr), fg, atol=1.5 / 255)
+
+
+def test_otsu_restatement_matches_opencv():
+    """oracle.saliency.otsu_u8 (getThreshVal_Otsu_8u restated; the CUDA threshold kernel follows it) against cv2.threshold."""
+    rng = np.random.default_rng(0)
+    for t in range(120):
+        h, w = rng.integers(8, 160, 2)
+        kind = t % 4
+        if kind == 0:
+            m = rng.random((h, w)) ** rng.uniform(0.3, 4)
+        elif kind == 1:
+            m = (rng.random((h, w)) > rng.random()) * rng.random()
+        elif kind == 2:
+            m = np.clip(rng.normal(rng.random(), 0.2, (h, w)), 0, 1)
+        else:
+            m = np.round(rng.random((h, w)) * rng.integers(2, 9)) / 8
+        u8 = (m.astype(np.float32) * 255).astype(np.uint8)
+        want, _ = cv2.threshold(u8, 0, 255, cv2.THRESH_BINARY + cv2.THRESH_OTSU)
+        assert S.otsu_u8(u8) == int(want)
+        assert S.adaptive_threshold(m.astype(np.float32), use_cv=False) == S.adaptive_threshold(m.astype(np.float32), use_cv=True)

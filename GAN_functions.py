@@ -10,7 +10,7 @@ from cic_b200.gan import (  # noqa: F401
     AdaptiveQuantizationLayer, SelfAttention, build_adaptive_compression_model, build_encoder, build_generator,
     build_latent_saliency_model, build_rate_distortion_optimizer, compute_metrics, estimate_compression_ratio)
 from cic_b200.saliency import (  # noqa: F401
-    compute_saliency_map, create_directories, create_saliency_mask, load_and_preprocess_image, save_image)
+    compute_saliency_map, create_directories, create_saliency_mask, enhance_saliency_map, load_and_preprocess_image, save_image)
 
 
 def _out_of_scope(name, why):
@@ -22,6 +22,5 @@ def _out_of_scope(name, why):
 
 build_discriminator = _out_of_scope("build_discriminator", "training only (GAN_train.py:154)")
 SpectralNormalization = _out_of_scope("SpectralNormalization", "dead code in the reference (never instantiated)")
-enhance_saliency_map = _out_of_scope("enhance_saliency_map", "never called by the reference")
 visualize_results = _out_of_scope("visualize_results", "matplotlib plotting")
 visualize_bit_allocation_by_bpp = _out_of_scope("visualize_bit_allocation_by_bpp", "matplotlib plotting")

@@ -91,6 +91,8 @@ PROTOTYPES = {
     "cic_symbol_entropy_bits": (_i, [_vp, _vp, _i, _i, _vp]),
     "cic_saliency_mask_workspace_bytes": (_sz, [_i, _i, _i]),
     "cic_saliency_mask_smooth": (_i, [_vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
+    "cic_saliency_enhance_workspace_bytes": (_sz, [_i, _i, _i]),
+    "cic_saliency_enhance": (_i, [_vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
     "cic_saliency_mask_binary_workspace_bytes": (_sz, [_i]),
     "cic_saliency_mask_binary": (_i, [_vp, _vp, C.c_double, _i, _vp, _i, _i, _i, _vp, _sz, _vp]),
     "cic_saliency_map_workspace_bytes": (_sz, [_i, _i, _i]),

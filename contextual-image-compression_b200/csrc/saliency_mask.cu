@@ -140,6 +140,36 @@ sal_scale_kernel(float* __restrict__ y, const float* __restrict__ mm, int hw) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += gridDim.x * blockDim.x) p[i] = __fdiv_rn(p[i], mx);
 }
 
+// ---- enhance_saliency_map (GAN_functions.py:123-157): bilateral -> Gaussian 3 / 9 / 15 -> 0.5 / 0.3 / 0.2 mix -> ^0.8 -> clip ------
+struct GaussTaps { float g[15]; int k; };
+
+// one separable pass with up to 15 float32 taps (cv2.GaussianBlur on CV_32F: float32 coefficients, BORDER_REFLECT_101)
+__global__ void __launch_bounds__(256)
+sal_gauss_kernel(const float* __restrict__ x, float* __restrict__ y, int H, int W, int axis, GaussTaps t) {
+  const int b = blockIdx.y, r = t.k >> 1;
+  const float* src = x + (size_t)b * H * W;
+  float* dst = y + (size_t)b * H * W;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H * W; i += gridDim.x * blockDim.x) {
+    const int py = i / W, px = i % W;
+    float acc = 0.f;
+    for (int k = 0; k < t.k; ++k) {
+      const float v = axis == 0 ? __ldg(src + (size_t)py * W + reflect101(px + k - r, W)) : __ldg(src + (size_t)reflect101(py + k - r, H) * W + px);
+      acc = fmaf(t.g[k], v, acc);
+    }
+    dst[i] = acc;
+  }
+}
+
+// acc (+)= w * g (float32, the reference's `enhanced_map += weights[i] * scale_map`); last: ^0.8 and clip to [0, 1]
+__global__ void __launch_bounds__(256)
+sal_enhance_mix_kernel(const float* __restrict__ g, float* __restrict__ acc, float w, int first, int last, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float a = __fadd_rn(first ? 0.f : acc[i], __fmul_rn(w, __ldg(g + i)));
+    if (last) a = fminf(fmaxf(powf(a, 0.8f), 0.f), 1.f);
+    acc[i] = a;
+  }
+}
+
 // ---- create_saliency_mask(smooth=False) and the adaptive threshold (GAN_functions.py:172-194, :204-206) -----------------------
 // hist[b]: 256 bins of the uint8 map ((uchar)(x * 255) when the map's maximum is <= 1, else (uchar)x) and 50 bins of
 // np.histogram(x, 50, range=(0, 1)) (a value belongs to the bin whose float32 edges float32(i * 0.02) enclose it; 1.0 goes to the last bin)
@@ -216,6 +246,61 @@ sal_binary_kernel(const float* __restrict__ x, float* __restrict__ y, const doub
 }  // namespace cic
 
 using namespace cic;
+
+extern "C" size_t cic_saliency_enhance_workspace_bytes(int batch, int h, int w) {
+  if (batch <= 0 || h <= 0 || w <= 0) return 0;
+  return 3 * (((size_t)batch * h * w * sizeof(float) + 255) & ~(size_t)255) + (((size_t)batch * 2 * sizeof(float) + 255) & ~(size_t)255) + 256;
+}
+
+extern "C" int cic_saliency_enhance(const float* d_saliency, float* d_out, int batch, int h, int w, void* d_workspace, size_t workspace_bytes,
+                                    void* stream) {
+  CIC_REQUIRE(batch >= 0 && h > 0 && w > 0, "cic_saliency_enhance: bad shape");
+  if (batch == 0) return CIC_OK;
+  CIC_REQUIRE(d_saliency && d_out, "cic_saliency_enhance: null pointer");
+  CIC_REQUIRE(batch <= 65535, "cic_saliency_enhance: at most 65535 maps per call");
+  CIC_REQUIRE(d_workspace && workspace_bytes >= cic_saliency_enhance_workspace_bytes(batch, h, w), "cic_saliency_enhance: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t plane = ((size_t)batch * h * w * sizeof(float) + 255) & ~(size_t)255;
+  float* filt = (float*)d_workspace;                       // bilateral output
+  float* t0 = (float*)((char*)d_workspace + plane);
+  float* t1 = (float*)((char*)d_workspace + 2 * plane);
+  float* mm = (float*)((char*)d_workspace + 3 * plane);
+  const int hw = h * w;
+  const size_t n = (size_t)batch * hw;
+  const int blocks = (hw + 255) / 256 < sm_count() * 4 ? (hw + 255) / 256 : sm_count() * 4;
+  sal_minmax_init_kernel<<<(batch + 127) / 128, 128, 0, st>>>(mm, batch);
+  sal_minmax_kernel<<<dim3(blocks, batch), 256, 0, st>>>(d_saliency, mm, hw);
+  const float coeff = (float)(-0.5 / (75.0 * 75.0));       // cv2.bilateralFilter(map, 9, 75, 75)
+  sal_bilateral_kernel<<<dim3((w + BL_T - 1) / BL_T, (h + BL_T - 1) / BL_T, batch), 256, 0, st>>>(d_saliency, filt, mm, h, w, coeff, coeff);
+  int launches = 3;
+  // cv2.getGaussianKernel(k, 0, CV_32F): fixed tables for k = 3 and 9 (OpenCV's bit-exact small kernels), the formula with
+  // sigma = 0.3 ((k - 1) / 2 - 1) + 0.8 = 2.6 for k = 15
+  const int ks[3] = {3, 9, 15};
+  const float wts[3] = {0.5f, 0.3f, 0.2f};
+  for (int s = 0; s < 3; ++s) {
+    GaussTaps t;
+    t.k = ks[s];
+    if (ks[s] == 3) {
+      const float g3[3] = {0.25f, 0.5f, 0.25f};
+      for (int i = 0; i < 3; ++i) t.g[i] = g3[i];
+    } else if (ks[s] == 9) {
+      const int g9[9] = {4, 13, 30, 51, 60, 51, 30, 13, 4};
+      for (int i = 0; i < 9; ++i) t.g[i] = (float)g9[i] / 256.f;
+    } else {
+      double e[15], sum = 0.0;
+      for (int i = 0; i < 15; ++i) { const double d = i - 7; e[i] = std::exp(-d * d / (2.0 * 2.6 * 2.6)); sum += e[i]; }
+      for (int i = 0; i < 15; ++i) t.g[i] = (float)(e[i] / sum);
+    }
+    sal_gauss_kernel<<<dim3(blocks, batch), 256, 0, st>>>(filt, t0, h, w, 0, t);
+    sal_gauss_kernel<<<dim3(blocks, batch), 256, 0, st>>>(t0, t1, h, w, 1, t);
+    const size_t mb = (n + 255) / 256;
+    sal_enhance_mix_kernel<<<(unsigned)(mb < (size_t)sm_count() * 8 ? mb : (size_t)sm_count() * 8), 256, 0, st>>>(t1, d_out, wts[s], s == 0, s == 2, n);
+    launches += 3;
+  }
+  for (int i = 0; i < launches; ++i) CIC_COUNT_LAUNCH();
+  CIC_CHECK_LAUNCH("saliency enhance kernels");
+  return CIC_OK;
+}
 
 extern "C" size_t cic_saliency_mask_binary_workspace_bytes(int batch) {
   if (batch <= 0) return 0;

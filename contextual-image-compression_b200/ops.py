@@ -216,6 +216,22 @@ def saliency_mask_smooth(saliency_map) -> torch.Tensor:
     return y[0] if single else y
 
 
+def saliency_enhance(saliency_map) -> torch.Tensor:
+    """enhance_saliency_map(saliency_map) (GAN_functions.py:123-157) on the device: bilateral(9, 75, 75) -> Gaussian 3 / 9 / 15 mixed
+    0.5 / 0.3 / 0.2 -> ^0.8 -> clip.  (H,W) or (B,H,W) -> float32 of the same shape."""
+    x = to_device_f32(saliency_map)
+    single = x.dim() == 2
+    if single:
+        x = x.unsqueeze(0)
+    if x.dim() != 3:
+        raise ValueError(f"saliency map must be (H,W) or (B,H,W), got {tuple(x.shape)}")
+    b, h, w = x.shape
+    y = torch.empty_like(x)
+    ws = torch.empty(int(_lib.lib.cic_saliency_enhance_workspace_bytes(b, h, w)), dtype=torch.uint8, device=x.device)
+    _lib.check(_lib.lib.cic_saliency_enhance(ptr(x), ptr(y), b, h, w, ptr(ws), ws.numel(), runtime.stream_ptr()))
+    return y[0] if single else y
+
+
 def saliency_mask_binary(saliency_map, threshold=None, return_threshold: bool = False):
     """create_saliency_mask(saliency_map, threshold, smooth=False) (GAN_functions.py:172-197, :204-206) on the device: the map
     compared with `threshold`, or with the reference's adaptive threshold (OpenCV's Otsu on the uint8 map vs the 70 % share of a

@@ -78,6 +78,12 @@ def compute_saliency_map(image, method="spectral_residual"):
     return ops.saliency_map(image, method).cpu().numpy()
 
 
+def enhance_saliency_map(saliency_map):
+    """GAN_functions.py:123-157 on the GPU (`ops.saliency_enhance`); the reference defines it and never calls it."""
+    from . import ops
+    return ops.saliency_enhance(np.asarray(saliency_map, np.float32)).cpu().numpy()
+
+
 def adaptive_threshold(saliency_map):
     """The threshold create_saliency_mask derives when none is given (GAN_functions.py:172-194): min(Otsu on the uint8 map, the
     lower edge of the first of 50 histogram bins whose cumulative share exceeds 0.7), clamped to [0.05, 0.5] - on the device."""

@@ -258,6 +258,13 @@ size_t cic_saliency_mask_workspace_bytes(int batch, int h, int w);
 int cic_saliency_mask_smooth(const float* d_saliency, float* d_mask, int batch, int h, int w, void* d_workspace,
                              size_t workspace_bytes, void* stream);
 
+/* enhance_saliency_map(saliency_map) (GAN_functions.py:123-157; defined by the reference, called nowhere in it):
+ * cv2.bilateralFilter(map, 9, 75, 75) -> cv2.GaussianBlur with 3x3, 9x9 and 15x15 kernels (sigma 0) mixed 0.5 / 0.3 / 0.2 -> ^0.8 ->
+ * clip to [0, 1].  d_saliency, d_out (B,H,W) float32, may not alias. */
+size_t cic_saliency_enhance_workspace_bytes(int batch, int h, int w);
+int cic_saliency_enhance(const float* d_saliency, float* d_out, int batch, int h, int w, void* d_workspace, size_t workspace_bytes,
+                         void* stream);
+
 /* create_saliency_mask(saliency_map, threshold, smooth=False) (GAN_functions.py:172-197, :204-206): mask = (map > threshold) as
  * float32 0 / 1.  adaptive != 0: the threshold of every map is min(Otsu of the uint8 map / 255 (cv2.threshold THRESH_OTSU), lower
  * edge of the first of 50 np.histogram bins on [0, 1] whose cumulative share exceeds 0.7) clamped to [0.05, 0.5] - computed on the

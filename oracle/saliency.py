@@ -331,3 +331,13 @@ def create_saliency_mask(saliency_map: np.ndarray, threshold=None, smooth: bool 
         return mask / peak if peak > 0 else mask
     final_threshold = adaptive_threshold(sal) if threshold is None else threshold
     return (sal > final_threshold).astype(np.float32)
+
+
+def enhance_saliency_map(saliency_map: np.ndarray) -> np.ndarray:
+    """GAN_functions.py:123-157 with the real OpenCV calls."""
+    import cv2
+    filtered = cv2.bilateralFilter(saliency_map.astype(np.float32), 9, 75, 75)
+    enhanced = np.zeros_like(saliency_map)
+    for scale, weight in zip((3, 9, 15), (0.5, 0.3, 0.2)):
+        enhanced += weight * cv2.GaussianBlur(filtered, (scale, scale), 0)
+    return np.clip(np.power(enhanced, 0.8), 0, 1)

@@ -452,6 +452,22 @@ def test_saliency_mask_binary_matches_opencv_and_numpy(cic):
     assert cic.saliency.adaptive_threshold(big) == osal.adaptive_threshold(big)
 
 
+@pytest.mark.parametrize("b,h,w", [(2, 128, 160), (1, 37, 61)])
+def test_saliency_enhance_matches_opencv(cic, b, h, w):
+    """cic_saliency_enhance (enhance_saliency_map, GAN_functions.py:123-157) against the reference's lines on the real OpenCV."""
+    from oracle import saliency as osal
+    rng = np.random.default_rng(h)
+    yy, xx = np.mgrid[0:h, 0:w]
+    maps = np.stack([(0.05 * rng.random((h, w)) + np.exp(-((yy - rng.uniform(0, h)) ** 2 + (xx - rng.uniform(0, w)) ** 2) / (2 * 20.0 ** 2))).astype(np.float32)
+                     for _ in range(b)])
+    maps /= maps.max()
+    got = cic.ops.saliency_enhance(maps).cpu().numpy()
+    for i in range(b):
+        np.testing.assert_allclose(got[i], osal.enhance_saliency_map(maps[i]), atol=2e-6)
+    import GAN_functions as gf
+    np.testing.assert_array_equal(gf.enhance_saliency_map(maps[0]), got[0])
+
+
 def _jpeg_image(h, w, kind, seed):
     from test_oracle_extras import _jpeg_test_image
     return _jpeg_test_image(h, w, kind, seed)

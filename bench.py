@@ -101,14 +101,56 @@ class ClockSampler:
                                          stderr=subprocess.DEVNULL, text=True)
         except Exception as e:  # noqa: BLE001
             self.err = repr(e)
+        # second sampler, used only when the NVML child produced nothing (seen once in ~40 runs: the child died before its first
+        # line): the profiling recipe's nvidia-smi loop
+        self.smi = None
+        try:
+            import subprocess
+            self.smi = subprocess.Popen(
+                ["nvidia-smi", f"--id={index}", "--query-gpu=timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap",
+                 "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:  # noqa: BLE001
+            self.smi = None
 
     def start(self):
         self.t0 = time.time()
 
+    def _smi_samples(self, t1):
+        """(inside clocks, all (t, clock), max clock, reasons) from the nvidia-smi loop."""
+        import datetime
+        if self.smi is None:
+            return [], [], None, set()
+        self.smi.terminate()
+        try:
+            out, _ = self.smi.communicate(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.smi.kill()
+            out, _ = self.smi.communicate()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        inside, allc, mx, reasons = [], [], None, set()
+        for ln in out.splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) != 7:
+                continue
+            try:
+                t = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                c, mx = int(f[1]), int(f[2])
+            except ValueError:
+                continue
+            allc.append((t, c))
+            if self.t0 <= t <= t1:
+                inside.append(c)
+                reasons.update(n for n, v in zip(names, f[3:]) if v.lower().startswith("active"))
+        return inside, allc, mx, reasons
+
     def stop(self):
         t1 = time.time()
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "error": self.err}
+            s_inside, s_all, s_mx, s_reasons = self._smi_samples(t1)
+            med = float(np.median(s_inside)) if s_inside else None
+            return {"sm_mhz": med, "sm_max_mhz": s_mx, "reasons": sorted(s_reasons), "samples": len(s_inside), "source": "nvidia-smi -lms 100",
+                    "error": self.err}
         time.sleep(0.02)
         self.proc.terminate()
         try:
@@ -128,11 +170,15 @@ class ClockSampler:
                     inside.append(c)
                     if f[2] != "-":
                         reasons.update(f[2].split(","))
+        source = "nvml"
+        s_inside, s_all, s_mx, s_reasons = self._smi_samples(t1)
+        if not allc and s_all:
+            inside, allc, mx, reasons, source = s_inside, s_all, s_mx, s_reasons, "nvidia-smi -lms 100"
         if not inside and allc:  # region shorter than one sampling period: the sample nearest to its middle
             mid = 0.5 * (self.t0 + t1)
             inside = [min(allc, key=lambda tc: abs(tc[0] - mid))[1]]
         med = float(np.median(inside)) if inside else None
-        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(inside)}
+        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(inside), "source": source}
 
 
 # ---- workloads -------------------------------------------------------------------------------------------------------------------

@@ -23,6 +23,7 @@ constexpr int FC_N = 32;                       // output channels
 constexpr int FC_ROWB = 128;                   // bytes per A / B row (K = 64 bf16)
 constexpr int FC_ABYTES = TC_BM * FC_ROWB;     // one A part (16 KB)
 constexpr int FC_MAX_PATCH = 2304;             // floats
+constexpr int FC_CTAS = 3;                     // CTAs per SM: one A buffer (32 KB) + weights + patch = 51 KB of shared memory, <= 75 registers
 
 struct FirstConvParams {
   const float* x;
@@ -60,13 +61,13 @@ __device__ __forceinline__ uint32_t fc_bf16x2_max(uint32_t a, uint32_t b) {
 }
 
 template <int CIN, int KS, int STRIDE, bool POOL, bool SPLIT>
-__global__ void __launch_bounds__(288, 2)
+__global__ void __launch_bounds__(288, FC_CTAS)
 first_conv_tc_kernel(const __grid_constant__ FirstConvParams p) {
   constexpr int NK = KS * KS * CIN, KCH = (NK + 7) / 8, KSTEPS = (NK + 15) / 16, ROWF = KS * CIN;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* a_buf = smem;                                   // [2 buffers][hi | lo][128 rows x 128 B]
-  uint8_t* b_img = smem + 4 * FC_ABYTES;                   // [hi | lo][32 rows x 128 B]
+  uint8_t* a_buf = smem;                                   // [hi | lo][128 rows x 128 B] (one buffer: the 3-9 MMAs of a tile retire long before the next tile is split)
+  uint8_t* b_img = smem + 2 * FC_ABYTES;                   // [hi | lo][32 rows x 128 B]
   float* patch = reinterpret_cast<float*>(b_img + 2 * FC_N * FC_ROWB);
   uint64_t* a_full = reinterpret_cast<uint64_t*>(patch + FC_MAX_PATCH + 8);
   uint64_t* a_empty = a_full + 2;
@@ -79,11 +80,11 @@ first_conv_tc_kernel(const __grid_constant__ FirstConvParams p) {
   // resident weights; zero A buffers (rows of invalid pixels and the K padding are never written again)
   for (int i = threadIdx.x; i < 2 * FC_N * FC_ROWB / 16; i += blockDim.x)
     reinterpret_cast<uint4*>(b_img)[i] = __ldg(reinterpret_cast<const uint4*>(p.wimg) + i);
-  for (int i = threadIdx.x; i < 4 * FC_ABYTES / 16; i += blockDim.x) reinterpret_cast<uint4*>(a_buf)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < 2 * FC_ABYTES / 16; i += blockDim.x) reinterpret_cast<uint4*>(a_buf)[i] = make_uint4(0, 0, 0, 0);
   if (warp == 4) {
     if (lane == 0) {
       for (int s = 0; s < 2; ++s) {
-        mbar_init(&a_full[s], 128); mbar_init(&a_empty[s], 1);
+        mbar_init(&a_full[s], 128); mbar_init(&a_empty[s], 1);   // (only [0] is used)
         mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 4);
       }
       fence_barrier_init();
@@ -174,10 +175,9 @@ first_conv_tc_kernel(const __grid_constant__ FirstConvParams p) {
       }
       fc_named_bar_sync(1, 128);  // everyone holds its patch values in registers: the staging buffer is free again
       if (t + (int)gridDim.x < p.total_tiles) lead_next = stage(t + gridDim.x);
-      const int buf = lt & 1;
-      mbar_wait(&a_empty[buf], (((uint32_t)lt >> 1) & 1u) ^ 1u);  // the MMAs that read this buffer have retired
+      mbar_wait(&a_empty[0], ((uint32_t)lt & 1u) ^ 1u);  // the MMAs of the previous tile have retired
       if (row_ok) {
-        uint8_t* row_hi = a_buf + (size_t)buf * 2 * FC_ABYTES + (size_t)r * FC_ROWB;
+        uint8_t* row_hi = a_buf + (size_t)r * FC_ROWB;
         uint8_t* row_lo = row_hi + FC_ABYTES;
 #pragma unroll
         for (int c = 0; c < KCH; ++c) {
@@ -196,7 +196,7 @@ first_conv_tc_kernel(const __grid_constant__ FirstConvParams p) {
         }
       }
       fc_fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
-      mbar_arrive(&a_full[buf]);
+      mbar_arrive(&a_full[0]);
     }
   } else if (warp == 4) {
     // ===== MMA issuer =====
@@ -207,11 +207,11 @@ first_conv_tc_kernel(const __grid_constant__ FirstConvParams p) {
       const int buf = lt & 1;
       const uint32_t ph = ((uint32_t)lt >> 1) & 1u;
       mbar_wait(&tmem_empty_bar[buf], ph ^ 1u);
-      mbar_wait(&a_full[buf], ph);
+      mbar_wait(&a_full[0], (uint32_t)lt & 1u);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t d = tmem_base + (uint32_t)(buf * FC_N);
-        const uint32_t a_hi = a_lo0 + (uint32_t)buf * (2 * FC_ABYTES >> 4), a_lo = a_hi + (FC_ABYTES >> 4);
+        const uint32_t a_hi = a_lo0, a_lo = a_hi + (FC_ABYTES >> 4);
         const uint32_t b_hi = b_lo0, b_lo = b_lo0 + (uint32_t)(FC_N * FC_ROWB >> 4);
 #pragma unroll
         for (int k = 0; k < KSTEPS; ++k) umma_bf16(d, umma_desc_from_lo<64>(a_hi + 2 * k), umma_desc_from_lo<64>(b_hi + 2 * k), idesc, k != 0);
@@ -219,7 +219,7 @@ first_conv_tc_kernel(const __grid_constant__ FirstConvParams p) {
         for (int k = 0; k < KSTEPS; ++k) umma_bf16(d, umma_desc_from_lo<64>(a_lo + 2 * k), umma_desc_from_lo<64>(b_hi + 2 * k), idesc, 1u);
 #pragma unroll
         for (int k = 0; k < KSTEPS; ++k) umma_bf16(d, umma_desc_from_lo<64>(a_hi + 2 * k), umma_desc_from_lo<64>(b_lo + 2 * k), idesc, 1u);
-        umma_commit(&a_empty[buf]);
+        umma_commit(&a_empty[0]);
         umma_commit(&tmem_full_bar[buf]);
       }
       __syncwarp();
@@ -345,13 +345,13 @@ static int launch_first_conv(FirstConvParams& p, const char* name, cudaStream_t 
   const size_t row_floats = (size_t)(p.tm.tiles_x ? p.tm.IW : p.W) * CIN;
   p.fast = ((p.W * CIN) & 3) == 0 && (row_floats & 3) == 0 && (reinterpret_cast<uintptr_t>(p.x) & 15) == 0 &&
            (p.tm.tiles_x || (((size_t)p.H * p.W * CIN) & 3) == 0);
-  const size_t smem = 4 * FC_ABYTES + 2 * FC_N * FC_ROWB + (FC_MAX_PATCH + 8) * sizeof(float) + 128 + 1024;
+  const size_t smem = 2 * FC_ABYTES + 2 * FC_N * FC_ROWB + (FC_MAX_PATCH + 8) * sizeof(float) + 128 + 1024;
   static DeviceOnce attr_set;  // function attributes are per device
   if (attr_set.todo()) {
     CIC_CHECK_CUDA(cudaFuncSetAttribute(first_conv_tc_kernel<CIN, KS, STRIDE, POOL, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set.done();
   }
-  const int slots = 2 * sm_count();
+  const int slots = FC_CTAS * sm_count();
   first_conv_tc_kernel<CIN, KS, STRIDE, POOL, SPLIT><<<p.total_tiles < slots ? p.total_tiles : slots, 288, smem, st>>>(p);
   CIC_COUNT_LAUNCH();
   CIC_CHECK_LAUNCH(name);

@@ -307,3 +307,49 @@ def test_import_shim_does_not_duplicate_modules(cic):
     assert importlib.import_module("contextual-image-compression_b200.models") is m2
     assert importlib.import_module("contextual-image-compression_b200.runtime") is r2 and cic.runtime is r2 and m2.runtime is r2
     assert GAN_functions.build_encoder.__module__ == "contextual-image-compression_b200.gan"
+
+
+def test_bench_clock_sampler_falls_back_to_the_nvidia_smi_loop():
+    """bench.py's clock block: when the NVML child produced nothing, the samples of the nvidia-smi loop that fall inside the timed
+    region are used (median clock, throttle reasons that were Active)."""
+    import importlib.util
+    import time
+    import datetime
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_for_test", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+
+    class Fake:
+        def __init__(self, out):
+            self.out = out
+
+        def terminate(self):
+            pass
+
+        def kill(self):
+            pass
+
+        def communicate(self, timeout=None):
+            return self.out, ""
+
+    now = time.time()
+    stamp = lambda t: datetime.datetime.fromtimestamp(t).strftime("%Y/%m/%d %H:%M:%S.%f")[:-3]   # noqa: E731
+    lines = [f"{stamp(now - 5.0)}, 1965, 1965, Not Active, Not Active, Not Active, Not Active",
+             f"{stamp(now + 0.10)}, 1650, 1965, Not Active, Not Active, Not Active, Active",
+             f"{stamp(now + 0.20)}, 1700, 1965, Not Active, Not Active, Not Active, Active",
+             f"{stamp(now + 0.30)}, 1680, 1965, Not Active, Not Active, Not Active, Not Active",
+             "garbage line"]
+    s = bench.ClockSampler.__new__(bench.ClockSampler)
+    s.proc, s.err, s.smi = Fake(""), None, Fake("\n".join(lines) + "\n")
+    s.t0 = now
+    time.sleep(0.45)
+    got = s.stop()
+    assert got["source"].startswith("nvidia-smi") and got["samples"] == 3
+    assert got["sm_mhz"] == 1680.0 and got["sm_max_mhz"] == 1965 and got["reasons"] == ["sw_power_cap"]
+    # the NVML child's samples win when it produced any
+    s = bench.ClockSampler.__new__(bench.ClockSampler)
+    s.proc, s.err, s.smi = Fake(f"max 1965\n{now + 0.1!r} 1800 sw_power_cap\n"), None, Fake("\n".join(lines) + "\n")
+    s.t0 = now
+    got = s.stop()
+    assert got["source"] == "nvml" and got["sm_mhz"] == 1800.0

@@ -8,9 +8,12 @@
 // made visible to the tensor core with fence.proxy.async).  The weights of both encoders ([128][64] bf16 hi/lo,
 // pre-swizzled at plan creation) stay resident in shared memory, so one 3-term split MMA group
 // (hi*hi + lo*hi + hi*lo, 12 tcgen05.mma, fp32 accumulate in TMEM) produces 128 pixels x (64 + 64) channels and
-// the image is read once for both encoders.  A and the accumulator are double-buffered; builders, the MMA warp and
-// the four epilogue warps (tcgen05.ld -> bias -> LeakyReLU -> bf16 hi/lo -> global) overlap across tiles; two CTAs
-// per SM.  This replaces two runs of the CUDA-core direct kernel (direct_conv.cu), which is FFMA-issue-bound
+// the image is read once for both encoders.  Builders, the MMA warp and the four epilogue warps (tcgen05.ld -> bias -> LeakyReLU ->
+// bf16 hi/lo -> global) of a CTA work on consecutive tiles; r02: ONE A buffer and ONE accumulator per CTA (the 12 MMAs of a tile
+// take ~0.3 us of the ~2 us a tile spends in the builders and the epilogue) and 2 x 64 pixel tiles (9 KB patch) keep a CTA at
+// 74 KB of shared memory, 128 TMEM columns and 72 registers, so THREE CTAs share an SM - the kernel is bound by how many warps
+// hide the epilogue's dependent chains (profiles/r02_ncu_conv1.md), and the co-resident CTAs overlap what the buffers did not.
+// This replaces two runs of the CUDA-core direct kernel (direct_conv.cu), which is FFMA-issue-bound
 // (3-register FFMA issues at half rate) at ~16 TFLOP/s.
 #include "plan.cuh"
 #include "tc_gemm.cuh"
@@ -20,7 +23,8 @@ namespace cic {
 constexpr int C1_K = 64;             // padded K
 constexpr int C1_ROWB = C1_K * 2;    // bytes per A / B row
 constexpr int C1_ABYTES = TC_BM * C1_ROWB;  // one A part (16 KB)
-constexpr int C1_MAX_PATCH = 4 * 194 * 4;   // floats: TW = 128, TH = 1 staged as 194 16-byte chunks per row (4 * 258 * 3 + padding)
+constexpr int C1_MAX_PATCH = 2400;          // floats: TW = 64, TH = 2 staged as 6 rows of 98 16-byte chunks (2352)
+constexpr int C1_CTAS = 3;                  // CTAs per SM: one A buffer + both encoders' weights + patch = 74 KB of shared memory
 
 struct Conv1Params {
   const float* x;
@@ -64,12 +68,12 @@ __device__ __forceinline__ void quad_transpose16(uint32_t (&p)[16], int lane) {
 }
 
 template <int N>
-__global__ void __launch_bounds__(288, 2)
+__global__ void __launch_bounds__(288, C1_CTAS)
 conv1_tc_kernel(const __grid_constant__ Conv1Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* a_buf = smem;                                   // [2 buffers][hi | lo][128 rows x 128 B]
-  uint8_t* b_img = smem + 4 * C1_ABYTES;                   // [hi | lo][N rows x 128 B]
+  uint8_t* a_buf = smem;                                   // [hi | lo][128 rows x 128 B] (one buffer: the 12 MMAs of a tile retire long before the next tile is split)
+  uint8_t* b_img = smem + 2 * C1_ABYTES;                   // [hi | lo][N rows x 128 B]
   float* patch = reinterpret_cast<float*>(b_img + 2 * N * C1_ROWB);
   uint64_t* a_full = reinterpret_cast<uint64_t*>(patch + C1_MAX_PATCH + 8);
   uint64_t* a_empty = a_full + 2;
@@ -83,7 +87,7 @@ conv1_tc_kernel(const __grid_constant__ Conv1Params p) {
   // resident weights + zero K padding (chunks 6, 7 of every A row are never written again)
   for (int i = threadIdx.x; i < 2 * N * C1_ROWB / 16; i += blockDim.x)
     reinterpret_cast<uint4*>(b_img)[i] = __ldg(reinterpret_cast<const uint4*>(p.wimg) + i);
-  for (int i = threadIdx.x; i < 4 * C1_ABYTES / 16; i += blockDim.x) reinterpret_cast<uint4*>(a_buf)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < 2 * C1_ABYTES / 16; i += blockDim.x) reinterpret_cast<uint4*>(a_buf)[i] = make_uint4(0, 0, 0, 0);
   if (warp == 4) {
     if (lane == 0) {
       for (int s = 0; s < 2; ++s) {
@@ -93,7 +97,7 @@ conv1_tc_kernel(const __grid_constant__ Conv1Params p) {
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, 2 * N);
+    tmem_alloc(tmem_slot, N);   // one accumulator (three CTAs x 128 columns fit the SM's 512)
     tmem_relinquish();
   }
   fence_proxy_async();
@@ -114,7 +118,7 @@ conv1_tc_kernel(const __grid_constant__ Conv1Params p) {
     // chunks: the first chunk holds the left padding pixel and the last one the right padding pixel - both entirely outside the
     // tile (zero fill), every other chunk entirely inside.  6 cp.async per thread and tile instead of 24.
     const int PWC = (PW3 + 1 + 3) >> 2;                      // 16-byte chunks per staged row (one leading float)
-    const bool fast = p.pad_l == 1 && (p.W & 3) == 0 && 2 * p.TW == p.W && (!p.tm.tiles_x || (p.tm.IW & 3) == 0) &&
+    const bool fast = p.pad_l == 1 && (p.W & 3) == 0 && (p.TW & 1) == 0 && (!p.tm.tiles_x || (p.tm.IW & 3) == 0) &&
                       ((size_t)PH * PWC * 4 <= (size_t)C1_MAX_PATCH) && ((reinterpret_cast<uintptr_t>(p.x) & 15) == 0);
     // floats per staged row; position of the row's first patch float (image float -3 of a row staged from float -4: odd, so the
     // gather below cannot use 8-byte loads on it directly)
@@ -141,12 +145,14 @@ conv1_tc_kernel(const __grid_constant__ Conv1Params p) {
       const int iy0 = 2 * oy0 - p.pad_t, ix0 = 2 * ox0 - p.pad_l;
       const bool ragged = vh < p.H || vw < p.W;
       if (fast && !ragged) {
-        // ox0 == 0 (one tile spans the row): chunk c of row pr covers floats 4c - 4 .. 4c - 1 of the image row
+        // the row's first patch float is float 3 ix0 = 6 ox0 - 3 of the item's row (ox0 a multiple of the even TW): staging starts
+        // at the aligned float below it; chunk c of row pr covers floats 3 ix0 - 1 + 4c .. + 3 and lies entirely inside or outside
+        const int s0 = 3 * ix0 - 1;
         for (int i = r; i < PH * PWC; i += 128) {
           const int pr = i / PWC, c = i - pr * PWC;
-          const int iy = iy0 + pr;
-          const bool ok = iy >= 0 && iy < p.H && c >= 1 && 4 * c - 4 < 3 * p.W;
-          const float* src = ok ? xb + (size_t)iy * row_stride + (4 * c - 4) : p.x;
+          const int iy = iy0 + pr, f0 = s0 + 4 * c;
+          const bool ok = iy >= 0 && iy < p.H && f0 >= 0 && f0 < 3 * p.W;
+          const float* src = ok ? xb + (size_t)iy * row_stride + f0 : p.x;
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(patch_s + (uint32_t)i * 16u), "l"(src), "r"(ok ? 16 : 0) : "memory");
         }
         return;
@@ -200,10 +206,9 @@ conv1_tc_kernel(const __grid_constant__ Conv1Params p) {
       named_bar_sync(1, 128);  // everyone holds its patch values in registers: the staging buffer is free again
       // the next tile's loads fly while this tile is split and stored (one staging buffer: no shared memory left for two)
       if (t + (int)gridDim.x < p.total_tiles) stage(t + gridDim.x);
-      const int buf = lt & 1;
-      mbar_wait(&a_empty[buf], (((uint32_t)lt >> 1) & 1u) ^ 1u);  // the MMAs that read this buffer have retired
+      mbar_wait(&a_empty[0], ((uint32_t)lt & 1u) ^ 1u);  // the MMAs of the previous tile have retired
       if (row_ok) {
-        uint8_t* row_hi = a_buf + (size_t)buf * 2 * C1_ABYTES + (size_t)r * C1_ROWB;
+        uint8_t* row_hi = a_buf + (size_t)r * C1_ROWB;
         uint8_t* row_lo = row_hi + C1_ABYTES;
 #pragma unroll
         for (int c = 0; c < 6; ++c) {
@@ -222,7 +227,7 @@ conv1_tc_kernel(const __grid_constant__ Conv1Params p) {
         }
       }
       fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
-      mbar_arrive(&a_full[buf]);
+      mbar_arrive(&a_full[0]);
     }
   } else if (warp == 4) {
     // ===== MMA issuer =====
@@ -230,14 +235,13 @@ conv1_tc_kernel(const __grid_constant__ Conv1Params p) {
     const uint32_t a_lo0 = (smem_u32(a_buf) & 0x3FFFF) >> 4, b_lo0 = (smem_u32(b_img) & 0x3FFFF) >> 4;
     int lt = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++lt) {
-      const int buf = lt & 1;
-      const uint32_t ph = ((uint32_t)lt >> 1) & 1u;
-      mbar_wait(&tmem_empty_bar[buf], ph ^ 1u);
-      mbar_wait(&a_full[buf], ph);
+      const uint32_t ph = (uint32_t)lt & 1u;
+      mbar_wait(&tmem_empty_bar[0], ph ^ 1u);
+      mbar_wait(&a_full[0], ph);
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t d = tmem_base + (uint32_t)(buf * N);
-        const uint32_t a_hi = a_lo0 + (uint32_t)buf * (2 * C1_ABYTES >> 4), a_lo = a_hi + (C1_ABYTES >> 4);
+        const uint32_t d = tmem_base;
+        const uint32_t a_hi = a_lo0, a_lo = a_hi + (C1_ABYTES >> 4);
         const uint32_t b_hi = b_lo0, b_lo = b_lo0 + (uint32_t)(N * C1_ROWB >> 4);
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_bf16(d, umma_desc_from_lo<64>(a_hi + 2 * k), umma_desc_from_lo<64>(b_hi + 2 * k), idesc, k != 0);
@@ -245,8 +249,8 @@ conv1_tc_kernel(const __grid_constant__ Conv1Params p) {
         for (int k = 0; k < 4; ++k) umma_bf16(d, umma_desc_from_lo<64>(a_lo + 2 * k), umma_desc_from_lo<64>(b_hi + 2 * k), idesc, 1u);
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_bf16(d, umma_desc_from_lo<64>(a_hi + 2 * k), umma_desc_from_lo<64>(b_lo + 2 * k), idesc, 1u);
-        umma_commit(&a_empty[buf]);
-        umma_commit(&tmem_full_bar[buf]);
+        umma_commit(&a_empty[0]);
+        umma_commit(&tmem_full_bar[0]);
       }
       __syncwarp();
     }
@@ -260,10 +264,9 @@ conv1_tc_kernel(const __grid_constant__ Conv1Params p) {
       const int b = t / tiles_per_img, ti = t % tiles_per_img;
       const int oy = (ti / p.tiles_x) * p.TH + yl, ox = (ti % p.tiles_x) * p.TW + xl;
       const bool valid = yl < p.TH && oy < p.Ho && ox < p.Wo;
-      const int buf = lt & 1;
-      mbar_wait_relaxed(&tmem_full_bar[buf], ((uint32_t)lt >> 1) & 1u);
+      mbar_wait_relaxed(&tmem_full_bar[0], (uint32_t)lt & 1u);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * N);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
       const size_t opix = (((size_t)b * p.Ho + oy) * p.Wo + ox) * 64;
 #pragma unroll 1
       for (int c = 0; c < N / 32; ++c) {
@@ -274,7 +277,7 @@ conv1_tc_kernel(const __grid_constant__ Conv1Params p) {
         if (c == N / 32 - 1) {
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[0]);
         }
         const bool quads = (p.TW & 3) == 0;  // rows 4q .. 4q+3 are consecutive pixels of one image row
         if (!quads && !valid) continue;
@@ -323,7 +326,7 @@ conv1_tc_kernel(const __grid_constant__ Conv1Params p) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, 2 * N);
+  if (warp == 4) tmem_dealloc(tmem_base, N);
 }
 
 // weights of one or two encoders, (4,4,3,64) fp32 each -> [hi | lo][N][64] bf16 rows in the swizzled smem image
@@ -352,13 +355,13 @@ int conv1_tc_pack(const float* w0, const float* w1, uint8_t* img, cudaStream_t s
 
 template <int N>
 static int launch_conv1_n(const Conv1Params& p, cudaStream_t st) {
-  const size_t smem = 4 * C1_ABYTES + 2 * N * C1_ROWB + (C1_MAX_PATCH + 8) * sizeof(float) + 128 + 1024;
+  const size_t smem = 2 * C1_ABYTES + 2 * N * C1_ROWB + (C1_MAX_PATCH + 8) * sizeof(float) + 128 + 1024;
   static DeviceOnce attr_set;  // function attributes are per device
   if (attr_set.todo()) {
     CIC_CHECK_CUDA(cudaFuncSetAttribute(conv1_tc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set.done();
   }
-  const int slots = 2 * sm_count();
+  const int slots = C1_CTAS * sm_count();
   conv1_tc_kernel<N><<<p.total_tiles < slots ? p.total_tiles : slots, 288, smem, st>>>(p);
   CIC_COUNT_LAUNCH();
   CIC_CHECK_LAUNCH("conv1_tc_kernel");
@@ -375,14 +378,15 @@ int launch_conv1_tc(const float* x, const uint8_t* wimg, const float* bias, int 
   Conv1Params p;
   memset(&p, 0, sizeof(p));
   p.x = x; p.tm = tm; p.batch = batch; p.H = H; p.W = W; p.Ho = H / 2; p.Wo = W / 2;
-  int tw = 128;
-  while (tw > p.Wo && tw > 1) tw >>= 1;  // largest power of two <= Wo (capped at 128)
+  int tw = 64;
+  while (tw > p.Wo && tw > 1) tw >>= 1;  // largest power of two <= Wo (capped at 64: a 2 x 64 tile needs a 6 x 130 pixel patch)
   p.TW = tw; p.TH = TC_BM / tw;
   if (p.TH > p.Ho) {
     int th = 1;
     while (th * 2 <= p.Ho) th *= 2;
     p.TH = th;
   }
+  while (p.TH > 1 && (2 * p.TH + 2) * (2 * p.TW + 2) * 3 > C1_MAX_PATCH) p.TH >>= 1;  // one-pixel-wide outputs: fewer rows per tile
   CIC_REQUIRE((2 * p.TH + 2) * (2 * p.TW + 2) * 3 <= C1_MAX_PATCH, "conv1_tc: patch too large");
   p.tiles_x = (p.Wo + p.TW - 1) / p.TW; p.tiles_y = (p.Ho + p.TH - 1) / p.TH;
   const long long total = (long long)batch * p.tiles_x * p.tiles_y;

@@ -808,6 +808,7 @@ class Bench:
                 flush.zero_()
                 return fn()
             return g
+        steps = max(steps, 20)      # a step is ~1 ms: three of them (the default of the secondary configs) are at the mercy of one host hiccup
         sampler = ClockSampler(self.nvml_idx) if headline else None
         ms_flush, _ = self.timed(lambda: flush.zero_(), steps, warmup)
         plan.set_profiling(True)
